@@ -1,0 +1,116 @@
+/* pcb200 -- C ABI of the B200-native photonic-crystal hot path (libpcb200.so).
+ *
+ * Drop-in boundary for paper_2's data-parallel path.  The reference is pure Python over
+ * CuPy (no FFI of its own), so each entry point below names the reference call it replaces
+ * (paths relative to /root/reference/paper_2).  Host code (Python, ctypes) owns the control
+ * flow; everything that touches O(N^3) data is behind these functions.
+ *
+ * Conventions
+ *   - complex128 everywhere = two doubles (re, im); "cols" arguments are host arrays of DEVICE
+ *     pointers, one per column; a column is one vector of 3*N^3 complex128 stored planar
+ *     [component c][i2][i1][i0] (i0 fastest) = the reference's row index r = c*nn + i0 + N*i1 + N^2*i2
+ *     (discretization.py:326-328).
+ *   - return value: 0 ok; < 0 CUDA / argument error, message via pcb_last_error().
+ *   - every call is ordered on the context's stream; calls that write HOST memory return after the
+ *     data is visible.  One context per GPU and per host thread.
+ *   - there is no CPU fallback: pcb_ctx_create fails when no CUDA device is present.
+ */
+#ifndef PCB200_H
+#define PCB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pcb_ctx pcb_ctx;     /* one GPU + one grid size N: stream, twiddles, workspaces        */
+typedef struct pcb_diel pcb_diel;   /* dielectric M: bit mask of Omega_1 + eps entries                 */
+typedef struct pcb_op pcb_op;       /* one k-point: symbol tables, gamma, shift, (optional) dielectric */
+
+/* dielectric kinds (discretization.py:352 chiral_handle, :368 pseudochiral_trivial_handle,
+ * :403 pseudochiral_crossdof_handle; NONE = `Diels = lambda x: x`, numerical_experiments.py:227) */
+enum { PCB_DIEL_KIND_NONE = 0, PCB_DIEL_KIND_CHIRAL = 1, PCB_DIEL_KIND_TRIVIAL = 2, PCB_DIEL_KIND_CROSSDOF = 3 };
+
+/* pcb_apply modes */
+enum {
+    PCB_APPLY_FFT = 0,   /* unnormalised forward 3-D DFT of every component (cupyx fftn, pcfft.py:149)            */
+    PCB_APPLY_IFFT = 1,  /* inverse 3-D DFT with 1/N^3 (ifftn, pcfft.py:151)                                      */
+    PCB_APPLY_A = 2,     /* AMA(x, a_fft, Diels)            pcfft.py:130-158                                      */
+    PCB_APPLY_H = 3,     /* AMA_BB(x, a_fft, b_fft, Diels, shift)   pcfft.py:160-181                              */
+    PCB_APPLY_P = 4,     /* H_block(x, inv_fft)  = K_P^-1 x  pcfft.py:50-70 with discretization.py:284-295        */
+    PCB_APPLY_M = 5,     /* Diels(x) in real space          discretization.py:352-453                             */
+    PCB_APPLY_KA = 6,    /* A_block_kernel(x, D_A)           pcfft.py:32-43 / _kernels.py:43-71                   */
+    PCB_APPLY_KAH = 7,   /* A_block_kernel(x, -conj(D_A))    pcfft.py:148                                         */
+    PCB_APPLY_KB = 8     /* H_block_kernel(x, D_B) = gamma K_B x   pcfft.py:18-30,176 / _kernels.py:13-41         */
+};
+
+const char* pcb_last_error(void);
+const char* pcb_backend(void);                 /* "cuda-sm_100a" (product) or "host-emu" (tests/emu only) */
+int pcb_device_count(int* n);
+int pcb_supported_sizes(int* sizes, int cap);  /* returns how many grid sizes N have FFT plans */
+
+int pcb_ctx_create(int device, int N, pcb_ctx** ctx);
+void pcb_ctx_destroy(pcb_ctx* ctx);
+int pcb_sync(pcb_ctx* ctx);
+int pcb_launch_count(pcb_ctx* ctx, long long* n);   /* kernels launched by this context so far */
+int pcb_mem_info(pcb_ctx* ctx, size_t* free_bytes, size_t* total_bytes);
+int pcb_timer_start(pcb_ctx* ctx);                  /* CUDA event on the context's stream */
+int pcb_timer_stop(pcb_ctx* ctx, float* ms);        /* second event + synchronize + elapsed */
+
+/* memory (replaces cupy.empty / cp.asarray / .get(); environment.py, lobpcg.py:365-369) */
+int pcb_malloc(pcb_ctx* ctx, size_t bytes, void** dptr);
+int pcb_free(pcb_ctx* ctx, void* dptr);
+int pcb_host_alloc(size_t bytes, void** hptr);      /* pinned host memory */
+int pcb_host_free(void* hptr);
+int pcb_memcpy_h2d(pcb_ctx* ctx, void* dst, const void* src, size_t bytes);
+int pcb_memcpy_d2h(pcb_ctx* ctx, void* dst, const void* src, size_t bytes);
+int pcb_memcpy_d2d(pcb_ctx* ctx, void* dst, const void* src, size_t bytes);
+int pcb_memset_zero(pcb_ctx* ctx, void* dst, size_t bytes);
+/* (R, k) row-major host block (the reference's array layout, leading dimension ld elements) <-> planar device columns */
+int pcb_block_upload(pcb_ctx* ctx, const void* host_rm, long long ld, int k, void* const* cols);
+int pcb_block_download(pcb_ctx* ctx, void* host_rm, long long ld, int k, const void* const* cols);
+/* x0 = rand + 1j*rand generated on the device (cp.random.rand, numerical_experiments.py:66,426): counter-based, seeded */
+int pcb_fill_uniform(pcb_ctx* ctx, int k, void* const* cols, unsigned long long seed);
+
+/* dielectric (discretization.py:352-453).  ind_e: int64 row indices r in [0, 3nn) of edge DoFs in Omega_1
+ * (dielectric.diel_io_index(..., 'edge')); ind_v: int64 cell indices in [0, nn) of volume DoFs (trivial only).
+ * ediag[3]: diagonal value inside Omega_1 per component (chiral: 1/eps);  eoff[6] = (re,im) of eps_12, eps_13, eps_23.
+ * stencil: the 2k averaging weights mfd_stencil(k, 0) (crossdof only). */
+int pcb_diel_create(pcb_ctx* ctx, int kind, const int64_t* ind_e, long long n_e, const int64_t* ind_v, long long n_v,
+                    const double* ediag, const double* eoff, int k, const double* stencil, pcb_diel** diel);
+void pcb_diel_destroy(pcb_diel* diel);
+
+/* operator for one k-point (numerical_experiments.py:434-448 pc_mfd_handle).  tables: [3][3][N] complex128,
+ * K_c(i0,i1,i2) = tables[c][0][i0] + tables[c][1][i1] + tables[c][2][i2]  (= a_fft, fft_blocks discretization.py:301-346);
+ * gamma = pnt, shift = relax_opt[0] as used by H, pshift the shift inside K_P^-1 (= shift for SCAL = 1). */
+int pcb_op_create(pcb_ctx* ctx, const double* tables, double gamma, double shift, double pshift, pcb_diel* diel,
+                  pcb_op** op);
+int pcb_op_update(pcb_op* op, const double* tables, double gamma, double shift, double pshift, pcb_diel* diel);
+void pcb_op_destroy(pcb_op* op);
+
+/* Y_j = op(X_j), j < ncols.  in[j] == out[j] (in place) is allowed for every mode except PCB_APPLY_H (which re-reads X in
+ * its last pass) and PCB_APPLY_M with the cross-DoF dielectric; distinct columns must not overlap. */
+int pcb_apply(pcb_op* op, int mode, int ncols, const void* const* in, void* const* out);
+
+/* LOBPCG block kernels
+ * pcb_residual: r_j = lambda_j x_j - hx_j (lobpcg.py:394-395); norms2[j] = ||r_j||^2 (environment.norms :131-143);
+ *   precond = 0: w_j = r_j;  1: w_j = K_P^-1 r_j (p_func fused, lobpcg.py:442).  norms2 is HOST memory. */
+int pcb_residual(pcb_op* op, int precond, int ncols, const void* const* x, const void* const* hx, void* const* w,
+                 const double* lambda, double* norms2);
+/* G = S^H S, T = S^H HS, both hermitized (orthogonalization.py:26-33,143-144); n x n row-major complex128 on the HOST */
+int pcb_gram2(pcb_ctx* ctx, int n, const void* const* s, const void* const* hs, void* G, void* T);
+/* _sep_update_after_rr (lobpcg.py:1248-1270): s/hs list the n_loc input columns [X(m) | W_act | P_act];
+ * E is (n_loc x m) row-major complex128 on the host.  Pn = [W_act P_act] E[m:], X <- X E[:m] + Pn (in place), P <- Pn. */
+int pcb_update(pcb_ctx* ctx, int m, int n_loc, void* const* s, void* const* hs, void* const* p_out, void* const* hp_out,
+               const void* E);
+/* out[j] = a_j^H b_j (complex128 on the host) -- diag(x^H y) of numerical_experiments.py:105-111, environment.dots */
+int pcb_coldots(pcb_ctx* ctx, int ncols, const void* const* a, const void* const* b, void* out);
+/* y_j = alpha x_j + beta y_j */
+int pcb_axpby(pcb_ctx* ctx, int ncols, const void* const* x, void* const* y, double alpha, double beta);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCB200_H */

@@ -1,0 +1,554 @@
+// pcb200 -- LOBPCG block kernels on the planar column layout (see pcb_common.cuh).
+//
+//   k_resid_precond : W = K_P^-1 (X diag(lambda) - HX) and column 2-norms of the raw residual in one pass
+//                     (lobpcg.py:394-397 + numerical_experiments.py:83 / pcfft.py:50-70 / discretization.py:284-295)
+//   k_gram2         : G = S^H S, T = S^H HS for a list of columns, Hermitian half only (orthogonalization.py:143-144)
+//   k_update        : P <- [W P] E_wp, X <- X E_x + P (same for HS) in one pass (lobpcg.py:1248-1270)
+//   k_coldots       : diag(A^H B) for column pairs (numerical_experiments.py:105-111, environment.py:131-157)
+//   layout helpers  : row-major (R, k) host layout <-> planar columns, index list -> bit mask
+// All reductions are two-stage (per-CTA partials, then a fixed-order sum) so results are deterministic.
+#pragma once
+#include "pcb_operator.cuh"
+
+#define PCB_MAXL 96          // max columns in one Gram / update call (3m, m <= 32)
+
+struct PcbColList {          // device pointers of up to PCB_MAXL columns (nullptr = zero column)
+    const cplx* p[PCB_MAXL];
+};
+struct PcbColListW {
+    cplx* p[PCB_MAXL];
+};
+
+// ---- cp.async (LDGSTS) helpers ------------------------------------------------------------------
+#ifdef PCB_EMU
+PCB_D void pcb_cp16(cplx* dst, const cplx* src) { *dst = *src; }
+PCB_D void pcb_cp_commit() {}
+template <int N> PCB_D void pcb_cp_wait() {}
+#else
+PCB_D void pcb_cp16(cplx* dst, const cplx* src) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src));
+}
+PCB_D void pcb_cp_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> PCB_D void pcb_cp_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+#endif
+
+PCB_D double pcb_warp_sum(double v) {
+    PCB_UNROLL
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---- layout: (R, k) row-major <-> planar columns -------------------------------------------------
+// rm[r*ld + j] <-> col[j][r];  32x32 tiles through shared memory, both sides coalesced.
+template <int TO_COLS>
+__global__ void __launch_bounds__(256) k_transpose(cplx* __restrict__ rm, long long ld, PcbColListW cols, int k, long long R) {
+    __shared__ cplx tile[32][33];
+    const long long r0 = (long long)blockIdx.x * 32;
+    const int j0 = blockIdx.y * 32;
+    const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;   // 32 x 8
+    if (TO_COLS) {
+        for (int rr = ty; rr < 32; rr += 8) {
+            const long long r = r0 + rr;
+            const int j = j0 + tx;
+            if (r < R && j < k) tile[rr][tx] = rm[r * ld + j];
+        }
+        __syncthreads();
+        for (int jj = ty; jj < 32; jj += 8) {
+            const long long r = r0 + tx;
+            const int j = j0 + jj;
+            if (r < R && j < k) cols.p[j][r] = tile[tx][jj];
+        }
+    } else {
+        for (int jj = ty; jj < 32; jj += 8) {
+            const long long r = r0 + tx;
+            const int j = j0 + jj;
+            if (r < R && j < k) tile[tx][jj] = cols.p[j][r];
+        }
+        __syncthreads();
+        for (int rr = ty; rr < 32; rr += 8) {
+            const long long r = r0 + rr;
+            const int j = j0 + tx;
+            if (r < R && j < k) rm[r * ld + j] = tile[rr][tx];
+        }
+    }
+}
+
+// mask[cell] |= bit for every index in the list (edge list: row index r = c*nn + cell -> bit c)
+__global__ void k_mask_from_index(const long long* __restrict__ ind, long long n, long long nn, int volume,
+                                  unsigned* __restrict__ mask32) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long r = ind[i];
+    if (r < 0 || r >= (volume ? nn : 3 * nn)) return;
+    const int c = volume ? 3 : (int)(r / nn);
+    const long long cell = volume ? r : r - c * nn;
+    atomicOr(mask32 + (cell >> 2), (1u << c) << (8 * (int)(cell & 3)));
+}
+
+// ---- preconditioner symbol: inverse of K_P = K_A K_A^H + gamma K_B + shift I at one grid point --------
+// (inverse_3_times_3_B -> inverse_3_times_3_block, discretization.py:224-295, cofactor formulas)
+struct PcbPinv { double f11, f22, f33; cplx f12, f13, f23; };
+PCB_HD PcbPinv pcb_pinv(const cplx k[3], double pnt, double shift) {
+    const double b0 = cabs2(k[0]), b1 = cabs2(k[1]), b2 = cabs2(k[2]);
+    const double d11 = pnt * b0 + b1 + b2 + shift;
+    const double d22 = b0 + pnt * b1 + b2 + shift;
+    const double d33 = b0 + b1 + pnt * b2 + shift;
+    const double g = pnt - 1.0;
+    const cplx d12 = cscale(cmulc(k[0], k[1]), g);
+    const cplx d13 = cscale(cmulc(k[0], k[2]), g);
+    const cplx d23 = cscale(cmulc(k[1], k[2]), g);
+    const cplx t = cmul(cmul(d12, d23), cconj(d13));
+    const double det = (d11 * d22 * d33 - (d11 * cabs2(d23) + d22 * cabs2(d13) + d33 * cabs2(d12))) + 2.0 * t.x;
+    const double id = 1.0 / det;
+    PcbPinv f;
+    f.f11 = (d22 * d33 - cabs2(d23)) * id;
+    f.f22 = (d11 * d33 - cabs2(d13)) * id;
+    f.f33 = (d11 * d22 - cabs2(d12)) * id;
+    f.f12 = cscale(csub(cmul(d13, cconj(d23)), cscale(d12, d33)), id);
+    f.f13 = cscale(csub(cmul(d12, d23), cscale(d13, d22)), id);
+    f.f23 = cscale(csub(cmul(d13, cconj(d12)), cscale(d23, d11)), id);
+    return f;
+}
+PCB_HD void pcb_pinv_apply(const PcbPinv& f, const cplx r[3], cplx w[3]) {   // H_block with inv_fft (pcfft.py:50-70)
+    w[0] = cfma(f.f12, r[1], cfma(f.f13, r[2], cscale(r[0], f.f11)));
+    w[1] = cfmac(f.f12, r[0], cfma(f.f23, r[2], cscale(r[1], f.f22)));
+    w[2] = cfmac(f.f13, r[0], cfmac(f.f23, r[1], cscale(r[2], f.f33)));
+}
+
+#define PCB_RP_CH 8     // columns per CTA chunk in k_resid_precond
+#define PCB_MAXC_RP 32  // columns per k_resid_precond launch
+struct PcbResidArgs {
+    const cplx* x[PCB_MAXC_RP];
+    const cplx* hx[PCB_MAXC_RP];
+    cplx* w[PCB_MAXC_RP];
+    double lambda[PCB_MAXC_RP];
+};
+
+// MODE 0: W = lambda X - HX (no preconditioner);  1: W = K_P^-1 (lambda X - HX);  2: W = K_P^-1 X (P_func alone)
+// partial[(blockIdx.x * ncols) + j] = sum over this CTA's points of |r_j|^2  (raw residual, before K_P^-1)
+template <int MODE>
+__global__ void __launch_bounds__(256) k_resid_precond(PcbOp op, PcbResidArgs a, int ncols, double* __restrict__ partial) {
+    __shared__ double red[8][PCB_RP_CH];
+    const int N = op.N;
+    const long long nn = op.nn;
+    const int j0 = blockIdx.y * PCB_RP_CH;
+    double acc[PCB_RP_CH];
+    PCB_UNROLL
+    for (int j = 0; j < PCB_RP_CH; ++j) acc[j] = 0.0;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < nn; p += (long long)gridDim.x * blockDim.x) {
+        PcbPinv f;
+        if (MODE) {
+            const int i0 = (int)(p % N), i1 = (int)((p / N) % N), i2 = (int)(p / ((long long)N * N));
+            const Sym3 s = pcb_symbol(op.T, N, i0, i1, i2);
+            f = pcb_pinv(s.k, op.gamma, op.pshift);
+        }
+        PCB_UNROLL
+        for (int j = 0; j < PCB_RP_CH; ++j) {
+            const int jj = j0 + j;
+            if (jj < ncols) {
+                cplx r[3], w[3];
+                PCB_UNROLL
+                for (int c = 0; c < 3; ++c) {
+                    const cplx x = a.x[jj][c * nn + p];
+                    if (MODE == 2) r[c] = x;
+                    else {
+                        const cplx h = a.hx[jj][c * nn + p];
+                        r[c] = cmake(fma(x.x, a.lambda[jj], -h.x), fma(x.y, a.lambda[jj], -h.y));
+                    }
+                }
+                acc[j] += cabs2(r[0]) + cabs2(r[1]) + cabs2(r[2]);
+                if (MODE) pcb_pinv_apply(f, r, w);
+                else { w[0] = r[0]; w[1] = r[1]; w[2] = r[2]; }
+                PCB_UNROLL
+                for (int c = 0; c < 3; ++c) a.w[jj][c * nn + p] = w[c];
+            }
+        }
+    }
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    PCB_UNROLL
+    for (int j = 0; j < PCB_RP_CH; ++j) {
+        const double v = pcb_warp_sum(acc[j]);
+        if (lane == 0) red[warp][j] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < PCB_RP_CH) {
+        double v = 0.0;
+        for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+        const int jj = j0 + threadIdx.x;
+        if (jj < ncols) partial[(long long)blockIdx.x * ncols + jj] = v;
+    }
+}
+
+// out[j] = sum_b partial[b*n + j] in fixed order (deterministic)
+__global__ void k_sum_partials(const double* __restrict__ partial, int nblocks, int n, double* __restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    double v = 0.0;
+    for (int b = 0; b < nblocks; ++b) v += partial[(long long)b * n + j];
+    out[j] = v;
+}
+
+// ---- Gram pair ----------------------------------------------------------------------------------
+// n = 4*nb columns (padded with zero columns).  Thread (ia <= ib, row-group g) owns the 4x4 block
+// { (ia + nb*j, ib + nb*j') } of both G and T; the strided column sets make the shared-memory reads
+// of a quarter warp contiguous.  Row tiles of TR rows are double-buffered with cp.async.
+#define PCB_GRAM_TR 32
+#define PCB_GRAM_NT 256
+
+PCB_HD void pcb_pair_from_index(int p, int nb, int& ia, int& ib) {   // row-major upper triangle incl. diagonal
+    int a = 0, rem = p;
+    while (rem >= nb - a) { rem -= nb - a; ++a; }
+    ia = a; ib = a + rem;
+}
+
+__global__ void __launch_bounds__(PCB_GRAM_NT) k_gram2(PcbColList S, PcbColList HS, int nb, long long R, int PP, int npairs,
+                                                        cplx* __restrict__ partial /* [gridDim.x][2][n*n] */) {
+    PCB_DYN_SMEM(cplx, sm);
+    const int n = 4 * nb, NP = n | 1;
+    const int tileElems = PCB_GRAM_TR * NP;             // one array, one stage
+    const int tid = threadIdx.x;
+    const int G = PCB_GRAM_NT / PP;
+    const int g = tid / PP;
+    const int pl = tid % PP;
+    const int p = blockIdx.y * PP + pl;
+    const bool active = (g < G) && (p < npairs);
+    int ia = 0, ib = 0;
+    if (active) pcb_pair_from_index(p, nb, ia, ib);
+
+    cplx accG[4][4], accT[4][4];
+    PCB_UNROLL
+    for (int j = 0; j < 4; ++j) {
+        PCB_UNROLL
+        for (int l = 0; l < 4; ++l) { accG[j][l] = cmake(0.0, 0.0); accT[j][l] = cmake(0.0, 0.0); }
+    }
+
+    const long long ntiles = (R + PCB_GRAM_TR - 1) / PCB_GRAM_TR;
+    auto load_tile = [&](long long t, int stage) {
+        cplx* s0 = sm + (size_t)stage * 2 * tileElems;
+        cplx* h0 = s0 + tileElems;
+        const long long r0 = t * PCB_GRAM_TR;
+        for (int idx = tid; idx < n * PCB_GRAM_TR; idx += PCB_GRAM_NT) {
+            const int c = idx / PCB_GRAM_TR, rr = idx % PCB_GRAM_TR;
+            const long long r = r0 + rr;
+            const cplx* sp = S.p[c];
+            const cplx* hp = HS.p[c];
+            if (sp != nullptr && r < R) {
+                pcb_cp16(s0 + rr * NP + c, sp + r);
+                pcb_cp16(h0 + rr * NP + c, hp + r);
+            } else {
+                s0[rr * NP + c] = cmake(0.0, 0.0);
+                h0[rr * NP + c] = cmake(0.0, 0.0);
+            }
+        }
+        pcb_cp_commit();
+    };
+
+    long long t = blockIdx.x;
+    int stage = 0;
+    if (t < ntiles) load_tile(t, 0);
+    for (; t < ntiles; t += gridDim.x) {
+        const long long tn = t + gridDim.x;
+        if (tn < ntiles) { load_tile(tn, stage ^ 1); pcb_cp_wait<1>(); } else { pcb_cp_wait<0>(); }
+        __syncthreads();
+        if (active) {
+            const cplx* s0 = sm + (size_t)stage * 2 * tileElems;
+            const cplx* h0 = s0 + tileElems;
+            for (int rr = g; rr < PCB_GRAM_TR; rr += G) {
+                cplx a[4], b[4], hb[4];
+                PCB_UNROLL
+                for (int j = 0; j < 4; ++j) {
+                    a[j] = s0[rr * NP + ia + nb * j];
+                    b[j] = s0[rr * NP + ib + nb * j];
+                    hb[j] = h0[rr * NP + ib + nb * j];
+                }
+                PCB_UNROLL
+                for (int j = 0; j < 4; ++j) {
+                    PCB_UNROLL
+                    for (int l = 0; l < 4; ++l) {
+                        accG[j][l] = cfmac(a[j], b[l], accG[j][l]);
+                        accT[j][l] = cfmac(a[j], hb[l], accT[j][l]);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        stage ^= 1;
+    }
+    // reduce the row groups of this CTA through shared memory (fixed order), then write the partial block
+    cplx* red = sm;   // reuse: PP * 32 complex
+    for (int gg = 1; gg < G; ++gg) {
+        if (active && g == gg) {
+            PCB_UNROLL
+            for (int j = 0; j < 4; ++j) {
+                PCB_UNROLL
+                for (int l = 0; l < 4; ++l) {
+                    red[(j * 4 + l) * PP + pl] = accG[j][l];
+                    red[(16 + j * 4 + l) * PP + pl] = accT[j][l];
+                }
+            }
+        }
+        __syncthreads();
+        if (active && g == 0) {
+            PCB_UNROLL
+            for (int j = 0; j < 4; ++j) {
+                PCB_UNROLL
+                for (int l = 0; l < 4; ++l) {
+                    accG[j][l] = cadd(accG[j][l], red[(j * 4 + l) * PP + pl]);
+                    accT[j][l] = cadd(accT[j][l], red[(16 + j * 4 + l) * PP + pl]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (active && g == 0) {
+        cplx* out = partial + (size_t)blockIdx.x * 2 * n * n;
+        PCB_UNROLL
+        for (int j = 0; j < 4; ++j) {
+            PCB_UNROLL
+            for (int l = 0; l < 4; ++l) {
+                const int ra = ia + nb * j, cb = ib + nb * l;
+                out[ra * n + cb] = accG[j][l];
+                out[n * n + ra * n + cb] = accT[j][l];
+            }
+        }
+    }
+}
+
+// Sum the per-CTA partials in fixed order and complete the Hermitian matrices:
+// entry (a,b) was computed iff (a mod nb) <= (b mod nb); the others are conj of (b,a).
+__global__ void k_gram_finish(const cplx* __restrict__ partial, int nblocks, int nb, cplx* __restrict__ out /* [2][n*n] */) {
+    const int n = 4 * nb;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= 2 * n * n) return;
+    const int which = e / (n * n), ab = e % (n * n);
+    const int a = ab / n, b = ab % n;
+    const bool direct = (a % nb) <= (b % nb);
+    const int src = direct ? a * n + b : b * n + a;
+    cplx v = cmake(0.0, 0.0);
+    for (int k = 0; k < nblocks; ++k) v = cadd(v, partial[(size_t)k * 2 * n * n + which * n * n + src]);
+    out[e] = direct ? v : cconj(v);
+}
+
+// ---- subspace update --------------------------------------------------------------------------
+// in[0..m) = X columns, in[m..nl) = active W then active P columns; E is (nl x mp) row-major, mp = 8*JB
+// (zero padded).  Pn_j = sum_{k>=m} s_k E_kj ;  X_j <- sum_{k<m} s_k E_kj + Pn_j ;  P_j <- Pn_j ; same for HS.
+#define PCB_UPD_NT 128
+template <int JB>   // JB = mp / 8 output groups; rows per tile = NT / JB
+__global__ void __launch_bounds__(PCB_UPD_NT) k_update(PcbColList Sin, PcbColList HSin, PcbColListW Xout, PcbColListW HXout,
+                                                        PcbColListW Pout, PcbColListW HPout, const cplx* __restrict__ E,
+                                                        int m, int nl, long long R) {
+    constexpr int TR = PCB_UPD_NT / JB;
+    constexpr int MP = 8 * JB;
+    PCB_DYN_SMEM(cplx, sm);
+    cplx* sE = sm;                       // [nl][MP]
+    cplx* sS = sE + (size_t)nl * MP;     // [nl][TR]
+    cplx* sH = sS + (size_t)nl * TR;     // [nl][TR]
+    const int tid = threadIdx.x;
+    for (int i = tid; i < nl * MP; i += PCB_UPD_NT) sE[i] = E[i];
+    const int rr = tid % TR, jb = tid / TR;
+    const long long ntiles = (R + TR - 1) / TR;
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const long long r0 = t * TR;
+        __syncthreads();   // previous tile fully consumed (and sE visible on the first trip)
+        for (int idx = tid; idx < nl * TR; idx += PCB_UPD_NT) {
+            const int k = idx / TR, q = idx % TR;
+            const long long r = r0 + q;
+            if (r < R) {
+                pcb_cp16(sS + k * TR + q, Sin.p[k] + r);
+                pcb_cp16(sH + k * TR + q, HSin.p[k] + r);
+            } else {
+                sS[k * TR + q] = cmake(0.0, 0.0);
+                sH[k * TR + q] = cmake(0.0, 0.0);
+            }
+        }
+        pcb_cp_commit();
+        pcb_cp_wait<0>();
+        __syncthreads();
+        cplx xs[8], xh[8], ps[8], ph[8];
+        PCB_UNROLL
+        for (int j = 0; j < 8; ++j) { xs[j] = xh[j] = ps[j] = ph[j] = cmake(0.0, 0.0); }
+        for (int k = 0; k < m; ++k) {
+            const cplx s = sS[k * TR + rr], h = sH[k * TR + rr];
+            PCB_UNROLL
+            for (int j = 0; j < 8; ++j) {
+                const cplx e = sE[k * MP + jb * 8 + j];
+                xs[j] = cfma(s, e, xs[j]);
+                xh[j] = cfma(h, e, xh[j]);
+            }
+        }
+        for (int k = m; k < nl; ++k) {
+            const cplx s = sS[k * TR + rr], h = sH[k * TR + rr];
+            PCB_UNROLL
+            for (int j = 0; j < 8; ++j) {
+                const cplx e = sE[k * MP + jb * 8 + j];
+                ps[j] = cfma(s, e, ps[j]);
+                ph[j] = cfma(h, e, ph[j]);
+            }
+        }
+        const long long r = r0 + rr;
+        if (r < R) {
+            PCB_UNROLL
+            for (int j = 0; j < 8; ++j) {
+                const int jj = jb * 8 + j;
+                if (jj < m) {
+                    Xout.p[jj][r] = cadd(xs[j], ps[j]);
+                    HXout.p[jj][r] = cadd(xh[j], ph[j]);
+                    Pout.p[jj][r] = ps[j];
+                    HPout.p[jj][r] = ph[j];
+                }
+            }
+        }
+    }
+}
+
+// ---- diag(A^H B) for column pairs -------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_coldots(PcbColList A, PcbColList B, int ncols, long long R, cplx* __restrict__ partial) {
+    __shared__ double red[8][2];
+    const int j = blockIdx.y;
+    const cplx* __restrict__ a = A.p[j];
+    const cplx* __restrict__ b = B.p[j];
+    double sr = 0.0, si = 0.0;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < R; r += (long long)gridDim.x * blockDim.x) {
+        const cplx x = a[r], y = b[r];
+        sr += x.x * y.x + x.y * y.y;
+        si += x.x * y.y - x.y * y.x;
+    }
+    sr = pcb_warp_sum(sr);
+    si = pcb_warp_sum(si);
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    if (lane == 0) { red[warp][0] = sr; red[warp][1] = si; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double vr = 0.0, vi = 0.0;
+        for (int w = 0; w < 8; ++w) { vr += red[w][0]; vi += red[w][1]; }
+        partial[(long long)blockIdx.x * ncols + j] = cmake(vr, vi);
+    }
+}
+
+// ---- linear combination helper: Y = a*X + b*Y on columns (used by the drop-in operator wrappers) ------
+__global__ void k_axpby(const cplx* __restrict__ x, cplx* __restrict__ y, double a, double b, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const cplx u = x[i], v = y[i];
+        y[i] = cmake(a * u.x + b * v.x, a * u.y + b * v.y);
+    }
+}
+
+// ---- dielectric multiply as a stand-alone real-space kernel ---------------------------------------
+// Point-wise types (none / chiral / trivial): Y = M X in one pass (the drop-in Diels(x) callable).
+__global__ void __launch_bounds__(256) k_diel_point(PcbOp op, const cplx* __restrict__ X, cplx* __restrict__ Y) {
+    const long long nn = op.nn;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < nn; p += (long long)gridDim.x * blockDim.x) {
+        cplx u[3] = {X[p], X[nn + p], X[2 * nn + p]};
+        unsigned m = op.diel ? op.mask[p] : 0u;
+        if (op.diel == PCB_DIEL_CHIRAL) m &= 7u;
+        // (inline copy of pcb_diel_point to keep this header independent of pcb_operator.cuh)
+        const double d0 = (m & 1u) ? op.ediag[0] : 1.0, d1 = (m & 2u) ? op.ediag[1] : 1.0, d2 = (m & 4u) ? op.ediag[2] : 1.0;
+        cplx y0 = cscale(u[0], d0), y1 = cscale(u[1], d1), y2 = cscale(u[2], d2);
+        if (m & 8u) {
+            y0 = cfma(op.eoff[0], u[1], cfma(op.eoff[1], u[2], y0));
+            y1 = cfmac(op.eoff[0], u[0], cfma(op.eoff[2], u[2], y1));
+            y2 = cfmac(op.eoff[1], u[0], cfmac(op.eoff[2], u[1], y2));
+        }
+        Y[p] = y0; Y[nn + p] = y1; Y[2 * nn + p] = y2;
+    }
+}
+
+// Cross-DoF dielectric (discretization.py:403-453): diagonal + eps_ab * S_ab couplings,
+// S_ab = (I_a T_ab + T_ab I_b)/2,  T_ab = c (x) c^T on two of the three axes (stencil c with 2k taps).
+// One thread per grid point computes all three output components (gather form); out of place.
+struct PcbStencil { int k; double w[8]; };   // taps w[j] at offsets (1-k+j), j < 2k
+PCB_HD int pcb_wrap(int i, int N) { i %= N; return i < 0 ? i + N : i; }
+
+__global__ void __launch_bounds__(128) k_diel_crossdof(PcbOp op, PcbStencil st, const cplx* __restrict__ X, cplx* __restrict__ Y) {
+    const int N = op.N;
+    const long long nn = op.nn;
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nn) return;
+    int i[3] = {(int)(p % N), (int)((p / N) % N), (int)(p / ((long long)N * N))};
+    const unsigned mp = op.mask[p];
+    cplx y[3];
+    PCB_UNROLL
+    for (int c = 0; c < 3; ++c) y[c] = cscale(X[c * nn + p], ((mp >> c) & 1u) ? op.ediag[c] : 1.0);
+    // pairs (a,b): (0,1) c-axis 2, ct-axis 1;  (0,2) c-axis 2, ct-axis 0;  (1,2) c-axis 1, ct-axis 0
+    const int PA[3] = {0, 0, 1}, PB[3] = {1, 2, 2}, CAX[3] = {2, 2, 1}, TAX[3] = {1, 0, 0};
+    const int taps = 2 * st.k;
+    for (int pr = 0; pr < 3; ++pr) {
+        const cplx e = op.eoff[pr];
+        if (e.x == 0.0 && e.y == 0.0) continue;
+        const int a = PA[pr], b = PB[pr], cax = CAX[pr], tax = TAX[pr];
+        const double Ia = (double)((mp >> a) & 1u), Ib_p = (double)((mp >> b) & 1u);
+        cplx sa = cmake(0.0, 0.0), sb = cmake(0.0, 0.0);
+        for (int j1 = 0; j1 < taps; ++j1) {
+            for (int j2 = 0; j2 < taps; ++j2) {
+                const double w = st.w[j1] * st.w[j2];
+                const int oc = 1 - st.k + j1, ot = 1 - st.k + j2;
+                // y_a(p) += e/2 * T(p,q) (I_a(p) + I_b(q)) x_b(q),  q = p + oc on c-axis, - ot on ct-axis
+                int q[3] = {i[0], i[1], i[2]};
+                q[cax] = pcb_wrap(i[cax] + oc, N);
+                q[tax] = pcb_wrap(i[tax] - ot, N);
+                const long long qi = q[0] + (long long)N * (q[1] + (long long)N * q[2]);
+                const double Ibq = (double)((op.mask[qi] >> b) & 1u);
+                sa = cadd(sa, cscale(X[b * nn + qi], w * 0.5 * (Ia + Ibq)));
+                // y_b(p) += conj(e)/2 * T(p',p) (I_a(p') + I_b(p)) x_a(p'),  p' = p - oc on c-axis, + ot on ct-axis
+                int pp[3] = {i[0], i[1], i[2]};
+                pp[cax] = pcb_wrap(i[cax] - oc, N);
+                pp[tax] = pcb_wrap(i[tax] + ot, N);
+                const long long pi_ = pp[0] + (long long)N * (pp[1] + (long long)N * pp[2]);
+                const double Iap = (double)((op.mask[pi_] >> a) & 1u);
+                sb = cadd(sb, cscale(X[a * nn + pi_], w * 0.5 * (Iap + Ib_p)));
+            }
+        }
+        y[a] = cfma(e, sa, y[a]);
+        y[b] = cfmac(e, sb, y[b]);
+    }
+    PCB_UNROLL
+    for (int c = 0; c < 3; ++c) Y[c * nn + p] = y[c];
+}
+
+// ---- stand-alone point-wise symbol multiplies (drop-in A_block / H_block kernels) ---------------------
+// MODE 0: Y = k x X (K_A, _kernels.py:43-71);  1: Y = (-conj k) x X (K_A^H, pcfft.py:148);
+// MODE 2: Y = gamma conj(k) (k . X)  (h_block with D_B = gamma*(|k_c|^2, conj(k_a) k_b), pcfft.py:176)
+template <int MODE>
+__global__ void __launch_bounds__(256) k_symbol_point(PcbOp op, PcbCols cols) {
+    const int N = op.N;
+    const long long nn = op.nn;
+    const cplx* __restrict__ X = cols.in[blockIdx.y];
+    cplx* __restrict__ Y = cols.out[blockIdx.y];
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < nn; p += (long long)gridDim.x * blockDim.x) {
+        const int i0 = (int)(p % N), i1 = (int)((p / N) % N), i2 = (int)(p / ((long long)N * N));
+        const Sym3 s = pcb_symbol(op.T, N, i0, i1, i2);
+        cplx x[3] = {X[p], X[nn + p], X[2 * nn + p]}, z[3];
+        if (MODE == 0) {
+            pcb_cross(s.k, x, z);
+        } else if (MODE == 1) {
+            cplx a[3];
+            PCB_UNROLL
+            for (int c = 0; c < 3; ++c) a[c] = cmake(-s.k[c].x, s.k[c].y);
+            pcb_cross(a, x, z);
+        } else {
+            cplx dot = cadd(cadd(cmul(s.k[0], x[0]), cmul(s.k[1], x[1])), cmul(s.k[2], x[2]));
+            dot = cscale(dot, op.gamma);
+            PCB_UNROLL
+            for (int c = 0; c < 3; ++c) z[c] = cmulc(s.k[c], dot);
+        }
+        Y[p] = z[0]; Y[nn + p] = z[1]; Y[2 * nn + p] = z[2];
+    }
+}
+
+// ---- x0 = U[0,1) + i U[0,1) on the device: counter-based (splitmix64 of (seed, column, element)) ---------
+PCB_HD unsigned long long pcb_mix64(unsigned long long z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__global__ void __launch_bounds__(256) k_fill_uniform(PcbColListW cols, long long R, unsigned long long seed) {
+    cplx* __restrict__ Y = cols.p[blockIdx.y];
+    const unsigned long long base = pcb_mix64(seed ^ (0xD1B54A32D192ED03ull * (unsigned long long)(blockIdx.y + 1)));
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < R; r += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long a = pcb_mix64(base + 2ull * (unsigned long long)r);
+        const unsigned long long b = pcb_mix64(base + 2ull * (unsigned long long)r + 1ull);
+        Y[r] = cmake((double)(a >> 11) * (1.0 / 9007199254740992.0), (double)(b >> 11) * (1.0 / 9007199254740992.0));
+    }
+}

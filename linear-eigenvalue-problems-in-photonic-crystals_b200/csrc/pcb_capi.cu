@@ -1,0 +1,593 @@
+// pcb200 -- C ABI (include/pcb200.h) over the sm_100a kernels.  No CPU path: a context can only be
+// created on a CUDA device (the PCB_EMU build of this same file is test infrastructure, see tests/emu).
+#include "pcb_block.cuh"
+#include "../../include/pcb200.h"
+
+#include <cstdarg>
+#include <vector>
+
+// ---- error string ---------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+void pcb_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+// ---- plan registry --------------------------------------------------------------------------------------
+#define PCB_PLAN(N, R1, R2) extern const PcbOpLaunch pcb_plan_##N;
+#include <pcb_plans.inc>
+#undef PCB_PLAN
+static const PcbOpLaunch* const g_plans[] = {
+#define PCB_PLAN(N, R1, R2) &pcb_plan_##N,
+#include <pcb_plans.inc>
+#undef PCB_PLAN
+};
+static const int g_nplans = (int)(sizeof g_plans / sizeof g_plans[0]);
+const PcbOpLaunch* pcb_find_plan(int N) {
+    for (int i = 0; i < g_nplans; ++i)
+        if (g_plans[i]->N == N) return g_plans[i];
+    return nullptr;
+}
+
+// ---- objects ----------------------------------------------------------------------------------------------
+struct pcb_ctx {
+    int device = 0;
+    int N = 0;
+    long long nn = 0, R = 0;
+    cudaStream_t stream = nullptr;
+    const PcbOpLaunch* plan = nullptr;
+    cplx* tw = nullptr;             // [R1][R2] forward twiddles exp(-2 pi i k1 n2 / N)
+    double* partial = nullptr;      // reduction partials (device)
+    size_t partial_bytes = 0;
+    void* hstage = nullptr;         // pinned host staging for small results / E matrices
+    size_t hstage_bytes = 0;
+    void* dsmall = nullptr;         // small device buffer (E matrix, reduced results)
+    size_t dsmall_bytes = 0;
+    cplx* scratch = nullptr;        // work columns (cross-DoF dielectric, block transposes)
+    size_t scratch_bytes = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    long long launches = 0;
+    int sms = 148;
+};
+struct pcb_diel {
+    pcb_ctx* ctx;
+    int kind;
+    unsigned char* mask;    // [nn] (padded to 4)
+    double ediag[3];
+    cplx eoff[3];
+    PcbStencil st;
+};
+struct pcb_op {
+    pcb_ctx* ctx;
+    cplx* T;                // [3][3][N] device
+    PcbOp d;                // kernel-side description
+    pcb_diel* diel;
+};
+
+#define PCB_CHECK_ARG(cond, msg)               \
+    do {                                       \
+        if (!(cond)) {                         \
+            pcb_set_error("%s: %s", __func__, msg); \
+            return -2;                         \
+        }                                      \
+    } while (0)
+
+static int ensure(pcb_ctx*, void** p, size_t* have, size_t want, bool host) {
+    if (*have >= want) return 0;
+    if (*p) {
+        if (host) PCB_CUDA_OK(cudaFreeHost(*p)); else PCB_CUDA_OK(cudaFree(*p));
+        *p = nullptr; *have = 0;
+    }
+    if (host) PCB_CUDA_OK(cudaMallocHost(p, want)); else PCB_CUDA_OK(cudaMalloc(p, want));
+    *have = want;
+    return 0;
+}
+static int ensure_partial(pcb_ctx* c, size_t bytes) { return ensure(c, (void**)&c->partial, &c->partial_bytes, bytes, false); }
+static int ensure_hstage(pcb_ctx* c, size_t bytes) { return ensure(c, &c->hstage, &c->hstage_bytes, bytes, true); }
+static int ensure_dsmall(pcb_ctx* c, size_t bytes) { return ensure(c, &c->dsmall, &c->dsmall_bytes, bytes, false); }
+static int ensure_scratch(pcb_ctx* c, size_t bytes) { return ensure(c, (void**)&c->scratch, &c->scratch_bytes, bytes, false); }
+
+static int grid_for(pcb_ctx* c, long long items, int per_block, int waves) {
+    long long b = (items + per_block - 1) / per_block;
+    long long cap = (long long)c->sms * waves;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+extern "C" {
+
+const char* pcb_last_error(void) { return g_err; }
+const char* pcb_backend(void) {
+#ifdef PCB_EMU
+    return "host-emu";
+#else
+    return "cuda-sm_100a";
+#endif
+}
+int pcb_device_count(int* n) {
+    PCB_CHECK_ARG(n, "null");
+    PCB_CUDA_OK(cudaGetDeviceCount(n));
+    return 0;
+}
+int pcb_supported_sizes(int* sizes, int cap) {
+    for (int i = 0; i < g_nplans && i < cap; ++i) sizes[i] = g_plans[i]->N;
+    return g_nplans;
+}
+
+int pcb_ctx_create(int device, int N, pcb_ctx** out) {
+    PCB_CHECK_ARG(out, "null");
+    const PcbOpLaunch* plan = pcb_find_plan(N);
+    if (!plan) { pcb_set_error("pcb_ctx_create: no FFT plan for N = %d (see pcb_supported_sizes)", N); return -2; }
+    int ndev = 0;
+    PCB_CUDA_OK(cudaGetDeviceCount(&ndev));
+    if (ndev <= 0 || device < 0 || device >= ndev) { pcb_set_error("pcb_ctx_create: CUDA device %d not available (%d devices)", device, ndev); return -3; }
+    PCB_CUDA_OK(cudaSetDevice(device));
+    pcb_ctx* c = new pcb_ctx;
+    c->device = device; c->N = N; c->nn = (long long)N * N * N; c->R = 3 * c->nn; c->plan = plan;
+#ifndef PCB_EMU
+    cudaDeviceProp prop;
+    PCB_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    c->sms = prop.multiProcessorCount;
+    if (prop.major < 10) { pcb_set_error("pcb_ctx_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); delete c; return -3; }
+#else
+    c->sms = 2;
+#endif
+    PCB_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    PCB_CUDA_OK(cudaEventCreate(&c->ev0));
+    PCB_CUDA_OK(cudaEventCreate(&c->ev1));
+    std::vector<cplx> tw((size_t)N);
+    for (int k1 = 0; k1 < plan->r1; ++k1)
+        for (int n2 = 0; n2 < plan->r2; ++n2) {
+            const double ang = -2.0 * M_PI * (double)((long long)k1 * n2 % N) / (double)N;
+            tw[(size_t)k1 * plan->r2 + n2] = cmake(cos(ang), sin(ang));
+        }
+    PCB_CUDA_OK(cudaMalloc(&c->tw, sizeof(cplx) * N));
+    PCB_CUDA_OK(cudaMemcpy(c->tw, tw.data(), sizeof(cplx) * N, cudaMemcpyHostToDevice));
+    *out = c;
+    return 0;
+}
+void pcb_ctx_destroy(pcb_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->tw) cudaFree(c->tw);
+    if (c->partial) cudaFree(c->partial);
+    if (c->dsmall) cudaFree(c->dsmall);
+    if (c->scratch) cudaFree(c->scratch);
+    if (c->hstage) cudaFreeHost(c->hstage);
+    cudaEventDestroy(c->ev0);
+    cudaEventDestroy(c->ev1);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+int pcb_sync(pcb_ctx* c) { PCB_CUDA_OK(cudaStreamSynchronize(c->stream)); PCB_CUDA_OK(cudaGetLastError()); return 0; }
+int pcb_launch_count(pcb_ctx* c, long long* n) { *n = c->launches; return 0; }
+int pcb_mem_info(pcb_ctx* c, size_t* f, size_t* t) { PCB_CUDA_OK(cudaSetDevice(c->device)); PCB_CUDA_OK(cudaMemGetInfo(f, t)); return 0; }
+int pcb_timer_start(pcb_ctx* c) { PCB_CUDA_OK(cudaEventRecord(c->ev0, c->stream)); return 0; }
+int pcb_timer_stop(pcb_ctx* c, float* ms) {
+    PCB_CUDA_OK(cudaEventRecord(c->ev1, c->stream));
+    PCB_CUDA_OK(cudaEventSynchronize(c->ev1));
+    PCB_CUDA_OK(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return 0;
+}
+
+// ---- memory -------------------------------------------------------------------------------------------------
+int pcb_malloc(pcb_ctx* c, size_t bytes, void** dptr) {
+    PCB_CUDA_OK(cudaSetDevice(c->device));
+    PCB_CUDA_OK(cudaMalloc(dptr, bytes));
+    return 0;
+}
+int pcb_free(pcb_ctx* c, void* dptr) {
+    PCB_CUDA_OK(cudaSetDevice(c->device));
+    PCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+    PCB_CUDA_OK(cudaFree(dptr));
+    return 0;
+}
+int pcb_host_alloc(size_t bytes, void** hptr) { PCB_CUDA_OK(cudaMallocHost(hptr, bytes)); return 0; }
+int pcb_host_free(void* hptr) { PCB_CUDA_OK(cudaFreeHost(hptr)); return 0; }
+int pcb_memcpy_h2d(pcb_ctx* c, void* dst, const void* src, size_t bytes) {
+    PCB_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    PCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int pcb_memcpy_d2h(pcb_ctx* c, void* dst, const void* src, size_t bytes) {
+    PCB_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    PCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int pcb_memcpy_d2d(pcb_ctx* c, void* dst, const void* src, size_t bytes) {
+    PCB_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    return 0;
+}
+int pcb_memset_zero(pcb_ctx* c, void* dst, size_t bytes) { PCB_CUDA_OK(cudaMemsetAsync(dst, 0, bytes, c->stream)); return 0; }
+
+static int transpose_cols(pcb_ctx* c, cplx* rm, long long ld, int k, void* const* cols, bool to_cols) {
+    PcbColListW L;
+    for (int j0 = 0; j0 < k; j0 += PCB_MAXL) {
+        const int kk = (k - j0 < PCB_MAXL) ? k - j0 : PCB_MAXL;
+        for (int j = 0; j < kk; ++j) L.p[j] = (cplx*)cols[j0 + j];
+        dim3 grid((unsigned)((c->R + 31) / 32), (unsigned)((kk + 31) / 32), 1);
+        if (to_cols) PCB_LAUNCH(k_transpose<1>, grid, dim3(256, 1, 1), 0, c->stream, rm + j0, ld, L, kk, c->R);
+        else PCB_LAUNCH(k_transpose<0>, grid, dim3(256, 1, 1), 0, c->stream, rm + j0, ld, L, kk, c->R);
+        PCB_CUDA_OK(cudaGetLastError());
+        c->launches++;
+    }
+    return 0;
+}
+// The block travels as one (R, kc) slab per chunk of columns: host row-major -> device staging -> planar columns.
+int pcb_block_upload(pcb_ctx* c, const void* host_rm, long long ld, int k, void* const* cols) {
+    PCB_CHECK_ARG(host_rm && cols && k > 0 && ld >= k, "bad arguments");
+    PCB_CUDA_OK(cudaSetDevice(c->device));
+    if (ensure_scratch(c, sizeof(cplx) * (size_t)c->R * (size_t)k)) return -1;
+    if (ld == k) {
+        PCB_CUDA_OK(cudaMemcpyAsync(c->scratch, host_rm, sizeof(cplx) * (size_t)c->R * k, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        PCB_CUDA_OK(cudaMemcpy2DAsync(c->scratch, sizeof(cplx) * k, host_rm, sizeof(cplx) * ld, sizeof(cplx) * k, (size_t)c->R,
+                                      cudaMemcpyHostToDevice, c->stream));
+    }
+    if (transpose_cols(c, c->scratch, k, k, cols, true)) return -1;
+    PCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int pcb_block_download(pcb_ctx* c, void* host_rm, long long ld, int k, const void* const* cols) {
+    PCB_CHECK_ARG(host_rm && cols && k > 0 && ld >= k, "bad arguments");
+    PCB_CUDA_OK(cudaSetDevice(c->device));
+    if (ensure_scratch(c, sizeof(cplx) * (size_t)c->R * (size_t)k)) return -1;
+    if (transpose_cols(c, c->scratch, k, k, (void* const*)cols, false)) return -1;
+    if (ld == k) {
+        PCB_CUDA_OK(cudaMemcpyAsync(host_rm, c->scratch, sizeof(cplx) * (size_t)c->R * k, cudaMemcpyDeviceToHost, c->stream));
+    } else {
+        PCB_CUDA_OK(cudaMemcpy2DAsync(host_rm, sizeof(cplx) * ld, c->scratch, sizeof(cplx) * k, sizeof(cplx) * k, (size_t)c->R,
+                                      cudaMemcpyDeviceToHost, c->stream));
+    }
+    PCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int pcb_fill_uniform(pcb_ctx* c, int k, void* const* cols, unsigned long long seed) {
+    PCB_CHECK_ARG(cols && k > 0, "bad arguments");
+    PcbColListW L;
+    for (int j0 = 0; j0 < k; j0 += PCB_MAXL) {
+        const int kk = (k - j0 < PCB_MAXL) ? k - j0 : PCB_MAXL;
+        for (int j = 0; j < kk; ++j) L.p[j] = (cplx*)cols[j0 + j];
+        dim3 grid((unsigned)grid_for(c, c->R, 256, 8), (unsigned)kk, 1);
+        PCB_LAUNCH(k_fill_uniform, grid, dim3(256, 1, 1), 0, c->stream, L, c->R, seed + 0x1000ull * (unsigned long long)j0);
+        PCB_CUDA_OK(cudaGetLastError());
+        c->launches++;
+    }
+    return 0;
+}
+
+// ---- dielectric -----------------------------------------------------------------------------------------------
+int pcb_diel_create(pcb_ctx* c, int kind, const int64_t* ind_e, long long n_e, const int64_t* ind_v, long long n_v,
+                    const double* ediag, const double* eoff, int k, const double* stencil, pcb_diel** out) {
+    PCB_CHECK_ARG(out && kind >= PCB_DIEL_NONE && kind <= PCB_DIEL_CROSSDOF, "bad kind");
+    PCB_CUDA_OK(cudaSetDevice(c->device));
+    pcb_diel* d = new pcb_diel;
+    d->ctx = c; d->kind = kind; d->mask = nullptr;
+    for (int i = 0; i < 3; ++i) { d->ediag[i] = ediag ? ediag[i] : 1.0; d->eoff[i] = eoff ? cmake(eoff[2 * i], eoff[2 * i + 1]) : cmake(0.0, 0.0); }
+    d->st.k = 1; for (int i = 0; i < 8; ++i) d->st.w[i] = 0.0;
+    if (kind == PCB_DIEL_CROSSDOF) {
+        if (k < 1 || k > 4 || !stencil) { pcb_set_error("pcb_diel_create: crossdof needs 1 <= k <= 4 and the 2k stencil weights"); delete d; return -2; }
+        d->st.k = k;
+        for (int i = 0; i < 2 * k; ++i) d->st.w[i] = stencil[i];
+    }
+    const size_t mbytes = (size_t)((c->nn + 3) / 4) * 4;
+    PCB_CUDA_OK(cudaMalloc(&d->mask, mbytes));
+    PCB_CUDA_OK(cudaMemsetAsync(d->mask, 0, mbytes, c->stream));
+    const int64_t* lists[2] = {ind_e, ind_v};
+    const long long counts[2] = {n_e, (kind == PCB_DIEL_TRIVIAL) ? n_v : 0};
+    for (int which = 0; which < 2; ++which) {
+        const long long n = counts[which];
+        if (n <= 0 || !lists[which]) continue;
+        long long* dind = nullptr;
+        PCB_CUDA_OK(cudaMalloc(&dind, sizeof(long long) * (size_t)n));
+        PCB_CUDA_OK(cudaMemcpyAsync(dind, lists[which], sizeof(long long) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+        dim3 grid((unsigned)((n + 255) / 256), 1, 1);
+        PCB_LAUNCH(k_mask_from_index, grid, dim3(256, 1, 1), 0, c->stream, (const long long*)dind, n, c->nn, which, (unsigned*)d->mask);
+        PCB_CUDA_OK(cudaGetLastError());
+        c->launches++;
+        PCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+        PCB_CUDA_OK(cudaFree(dind));
+    }
+    PCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+    *out = d;
+    return 0;
+}
+void pcb_diel_destroy(pcb_diel* d) {
+    if (!d) return;
+    cudaSetDevice(d->ctx->device);
+    cudaStreamSynchronize(d->ctx->stream);
+    if (d->mask) cudaFree(d->mask);
+    delete d;
+}
+
+// ---- operator ---------------------------------------------------------------------------------------------------
+static void op_fill(pcb_op* o, double gamma, double shift, double pshift, pcb_diel* diel) {
+    pcb_ctx* c = o->ctx;
+    o->diel = diel;
+    o->d.N = c->N; o->d.nn = c->nn; o->d.T = o->T;
+    o->d.gamma = gamma; o->d.shift = shift; o->d.pshift = pshift;
+    o->d.inv_n3 = 1.0 / (double)c->nn;
+    o->d.diel = diel ? diel->kind : PCB_DIEL_NONE;
+    o->d.mask = diel ? diel->mask : nullptr;
+    for (int i = 0; i < 3; ++i) {
+        o->d.ediag[i] = diel ? diel->ediag[i] : 1.0;
+        o->d.eoff[i] = diel ? diel->eoff[i] : cmake(0.0, 0.0);
+    }
+}
+int pcb_op_update(pcb_op* o, const double* tables, double gamma, double shift, double pshift, pcb_diel* diel) {
+    PCB_CHECK_ARG(o && tables, "null");
+    pcb_ctx* c = o->ctx;
+    PCB_CHECK_ARG(!diel || diel->ctx == c, "dielectric belongs to another context");
+    PCB_CUDA_OK(cudaSetDevice(c->device));
+    const size_t bytes = sizeof(cplx) * 9 * (size_t)c->N;
+    if (ensure_hstage(c, bytes > 65536 ? bytes : 65536)) return -1;
+    PCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+    memcpy(c->hstage, tables, bytes);
+    PCB_CUDA_OK(cudaMemcpyAsync(o->T, c->hstage, bytes, cudaMemcpyHostToDevice, c->stream));
+    PCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+    op_fill(o, gamma, shift, pshift, diel);
+    return 0;
+}
+int pcb_op_create(pcb_ctx* c, const double* tables, double gamma, double shift, double pshift, pcb_diel* diel, pcb_op** out) {
+    PCB_CHECK_ARG(c && tables && out, "null");
+    PCB_CUDA_OK(cudaSetDevice(c->device));
+    pcb_op* o = new pcb_op;
+    o->ctx = c; o->T = nullptr; o->diel = nullptr;
+    PCB_CUDA_OK(cudaMalloc(&o->T, sizeof(cplx) * 9 * (size_t)c->N));
+    if (int rc = pcb_op_update(o, tables, gamma, shift, pshift, diel)) { cudaFree(o->T); delete o; return rc; }
+    *out = o;
+    return 0;
+}
+void pcb_op_destroy(pcb_op* o) {
+    if (!o) return;
+    cudaSetDevice(o->ctx->device);
+    cudaStreamSynchronize(o->ctx->stream);
+    if (o->T) cudaFree(o->T);
+    delete o;
+}
+
+static int launch_crossdof(pcb_op* o, const cplx* X, cplx* Y) {
+    pcb_ctx* c = o->ctx;
+    dim3 grid((unsigned)((c->nn + 127) / 128), 1, 1);
+    PCB_LAUNCH(k_diel_crossdof, grid, dim3(128, 1, 1), 0, c->stream, o->d, o->diel->st, X, Y);
+    PCB_CUDA_OK(cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
+int pcb_apply(pcb_op* o, int mode, int ncols, const void* const* in, void* const* out) {
+    PCB_CHECK_ARG(o && in && out && ncols > 0, "bad arguments");
+    pcb_ctx* c = o->ctx;
+    PCB_CUDA_OK(cudaSetDevice(c->device));
+    const PcbOpLaunch* pl = c->plan;
+    const bool cross = (o->d.diel == PCB_DIEL_CROSSDOF);
+    for (int j0 = 0; j0 < ncols; j0 += PCB_MAXC) {
+        const int kc = (ncols - j0 < PCB_MAXC) ? ncols - j0 : PCB_MAXC;
+        PcbCols cols;
+        for (int j = 0; j < kc; ++j) { cols.in[j] = (const cplx*)in[j0 + j]; cols.out[j] = (cplx*)out[j0 + j]; }
+        switch (mode) {
+            case PCB_APPLY_FFT: case PCB_APPLY_IFFT:
+                // plain transforms are in place on `out`; copy first when out of place
+                for (int j = 0; j < kc; ++j)
+                    if (cols.in[j] != cols.out[j]) PCB_CUDA_OK(cudaMemcpyAsync(cols.out[j], cols.in[j], sizeof(cplx) * (size_t)c->R, cudaMemcpyDeviceToDevice, c->stream));
+                if (pl->apply(o->d, cols, kc, mode == PCB_APPLY_FFT ? 0 : 1, c->tw, c->stream)) return -1;
+                c->launches += 3;
+                break;
+            case PCB_APPLY_A: case PCB_APPLY_H: {
+                const int last = (mode == PCB_APPLY_A) ? PCB_PASS_XINV_A : PCB_PASS_XINV_H;
+                if (!cross) {
+                    const int seq[5] = {PCB_PASS_XFWD_SYM, PCB_PASS_YFWD, PCB_PASS_ZMID, PCB_PASS_YINV, last};
+                    for (int i = 0; i < 5; ++i) if (pl->pass(o->d, cols, kc, seq[i], c->tw, c->stream)) return -1;
+                    c->launches += 5;
+                } else {
+                    // cross-DoF M is a stencil in real space: forward passes into scratch, M scratch -> out, inverse in place
+                    if (ensure_scratch(c, sizeof(cplx) * (size_t)c->R * (size_t)kc)) return -1;
+                    PcbCols tmp = cols;
+                    for (int j = 0; j < kc; ++j) tmp.out[j] = c->scratch + (size_t)j * c->R;
+                    const int fwd[3] = {PCB_PASS_XFWD_SYM, PCB_PASS_YFWD, PCB_PASS_ZFWD};
+                    for (int i = 0; i < 3; ++i) if (pl->pass(o->d, tmp, kc, fwd[i], c->tw, c->stream)) return -1;
+                    for (int j = 0; j < kc; ++j) if (launch_crossdof(o, tmp.out[j], cols.out[j])) return -1;
+                    const int inv[3] = {PCB_PASS_ZINV, PCB_PASS_YINV, last};
+                    for (int i = 0; i < 3; ++i) if (pl->pass(o->d, cols, kc, inv[i], c->tw, c->stream)) return -1;
+                    c->launches += 6;
+                }
+            } break;
+            case PCB_APPLY_P: {
+                PcbResidArgs a;
+                for (int j = 0; j < kc; ++j) { a.x[j] = cols.in[j]; a.hx[j] = nullptr; a.w[j] = cols.out[j]; a.lambda[j] = 0.0; }
+                const int gx = grid_for(c, c->nn, 256, 4);
+                if (ensure_partial(c, sizeof(double) * (size_t)gx * PCB_MAXC_RP)) return -1;
+                dim3 grid((unsigned)gx, (unsigned)((kc + PCB_RP_CH - 1) / PCB_RP_CH), 1);
+                PCB_LAUNCH(k_resid_precond<2>, grid, dim3(256, 1, 1), 0, c->stream, o->d, a, kc, c->partial);
+                PCB_CUDA_OK(cudaGetLastError());
+                c->launches++;
+            } break;
+            case PCB_APPLY_M:
+                for (int j = 0; j < kc; ++j) {
+                    if (cross) {
+                        PCB_CHECK_ARG(cols.in[j] != cols.out[j], "cross-DoF dielectric cannot run in place");
+                        if (launch_crossdof(o, cols.in[j], cols.out[j])) return -1;
+                    } else {
+                        dim3 grid((unsigned)grid_for(c, c->nn, 256, 8), 1, 1);
+                        PCB_LAUNCH(k_diel_point, grid, dim3(256, 1, 1), 0, c->stream, o->d, cols.in[j], cols.out[j]);
+                        PCB_CUDA_OK(cudaGetLastError());
+                        c->launches++;
+                    }
+                }
+                break;
+            case PCB_APPLY_KA: case PCB_APPLY_KAH: case PCB_APPLY_KB: {
+                dim3 grid((unsigned)grid_for(c, c->nn, 256, 8), (unsigned)kc, 1);
+                if (mode == PCB_APPLY_KA) PCB_LAUNCH(k_symbol_point<0>, grid, dim3(256, 1, 1), 0, c->stream, o->d, cols);
+                else if (mode == PCB_APPLY_KAH) PCB_LAUNCH(k_symbol_point<1>, grid, dim3(256, 1, 1), 0, c->stream, o->d, cols);
+                else PCB_LAUNCH(k_symbol_point<2>, grid, dim3(256, 1, 1), 0, c->stream, o->d, cols);
+                PCB_CUDA_OK(cudaGetLastError());
+                c->launches++;
+            } break;
+            default:
+                pcb_set_error("pcb_apply: unknown mode %d", mode);
+                return -2;
+        }
+    }
+    return 0;
+}
+
+// ---- block kernels ----------------------------------------------------------------------------------------------
+int pcb_residual(pcb_op* o, int precond, int ncols, const void* const* x, const void* const* hx, void* const* w,
+                 const double* lambda, double* norms2) {
+    PCB_CHECK_ARG(o && x && hx && w && lambda && norms2 && ncols > 0, "bad arguments");
+    pcb_ctx* c = o->ctx;
+    PCB_CUDA_OK(cudaSetDevice(c->device));
+    const int gx = grid_for(c, c->nn, 256, 4);
+    if (ensure_partial(c, sizeof(double) * (size_t)gx * PCB_MAXC_RP + sizeof(double) * PCB_MAXC_RP)) return -1;
+    if (ensure_hstage(c, 65536)) return -1;
+    for (int j0 = 0; j0 < ncols; j0 += PCB_MAXC_RP) {
+        const int kc = (ncols - j0 < PCB_MAXC_RP) ? ncols - j0 : PCB_MAXC_RP;
+        PcbResidArgs a;
+        for (int j = 0; j < kc; ++j) {
+            a.x[j] = (const cplx*)x[j0 + j]; a.hx[j] = (const cplx*)hx[j0 + j]; a.w[j] = (cplx*)w[j0 + j]; a.lambda[j] = lambda[j0 + j];
+        }
+        dim3 grid((unsigned)gx, (unsigned)((kc + PCB_RP_CH - 1) / PCB_RP_CH), 1);
+        if (precond) PCB_LAUNCH(k_resid_precond<1>, grid, dim3(256, 1, 1), 0, c->stream, o->d, a, kc, c->partial);
+        else PCB_LAUNCH(k_resid_precond<0>, grid, dim3(256, 1, 1), 0, c->stream, o->d, a, kc, c->partial);
+        PCB_CUDA_OK(cudaGetLastError());
+        double* dout = c->partial + (size_t)gx * PCB_MAXC_RP;
+        PCB_LAUNCH(k_sum_partials, dim3(1, 1, 1), dim3(64, 1, 1), 0, c->stream, (const double*)c->partial, gx, kc, dout);
+        PCB_CUDA_OK(cudaGetLastError());
+        c->launches += 2;
+        PCB_CUDA_OK(cudaMemcpyAsync(c->hstage, dout, sizeof(double) * kc, cudaMemcpyDeviceToHost, c->stream));
+        PCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+        memcpy(norms2 + j0, c->hstage, sizeof(double) * kc);
+    }
+    return 0;
+}
+
+int pcb_gram2(pcb_ctx* c, int n, const void* const* s, const void* const* hs, void* G, void* T) {
+    PCB_CHECK_ARG(c && s && hs && G && T && n > 0 && n <= PCB_MAXL, "bad arguments (n <= 96)");
+    PCB_CUDA_OK(cudaSetDevice(c->device));
+    const int nb = (n + 3) / 4, np4 = 4 * nb;
+    PcbColList S, HS;
+    // column a of the padded problem maps to input column: strided sets {ia + nb*j} -> keep natural order, pad with null
+    for (int j = 0; j < PCB_MAXL; ++j) { S.p[j] = (j < n) ? (const cplx*)s[j] : nullptr; HS.p[j] = (j < n) ? (const cplx*)hs[j] : nullptr; }
+    const int npairs = nb * (nb + 1) / 2;
+    int PP = npairs < PCB_GRAM_NT ? npairs : PCB_GRAM_NT;
+    const int gy = (npairs + PP - 1) / PP;
+    const int NP = np4 | 1;
+    const size_t tile = (size_t)PCB_GRAM_TR * NP * sizeof(cplx);
+    size_t smem = 4 * tile;
+    const size_t red = (size_t)PP * 32 * sizeof(cplx);
+    if (smem < red) smem = red;
+    const long long ntiles = (c->R + PCB_GRAM_TR - 1) / PCB_GRAM_TR;
+    int per_sm = (int)((size_t)220 * 1024 / smem); if (per_sm < 1) per_sm = 1; if (per_sm > 4) per_sm = 4;
+    long long gx = (long long)c->sms * per_sm / gy; if (gx < 1) gx = 1; if (gx > ntiles) gx = ntiles;
+    const size_t pbytes = sizeof(cplx) * (size_t)gx * 2 * np4 * np4;
+    if (ensure_partial(c, pbytes)) return -1;
+    if (ensure_dsmall(c, sizeof(cplx) * 2 * PCB_MAXL * PCB_MAXL + 65536)) return -1;
+    if (ensure_hstage(c, sizeof(cplx) * 2 * PCB_MAXL * PCB_MAXL + 65536)) return -1;
+    PCB_CUDA_OK(cudaMemsetAsync(c->partial, 0, pbytes, c->stream));
+#ifndef PCB_EMU
+    if (smem > 48 * 1024) PCB_CUDA_OK(cudaFuncSetAttribute(k_gram2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#endif
+    dim3 grid((unsigned)gx, (unsigned)gy, 1);
+    PCB_LAUNCH(k_gram2, grid, dim3(PCB_GRAM_NT, 1, 1), smem, c->stream, S, HS, nb, c->R, PP, npairs, (cplx*)c->partial);
+    PCB_CUDA_OK(cudaGetLastError());
+    cplx* dout = (cplx*)c->dsmall;
+    const int ne = 2 * np4 * np4;
+    PCB_LAUNCH(k_gram_finish, dim3((unsigned)((ne + 127) / 128), 1, 1), dim3(128, 1, 1), 0, c->stream, (const cplx*)c->partial, (int)gx, nb, dout);
+    PCB_CUDA_OK(cudaGetLastError());
+    c->launches += 2;
+    PCB_CUDA_OK(cudaMemcpyAsync(c->hstage, dout, sizeof(cplx) * ne, cudaMemcpyDeviceToHost, c->stream));
+    PCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+    const cplx* h = (const cplx*)c->hstage;
+    cplx* g = (cplx*)G; cplx* t = (cplx*)T;
+    // hermitize on the host (hermitize(), orthogonalization.py:26-33): (M + M^H)/2
+    for (int a = 0; a < n; ++a)
+        for (int b = 0; b < n; ++b) {
+            const cplx gab = h[a * np4 + b], gba = h[b * np4 + a];
+            const cplx tab = h[np4 * np4 + a * np4 + b], tba = h[np4 * np4 + b * np4 + a];
+            g[a * n + b] = cmake(0.5 * (gab.x + gba.x), 0.5 * (gab.y - gba.y));
+            t[a * n + b] = cmake(0.5 * (tab.x + tba.x), 0.5 * (tab.y - tba.y));
+        }
+    return 0;
+}
+
+int pcb_update(pcb_ctx* c, int m, int nl, void* const* s, void* const* hs, void* const* p_out, void* const* hp_out, const void* E) {
+    PCB_CHECK_ARG(c && s && hs && p_out && hp_out && E && m > 0 && nl >= m && nl <= PCB_MAXL && m <= 32, "bad arguments");
+    PCB_CUDA_OK(cudaSetDevice(c->device));
+    const int JB = (m + 7) / 8;
+    PCB_CHECK_ARG(JB == 1 || JB == 2 || JB == 3 || JB == 4, "m <= 32");
+    if (ensure_hstage(c, sizeof(cplx) * 2 * PCB_MAXL * PCB_MAXL + 65536)) return -1;
+    if (ensure_dsmall(c, sizeof(cplx) * 2 * PCB_MAXL * PCB_MAXL + 65536)) return -1;
+    const int JBk = (JB == 3) ? 4 : JB;        // kernel variants: 8, 16 or 32 output columns
+    const int MPk = 8 * JBk;
+    const int TRs[5] = {0, 128, 64, 32, 32};   // rows per tile = NT / JBk with NT = 128
+    PCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+    cplx* he = (cplx*)c->hstage;
+    const cplx* e = (const cplx*)E;
+    for (int k = 0; k < nl; ++k)
+        for (int j = 0; j < MPk; ++j) he[k * MPk + j] = (j < m) ? e[k * m + j] : cmake(0.0, 0.0);
+    PCB_CUDA_OK(cudaMemcpyAsync(c->dsmall, he, sizeof(cplx) * nl * MPk, cudaMemcpyHostToDevice, c->stream));
+    PcbColList Sin, HSin;
+    PcbColListW X, HX, P, HP;
+    for (int k = 0; k < PCB_MAXL; ++k) {
+        Sin.p[k] = (k < nl) ? (const cplx*)s[k] : nullptr; HSin.p[k] = (k < nl) ? (const cplx*)hs[k] : nullptr;
+        X.p[k] = (k < m) ? (cplx*)s[k] : nullptr; HX.p[k] = (k < m) ? (cplx*)hs[k] : nullptr;
+        P.p[k] = (k < m) ? (cplx*)p_out[k] : nullptr; HP.p[k] = (k < m) ? (cplx*)hp_out[k] : nullptr;
+    }
+    const int TR = TRs[JBk];
+    const size_t smem = sizeof(cplx) * ((size_t)nl * MPk + 2 * (size_t)nl * TR);
+    const long long ntiles = (c->R + TR - 1) / TR;
+    int per_sm = (int)((size_t)220 * 1024 / smem); if (per_sm < 1) per_sm = 1; if (per_sm > 8) per_sm = 8;
+    long long gx = (long long)c->sms * per_sm; if (gx > ntiles) gx = ntiles;
+    dim3 grid((unsigned)gx, 1, 1);
+#ifndef PCB_EMU
+#define PCB_UPD_ATTR(K) if (smem > 48 * 1024) PCB_CUDA_OK(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
+#else
+#define PCB_UPD_ATTR(K)
+#endif
+    const cplx* dE = (const cplx*)c->dsmall;
+    if (JBk == 1) { PCB_UPD_ATTR(k_update<1>); PCB_LAUNCH(k_update<1>, grid, dim3(PCB_UPD_NT, 1, 1), smem, c->stream, Sin, HSin, X, HX, P, HP, dE, m, nl, c->R); }
+    else if (JBk == 2) { PCB_UPD_ATTR(k_update<2>); PCB_LAUNCH(k_update<2>, grid, dim3(PCB_UPD_NT, 1, 1), smem, c->stream, Sin, HSin, X, HX, P, HP, dE, m, nl, c->R); }
+    else { PCB_UPD_ATTR(k_update<4>); PCB_LAUNCH(k_update<4>, grid, dim3(PCB_UPD_NT, 1, 1), smem, c->stream, Sin, HSin, X, HX, P, HP, dE, m, nl, c->R); }
+    PCB_CUDA_OK(cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
+int pcb_coldots(pcb_ctx* c, int ncols, const void* const* a, const void* const* b, void* out) {
+    PCB_CHECK_ARG(c && a && b && out && ncols > 0 && ncols <= PCB_MAXL, "bad arguments");
+    PCB_CUDA_OK(cudaSetDevice(c->device));
+    const int gx = grid_for(c, c->R, 256, 4);
+    if (ensure_partial(c, sizeof(cplx) * ((size_t)gx + 1) * PCB_MAXL)) return -1;
+    if (ensure_hstage(c, 65536)) return -1;
+    PcbColList A, B;
+    for (int j = 0; j < PCB_MAXL; ++j) { A.p[j] = (j < ncols) ? (const cplx*)a[j] : nullptr; B.p[j] = (j < ncols) ? (const cplx*)b[j] : nullptr; }
+    dim3 grid((unsigned)gx, (unsigned)ncols, 1);
+    PCB_LAUNCH(k_coldots, grid, dim3(256, 1, 1), 0, c->stream, A, B, ncols, c->R, (cplx*)c->partial);
+    PCB_CUDA_OK(cudaGetLastError());
+    double* dout = c->partial + 2 * (size_t)gx * PCB_MAXL;
+    PCB_LAUNCH(k_sum_partials, dim3((unsigned)((2 * ncols + 63) / 64), 1, 1), dim3(64, 1, 1), 0, c->stream, (const double*)c->partial, gx, 2 * ncols, dout);
+    PCB_CUDA_OK(cudaGetLastError());
+    c->launches += 2;
+    PCB_CUDA_OK(cudaMemcpyAsync(c->hstage, dout, sizeof(cplx) * ncols, cudaMemcpyDeviceToHost, c->stream));
+    PCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+    memcpy(out, c->hstage, sizeof(cplx) * ncols);
+    return 0;
+}
+
+int pcb_axpby(pcb_ctx* c, int ncols, const void* const* x, void* const* y, double alpha, double beta) {
+    PCB_CHECK_ARG(c && x && y && ncols > 0, "bad arguments");
+    PCB_CUDA_OK(cudaSetDevice(c->device));
+    for (int j = 0; j < ncols; ++j) {
+        dim3 grid((unsigned)grid_for(c, c->R, 256, 8), 1, 1);
+        PCB_LAUNCH(k_axpby, grid, dim3(256, 1, 1), 0, c->stream, (const cplx*)x[j], (cplx*)y[j], alpha, beta, c->R);
+        PCB_CUDA_OK(cudaGetLastError());
+        c->launches++;
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,425 @@
+// pcb200 -- the matrix-free operator  H x = K_A IFFT3( M FFT3( K_A^H x ) ) + gamma K_B x + shift x
+// (reference: pcfft.py:130-181, _kernels.py:13-71, discretization.py:352-401) as hand-written
+// mixed-radix complex128 FFT passes with the Fourier symbols and the dielectric multiply fused in.
+//
+// One block apply = five global passes over the destination column (all in place except the
+// first, which reads X and writes the destination):
+//
+//   xfwd   x-lines:  y = (-conj k) x x  fused on load, forward FFT along i0          (K_A^H, pass 1)
+//   yline  y-lines:  forward FFT along i1                                            (pass 2)
+//   zmid   z-lines:  forward FFT along i2, M (point-wise, real space), inverse FFT   (pass 3)
+//   yline  y-lines:  inverse FFT along i1                                            (pass 4)
+//   xinv   x-lines:  inverse FFT along i0, 1/N^3, k x v, + gamma conj(k)(k.x) + shift x on store
+//
+// Every 1-D FFT of length N = R1*R2 is two in-register radix codelets with ONE shared-memory
+// exchange between them:  global -> regs (radix R1) -> smem -> regs (radix R2) -> global.
+// y/z lines are processed for 8 consecutive i0 at once (128-byte segments, fully coalesced);
+// coprime factorisations use the Good-Thomas maps there (no twiddles), x-lines always use
+// Cooley-Tukey so that global accesses stay contiguous.  The z pass keeps the data in
+// registers between the last forward radix and the first inverse radix, so FFT+M+IFFT along
+// z costs two exchanges.
+#pragma once
+#include "pcb_common.cuh"
+
+#define PCB_MAXC 32   // columns per launch (pointer lists travel in kernel parameter space)
+
+struct PcbCols {
+    const cplx* in[PCB_MAXC];   // source columns (X)
+    cplx* out[PCB_MAXC];        // destination / work columns
+};
+
+constexpr int pcb_gcd(int a, int b) { return b == 0 ? a : pcb_gcd(b, a % b); }
+constexpr int pcb_modinv(int a, int m) {   // a^-1 mod m (m small)
+    for (int x = 1; x < m; ++x) if ((a * x) % m == 1) return x;
+    return 1;
+}
+
+template <int N_, int R1_, int R2_>
+struct Plan {
+    static constexpr int N = N_, R1 = R1_, R2 = R2_;
+    static_assert(R1_ * R2_ == N_, "N = R1 * R2");
+    static constexpr bool PFA = pcb_gcd(R1_, R2_) == 1;
+    static constexpr int U = pcb_modinv(R2_ % R1_, R1_);   // R2^-1 mod R1
+    static constexpr int V = pcb_modinv(R1_ % R2_, R2_);   // R1^-1 mod R2
+    static constexpr int R2P = R2_ | 1;                    // odd stride: conflict-free strided smem access
+    // index maps of the strided (y/z) passes
+    PCB_HD static int lin(int n1, int n2) { return PFA ? (R2 * n1 + R1 * n2) % N : n1 * R2 + n2; }
+    PCB_HD static int lout(int k1, int k2) { return PFA ? (R2 * U * k1 + R1 * V * k2) % N : k1 + R1 * k2; }
+};
+
+// z = a x v  (cross product, _kernels.py:51-66)
+PCB_HD void pcb_cross(const cplx a[3], const cplx v[3], cplx z[3]) {
+    z[0] = csub(cmul(a[1], v[2]), cmul(a[2], v[1]));
+    z[1] = csub(cmul(a[2], v[0]), cmul(a[0], v[2]));
+    z[2] = csub(cmul(a[0], v[1]), cmul(a[1], v[0]));
+}
+
+// ---------------------------------------------------------------------------------------
+// Pass 1: x-lines forward.  SYM: 0 plain FFT, 1 multiply by K_A^H = (-conj k) x . on load.
+// Tile = LX consecutive rows (a row = all i0 for one (i1,i2)), all three components.
+// ---------------------------------------------------------------------------------------
+template <class P, int LX, int NT, int SYM>
+__global__ void __launch_bounds__(NT) k_xfwd(PcbOp op, PcbCols cols, const cplx* __restrict__ tw) {
+    constexpr int N = P::N, R1 = P::R1, R2 = P::R2, R2P = P::R2P;
+    PCB_DYN_SMEM(cplx, sm);   // [3][LX][R1][R2P]
+    const int col = blockIdx.y;
+    const cplx* __restrict__ X = cols.in[col];
+    cplx* __restrict__ Y = cols.out[col];
+    const long long nn = op.nn;
+    const int row0 = blockIdx.x * LX;
+    const int nrows = N * N;
+    const int tid = threadIdx.x;
+
+    for (int item = tid; item < LX * R2; item += NT) {
+        const int r = item / R2, n2 = item % R2;
+        const int row = row0 + r;
+        if (row >= nrows) continue;
+        const int i1 = row % N, i2 = row / N;
+        cplx v[3][R1];
+        cplx kc[3];
+        if (SYM) {
+            PCB_UNROLL
+            for (int c = 0; c < 3; ++c) {
+                const cplx b = __ldg(op.T + (c * 3 + 1) * N + i1);
+                const cplx d = __ldg(op.T + (c * 3 + 2) * N + i2);
+                kc[c] = cadd(b, d);
+            }
+        }
+        PCB_UNROLL
+        for (int n1 = 0; n1 < R1; ++n1) {
+            const int i0 = n1 * R2 + n2;
+            const long long e = (long long)row * N + i0;
+            cplx x[3];
+            PCB_UNROLL
+            for (int c = 0; c < 3; ++c) x[c] = X[c * nn + e];
+            if (SYM) {
+                cplx a[3], z[3];
+                PCB_UNROLL
+                for (int c = 0; c < 3; ++c) {
+                    const cplx k = cadd(kc[c], __ldg(op.T + (c * 3 + 0) * N + i0));
+                    a[c] = cmake(-k.x, k.y);   // -conj(k)
+                }
+                pcb_cross(a, x, z);
+                PCB_UNROLL
+                for (int c = 0; c < 3; ++c) v[c][n1] = z[c];
+            } else {
+                PCB_UNROLL
+                for (int c = 0; c < 3; ++c) v[c][n1] = x[c];
+            }
+        }
+        PCB_UNROLL
+        for (int c = 0; c < 3; ++c) {
+            Dft<R1, -1>::run(v[c]);
+            PCB_UNROLL
+            for (int k1 = 0; k1 < R1; ++k1) {
+                cplx val = v[c][k1];
+                if (k1 > 0) val = cmul(val, __ldg(tw + k1 * R2 + n2));
+                sm[((c * LX + r) * R1 + k1) * R2P + n2] = val;
+            }
+        }
+    }
+    __syncthreads();
+    for (int item = tid; item < 3 * LX * R1; item += NT) {
+        const int k1 = item % R1;
+        const int r = (item / R1) % LX;
+        const int c = item / (R1 * LX);
+        const int row = row0 + r;
+        if (row >= nrows) continue;
+        cplx v[R2];
+        PCB_UNROLL
+        for (int n2 = 0; n2 < R2; ++n2) v[n2] = sm[((c * LX + r) * R1 + k1) * R2P + n2];
+        Dft<R2, -1>::run(v);
+        cplx* __restrict__ dst = Y + c * nn + (long long)row * N + k1;
+        PCB_UNROLL
+        for (int k2 = 0; k2 < R2; ++k2) dst[R1 * k2] = v[k2];
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Pass 5: x-lines inverse.  MODE 0: plain IFFT * 1/N^3;  1: A = K_A . ;  2: H = K_A . + gamma K_B x + shift x
+// Reads the work column W (in Fourier-x order), the source column X (MODE 2) and writes OUT
+// (OUT may alias W: each CTA only touches its own rows).
+// ---------------------------------------------------------------------------------------
+template <class P, int LX, int NT, int MODE>
+__global__ void __launch_bounds__(NT) k_xinv(PcbOp op, PcbCols cols, const cplx* __restrict__ tw) {
+    constexpr int N = P::N, R1 = P::R1, R2 = P::R2, R2P = P::R2P;
+    PCB_DYN_SMEM(cplx, sm);   // [3][LX][R1][R2P]
+    const int col = blockIdx.y;
+    const cplx* __restrict__ X = cols.in[col];
+    cplx* __restrict__ W = cols.out[col];
+    const long long nn = op.nn;
+    const int row0 = blockIdx.x * LX;
+    const int nrows = N * N;
+    const int tid = threadIdx.x;
+
+    for (int item = tid; item < 3 * LX * R1; item += NT) {
+        const int k1 = item % R1;
+        const int r = (item / R1) % LX;
+        const int c = item / (R1 * LX);
+        const int row = row0 + r;
+        if (row >= nrows) continue;
+        cplx v[R2];
+        const cplx* __restrict__ src = W + c * nn + (long long)row * N + k1;
+        PCB_UNROLL
+        for (int k2 = 0; k2 < R2; ++k2) v[k2] = src[R1 * k2];
+        Dft<R2, +1>::run(v);
+        PCB_UNROLL
+        for (int n2 = 0; n2 < R2; ++n2) {
+            cplx val = v[n2];
+            if (k1 > 0) { const cplx t = __ldg(tw + k1 * R2 + n2); val = cmul(val, cmake(t.x, -t.y)); }
+            sm[((c * LX + r) * R1 + k1) * R2P + n2] = val;
+        }
+    }
+    __syncthreads();
+    for (int item = tid; item < LX * R2; item += NT) {
+        const int r = item / R2, n2 = item % R2;
+        const int row = row0 + r;
+        if (row >= nrows) continue;
+        const int i1 = row % N, i2 = row / N;
+        cplx v[3][R1];
+        PCB_UNROLL
+        for (int c = 0; c < 3; ++c) {
+            PCB_UNROLL
+            for (int k1 = 0; k1 < R1; ++k1) v[c][k1] = sm[((c * LX + r) * R1 + k1) * R2P + n2];
+            Dft<R1, +1>::run(v[c]);
+        }
+        cplx kc[3];
+        if (MODE) {
+            PCB_UNROLL
+            for (int c = 0; c < 3; ++c) {
+                const cplx b = __ldg(op.T + (c * 3 + 1) * N + i1);
+                const cplx d = __ldg(op.T + (c * 3 + 2) * N + i2);
+                kc[c] = cadd(b, d);
+            }
+        }
+        PCB_UNROLL
+        for (int n1 = 0; n1 < R1; ++n1) {
+            const int i0 = n1 * R2 + n2;
+            const long long e = (long long)row * N + i0;
+            cplx u[3], z[3];
+            PCB_UNROLL
+            for (int c = 0; c < 3; ++c) u[c] = cscale(v[c][n1], op.inv_n3);
+            if (MODE) {
+                cplx k[3];
+                PCB_UNROLL
+                for (int c = 0; c < 3; ++c) k[c] = cadd(kc[c], __ldg(op.T + (c * 3 + 0) * N + i0));
+                pcb_cross(k, u, z);
+                if (MODE == 2) {
+                    cplx x[3];
+                    PCB_UNROLL
+                    for (int c = 0; c < 3; ++c) x[c] = X[c * nn + e];
+                    // gamma K_B x = gamma conj(k) (k . x)   (h_block with D_B, pcfft.py:176)
+                    cplx dot = cadd(cadd(cmul(k[0], x[0]), cmul(k[1], x[1])), cmul(k[2], x[2]));
+                    dot = cscale(dot, op.gamma);
+                    PCB_UNROLL
+                    for (int c = 0; c < 3; ++c) {
+                        cplx t = cfmac(k[c], dot, z[c]);
+                        t.x = fma(op.shift, x[c].x, t.x);
+                        t.y = fma(op.shift, x[c].y, t.y);
+                        z[c] = t;
+                    }
+                }
+            } else {
+                PCB_UNROLL
+                for (int c = 0; c < 3; ++c) z[c] = u[c];
+            }
+            PCB_UNROLL
+            for (int c = 0; c < 3; ++c) W[c * nn + e] = z[c];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Passes 2/4 (and the split z passes of the cross-DoF variant): strided lines, in place.
+// DIM 1: lines along i1 (tile = 8 i0 x one i2);  DIM 2: lines along i2 (tile = 8 i0 x one i1).
+// A CTA handles the three components of one tile.
+// ---------------------------------------------------------------------------------------
+template <class P, int DIM, int DIR, int NT>
+__global__ void __launch_bounds__(NT) k_line(PcbOp op, PcbCols cols, const cplx* __restrict__ tw) {
+    constexpr int N = P::N, R1 = P::R1, R2 = P::R2;
+    PCB_DYN_SMEM(cplx, sm);   // [3][N][8]
+    const int col = blockIdx.y;
+    cplx* __restrict__ Y = cols.out[col];
+    const long long nn = op.nn;
+    constexpr int NT0 = (N + 7) / 8;
+    const int t0 = blockIdx.x % NT0, other = blockIdx.x / NT0;
+    const long long sline = (DIM == 1) ? N : (long long)N * N;
+    const long long sother = (DIM == 1) ? (long long)N * N : N;
+    const int tid = threadIdx.x;
+
+    for (int item = tid; item < 3 * R2 * 8; item += NT) {
+        const int i0l = item % 8, n2 = (item / 8) % R2, c = item / (8 * R2);
+        const int i0 = t0 * 8 + i0l;
+        if (i0 >= N) continue;
+        cplx* __restrict__ base = Y + c * nn + other * sother + i0;
+        cplx v[R1];
+        PCB_UNROLL
+        for (int n1 = 0; n1 < R1; ++n1) v[n1] = base[P::lin(n1, n2) * sline];
+        Dft<R1, DIR>::run(v);
+        PCB_UNROLL
+        for (int k1 = 0; k1 < R1; ++k1) {
+            cplx val = v[k1];
+            if (!P::PFA && k1 > 0) {
+                const cplx t = __ldg(tw + k1 * R2 + n2);
+                val = cmul(val, cmake(t.x, DIR < 0 ? t.y : -t.y));
+            }
+            sm[(c * N + k1 * R2 + n2) * 8 + i0l] = val;
+        }
+    }
+    __syncthreads();
+    for (int item = tid; item < 3 * R1 * 8; item += NT) {
+        const int i0l = item % 8, k1 = (item / 8) % R1, c = item / (8 * R1);
+        const int i0 = t0 * 8 + i0l;
+        if (i0 >= N) continue;
+        cplx v[R2];
+        PCB_UNROLL
+        for (int n2 = 0; n2 < R2; ++n2) v[n2] = sm[(c * N + k1 * R2 + n2) * 8 + i0l];
+        Dft<R2, DIR>::run(v);
+        cplx* __restrict__ base = Y + c * nn + other * sother + i0;
+        PCB_UNROLL
+        for (int k2 = 0; k2 < R2; ++k2) base[P::lout(k1, k2) * sline] = v[k2];
+    }
+}
+
+// Point-wise dielectric multiply on the three components at one grid point (real space).
+// chiral: rows in Omega_1 scaled by 1/eps (discretization.py:352-366); trivial: Hermitian 3x3
+// with diagonal eps_cc on edge DoFs and off-diagonals on the cell's volume DoF (:368-401).
+PCB_HD void pcb_diel_point(const PcbOp& op, unsigned m, cplx u[3]) {
+    const double d0 = (m & 1u) ? op.ediag[0] : 1.0;
+    const double d1 = (m & 2u) ? op.ediag[1] : 1.0;
+    const double d2 = (m & 4u) ? op.ediag[2] : 1.0;
+    cplx y0 = cscale(u[0], d0), y1 = cscale(u[1], d1), y2 = cscale(u[2], d2);
+    if (m & 8u) {
+        y0 = cfma(op.eoff[0], u[1], cfma(op.eoff[1], u[2], y0));
+        y1 = cfmac(op.eoff[0], u[0], cfma(op.eoff[2], u[2], y1));
+        y2 = cfmac(op.eoff[1], u[0], cfmac(op.eoff[2], u[1], y2));
+    }
+    u[0] = y0; u[1] = y1; u[2] = y2;
+}
+
+// ---------------------------------------------------------------------------------------
+// Pass 3: z-lines: forward FFT, dielectric multiply M in real space, inverse FFT; in place.
+// DIEL: 0 identity, 1 component-wise (chiral), 2 coupled 3x3 at a point (trivial).
+// Tile = 8 i0 x one i1, all i2, three components.
+// ---------------------------------------------------------------------------------------
+template <class P, int DIEL, int NT>
+__global__ void __launch_bounds__(NT) k_zmid(PcbOp op, PcbCols cols, const cplx* __restrict__ tw) {
+    constexpr int N = P::N, R1 = P::R1, R2 = P::R2;
+    PCB_DYN_SMEM(cplx, sm);   // [3][N][8] complex, then [N][8] mask bytes
+    unsigned char* msk = reinterpret_cast<unsigned char*>(sm + 3 * N * 8);
+    const int col = blockIdx.y;
+    cplx* __restrict__ Y = cols.out[col];
+    const long long nn = op.nn;
+    constexpr int NT0 = (N + 7) / 8;
+    const int t0 = blockIdx.x % NT0, i1 = blockIdx.x / NT0;
+    const long long sline = (long long)N * N;
+    const int tid = threadIdx.x;
+
+    if (DIEL) {
+        for (int item = tid; item < N * 8; item += NT) {
+            const int i0l = item % 8, i2 = item / 8;
+            const int i0 = t0 * 8 + i0l;
+            msk[item] = (i0 < N) ? op.mask[((long long)i2 * N + i1) * N + i0] : 0;
+        }
+    }
+    for (int item = tid; item < 3 * R2 * 8; item += NT) {
+        const int i0l = item % 8, n2 = (item / 8) % R2, c = item / (8 * R2);
+        const int i0 = t0 * 8 + i0l;
+        if (i0 >= N) continue;
+        const cplx* __restrict__ base = Y + c * nn + (long long)i1 * N + i0;
+        cplx v[R1];
+        PCB_UNROLL
+        for (int n1 = 0; n1 < R1; ++n1) v[n1] = base[P::lin(n1, n2) * sline];
+        Dft<R1, -1>::run(v);
+        PCB_UNROLL
+        for (int k1 = 0; k1 < R1; ++k1) {
+            cplx val = v[k1];
+            if (!P::PFA && k1 > 0) val = cmul(val, __ldg(tw + k1 * R2 + n2));
+            sm[(c * N + k1 * R2 + n2) * 8 + i0l] = val;
+        }
+    }
+    __syncthreads();
+    if (DIEL == 2) {
+        for (int item = tid; item < R1 * 8; item += NT) {
+            const int i0l = item % 8, k1 = item / 8;
+            if (t0 * 8 + i0l >= N) continue;
+            cplx v[3][R2];
+            PCB_UNROLL
+            for (int c = 0; c < 3; ++c) {
+                PCB_UNROLL
+                for (int n2 = 0; n2 < R2; ++n2) v[c][n2] = sm[(c * N + k1 * R2 + n2) * 8 + i0l];
+                Dft<R2, -1>::run(v[c]);
+            }
+            PCB_UNROLL
+            for (int k2 = 0; k2 < R2; ++k2) {
+                const int i2 = P::lout(k1, k2);
+                cplx u[3] = {v[0][k2], v[1][k2], v[2][k2]};
+                pcb_diel_point(op, msk[i2 * 8 + i0l], u);
+                v[0][k2] = u[0]; v[1][k2] = u[1]; v[2][k2] = u[2];
+            }
+            PCB_UNROLL
+            for (int c = 0; c < 3; ++c) {
+                Dft<R2, +1>::run(v[c]);
+                PCB_UNROLL
+                for (int n2 = 0; n2 < R2; ++n2) {
+                    cplx val = v[c][n2];
+                    if (!P::PFA && k1 > 0) { const cplx t = __ldg(tw + k1 * R2 + n2); val = cmul(val, cmake(t.x, -t.y)); }
+                    sm[(c * N + k1 * R2 + n2) * 8 + i0l] = val;
+                }
+            }
+        }
+    } else {
+        for (int item = tid; item < 3 * R1 * 8; item += NT) {
+            const int i0l = item % 8, k1 = (item / 8) % R1, c = item / (8 * R1);
+            if (t0 * 8 + i0l >= N) continue;
+            cplx v[R2];
+            PCB_UNROLL
+            for (int n2 = 0; n2 < R2; ++n2) v[n2] = sm[(c * N + k1 * R2 + n2) * 8 + i0l];
+            Dft<R2, -1>::run(v);
+            if (DIEL == 1) {
+                const double s = op.ediag[c];
+                PCB_UNROLL
+                for (int k2 = 0; k2 < R2; ++k2) {
+                    const unsigned m = msk[P::lout(k1, k2) * 8 + i0l];
+                    if ((m >> c) & 1u) v[k2] = cscale(v[k2], s);
+                }
+            }
+            Dft<R2, +1>::run(v);
+            PCB_UNROLL
+            for (int n2 = 0; n2 < R2; ++n2) {
+                cplx val = v[n2];
+                if (!P::PFA && k1 > 0) { const cplx t = __ldg(tw + k1 * R2 + n2); val = cmul(val, cmake(t.x, -t.y)); }
+                sm[(c * N + k1 * R2 + n2) * 8 + i0l] = val;
+            }
+        }
+    }
+    __syncthreads();
+    for (int item = tid; item < 3 * R2 * 8; item += NT) {
+        const int i0l = item % 8, n2 = (item / 8) % R2, c = item / (8 * R2);
+        const int i0 = t0 * 8 + i0l;
+        if (i0 >= N) continue;
+        cplx v[R1];
+        PCB_UNROLL
+        for (int k1 = 0; k1 < R1; ++k1) v[k1] = sm[(c * N + k1 * R2 + n2) * 8 + i0l];
+        Dft<R1, +1>::run(v);
+        cplx* __restrict__ base = Y + c * nn + (long long)i1 * N + i0;
+        PCB_UNROLL
+        for (int n1 = 0; n1 < R1; ++n1) base[P::lin(n1, n2) * sline] = v[n1];
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Launch table: one entry per supported grid size, filled by the per-size translation units.
+// ---------------------------------------------------------------------------------------
+struct PcbOpLaunch {
+    int N;
+    int r1, r2;
+    // mode: 0 plain 3-D FFT forward, 1 plain inverse (1/N^3), 2 A = AMA^H, 3 H = AMA^H + gamma B^H B + shift
+    int (*apply)(const PcbOp& op, const PcbCols& cols, int ncols, int mode, const cplx* tw, cudaStream_t s);
+    // split passes used by the cross-DoF dielectric and by the tests: pass ids below
+    int (*pass)(const PcbOp& op, const PcbCols& cols, int ncols, int pass_id, const cplx* tw, cudaStream_t s);
+};
+enum { PCB_PASS_XFWD_SYM = 0, PCB_PASS_XFWD = 1, PCB_PASS_YFWD = 2, PCB_PASS_ZFWD = 3, PCB_PASS_ZINV = 4,
+       PCB_PASS_YINV = 5, PCB_PASS_XINV = 6, PCB_PASS_XINV_A = 7, PCB_PASS_XINV_H = 8, PCB_PASS_ZMID = 9 };
+
+const PcbOpLaunch* pcb_find_plan(int N);

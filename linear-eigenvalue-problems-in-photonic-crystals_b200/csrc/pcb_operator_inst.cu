@@ -1,0 +1,83 @@
+// pcb200 -- per-grid-size instantiation of the operator passes.
+// Compiled once per supported N with -DPCB_N=.. -DPCB_R1=.. -DPCB_R2=.. (see build.py), so the
+// sizes build in parallel and each object only carries the codelets it needs.
+#include "pcb_operator.cuh"
+
+#ifndef PCB_N
+#error "compile with -DPCB_N -DPCB_R1 -DPCB_R2"
+#endif
+
+namespace {
+
+typedef Plan<PCB_N, PCB_R1, PCB_R2> P;
+constexpr int NT = 128;
+constexpr int kRowBytes = 3 * P::R1 * P::R2P * (int)sizeof(cplx);
+constexpr int LX = (8 * kRowBytes <= 65536) ? 8 : (4 * kRowBytes <= 65536) ? 4 : (2 * kRowBytes <= 65536) ? 2 : 1;
+constexpr int kSmemX = LX * kRowBytes;
+constexpr int kSmemL = 3 * P::N * 8 * (int)sizeof(cplx);
+constexpr int kSmemZ = kSmemL + P::N * 8;
+
+template <class K>
+int set_smem(K kern, int bytes) {
+    if (bytes > 48 * 1024) PCB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    return 0;
+}
+
+#define PCB_GO(KERN, GRIDX, SMEM)                                                   \
+    do {                                                                            \
+        auto kfn = KERN;                                                            \
+        if (set_smem(kfn, (SMEM))) return -1;                                       \
+        dim3 grid((unsigned)(GRIDX), (unsigned)ncols, 1);                           \
+        PCB_LAUNCH(kfn, grid, dim3(NT, 1, 1), (size_t)(SMEM), s, op, cols, tw);      \
+        PCB_CUDA_OK(cudaGetLastError());                                            \
+    } while (0)
+
+constexpr int GX = (P::N * P::N + LX - 1) / LX;          // x tiles per column
+constexpr int GL = ((P::N + 7) / 8) * P::N;              // strided-line tiles per column
+
+int run_pass(const PcbOp& op, const PcbCols& cols, int ncols, int pass_id, const cplx* tw, cudaStream_t s) {
+    switch (pass_id) {
+        case PCB_PASS_XFWD_SYM: PCB_GO((k_xfwd<P, LX, NT, 1>), GX, kSmemX); break;
+        case PCB_PASS_XFWD:     PCB_GO((k_xfwd<P, LX, NT, 0>), GX, kSmemX); break;
+        case PCB_PASS_YFWD:     PCB_GO((k_line<P, 1, -1, NT>), GL, kSmemL); break;
+        case PCB_PASS_ZFWD:     PCB_GO((k_line<P, 2, -1, NT>), GL, kSmemL); break;
+        case PCB_PASS_ZINV:     PCB_GO((k_line<P, 2, +1, NT>), GL, kSmemL); break;
+        case PCB_PASS_YINV:     PCB_GO((k_line<P, 1, +1, NT>), GL, kSmemL); break;
+        case PCB_PASS_XINV:     PCB_GO((k_xinv<P, LX, NT, 0>), GX, kSmemX); break;
+        case PCB_PASS_XINV_A:   PCB_GO((k_xinv<P, LX, NT, 1>), GX, kSmemX); break;
+        case PCB_PASS_XINV_H:   PCB_GO((k_xinv<P, LX, NT, 2>), GX, kSmemX); break;
+        case PCB_PASS_ZMID:
+            if (op.diel == PCB_DIEL_NONE) PCB_GO((k_zmid<P, 0, NT>), GL, kSmemZ);
+            else if (op.diel == PCB_DIEL_CHIRAL) PCB_GO((k_zmid<P, 1, NT>), GL, kSmemZ);
+            else if (op.diel == PCB_DIEL_TRIVIAL) PCB_GO((k_zmid<P, 2, NT>), GL, kSmemZ);
+            else { pcb_set_error("zmid: dielectric type %d has no fused z pass", op.diel); return -1; }
+            break;
+        default: pcb_set_error("unknown pass id %d", pass_id); return -1;
+    }
+    return 0;
+}
+
+int run_apply(const PcbOp& op, const PcbCols& cols, int ncols, int mode, const cplx* tw, cudaStream_t s) {
+    static const int fwd[] = {PCB_PASS_XFWD, PCB_PASS_YFWD, PCB_PASS_ZFWD};
+    static const int inv[] = {PCB_PASS_ZINV, PCB_PASS_YINV, PCB_PASS_XINV};
+    static const int opA[] = {PCB_PASS_XFWD_SYM, PCB_PASS_YFWD, PCB_PASS_ZMID, PCB_PASS_YINV, PCB_PASS_XINV_A};
+    static const int opH[] = {PCB_PASS_XFWD_SYM, PCB_PASS_YFWD, PCB_PASS_ZMID, PCB_PASS_YINV, PCB_PASS_XINV_H};
+    const int* seq;
+    int n;
+    switch (mode) {
+        case 0: seq = fwd; n = 3; break;
+        case 1: seq = inv; n = 3; break;
+        case 2: seq = opA; n = 5; break;
+        case 3: seq = opH; n = 5; break;
+        default: pcb_set_error("unknown apply mode %d", mode); return -1;
+    }
+    for (int i = 0; i < n; ++i)
+        if (run_pass(op, cols, ncols, seq[i], tw, s)) return -1;
+    return 0;
+}
+
+}  // namespace
+
+#define PCB_CAT2(a, b) a##b
+#define PCB_CAT(a, b) PCB_CAT2(a, b)
+extern const PcbOpLaunch PCB_CAT(pcb_plan_, PCB_N) = {PCB_N, PCB_R1, PCB_R2, run_apply, run_pass};

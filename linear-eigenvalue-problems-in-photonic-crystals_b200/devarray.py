@@ -1,0 +1,225 @@
+"""Device context and the column-planar device block (the stand-in for ``cupy.ndarray`` on this path).
+
+A ``DeviceBlock`` is the reference's ``(3 n^3, k)`` complex128 array (lobpcg.py:365) kept on the
+GPU as k independent planar columns ("Data layout in HBM").  Column slicing
+``blk[:, a:b]`` / ``blk[:, [j0, j1]]`` yields views (pointer lists, no copies) -- this is what
+turns the reference's soft-locking compaction (lobpcg.py:431-436) into index bookkeeping.
+The reference's row-major layout exists only at ``from_host`` / ``get``.
+"""
+import ctypes as C
+import os
+import weakref
+
+import numpy as np
+
+from . import _lib as L
+
+_contexts = {}
+_default_device = None
+
+
+def set_device(device):
+    """Select the CUDA device used by contexts created afterwards (one process per GPU)."""
+    global _default_device
+    _default_device = int(device)
+
+
+def default_device():
+    if _default_device is not None:
+        return _default_device
+    return int(os.environ.get("PCB200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+
+
+class Context:
+    """One GPU + one grid size N (pcb_ctx)."""
+
+    def __init__(self, N, device=None):
+        self.N = int(N)
+        self.nn = self.N ** 3
+        self.R = 3 * self.nn
+        self.device = default_device() if device is None else int(device)
+        h = C.c_void_p()
+        L.check(L.lib().pcb_ctx_create(self.device, self.N, C.byref(h)), "pcb_ctx_create")
+        self.h = h
+        self._lib = L.lib()
+        self._fin = weakref.finalize(self, self._lib.pcb_ctx_destroy, h)
+
+    # -- plumbing ---------------------------------------------------------------------
+    def sync(self):
+        L.check(self._lib.pcb_sync(self.h), "pcb_sync")
+
+    def launches(self):
+        n = C.c_longlong()
+        L.check(self._lib.pcb_launch_count(self.h, C.byref(n)), "pcb_launch_count")
+        return n.value
+
+    def mem_info(self):
+        f, t = C.c_size_t(), C.c_size_t()
+        L.check(self._lib.pcb_mem_info(self.h, C.byref(f), C.byref(t)), "pcb_mem_info")
+        return f.value, t.value
+
+    def timer_start(self):
+        L.check(self._lib.pcb_timer_start(self.h), "pcb_timer_start")
+
+    def timer_stop(self):
+        ms = C.c_float()
+        L.check(self._lib.pcb_timer_stop(self.h, C.byref(ms)), "pcb_timer_stop")
+        return ms.value
+
+    def malloc(self, nbytes):
+        p = C.c_void_p()
+        L.check(self._lib.pcb_malloc(self.h, nbytes, C.byref(p)), f"pcb_malloc({nbytes})")
+        return p.value
+
+    def free(self, ptr):
+        L.check(self._lib.pcb_free(self.h, ptr), "pcb_free")
+
+    # -- blocks -------------------------------------------------------------------------
+    def empty(self, k):
+        return DeviceBlock(self, int(k))
+
+    def from_host(self, x):
+        return DeviceBlock.from_host(self, x)
+
+    def random_block(self, k, seed):
+        """x0 = rand + 1j*rand on the device (numerical_experiments.py:66)."""
+        b = DeviceBlock(self, int(k))
+        L.check(self._lib.pcb_fill_uniform(self.h, b.k, L.ptr_array(b.ptrs), int(seed)), "pcb_fill_uniform")
+        return b
+
+
+def get_context(N, device=None):
+    """Cached context for (device, N)."""
+    dev = default_device() if device is None else int(device)
+    key = (L.lib_path(), dev, int(N))
+    if key not in _contexts:
+        _contexts[key] = Context(N, dev)
+    return _contexts[key]
+
+
+def drop_contexts():
+    _contexts.clear()
+
+
+class _Allocation:
+    """Owner of one cudaMalloc; freed when the last view dies."""
+
+    def __init__(self, ctx, nbytes):
+        self.ctx = ctx
+        self.ptr = ctx.malloc(nbytes)
+        self._fin = weakref.finalize(self, _free, ctx, self.ptr)
+
+
+def _free(ctx, ptr):
+    try:
+        ctx.free(ptr)
+    except Exception:
+        pass
+
+
+class DeviceBlock:
+    """k planar columns of 3 N^3 complex128 on the GPU; behaves like an (R, k) array for the
+    operations the hot path uses (shape, column slicing, get/set, copy)."""
+
+    __array_priority__ = 1000
+
+    def __init__(self, ctx, k=None, _owners=None, _ptrs=None, vec=False):
+        self.ctx = ctx
+        self.vec = vec          # True: presents itself as a 1-D vector of length R
+        if _ptrs is None:
+            a = _Allocation(ctx, 16 * ctx.R * max(k, 1))
+            self._owners = (a,)
+            self.ptrs = [a.ptr + 16 * ctx.R * j for j in range(k)]
+        else:
+            self._owners = _owners
+            self.ptrs = list(_ptrs)
+
+    # -- array-like surface ---------------------------------------------------------------
+    @property
+    def k(self):
+        return len(self.ptrs)
+
+    @property
+    def shape(self):
+        return (self.ctx.R,) if self.vec else (self.ctx.R, self.k)
+
+    @property
+    def ndim(self):
+        return 1 if self.vec else 2
+
+    dtype = np.dtype(np.complex128)
+
+    def cols(self, idx):
+        """View of the listed columns."""
+        return DeviceBlock(self.ctx, _owners=self._owners, _ptrs=[self.ptrs[int(j)] for j in idx])
+
+    def __getitem__(self, key):
+        if isinstance(key, tuple) and len(key) == 2 and key[0] == slice(None):
+            c = key[1]
+            if isinstance(c, slice):
+                return self.cols(range(*c.indices(self.k)))
+            if isinstance(c, (int, np.integer)):
+                v = self.cols([c])
+                v.vec = True
+                return v
+            return self.cols(list(c))
+        raise IndexError("DeviceBlock supports column selection only: blk[:, a:b], blk[:, j], blk[:, [..]]")
+
+    def __setitem__(self, key, value):
+        dst = self[key]
+        if isinstance(value, DeviceBlock):
+            dst.assign(value)
+        else:
+            dst.set(np.asarray(value))
+
+    def assign(self, src):
+        """Column-wise device copy src -> self."""
+        if src.k != self.k:
+            raise ValueError(f"column count mismatch {src.k} vs {self.k}")
+        lib = L.lib()
+        for d, s in zip(self.ptrs, src.ptrs):
+            if d != s:
+                L.check(lib.pcb_memcpy_d2d(self.ctx.h, d, s, 16 * self.ctx.R), "pcb_memcpy_d2d")
+
+    def copy(self):
+        out = DeviceBlock(self.ctx, self.k, vec=self.vec)
+        out.assign(self)
+        return out
+
+    def set(self, host):
+        host = np.ascontiguousarray(host, dtype=np.complex128)
+        if host.ndim == 1:
+            host = host.reshape(-1, 1)
+        if host.shape != (self.ctx.R, self.k):
+            raise ValueError(f"host block has shape {host.shape}, expected {(self.ctx.R, self.k)}")
+        L.check(L.lib().pcb_block_upload(self.ctx.h, host.ctypes.data, host.shape[1], self.k, L.ptr_array(self.ptrs)),
+                "pcb_block_upload")
+
+    def get(self, out=None):
+        """Row-major (R, k) NumPy copy (``cupy.ndarray.get``)."""
+        if out is None:
+            out = np.empty((self.ctx.R, self.k), dtype=np.complex128)
+        L.check(L.lib().pcb_block_download(self.ctx.h, out.ctypes.data, out.shape[1], self.k, L.ptr_array(self.ptrs)),
+                "pcb_block_download")
+        return out.reshape(-1) if self.vec else out
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.get()
+        return a if dtype is None else a.astype(dtype)
+
+    @staticmethod
+    def from_host(ctx, x):
+        x = np.asarray(x)
+        vec = x.ndim == 1
+        b = DeviceBlock(ctx, 1 if vec else x.shape[1], vec=vec)
+        b.set(x)
+        return b
+
+
+def as_block(ctx, x):
+    """Device view of x: DeviceBlock stays, NumPy arrays are uploaded.  Returns (block, was_host)."""
+    if isinstance(x, DeviceBlock):
+        if x.ctx is not ctx:
+            raise ValueError("block belongs to another context (grid size / device)")
+        return x, False
+    return DeviceBlock.from_host(ctx, x), True

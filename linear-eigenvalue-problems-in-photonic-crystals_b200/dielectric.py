@@ -1,0 +1,191 @@
+"""Lattice geometry on the host: k-path data, DoF meshes and the index sets of Omega_1.
+
+Mirrors the public surface of paper_2/dielectric.py (diel_info :20-35, diel_alpha :37-49,
+diel_io_index :58-97, mesh3d_*_dofs :104-130, FLAG_* :157-261).  Runs once per lattice in NumPy
+(host set-up, < 1 s at N = 120 once cached); the GPU only ever sees the resulting
+int64 index lists, which the C ABI packs into a per-cell bit mask.  The ``.bin`` wire format
+(raw little-endian int64) and directory layout are the reference's.
+"""
+import os
+import time
+
+import numpy as np
+from numpy import pi
+
+from .environment import (CHIRAL_EPS_EG, DIEL_LIB, DIEL_PATH, GAP, GREEN, PSEUDOCHIRAL_EPS_LOC, RED, RESET, say)
+
+
+def diel_info(d_flag, option=None):
+    """Coordinate transform `ct`, symmetry points `sym`, or both (dielectric.py:20-35)."""
+    name = d_flag.split("_")[0]
+    ct = np.array(DIEL_LIB["CT_" + name])
+    sym = np.array(DIEL_LIB["sym_" + name])
+    if option == "ct":
+        return ct
+    if option == "sym":
+        return sym
+    return ct, sym
+
+
+def diel_alpha(d_flag, no, gap=GAP):
+    """Translation vector number `no` of the path (dielectric.py:37-49)."""
+    sym = np.array(DIEL_LIB["sym_" + d_flag.split("_")[0]])
+    seg, pos = divmod(no, gap)
+    if pos == 0:
+        return sym[seg, :]
+    return (pos * sym[seg + 1, :] + (gap - pos) * sym[seg, :]) / gap
+
+
+def kpath(d_flag, gap=GAP):
+    """All translation vectors of the band path, in the order of bandgap()
+    (numerical_experiments.py:342-346): `gap` points per segment, end point included."""
+    sym = diel_info(d_flag, "sym").astype(float)
+    nseg = sym.shape[0] - 1
+    alphas = np.zeros((nseg * gap, 3))
+    for s in range(nseg):
+        alphas[(s + 1) * gap - 1, :] = sym[s + 1, :]
+        for j in range(gap - 1):
+            alphas[s * gap + j, :] = ((j + 1) * sym[s + 1, :] + (gap - j - 1) * sym[s, :]) / gap
+    return alphas
+
+
+def diel_chiral_const(d_flag="sc_curv"):
+    return CHIRAL_EPS_EG[d_flag]
+
+
+def diel_pseudochiral_const(no=0):
+    return PSEUDOCHIRAL_EPS_LOC[no]
+
+
+# ---------------------------------------------------------------------------------------------
+# DoF meshes (dielectric.py:104-130): row r = c*N^3 + i0 + N*i1 + N^2*i2
+# ---------------------------------------------------------------------------------------------
+def _grid(N):
+    ax = np.arange(N)
+    return np.tile(ax, N * N), np.tile(np.repeat(ax, N), N), np.repeat(ax, N * N)
+
+
+def mesh3d_edge_dofs(N):
+    """(3 N^3, 3) coordinates of the edge DoFs: component c sits half a cell along axis c."""
+    i0, i1, i2 = _grid(N)
+    blocks = []
+    for c in range(3):
+        cols = [i0 / N, i1 / N, i2 / N]
+        cols[c] = ((i0, i1, i2)[c] + 0.5) / N
+        blocks.append(np.column_stack(cols))
+    return np.vstack(blocks)
+
+
+def mesh3d_volume_dofs(N):
+    """(N^3, 3) coordinates of the cell centres."""
+    i0, i1, i2 = _grid(N)
+    return np.column_stack(((i0 + 0.5) / N, (i1 + 0.5) / N, (i2 + 0.5) / N))
+
+
+# ---------------------------------------------------------------------------------------------
+# Flag functions (dielectric.py:157-261): indices of the points inside the dielectric
+# ---------------------------------------------------------------------------------------------
+def FLAG_sc_flat1(coo):
+    x, y, z = coo[:, 0], coo[:, 1], coo[:, 2]
+    q = 0.25
+    return np.where((x <= q) & (y <= q) | (x <= q) & (z <= q) | (y <= q) & (z <= q))[0]
+
+
+def FLAG_sc_flat2(coo):
+    x, y, z = coo[:, 0], coo[:, 1], coo[:, 2]
+    return np.where((x <= 0.25) & (y <= 0.25)
+                    | (x <= 0.25) & (z >= 0.25) & (z <= 0.5)
+                    | (y >= 0.5) & (y <= 0.75) & (z >= 0.5) & (z <= 0.75)
+                    | (x >= 0.5) & (x <= 0.75) & (z >= 0.75))[0]
+
+
+def FLAG_sc_curv(coo_in):
+    """Sphere of radius 0.345 joined by three axis-parallel rods of radius 0.11 (cell centre)."""
+    rod, ball = 0.11, 0.345
+    p = coo_in - 0.5
+    xx, yy, zz = p[:, 0] ** 2, p[:, 1] ** 2, p[:, 2] ** 2
+    return np.where((xx + yy + zz <= ball ** 2) | (xx + yy <= rod ** 2) | (xx + zz <= rod ** 2) | (yy + zz <= rod ** 2))[0]
+
+
+def FLAG_bcc_gyroid(coo, double_flag=False):
+    r = coo.T
+    g = np.sin(2 * pi * r[0]) * np.cos(2 * pi * r[1]) + np.sin(2 * pi * r[1]) * np.cos(2 * pi * r[2]) + \
+        np.sin(2 * pi * r[2]) * np.cos(2 * pi * r[0])
+    return np.where((np.abs(g) if double_flag else g) > 1.1)[0]
+
+
+def FLAG_bcc_sg(coo):
+    return FLAG_bcc_gyroid(coo, double_flag=False)
+
+
+def FLAG_bcc_dg(coo):
+    return FLAG_bcc_gyroid(coo, double_flag=True)
+
+
+def FLAG_fcc(coo_in, chunk=1 << 18):
+    """Diamond network: 18 spheres (r = 0.12) at the lattice sites plus 16 prolate spheroids
+    (semi-minor axis 0.11) along the four bonds leaving each of the four basis sites."""
+    r_sph, b_ell = 0.12, 0.11
+    pts = np.array(coo_in, dtype=float)
+    if pts.ndim == 1:
+        pts = pts.reshape(3, 1)
+    elif pts.shape[0] != 3:
+        pts = pts.T
+    basis = np.array([[0, 0, 0.5, 0.5], [0, 0.5, 0, 0.5], [0, 0.5, 0.5, 0]], dtype=float)
+    quarter = np.ones(3) * 0.25
+    sites = np.hstack((np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1], [0, 1, 1], [1, 0, 1], [1, 1, 0],
+                                 [1, 1, 1], [0, 0.5, 0.5], [0.5, 0, 0.5], [0.5, 0.5, 0], [1, 0.5, 0.5],
+                                 [0.5, 1, 0.5], [0.5, 0.5, 1]], dtype=float).T, quarter[:, None] + basis))
+    bonds = []
+    for i in range(4):
+        mid = (basis[:, i] + quarter) / 2
+        half = (basis[:, i] - quarter) / 2
+        length = np.linalg.norm(half)
+        bonds.append((mid, length, half / length))
+    inside = np.zeros(pts.shape[1], dtype=bool)
+    for s in range(0, pts.shape[1], chunk):
+        x = pts[:, s:s + chunk]
+        hit = np.any(np.sum((x[:, :, None] - sites[:, None, :]) ** 2, axis=0) < r_sph * r_sph, axis=1)
+        for mid, length, direction in bonds:
+            X = x[:, None, :] - (mid[:, None] + basis)[:, :, None]
+            major = np.hypot(b_ell, length)
+            along = np.tensordot(direction, X, axes=([0], [0])) ** 2
+            across = np.sum(X ** 2, axis=0) - along
+            hit |= np.any((along / major ** 2) + (across / b_ell ** 2) < 1, axis=0)
+        inside[s:s + chunk] = hit
+    return np.where(inside)[0]
+
+
+_FLAGS = {"sc_flat1": FLAG_sc_flat1, "sc_flat2": FLAG_sc_flat2, "sc_curv": FLAG_sc_curv,
+          "bcc_sg": FLAG_bcc_sg, "bcc_dg": FLAG_bcc_dg, "fcc": FLAG_fcc}
+
+
+def compute_index(N, d_flag, dofs="edge"):
+    """Index set of Omega_1 computed from the geometry (the compute branch of diel_io_index)."""
+    ct = diel_info(d_flag, option="ct")
+    mesh = mesh3d_edge_dofs(N) if dofs == "edge" else mesh3d_volume_dofs(N)
+    return np.asarray(_FLAGS[d_flag](mesh @ np.linalg.inv(ct.T)), dtype=np.int64)
+
+
+def diel_io_index(N, d_flag, dofs="edge", gpu=True, cache=True):
+    """Indices of the dielectric edge / volume DoFs (dielectric.py:58-97).
+
+    Loads ``DIEL_PATH/<dofs>_dofs/<d_flag>_<N>.bin`` (raw int64) when present, otherwise computes
+    the set from the geometry and -- like the reference -- stores it there if the directory exists.
+    Always returns a host int64 array (`gpu` is accepted for signature compatibility: the device
+    representation is a bit mask owned by the dielectric handle)."""
+    if d_flag is None:
+        rng = np.random.default_rng()
+        return rng.integers(0, 3 * N ** 3 - 1, size=int(0.372 * 3 * N ** 3)).astype(np.int64)
+    t0 = time.time()
+    path = os.path.join(DIEL_PATH, dofs + "_dofs", f"{d_flag}_{N}.bin")
+    if os.path.exists(path):
+        ind = np.fromfile(path, dtype=np.int64)
+        say(f"{GREEN}Index file already exists.{RESET}")
+    else:
+        ind = compute_index(N, d_flag, dofs)
+        if cache and os.path.isdir(os.path.dirname(path)):
+            say(f"{RED}New lattice type {d_flag} or size {N} isn't computed.{RESET}")
+            ind.tofile(path)
+    say(f"Dielectric {dofs} indices for {d_flag} with N = {N} loaded, {time.time() - t0:<6.3f}s elapsed.")
+    return ind

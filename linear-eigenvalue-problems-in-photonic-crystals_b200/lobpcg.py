@@ -1,0 +1,173 @@
+"""Soft-locking LOBPCG on the GPU (public surface of paper_2/lobpcg.py for the default solver).
+
+``lobpcg_sep_softlock`` keeps the reference's signature, return convention and failure behaviour
+(lobpcg.py:325-492) and reproduces its iteration exactly -- including the initial-lambda quirk
+(:379-381), the iteration-0 search space without P, the absolute residual test and the ascending
+soft-lock order -- but every O(R) step is one fused kernel of libpcb200.so:
+
+    residual + column norms + preconditioner      pcb_residual   (lobpcg.py:394-397,442)
+    soft-lock "compaction"                         pointer lists  (lobpcg.py:431-436: no data moves)
+    H on the active block                          pcb_apply      (lobpcg.py:443)
+    Gram pair S^H S, S^H HS                        pcb_gram2      (orthogonalization.py:143-144)
+    P <- [W P] E, X <- X E + P (and HS)            pcb_update     (lobpcg.py:1248-1270)
+
+Host Python owns the control flow and the n_loc x n_loc Rayleigh-Ritz (LAPACK via NumPy).
+"""
+import time
+
+import numpy as np
+
+from . import _lib as L
+from . import devarray
+from .devarray import DeviceBlock
+from .environment import GREEN, MAXITER, RED, RESET, TOL, YELLOW, say
+from .orthogonalization import gram_pair, hermitize, rr_small
+from .pcfft import Operator, OperatorCallable
+
+
+def _fused_operator(h_func_in, p_func, shift):
+    """The Operator when (h_func, p_func) are the callables of pc_mfd_handle for one operator."""
+    if (shift == 0.0 and isinstance(h_func_in, OperatorCallable) and isinstance(p_func, OperatorCallable)
+            and h_func_in.op is p_func.op and h_func_in.mode == L.APPLY_H and p_func.mode == L.APPLY_P):
+        return h_func_in.op
+    return None
+
+
+def _call_into(func, src, dst):
+    """dst <- func(src) for a generic callable over DeviceBlocks."""
+    out = func(src)
+    if not isinstance(out, DeviceBlock):
+        out = DeviceBlock.from_host(src.ctx, out)
+    dst.assign(out)
+
+
+def _context_of(h_func_in, x0):
+    if isinstance(x0, DeviceBlock):
+        return x0.ctx
+    if isinstance(h_func_in, OperatorCallable):
+        return h_func_in.op.ctx
+    n = round((x0.shape[0] // 3) ** (1 / 3))
+    return devarray.get_context(n)
+
+
+def lobpcg_sep_softlock(h_func_in, p_func, x0, nev, shift=0.0, tol=TOL, maxiter=MAXITER, history=False,
+                        longortho=False, singleprecision=False, maxstagniter=50, trace=None):
+    """LOBPCG with soft locking; [X, W, P] and their images live in two 3m-column device blocks.
+
+    Returns ``(lambdas[:m] - shift, x, info)`` with ``x`` a DeviceBlock (R x m), ``info = [iterations,
+    seconds]`` (+ residual history when ``history``); ``(None, None, None)`` on NaN / Cholesky failure /
+    blow-up, exactly like the reference.  ``trace`` (list) receives per-iteration dicts for tests."""
+    if longortho or singleprecision:
+        raise NotImplementedError("longortho / singleprecision variants are outside the ported hot path "
+                                  "(SURVEY.md 2.2: not used by any default runner)")
+    t_h = time.time()
+    ctx = _context_of(h_func_in, x0)
+    m = x0.shape[1]
+    op = _fused_operator(h_func_in, p_func, shift)
+    if shift == 0.0:
+        h_func = h_func_in
+    else:
+        def h_func(x):
+            y = h_func_in(x)
+            L.check(L.lib().pcb_axpby(ctx.h, x.k, L.ptr_array(x.ptrs), L.ptr_array(y.ptrs), float(shift), 1.0), "pcb_axpby")
+            return y
+    res_op = op if op is not None else _residual_helper(ctx)
+
+    S, HS = ctx.empty(3 * m), ctx.empty(3 * m)
+    X, W, P = S[:, :m], S[:, m:2 * m], S[:, 2 * m:]
+    HX, HW, HP = HS[:, :m], HS[:, m:2 * m], HS[:, 2 * m:]
+    if isinstance(x0, DeviceBlock):
+        X.assign(x0)
+    else:
+        X.set(np.asarray(x0))
+
+    if op is not None:
+        op.apply_into(L.APPLY_H, X, HX)
+    else:
+        _call_into(h_func, X, HX)
+    # Initial lambda (lobpcg.py:379-381): the m x m Gram matrices are themselves fed to RR.
+    ss, shs = gram_pair(X, HX)
+    try:
+        lambdas, _ = rr_small(hermitize(ss.conj().T @ ss), hermitize(ss.conj().T @ shs))
+    except np.linalg.LinAlgError:
+        return None, None, None
+    res_his = np.empty(maxiter)
+    ctx.sync()
+    say(f"Time for LOBPCG initialization: {time.time() - t_h:<6.2f}s.")
+
+    t_tot_h = time.time()
+    iter_ = 0
+    for iter_ in range(maxiter):
+        t_iter_h = time.time()
+        # residual (+ preconditioner on the fused path), norms, active set
+        res_nrms = res_op.residual(X, HX, W, lambdas[:m], precond=op is not None)
+        res_his[iter_] = np.linalg.norm(res_nrms[:nev])
+        ind_act = np.where(res_nrms > tol)[0]
+        n_act = len(ind_act)
+        if trace is not None:
+            trace.append({"res": res_nrms.copy(), "n_act": n_act, "lambdas": np.array(lambdas[:m])})
+        say(f"Iter = {iter_:<4d}, res_nrm = {np.linalg.norm(res_nrms):<6.2e}, n_act = {n_act:<3d}.", end=" ")
+        if np.isnan(res_nrms).any():
+            say(f"{RED}Nan occurs in residuals.{RESET}")
+            return None, None, None
+        if (iter_ > maxstagniter and (res_nrms[0] > 1000 or res_nrms[0] > res_his[1])) or \
+                (iter_ > 2 * maxstagniter and res_nrms[0] > 50):
+            if np.linalg.norm(res_nrms[:nev]) < res_his[maxstagniter // 2] * 0.1:
+                say(f"{YELLOW}Stagnation warning.{RESET}")
+            else:
+                say(f"{YELLOW}Stagnation detected, probably blowup but no nan occurs.{RESET}")
+                return None, None, None
+        if max(res_nrms[:nev]) < tol:
+            say(f"{GREEN}convergence reached.{RESET}")
+            break
+        n_loc = m + 2 * n_act if iter_ > 0 else m + n_act
+
+        # soft locking = column views of the active W / P / HP (no copies)
+        W_act, HW_act = W.cols(ind_act), HW.cols(ind_act)
+        if op is not None:
+            op.apply_into(L.APPLY_H, W_act, HW_act)          # W already holds K_P^-1 r
+        else:
+            _call_into(p_func, W_act, W_act)
+            _call_into(h_func, W_act, HW_act)
+        if iter_ > 0:
+            s_loc = DeviceBlock(ctx, _owners=S._owners, _ptrs=X.ptrs + W_act.ptrs + P.cols(ind_act).ptrs)
+            hs_loc = DeviceBlock(ctx, _owners=HS._owners, _ptrs=HX.ptrs + HW_act.ptrs + HP.cols(ind_act).ptrs)
+        else:
+            s_loc = DeviceBlock(ctx, _owners=S._owners, _ptrs=X.ptrs + W_act.ptrs)
+            hs_loc = DeviceBlock(ctx, _owners=HS._owners, _ptrs=HX.ptrs + HW_act.ptrs)
+
+        try:
+            ss, shs = gram_pair(s_loc, hs_loc)
+            lambdas, eigvec = rr_small(ss, shs)
+        except np.linalg.LinAlgError:
+            return None, None, None
+        if np.isnan(lambdas).any() or np.isnan(eigvec).any():
+            say(f"{RED}Nan occurs after Rayleigh-Ritz procedure.{RESET}")
+            return None, None, None
+        lambdas, eigvec = lambdas[:m], np.ascontiguousarray(eigvec[:, :m])
+
+        # _sep_update_after_rr (lobpcg.py:1248-1270) in one pass
+        L.check(L.lib().pcb_update(ctx.h, m, n_loc, L.ptr_array(s_loc.ptrs), L.ptr_array(hs_loc.ptrs),
+                                   L.ptr_array(P.ptrs), L.ptr_array(HP.ptrs), eigvec.ctypes.data), "pcb_update")
+        say(f"Runtime = {time.time() - t_iter_h:<6.4f}s.")
+
+    ctx.sync()
+    t_tot = time.time() - t_tot_h
+    say(f"\nA complete procedure of lobpcg is done, {t_tot:<6.2f}s elapsed.")
+    info = np.array([iter_, t_tot])
+    if history:
+        info = np.append(info, res_his[1:iter_])
+    x = X.copy()      # detach the result from the 3m-column work block
+    return lambdas[:m] - shift, x, info
+
+
+_helpers = {}
+
+
+def _residual_helper(ctx):
+    """An identity-symbol Operator: gives the generic (non-fused) path access to pcb_residual."""
+    key = id(ctx)
+    if key not in _helpers:
+        from .discretization import FourierSymbols
+        _helpers[key] = Operator(FourierSymbols(ctx.N, 1, np.eye(3)), 0.0, 0.0, 0.0, None, device=ctx.device)
+    return _helpers[key]

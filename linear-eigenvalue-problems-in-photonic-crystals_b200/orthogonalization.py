@@ -1,0 +1,70 @@
+"""Rayleigh-Ritz with Cholesky whitening (public surface of paper_2/orthogonalization.py used by the
+default solver: hermitize :26-33, rayleigh_ritz_chol_sep :140-154, short_qr :36-46).
+
+The two tall-skinny Gram products -- the only O(R) part -- run in one fused pass on the GPU
+(pcb_gram2: S and HS are read once, Hermitian half only).  The remaining n_loc x n_loc dense algebra
+(n_loc <= 96) is the library call the north star leaves on the host: LAPACK potrf / trtri / zheevd
+through NumPy."""
+import time
+
+import numpy as np
+
+from . import _lib as L
+from .devarray import DeviceBlock
+
+
+def hermitize(M):
+    """(M + M^H)/2 (orthogonalization.py:26-33)."""
+    return (M + M.T.conj()) / 2
+
+
+def gram_pair(s, hs):
+    """(hermitize(S^H S), hermitize(S^H HS)) for DeviceBlocks, as host arrays."""
+    n = s.k
+    G = np.empty((n, n), dtype=np.complex128)
+    T = np.empty((n, n), dtype=np.complex128)
+    L.check(L.lib().pcb_gram2(s.ctx.h, n, L.ptr_array(s.ptrs), L.ptr_array(hs.ptrs), G.ctypes.data, T.ctypes.data), "pcb_gram2")
+    return G, T
+
+
+def rr_small(ss, shs):
+    """L = inv(chol(G)); eigh(L T L^H); E = L^H V (orthogonalization.py:148-151) on the small matrices."""
+    Lm = np.linalg.inv(np.linalg.cholesky(ss))
+    t = (Lm @ shs) @ Lm.conj().T
+    lam, v = np.linalg.eigh(t)
+    return lam, Lm.conj().T @ v
+
+
+def rayleigh_ritz_chol_sep(s, hs):
+    """(lambda ascending, eigvec, seconds)  (orthogonalization.py:140-154).
+
+    `s`, `hs`: DeviceBlocks (R x n_loc) -> fused device Gram pair; or small host matrices (the
+    reference feeds the m x m Gram matrices themselves to RR for its initial lambda, lobpcg.py:379-381)."""
+    t0 = time.time()
+    if isinstance(s, DeviceBlock):
+        ss, shs = gram_pair(s, hs)
+    else:
+        s, hs = np.asarray(s), np.asarray(hs)
+        ss, shs = hermitize(s.conj().T @ s), hermitize(s.conj().T @ hs)
+    lam, vec = rr_small(ss, shs)
+    return lam, vec, time.time() - t0
+
+
+def short_qr(x):
+    """CholQR: x inv(chol(herm(x^H x)))^H (orthogonalization.py:36-46) on a DeviceBlock, in place."""
+    G, _ = gram_pair(x, x)
+    Linv = np.linalg.inv(np.linalg.cholesky(G))
+    E = np.ascontiguousarray(Linv.conj().T)
+    return block_times_small(x, E)
+
+
+def block_times_small(x, E):
+    """x <- x @ E for a DeviceBlock x (R x m) and host E (m x m), via the fused update kernel with an empty P part."""
+    m = x.k
+    tmp = DeviceBlock(x.ctx, m)
+    hx_dummy = DeviceBlock(x.ctx, m)
+    hx_dummy.assign(x)
+    E = np.ascontiguousarray(E, dtype=np.complex128)
+    L.check(L.lib().pcb_update(x.ctx.h, m, m, L.ptr_array(x.ptrs), L.ptr_array(hx_dummy.ptrs), L.ptr_array(tmp.ptrs),
+                               L.ptr_array(DeviceBlock(x.ctx, m).ptrs), E.ctypes.data), "pcb_update")
+    return x

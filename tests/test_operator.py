@@ -1,0 +1,52 @@
+"""Operator parity: CUDA path (through the C ABI) vs the golden outputs of the unmodified reference
+and vs the oracle on seeded inputs."""
+import numpy as np
+import pytest
+
+from conftest import relerr
+
+TOL = 1e-12   # relative, complex128: FFT + symbol rounding differences only
+
+
+def _setup(pcb, oracle, case):
+    N, d_flag, alpha, typ = case["N"], case["d_flag"], np.array(case["alpha"]), case["type"]
+    ne, mfd = pcb.numerical_experiments, pcb.discretization
+    relax, pnt = mfd.set_relaxation(alpha)
+    ct = pcb.dielectric.diel_info(d_flag, option="ct")
+    a_fft, b_fft = mfd.fft_blocks(N, 1, ct, alpha=alpha)
+    inv_fft = mfd.inverse_3_times_3_B(b_fft, pnt, relax[0])
+    b_fft = (pnt * b_fft[0], pnt * b_fft[1])
+    Diels = None if typ is None else getattr(mfd, typ + "_handle")(N, d_flag, eps_opt=case["eps_opt"])
+    A, H, P = ne.pc_mfd_handle(a_fft, b_fft, Diels, inv_fft, relax[0])
+    x = oracle.random_x0(3 * N ** 3, case["m"], case["seed"])
+    return A, H, P, Diels, x
+
+
+def test_operator_vs_reference_golden(pcb, oracle, golden):
+    z, man = golden
+    for case in man["operator"]:
+        if pcb.backend_name == "emu" and case["N"] > 8:
+            continue
+        A, H, P, Diels, x = _setup(pcb, oracle, case)
+        key = case["key"]
+        assert relerr(H(x), z[key + "_H"]) < TOL, key
+        assert relerr(A(x), z[key + "_A"]) < TOL, key
+        assert relerr(P(x), z[key + "_P"]) < TOL, key
+        if Diels is not None:
+            assert relerr(Diels(x), z[key + "_M"]) < TOL, key
+
+
+def test_symbols_vs_reference_golden(pcb, golden):
+    z, man = golden
+    mfd = pcb.discretization
+    for case in man["symbols"]:
+        N, alpha = case["N"], np.array(case["alpha"])
+        ct = pcb.dielectric.diel_info(case["d_flag"], option="ct")
+        relax, pnt = mfd.set_relaxation(alpha)
+        assert relax[0] == pytest.approx(case["shift"], rel=0, abs=0)
+        assert pnt == pytest.approx(case["gamma"], rel=1e-15)
+        a_fft, b_fft = mfd.fft_blocks(N, 1, ct, alpha=alpha)
+        k = case["key"]
+        assert relerr(a_fft.toarray(), z[k + "_a"]) < 1e-14
+        b0, b1 = mfd.PenaltySymbols(a_fft, pnt).toarray()
+        assert relerr(b0, z[k + "_b0"]) < 1e-14 and relerr(b1, z[k + "_b1"]) < 1e-14
