@@ -1,0 +1,331 @@
+#!/usr/bin/env python3
+"""Benchmark of the hot path (BASELINE.json metric: op-applies/s and seconds-to-10-bands per k-point at N=120).
+
+    python bench.py [--gpus N --steps K --warmup W]                 # this repo's CUDA path
+    python bench.py --impl reference [--gpus N --steps K --warmup W] # the reference algorithm on the host CPU
+
+One STEP = one block application of H = A M A^H + gamma B^H B + shift to m = 16 columns (16 op-applies) of the
+workload "fcc, isotropic eps=13, N=120" (BASELINE configs[1]) at one k-point of the FCC path; with N GPUs every
+rank works on its own k-point of the path (k-path sharding: no data-path collective -> "weak" scaling).
+Timed with CUDA events on the library's stream (pcb_timer_*), max over ranks, inputs resident in HBM
+(1.33 GB per block >> 126 MB L2, so every step streams from DRAM).  Extra legs, all reported in the single JSON line:
+  e2e         the same step through the reference-facing callable H_func(x) with HOST (pinned) buffers:
+              upload + apply + download inside the timed region
+  lobpcg      seconds to converge the lowest 10 bands (tol 1e-4) for the rank's k-points, warm-started like bandgap()
+  passes      device time of each of the five kernels of one block apply (pcb_apply_timed)
+  cpu_baseline the oracle's NumPy/pocketfft restatement of the same apply on the host cores (bounded sample)
+"""
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = "linear-eigenvalue-problems-in-photonic-crystals_b200"
+sys.path.insert(0, ROOT)
+os.environ.setdefault("PCB200_QUIET", "1")
+
+N_GRID, NEV, M_BLOCK, LATTICE, DTYPE_TYPE = 120, 10, 16, "fcc", "chiral"
+B_OP_PER_N3 = 336.0   # algorithmic bytes per op-apply / N^3 (DESIGN.md "Roofline")
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.proc, self.path = None, os.path.join("/tmp", f"pcb_clocks_{os.getpid()}.csv")
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(device), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            busy = sorted(sm)[len(sm) // 2:]          # upper half = samples under load
+            out.update(sm_mhz=statistics.median(busy), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        return out
+
+
+class Dist:
+    """torch.distributed plumbing for N > 1 (barrier + max-reduce of timings); nothing for N = 1."""
+
+    def __init__(self, n_gpus):
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        self.td = None
+        if self.world > 1:
+            import torch
+            import torch.distributed as td
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            use_nccl = torch.cuda.is_available()
+            if use_nccl:
+                torch.cuda.set_device(self.local)
+            td.init_process_group(backend="nccl" if use_nccl else "gloo")
+            self.td, self.torch = td, torch
+            self.dev = torch.device("cuda", self.local) if use_nccl else torch.device("cpu")
+
+    def barrier(self):
+        if self.td is not None:
+            self.td.barrier()
+
+    def max(self, v):
+        if self.td is None:
+            return float(v)
+        t = self.torch.tensor([float(v)], dtype=self.torch.float64, device=self.dev)
+        self.td.all_reduce(t, op=self.td.ReduceOp.MAX)
+        return float(t.item())
+
+    def gather(self, obj):
+        if self.td is None:
+            return [obj]
+        out = [None] * self.world if self.rank == 0 else None
+        self.td.gather_object(obj, out, dst=0)
+        return out
+
+    def close(self):
+        if self.td is not None:
+            self.td.destroy_process_group()
+
+
+def fcc_alpha(pcb, rank, world):
+    """k-point of this rank: first point of its contiguous chunk of the 120-point FCC path (numerical_experiments.kpath_chunks)."""
+    ne = pcb.numerical_experiments
+    alphas = pcb.dielectric.kpath(LATTICE)
+    chunk = ne.kpath_chunks(alphas.shape[0], world)[rank]
+    # rank 0's chunk starts at index 0 = first interior point of X-U; use the chunk's own k-points
+    return alphas, chunk
+
+
+def build_ops(pcb, n, alpha, Diels):
+    mfd, ne = pcb.discretization, pcb.numerical_experiments
+    relax, pnt = mfd.set_relaxation(alpha)
+    ct = pcb.dielectric.diel_info(LATTICE, option="ct")
+    a_fft, b_fft = mfd.fft_blocks(n, 1, ct, alpha=alpha)
+    inv_fft = mfd.inverse_3_times_3_B(b_fft, pnt, relax[0])
+    b_fft = (pnt * b_fft[0], pnt * b_fft[1])
+    return ne.pc_mfd_handle(a_fft, b_fft, Diels, inv_fft, relax[0]), relax[0]
+
+
+def cpu_apply_rate(n, alpha, cols, reps, warm, workers):
+    """Oracle port of AMA_BB (oracle/pc_oracle.py) on the host: op-applies/s on `cols` columns."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pc_oracle as oc
+    pcb = importlib.import_module(PKG)
+    oc.FFT_WORKERS = workers
+    a_fft, b_fft, inv_fft, shift, _ = oc.assemble_symbols(n, LATTICE, alpha)
+    ind_e = pcb.dielectric.compute_index(n, LATTICE, "edge")     # geometry only (chunked; same index set as the oracle's)
+    A, H, P = oc.pc_mfd_handle(a_fft, b_fft, oc.chiral_handle(n, LATTICE, ind_e=ind_e), inv_fft, shift)
+    x = oc.random_x0(3 * n ** 3, cols, 1)
+    for _ in range(warm):
+        H(x)
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        H(x)
+        times.append(time.perf_counter() - t0)
+    return cols / (sum(times) / len(times)), times
+
+
+def run_reference(args):
+    """--impl reference: the reference algorithm's CPU implementation (oracle port; the reference itself is Python+CuPy and
+    cannot be imported on the GPU box) on this arm's config, all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n = args.n
+    pcb = importlib.import_module(PKG)
+    alphas = pcb.dielectric.kpath(LATTICE)
+    alpha = alphas[0]
+    cols = 1
+    t0 = time.perf_counter()
+    rate, times = cpu_apply_rate(n, alpha, cols, args.steps, args.warmup, cores)
+    ms = 1e3 * sum(times) / len(times)
+    sample = f"{cols} column(s) of the {M_BLOCK}-column block per step (H apply, N={n}, scipy.fft workers={cores})"
+    line = {"impl": "reference", "metric": "op_applies_per_sec", "value": rate, "unit": "op-applies/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{LATTICE} {DTYPE_TYPE} eps=13 N={n} m={M_BLOCK} H block apply (configs[1])", "N": n,
+                       "lattice": LATTICE, "type": DTYPE_TYPE, "cols_per_step": cols},
+            "cpu_baseline": {"value": rate, "unit": "op-applies/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": "op-applies/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": time.perf_counter() - t0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="pcb200", choices=["pcb200", "reference"])
+    ap.add_argument("--n", type=int, default=N_GRID)
+    ap.add_argument("--kpoints", type=int, default=3, help="k-points per rank for the LOBPCG leg (0 = skip)")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    dist = Dist(args.gpus)
+    pcb = importlib.import_module(PKG)
+    pcb.set_device(dist.local)
+    if pcb.backend() != "cuda-sm_100a":
+        raise SystemExit("bench.py requires the CUDA build of libpcb200.so")
+    n, m = args.n, M_BLOCK
+    ne, mfd = pcb.numerical_experiments, pcb.discretization
+    ctx = pcb.get_context(n)
+    alphas, chunk = fcc_alpha(pcb, dist.rank, dist.world)
+    Diels = mfd.chiral_handle(n, LATTICE)
+    (A, H, P), shift = build_ops(pcb, n, alphas[chunk[0]], Diels)
+    op = H.op
+    X, Y = ctx.random_block(m, 1234 + dist.rank), ctx.empty(m)
+    ctx.sync()
+
+    # ---- device-resident block applies ---------------------------------------------------------------------
+    sampler = ClockSampler(dist.local) if dist.rank == 0 else None
+    for _ in range(args.warmup):
+        op.apply_into(pcb._lib.APPLY_H, X, Y)
+    ctx.sync()
+    dist.barrier()
+    l0 = ctx.launches()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        op.apply_into(pcb._lib.APPLY_H, X, Y)
+    ms_total = ctx.timer_stop()
+    launches = ctx.launches() - l0
+    dist.barrier()
+    ms_total = dist.max(ms_total)
+    clocks = sampler.stop() if sampler else None
+    ms_step = ms_total / args.steps
+    value = dist.world * m * args.steps / (ms_total * 1e-3)
+
+    # ---- per-pass device times -------------------------------------------------------------------------------
+    import ctypes as C
+    pass_ms = np.zeros(5)
+    reps = 5
+    buf, npass = (C.c_float * 8)(), C.c_int()
+    for _ in range(reps):
+        pcb._lib.check(pcb._lib.lib().pcb_apply_timed(op.h, pcb._lib.APPLY_H, m, pcb._lib.ptr_array(X.ptrs),
+                                                      pcb._lib.ptr_array(Y.ptrs), buf, C.byref(npass)), "pcb_apply_timed")
+        pass_ms += np.array(buf[:5])
+    pass_ms /= reps
+    col_bytes = 48.0 * n ** 3            # one column, one direction
+    pass_bytes = np.array([2, 2, 2, 2, 3]) * col_bytes * m
+    names = ["x_fwd+KAh", "y_fwd", "z_fwd+M+z_inv", "y_inv", "x_inv+KA+gKB+shift"]
+    passes = [{"name": nm, "ms": float(t), "GBps": float(b / (t * 1e-3) / 1e9)} for nm, t, b in zip(names, pass_ms, pass_bytes)]
+
+    peak, peak_src = measured_peak()
+    achieved = B_OP_PER_N3 * n ** 3 * m / (ms_step * 1e-3) / 1e9 * 1.0     # per rank: every rank runs the same step
+    roofline = {"bound": "hbm", "kernel": "op-apply = 5 fused FFT passes (k_xfwd, k_line, k_zmid, k_line, k_xinv)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": B_OP_PER_N3 * n ** 3 * m,
+                "moved_bytes_per_launch": float(pass_bytes.sum()), "moved_GBps": float(pass_bytes.sum() / (ms_step * 1e-3) / 1e9)}
+
+    # ---- end to end: host (pinned) buffers through the reference-facing callable ---------------------------------
+    xh, yh = pcb.pinned_empty((ctx.R, m)), pcb.pinned_empty((ctx.R, m))
+    X.get(out=xh)
+    for _ in range(2):
+        H(xh, out=yh)
+    ctx.sync()
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        H(xh, out=yh)
+    ctx.sync()
+    e2e_s = dist.max(time.perf_counter() - t0)
+    e2e = {"value": dist.world * m * args.e2e_steps / e2e_s, "unit": "op-applies/s", "h2d_bytes_per_step": int(xh.nbytes),
+           "d2h_bytes_per_step": int(yh.nbytes), "ms_per_step": 1e3 * e2e_s / args.e2e_steps, "steps": args.e2e_steps,
+           "api": "H_func(x_host, out=y_host) from numerical_experiments.pc_mfd_handle"}
+    pcb.devarray.pinned_free(xh)
+    pcb.devarray.pinned_free(yh)
+    del X, Y
+
+    # ---- LOBPCG: seconds to 10 bands for this rank's k-points (warm-started chain, as bandgap()) -----------------
+    lob = None
+    if args.kpoints > 0:
+        secs, iters, x = [], [], None
+        for j, idx in enumerate(chunk[:args.kpoints]):
+            (A, H, P), shift = build_ops(pcb, n, alphas[idx], Diels)
+            x0 = ctx.random_block(m, 1000 + idx) if x is None else x
+            lam, x, info = pcb.lobpcg.lobpcg_sep_softlock(H, P, x0, NEV, tol=1e-4)
+            if lam is None:
+                secs.append(float("nan")); iters.append(-1); x = None
+                continue
+            secs.append(float(info[1])); iters.append(int(info[0]))
+        allr = dist.gather({"rank": dist.rank, "k_indices": [int(i) for i in chunk[:args.kpoints]], "sec": secs, "iters": iters})
+        if dist.rank == 0:
+            flat_s = [s for r in allr for s in r["sec"]]
+            flat_i = [i for r in allr for i in r["iters"]]
+            lob = {"sec_to_10_bands_mean": float(np.mean(flat_s)), "sec_to_10_bands": flat_s, "iterations": flat_i,
+                   "ms_per_iteration": float(1e3 * np.sum(flat_s) / max(1, np.sum(flat_i))), "tol": 1e-4,
+                   "k_indices": [r["k_indices"] for r in allr], "first_of_chunk": "random start (seed 1000+idx), rest warm-started"}
+
+    # ---- CPU baseline (rank 0, N=1 only) --------------------------------------------------------------------------
+    cpu = None
+    if dist.rank == 0 and dist.world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        cols = 2
+        rate, times = cpu_apply_rate(n, alphas[chunk[0]], cols, 3, 1, cores)
+        cpu = {"value": rate, "unit": "op-applies/s", "cores": cores, "kind": "port",
+               "sample": f"{cols} of the {m} columns of one step, 3 timed reps after 1 warm-up (oracle AMA_BB, scipy.fft workers={cores})"}
+
+    if dist.rank == 0:
+        line = {"metric": "op_applies_per_sec", "value": value, "unit": "op-applies/s", "n_gpus": dist.world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"{LATTICE} {DTYPE_TYPE} eps=13 N={n} m={m} H block apply (configs[1]); one k-point of the FCC path per GPU",
+                           "N": n, "lattice": LATTICE, "type": DTYPE_TYPE, "cols_per_step": m, "l2": "inputs exceed L2 (1.33 GB per block)",
+                           "parallelism": f"k-path sharding x{dist.world}, no collective"},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                "passes": passes, "lobpcg": lob}
+        print(json.dumps(line), flush=True)
+    dist.close()
+
+
+if __name__ == "__main__":
+    main()

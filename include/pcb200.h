@@ -94,12 +94,19 @@ void pcb_op_destroy(pcb_op* op);
  * its last pass) and PCB_APPLY_M with the cross-DoF dielectric; distinct columns must not overlap. */
 int pcb_apply(pcb_op* op, int mode, int ncols, const void* const* in, void* const* out);
 
+/* Same as pcb_apply for PCB_APPLY_A / PCB_APPLY_H, with a CUDA event between the passes: pass_ms[i] = device time of
+ * pass i (x-forward+K_A^H, y-forward, z-forward+M+z-inverse, y-inverse, x-inverse+K_A+gamma K_B+shift), npass <- 5.
+ * Measurement aid for bench.py's per-pass roofline; not used by the solver. */
+int pcb_apply_timed(pcb_op* op, int mode, int ncols, const void* const* in, void* const* out, float* pass_ms, int* npass);
+
 /* LOBPCG block kernels
  * pcb_residual: r_j = lambda_j x_j - hx_j (lobpcg.py:394-395); norms2[j] = ||r_j||^2 (environment.norms :131-143);
  *   precond = 0: w_j = r_j;  1: w_j = K_P^-1 r_j (p_func fused, lobpcg.py:442).  norms2 is HOST memory. */
 int pcb_residual(pcb_op* op, int precond, int ncols, const void* const* x, const void* const* hx, void* const* w,
                  const double* lambda, double* norms2);
-/* G = S^H S, T = S^H HS, both hermitized (orthogonalization.py:26-33,143-144); n x n row-major complex128 on the HOST */
+/* G = S^H S, T = S^H HS, both hermitized (orthogonalization.py:26-33,143-144); n x n row-major complex128 on the HOST.
+ * Only one triangle (of 4x4 column blocks) is accumulated and completed by conjugation: HS must be H S with H Hermitian,
+ * so that S^H HS is Hermitian up to rounding -- which is the only way the solver uses it. */
 int pcb_gram2(pcb_ctx* ctx, int n, const void* const* s, const void* const* hs, void* G, void* T);
 /* _sep_update_after_rr (lobpcg.py:1248-1270): s/hs list the n_loc input columns [X(m) | W_act | P_act];
  * E is (n_loc x m) row-major complex128 on the host.  Pn = [W_act P_act] E[m:], X <- X E[:m] + Pn (in place), P <- Pn. */

@@ -435,6 +435,30 @@ int pcb_apply(pcb_op* o, int mode, int ncols, const void* const* in, void* const
     return 0;
 }
 
+int pcb_apply_timed(pcb_op* o, int mode, int ncols, const void* const* in, void* const* out, float* pass_ms, int* npass) {
+    PCB_CHECK_ARG(o && in && out && pass_ms && npass && ncols > 0 && ncols <= PCB_MAXC, "bad arguments (ncols <= 32)");
+    PCB_CHECK_ARG(mode == PCB_APPLY_A || mode == PCB_APPLY_H, "mode must be PCB_APPLY_A or PCB_APPLY_H");
+    PCB_CHECK_ARG(o->d.diel != PCB_DIEL_CROSSDOF, "not available for the cross-DoF dielectric");
+    pcb_ctx* c = o->ctx;
+    PCB_CUDA_OK(cudaSetDevice(c->device));
+    PcbCols cols;
+    for (int j = 0; j < ncols; ++j) { cols.in[j] = (const cplx*)in[j]; cols.out[j] = (cplx*)out[j]; }
+    const int seq[5] = {PCB_PASS_XFWD_SYM, PCB_PASS_YFWD, PCB_PASS_ZMID, PCB_PASS_YINV, mode == PCB_APPLY_A ? PCB_PASS_XINV_A : PCB_PASS_XINV_H};
+    cudaEvent_t ev[6];
+    for (int i = 0; i < 6; ++i) PCB_CUDA_OK(cudaEventCreate(&ev[i]));
+    PCB_CUDA_OK(cudaEventRecord(ev[0], c->stream));
+    for (int i = 0; i < 5; ++i) {
+        if (c->plan->pass(o->d, cols, ncols, seq[i], c->tw, c->stream)) return -1;
+        PCB_CUDA_OK(cudaEventRecord(ev[i + 1], c->stream));
+    }
+    c->launches += 5;
+    PCB_CUDA_OK(cudaEventSynchronize(ev[5]));
+    for (int i = 0; i < 5; ++i) PCB_CUDA_OK(cudaEventElapsedTime(&pass_ms[i], ev[i], ev[i + 1]));
+    for (int i = 0; i < 6; ++i) PCB_CUDA_OK(cudaEventDestroy(ev[i]));
+    *npass = 5;
+    return 0;
+}
+
 // ---- block kernels ----------------------------------------------------------------------------------------------
 int pcb_residual(pcb_op* o, int precond, int ncols, const void* const* x, const void* const* hx, void* const* w,
                  const double* lambda, double* norms2) {

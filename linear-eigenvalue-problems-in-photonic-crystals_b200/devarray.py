@@ -216,6 +216,28 @@ class DeviceBlock:
         return b
 
 
+_pinned = {}
+
+
+def pinned_empty(shape, dtype=np.complex128):
+    """NumPy array over page-locked host memory (pcb_host_alloc) for full-speed H2D/D2H.
+    The buffer lives until pinned_free(arr) or process exit."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    p = C.c_void_p()
+    L.check(L.lib().pcb_host_alloc(max(n, 1), C.byref(p)), "pcb_host_alloc")
+    buf = (C.c_char * n).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    _pinned[arr.ctypes.data] = (p.value, buf)
+    return arr
+
+
+def pinned_free(arr):
+    ent = _pinned.pop(arr.ctypes.data, None)
+    if ent is not None:
+        L.check(L.lib().pcb_host_free(ent[0]), "pcb_host_free")
+
+
 def as_block(ctx, x):
     """Device view of x: DeviceBlock stays, NumPy arrays are uploaded.  Returns (block, was_host)."""
     if isinstance(x, DeviceBlock):

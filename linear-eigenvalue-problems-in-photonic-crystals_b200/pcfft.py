@@ -62,12 +62,18 @@ class Operator:
         L.check(self._lib.pcb_apply(self.h, mode, src.k, L.ptr_array(src.ptrs), L.ptr_array(dst.ptrs)), "pcb_apply")
         return dst
 
-    def apply(self, mode, x):
-        """Functional form used by the drop-in callables: returns a new array of x's kind."""
+    def apply(self, mode, x, out=None):
+        """Functional form used by the drop-in callables: returns a new array of x's kind
+        (`out`: optional preallocated host array -- e.g. pinned -- receiving the result of a host-array call)."""
         blk, was_host = devarray.as_block(self.ctx, x)
-        out = DeviceBlock(self.ctx, blk.k, vec=blk.vec)
-        self.apply_into(mode, blk, out)
-        return out.get() if was_host else out
+        res = DeviceBlock(self.ctx, blk.k, vec=blk.vec)
+        self.apply_into(mode, blk, res)
+        if not was_host:
+            return res
+        if out is not None:
+            res.get(out=out.reshape(self.ctx.R, -1))
+            return out
+        return res.get()
 
     def residual(self, x, hx, w, lambdas, precond=True):
         """w_j = [K_P^-1] (lambda_j x_j - hx_j); returns ||lambda_j x_j - hx_j||_2 (lobpcg.py:394-397,442)."""
@@ -87,8 +93,8 @@ class OperatorCallable:
     def __init__(self, op, mode):
         self.op, self.mode = op, mode
 
-    def __call__(self, x):
-        return self.op.apply(self.mode, x)
+    def __call__(self, x, out=None):
+        return self.op.apply(self.mode, x, out=out)
 
 
 def _sym_consistency(a_fft, b_fft=None, inv_fft=None):

@@ -1,0 +1,110 @@
+"""LOBPCG block kernels through the C ABI vs NumPy: Gram pair, fused update, residual+preconditioner, column dots,
+layout round trip, device RNG."""
+import numpy as np
+import pytest
+
+from conftest import relerr
+
+
+def _blocks(pcb, N, k, seed):
+    ctx = pcb.get_context(N)
+    rng = np.random.default_rng(seed)
+    a = rng.standard_normal((ctx.R, k)) + 1j * rng.standard_normal((ctx.R, k))
+    return ctx, a, ctx.from_host(a)
+
+
+@pytest.mark.parametrize("N,n", [(6, 5), (8, 16), (8, 24), (6, 48), (6, 33)])
+def test_gram_pair(pcb, N, n):
+    ctx, s, S = _blocks(pcb, N, n, 1)
+    # HS = D S with a real diagonal D: like H S in LOBPCG, S^H HS is Hermitian (pcb_gram2 computes one triangle)
+    d = np.random.default_rng(2).standard_normal((ctx.R, 1))
+    hs = d * s
+    HS = ctx.from_host(hs)
+    G, T = pcb.orthogonalization.gram_pair(S, HS)
+    g = s.conj().T @ s
+    t = s.conj().T @ hs
+    assert relerr(G, (g + g.conj().T) / 2) < 1e-13
+    assert relerr(T, (t + t.conj().T) / 2) < 1e-13
+
+
+@pytest.mark.parametrize("N,m,n_act,first", [(6, 16, 16, False), (6, 16, 5, False), (8, 8, 3, False), (6, 16, 7, True), (6, 32, 20, False), (6, 20, 20, False)])
+def test_update(pcb, N, m, n_act, first):
+    """_sep_update_after_rr (lobpcg.py:1248-1270) incl. the soft-lock column views and in-place P."""
+    import ctypes as C
+    L = pcb._lib
+    ctx, s, S = _blocks(pcb, N, 3 * m, 3)
+    _, hs, HS = _blocks(pcb, N, 3 * m, 4)
+    rng = np.random.default_rng(5)
+    act = np.sort(rng.choice(m, n_act, replace=False))
+    n_loc = m + (1 if first else 2) * n_act
+    E = np.ascontiguousarray(rng.standard_normal((n_loc, m)) + 1j * rng.standard_normal((n_loc, m)))
+    X, W, P = S[:, :m], S[:, m:2 * m], S[:, 2 * m:]
+    HX, HW, HP = HS[:, :m], HS[:, m:2 * m], HS[:, 2 * m:]
+    sl = X.ptrs + W.cols(act).ptrs + ([] if first else P.cols(act).ptrs)
+    hl = HX.ptrs + HW.cols(act).ptrs + ([] if first else HP.cols(act).ptrs)
+    L.check(L.lib().pcb_update(ctx.h, m, n_loc, L.ptr_array(sl), L.ptr_array(hl), L.ptr_array(P.ptrs), L.ptr_array(HP.ptrs),
+                               E.ctypes.data), "pcb_update")
+    for a, A in ((s, S), (hs, HS)):
+        cols = [a[:, m + act]] + ([] if first else [a[:, 2 * m + act]])
+        pn = np.concatenate(cols, axis=1) @ E[m:]
+        xn = a[:, :m] @ E[:m] + pn
+        got = A.get()
+        assert relerr(got[:, :m], xn) < 1e-13
+        assert relerr(got[:, 2 * m:], pn) < 1e-13
+        assert np.array_equal(got[:, m:2 * m], a[:, m:2 * m])     # W untouched
+
+
+def test_residual_precond_and_dots(pcb, oracle):
+    N, k = 8, 11
+    alpha = np.array([0.3, 0.0, 0.1])
+    ne, mfd = pcb.numerical_experiments, pcb.discretization
+    relax, pnt = mfd.set_relaxation(alpha)
+    a_fft, b_fft = mfd.fft_blocks(N, 1, pcb.dielectric.diel_info("fcc", option="ct"), alpha=alpha)
+    inv_fft = mfd.inverse_3_times_3_B(b_fft, pnt, relax[0])
+    A, H, P = ne.pc_mfd_handle(a_fft, (pnt * b_fft[0], pnt * b_fft[1]), None, inv_fft, relax[0])
+    ctx, x, X = _blocks(pcb, N, k, 7)
+    _, hx, HX = _blocks(pcb, N, k, 8)
+    lam = np.linspace(0.5, 3.0, k)
+    Wd = ctx.empty(k)
+    nr = H.op.residual(X, HX, Wd, lam, precond=True)
+    r = x * lam - hx
+    assert np.allclose(nr, np.linalg.norm(r, axis=0), rtol=1e-13)
+    ao, bo, io, sh, _ = oracle.assemble_symbols(N, "fcc", alpha)
+    assert relerr(Wd.get(), oracle.h_block(r, io)) < 1e-12
+    nr2 = H.op.residual(X, HX, Wd, lam, precond=False)
+    assert relerr(Wd.get(), r) < 1e-15 and np.allclose(nr2, nr, rtol=1e-14)
+    d = pcb.pcfft.column_dots(X, HX)
+    assert relerr(d, np.einsum("ij,ij->j", x.conj(), hx)) < 1e-13
+    assert np.allclose(pcb.environment.norms(X), np.linalg.norm(x, axis=0), rtol=1e-13)
+
+
+def test_layout_roundtrip_views_and_rng(pcb):
+    ctx, a, A = _blocks(pcb, 6, 7, 9)
+    assert np.array_equal(A.get(), a)
+    assert np.array_equal(A[:, 2:5].get(), a[:, 2:5])
+    assert np.array_equal(A[:, [6, 0]].get(), a[:, [6, 0]])
+    assert np.array_equal(A[:, 3].get(), a[:, 3])
+    B = ctx.empty(7)
+    B[:, :] = A
+    B[:, 1:3] = a[:, 4:6]
+    want = a.copy(); want[:, 1:3] = a[:, 4:6]
+    assert np.array_equal(B.get(), want)
+    r1, r2, r3 = ctx.random_block(3, 42).get(), ctx.random_block(3, 42).get(), ctx.random_block(3, 43).get()
+    assert np.array_equal(r1, r2) and not np.array_equal(r1, r3)
+    assert 0 <= r1.real.min() and r1.real.max() < 1 and 0 <= r1.imag.min() and r1.imag.max() < 1
+    assert abs(r1.real.mean() - 0.5) < 0.05 and abs(np.corrcoef(r1.real[:, 0], r1.imag[:, 0])[0, 1]) < 0.1
+
+
+def test_fft_roundtrip_and_scipy(pcb):
+    import scipy.fft as sfft
+    for N in ([6, 8, 12, 16] if pcb.backend_name == "emu" else [6, 8, 12, 16, 24, 32, 48, 64, 72, 80, 96, 100]):
+        ctx, a, A = _blocks(pcb, N, 2, N)
+        F = pcb.pcfft.fftn3(A)
+        want = np.empty_like(a)
+        for j in range(2):
+            for c in range(3):
+                v = a[c * N ** 3:(c + 1) * N ** 3, j].reshape(N, N, N)          # [i2, i1, i0]
+                want[c * N ** 3:(c + 1) * N ** 3, j] = sfft.fftn(v).ravel()
+        assert relerr(F.get(), want) < 1e-13, N
+        back = pcb.pcfft.fftn3(F, inverse=True)
+        assert relerr(back.get(), a) < 1e-13, N
