@@ -52,7 +52,7 @@ class ClockSampler:
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(device), f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -199,7 +199,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="pcb200", choices=["pcb200", "reference"])
     ap.add_argument("--n", type=int, default=N_GRID)

@@ -15,6 +15,7 @@ import numpy as np
 from . import _lib as L
 
 _contexts = {}
+_immortal = []
 _default_device = None
 
 
@@ -42,6 +43,7 @@ class Context:
         L.check(L.lib().pcb_ctx_create(self.device, self.N, C.byref(h)), "pcb_ctx_create")
         self.h = h
         self._lib = L.lib()
+        _immortal.append(self)      # see drop_contexts(): destroyed at interpreter exit only
         self._fin = weakref.finalize(self, self._lib.pcb_ctx_destroy, h)
 
     # -- plumbing ---------------------------------------------------------------------
@@ -98,7 +100,11 @@ def get_context(N, device=None):
 
 
 def drop_contexts():
-    _contexts.clear()
+    """Synchronise every cached context.  Contexts are deliberately never destroyed before interpreter exit:
+    blocks, operators and dielectric handles point into them, and Python may finalise a garbage cycle in any
+    order (at exit, weakref.finalize runs in reverse creation order, i.e. contexts last)."""
+    for ctx in _contexts.values():
+        ctx.sync()
 
 
 class _Allocation:
