@@ -14,7 +14,7 @@ PICK = [
     ("chiral", "bandgap_sc_curv0.json", "sc_curv", "sc_curv", 0, [19, 59, 79]),
     ("chiral", "bandgap_bcc_single_gyroid0.json", "bcc_single_gyroid", "bcc_sg", 0, [59]),
     ("pseudochiral_trivial", "bandgap_sc_curv0.json", "sc_curv", "sc_curv", 0, [59]),
-    ("pseudochiral_crossdof", "bandgap_bcc_sg0.json", "bcc_sg", "bcc_sg", 0, [59]),
+    ("pseudochiral_crossdof", "bandgap_bcc_sg0.json", "bcc_single_gyroid", "bcc_sg", 0, [59]),
     ("pseudochiral_crossdof", "bandgap_fcc0.json", "fcc", "fcc", 0, [39]),
 ]
 out = []
