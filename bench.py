@@ -206,6 +206,7 @@ def main():
     ap.add_argument("--kpoints", type=int, default=3, help="k-points per rank for the LOBPCG leg (0 = skip)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-blocks", action="store_true", help="skip the LOBPCG block-kernel micro-timings")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -266,6 +267,36 @@ def main():
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": B_OP_PER_N3 * n ** 3 * m,
                 "moved_bytes_per_launch": float(pass_bytes.sum()), "moved_GBps": float(pass_bytes.sum() / (ms_step * 1e-3) / 1e9)}
 
+    # ---- LOBPCG block kernels on the same shapes (m = 16 active columns, n_loc = 48) --------------------------------
+    blocks = []
+    if not args.no_blocks:
+        L = pcb._lib
+        S, HS = ctx.random_block(3 * m, 77), ctx.random_block(3 * m, 78)
+        lam = np.linspace(1.0, 2.0, m)
+        Rb = 16.0 * ctx.R        # bytes of one column
+
+        def timed(fn, reps=10):
+            fn(); ctx.sync(); ctx.timer_start()
+            for _ in range(reps):
+                fn()
+            return ctx.timer_stop() / reps
+
+        t = timed(lambda: op.residual(S[:, :m], HS[:, :m], S[:, m:2 * m], lam, precond=True))
+        blocks.append({"name": "residual+norms+precond (m=16)", "ms": t, "GBps": 3 * m * Rb / t / 1e6})
+        G = np.empty((3 * m, 3 * m), dtype=np.complex128); T = np.empty_like(G)
+        t = timed(lambda: L.check(L.lib().pcb_gram2(ctx.h, 3 * m, L.ptr_array(S.ptrs), L.ptr_array(HS.ptrs), G.ctypes.data, T.ctypes.data), "gram2"))
+        nl = 3 * m
+        blocks.append({"name": "gram pair (n_loc=48)", "ms": t, "GBps": 2 * nl * Rb / t / 1e6,
+                       "GFLOPs": 8.0 * ctx.R * nl * (nl + 1) / t / 1e6})
+        E = np.ascontiguousarray(np.random.default_rng(0).standard_normal((nl, m)) + 0j) / nl
+        t = timed(lambda: L.check(L.lib().pcb_update(ctx.h, m, nl, L.ptr_array(S.ptrs), L.ptr_array(HS.ptrs), L.ptr_array(S[:, 2 * m:].ptrs),
+                                                     L.ptr_array(HS[:, 2 * m:].ptrs), E.ctypes.data), "update"))
+        blocks.append({"name": "fused update (m=16, n_loc=48)", "ms": t, "GBps": (2 * nl + 4 * m) * Rb / t / 1e6,
+                       "GFLOPs": 16.0 * ctx.R * m * nl / t / 1e6})
+        t = timed(lambda: op.apply_into(L.APPLY_H, S[:, :m], HS[:, :m]))
+        blocks.append({"name": "H apply (16 columns)", "ms": t, "GBps": B_OP_PER_N3 * n ** 3 * m / t / 1e6})
+        del S, HS
+
     # ---- end to end: host (pinned) buffers through the reference-facing callable ---------------------------------
     xh, yh = pcb.pinned_empty((ctx.R, m)), pcb.pinned_empty((ctx.R, m))
     X.get(out=xh)
@@ -322,7 +353,7 @@ def main():
                            "N": n, "lattice": LATTICE, "type": DTYPE_TYPE, "cols_per_step": m, "l2": "inputs exceed L2 (1.33 GB per block)",
                            "parallelism": f"k-path sharding x{dist.world}, no collective"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-                "passes": passes, "lobpcg": lob}
+                "passes": passes, "block_kernels": blocks, "lobpcg": lob}
         print(json.dumps(line), flush=True)
     dist.close()
 
