@@ -24,13 +24,13 @@ Diels = getattr(mfd, typ + "_handle")(N, "fcc")
 A, H, P = ne.pc_mfd_handle(a_fft, (pnt * b_fft[0], pnt * b_fft[1]), Diels, inv_fft, relax[0])
 ctx = pcb.get_context(N)
 X, Y = ctx.random_block(m, 1), ctx.empty(m)
-for _ in range(3):
+for _ in range(2):
     H.op.apply_into(L.APPLY_H, X, Y)
 ctx.sync()
 if blocks:
     S, HS = ctx.random_block(3 * m, 2), ctx.random_block(3 * m, 3)
     lam = np.linspace(1, 2, m)
-    for _ in range(2):
+    for _ in range(1):
         H.op.residual(S[:, :m], HS[:, :m], S[:, m:2 * m], lam, precond=True)
         pcb.orthogonalization.gram_pair(S, HS)
         E = np.ascontiguousarray(np.random.default_rng(0).standard_normal((3 * m, m)) + 0j) / (3 * m)
