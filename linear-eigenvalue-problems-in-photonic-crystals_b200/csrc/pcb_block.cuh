@@ -19,20 +19,6 @@ struct PcbColListW {
     cplx* p[PCB_MAXL];
 };
 
-// ---- cp.async (LDGSTS) helpers ------------------------------------------------------------------
-#ifdef PCB_EMU
-PCB_D void pcb_cp16(cplx* dst, const cplx* src) { *dst = *src; }
-PCB_D void pcb_cp_commit() {}
-template <int N> PCB_D void pcb_cp_wait() {}
-#else
-PCB_D void pcb_cp16(cplx* dst, const cplx* src) {
-    unsigned d = (unsigned)__cvta_generic_to_shared(dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src));
-}
-PCB_D void pcb_cp_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N> PCB_D void pcb_cp_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
-#endif
-
 PCB_D double pcb_warp_sum(double v) {
     PCB_UNROLL
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -189,12 +175,18 @@ __global__ void k_sum_partials(const double* __restrict__ partial, int nblocks, 
     out[j] = v;
 }
 
-// ---- Gram pair ----------------------------------------------------------------------------------
-// n = 4*nb columns (padded with zero columns).  Thread (ia <= ib, row-group g) owns the 4x4 block
-// { (ia + nb*j, ib + nb*j') } of both G and T; the strided column sets make the shared-memory reads
-// of a quarter warp contiguous.  Row tiles of TR rows are double-buffered with cp.async.
-#define PCB_GRAM_TR 32
-#define PCB_GRAM_NT 256
+// ---- Gram pair on the FP64 tensor pipe (DMMA m8n8k4) ------------------------------------------------------------
+// G = S^H S and T = S^H HS as REAL GEMMs over K = 2R (re/im interleaved, exactly the memory order of a complex column):
+//   Re G_ab = sum_k A[a][k] Bre[k][b],  A[a][2r] = Re s_ra, A[a][2r+1] = Im s_ra,  Bre = same layout for column b
+//   Im G_ab = sum_k A'[a][k] Bsw[k][b], A' = (Re s_ra, -Im s_ra),                   Bsw[2r] = Im s_rb, Bsw[2r+1] = Re s_rb
+// Columns are grouped in tiles of 8; only tile pairs (ta <= tb) are accumulated (Hermitian completion in k_gram_finish).
+// Each warp owns up to PCB_GM_PPW tile pairs x {Re G, Im G, Re T, Im T} = 4 DMMAs per pair and k4-step (two rows);
+// a fragment is ONE double per lane, so shared-memory traffic per flop is ~4x lower than with per-thread register tiles.
+// Row tiles of PCB_GM_TR rows are staged [column][row] (+2 rows pad: conflict-free LDS.64) with double-buffered cp.async.
+#define PCB_GM_TR 32
+#define PCB_GM_LD (PCB_GM_TR + 2)
+#define PCB_GM_PPW 4
+#define PCB_GM_MAXW 20
 
 PCB_HD void pcb_pair_from_index(int p, int nb, int& ia, int& ib) {   // row-major upper triangle incl. diagonal
     int a = 0, rem = p;
@@ -202,48 +194,50 @@ PCB_HD void pcb_pair_from_index(int p, int nb, int& ia, int& ib) {   // row-majo
     ia = a; ib = a + rem;
 }
 
-__global__ void __launch_bounds__(PCB_GRAM_NT) k_gram2(PcbColList S, PcbColList HS, int nb, long long R, int PP, int npairs,
-                                                        cplx* __restrict__ partial /* [gridDim.x][2][n*n] */) {
-    PCB_DYN_SMEM(cplx, sm);
-    const int n = 4 * nb, NP = n | 1;
-    const int tileElems = PCB_GRAM_TR * NP;             // one array, one stage
-    const int tid = threadIdx.x;
-    const int G = PCB_GRAM_NT / PP;
-    const int g = tid / PP;
-    const int pl = tid % PP;
-    const int p = blockIdx.y * PP + pl;
-    const bool active = (g < G) && (p < npairs);
-    int ia = 0, ib = 0;
-    if (active) pcb_pair_from_index(p, nb, ia, ib);
-
-    cplx accG[4][4], accT[4][4];
+__global__ void __launch_bounds__(32 * PCB_GM_MAXW, 1)
+k_gram2(PcbColList S, PcbColList HS, int n, int nt, long long R, cplx* __restrict__ partial /* [gridDim.x][2][nc*nc] */) {
+    PCB_DYN_SMEM(cplx, sm);                      // [2 stages][2: S, HS][nc][LD]
+    const int nc = 8 * nt;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int warp = tid >> 5, lane = tid & 31, W = nthr >> 5;
+    const int g = lane >> 2, tig = lane & 3;
+    const size_t matElems = (size_t)nc * PCB_GM_LD;
+    // tile pairs of this warp
+    const int npairs = nt * (nt + 1) / 2;
+    const int base = npairs / W, extra = npairs % W;
+    const int cnt = base + (warp < extra ? 1 : 0);
+    const int p0 = warp * base + (warp < extra ? warp : extra);
+    int ta[PCB_GM_PPW], tb[PCB_GM_PPW];
     PCB_UNROLL
-    for (int j = 0; j < 4; ++j) {
-        PCB_UNROLL
-        for (int l = 0; l < 4; ++l) { accG[j][l] = cmake(0.0, 0.0); accT[j][l] = cmake(0.0, 0.0); }
+    for (int i = 0; i < PCB_GM_PPW; ++i) {
+        ta[i] = tb[i] = 0;
+        if (i < cnt) pcb_pair_from_index(p0 + i, nt, ta[i], tb[i]);
     }
-
-    const long long ntiles = (R + PCB_GRAM_TR - 1) / PCB_GRAM_TR;
+    double acc[PCB_GM_PPW][4][2];
+    PCB_UNROLL
+    for (int i = 0; i < PCB_GM_PPW; ++i) {
+        PCB_UNROLL
+        for (int q = 0; q < 4; ++q) acc[i][q][0] = acc[i][q][1] = 0.0;
+    }
+    // zero the padding columns (never loaded) of both stages
+    for (int idx = tid; idx < 4 * (nc - n) * PCB_GM_LD; idx += nthr) {
+        const int buf = idx / ((nc - n) * PCB_GM_LD), rem = idx % ((nc - n) * PCB_GM_LD);
+        sm[(size_t)buf * matElems + (size_t)(n + rem / PCB_GM_LD) * PCB_GM_LD + rem % PCB_GM_LD] = cmake(0.0, 0.0);
+    }
+    const long long ntiles = (R + PCB_GM_TR - 1) / PCB_GM_TR;
     auto load_tile = [&](long long t, int stage) {
-        cplx* s0 = sm + (size_t)stage * 2 * tileElems;
-        cplx* h0 = s0 + tileElems;
-        const long long r0 = t * PCB_GRAM_TR;
-        for (int idx = tid; idx < n * PCB_GRAM_TR; idx += PCB_GRAM_NT) {
-            const int c = idx / PCB_GRAM_TR, rr = idx % PCB_GRAM_TR;
+        const long long r0 = t * PCB_GM_TR;
+        for (int idx = tid; idx < 2 * n * PCB_GM_TR; idx += nthr) {
+            const int which = idx / (n * PCB_GM_TR), rem = idx % (n * PCB_GM_TR);
+            const int c = rem / PCB_GM_TR, rr = rem % PCB_GM_TR;
             const long long r = r0 + rr;
-            const cplx* sp = S.p[c];
-            const cplx* hp = HS.p[c];
-            if (sp != nullptr && r < R) {
-                pcb_cp16(s0 + rr * NP + c, sp + r);
-                pcb_cp16(h0 + rr * NP + c, hp + r);
-            } else {
-                s0[rr * NP + c] = cmake(0.0, 0.0);
-                h0[rr * NP + c] = cmake(0.0, 0.0);
-            }
+            cplx* dst = sm + (size_t)(stage * 2 + which) * matElems + (size_t)c * PCB_GM_LD + rr;
+            const cplx* src = which ? HS.p[c] : S.p[c];
+            if (src != nullptr && r < R) pcb_cp16(dst, src + r);
+            else *dst = cmake(0.0, 0.0);
         }
         pcb_cp_commit();
     };
-
     long long t = blockIdx.x;
     int stage = 0;
     if (t < ntiles) load_tile(t, 0);
@@ -251,154 +245,155 @@ __global__ void __launch_bounds__(PCB_GRAM_NT) k_gram2(PcbColList S, PcbColList 
         const long long tn = t + gridDim.x;
         if (tn < ntiles) { load_tile(tn, stage ^ 1); pcb_cp_wait<1>(); } else { pcb_cp_wait<0>(); }
         __syncthreads();
-        if (active) {
-            const cplx* s0 = sm + (size_t)stage * 2 * tileElems;
-            const cplx* h0 = s0 + tileElems;
-            for (int rr = g; rr < PCB_GRAM_TR; rr += G) {
-                cplx a[4], b[4], hb[4];
-                PCB_UNROLL
-                for (int j = 0; j < 4; ++j) {
-                    a[j] = s0[rr * NP + ia + nb * j];
-                    b[j] = s0[rr * NP + ib + nb * j];
-                    hb[j] = h0[rr * NP + ib + nb * j];
-                }
-                PCB_UNROLL
-                for (int j = 0; j < 4; ++j) {
-                    PCB_UNROLL
-                    for (int l = 0; l < 4; ++l) {
-                        accG[j][l] = cfmac(a[j], b[l], accG[j][l]);
-                        accT[j][l] = cfmac(a[j], hb[l], accT[j][l]);
-                    }
+        const double* s0 = reinterpret_cast<const double*>(sm + (size_t)(stage * 2) * matElems);
+        const double* h0 = reinterpret_cast<const double*>(sm + (size_t)(stage * 2 + 1) * matElems);
+        PCB_UNROLL
+        for (int i = 0; i < PCB_GM_PPW; ++i) {
+            if (i < cnt) {
+                const double* pa = s0 + (size_t)(ta[i] * 8 + g) * (2 * PCB_GM_LD);
+                const double* pb = s0 + (size_t)(tb[i] * 8 + g) * (2 * PCB_GM_LD);
+                const double* ph = h0 + (size_t)(tb[i] * 8 + g) * (2 * PCB_GM_LD);
+                for (int step = 0; step < PCB_GM_TR / 2; ++step) {
+                    const int o = 4 * step + tig, os = 4 * step + (tig ^ 1);
+                    const double a = pa[o];
+                    const double a2 = (tig & 1) ? -a : a;
+                    pcb_dmma(acc[i][0][0], acc[i][0][1], a, pb[o]);
+                    pcb_dmma(acc[i][1][0], acc[i][1][1], a2, pb[os]);
+                    pcb_dmma(acc[i][2][0], acc[i][2][1], a, ph[o]);
+                    pcb_dmma(acc[i][3][0], acc[i][3][1], a2, ph[os]);
                 }
             }
         }
         __syncthreads();
         stage ^= 1;
     }
-    // reduce the row groups of this CTA through shared memory (fixed order), then write the partial block
-    cplx* red = sm;   // reuse: PP * 32 complex
-    for (int gg = 1; gg < G; ++gg) {
-        if (active && g == gg) {
+    cplx* out = partial + (size_t)blockIdx.x * 2 * nc * nc;
+    PCB_UNROLL
+    for (int i = 0; i < PCB_GM_PPW; ++i) {
+        if (i < cnt) {
+            const int ra = ta[i] * 8 + g;
             PCB_UNROLL
-            for (int j = 0; j < 4; ++j) {
-                PCB_UNROLL
-                for (int l = 0; l < 4; ++l) {
-                    red[(j * 4 + l) * PP + pl] = accG[j][l];
-                    red[(16 + j * 4 + l) * PP + pl] = accT[j][l];
-                }
-            }
-        }
-        __syncthreads();
-        if (active && g == 0) {
-            PCB_UNROLL
-            for (int j = 0; j < 4; ++j) {
-                PCB_UNROLL
-                for (int l = 0; l < 4; ++l) {
-                    accG[j][l] = cadd(accG[j][l], red[(j * 4 + l) * PP + pl]);
-                    accT[j][l] = cadd(accT[j][l], red[(16 + j * 4 + l) * PP + pl]);
-                }
-            }
-        }
-        __syncthreads();
-    }
-    if (active && g == 0) {
-        cplx* out = partial + (size_t)blockIdx.x * 2 * n * n;
-        PCB_UNROLL
-        for (int j = 0; j < 4; ++j) {
-            PCB_UNROLL
-            for (int l = 0; l < 4; ++l) {
-                const int ra = ia + nb * j, cb = ib + nb * l;
-                out[ra * n + cb] = accG[j][l];
-                out[n * n + ra * n + cb] = accT[j][l];
+            for (int j = 0; j < 2; ++j) {
+                const int cb = tb[i] * 8 + 2 * tig + j;
+                out[ra * nc + cb] = cmake(acc[i][0][j], acc[i][1][j]);
+                out[nc * nc + ra * nc + cb] = cmake(acc[i][2][j], acc[i][3][j]);
             }
         }
     }
 }
 
 // Sum the per-CTA partials in fixed order and complete the Hermitian matrices:
-// entry (a,b) was computed iff (a mod nb) <= (b mod nb); the others are conj of (b,a).
-__global__ void k_gram_finish(const cplx* __restrict__ partial, int nblocks, int nb, cplx* __restrict__ out /* [2][n*n] */) {
-    const int n = 4 * nb;
+// entry (a,b) was accumulated iff tile(a) <= tile(b); the others are conj of (b,a).
+__global__ void k_gram_finish(const cplx* __restrict__ partial, int nblocks, int nt, cplx* __restrict__ out /* [2][nc*nc] */) {
+    const int nc = 8 * nt;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= 2 * n * n) return;
-    const int which = e / (n * n), ab = e % (n * n);
-    const int a = ab / n, b = ab % n;
-    const bool direct = (a % nb) <= (b % nb);
-    const int src = direct ? a * n + b : b * n + a;
+    if (e >= 2 * nc * nc) return;
+    const int which = e / (nc * nc), ab = e % (nc * nc);
+    const int a = ab / nc, b = ab % nc;
+    const bool direct = (a / 8) <= (b / 8);
+    const int src = direct ? a * nc + b : b * nc + a;
     cplx v = cmake(0.0, 0.0);
-    for (int k = 0; k < nblocks; ++k) v = cadd(v, partial[(size_t)k * 2 * n * n + which * n * n + src]);
+    for (int k = 0; k < nblocks; ++k) v = cadd(v, partial[(size_t)k * 2 * nc * nc + which * nc * nc + src]);
     out[e] = direct ? v : cconj(v);
 }
 
-// ---- subspace update --------------------------------------------------------------------------
-// in[0..m) = X columns, in[m..nl) = active W then active P columns; E is (nl x mp) row-major, mp = 8*JB
-// (zero padded).  Pn_j = sum_{k>=m} s_k E_kj ;  X_j <- sum_{k<m} s_k E_kj + Pn_j ;  P_j <- Pn_j ; same for HS.
-#define PCB_UPD_NT 128
-template <int JB>   // JB = mp / 8 output groups; rows per tile = NT / JB
-__global__ void __launch_bounds__(PCB_UPD_NT) k_update(PcbColList Sin, PcbColList HSin, PcbColListW Xout, PcbColListW HXout,
-                                                        PcbColListW Pout, PcbColListW HPout, const cplx* __restrict__ E,
-                                                        int m, int nl, long long R) {
-    constexpr int TR = PCB_UPD_NT / JB;
-    constexpr int MP = 8 * JB;
+// ---- subspace update on the FP64 tensor pipe -----------------------------------------------------------------------
+// Y = S E as a real GEMM: per row r, A[r][2k] = Re s_rk, A[r][2k+1] = Im s_rk (memory order of a complex element),
+// B[2k][2j] = Re E_kj, B[2k][2j+1] = Im E_kj, B[2k+1][2j] = -Im E_kj, B[2k+1][2j+1] = Re E_kj; the C fragment of a lane is
+// (Re, Im) of one output element -> one 16-byte store.  Input columns: kx X-columns then kp active W/P-columns (both
+// padded to even with null = zero columns); E' is ((kx+kp) x MPp) complex, rows in the same order.  The accumulator first
+// runs over the W/P part (-> Pn, stored to P/HP), then continues over the X part (-> X E_x + Pn, stored in place).
+// A CTA stages TR rows of all input columns of S and HS ([column][row], cp.async double buffer); warp (rt, jp) owns the
+// 8-row tile rt and the output column tiles {2jp, 2jp+1} (4 complex columns each) of both S and HS.
+template <int TR>
+struct PcbUpd {
+    static constexpr int LD = TR + 4;      // complex; LD*16 mod 128 == 64: the two k-columns of an A fragment hit disjoint banks
+};
+
+template <int TR>
+__global__ void __launch_bounds__(512, 1)
+k_update(PcbColList Sin, PcbColList HSin, PcbColListW Xout, PcbColListW HXout, PcbColListW Pout, PcbColListW HPout,
+         const cplx* __restrict__ E, int m, int kx, int kp, int MPp, long long R) {
+    constexpr int LD = PcbUpd<TR>::LD;
     PCB_DYN_SMEM(cplx, sm);
-    cplx* sE = sm;                       // [nl][MP]
-    cplx* sS = sE + (size_t)nl * MP;     // [nl][TR]
-    cplx* sH = sS + (size_t)nl * TR;     // [nl][TR]
-    const int tid = threadIdx.x;
-    for (int i = tid; i < nl * MP; i += PCB_UPD_NT) sE[i] = E[i];
-    const int rr = tid % TR, jb = tid / TR;
+    const int nl = kx + kp;
+    cplx* sE = sm;                                   // [nl][MPp]
+    cplx* sT = sE + (size_t)nl * MPp;                // [2 stages][2: S, HS][nl][LD]
+    const size_t matElems = (size_t)nl * LD;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, tig = lane & 3;
+    constexpr int RT = TR / 8;
+    const int rt = warp % RT, jp = warp / RT;
+    for (int i = tid; i < nl * MPp; i += nthr) sE[i] = E[i];
     const long long ntiles = (R + TR - 1) / TR;
-    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    auto load_tile = [&](long long t, int stage) {
         const long long r0 = t * TR;
-        __syncthreads();   // previous tile fully consumed (and sE visible on the first trip)
-        for (int idx = tid; idx < nl * TR; idx += PCB_UPD_NT) {
-            const int k = idx / TR, q = idx % TR;
-            const long long r = r0 + q;
-            if (r < R) {
-                pcb_cp16(sS + k * TR + q, Sin.p[k] + r);
-                pcb_cp16(sH + k * TR + q, HSin.p[k] + r);
-            } else {
-                sS[k * TR + q] = cmake(0.0, 0.0);
-                sH[k * TR + q] = cmake(0.0, 0.0);
-            }
+        for (int idx = tid; idx < 2 * nl * TR; idx += nthr) {
+            const int which = idx / (nl * TR), rem = idx % (nl * TR);
+            const int c = rem / TR, rr = rem % TR;
+            const long long r = r0 + rr;
+            cplx* dst = sT + (size_t)(stage * 2 + which) * matElems + (size_t)c * LD + rr;
+            const cplx* src = which ? HSin.p[c] : Sin.p[c];
+            if (src != nullptr && r < R) pcb_cp16(dst, src + r);
+            else *dst = cmake(0.0, 0.0);
         }
         pcb_cp_commit();
-        pcb_cp_wait<0>();
+    };
+    // B-fragment addressing (constant per lane): element (k + (tig>>1), j + (g>>1)), component (g&1)^(tig&1), sign
+    const int bk = tig >> 1, bcomp = (g & 1) ^ (tig & 1);
+    const double bsign = ((tig & 1) && !(g & 1)) ? -1.0 : 1.0;
+    const double* sEd = reinterpret_cast<const double*>(sE);
+    long long t = blockIdx.x;
+    int stage = 0;
+    if (t < ntiles) load_tile(t, 0);
+    for (; t < ntiles; t += gridDim.x) {
+        const long long tn = t + gridDim.x;
+        if (tn < ntiles) { load_tile(tn, stage ^ 1); pcb_cp_wait<1>(); } else { pcb_cp_wait<0>(); }
         __syncthreads();
-        cplx xs[8], xh[8], ps[8], ph[8];
+        const double* s0 = reinterpret_cast<const double*>(sT + (size_t)(stage * 2) * matElems);
+        const double* h0 = reinterpret_cast<const double*>(sT + (size_t)(stage * 2 + 1) * matElems);
+        double acc[2][2][2];     // [S|HS][j-tile][c0,c1]
         PCB_UNROLL
-        for (int j = 0; j < 8; ++j) { xs[j] = xh[j] = ps[j] = ph[j] = cmake(0.0, 0.0); }
-        for (int k = 0; k < m; ++k) {
-            const cplx s = sS[k * TR + rr], h = sH[k * TR + rr];
+        for (int q = 0; q < 2; ++q) {
             PCB_UNROLL
-            for (int j = 0; j < 8; ++j) {
-                const cplx e = sE[k * MP + jb * 8 + j];
-                xs[j] = cfma(s, e, xs[j]);
-                xh[j] = cfma(h, e, xh[j]);
-            }
+            for (int j = 0; j < 2; ++j) acc[q][j][0] = acc[q][j][1] = 0.0;
         }
-        for (int k = m; k < nl; ++k) {
-            const cplx s = sS[k * TR + rr], h = sH[k * TR + rr];
-            PCB_UNROLL
-            for (int j = 0; j < 8; ++j) {
-                const cplx e = sE[k * MP + jb * 8 + j];
-                ps[j] = cfma(s, e, ps[j]);
-                ph[j] = cfma(h, e, ph[j]);
+        const long long r = t * TR + rt * 8 + g;
+        const int aoff = (rt * 8 + g) * 2 + (tig & 1);
+        PCB_UNROLL
+        for (int part = 0; part < 2; ++part) {
+            const int k0 = part == 0 ? kx : 0, k1 = part == 0 ? nl : kx;
+            for (int k = k0; k < k1; k += 2) {
+                const int ka = k + (tig >> 1);
+                const double as = s0[(size_t)ka * (2 * LD) + aoff];
+                const double ah = h0[(size_t)ka * (2 * LD) + aoff];
+                PCB_UNROLL
+                for (int j = 0; j < 2; ++j) {
+                    const int jc = (2 * jp + j) * 4 + (g >> 1);
+                    const double b = bsign * sEd[((size_t)(k + bk) * MPp + jc) * 2 + bcomp];
+                    pcb_dmma(acc[0][j][0], acc[0][j][1], as, b);
+                    pcb_dmma(acc[1][j][0], acc[1][j][1], ah, b);
+                }
             }
-        }
-        const long long r = r0 + rr;
-        if (r < R) {
-            PCB_UNROLL
-            for (int j = 0; j < 8; ++j) {
-                const int jj = jb * 8 + j;
-                if (jj < m) {
-                    Xout.p[jj][r] = cadd(xs[j], ps[j]);
-                    HXout.p[jj][r] = cadd(xh[j], ph[j]);
-                    Pout.p[jj][r] = ps[j];
-                    HPout.p[jj][r] = ph[j];
+            if (r < R) {
+                PCB_UNROLL
+                for (int j = 0; j < 2; ++j) {
+                    const int jj = (2 * jp + j) * 4 + tig;
+                    if (jj < m) {
+                        if (part == 0) {
+                            Pout.p[jj][r] = cmake(acc[0][j][0], acc[0][j][1]);
+                            HPout.p[jj][r] = cmake(acc[1][j][0], acc[1][j][1]);
+                        } else {
+                            Xout.p[jj][r] = cmake(acc[0][j][0], acc[0][j][1]);
+                            HXout.p[jj][r] = cmake(acc[1][j][0], acc[1][j][1]);
+                        }
+                    }
                 }
             }
         }
+        __syncthreads();
+        stage ^= 1;
     }
 }
 

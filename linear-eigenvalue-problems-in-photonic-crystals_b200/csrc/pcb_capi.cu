@@ -374,14 +374,14 @@ int pcb_apply(pcb_op* o, int mode, int ncols, const void* const* in, void* const
                 // plain transforms are in place on `out`; copy first when out of place
                 for (int j = 0; j < kc; ++j)
                     if (cols.in[j] != cols.out[j]) PCB_CUDA_OK(cudaMemcpyAsync(cols.out[j], cols.in[j], sizeof(cplx) * (size_t)c->R, cudaMemcpyDeviceToDevice, c->stream));
-                if (pl->apply(o->d, cols, kc, mode == PCB_APPLY_FFT ? 0 : 1, c->tw, c->stream)) return -1;
+                if (pl->apply(o->d, cols, kc, mode == PCB_APPLY_FFT ? 0 : 1, c->tw, c->stream, c->sms)) return -1;
                 c->launches += 3;
                 break;
             case PCB_APPLY_A: case PCB_APPLY_H: {
                 const int last = (mode == PCB_APPLY_A) ? PCB_PASS_XINV_A : PCB_PASS_XINV_H;
                 if (!cross) {
                     const int seq[5] = {PCB_PASS_XFWD_SYM, PCB_PASS_YFWD, PCB_PASS_ZMID, PCB_PASS_YINV, last};
-                    for (int i = 0; i < 5; ++i) if (pl->pass(o->d, cols, kc, seq[i], c->tw, c->stream)) return -1;
+                    for (int i = 0; i < 5; ++i) if (pl->pass(o->d, cols, kc, seq[i], c->tw, c->stream, c->sms)) return -1;
                     c->launches += 5;
                 } else {
                     // cross-DoF M is a stencil in real space: forward passes into scratch, M scratch -> out, inverse in place
@@ -389,10 +389,10 @@ int pcb_apply(pcb_op* o, int mode, int ncols, const void* const* in, void* const
                     PcbCols tmp = cols;
                     for (int j = 0; j < kc; ++j) tmp.out[j] = c->scratch + (size_t)j * c->R;
                     const int fwd[3] = {PCB_PASS_XFWD_SYM, PCB_PASS_YFWD, PCB_PASS_ZFWD};
-                    for (int i = 0; i < 3; ++i) if (pl->pass(o->d, tmp, kc, fwd[i], c->tw, c->stream)) return -1;
+                    for (int i = 0; i < 3; ++i) if (pl->pass(o->d, tmp, kc, fwd[i], c->tw, c->stream, c->sms)) return -1;
                     for (int j = 0; j < kc; ++j) if (launch_crossdof(o, tmp.out[j], cols.out[j])) return -1;
                     const int inv[3] = {PCB_PASS_ZINV, PCB_PASS_YINV, last};
-                    for (int i = 0; i < 3; ++i) if (pl->pass(o->d, cols, kc, inv[i], c->tw, c->stream)) return -1;
+                    for (int i = 0; i < 3; ++i) if (pl->pass(o->d, cols, kc, inv[i], c->tw, c->stream, c->sms)) return -1;
                     c->launches += 6;
                 }
             } break;
@@ -448,7 +448,7 @@ int pcb_apply_timed(pcb_op* o, int mode, int ncols, const void* const* in, void*
     for (int i = 0; i < 6; ++i) PCB_CUDA_OK(cudaEventCreate(&ev[i]));
     PCB_CUDA_OK(cudaEventRecord(ev[0], c->stream));
     for (int i = 0; i < 5; ++i) {
-        if (c->plan->pass(o->d, cols, ncols, seq[i], c->tw, c->stream)) return -1;
+        if (c->plan->pass(o->d, cols, ncols, seq[i], c->tw, c->stream, c->sms)) return -1;
         PCB_CUDA_OK(cudaEventRecord(ev[i + 1], c->stream));
     }
     c->launches += 5;
@@ -492,35 +492,31 @@ int pcb_residual(pcb_op* o, int precond, int ncols, const void* const* x, const 
 int pcb_gram2(pcb_ctx* c, int n, const void* const* s, const void* const* hs, void* G, void* T) {
     PCB_CHECK_ARG(c && s && hs && G && T && n > 0 && n <= PCB_MAXL, "bad arguments (n <= 96)");
     PCB_CUDA_OK(cudaSetDevice(c->device));
-    const int nb = (n + 3) / 4, np4 = 4 * nb;
+    const int nt = (n + 7) / 8, nc = 8 * nt;
     PcbColList S, HS;
-    // column a of the padded problem maps to input column: strided sets {ia + nb*j} -> keep natural order, pad with null
     for (int j = 0; j < PCB_MAXL; ++j) { S.p[j] = (j < n) ? (const cplx*)s[j] : nullptr; HS.p[j] = (j < n) ? (const cplx*)hs[j] : nullptr; }
-    const int npairs = nb * (nb + 1) / 2;
-    int PP = npairs < PCB_GRAM_NT ? npairs : PCB_GRAM_NT;
-    const int gy = (npairs + PP - 1) / PP;
-    const int NP = np4 | 1;
-    const size_t tile = (size_t)PCB_GRAM_TR * NP * sizeof(cplx);
-    size_t smem = 4 * tile;
-    const size_t red = (size_t)PP * 32 * sizeof(cplx);
-    if (smem < red) smem = red;
-    const long long ntiles = (c->R + PCB_GRAM_TR - 1) / PCB_GRAM_TR;
-    int per_sm = (int)((size_t)220 * 1024 / smem); if (per_sm < 1) per_sm = 1; if (per_sm > 4) per_sm = 4;
-    long long gx = (long long)c->sms * per_sm / gy; if (gx < 1) gx = 1; if (gx > ntiles) gx = ntiles;
-    const size_t pbytes = sizeof(cplx) * (size_t)gx * 2 * np4 * np4;
+    const int npairs = nt * (nt + 1) / 2;
+    int W = 4 * ((npairs + 4 * PCB_GM_PPW - 1) / (4 * PCB_GM_PPW));     // multiple of 4 warps, <= PPW tile pairs per warp
+    if (W > PCB_GM_MAXW) { pcb_set_error("pcb_gram2: n = %d needs %d warps", n, W); return -2; }
+    const size_t smem = sizeof(cplx) * 4 * (size_t)nc * PCB_GM_LD;
+    const long long ntiles = (c->R + PCB_GM_TR - 1) / PCB_GM_TR;
+    int per_sm = (int)((size_t)224 * 1024 / (smem + 1024)); if (per_sm < 1) per_sm = 1;
+    const int by_threads = 2048 / (32 * W); if (per_sm > by_threads) per_sm = by_threads;
+    if (per_sm > 4) per_sm = 4;
+    long long gx = (long long)c->sms * per_sm; if (gx > ntiles) gx = ntiles;
+    const size_t pbytes = sizeof(cplx) * (size_t)gx * 2 * nc * nc;
     if (ensure_partial(c, pbytes)) return -1;
     if (ensure_dsmall(c, sizeof(cplx) * 2 * PCB_MAXL * PCB_MAXL + 65536)) return -1;
     if (ensure_hstage(c, sizeof(cplx) * 2 * PCB_MAXL * PCB_MAXL + 65536)) return -1;
-    PCB_CUDA_OK(cudaMemsetAsync(c->partial, 0, pbytes, c->stream));
 #ifndef PCB_EMU
     if (smem > 48 * 1024) PCB_CUDA_OK(cudaFuncSetAttribute(k_gram2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 #endif
-    dim3 grid((unsigned)gx, (unsigned)gy, 1);
-    PCB_LAUNCH(k_gram2, grid, dim3(PCB_GRAM_NT, 1, 1), smem, c->stream, S, HS, nb, c->R, PP, npairs, (cplx*)c->partial);
+    dim3 grid((unsigned)gx, 1, 1);
+    PCB_LAUNCH(k_gram2, grid, dim3(32 * W, 1, 1), smem, c->stream, S, HS, n, nt, c->R, (cplx*)c->partial);
     PCB_CUDA_OK(cudaGetLastError());
     cplx* dout = (cplx*)c->dsmall;
-    const int ne = 2 * np4 * np4;
-    PCB_LAUNCH(k_gram_finish, dim3((unsigned)((ne + 127) / 128), 1, 1), dim3(128, 1, 1), 0, c->stream, (const cplx*)c->partial, (int)gx, nb, dout);
+    const int ne = 2 * nc * nc;
+    PCB_LAUNCH(k_gram_finish, dim3((unsigned)((ne + 127) / 128), 1, 1), dim3(128, 1, 1), 0, c->stream, (const cplx*)c->partial, (int)gx, nt, dout);
     PCB_CUDA_OK(cudaGetLastError());
     c->launches += 2;
     PCB_CUDA_OK(cudaMemcpyAsync(c->hstage, dout, sizeof(cplx) * ne, cudaMemcpyDeviceToHost, c->stream));
@@ -530,8 +526,8 @@ int pcb_gram2(pcb_ctx* c, int n, const void* const* s, const void* const* hs, vo
     // hermitize on the host (hermitize(), orthogonalization.py:26-33): (M + M^H)/2
     for (int a = 0; a < n; ++a)
         for (int b = 0; b < n; ++b) {
-            const cplx gab = h[a * np4 + b], gba = h[b * np4 + a];
-            const cplx tab = h[np4 * np4 + a * np4 + b], tba = h[np4 * np4 + b * np4 + a];
+            const cplx gab = h[a * nc + b], gba = h[b * nc + a];
+            const cplx tab = h[nc * nc + a * nc + b], tba = h[nc * nc + b * nc + a];
             g[a * n + b] = cmake(0.5 * (gab.x + gba.x), 0.5 * (gab.y - gba.y));
             t[a * n + b] = cmake(0.5 * (tab.x + tba.x), 0.5 * (tab.y - tba.y));
         }
@@ -541,41 +537,51 @@ int pcb_gram2(pcb_ctx* c, int n, const void* const* s, const void* const* hs, vo
 int pcb_update(pcb_ctx* c, int m, int nl, void* const* s, void* const* hs, void* const* p_out, void* const* hp_out, const void* E) {
     PCB_CHECK_ARG(c && s && hs && p_out && hp_out && E && m > 0 && nl >= m && nl <= PCB_MAXL && m <= 32, "bad arguments");
     PCB_CUDA_OK(cudaSetDevice(c->device));
-    const int JB = (m + 7) / 8;
-    PCB_CHECK_ARG(JB == 1 || JB == 2 || JB == 3 || JB == 4, "m <= 32");
+    const int MP = 8 * ((m + 7) / 8), MPp = MP + 2, JT = MP / 4;       // output columns padded to 8; E' row stride (conflict-free)
+    const int kx = (m + 1) & ~1, kp = (nl - m + 1) & ~1, nlp = kx + kp; // even column counts: a k-step covers two columns
+    PCB_CHECK_ARG(nlp <= PCB_MAXL + 2, "too many columns");
     if (ensure_hstage(c, sizeof(cplx) * 2 * PCB_MAXL * PCB_MAXL + 65536)) return -1;
     if (ensure_dsmall(c, sizeof(cplx) * 2 * PCB_MAXL * PCB_MAXL + 65536)) return -1;
-    const int JBk = (JB == 3) ? 4 : JB;        // kernel variants: 8, 16 or 32 output columns
-    const int MPk = 8 * JBk;
-    const int TRs[5] = {0, 128, 64, 32, 32};   // rows per tile = NT / JBk with NT = 128
     PCB_CUDA_OK(cudaStreamSynchronize(c->stream));
     cplx* he = (cplx*)c->hstage;
     const cplx* e = (const cplx*)E;
-    for (int k = 0; k < nl; ++k)
-        for (int j = 0; j < MPk; ++j) he[k * MPk + j] = (j < m) ? e[k * m + j] : cmake(0.0, 0.0);
-    PCB_CUDA_OK(cudaMemcpyAsync(c->dsmall, he, sizeof(cplx) * nl * MPk, cudaMemcpyHostToDevice, c->stream));
     PcbColList Sin, HSin;
     PcbColListW X, HX, P, HP;
     for (int k = 0; k < PCB_MAXL; ++k) {
-        Sin.p[k] = (k < nl) ? (const cplx*)s[k] : nullptr; HSin.p[k] = (k < nl) ? (const cplx*)hs[k] : nullptr;
+        Sin.p[k] = nullptr; HSin.p[k] = nullptr;
         X.p[k] = (k < m) ? (cplx*)s[k] : nullptr; HX.p[k] = (k < m) ? (cplx*)hs[k] : nullptr;
         P.p[k] = (k < m) ? (cplx*)p_out[k] : nullptr; HP.p[k] = (k < m) ? (cplx*)hp_out[k] : nullptr;
     }
-    const int TR = TRs[JBk];
-    const size_t smem = sizeof(cplx) * ((size_t)nl * MPk + 2 * (size_t)nl * TR);
-    const long long ntiles = (c->R + TR - 1) / TR;
-    int per_sm = (int)((size_t)220 * 1024 / smem); if (per_sm < 1) per_sm = 1; if (per_sm > 8) per_sm = 8;
-    long long gx = (long long)c->sms * per_sm; if (gx > ntiles) gx = ntiles;
-    dim3 grid((unsigned)gx, 1, 1);
-#ifndef PCB_EMU
-#define PCB_UPD_ATTR(K) if (smem > 48 * 1024) PCB_CUDA_OK(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
-#else
-#define PCB_UPD_ATTR(K)
-#endif
+    for (int k = 0; k < nlp; ++k) {
+        const int src = (k < kx) ? (k < m ? k : -1) : (k - kx + m < nl ? k - kx + m : -1);   // input column or zero padding
+        if (k < PCB_MAXL) { Sin.p[k] = src >= 0 ? (const cplx*)s[src] : nullptr; HSin.p[k] = src >= 0 ? (const cplx*)hs[src] : nullptr; }
+        else if (src >= 0) { pcb_set_error("pcb_update: column list overflow"); return -2; }
+        for (int j = 0; j < MPp; ++j) he[k * MPp + j] = (src >= 0 && j < m) ? e[src * m + j] : cmake(0.0, 0.0);
+    }
+    PCB_CUDA_OK(cudaMemcpyAsync(c->dsmall, he, sizeof(cplx) * nlp * MPp, cudaMemcpyHostToDevice, c->stream));
     const cplx* dE = (const cplx*)c->dsmall;
-    if (JBk == 1) { PCB_UPD_ATTR(k_update<1>); PCB_LAUNCH(k_update<1>, grid, dim3(PCB_UPD_NT, 1, 1), smem, c->stream, Sin, HSin, X, HX, P, HP, dE, m, nl, c->R); }
-    else if (JBk == 2) { PCB_UPD_ATTR(k_update<2>); PCB_LAUNCH(k_update<2>, grid, dim3(PCB_UPD_NT, 1, 1), smem, c->stream, Sin, HSin, X, HX, P, HP, dE, m, nl, c->R); }
-    else { PCB_UPD_ATTR(k_update<4>); PCB_LAUNCH(k_update<4>, grid, dim3(PCB_UPD_NT, 1, 1), smem, c->stream, Sin, HSin, X, HX, P, HP, dE, m, nl, c->R); }
+    // rows per tile: 32 when the double-buffered stage fits in shared memory, else 16
+    const size_t smem32 = sizeof(cplx) * ((size_t)nlp * MPp + 4 * (size_t)nlp * PcbUpd<32>::LD);
+    const size_t smem16 = sizeof(cplx) * ((size_t)nlp * MPp + 4 * (size_t)nlp * PcbUpd<16>::LD);
+    const bool big = smem32 <= (size_t)200 * 1024;
+    const int TR = big ? 32 : 16;
+    const size_t smem = big ? smem32 : smem16;
+    const int warps = (TR / 8) * (JT / 2);
+    const long long ntiles = (c->R + TR - 1) / TR;
+    int per_sm = (int)((size_t)224 * 1024 / (smem + 1024)); if (per_sm < 1) per_sm = 1; if (per_sm > 4) per_sm = 4;
+    long long gx = (long long)c->sms * per_sm; if (gx > ntiles) gx = ntiles;
+    dim3 grid((unsigned)gx, 1, 1), block((unsigned)(32 * warps), 1, 1);
+    if (big) {
+#ifndef PCB_EMU
+        if (smem > 48 * 1024) PCB_CUDA_OK(cudaFuncSetAttribute(k_update<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#endif
+        PCB_LAUNCH(k_update<32>, grid, block, smem, c->stream, Sin, HSin, X, HX, P, HP, dE, m, kx, kp, MPp, c->R);
+    } else {
+#ifndef PCB_EMU
+        if (smem > 48 * 1024) PCB_CUDA_OK(cudaFuncSetAttribute(k_update<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#endif
+        PCB_LAUNCH(k_update<16>, grid, block, smem, c->stream, Sin, HSin, X, HX, P, HP, dE, m, kx, kp, MPp, c->R);
+    }
     PCB_CUDA_OK(cudaGetLastError());
     c->launches++;
     return 0;

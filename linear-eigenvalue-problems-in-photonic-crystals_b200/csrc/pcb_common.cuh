@@ -57,6 +57,17 @@ PCB_HD cplx cfmac(cplx a, cplx b, cplx c) { /* conj(a)*b + c */
     return cmake(fma(a.x, b.x, fma(a.y, b.y, c.x)), fma(a.x, b.y, fma(-a.y, b.x, c.y)));
 }
 
+// FP64 tensor-core MMA (DMMA): D(8x8) += A(8x4) B(4x8).  Fragment layout (PTX ISA, m8n8k4 .f64):
+//   a = A[lane>>2][lane&3],  b = B[lane&3][lane>>2],  (c0, c1) = C[lane>>2][2*(lane&3) + {0,1}].
+#ifdef PCB_EMU
+PCB_D void pcb_dmma(double& c0, double& c1, double a, double b) { pcbemu::mma884(c0, c1, a, b); }
+#else
+PCB_D void pcb_dmma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+#endif
+
 #include "pcb_codelets.cuh"
 
 // ---- error handling -------------------------------------------------------------------

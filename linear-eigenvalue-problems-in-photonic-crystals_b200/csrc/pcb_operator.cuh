@@ -54,178 +54,260 @@ PCB_HD void pcb_cross(const cplx a[3], const cplx v[3], cplx z[3]) {
     z[2] = csub(cmul(a[0], v[1]), cmul(a[1], v[0]));
 }
 
+// ---- cp.async (LDGSTS) helpers: global -> shared without staging in registers ------------------------
+#ifdef PCB_EMU
+PCB_D void pcb_cp16(cplx* dst, const cplx* src) { *dst = *src; }
+PCB_D void pcb_cp8(void* dst, const void* src) { memcpy(dst, src, 8); }
+PCB_D void pcb_cp_commit() {}
+template <int N> PCB_D void pcb_cp_wait() {}
+#else
+PCB_D void pcb_cp16(cplx* dst, const cplx* src) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src));
+}
+PCB_D void pcb_cp8(void* dst, const void* src) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(src));
+}
+PCB_D void pcb_cp_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> PCB_D void pcb_cp_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+#endif
+
 // ---------------------------------------------------------------------------------------
 // Pass 1: x-lines forward.  SYM: 0 plain FFT, 1 multiply by K_A^H = (-conj k) x . on load.
-// Tile = LX consecutive rows (a row = all i0 for one (i1,i2)), all three components.
+// Persistent CTAs; a tile = LX consecutive rows (a row = all i0 for one (i1,i2)) x three components = 3 contiguous
+// chunks of LX*N elements.  Tile t+1 streams into the other shared-memory stage with cp.async while tile t is
+// transformed; the radix-R1 -> radix-R2 exchange happens IN PLACE in the stage ([c][row][n1|k1][n2], row stride R2P).
 // ---------------------------------------------------------------------------------------
-template <class P, int LX, int NT, int SYM>
-__global__ void __launch_bounds__(NT) k_xfwd(PcbOp op, PcbCols cols, const cplx* __restrict__ tw) {
+template <class P, int LX>
+PCB_D void pcb_xtile_load(cplx* __restrict__ st, const cplx* __restrict__ X, long long nn, int row0, int nrows, int tid, int nthr,
+                          bool kmajor) {
     constexpr int N = P::N, R1 = P::R1, R2 = P::R2, R2P = P::R2P;
-    PCB_DYN_SMEM(cplx, sm);   // [3][LX][R1][R2P]
-    const int col = blockIdx.y;
-    const cplx* __restrict__ X = cols.in[col];
-    cplx* __restrict__ Y = cols.out[col];
+    for (int e = tid; e < 3 * LX * N; e += nthr) {
+        const int c = e / (LX * N), rem = e % (LX * N);
+        const int r = rem / N, i0 = rem % N;
+        if (row0 + r >= nrows) continue;
+        // forward input (natural order): slot (n1, n2) with i0 = n1*R2 + n2; inverse input (Fourier order): slot (k1, k2), k = k1 + R1*k2
+        const int hi = kmajor ? i0 % R1 : i0 / R2, lo = kmajor ? i0 / R1 : i0 % R2;
+        pcb_cp16(st + ((c * LX + r) * R1 + hi) * R2P + lo, X + c * nn + (long long)(row0 + r) * N + i0);
+    }
+}
+
+template <class P, int LX, int NT, int SYM>
+__global__ void __launch_bounds__(NT) k_xfwd(PcbOp op, PcbCols cols, const cplx* __restrict__ tw, int ncols) {
+    constexpr int N = P::N, R1 = P::R1, R2 = P::R2, R2P = P::R2P;
+    constexpr int STAGE = 3 * LX * R1 * R2P;
+    PCB_DYN_SMEM(cplx, sm);   // [2 stages][3][LX][R1][R2P]
     const long long nn = op.nn;
-    const int row0 = blockIdx.x * LX;
     const int nrows = N * N;
+    const int tpc = (nrows + LX - 1) / LX;          // tiles per column
+    const int total = tpc * ncols;
     const int tid = threadIdx.x;
 
-    for (int item = tid; item < LX * R2; item += NT) {
-        const int r = item / R2, n2 = item % R2;
-        const int row = row0 + r;
-        if (row >= nrows) continue;
-        const int i1 = row % N, i2 = row / N;
-        cplx v[3][R1];
-        cplx kc[3];
-        if (SYM) {
-            PCB_UNROLL
-            for (int c = 0; c < 3; ++c) {
-                const cplx b = __ldg(op.T + (c * 3 + 1) * N + i1);
-                const cplx d = __ldg(op.T + (c * 3 + 2) * N + i2);
-                kc[c] = cadd(b, d);
-            }
+    int tile = blockIdx.x, stage = 0;
+    if (tile < total) {
+        pcb_xtile_load<P, LX>(sm, cols.in[tile / tpc], nn, (tile % tpc) * LX, nrows, tid, NT, false);
+        pcb_cp_commit();
+    }
+    for (; tile < total; tile += gridDim.x) {
+        const int next = tile + gridDim.x;
+        if (next < total) {
+            pcb_xtile_load<P, LX>(sm + (stage ^ 1) * STAGE, cols.in[next / tpc], nn, (next % tpc) * LX, nrows, tid, NT, false);
+            pcb_cp_commit();
+            pcb_cp_wait<1>();
+        } else {
+            pcb_cp_wait<0>();
         }
-        PCB_UNROLL
-        for (int n1 = 0; n1 < R1; ++n1) {
-            const int i0 = n1 * R2 + n2;
-            const long long e = (long long)row * N + i0;
-            cplx x[3];
-            PCB_UNROLL
-            for (int c = 0; c < 3; ++c) x[c] = X[c * nn + e];
+        __syncthreads();
+        cplx* __restrict__ st = sm + stage * STAGE;
+        cplx* __restrict__ Y = cols.out[tile / tpc];
+        const int row0 = (tile % tpc) * LX;
+
+        for (int item = tid; item < LX * R2; item += NT) {
+            const int r = item / R2, n2 = item % R2;
+            const int row = row0 + r;
+            if (row >= nrows) continue;
+            const int i1 = row % N, i2 = row / N;
+            cplx v[3][R1];
+            cplx kc[3];
             if (SYM) {
-                cplx a[3], z[3];
                 PCB_UNROLL
                 for (int c = 0; c < 3; ++c) {
-                    const cplx k = cadd(kc[c], __ldg(op.T + (c * 3 + 0) * N + i0));
-                    a[c] = cmake(-k.x, k.y);   // -conj(k)
+                    const cplx b = __ldg(op.T + (c * 3 + 1) * N + i1);
+                    const cplx d = __ldg(op.T + (c * 3 + 2) * N + i2);
+                    kc[c] = cadd(b, d);
                 }
-                pcb_cross(a, x, z);
-                PCB_UNROLL
-                for (int c = 0; c < 3; ++c) v[c][n1] = z[c];
-            } else {
-                PCB_UNROLL
-                for (int c = 0; c < 3; ++c) v[c][n1] = x[c];
             }
-        }
-        PCB_UNROLL
-        for (int c = 0; c < 3; ++c) {
-            Dft<R1, -1>::run(v[c]);
             PCB_UNROLL
-            for (int k1 = 0; k1 < R1; ++k1) {
-                cplx val = v[c][k1];
-                if (k1 > 0) val = cmul(val, __ldg(tw + k1 * R2 + n2));
-                sm[((c * LX + r) * R1 + k1) * R2P + n2] = val;
+            for (int n1 = 0; n1 < R1; ++n1) {
+                cplx x[3];
+                PCB_UNROLL
+                for (int c = 0; c < 3; ++c) x[c] = st[((c * LX + r) * R1 + n1) * R2P + n2];
+                if (SYM) {
+                    const int i0 = n1 * R2 + n2;
+                    cplx a[3], z[3];
+                    PCB_UNROLL
+                    for (int c = 0; c < 3; ++c) {
+                        const cplx k = cadd(kc[c], __ldg(op.T + (c * 3 + 0) * N + i0));
+                        a[c] = cmake(-k.x, k.y);   // -conj(k)
+                    }
+                    pcb_cross(a, x, z);
+                    PCB_UNROLL
+                    for (int c = 0; c < 3; ++c) v[c][n1] = z[c];
+                } else {
+                    PCB_UNROLL
+                    for (int c = 0; c < 3; ++c) v[c][n1] = x[c];
+                }
+            }
+            PCB_UNROLL
+            for (int c = 0; c < 3; ++c) {
+                Dft<R1, -1>::run(v[c]);
+                PCB_UNROLL
+                for (int k1 = 0; k1 < R1; ++k1) {
+                    cplx val = v[c][k1];
+                    if (k1 > 0) val = cmul(val, __ldg(tw + k1 * R2 + n2));
+                    st[((c * LX + r) * R1 + k1) * R2P + n2] = val;
+                }
             }
         }
-    }
-    __syncthreads();
-    for (int item = tid; item < 3 * LX * R1; item += NT) {
-        const int k1 = item % R1;
-        const int r = (item / R1) % LX;
-        const int c = item / (R1 * LX);
-        const int row = row0 + r;
-        if (row >= nrows) continue;
-        cplx v[R2];
-        PCB_UNROLL
-        for (int n2 = 0; n2 < R2; ++n2) v[n2] = sm[((c * LX + r) * R1 + k1) * R2P + n2];
-        Dft<R2, -1>::run(v);
-        cplx* __restrict__ dst = Y + c * nn + (long long)row * N + k1;
-        PCB_UNROLL
-        for (int k2 = 0; k2 < R2; ++k2) dst[R1 * k2] = v[k2];
+        __syncthreads();
+        for (int item = tid; item < 3 * LX * R1; item += NT) {
+            const int k1 = item % R1;
+            const int r = (item / R1) % LX;
+            const int c = item / (R1 * LX);
+            const int row = row0 + r;
+            if (row >= nrows) continue;
+            cplx v[R2];
+            PCB_UNROLL
+            for (int n2 = 0; n2 < R2; ++n2) v[n2] = st[((c * LX + r) * R1 + k1) * R2P + n2];
+            Dft<R2, -1>::run(v);
+            cplx* __restrict__ dst = Y + c * nn + (long long)row * N + k1;
+            PCB_UNROLL
+            for (int k2 = 0; k2 < R2; ++k2) dst[R1 * k2] = v[k2];
+        }
+        __syncthreads();     // stage is free for the prefetch issued in the next trip
+        stage ^= 1;
     }
 }
 
 // ---------------------------------------------------------------------------------------
 // Pass 5: x-lines inverse.  MODE 0: plain IFFT * 1/N^3;  1: A = K_A . ;  2: H = K_A . + gamma K_B x + shift x
-// Reads the work column W (in Fourier-x order), the source column X (MODE 2) and writes OUT
-// (OUT may alias W: each CTA only touches its own rows).
+// Reads the work column W (Fourier-x order), the source column X (MODE 2, staged by cp.async while the radix-R2 step
+// runs) and writes OUT (= W's column: each tile only touches its own rows).  Same persistent double-buffered structure.
 // ---------------------------------------------------------------------------------------
 template <class P, int LX, int NT, int MODE>
-__global__ void __launch_bounds__(NT) k_xinv(PcbOp op, PcbCols cols, const cplx* __restrict__ tw) {
+__global__ void __launch_bounds__(NT) k_xinv(PcbOp op, PcbCols cols, const cplx* __restrict__ tw, int ncols) {
     constexpr int N = P::N, R1 = P::R1, R2 = P::R2, R2P = P::R2P;
-    PCB_DYN_SMEM(cplx, sm);   // [3][LX][R1][R2P]
-    const int col = blockIdx.y;
-    const cplx* __restrict__ X = cols.in[col];
-    cplx* __restrict__ W = cols.out[col];
+    constexpr int STAGE = 3 * LX * R1 * R2P;
+    PCB_DYN_SMEM(cplx, sm);   // [2 stages][3][LX][R1][R2P] (+ [3][LX][R1][R2P] for X when MODE == 2)
+    cplx* __restrict__ xs = sm + 2 * STAGE;
     const long long nn = op.nn;
-    const int row0 = blockIdx.x * LX;
     const int nrows = N * N;
+    const int tpc = (nrows + LX - 1) / LX;
+    const int total = tpc * ncols;
     const int tid = threadIdx.x;
 
-    for (int item = tid; item < 3 * LX * R1; item += NT) {
-        const int k1 = item % R1;
-        const int r = (item / R1) % LX;
-        const int c = item / (R1 * LX);
-        const int row = row0 + r;
-        if (row >= nrows) continue;
-        cplx v[R2];
-        const cplx* __restrict__ src = W + c * nn + (long long)row * N + k1;
-        PCB_UNROLL
-        for (int k2 = 0; k2 < R2; ++k2) v[k2] = src[R1 * k2];
-        Dft<R2, +1>::run(v);
-        PCB_UNROLL
-        for (int n2 = 0; n2 < R2; ++n2) {
-            cplx val = v[n2];
-            if (k1 > 0) { const cplx t = __ldg(tw + k1 * R2 + n2); val = cmul(val, cmake(t.x, -t.y)); }
-            sm[((c * LX + r) * R1 + k1) * R2P + n2] = val;
-        }
+    int tile = blockIdx.x, stage = 0;
+    if (tile < total) {
+        pcb_xtile_load<P, LX>(sm, cols.out[tile / tpc], nn, (tile % tpc) * LX, nrows, tid, NT, true);
+        pcb_cp_commit();
     }
-    __syncthreads();
-    for (int item = tid; item < LX * R2; item += NT) {
-        const int r = item / R2, n2 = item % R2;
-        const int row = row0 + r;
-        if (row >= nrows) continue;
-        const int i1 = row % N, i2 = row / N;
-        cplx v[3][R1];
-        PCB_UNROLL
-        for (int c = 0; c < 3; ++c) {
-            PCB_UNROLL
-            for (int k1 = 0; k1 < R1; ++k1) v[c][k1] = sm[((c * LX + r) * R1 + k1) * R2P + n2];
-            Dft<R1, +1>::run(v[c]);
+    for (; tile < total; tile += gridDim.x) {
+        const int next = tile + gridDim.x;
+        const int row0 = (tile % tpc) * LX;
+        int pending = 0;
+        if (MODE == 2) {
+            pcb_xtile_load<P, LX>(xs, cols.in[tile / tpc], nn, row0, nrows, tid, NT, false);
+            pcb_cp_commit();
+            ++pending;
         }
-        cplx kc[3];
-        if (MODE) {
+        if (next < total) {
+            pcb_xtile_load<P, LX>(sm + (stage ^ 1) * STAGE, cols.out[next / tpc], nn, (next % tpc) * LX, nrows, tid, NT, true);
+            pcb_cp_commit();
+            ++pending;
+        }
+        // groups in flight, oldest first: W(tile) | X(tile) | W(next)  ->  W(tile) must have landed
+        if (pending == 2) pcb_cp_wait<2>(); else if (pending == 1) pcb_cp_wait<1>(); else pcb_cp_wait<0>();
+        __syncthreads();
+        cplx* __restrict__ st = sm + stage * STAGE;
+        cplx* __restrict__ W = cols.out[tile / tpc];
+
+        for (int item = tid; item < 3 * LX * R1; item += NT) {
+            const int k1 = item % R1;
+            const int r = (item / R1) % LX;
+            const int c = item / (R1 * LX);
+            if (row0 + r >= nrows) continue;
+            cplx v[R2];
+            PCB_UNROLL
+            for (int k2 = 0; k2 < R2; ++k2) v[k2] = st[((c * LX + r) * R1 + k1) * R2P + k2];
+            Dft<R2, +1>::run(v);
+            PCB_UNROLL
+            for (int n2 = 0; n2 < R2; ++n2) {
+                cplx val = v[n2];
+                if (k1 > 0) { const cplx t = __ldg(tw + k1 * R2 + n2); val = cmul(val, cmake(t.x, -t.y)); }
+                st[((c * LX + r) * R1 + k1) * R2P + n2] = val;
+            }
+        }
+        if (MODE == 2) { if (next < total) pcb_cp_wait<1>(); else pcb_cp_wait<0>(); }   // X(tile) has landed
+        __syncthreads();
+        for (int item = tid; item < LX * R2; item += NT) {
+            const int r = item / R2, n2 = item % R2;
+            const int row = row0 + r;
+            if (row >= nrows) continue;
+            const int i1 = row % N, i2 = row / N;
+            cplx v[3][R1];
             PCB_UNROLL
             for (int c = 0; c < 3; ++c) {
-                const cplx b = __ldg(op.T + (c * 3 + 1) * N + i1);
-                const cplx d = __ldg(op.T + (c * 3 + 2) * N + i2);
-                kc[c] = cadd(b, d);
+                PCB_UNROLL
+                for (int k1 = 0; k1 < R1; ++k1) v[c][k1] = st[((c * LX + r) * R1 + k1) * R2P + n2];
+                Dft<R1, +1>::run(v[c]);
             }
-        }
-        PCB_UNROLL
-        for (int n1 = 0; n1 < R1; ++n1) {
-            const int i0 = n1 * R2 + n2;
-            const long long e = (long long)row * N + i0;
-            cplx u[3], z[3];
-            PCB_UNROLL
-            for (int c = 0; c < 3; ++c) u[c] = cscale(v[c][n1], op.inv_n3);
+            cplx kc[3];
             if (MODE) {
-                cplx k[3];
                 PCB_UNROLL
-                for (int c = 0; c < 3; ++c) k[c] = cadd(kc[c], __ldg(op.T + (c * 3 + 0) * N + i0));
-                pcb_cross(k, u, z);
-                if (MODE == 2) {
-                    cplx x[3];
-                    PCB_UNROLL
-                    for (int c = 0; c < 3; ++c) x[c] = X[c * nn + e];
-                    // gamma K_B x = gamma conj(k) (k . x)   (h_block with D_B, pcfft.py:176)
-                    cplx dot = cadd(cadd(cmul(k[0], x[0]), cmul(k[1], x[1])), cmul(k[2], x[2]));
-                    dot = cscale(dot, op.gamma);
-                    PCB_UNROLL
-                    for (int c = 0; c < 3; ++c) {
-                        cplx t = cfmac(k[c], dot, z[c]);
-                        t.x = fma(op.shift, x[c].x, t.x);
-                        t.y = fma(op.shift, x[c].y, t.y);
-                        z[c] = t;
-                    }
+                for (int c = 0; c < 3; ++c) {
+                    const cplx b = __ldg(op.T + (c * 3 + 1) * N + i1);
+                    const cplx d = __ldg(op.T + (c * 3 + 2) * N + i2);
+                    kc[c] = cadd(b, d);
                 }
-            } else {
-                PCB_UNROLL
-                for (int c = 0; c < 3; ++c) z[c] = u[c];
             }
             PCB_UNROLL
-            for (int c = 0; c < 3; ++c) W[c * nn + e] = z[c];
+            for (int n1 = 0; n1 < R1; ++n1) {
+                const int i0 = n1 * R2 + n2;
+                const long long e = (long long)row * N + i0;
+                cplx u[3], z[3];
+                PCB_UNROLL
+                for (int c = 0; c < 3; ++c) u[c] = cscale(v[c][n1], op.inv_n3);
+                if (MODE) {
+                    cplx k[3];
+                    PCB_UNROLL
+                    for (int c = 0; c < 3; ++c) k[c] = cadd(kc[c], __ldg(op.T + (c * 3 + 0) * N + i0));
+                    pcb_cross(k, u, z);
+                    if (MODE == 2) {
+                        cplx x[3];
+                        PCB_UNROLL
+                        for (int c = 0; c < 3; ++c) x[c] = xs[((c * LX + r) * R1 + n1) * R2P + n2];
+                        // gamma K_B x = gamma conj(k) (k . x)   (h_block with D_B, pcfft.py:176)
+                        cplx dot = cadd(cadd(cmul(k[0], x[0]), cmul(k[1], x[1])), cmul(k[2], x[2]));
+                        dot = cscale(dot, op.gamma);
+                        PCB_UNROLL
+                        for (int c = 0; c < 3; ++c) {
+                            cplx t = cfmac(k[c], dot, z[c]);
+                            t.x = fma(op.shift, x[c].x, t.x);
+                            t.y = fma(op.shift, x[c].y, t.y);
+                            z[c] = t;
+                        }
+                    }
+                } else {
+                    PCB_UNROLL
+                    for (int c = 0; c < 3; ++c) z[c] = u[c];
+                }
+                PCB_UNROLL
+                for (int c = 0; c < 3; ++c) W[c * nn + e] = z[c];
+            }
         }
+        __syncthreads();
+        stage ^= 1;
     }
 }
 
@@ -300,111 +382,145 @@ PCB_HD void pcb_diel_point(const PcbOp& op, unsigned m, cplx u[3]) {
 // ---------------------------------------------------------------------------------------
 // Pass 3: z-lines: forward FFT, dielectric multiply M in real space, inverse FFT; in place.
 // DIEL: 0 identity, 1 component-wise (chiral), 2 coupled 3x3 at a point (trivial).
-// Tile = 8 i0 x one i1, all i2, three components.
+// Persistent CTAs; tile = 8 consecutive i0 x one i1, all i2, three components (3*N segments of 128 B), streamed into
+// one of two shared-memory stages with cp.async while the previous tile is transformed.  The line element with
+// digits (a, b) always lives in slot P::lin(a, b) of its stage, so all four radix steps exchange in place.
 // ---------------------------------------------------------------------------------------
+template <class P>
+PCB_D void pcb_ztile_load(cplx* __restrict__ st, const cplx* __restrict__ Y, long long nn, int t0, int i1, int tid, int nthr) {
+    constexpr int N = P::N;
+    for (int e = tid; e < 3 * N * 8; e += nthr) {
+        const int i0l = e % 8, i2 = (e / 8) % N, c = e / (8 * N);
+        const int i0 = t0 * 8 + i0l;
+        if (i0 < N) pcb_cp16(st + (c * N + i2) * 8 + i0l, Y + c * nn + ((long long)i2 * N + i1) * N + i0);
+    }
+}
+
 template <class P, int DIEL, int NT>
-__global__ void __launch_bounds__(NT) k_zmid(PcbOp op, PcbCols cols, const cplx* __restrict__ tw) {
+__global__ void __launch_bounds__(NT) k_zmid(PcbOp op, PcbCols cols, const cplx* __restrict__ tw, int ncols) {
     constexpr int N = P::N, R1 = P::R1, R2 = P::R2;
-    PCB_DYN_SMEM(cplx, sm);   // [3][N][8] complex, then [N][8] mask bytes
-    unsigned char* msk = reinterpret_cast<unsigned char*>(sm + 3 * N * 8);
-    const int col = blockIdx.y;
-    cplx* __restrict__ Y = cols.out[col];
+    constexpr int STAGE = 3 * N * 8;
+    PCB_DYN_SMEM(cplx, sm);   // [2 stages][3][N][8]
     const long long nn = op.nn;
     constexpr int NT0 = (N + 7) / 8;
-    const int t0 = blockIdx.x % NT0, i1 = blockIdx.x / NT0;
+    const int tpc = NT0 * N;
+    const int total = tpc * ncols;
     const long long sline = (long long)N * N;
     const int tid = threadIdx.x;
 
-    if (DIEL) {
-        for (int item = tid; item < N * 8; item += NT) {
-            const int i0l = item % 8, i2 = item / 8;
-            const int i0 = t0 * 8 + i0l;
-            msk[item] = (i0 < N) ? op.mask[((long long)i2 * N + i1) * N + i0] : 0;
-        }
+    int tile = blockIdx.x, stage = 0;
+    if (tile < total) {
+        pcb_ztile_load<P>(sm, cols.out[tile / tpc], nn, (tile % tpc) % NT0, (tile % tpc) / NT0, tid, NT);
+        pcb_cp_commit();
     }
-    for (int item = tid; item < 3 * R2 * 8; item += NT) {
-        const int i0l = item % 8, n2 = (item / 8) % R2, c = item / (8 * R2);
-        const int i0 = t0 * 8 + i0l;
-        if (i0 >= N) continue;
-        const cplx* __restrict__ base = Y + c * nn + (long long)i1 * N + i0;
-        cplx v[R1];
-        PCB_UNROLL
-        for (int n1 = 0; n1 < R1; ++n1) v[n1] = base[P::lin(n1, n2) * sline];
-        Dft<R1, -1>::run(v);
-        PCB_UNROLL
-        for (int k1 = 0; k1 < R1; ++k1) {
-            cplx val = v[k1];
-            if (!P::PFA && k1 > 0) val = cmul(val, __ldg(tw + k1 * R2 + n2));
-            sm[(c * N + k1 * R2 + n2) * 8 + i0l] = val;
+    for (; tile < total; tile += gridDim.x) {
+        const int next = tile + gridDim.x;
+        if (next < total) {
+            pcb_ztile_load<P>(sm + (stage ^ 1) * STAGE, cols.out[next / tpc], nn, (next % tpc) % NT0, (next % tpc) / NT0, tid, NT);
+            pcb_cp_commit();
+            pcb_cp_wait<1>();
+        } else {
+            pcb_cp_wait<0>();
         }
-    }
-    __syncthreads();
-    if (DIEL == 2) {
-        for (int item = tid; item < R1 * 8; item += NT) {
-            const int i0l = item % 8, k1 = item / 8;
+        __syncthreads();
+        cplx* __restrict__ st = sm + stage * STAGE;
+        cplx* __restrict__ Y = cols.out[tile / tpc];
+        const int t0 = (tile % tpc) % NT0, i1 = (tile % tpc) / NT0;
+
+        // forward radix R1 over n1 (fixed n2)
+        for (int item = tid; item < 3 * R2 * 8; item += NT) {
+            const int i0l = item % 8, n2 = (item / 8) % R2, c = item / (8 * R2);
             if (t0 * 8 + i0l >= N) continue;
-            cplx v[3][R2];
+            cplx v[R1];
             PCB_UNROLL
-            for (int c = 0; c < 3; ++c) {
-                PCB_UNROLL
-                for (int n2 = 0; n2 < R2; ++n2) v[c][n2] = sm[(c * N + k1 * R2 + n2) * 8 + i0l];
-                Dft<R2, -1>::run(v[c]);
+            for (int n1 = 0; n1 < R1; ++n1) v[n1] = st[(c * N + P::lin(n1, n2)) * 8 + i0l];
+            Dft<R1, -1>::run(v);
+            PCB_UNROLL
+            for (int k1 = 0; k1 < R1; ++k1) {
+                cplx val = v[k1];
+                if (!P::PFA && k1 > 0) val = cmul(val, __ldg(tw + k1 * R2 + n2));
+                st[(c * N + P::lin(k1, n2)) * 8 + i0l] = val;
             }
-            PCB_UNROLL
-            for (int k2 = 0; k2 < R2; ++k2) {
-                const int i2 = P::lout(k1, k2);
-                cplx u[3] = {v[0][k2], v[1][k2], v[2][k2]};
-                pcb_diel_point(op, msk[i2 * 8 + i0l], u);
-                v[0][k2] = u[0]; v[1][k2] = u[1]; v[2][k2] = u[2];
-            }
-            PCB_UNROLL
-            for (int c = 0; c < 3; ++c) {
-                Dft<R2, +1>::run(v[c]);
+        }
+        __syncthreads();
+        // forward radix R2 (-> real space), M, inverse radix R2
+        if (DIEL == 2) {
+            for (int item = tid; item < R1 * 8; item += NT) {
+                const int i0l = item % 8, k1 = item / 8;
+                const int i0 = t0 * 8 + i0l;
+                if (i0 >= N) continue;
+                unsigned char mk[R2];
                 PCB_UNROLL
-                for (int n2 = 0; n2 < R2; ++n2) {
-                    cplx val = v[c][n2];
-                    if (!P::PFA && k1 > 0) { const cplx t = __ldg(tw + k1 * R2 + n2); val = cmul(val, cmake(t.x, -t.y)); }
-                    sm[(c * N + k1 * R2 + n2) * 8 + i0l] = val;
+                for (int k2 = 0; k2 < R2; ++k2) mk[k2] = __ldg(op.mask + ((long long)P::lout(k1, k2) * N + i1) * N + i0);
+                cplx v[3][R2];
+                PCB_UNROLL
+                for (int c = 0; c < 3; ++c) {
+                    PCB_UNROLL
+                    for (int n2 = 0; n2 < R2; ++n2) v[c][n2] = st[(c * N + P::lin(k1, n2)) * 8 + i0l];
+                    Dft<R2, -1>::run(v[c]);
                 }
-            }
-        }
-    } else {
-        for (int item = tid; item < 3 * R1 * 8; item += NT) {
-            const int i0l = item % 8, k1 = (item / 8) % R1, c = item / (8 * R1);
-            if (t0 * 8 + i0l >= N) continue;
-            cplx v[R2];
-            PCB_UNROLL
-            for (int n2 = 0; n2 < R2; ++n2) v[n2] = sm[(c * N + k1 * R2 + n2) * 8 + i0l];
-            Dft<R2, -1>::run(v);
-            if (DIEL == 1) {
-                const double s = op.ediag[c];
                 PCB_UNROLL
                 for (int k2 = 0; k2 < R2; ++k2) {
-                    const unsigned m = msk[P::lout(k1, k2) * 8 + i0l];
-                    if ((m >> c) & 1u) v[k2] = cscale(v[k2], s);
+                    cplx u[3] = {v[0][k2], v[1][k2], v[2][k2]};
+                    pcb_diel_point(op, mk[k2], u);
+                    v[0][k2] = u[0]; v[1][k2] = u[1]; v[2][k2] = u[2];
+                }
+                PCB_UNROLL
+                for (int c = 0; c < 3; ++c) {
+                    Dft<R2, +1>::run(v[c]);
+                    PCB_UNROLL
+                    for (int n2 = 0; n2 < R2; ++n2) {
+                        cplx val = v[c][n2];
+                        if (!P::PFA && k1 > 0) { const cplx t = __ldg(tw + k1 * R2 + n2); val = cmul(val, cmake(t.x, -t.y)); }
+                        st[(c * N + P::lin(k1, n2)) * 8 + i0l] = val;
+                    }
                 }
             }
-            Dft<R2, +1>::run(v);
-            PCB_UNROLL
-            for (int n2 = 0; n2 < R2; ++n2) {
-                cplx val = v[n2];
-                if (!P::PFA && k1 > 0) { const cplx t = __ldg(tw + k1 * R2 + n2); val = cmul(val, cmake(t.x, -t.y)); }
-                sm[(c * N + k1 * R2 + n2) * 8 + i0l] = val;
+        } else {
+            for (int item = tid; item < 3 * R1 * 8; item += NT) {
+                const int i0l = item % 8, k1 = (item / 8) % R1, c = item / (8 * R1);
+                const int i0 = t0 * 8 + i0l;
+                if (i0 >= N) continue;
+                unsigned char mk[R2];
+                if (DIEL == 1) {
+                    PCB_UNROLL
+                    for (int k2 = 0; k2 < R2; ++k2) mk[k2] = __ldg(op.mask + ((long long)P::lout(k1, k2) * N + i1) * N + i0);
+                }
+                cplx v[R2];
+                PCB_UNROLL
+                for (int n2 = 0; n2 < R2; ++n2) v[n2] = st[(c * N + P::lin(k1, n2)) * 8 + i0l];
+                Dft<R2, -1>::run(v);
+                if (DIEL == 1) {
+                    const double sc = op.ediag[c];
+                    PCB_UNROLL
+                    for (int k2 = 0; k2 < R2; ++k2)
+                        if ((mk[k2] >> c) & 1u) v[k2] = cscale(v[k2], sc);
+                }
+                Dft<R2, +1>::run(v);
+                PCB_UNROLL
+                for (int n2 = 0; n2 < R2; ++n2) {
+                    cplx val = v[n2];
+                    if (!P::PFA && k1 > 0) { const cplx t = __ldg(tw + k1 * R2 + n2); val = cmul(val, cmake(t.x, -t.y)); }
+                    st[(c * N + P::lin(k1, n2)) * 8 + i0l] = val;
+                }
             }
         }
-    }
-    __syncthreads();
-    for (int item = tid; item < 3 * R2 * 8; item += NT) {
-        const int i0l = item % 8, n2 = (item / 8) % R2, c = item / (8 * R2);
-        const int i0 = t0 * 8 + i0l;
-        if (i0 >= N) continue;
-        cplx v[R1];
-        PCB_UNROLL
-        for (int k1 = 0; k1 < R1; ++k1) v[k1] = sm[(c * N + k1 * R2 + n2) * 8 + i0l];
-        Dft<R1, +1>::run(v);
-        cplx* __restrict__ base = Y + c * nn + (long long)i1 * N + i0;
-        PCB_UNROLL
-        for (int n1 = 0; n1 < R1; ++n1) base[P::lin(n1, n2) * sline] = v[n1];
+        __syncthreads();
+        // inverse radix R1 and store
+        for (int item = tid; item < 3 * R2 * 8; item += NT) {
+            const int i0l = item % 8, n2 = (item / 8) % R2, c = item / (8 * R2);
+            const int i0 = t0 * 8 + i0l;
+            if (i0 >= N) continue;
+            cplx v[R1];
+            PCB_UNROLL
+            for (int k1 = 0; k1 < R1; ++k1) v[k1] = st[(c * N + P::lin(k1, n2)) * 8 + i0l];
+            Dft<R1, +1>::run(v);
+            cplx* __restrict__ base = Y + c * nn + (long long)i1 * N + i0;
+            PCB_UNROLL
+            for (int n1 = 0; n1 < R1; ++n1) base[P::lin(n1, n2) * sline] = v[n1];
+        }
+        __syncthreads();
+        stage ^= 1;
     }
 }
 
@@ -415,9 +531,9 @@ struct PcbOpLaunch {
     int N;
     int r1, r2;
     // mode: 0 plain 3-D FFT forward, 1 plain inverse (1/N^3), 2 A = AMA^H, 3 H = AMA^H + gamma B^H B + shift
-    int (*apply)(const PcbOp& op, const PcbCols& cols, int ncols, int mode, const cplx* tw, cudaStream_t s);
+    int (*apply)(const PcbOp& op, const PcbCols& cols, int ncols, int mode, const cplx* tw, cudaStream_t s, int sms);
     // split passes used by the cross-DoF dielectric and by the tests: pass ids below
-    int (*pass)(const PcbOp& op, const PcbCols& cols, int ncols, int pass_id, const cplx* tw, cudaStream_t s);
+    int (*pass)(const PcbOp& op, const PcbCols& cols, int ncols, int pass_id, const cplx* tw, cudaStream_t s, int sms);
 };
 enum { PCB_PASS_XFWD_SYM = 0, PCB_PASS_XFWD = 1, PCB_PASS_YFWD = 2, PCB_PASS_ZFWD = 3, PCB_PASS_ZINV = 4,
        PCB_PASS_YINV = 5, PCB_PASS_XINV = 6, PCB_PASS_XINV_A = 7, PCB_PASS_XINV_H = 8, PCB_PASS_ZMID = 9 };

@@ -13,16 +13,26 @@ typedef Plan<PCB_N, PCB_R1, PCB_R2> P;
 constexpr int NT = 128;
 constexpr int kRowBytes = 3 * P::R1 * P::R2P * (int)sizeof(cplx);
 constexpr int LX = (8 * kRowBytes <= 65536) ? 8 : (4 * kRowBytes <= 65536) ? 4 : (2 * kRowBytes <= 65536) ? 2 : 1;
-constexpr int kSmemX = LX * kRowBytes;
+constexpr int kStageX = LX * kRowBytes;               // one x-tile (three components)
+constexpr int kSmemXF = 2 * kStageX;                    // forward: two stages
+constexpr int kSmemXI = 2 * kStageX;                    // inverse modes 0/1
+constexpr int kSmemXH = 3 * kStageX;                    // inverse mode 2: + staged X tile
 constexpr int kSmemL = 3 * P::N * 8 * (int)sizeof(cplx);
-constexpr int kSmemZ = kSmemL + P::N * 8;
+constexpr int kSmemZ = 2 * kSmemL;                       // two stages
 
 template <class K>
 int set_smem(K kern, int bytes) {
     if (bytes > 48 * 1024) PCB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     return 0;
 }
+inline int ctas_per_sm(int smem, int regs_hint_threads) {
+    int n = (224 * 1024) / (smem + 1024);
+    if (n < 1) n = 1;
+    if (n > regs_hint_threads) n = regs_hint_threads;
+    return n;
+}
 
+// one CTA per tile (y lines and the split z passes)
 #define PCB_GO(KERN, GRIDX, SMEM)                                                   \
     do {                                                                            \
         auto kfn = KERN;                                                            \
@@ -31,25 +41,37 @@ int set_smem(K kern, int bytes) {
         PCB_LAUNCH(kfn, grid, dim3(NT, 1, 1), (size_t)(SMEM), s, op, cols, tw);      \
         PCB_CUDA_OK(cudaGetLastError());                                            \
     } while (0)
+// persistent CTAs striding over (column, tile)
+#define PCB_GO_P(KERN, TILES, SMEM, MAXCTA)                                         \
+    do {                                                                            \
+        auto kfn = KERN;                                                            \
+        if (set_smem(kfn, (SMEM))) return -1;                                       \
+        long long gx = (long long)sms * ctas_per_sm((SMEM), (MAXCTA));              \
+        const long long tot = (long long)(TILES) * ncols;                           \
+        if (gx > tot) gx = tot;                                                     \
+        dim3 grid((unsigned)gx, 1, 1);                                              \
+        PCB_LAUNCH(kfn, grid, dim3(NT, 1, 1), (size_t)(SMEM), s, op, cols, tw, ncols); \
+        PCB_CUDA_OK(cudaGetLastError());                                            \
+    } while (0)
 
 constexpr int GX = (P::N * P::N + LX - 1) / LX;          // x tiles per column
 constexpr int GL = ((P::N + 7) / 8) * P::N;              // strided-line tiles per column
 
-int run_pass(const PcbOp& op, const PcbCols& cols, int ncols, int pass_id, const cplx* tw, cudaStream_t s) {
+int run_pass(const PcbOp& op, const PcbCols& cols, int ncols, int pass_id, const cplx* tw, cudaStream_t s, int sms) {
     switch (pass_id) {
-        case PCB_PASS_XFWD_SYM: PCB_GO((k_xfwd<P, LX, NT, 1>), GX, kSmemX); break;
-        case PCB_PASS_XFWD:     PCB_GO((k_xfwd<P, LX, NT, 0>), GX, kSmemX); break;
+        case PCB_PASS_XFWD_SYM: PCB_GO_P((k_xfwd<P, LX, NT, 1>), GX, kSmemXF, 3); break;
+        case PCB_PASS_XFWD:     PCB_GO_P((k_xfwd<P, LX, NT, 0>), GX, kSmemXF, 3); break;
         case PCB_PASS_YFWD:     PCB_GO((k_line<P, 1, -1, NT>), GL, kSmemL); break;
         case PCB_PASS_ZFWD:     PCB_GO((k_line<P, 2, -1, NT>), GL, kSmemL); break;
         case PCB_PASS_ZINV:     PCB_GO((k_line<P, 2, +1, NT>), GL, kSmemL); break;
         case PCB_PASS_YINV:     PCB_GO((k_line<P, 1, +1, NT>), GL, kSmemL); break;
-        case PCB_PASS_XINV:     PCB_GO((k_xinv<P, LX, NT, 0>), GX, kSmemX); break;
-        case PCB_PASS_XINV_A:   PCB_GO((k_xinv<P, LX, NT, 1>), GX, kSmemX); break;
-        case PCB_PASS_XINV_H:   PCB_GO((k_xinv<P, LX, NT, 2>), GX, kSmemX); break;
+        case PCB_PASS_XINV:     PCB_GO_P((k_xinv<P, LX, NT, 0>), GX, kSmemXI, 3); break;
+        case PCB_PASS_XINV_A:   PCB_GO_P((k_xinv<P, LX, NT, 1>), GX, kSmemXI, 3); break;
+        case PCB_PASS_XINV_H:   PCB_GO_P((k_xinv<P, LX, NT, 2>), GX, kSmemXH, 3); break;
         case PCB_PASS_ZMID:
-            if (op.diel == PCB_DIEL_NONE) PCB_GO((k_zmid<P, 0, NT>), GL, kSmemZ);
-            else if (op.diel == PCB_DIEL_CHIRAL) PCB_GO((k_zmid<P, 1, NT>), GL, kSmemZ);
-            else if (op.diel == PCB_DIEL_TRIVIAL) PCB_GO((k_zmid<P, 2, NT>), GL, kSmemZ);
+            if (op.diel == PCB_DIEL_NONE) PCB_GO_P((k_zmid<P, 0, NT>), GL, kSmemZ, 4);
+            else if (op.diel == PCB_DIEL_CHIRAL) PCB_GO_P((k_zmid<P, 1, NT>), GL, kSmemZ, 4);
+            else if (op.diel == PCB_DIEL_TRIVIAL) PCB_GO_P((k_zmid<P, 2, NT>), GL, kSmemZ, 2);
             else { pcb_set_error("zmid: dielectric type %d has no fused z pass", op.diel); return -1; }
             break;
         default: pcb_set_error("unknown pass id %d", pass_id); return -1;
@@ -57,7 +79,7 @@ int run_pass(const PcbOp& op, const PcbCols& cols, int ncols, int pass_id, const
     return 0;
 }
 
-int run_apply(const PcbOp& op, const PcbCols& cols, int ncols, int mode, const cplx* tw, cudaStream_t s) {
+int run_apply(const PcbOp& op, const PcbCols& cols, int ncols, int mode, const cplx* tw, cudaStream_t s, int sms) {
     static const int fwd[] = {PCB_PASS_XFWD, PCB_PASS_YFWD, PCB_PASS_ZFWD};
     static const int inv[] = {PCB_PASS_ZINV, PCB_PASS_YINV, PCB_PASS_XINV};
     static const int opA[] = {PCB_PASS_XFWD_SYM, PCB_PASS_YFWD, PCB_PASS_ZMID, PCB_PASS_YINV, PCB_PASS_XINV_A};
@@ -72,7 +94,7 @@ int run_apply(const PcbOp& op, const PcbCols& cols, int ncols, int mode, const c
         default: pcb_set_error("unknown apply mode %d", mode); return -1;
     }
     for (int i = 0; i < n; ++i)
-        if (run_pass(op, cols, ncols, seq[i], tw, s)) return -1;
+        if (run_pass(op, cols, ncols, seq[i], tw, s, sms)) return -1;
     return 0;
 }
 

@@ -187,6 +187,27 @@ inline T shfl(T v, int src_lane) {
     return r;
 }
 
+// mma.sync.aligned.m8n8k4.row.col.f64: D(8x8) += A(8x4) * B(4x8); lane holds A[lane>>2][lane&3], B[lane&3][lane>>2],
+// C[lane>>2][2*(lane&3) + {0,1}]  (PTX ISA fragment layout).
+inline void mma884(double& c0, double& c1, double a, double b) {
+    Block* blk = cur_block();
+    Fiber& f = cur_fiber();
+    const int w = f.lin / 32, l = f.lin % 32;
+    memcpy(blk->xchg[w][l], &a, 8);
+    memcpy(blk->xchg[w][l] + 8, &b, 8);
+    yield_state(2);
+    const int row = l >> 2, tig = l & 3;
+    for (int k = 0; k < 4; ++k) {
+        double av, b0, b1;
+        memcpy(&av, blk->xchg[w][row * 4 + k], 8);
+        memcpy(&b0, blk->xchg[w][(2 * tig) * 4 + k] + 8, 8);
+        memcpy(&b1, blk->xchg[w][(2 * tig + 1) * 4 + k] + 8, 8);
+        c0 += av * b0;
+        c1 += av * b1;
+    }
+    yield_state(2);
+}
+
 }  // namespace pcbemu
 
 #define threadIdx (pcbemu::cur_fiber().tid)
