@@ -225,16 +225,16 @@ k_gram2(PcbColList S, PcbColList HS, int n, int nt, long long R, cplx* __restric
         sm[(size_t)buf * matElems + (size_t)(n + rem / PCB_GM_LD) * PCB_GM_LD + rem % PCB_GM_LD] = cmake(0.0, 0.0);
     }
     const long long ntiles = (R + PCB_GM_TR - 1) / PCB_GM_TR;
-    auto load_tile = [&](long long t, int stage) {
-        const long long r0 = t * PCB_GM_TR;
-        for (int idx = tid; idx < 2 * n * PCB_GM_TR; idx += nthr) {
-            const int which = idx / (n * PCB_GM_TR), rem = idx % (n * PCB_GM_TR);
-            const int c = rem / PCB_GM_TR, rr = rem % PCB_GM_TR;
-            const long long r = r0 + rr;
-            cplx* dst = sm + (size_t)(stage * 2 + which) * matElems + (size_t)c * PCB_GM_LD + rr;
-            const cplx* src = which ? HS.p[c] : S.p[c];
-            if (src != nullptr && r < R) pcb_cp16(dst, src + r);
-            else *dst = cmake(0.0, 0.0);
+    auto load_tile = [&](long long t, int stage) {      // warp per column, lane per row (PCB_GM_TR == 32): no index arithmetic
+        const long long r = t * PCB_GM_TR + lane;
+        cplx* d0 = sm + (size_t)(stage * 2) * matElems + lane;
+        for (int c = warp; c < n; c += W) {
+            const cplx* sp = S.p[c];
+            const cplx* hp = HS.p[c];
+            cplx* ds = d0 + (size_t)c * PCB_GM_LD;
+            cplx* dh = ds + matElems;
+            if (sp != nullptr && r < R) { pcb_cp16(ds, sp + r); pcb_cp16(dh, hp + r); }
+            else { *ds = cmake(0.0, 0.0); *dh = cmake(0.0, 0.0); }
         }
         pcb_cp_commit();
     };
@@ -253,6 +253,7 @@ k_gram2(PcbColList S, PcbColList HS, int n, int nt, long long R, cplx* __restric
                 const double* pa = s0 + (size_t)(ta[i] * 8 + g) * (2 * PCB_GM_LD);
                 const double* pb = s0 + (size_t)(tb[i] * 8 + g) * (2 * PCB_GM_LD);
                 const double* ph = h0 + (size_t)(tb[i] * 8 + g) * (2 * PCB_GM_LD);
+                PCB_UNROLL
                 for (int step = 0; step < PCB_GM_TR / 2; ++step) {
                     const int o = 4 * step + tig, os = 4 * step + (tig ^ 1);
                     const double a = pa[o];
@@ -317,36 +318,41 @@ k_update(PcbColList Sin, PcbColList HSin, PcbColListW Xout, PcbColListW HXout, P
     constexpr int LD = PcbUpd<TR>::LD;
     PCB_DYN_SMEM(cplx, sm);
     const int nl = kx + kp;
-    cplx* sE = sm;                                   // [nl][MPp]
-    cplx* sT = sE + (size_t)nl * MPp;                // [2 stages][2: S, HS][nl][LD]
+    const int LDE = 2 * MPp;                         // doubles per row of the real-expanded E (MPp = MP + 2: LDE mod 16 == 4)
+    double* sEr = reinterpret_cast<double*>(sm);     // [2 nl][LDE]: row 2k = (Re E_k., Im E_k.), row 2k+1 = (-Im E_k., Re E_k.)
+    cplx* sT = sm + (size_t)2 * nl * MPp;            // [2 stages][2: S, HS][nl][LD]
     const size_t matElems = (size_t)nl * LD;
     const int tid = threadIdx.x, nthr = blockDim.x;
-    const int warp = tid >> 5, lane = tid & 31;
+    const int warp = tid >> 5, lane = tid & 31, W = nthr >> 5;
     const int g = lane >> 2, tig = lane & 3;
     constexpr int RT = TR / 8;
     const int rt = warp % RT, jp = warp / RT;
-    for (int i = tid; i < nl * MPp; i += nthr) sE[i] = E[i];
+    for (int i = tid; i < nl * MPp; i += nthr) {
+        const cplx e = E[i];
+        const int k = i / MPp, j = i % MPp;
+        sEr[(size_t)(2 * k) * LDE + 2 * j] = e.x;       sEr[(size_t)(2 * k) * LDE + 2 * j + 1] = e.y;
+        sEr[(size_t)(2 * k + 1) * LDE + 2 * j] = -e.y;  sEr[(size_t)(2 * k + 1) * LDE + 2 * j + 1] = e.x;
+    }
     const long long ntiles = (R + TR - 1) / TR;
-    auto load_tile = [&](long long t, int stage) {
-        const long long r0 = t * TR;
-        for (int idx = tid; idx < 2 * nl * TR; idx += nthr) {
-            const int which = idx / (nl * TR), rem = idx % (nl * TR);
-            const int c = rem / TR, rr = rem % TR;
-            const long long r = r0 + rr;
-            cplx* dst = sT + (size_t)(stage * 2 + which) * matElems + (size_t)c * LD + rr;
-            const cplx* src = which ? HSin.p[c] : Sin.p[c];
-            if (src != nullptr && r < R) pcb_cp16(dst, src + r);
-            else *dst = cmake(0.0, 0.0);
+    auto load_tile = [&](long long t, int stage) {      // TR lanes of a warp per column (two columns per trip when TR == 16)
+        constexpr int CPW = 32 / TR;
+        const int sub = lane / TR, rr = lane % TR;
+        const long long r = t * TR + rr;
+        cplx* d0 = sT + (size_t)(stage * 2) * matElems + rr;
+        for (int c = warp * CPW + sub; c < nl; c += W * CPW) {
+            const cplx* sp = Sin.p[c];
+            const cplx* hp = HSin.p[c];
+            cplx* ds = d0 + (size_t)c * LD;
+            cplx* dh = ds + matElems;
+            if (sp != nullptr && r < R) { pcb_cp16(ds, sp + r); pcb_cp16(dh, hp + r); }
+            else { *ds = cmake(0.0, 0.0); *dh = cmake(0.0, 0.0); }
         }
         pcb_cp_commit();
     };
-    // B-fragment addressing (constant per lane): element (k + (tig>>1), j + (g>>1)), component (g&1)^(tig&1), sign
-    const int bk = tig >> 1, bcomp = (g & 1) ^ (tig & 1);
-    const double bsign = ((tig & 1) && !(g & 1)) ? -1.0 : 1.0;
-    const double* sEd = reinterpret_cast<const double*>(sE);
     long long t = blockIdx.x;
     int stage = 0;
     if (t < ntiles) load_tile(t, 0);
+    const double* bbase = sEr + (size_t)tig * LDE + 8 * (2 * jp) + g;     // B fragment: row 2k + tig, column 8 jt + g
     for (; t < ntiles; t += gridDim.x) {
         const long long tn = t + gridDim.x;
         if (tn < ntiles) { load_tile(tn, stage ^ 1); pcb_cp_wait<1>(); } else { pcb_cp_wait<0>(); }
@@ -360,21 +366,23 @@ k_update(PcbColList Sin, PcbColList HSin, PcbColListW Xout, PcbColListW HXout, P
             for (int j = 0; j < 2; ++j) acc[q][j][0] = acc[q][j][1] = 0.0;
         }
         const long long r = t * TR + rt * 8 + g;
-        const int aoff = (rt * 8 + g) * 2 + (tig & 1);
+        // A fragment: element (row rt*8 + g, column k + (tig>>1)), component tig&1
+        const int aoff = (tig >> 1) * (2 * LD) + (rt * 8 + g) * 2 + (tig & 1);
         PCB_UNROLL
         for (int part = 0; part < 2; ++part) {
             const int k0 = part == 0 ? kx : 0, k1 = part == 0 ? nl : kx;
+#ifndef PCB_EMU
+#pragma unroll 4
+#endif
             for (int k = k0; k < k1; k += 2) {
-                const int ka = k + (tig >> 1);
-                const double as = s0[(size_t)ka * (2 * LD) + aoff];
-                const double ah = h0[(size_t)ka * (2 * LD) + aoff];
-                PCB_UNROLL
-                for (int j = 0; j < 2; ++j) {
-                    const int jc = (2 * jp + j) * 4 + (g >> 1);
-                    const double b = bsign * sEd[((size_t)(k + bk) * MPp + jc) * 2 + bcomp];
-                    pcb_dmma(acc[0][j][0], acc[0][j][1], as, b);
-                    pcb_dmma(acc[1][j][0], acc[1][j][1], ah, b);
-                }
+                const double as = s0[(size_t)k * (2 * LD) + aoff];
+                const double ah = h0[(size_t)k * (2 * LD) + aoff];
+                const double b0 = bbase[(size_t)(2 * k) * LDE];
+                const double b1 = bbase[(size_t)(2 * k) * LDE + 8];
+                pcb_dmma(acc[0][0][0], acc[0][0][1], as, b0);
+                pcb_dmma(acc[1][0][0], acc[1][0][1], ah, b0);
+                pcb_dmma(acc[0][1][0], acc[0][1][1], as, b1);
+                pcb_dmma(acc[1][1][0], acc[1][1][1], ah, b1);
             }
             if (r < R) {
                 PCB_UNROLL

@@ -561,9 +561,9 @@ int pcb_update(pcb_ctx* c, int m, int nl, void* const* s, void* const* hs, void*
     PCB_CUDA_OK(cudaMemcpyAsync(c->dsmall, he, sizeof(cplx) * nlp * MPp, cudaMemcpyHostToDevice, c->stream));
     const cplx* dE = (const cplx*)c->dsmall;
     // rows per tile: 32 when the double-buffered stage fits in shared memory, else 16
-    const size_t smem32 = sizeof(cplx) * ((size_t)nlp * MPp + 4 * (size_t)nlp * PcbUpd<32>::LD);
-    const size_t smem16 = sizeof(cplx) * ((size_t)nlp * MPp + 4 * (size_t)nlp * PcbUpd<16>::LD);
-    const bool big = smem32 <= (size_t)200 * 1024;
+    const size_t smem32 = sizeof(cplx) * (2 * (size_t)nlp * MPp + 4 * (size_t)nlp * PcbUpd<32>::LD);
+    const size_t smem16 = sizeof(cplx) * (2 * (size_t)nlp * MPp + 4 * (size_t)nlp * PcbUpd<16>::LD);
+    const bool big = smem32 <= (size_t)224 * 1024;
     const int TR = big ? 32 : 16;
     const size_t smem = big ? smem32 : smem16;
     const int warps = (TR / 8) * (JT / 2);

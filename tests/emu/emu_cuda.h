@@ -13,7 +13,6 @@
 #error "emu_cuda.h is only for the PCB_EMU host-emulation build"
 #endif
 
-#include <ucontext.h>
 #include <chrono>
 #include <cmath>
 #include <cstdint>
@@ -50,8 +49,22 @@ enum { cudaStreamNonBlocking = 1 };
 
 namespace pcbemu {
 
+// Minimal x86-64 cooperative context switch (callee-saved registers + stack pointer); ucontext's swapcontext makes a
+// signal-mask system call per switch, which dominated the emulation time.
+#if !defined(__x86_64__)
+#error "tests/emu needs x86-64"
+#endif
+__attribute__((naked, noinline)) static void ctx_switch(void** /*save_sp: rdi*/, void* /*load_sp: rsi*/) {
+    asm volatile(
+        "pushq %rbp\n pushq %rbx\n pushq %r12\n pushq %r13\n pushq %r14\n pushq %r15\n"
+        "movq %rsp, (%rdi)\n"
+        "movq %rsi, %rsp\n"
+        "popq %r15\n popq %r14\n popq %r13\n popq %r12\n popq %rbx\n popq %rbp\n"
+        "ret\n");
+}
+
 struct Fiber {
-    ucontext_t ctx;
+    void* sp = nullptr;
     char* stack = nullptr;
     uint3 tid;
     int lin = 0;            // linear thread index in block
@@ -60,7 +73,7 @@ struct Fiber {
 
 struct Block {
     std::vector<Fiber> fibers;
-    ucontext_t sched;
+    void* sched_sp = nullptr;
     std::function<void()> body;
     uint3 bid;
     dim3 bdim, gdim;
@@ -77,7 +90,7 @@ inline void yield_state(int st) {
     Block* b = cur_block();
     Fiber& f = b->fibers[b->cur];
     f.state = st;
-    swapcontext(&f.ctx, &b->sched);
+    ctx_switch(&f.sp, b->sched_sp);
 }
 
 inline void fiber_entry() {
@@ -85,7 +98,8 @@ inline void fiber_entry() {
     b->body();
     Fiber& f = b->fibers[b->cur];
     f.state = 3;
-    swapcontext(&f.ctx, &b->sched);
+    ctx_switch(&f.sp, b->sched_sp);
+    abort();   // a finished fiber is never resumed
 }
 
 static const size_t kStack = 512 * 1024;
@@ -95,12 +109,16 @@ inline void run_block(Block& b) {
     const int nt = (int)b.fibers.size();
     for (int i = 0; i < nt; ++i) {
         Fiber& f = b.fibers[i];
-        getcontext(&f.ctx);
-        f.ctx.uc_stack.ss_sp = f.stack;
-        f.ctx.uc_stack.ss_size = kStack;
-        f.ctx.uc_link = &b.sched;
+        // initial frame: six zeroed callee-saved slots, then the entry point as the "return address" (16-byte aligned
+        // slot, so that the stack is misaligned by 8 at function entry exactly as after a call)
+        uintptr_t top = ((uintptr_t)f.stack + kStack) & ~(uintptr_t)15;
+        void** frame = (void**)(top - 16);       // [0] = return address slot, [1] = padding
+        frame[0] = (void*)&fiber_entry;
+        frame[1] = nullptr;
+        void** sp = frame - 6;
+        for (int q = 0; q < 6; ++q) sp[q] = nullptr;
+        f.sp = sp;
         f.state = 0;
-        makecontext(&f.ctx, (void (*)())fiber_entry, 0);
     }
     for (;;) {
         bool progressed = false;
@@ -109,7 +127,7 @@ inline void run_block(Block& b) {
             Fiber& f = b.fibers[i];
             if (f.state == 0) {
                 b.cur = i;
-                swapcontext(&b.sched, &f.ctx);
+                ctx_switch(&b.sched_sp, f.sp);
                 progressed = true;
             }
             if (f.state == 3) ++done;

@@ -48,8 +48,8 @@ def test_lobpcg_vs_reference_golden(pcb, oracle, golden):
         assert np.allclose(info[2:], ref_hist, rtol=2e-3, atol=0), key   # rounding differences amplify along the iteration
         w_pnt, w_re = pcb.numerical_experiments.recompute_normalize_print(lam[:nev], x[:, :nev], A, shift)
         res = pcb.numerical_experiments.recompute_normalize_print.last_residuals
-        assert np.allclose(w_re, z[key + "_wre"], rtol=0, atol=1e-9), key
-        assert np.allclose(w_pnt, z[key + "_wpnt"], rtol=0, atol=1e-9), key
+        assert np.allclose(w_re, z[key + "_wre"], rtol=0, atol=2e-8), key     # omega = sqrt(lambda): zero modes (lambda ~ 1e-13) are ill-conditioned
+        assert np.allclose(w_pnt, z[key + "_wpnt"], rtol=0, atol=2e-8), key
         assert np.all(res[:nev] < 50 * case["tol"]), key    # A-residuals (without penalty) stay at tolerance level
         ran += 1
     assert ran > 0
