@@ -93,8 +93,14 @@ PCB_D void pcb_xtile_load(cplx* __restrict__ st, const cplx* __restrict__ X, lon
     }
 }
 
+// slot of grid point (r, i0) of component c in an x-tile stage
+template <class P, int LX>
+PCB_HD int pcb_xslot(int c, int r, int i0) {
+    return ((c * LX + r) * P::R1 + i0 / P::R2) * P::R2P + i0 % P::R2;
+}
+
 template <class P, int LX, int NT, int SYM>
-__global__ void __launch_bounds__(NT) k_xfwd(PcbOp op, PcbCols cols, const cplx* __restrict__ tw, int ncols) {
+__global__ void __launch_bounds__(NT, 2) k_xfwd(PcbOp op, PcbCols cols, const cplx* __restrict__ tw, int ncols) {
     constexpr int N = P::N, R1 = P::R1, R2 = P::R2, R2P = P::R2P;
     constexpr int STAGE = 3 * LX * R1 * R2P;
     PCB_DYN_SMEM(cplx, sm);   // [2 stages][3][LX][R1][R2P]
@@ -123,63 +129,49 @@ __global__ void __launch_bounds__(NT) k_xfwd(PcbOp op, PcbCols cols, const cplx*
         cplx* __restrict__ Y = cols.out[tile / tpc];
         const int row0 = (tile % tpc) * LX;
 
-        for (int item = tid; item < LX * R2; item += NT) {
-            const int r = item / R2, n2 = item % R2;
-            const int row = row0 + r;
-            if (row >= nrows) continue;
-            const int i1 = row % N, i2 = row / N;
-            cplx v[3][R1];
-            cplx kc[3];
-            if (SYM) {
+        if (SYM) {   // point-wise: v <- (-conj k) x v, all threads
+            for (int e = tid; e < LX * N; e += NT) {
+                const int r = e / N, i0 = e % N;
+                const int row = row0 + r;
+                if (row >= nrows) continue;
+                const Sym3 sy = pcb_symbol(op.T, N, i0, row % N, row / N);
+                cplx a[3], x[3], z[3];
                 PCB_UNROLL
                 for (int c = 0; c < 3; ++c) {
-                    const cplx b = __ldg(op.T + (c * 3 + 1) * N + i1);
-                    const cplx d = __ldg(op.T + (c * 3 + 2) * N + i2);
-                    kc[c] = cadd(b, d);
+                    a[c] = cmake(-sy.k[c].x, sy.k[c].y);
+                    x[c] = st[pcb_xslot<P, LX>(c, r, i0)];
                 }
-            }
-            PCB_UNROLL
-            for (int n1 = 0; n1 < R1; ++n1) {
-                cplx x[3];
+                pcb_cross(a, x, z);
                 PCB_UNROLL
-                for (int c = 0; c < 3; ++c) x[c] = st[((c * LX + r) * R1 + n1) * R2P + n2];
-                if (SYM) {
-                    const int i0 = n1 * R2 + n2;
-                    cplx a[3], z[3];
-                    PCB_UNROLL
-                    for (int c = 0; c < 3; ++c) {
-                        const cplx k = cadd(kc[c], __ldg(op.T + (c * 3 + 0) * N + i0));
-                        a[c] = cmake(-k.x, k.y);   // -conj(k)
-                    }
-                    pcb_cross(a, x, z);
-                    PCB_UNROLL
-                    for (int c = 0; c < 3; ++c) v[c][n1] = z[c];
-                } else {
-                    PCB_UNROLL
-                    for (int c = 0; c < 3; ++c) v[c][n1] = x[c];
-                }
+                for (int c = 0; c < 3; ++c) st[pcb_xslot<P, LX>(c, r, i0)] = z[c];
             }
+            __syncthreads();
+        }
+        // radix R1 over n1 (fixed n2), twiddle, in place
+        for (int item = tid; item < 3 * LX * R2; item += NT) {
+            const int n2 = item % R2, cr = item / R2;          // cr = c*LX + r
+            if (row0 + cr % LX >= nrows) continue;
+            cplx v[R1];
             PCB_UNROLL
-            for (int c = 0; c < 3; ++c) {
-                Dft<R1, -1>::run(v[c]);
-                PCB_UNROLL
-                for (int k1 = 0; k1 < R1; ++k1) {
-                    cplx val = v[c][k1];
-                    if (k1 > 0) val = cmul(val, __ldg(tw + k1 * R2 + n2));
-                    st[((c * LX + r) * R1 + k1) * R2P + n2] = val;
-                }
+            for (int n1 = 0; n1 < R1; ++n1) v[n1] = st[(cr * R1 + n1) * R2P + n2];
+            Dft<R1, -1>::run(v);
+            PCB_UNROLL
+            for (int k1 = 0; k1 < R1; ++k1) {
+                cplx val = v[k1];
+                if (k1 > 0) val = cmul(val, __ldg(tw + k1 * R2 + n2));
+                st[(cr * R1 + k1) * R2P + n2] = val;
             }
         }
         __syncthreads();
+        // radix R2 over n2 (fixed k1) and store: k = k1 + R1*k2
         for (int item = tid; item < 3 * LX * R1; item += NT) {
-            const int k1 = item % R1;
-            const int r = (item / R1) % LX;
-            const int c = item / (R1 * LX);
+            const int k1 = item % R1, cr = item / R1;
+            const int r = cr % LX, c = cr / LX;
             const int row = row0 + r;
             if (row >= nrows) continue;
             cplx v[R2];
             PCB_UNROLL
-            for (int n2 = 0; n2 < R2; ++n2) v[n2] = st[((c * LX + r) * R1 + k1) * R2P + n2];
+            for (int n2 = 0; n2 < R2; ++n2) v[n2] = st[(cr * R1 + k1) * R2P + n2];
             Dft<R2, -1>::run(v);
             cplx* __restrict__ dst = Y + c * nn + (long long)row * N + k1;
             PCB_UNROLL
@@ -192,15 +184,15 @@ __global__ void __launch_bounds__(NT) k_xfwd(PcbOp op, PcbCols cols, const cplx*
 
 // ---------------------------------------------------------------------------------------
 // Pass 5: x-lines inverse.  MODE 0: plain IFFT * 1/N^3;  1: A = K_A . ;  2: H = K_A . + gamma K_B x + shift x
-// Reads the work column W (Fourier-x order), the source column X (MODE 2, staged by cp.async while the radix-R2 step
-// runs) and writes OUT (= W's column: each tile only touches its own rows).  Same persistent double-buffered structure.
+// Reads the work column W (Fourier-x order) through the cp.async stages, transforms in place, then a point-wise phase
+// (all threads, fully coalesced) applies 1/N^3, k x v and -- MODE 2 -- adds gamma conj(k)(k.x) + shift x with X read
+// straight from global memory, and stores to OUT (= W's column: each tile only touches its own rows).
 // ---------------------------------------------------------------------------------------
 template <class P, int LX, int NT, int MODE>
-__global__ void __launch_bounds__(NT) k_xinv(PcbOp op, PcbCols cols, const cplx* __restrict__ tw, int ncols) {
+__global__ void __launch_bounds__(NT, 2) k_xinv(PcbOp op, PcbCols cols, const cplx* __restrict__ tw, int ncols) {
     constexpr int N = P::N, R1 = P::R1, R2 = P::R2, R2P = P::R2P;
     constexpr int STAGE = 3 * LX * R1 * R2P;
-    PCB_DYN_SMEM(cplx, sm);   // [2 stages][3][LX][R1][R2P] (+ [3][LX][R1][R2P] for X when MODE == 2)
-    cplx* __restrict__ xs = sm + 2 * STAGE;
+    PCB_DYN_SMEM(cplx, sm);   // [2 stages][3][LX][R1][R2P]
     const long long nn = op.nn;
     const int nrows = N * N;
     const int tpc = (nrows + LX - 1) / LX;
@@ -215,96 +207,81 @@ __global__ void __launch_bounds__(NT) k_xinv(PcbOp op, PcbCols cols, const cplx*
     for (; tile < total; tile += gridDim.x) {
         const int next = tile + gridDim.x;
         const int row0 = (tile % tpc) * LX;
-        int pending = 0;
-        if (MODE == 2) {
-            pcb_xtile_load<P, LX>(xs, cols.in[tile / tpc], nn, row0, nrows, tid, NT, false);
-            pcb_cp_commit();
-            ++pending;
-        }
         if (next < total) {
             pcb_xtile_load<P, LX>(sm + (stage ^ 1) * STAGE, cols.out[next / tpc], nn, (next % tpc) * LX, nrows, tid, NT, true);
             pcb_cp_commit();
-            ++pending;
+            pcb_cp_wait<1>();
+        } else {
+            pcb_cp_wait<0>();
         }
-        // groups in flight, oldest first: W(tile) | X(tile) | W(next)  ->  W(tile) must have landed
-        if (pending == 2) pcb_cp_wait<2>(); else if (pending == 1) pcb_cp_wait<1>(); else pcb_cp_wait<0>();
         __syncthreads();
         cplx* __restrict__ st = sm + stage * STAGE;
+        const cplx* __restrict__ X = cols.in[tile / tpc];
         cplx* __restrict__ W = cols.out[tile / tpc];
 
+        // inverse radix R2 over k2 (fixed k1), conjugate twiddle, in place
         for (int item = tid; item < 3 * LX * R1; item += NT) {
-            const int k1 = item % R1;
-            const int r = (item / R1) % LX;
-            const int c = item / (R1 * LX);
-            if (row0 + r >= nrows) continue;
+            const int k1 = item % R1, cr = item / R1;
+            if (row0 + cr % LX >= nrows) continue;
             cplx v[R2];
             PCB_UNROLL
-            for (int k2 = 0; k2 < R2; ++k2) v[k2] = st[((c * LX + r) * R1 + k1) * R2P + k2];
+            for (int k2 = 0; k2 < R2; ++k2) v[k2] = st[(cr * R1 + k1) * R2P + k2];
             Dft<R2, +1>::run(v);
             PCB_UNROLL
             for (int n2 = 0; n2 < R2; ++n2) {
                 cplx val = v[n2];
                 if (k1 > 0) { const cplx t = __ldg(tw + k1 * R2 + n2); val = cmul(val, cmake(t.x, -t.y)); }
-                st[((c * LX + r) * R1 + k1) * R2P + n2] = val;
+                st[(cr * R1 + k1) * R2P + n2] = val;
             }
         }
-        if (MODE == 2) { if (next < total) pcb_cp_wait<1>(); else pcb_cp_wait<0>(); }   // X(tile) has landed
         __syncthreads();
-        for (int item = tid; item < LX * R2; item += NT) {
-            const int r = item / R2, n2 = item % R2;
+        // inverse radix R1 over k1 (fixed n2), in place: slot (n1, n2) <-> i0 = n1*R2 + n2
+        for (int item = tid; item < 3 * LX * R2; item += NT) {
+            const int n2 = item % R2, cr = item / R2;
+            if (row0 + cr % LX >= nrows) continue;
+            cplx v[R1];
+            PCB_UNROLL
+            for (int k1 = 0; k1 < R1; ++k1) v[k1] = st[(cr * R1 + k1) * R2P + n2];
+            Dft<R1, +1>::run(v);
+            PCB_UNROLL
+            for (int n1 = 0; n1 < R1; ++n1) st[(cr * R1 + n1) * R2P + n2] = v[n1];
+        }
+        __syncthreads();
+        // point-wise epilogue and store
+        for (int e = tid; e < LX * N; e += NT) {
+            const int r = e / N, i0 = e % N;
             const int row = row0 + r;
             if (row >= nrows) continue;
-            const int i1 = row % N, i2 = row / N;
-            cplx v[3][R1];
-            PCB_UNROLL
-            for (int c = 0; c < 3; ++c) {
+            const long long g = (long long)row * N + i0;
+            cplx x[3];
+            if (MODE == 2) {
                 PCB_UNROLL
-                for (int k1 = 0; k1 < R1; ++k1) v[c][k1] = st[((c * LX + r) * R1 + k1) * R2P + n2];
-                Dft<R1, +1>::run(v[c]);
+                for (int c = 0; c < 3; ++c) x[c] = X[c * nn + g];
             }
-            cplx kc[3];
+            cplx u[3], z[3];
+            PCB_UNROLL
+            for (int c = 0; c < 3; ++c) u[c] = cscale(st[pcb_xslot<P, LX>(c, r, i0)], op.inv_n3);
             if (MODE) {
-                PCB_UNROLL
-                for (int c = 0; c < 3; ++c) {
-                    const cplx b = __ldg(op.T + (c * 3 + 1) * N + i1);
-                    const cplx d = __ldg(op.T + (c * 3 + 2) * N + i2);
-                    kc[c] = cadd(b, d);
+                const Sym3 sy = pcb_symbol(op.T, N, i0, row % N, row / N);
+                pcb_cross(sy.k, u, z);
+                if (MODE == 2) {
+                    // gamma K_B x = gamma conj(k) (k . x)   (h_block with D_B, pcfft.py:176)
+                    cplx dot = cadd(cadd(cmul(sy.k[0], x[0]), cmul(sy.k[1], x[1])), cmul(sy.k[2], x[2]));
+                    dot = cscale(dot, op.gamma);
+                    PCB_UNROLL
+                    for (int c = 0; c < 3; ++c) {
+                        cplx t = cfmac(sy.k[c], dot, z[c]);
+                        t.x = fma(op.shift, x[c].x, t.x);
+                        t.y = fma(op.shift, x[c].y, t.y);
+                        z[c] = t;
+                    }
                 }
+            } else {
+                PCB_UNROLL
+                for (int c = 0; c < 3; ++c) z[c] = u[c];
             }
             PCB_UNROLL
-            for (int n1 = 0; n1 < R1; ++n1) {
-                const int i0 = n1 * R2 + n2;
-                const long long e = (long long)row * N + i0;
-                cplx u[3], z[3];
-                PCB_UNROLL
-                for (int c = 0; c < 3; ++c) u[c] = cscale(v[c][n1], op.inv_n3);
-                if (MODE) {
-                    cplx k[3];
-                    PCB_UNROLL
-                    for (int c = 0; c < 3; ++c) k[c] = cadd(kc[c], __ldg(op.T + (c * 3 + 0) * N + i0));
-                    pcb_cross(k, u, z);
-                    if (MODE == 2) {
-                        cplx x[3];
-                        PCB_UNROLL
-                        for (int c = 0; c < 3; ++c) x[c] = xs[((c * LX + r) * R1 + n1) * R2P + n2];
-                        // gamma K_B x = gamma conj(k) (k . x)   (h_block with D_B, pcfft.py:176)
-                        cplx dot = cadd(cadd(cmul(k[0], x[0]), cmul(k[1], x[1])), cmul(k[2], x[2]));
-                        dot = cscale(dot, op.gamma);
-                        PCB_UNROLL
-                        for (int c = 0; c < 3; ++c) {
-                            cplx t = cfmac(k[c], dot, z[c]);
-                            t.x = fma(op.shift, x[c].x, t.x);
-                            t.y = fma(op.shift, x[c].y, t.y);
-                            z[c] = t;
-                        }
-                    }
-                } else {
-                    PCB_UNROLL
-                    for (int c = 0; c < 3; ++c) z[c] = u[c];
-                }
-                PCB_UNROLL
-                for (int c = 0; c < 3; ++c) W[c * nn + e] = z[c];
-            }
+            for (int c = 0; c < 3; ++c) W[c * nn + g] = z[c];
         }
         __syncthreads();
         stage ^= 1;
@@ -397,7 +374,7 @@ PCB_D void pcb_ztile_load(cplx* __restrict__ st, const cplx* __restrict__ Y, lon
 }
 
 template <class P, int DIEL, int NT>
-__global__ void __launch_bounds__(NT) k_zmid(PcbOp op, PcbCols cols, const cplx* __restrict__ tw, int ncols) {
+__global__ void __launch_bounds__(NT, (DIEL == 2 ? 1 : 2)) k_zmid(PcbOp op, PcbCols cols, const cplx* __restrict__ tw, int ncols) {
     constexpr int N = P::N, R1 = P::R1, R2 = P::R2;
     constexpr int STAGE = 3 * N * 8;
     PCB_DYN_SMEM(cplx, sm);   // [2 stages][3][N][8]

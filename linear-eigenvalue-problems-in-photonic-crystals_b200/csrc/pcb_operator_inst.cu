@@ -10,13 +10,14 @@
 namespace {
 
 typedef Plan<PCB_N, PCB_R1, PCB_R2> P;
-constexpr int NT = 128;
+constexpr int NT = 128;      // y lines and split z passes (one CTA per tile)
+constexpr int NTP = 256;     // persistent x / z-mid kernels
 constexpr int kRowBytes = 3 * P::R1 * P::R2P * (int)sizeof(cplx);
 constexpr int LX = (8 * kRowBytes <= 65536) ? 8 : (4 * kRowBytes <= 65536) ? 4 : (2 * kRowBytes <= 65536) ? 2 : 1;
 constexpr int kStageX = LX * kRowBytes;               // one x-tile (three components)
 constexpr int kSmemXF = 2 * kStageX;                    // forward: two stages
 constexpr int kSmemXI = 2 * kStageX;                    // inverse modes 0/1
-constexpr int kSmemXH = 3 * kStageX;                    // inverse mode 2: + staged X tile
+constexpr int kSmemXH = 2 * kStageX;                    // inverse mode 2 reads X straight from global in its point-wise phase
 constexpr int kSmemL = 3 * P::N * 8 * (int)sizeof(cplx);
 constexpr int kSmemZ = 2 * kSmemL;                       // two stages
 
@@ -50,7 +51,7 @@ inline int ctas_per_sm(int smem, int regs_hint_threads) {
         const long long tot = (long long)(TILES) * ncols;                           \
         if (gx > tot) gx = tot;                                                     \
         dim3 grid((unsigned)gx, 1, 1);                                              \
-        PCB_LAUNCH(kfn, grid, dim3(NT, 1, 1), (size_t)(SMEM), s, op, cols, tw, ncols); \
+        PCB_LAUNCH(kfn, grid, dim3(NTP, 1, 1), (size_t)(SMEM), s, op, cols, tw, ncols); \
         PCB_CUDA_OK(cudaGetLastError());                                            \
     } while (0)
 
@@ -59,19 +60,19 @@ constexpr int GL = ((P::N + 7) / 8) * P::N;              // strided-line tiles p
 
 int run_pass(const PcbOp& op, const PcbCols& cols, int ncols, int pass_id, const cplx* tw, cudaStream_t s, int sms) {
     switch (pass_id) {
-        case PCB_PASS_XFWD_SYM: PCB_GO_P((k_xfwd<P, LX, NT, 1>), GX, kSmemXF, 3); break;
-        case PCB_PASS_XFWD:     PCB_GO_P((k_xfwd<P, LX, NT, 0>), GX, kSmemXF, 3); break;
+        case PCB_PASS_XFWD_SYM: PCB_GO_P((k_xfwd<P, LX, NTP, 1>), GX, kSmemXF, 2); break;
+        case PCB_PASS_XFWD:     PCB_GO_P((k_xfwd<P, LX, NTP, 0>), GX, kSmemXF, 2); break;
         case PCB_PASS_YFWD:     PCB_GO((k_line<P, 1, -1, NT>), GL, kSmemL); break;
         case PCB_PASS_ZFWD:     PCB_GO((k_line<P, 2, -1, NT>), GL, kSmemL); break;
         case PCB_PASS_ZINV:     PCB_GO((k_line<P, 2, +1, NT>), GL, kSmemL); break;
         case PCB_PASS_YINV:     PCB_GO((k_line<P, 1, +1, NT>), GL, kSmemL); break;
-        case PCB_PASS_XINV:     PCB_GO_P((k_xinv<P, LX, NT, 0>), GX, kSmemXI, 3); break;
-        case PCB_PASS_XINV_A:   PCB_GO_P((k_xinv<P, LX, NT, 1>), GX, kSmemXI, 3); break;
-        case PCB_PASS_XINV_H:   PCB_GO_P((k_xinv<P, LX, NT, 2>), GX, kSmemXH, 3); break;
+        case PCB_PASS_XINV:     PCB_GO_P((k_xinv<P, LX, NTP, 0>), GX, kSmemXI, 2); break;
+        case PCB_PASS_XINV_A:   PCB_GO_P((k_xinv<P, LX, NTP, 1>), GX, kSmemXI, 2); break;
+        case PCB_PASS_XINV_H:   PCB_GO_P((k_xinv<P, LX, NTP, 2>), GX, kSmemXH, 2); break;
         case PCB_PASS_ZMID:
-            if (op.diel == PCB_DIEL_NONE) PCB_GO_P((k_zmid<P, 0, NT>), GL, kSmemZ, 4);
-            else if (op.diel == PCB_DIEL_CHIRAL) PCB_GO_P((k_zmid<P, 1, NT>), GL, kSmemZ, 4);
-            else if (op.diel == PCB_DIEL_TRIVIAL) PCB_GO_P((k_zmid<P, 2, NT>), GL, kSmemZ, 2);
+            if (op.diel == PCB_DIEL_NONE) PCB_GO_P((k_zmid<P, 0, NTP>), GL, kSmemZ, 2);
+            else if (op.diel == PCB_DIEL_CHIRAL) PCB_GO_P((k_zmid<P, 1, NTP>), GL, kSmemZ, 2);
+            else if (op.diel == PCB_DIEL_TRIVIAL) PCB_GO_P((k_zmid<P, 2, NTP>), GL, kSmemZ, 2);
             else { pcb_set_error("zmid: dielectric type %d has no fused z pass", op.diel); return -1; }
             break;
         default: pcb_set_error("unknown pass id %d", pass_id); return -1;
