@@ -311,7 +311,7 @@ struct PcbUpd {
     static constexpr int LD = TR + 4;      // complex; LD*16 mod 128 == 64: the two k-columns of an A fragment hit disjoint banks
 };
 
-template <int TR>
+template <int TR, int JW>   // JW = output column tiles (of 4 complex columns) per warp
 __global__ void __launch_bounds__(512, 1)
 k_update(PcbColList Sin, PcbColList HSin, PcbColListW Xout, PcbColListW HXout, PcbColListW Pout, PcbColListW HPout,
          const cplx* __restrict__ E, int m, int kx, int kp, int MPp, long long R) {
@@ -326,7 +326,7 @@ k_update(PcbColList Sin, PcbColList HSin, PcbColListW Xout, PcbColListW HXout, P
     const int warp = tid >> 5, lane = tid & 31, W = nthr >> 5;
     const int g = lane >> 2, tig = lane & 3;
     constexpr int RT = TR / 8;
-    const int rt = warp % RT, jp = warp / RT;
+    const int rt = warp % RT, jp = warp / RT;      // warp (rt, jp): rows rt*8.., column tiles JW*jp ..
     for (int i = tid; i < nl * MPp; i += nthr) {
         const cplx e = E[i];
         const int k = i / MPp, j = i % MPp;
@@ -352,18 +352,18 @@ k_update(PcbColList Sin, PcbColList HSin, PcbColListW Xout, PcbColListW HXout, P
     long long t = blockIdx.x;
     int stage = 0;
     if (t < ntiles) load_tile(t, 0);
-    const double* bbase = sEr + (size_t)tig * LDE + 8 * (2 * jp) + g;     // B fragment: row 2k + tig, column 8 jt + g
+    const double* bbase = sEr + (size_t)tig * LDE + 8 * (JW * jp) + g;    // B fragment: row 2k + tig, column 8 jt + g
     for (; t < ntiles; t += gridDim.x) {
         const long long tn = t + gridDim.x;
         if (tn < ntiles) { load_tile(tn, stage ^ 1); pcb_cp_wait<1>(); } else { pcb_cp_wait<0>(); }
         __syncthreads();
         const double* s0 = reinterpret_cast<const double*>(sT + (size_t)(stage * 2) * matElems);
         const double* h0 = reinterpret_cast<const double*>(sT + (size_t)(stage * 2 + 1) * matElems);
-        double acc[2][2][2];     // [S|HS][j-tile][c0,c1]
+        double acc[2][JW][2];     // [S|HS][j-tile][c0,c1]
         PCB_UNROLL
         for (int q = 0; q < 2; ++q) {
             PCB_UNROLL
-            for (int j = 0; j < 2; ++j) acc[q][j][0] = acc[q][j][1] = 0.0;
+            for (int j = 0; j < JW; ++j) acc[q][j][0] = acc[q][j][1] = 0.0;
         }
         const long long r = t * TR + rt * 8 + g;
         // A fragment: element (row rt*8 + g, column k + (tig>>1)), component tig&1
@@ -377,17 +377,17 @@ k_update(PcbColList Sin, PcbColList HSin, PcbColListW Xout, PcbColListW HXout, P
             for (int k = k0; k < k1; k += 2) {
                 const double as = s0[(size_t)k * (2 * LD) + aoff];
                 const double ah = h0[(size_t)k * (2 * LD) + aoff];
-                const double b0 = bbase[(size_t)(2 * k) * LDE];
-                const double b1 = bbase[(size_t)(2 * k) * LDE + 8];
-                pcb_dmma(acc[0][0][0], acc[0][0][1], as, b0);
-                pcb_dmma(acc[1][0][0], acc[1][0][1], ah, b0);
-                pcb_dmma(acc[0][1][0], acc[0][1][1], as, b1);
-                pcb_dmma(acc[1][1][0], acc[1][1][1], ah, b1);
+                PCB_UNROLL
+                for (int j = 0; j < JW; ++j) {
+                    const double bj = bbase[(size_t)(2 * k) * LDE + 8 * j];
+                    pcb_dmma(acc[0][j][0], acc[0][j][1], as, bj);
+                    pcb_dmma(acc[1][j][0], acc[1][j][1], ah, bj);
+                }
             }
             if (r < R) {
                 PCB_UNROLL
-                for (int j = 0; j < 2; ++j) {
-                    const int jj = (2 * jp + j) * 4 + tig;
+                for (int j = 0; j < JW; ++j) {
+                    const int jj = (JW * jp + j) * 4 + tig;
                     if (jj < m) {
                         if (part == 0) {
                             Pout.p[jj][r] = cmake(acc[0][j][0], acc[0][j][1]);

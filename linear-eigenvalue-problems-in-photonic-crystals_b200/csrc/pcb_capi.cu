@@ -566,22 +566,25 @@ int pcb_update(pcb_ctx* c, int m, int nl, void* const* s, void* const* hs, void*
     const bool big = smem32 <= (size_t)224 * 1024;
     const int TR = big ? 32 : 16;
     const size_t smem = big ? smem32 : smem16;
-    const int warps = (TR / 8) * (JT / 2);
+    const int JW = ((TR / 8) * JT <= 16) ? 1 : 2;          // one column tile per warp while that keeps <= 16 warps per CTA
+    const int warps = (TR / 8) * (JT / JW);
     const long long ntiles = (c->R + TR - 1) / TR;
     int per_sm = (int)((size_t)224 * 1024 / (smem + 1024)); if (per_sm < 1) per_sm = 1; if (per_sm > 4) per_sm = 4;
     long long gx = (long long)c->sms * per_sm; if (gx > ntiles) gx = ntiles;
     dim3 grid((unsigned)gx, 1, 1), block((unsigned)(32 * warps), 1, 1);
-    if (big) {
 #ifndef PCB_EMU
-        if (smem > 48 * 1024) PCB_CUDA_OK(cudaFuncSetAttribute(k_update<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#define PCB_UPD_GO(K)                                                                                              \
+    do {                                                                                                           \
+        if (smem > 48 * 1024) PCB_CUDA_OK(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        PCB_LAUNCH(K, grid, block, smem, c->stream, Sin, HSin, X, HX, P, HP, dE, m, kx, kp, MPp, c->R);            \
+    } while (0)
+#else
+#define PCB_UPD_GO(K) PCB_LAUNCH(K, grid, block, smem, c->stream, Sin, HSin, X, HX, P, HP, dE, m, kx, kp, MPp, c->R)
 #endif
-        PCB_LAUNCH(k_update<32>, grid, block, smem, c->stream, Sin, HSin, X, HX, P, HP, dE, m, kx, kp, MPp, c->R);
-    } else {
-#ifndef PCB_EMU
-        if (smem > 48 * 1024) PCB_CUDA_OK(cudaFuncSetAttribute(k_update<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-#endif
-        PCB_LAUNCH(k_update<16>, grid, block, smem, c->stream, Sin, HSin, X, HX, P, HP, dE, m, kx, kp, MPp, c->R);
-    }
+    if (big && JW == 1) PCB_UPD_GO((k_update<32, 1>));
+    else if (big) PCB_UPD_GO((k_update<32, 2>));
+    else if (JW == 1) PCB_UPD_GO((k_update<16, 1>));
+    else PCB_UPD_GO((k_update<16, 2>));
     PCB_CUDA_OK(cudaGetLastError());
     c->launches++;
     return 0;

@@ -28,6 +28,8 @@ struct PcbCols {
     cplx* out[PCB_MAXC];        // destination / work columns
 };
 
+// occupancy hint of the x passes: ask for `want` CTAs/SM (caps registers) only where the tile is small enough to allow it
+constexpr int pcb_min_ctas(int stage_bytes, int r1, int want) { return (want * stage_bytes <= 200 * 1024 && r1 <= 8) ? want : 1; }
 constexpr int pcb_gcd(int a, int b) { return b == 0 ? a : pcb_gcd(b, a % b); }
 constexpr int pcb_modinv(int a, int m) {   // a^-1 mod m (m small)
     for (int x = 1; x < m; ++x) if ((a * x) % m == 1) return x;
@@ -75,202 +77,167 @@ template <int N> PCB_D void pcb_cp_wait() { asm volatile("cp.async.wait_group %0
 
 // ---------------------------------------------------------------------------------------
 // Pass 1: x-lines forward.  SYM: 0 plain FFT, 1 multiply by K_A^H = (-conj k) x . on load.
-// Persistent CTAs; a tile = LX consecutive rows (a row = all i0 for one (i1,i2)) x three components = 3 contiguous
-// chunks of LX*N elements.  Tile t+1 streams into the other shared-memory stage with cp.async while tile t is
-// transformed; the radix-R1 -> radix-R2 exchange happens IN PLACE in the stage ([c][row][n1|k1][n2], row stride R2P).
+// Tile = LX consecutive rows (a row = all i0 for one (i1,i2)), all three components; one CTA per tile, registers stage the
+// radix-R1 input, shared memory the exchange.  (A persistent cp.async double-buffered variant was measured on B200 at
+// N = 120: its extra index arithmetic and barriers cost what the prefetch gained -- 0.63 vs 0.61 ms forward, 1.00 vs
+// 0.85 ms inverse for 16 columns -- so the simple form stays; the z pass, with twice the arithmetic per byte, keeps it.)
 // ---------------------------------------------------------------------------------------
-template <class P, int LX>
-PCB_D void pcb_xtile_load(cplx* __restrict__ st, const cplx* __restrict__ X, long long nn, int row0, int nrows, int tid, int nthr,
-                          bool kmajor) {
-    constexpr int N = P::N, R1 = P::R1, R2 = P::R2, R2P = P::R2P;
-    for (int e = tid; e < 3 * LX * N; e += nthr) {
-        const int c = e / (LX * N), rem = e % (LX * N);
-        const int r = rem / N, i0 = rem % N;
-        if (row0 + r >= nrows) continue;
-        // forward input (natural order): slot (n1, n2) with i0 = n1*R2 + n2; inverse input (Fourier order): slot (k1, k2), k = k1 + R1*k2
-        const int hi = kmajor ? i0 % R1 : i0 / R2, lo = kmajor ? i0 / R1 : i0 % R2;
-        pcb_cp16(st + ((c * LX + r) * R1 + hi) * R2P + lo, X + c * nn + (long long)(row0 + r) * N + i0);
-    }
-}
-
-// slot of grid point (r, i0) of component c in an x-tile stage
-template <class P, int LX>
-PCB_HD int pcb_xslot(int c, int r, int i0) {
-    return ((c * LX + r) * P::R1 + i0 / P::R2) * P::R2P + i0 % P::R2;
-}
-
 template <class P, int LX, int NT, int SYM>
-__global__ void __launch_bounds__(NT, 2) k_xfwd(PcbOp op, PcbCols cols, const cplx* __restrict__ tw, int ncols) {
+__global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * P::R1 * P::R2P * 16, P::R1, 4)) k_xfwd(PcbOp op, PcbCols cols, const cplx* __restrict__ tw) {
     constexpr int N = P::N, R1 = P::R1, R2 = P::R2, R2P = P::R2P;
-    constexpr int STAGE = 3 * LX * R1 * R2P;
-    PCB_DYN_SMEM(cplx, sm);   // [2 stages][3][LX][R1][R2P]
+    PCB_DYN_SMEM(cplx, sm);   // [3][LX][R1][R2P]
+    const int col = blockIdx.y;
+    const cplx* __restrict__ X = cols.in[col];
+    cplx* __restrict__ Y = cols.out[col];
     const long long nn = op.nn;
+    const int row0 = blockIdx.x * LX;
     const int nrows = N * N;
-    const int tpc = (nrows + LX - 1) / LX;          // tiles per column
-    const int total = tpc * ncols;
     const int tid = threadIdx.x;
 
-    int tile = blockIdx.x, stage = 0;
-    if (tile < total) {
-        pcb_xtile_load<P, LX>(sm, cols.in[tile / tpc], nn, (tile % tpc) * LX, nrows, tid, NT, false);
-        pcb_cp_commit();
-    }
-    for (; tile < total; tile += gridDim.x) {
-        const int next = tile + gridDim.x;
-        if (next < total) {
-            pcb_xtile_load<P, LX>(sm + (stage ^ 1) * STAGE, cols.in[next / tpc], nn, (next % tpc) * LX, nrows, tid, NT, false);
-            pcb_cp_commit();
-            pcb_cp_wait<1>();
-        } else {
-            pcb_cp_wait<0>();
+    for (int item = tid; item < LX * R2; item += NT) {
+        const int r = item / R2, n2 = item % R2;
+        const int row = row0 + r;
+        if (row >= nrows) continue;
+        const int i1 = row % N, i2 = row / N;
+        cplx v[3][R1];
+        cplx kc[3];
+        if (SYM) {
+            PCB_UNROLL
+            for (int c = 0; c < 3; ++c) {
+                const cplx b = __ldg(op.T + (c * 3 + 1) * N + i1);
+                const cplx d = __ldg(op.T + (c * 3 + 2) * N + i2);
+                kc[c] = cadd(b, d);
+            }
         }
-        __syncthreads();
-        cplx* __restrict__ st = sm + stage * STAGE;
-        cplx* __restrict__ Y = cols.out[tile / tpc];
-        const int row0 = (tile % tpc) * LX;
-
-        if (SYM) {   // point-wise: v <- (-conj k) x v, all threads
-            for (int e = tid; e < LX * N; e += NT) {
-                const int r = e / N, i0 = e % N;
-                const int row = row0 + r;
-                if (row >= nrows) continue;
-                const Sym3 sy = pcb_symbol(op.T, N, i0, row % N, row / N);
-                cplx a[3], x[3], z[3];
+        PCB_UNROLL
+        for (int n1 = 0; n1 < R1; ++n1) {
+            const int i0 = n1 * R2 + n2;
+            const long long e = (long long)row * N + i0;
+            cplx x[3];
+            PCB_UNROLL
+            for (int c = 0; c < 3; ++c) x[c] = X[c * nn + e];
+            if (SYM) {
+                cplx a[3], z[3];
                 PCB_UNROLL
                 for (int c = 0; c < 3; ++c) {
-                    a[c] = cmake(-sy.k[c].x, sy.k[c].y);
-                    x[c] = st[pcb_xslot<P, LX>(c, r, i0)];
+                    const cplx k = cadd(kc[c], __ldg(op.T + (c * 3 + 0) * N + i0));
+                    a[c] = cmake(-k.x, k.y);   // -conj(k)
                 }
                 pcb_cross(a, x, z);
                 PCB_UNROLL
-                for (int c = 0; c < 3; ++c) st[pcb_xslot<P, LX>(c, r, i0)] = z[c];
+                for (int c = 0; c < 3; ++c) v[c][n1] = z[c];
+            } else {
+                PCB_UNROLL
+                for (int c = 0; c < 3; ++c) v[c][n1] = x[c];
             }
-            __syncthreads();
         }
-        // radix R1 over n1 (fixed n2), twiddle, in place
-        for (int item = tid; item < 3 * LX * R2; item += NT) {
-            const int n2 = item % R2, cr = item / R2;          // cr = c*LX + r
-            if (row0 + cr % LX >= nrows) continue;
-            cplx v[R1];
-            PCB_UNROLL
-            for (int n1 = 0; n1 < R1; ++n1) v[n1] = st[(cr * R1 + n1) * R2P + n2];
-            Dft<R1, -1>::run(v);
+        PCB_UNROLL
+        for (int c = 0; c < 3; ++c) {
+            Dft<R1, -1>::run(v[c]);
             PCB_UNROLL
             for (int k1 = 0; k1 < R1; ++k1) {
-                cplx val = v[k1];
+                cplx val = v[c][k1];
                 if (k1 > 0) val = cmul(val, __ldg(tw + k1 * R2 + n2));
-                st[(cr * R1 + k1) * R2P + n2] = val;
+                sm[((c * LX + r) * R1 + k1) * R2P + n2] = val;
             }
         }
-        __syncthreads();
-        // radix R2 over n2 (fixed k1) and store: k = k1 + R1*k2
-        for (int item = tid; item < 3 * LX * R1; item += NT) {
-            const int k1 = item % R1, cr = item / R1;
-            const int r = cr % LX, c = cr / LX;
-            const int row = row0 + r;
-            if (row >= nrows) continue;
-            cplx v[R2];
-            PCB_UNROLL
-            for (int n2 = 0; n2 < R2; ++n2) v[n2] = st[(cr * R1 + k1) * R2P + n2];
-            Dft<R2, -1>::run(v);
-            cplx* __restrict__ dst = Y + c * nn + (long long)row * N + k1;
-            PCB_UNROLL
-            for (int k2 = 0; k2 < R2; ++k2) dst[R1 * k2] = v[k2];
-        }
-        __syncthreads();     // stage is free for the prefetch issued in the next trip
-        stage ^= 1;
+    }
+    __syncthreads();
+    for (int item = tid; item < 3 * LX * R1; item += NT) {
+        const int k1 = item % R1;
+        const int r = (item / R1) % LX;
+        const int c = item / (R1 * LX);
+        const int row = row0 + r;
+        if (row >= nrows) continue;
+        cplx v[R2];
+        PCB_UNROLL
+        for (int n2 = 0; n2 < R2; ++n2) v[n2] = sm[((c * LX + r) * R1 + k1) * R2P + n2];
+        Dft<R2, -1>::run(v);
+        cplx* __restrict__ dst = Y + c * nn + (long long)row * N + k1;
+        PCB_UNROLL
+        for (int k2 = 0; k2 < R2; ++k2) dst[R1 * k2] = v[k2];
     }
 }
 
 // ---------------------------------------------------------------------------------------
 // Pass 5: x-lines inverse.  MODE 0: plain IFFT * 1/N^3;  1: A = K_A . ;  2: H = K_A . + gamma K_B x + shift x
-// Reads the work column W (Fourier-x order) through the cp.async stages, transforms in place, then a point-wise phase
-// (all threads, fully coalesced) applies 1/N^3, k x v and -- MODE 2 -- adds gamma conj(k)(k.x) + shift x with X read
-// straight from global memory, and stores to OUT (= W's column: each tile only touches its own rows).
+// Reads the work column W (in Fourier-x order), the source column X (MODE 2) and writes OUT
+// (OUT may alias W: each CTA only touches its own rows).
 // ---------------------------------------------------------------------------------------
 template <class P, int LX, int NT, int MODE>
-__global__ void __launch_bounds__(NT, 2) k_xinv(PcbOp op, PcbCols cols, const cplx* __restrict__ tw, int ncols) {
+__global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * P::R1 * P::R2P * 16, P::R1, 3)) k_xinv(PcbOp op, PcbCols cols, const cplx* __restrict__ tw) {
     constexpr int N = P::N, R1 = P::R1, R2 = P::R2, R2P = P::R2P;
-    constexpr int STAGE = 3 * LX * R1 * R2P;
-    PCB_DYN_SMEM(cplx, sm);   // [2 stages][3][LX][R1][R2P]
+    PCB_DYN_SMEM(cplx, sm);   // [3][LX][R1][R2P]
+    const int col = blockIdx.y;
+    const cplx* __restrict__ X = cols.in[col];
+    cplx* __restrict__ W = cols.out[col];
     const long long nn = op.nn;
+    const int row0 = blockIdx.x * LX;
     const int nrows = N * N;
-    const int tpc = (nrows + LX - 1) / LX;
-    const int total = tpc * ncols;
     const int tid = threadIdx.x;
 
-    int tile = blockIdx.x, stage = 0;
-    if (tile < total) {
-        pcb_xtile_load<P, LX>(sm, cols.out[tile / tpc], nn, (tile % tpc) * LX, nrows, tid, NT, true);
-        pcb_cp_commit();
+    for (int item = tid; item < 3 * LX * R1; item += NT) {
+        const int k1 = item % R1;
+        const int r = (item / R1) % LX;
+        const int c = item / (R1 * LX);
+        const int row = row0 + r;
+        if (row >= nrows) continue;
+        cplx v[R2];
+        const cplx* __restrict__ src = W + c * nn + (long long)row * N + k1;
+        PCB_UNROLL
+        for (int k2 = 0; k2 < R2; ++k2) v[k2] = src[R1 * k2];
+        Dft<R2, +1>::run(v);
+        PCB_UNROLL
+        for (int n2 = 0; n2 < R2; ++n2) {
+            cplx val = v[n2];
+            if (k1 > 0) { const cplx t = __ldg(tw + k1 * R2 + n2); val = cmul(val, cmake(t.x, -t.y)); }
+            sm[((c * LX + r) * R1 + k1) * R2P + n2] = val;
+        }
     }
-    for (; tile < total; tile += gridDim.x) {
-        const int next = tile + gridDim.x;
-        const int row0 = (tile % tpc) * LX;
-        if (next < total) {
-            pcb_xtile_load<P, LX>(sm + (stage ^ 1) * STAGE, cols.out[next / tpc], nn, (next % tpc) * LX, nrows, tid, NT, true);
-            pcb_cp_commit();
-            pcb_cp_wait<1>();
-        } else {
-            pcb_cp_wait<0>();
+    __syncthreads();
+    for (int item = tid; item < LX * R2; item += NT) {
+        const int r = item / R2, n2 = item % R2;
+        const int row = row0 + r;
+        if (row >= nrows) continue;
+        const int i1 = row % N, i2 = row / N;
+        cplx v[3][R1];
+        PCB_UNROLL
+        for (int c = 0; c < 3; ++c) {
+            PCB_UNROLL
+            for (int k1 = 0; k1 < R1; ++k1) v[c][k1] = sm[((c * LX + r) * R1 + k1) * R2P + n2];
+            Dft<R1, +1>::run(v[c]);
         }
-        __syncthreads();
-        cplx* __restrict__ st = sm + stage * STAGE;
-        const cplx* __restrict__ X = cols.in[tile / tpc];
-        cplx* __restrict__ W = cols.out[tile / tpc];
-
-        // inverse radix R2 over k2 (fixed k1), conjugate twiddle, in place
-        for (int item = tid; item < 3 * LX * R1; item += NT) {
-            const int k1 = item % R1, cr = item / R1;
-            if (row0 + cr % LX >= nrows) continue;
-            cplx v[R2];
+        cplx kc[3];
+        if (MODE) {
             PCB_UNROLL
-            for (int k2 = 0; k2 < R2; ++k2) v[k2] = st[(cr * R1 + k1) * R2P + k2];
-            Dft<R2, +1>::run(v);
-            PCB_UNROLL
-            for (int n2 = 0; n2 < R2; ++n2) {
-                cplx val = v[n2];
-                if (k1 > 0) { const cplx t = __ldg(tw + k1 * R2 + n2); val = cmul(val, cmake(t.x, -t.y)); }
-                st[(cr * R1 + k1) * R2P + n2] = val;
+            for (int c = 0; c < 3; ++c) {
+                const cplx b = __ldg(op.T + (c * 3 + 1) * N + i1);
+                const cplx d = __ldg(op.T + (c * 3 + 2) * N + i2);
+                kc[c] = cadd(b, d);
             }
         }
-        __syncthreads();
-        // inverse radix R1 over k1 (fixed n2), in place: slot (n1, n2) <-> i0 = n1*R2 + n2
-        for (int item = tid; item < 3 * LX * R2; item += NT) {
-            const int n2 = item % R2, cr = item / R2;
-            if (row0 + cr % LX >= nrows) continue;
-            cplx v[R1];
-            PCB_UNROLL
-            for (int k1 = 0; k1 < R1; ++k1) v[k1] = st[(cr * R1 + k1) * R2P + n2];
-            Dft<R1, +1>::run(v);
-            PCB_UNROLL
-            for (int n1 = 0; n1 < R1; ++n1) st[(cr * R1 + n1) * R2P + n2] = v[n1];
-        }
-        __syncthreads();
-        // point-wise epilogue and store
-        for (int e = tid; e < LX * N; e += NT) {
-            const int r = e / N, i0 = e % N;
-            const int row = row0 + r;
-            if (row >= nrows) continue;
-            const long long g = (long long)row * N + i0;
-            cplx x[3];
-            if (MODE == 2) {
-                PCB_UNROLL
-                for (int c = 0; c < 3; ++c) x[c] = X[c * nn + g];
-            }
+        PCB_UNROLL
+        for (int n1 = 0; n1 < R1; ++n1) {
+            const int i0 = n1 * R2 + n2;
+            const long long e = (long long)row * N + i0;
             cplx u[3], z[3];
             PCB_UNROLL
-            for (int c = 0; c < 3; ++c) u[c] = cscale(st[pcb_xslot<P, LX>(c, r, i0)], op.inv_n3);
+            for (int c = 0; c < 3; ++c) u[c] = cscale(v[c][n1], op.inv_n3);
             if (MODE) {
-                const Sym3 sy = pcb_symbol(op.T, N, i0, row % N, row / N);
-                pcb_cross(sy.k, u, z);
+                cplx k[3];
+                PCB_UNROLL
+                for (int c = 0; c < 3; ++c) k[c] = cadd(kc[c], __ldg(op.T + (c * 3 + 0) * N + i0));
+                pcb_cross(k, u, z);
                 if (MODE == 2) {
+                    cplx x[3];
+                    PCB_UNROLL
+                    for (int c = 0; c < 3; ++c) x[c] = X[c * nn + e];
                     // gamma K_B x = gamma conj(k) (k . x)   (h_block with D_B, pcfft.py:176)
-                    cplx dot = cadd(cadd(cmul(sy.k[0], x[0]), cmul(sy.k[1], x[1])), cmul(sy.k[2], x[2]));
+                    cplx dot = cadd(cadd(cmul(k[0], x[0]), cmul(k[1], x[1])), cmul(k[2], x[2]));
                     dot = cscale(dot, op.gamma);
                     PCB_UNROLL
                     for (int c = 0; c < 3; ++c) {
-                        cplx t = cfmac(sy.k[c], dot, z[c]);
+                        cplx t = cfmac(k[c], dot, z[c]);
                         t.x = fma(op.shift, x[c].x, t.x);
                         t.y = fma(op.shift, x[c].y, t.y);
                         z[c] = t;
@@ -281,10 +248,8 @@ __global__ void __launch_bounds__(NT, 2) k_xinv(PcbOp op, PcbCols cols, const cp
                 for (int c = 0; c < 3; ++c) z[c] = u[c];
             }
             PCB_UNROLL
-            for (int c = 0; c < 3; ++c) W[c * nn + g] = z[c];
+            for (int c = 0; c < 3; ++c) W[c * nn + e] = z[c];
         }
-        __syncthreads();
-        stage ^= 1;
     }
 }
 

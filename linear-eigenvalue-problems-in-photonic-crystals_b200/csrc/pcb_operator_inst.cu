@@ -15,9 +15,6 @@ constexpr int NTP = 256;     // persistent x / z-mid kernels
 constexpr int kRowBytes = 3 * P::R1 * P::R2P * (int)sizeof(cplx);
 constexpr int LX = (8 * kRowBytes <= 65536) ? 8 : (4 * kRowBytes <= 65536) ? 4 : (2 * kRowBytes <= 65536) ? 2 : 1;
 constexpr int kStageX = LX * kRowBytes;               // one x-tile (three components)
-constexpr int kSmemXF = 2 * kStageX;                    // forward: two stages
-constexpr int kSmemXI = 2 * kStageX;                    // inverse modes 0/1
-constexpr int kSmemXH = 2 * kStageX;                    // inverse mode 2 reads X straight from global in its point-wise phase
 constexpr int kSmemL = 3 * P::N * 8 * (int)sizeof(cplx);
 constexpr int kSmemZ = 2 * kSmemL;                       // two stages
 
@@ -60,15 +57,15 @@ constexpr int GL = ((P::N + 7) / 8) * P::N;              // strided-line tiles p
 
 int run_pass(const PcbOp& op, const PcbCols& cols, int ncols, int pass_id, const cplx* tw, cudaStream_t s, int sms) {
     switch (pass_id) {
-        case PCB_PASS_XFWD_SYM: PCB_GO_P((k_xfwd<P, LX, NTP, 1>), GX, kSmemXF, 2); break;
-        case PCB_PASS_XFWD:     PCB_GO_P((k_xfwd<P, LX, NTP, 0>), GX, kSmemXF, 2); break;
+        case PCB_PASS_XFWD_SYM: PCB_GO((k_xfwd<P, LX, NT, 1>), GX, kStageX); break;
+        case PCB_PASS_XFWD:     PCB_GO((k_xfwd<P, LX, NT, 0>), GX, kStageX); break;
         case PCB_PASS_YFWD:     PCB_GO((k_line<P, 1, -1, NT>), GL, kSmemL); break;
         case PCB_PASS_ZFWD:     PCB_GO((k_line<P, 2, -1, NT>), GL, kSmemL); break;
         case PCB_PASS_ZINV:     PCB_GO((k_line<P, 2, +1, NT>), GL, kSmemL); break;
         case PCB_PASS_YINV:     PCB_GO((k_line<P, 1, +1, NT>), GL, kSmemL); break;
-        case PCB_PASS_XINV:     PCB_GO_P((k_xinv<P, LX, NTP, 0>), GX, kSmemXI, 2); break;
-        case PCB_PASS_XINV_A:   PCB_GO_P((k_xinv<P, LX, NTP, 1>), GX, kSmemXI, 2); break;
-        case PCB_PASS_XINV_H:   PCB_GO_P((k_xinv<P, LX, NTP, 2>), GX, kSmemXH, 2); break;
+        case PCB_PASS_XINV:     PCB_GO((k_xinv<P, LX, NT, 0>), GX, kStageX); break;
+        case PCB_PASS_XINV_A:   PCB_GO((k_xinv<P, LX, NT, 1>), GX, kStageX); break;
+        case PCB_PASS_XINV_H:   PCB_GO((k_xinv<P, LX, NT, 2>), GX, kStageX); break;
         case PCB_PASS_ZMID:
             if (op.diel == PCB_DIEL_NONE) PCB_GO_P((k_zmid<P, 0, NTP>), GL, kSmemZ, 2);
             else if (op.diel == PCB_DIEL_CHIRAL) PCB_GO_P((k_zmid<P, 1, NTP>), GL, kSmemZ, 2);
