@@ -160,6 +160,9 @@ _FLAGS = {"sc_flat1": FLAG_sc_flat1, "sc_flat2": FLAG_sc_flat2, "sc_curv": FLAG_
           "bcc_sg": FLAG_bcc_sg, "bcc_dg": FLAG_bcc_dg, "fcc": FLAG_fcc}
 
 
+_index_cache = {}     # (N, d_flag, dofs) -> int64 indices (in-process complement of the on-disk .bin cache)
+
+
 def compute_index(N, d_flag, dofs="edge"):
     """Index set of Omega_1 computed from the geometry (the compute branch of diel_io_index)."""
     ct = diel_info(d_flag, option="ct")
@@ -179,7 +182,9 @@ def diel_io_index(N, d_flag, dofs="edge", gpu=True, cache=True):
         return rng.integers(0, 3 * N ** 3 - 1, size=int(0.372 * 3 * N ** 3)).astype(np.int64)
     t0 = time.time()
     path = os.path.join(DIEL_PATH, dofs + "_dofs", f"{d_flag}_{N}.bin")
-    if os.path.exists(path):
+    if (N, d_flag, dofs) in _index_cache:
+        ind = _index_cache[(N, d_flag, dofs)]
+    elif os.path.exists(path):
         ind = np.fromfile(path, dtype=np.int64)
         say(f"{GREEN}Index file already exists.{RESET}")
     else:
@@ -187,5 +192,6 @@ def diel_io_index(N, d_flag, dofs="edge", gpu=True, cache=True):
         if cache and os.path.isdir(os.path.dirname(path)):
             say(f"{RED}New lattice type {d_flag} or size {N} isn't computed.{RESET}")
             ind.tofile(path)
+    _index_cache[(N, d_flag, dofs)] = ind
     say(f"Dielectric {dofs} indices for {d_flag} with N = {N} loaded, {time.time() - t0:<6.3f}s elapsed.")
     return ind
