@@ -117,6 +117,21 @@ int pcb_coldots(pcb_ctx* ctx, int ncols, const void* const* a, const void* const
 /* y_j = alpha x_j + beta y_j */
 int pcb_axpby(pcb_ctx* ctx, int ncols, const void* const* x, void* const* y, double alpha, double beta);
 
+/* ---- large-grid mode (BASELINE config 5): dense phase row-sharded, operator on whole columns ------------
+ * A SLAB context owns the i2 planes [z0, z1) of every column: its "column" is 3 * (z1-z0) * N^2 complex128 ([c][local cell]),
+ * and pcb_residual / pcb_gram2 / pcb_update / pcb_coldots / pcb_axpby / pcb_fill_uniform / block up/download work on it
+ * unchanged (pcb_apply: PCB_APPLY_P only).  With a communicator attached, pcb_gram2, pcb_residual and pcb_coldots
+ * all-reduce their n_loc x n_loc / per-column results over the ranks with NCCL before returning them -- the only
+ * collective of the dense phase.  The reference has no counterpart (single GPU, lobpcg.py / orthogonalization.py:143-144). */
+int pcb_ctx_create_slab(int device, int N, int z0, int z1, pcb_ctx** ctx);
+int pcb_comm_unique_id(void* id128);                                   /* rank 0: ncclGetUniqueId (128 bytes) */
+int pcb_comm_init(pcb_ctx* ctx, const void* id128, int rank, int world); /* every rank: ncclCommInitRank on the slab context */
+int pcb_comm_set_host_callbacks(pcb_ctx* ctx, void* allreduce_cb, void* p2p_cb);  /* host-emu test build only */
+int pcb_comm_destroy(pcb_ctx* ctx);
+/* slab layout <-> whole columns on their owner rank, one grouped ncclSend/ncclRecv per call (see pcb_capi.cu) */
+int pcb_slab_exchange(pcb_ctx* ctx, int to_full, int ncols, const int* owners, const int* zb, void* const* slab_cols,
+                      void* const* full_cols);
+
 #ifdef __cplusplus
 }
 #endif

@@ -56,6 +56,12 @@ SIGNATURES = {
     "pcb_update": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_void_pp, c_void_pp, c_void_pp, c_void_pp, C.c_void_p]),
     "pcb_coldots": (C.c_int, [C.c_void_p, C.c_int, c_void_pp, c_void_pp, C.c_void_p]),
     "pcb_axpby": (C.c_int, [C.c_void_p, C.c_int, c_void_pp, c_void_pp, C.c_double, C.c_double]),
+    "pcb_ctx_create_slab": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, c_void_pp]),
+    "pcb_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "pcb_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "pcb_comm_set_host_callbacks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pcb_comm_destroy": (C.c_int, [C.c_void_p]),
+    "pcb_slab_exchange": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), c_void_pp, c_void_pp]),
 }
 
 APPLY_FFT, APPLY_IFFT, APPLY_A, APPLY_H, APPLY_P, APPLY_M, APPLY_KA, APPLY_KAH, APPLY_KB = range(9)

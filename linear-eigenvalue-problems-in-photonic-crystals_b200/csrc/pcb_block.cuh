@@ -117,7 +117,7 @@ template <int MODE>
 __global__ void __launch_bounds__(256) k_resid_precond(PcbOp op, PcbResidArgs a, int ncols, double* __restrict__ partial) {
     __shared__ double red[8][PCB_RP_CH];
     const int N = op.N;
-    const long long nn = op.nn;
+    const long long nn = op.nloc;          // cells of this slab (= N^3 on a full context); also the component stride
     const int j0 = blockIdx.y * PCB_RP_CH;
     double acc[PCB_RP_CH];
     PCB_UNROLL
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(256) k_resid_precond(PcbOp op, PcbResidArgs a,
     for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < nn; p += (long long)gridDim.x * blockDim.x) {
         PcbPinv f;
         if (MODE) {
-            const int i0 = (int)(p % N), i1 = (int)((p / N) % N), i2 = (int)(p / ((long long)N * N));
+            const int i0 = (int)(p % N), i1 = (int)((p / N) % N), i2 = op.z0 + (int)(p / ((long long)N * N));
             const Sym3 s = pcb_symbol(op.T, N, i0, i1, i2);
             f = pcb_pinv(s.k, op.gamma, op.pshift);
         }
@@ -546,12 +546,16 @@ PCB_HD unsigned long long pcb_mix64(unsigned long long z) {
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
     return z ^ (z >> 31);
 }
-__global__ void __launch_bounds__(256) k_fill_uniform(PcbColListW cols, long long R, unsigned long long seed) {
+// The value of global row r_g = c*nn + cell depends on (seed, column, r_g) only, so a slab context (rows [c][off .. off+nloc))
+// generates exactly its part of the vector a full context would.
+__global__ void __launch_bounds__(256) k_fill_uniform(PcbColListW cols, long long nloc, long long nn, long long off, int col0,
+                                                      unsigned long long seed) {
     cplx* __restrict__ Y = cols.p[blockIdx.y];
-    const unsigned long long base = pcb_mix64(seed ^ (0xD1B54A32D192ED03ull * (unsigned long long)(blockIdx.y + 1)));
-    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < R; r += (long long)gridDim.x * blockDim.x) {
-        const unsigned long long a = pcb_mix64(base + 2ull * (unsigned long long)r);
-        const unsigned long long b = pcb_mix64(base + 2ull * (unsigned long long)r + 1ull);
+    const unsigned long long base = pcb_mix64(seed ^ (0xD1B54A32D192ED03ull * (unsigned long long)(col0 + blockIdx.y + 1)));
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < 3 * nloc; r += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long rg = (unsigned long long)((r / nloc) * nn + off + r % nloc);
+        const unsigned long long a = pcb_mix64(base + 2ull * rg);
+        const unsigned long long b = pcb_mix64(base + 2ull * rg + 1ull);
         Y[r] = cmake((double)(a >> 11) * (1.0 / 9007199254740992.0), (double)(b >> 11) * (1.0 / 9007199254740992.0));
     }
 }

@@ -5,6 +5,9 @@
 
 #include <cstdarg>
 #include <vector>
+#ifndef PCB_EMU
+#include <dlfcn.h>
+#endif
 
 // ---- error string ---------------------------------------------------------------------------------------
 static thread_local char g_err[1024] = "";
@@ -32,10 +35,38 @@ const PcbOpLaunch* pcb_find_plan(int N) {
 }
 
 // ---- objects ----------------------------------------------------------------------------------------------
+// ---- collectives of the large-grid mode: NCCL resolved at run time (dlopen), host callbacks in the emulation build ----
+struct PcbNcclId { char internal[128]; };      // ncclUniqueId
+struct PcbNccl {
+    void* lib = nullptr;
+    int (*GetUniqueId)(PcbNcclId*) = nullptr;
+    int (*CommInitRank)(void**, int, PcbNcclId, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+enum { PCB_NCCL_FLOAT64 = 8, PCB_NCCL_UINT8 = 1, PCB_NCCL_SUM = 0 };
+typedef int (*pcb_allreduce_cb)(double* buf, long long count);
+typedef int (*pcb_p2p_cb)(int nops, const int* is_send, const int* peer, void* const* ptr, const long long* bytes);
+struct PcbComm {
+    int rank = 0, world = 1;
+    void* nccl = nullptr;              // ncclComm_t
+    pcb_allreduce_cb allreduce_cb = nullptr;
+    pcb_p2p_cb p2p_cb = nullptr;
+};
+static PcbNccl g_nccl;
+
 struct pcb_ctx {
     int device = 0;
     int N = 0;
-    long long nn = 0, R = 0;
+    int z0 = 0, z1 = 0;             // i2 planes owned by this context (0..N on a full context)
+    long long nloc = 0;             // cells owned = (z1 - z0) N^2
+    PcbComm* comm = nullptr;        // collectives (slab contexts of the large-grid mode)
+    long long nn = 0, R = 0;        // N^3; rows of a column on this context = 3 * nloc
     cudaStream_t stream = nullptr;
     const PcbOpLaunch* plan = nullptr;
     cplx* tw = nullptr;             // [R1][R2] forward twiddles exp(-2 pi i k1 n2 / N)
@@ -97,6 +128,21 @@ static int grid_for(pcb_ctx* c, long long items, int per_block, int waves) {
     return (int)b;
 }
 
+// Sum `count` doubles over all ranks, in place on the device, ordered on the context's stream.  No-op without a communicator.
+static int comm_allreduce(pcb_ctx* c, double* dbuf, long long count) {
+    PcbComm* cm = c->comm;
+    if (!cm || cm->world <= 1) return 0;
+#ifdef PCB_EMU
+    if (!cm->allreduce_cb) { pcb_set_error("host-emu communicator has no allreduce callback"); return -4; }
+    if (cm->allreduce_cb(dbuf, count) != 0) { pcb_set_error("allreduce callback failed"); return -4; }
+    return 0;
+#else
+    const int rc = g_nccl.AllReduce(dbuf, dbuf, (size_t)count, PCB_NCCL_FLOAT64, PCB_NCCL_SUM, cm->nccl, c->stream);
+    if (rc != 0) { pcb_set_error("ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"); return -4; }
+    return 0;
+#endif
+}
+
 extern "C" {
 
 const char* pcb_last_error(void) { return g_err; }
@@ -117,7 +163,14 @@ int pcb_supported_sizes(int* sizes, int cap) {
     return g_nplans;
 }
 
-int pcb_ctx_create(int device, int N, pcb_ctx** out) {
+static int ctx_create(int device, int N, int z0, int z1, pcb_ctx** out);
+int pcb_ctx_create(int device, int N, pcb_ctx** out) { return ctx_create(device, N, 0, N, out); }
+int pcb_ctx_create_slab(int device, int N, int z0, int z1, pcb_ctx** out) {
+    if (z0 < 0 || z1 > N || z0 >= z1) { pcb_set_error("pcb_ctx_create_slab: need 0 <= z0 < z1 <= N"); return -2; }
+    return ctx_create(device, N, z0, z1, out);
+}
+}  // extern "C"
+static int ctx_create(int device, int N, int z0, int z1, pcb_ctx** out) {
     PCB_CHECK_ARG(out, "null");
     const PcbOpLaunch* plan = pcb_find_plan(N);
     if (!plan) { pcb_set_error("pcb_ctx_create: no FFT plan for N = %d (see pcb_supported_sizes)", N); return -2; }
@@ -126,7 +179,8 @@ int pcb_ctx_create(int device, int N, pcb_ctx** out) {
     if (ndev <= 0 || device < 0 || device >= ndev) { pcb_set_error("pcb_ctx_create: CUDA device %d not available (%d devices)", device, ndev); return -3; }
     PCB_CUDA_OK(cudaSetDevice(device));
     pcb_ctx* c = new pcb_ctx;
-    c->device = device; c->N = N; c->nn = (long long)N * N * N; c->R = 3 * c->nn; c->plan = plan;
+    c->device = device; c->N = N; c->nn = (long long)N * N * N; c->plan = plan;
+    c->z0 = z0; c->z1 = z1; c->nloc = (long long)(z1 - z0) * N * N; c->R = 3 * c->nloc;
 #ifndef PCB_EMU
     cudaDeviceProp prop;
     PCB_CUDA_OK(cudaGetDeviceProperties(&prop, device));
@@ -149,6 +203,7 @@ int pcb_ctx_create(int device, int N, pcb_ctx** out) {
     *out = c;
     return 0;
 }
+extern "C" {
 void pcb_ctx_destroy(pcb_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
@@ -253,7 +308,7 @@ int pcb_fill_uniform(pcb_ctx* c, int k, void* const* cols, unsigned long long se
         const int kk = (k - j0 < PCB_MAXL) ? k - j0 : PCB_MAXL;
         for (int j = 0; j < kk; ++j) L.p[j] = (cplx*)cols[j0 + j];
         dim3 grid((unsigned)grid_for(c, c->R, 256, 8), (unsigned)kk, 1);
-        PCB_LAUNCH(k_fill_uniform, grid, dim3(256, 1, 1), 0, c->stream, L, c->R, seed + 0x1000ull * (unsigned long long)j0);
+        PCB_LAUNCH(k_fill_uniform, grid, dim3(256, 1, 1), 0, c->stream, L, c->nloc, c->nn, (long long)c->z0 * c->N * c->N, j0, seed);
         PCB_CUDA_OK(cudaGetLastError());
         c->launches++;
     }
@@ -308,7 +363,7 @@ void pcb_diel_destroy(pcb_diel* d) {
 static void op_fill(pcb_op* o, double gamma, double shift, double pshift, pcb_diel* diel) {
     pcb_ctx* c = o->ctx;
     o->diel = diel;
-    o->d.N = c->N; o->d.nn = c->nn; o->d.T = o->T;
+    o->d.N = c->N; o->d.nn = c->nn; o->d.nloc = c->nloc; o->d.z0 = c->z0; o->d.T = o->T;
     o->d.gamma = gamma; o->d.shift = shift; o->d.pshift = pshift;
     o->d.inv_n3 = 1.0 / (double)c->nn;
     o->d.diel = diel ? diel->kind : PCB_DIEL_NONE;
@@ -365,6 +420,10 @@ int pcb_apply(pcb_op* o, int mode, int ncols, const void* const* in, void* const
     PCB_CUDA_OK(cudaSetDevice(c->device));
     const PcbOpLaunch* pl = c->plan;
     const bool cross = (o->d.diel == PCB_DIEL_CROSSDOF);
+    if (c->nloc != c->nn && mode != PCB_APPLY_P) {
+        pcb_set_error("pcb_apply: mode %d needs whole columns; a slab context only supports PCB_APPLY_P (gather with pcb_slab_exchange)", mode);
+        return -2;
+    }
     for (int j0 = 0; j0 < ncols; j0 += PCB_MAXC) {
         const int kc = (ncols - j0 < PCB_MAXC) ? ncols - j0 : PCB_MAXC;
         PcbCols cols;
@@ -399,7 +458,7 @@ int pcb_apply(pcb_op* o, int mode, int ncols, const void* const* in, void* const
             case PCB_APPLY_P: {
                 PcbResidArgs a;
                 for (int j = 0; j < kc; ++j) { a.x[j] = cols.in[j]; a.hx[j] = nullptr; a.w[j] = cols.out[j]; a.lambda[j] = 0.0; }
-                const int gx = grid_for(c, c->nn, 256, 4);
+                const int gx = grid_for(c, c->nloc, 256, 4);
                 if (ensure_partial(c, sizeof(double) * (size_t)gx * PCB_MAXC_RP)) return -1;
                 dim3 grid((unsigned)gx, (unsigned)((kc + PCB_RP_CH - 1) / PCB_RP_CH), 1);
                 PCB_LAUNCH(k_resid_precond<2>, grid, dim3(256, 1, 1), 0, c->stream, o->d, a, kc, c->partial);
@@ -465,7 +524,7 @@ int pcb_residual(pcb_op* o, int precond, int ncols, const void* const* x, const 
     PCB_CHECK_ARG(o && x && hx && w && lambda && norms2 && ncols > 0, "bad arguments");
     pcb_ctx* c = o->ctx;
     PCB_CUDA_OK(cudaSetDevice(c->device));
-    const int gx = grid_for(c, c->nn, 256, 4);
+    const int gx = grid_for(c, c->nloc, 256, 4);
     if (ensure_partial(c, sizeof(double) * (size_t)gx * PCB_MAXC_RP + sizeof(double) * PCB_MAXC_RP)) return -1;
     if (ensure_hstage(c, 65536)) return -1;
     for (int j0 = 0; j0 < ncols; j0 += PCB_MAXC_RP) {
@@ -482,6 +541,7 @@ int pcb_residual(pcb_op* o, int precond, int ncols, const void* const* x, const 
         PCB_LAUNCH(k_sum_partials, dim3(1, 1, 1), dim3(64, 1, 1), 0, c->stream, (const double*)c->partial, gx, kc, dout);
         PCB_CUDA_OK(cudaGetLastError());
         c->launches += 2;
+        if (comm_allreduce(c, dout, kc)) return -1;
         PCB_CUDA_OK(cudaMemcpyAsync(c->hstage, dout, sizeof(double) * kc, cudaMemcpyDeviceToHost, c->stream));
         PCB_CUDA_OK(cudaStreamSynchronize(c->stream));
         memcpy(norms2 + j0, c->hstage, sizeof(double) * kc);
@@ -519,6 +579,7 @@ int pcb_gram2(pcb_ctx* c, int n, const void* const* s, const void* const* hs, vo
     PCB_LAUNCH(k_gram_finish, dim3((unsigned)((ne + 127) / 128), 1, 1), dim3(128, 1, 1), 0, c->stream, (const cplx*)c->partial, (int)gx, nt, dout);
     PCB_CUDA_OK(cudaGetLastError());
     c->launches += 2;
+    if (comm_allreduce(c, (double*)dout, 2LL * ne)) return -1;      // large-grid mode: sum of the per-slab Gram pairs (NCCL)
     PCB_CUDA_OK(cudaMemcpyAsync(c->hstage, dout, sizeof(cplx) * ne, cudaMemcpyDeviceToHost, c->stream));
     PCB_CUDA_OK(cudaStreamSynchronize(c->stream));
     const cplx* h = (const cplx*)c->hstage;
@@ -605,6 +666,7 @@ int pcb_coldots(pcb_ctx* c, int ncols, const void* const* a, const void* const* 
     PCB_LAUNCH(k_sum_partials, dim3((unsigned)((2 * ncols + 63) / 64), 1, 1), dim3(64, 1, 1), 0, c->stream, (const double*)c->partial, gx, 2 * ncols, dout);
     PCB_CUDA_OK(cudaGetLastError());
     c->launches += 2;
+    if (comm_allreduce(c, dout, 2LL * ncols)) return -1;
     PCB_CUDA_OK(cudaMemcpyAsync(c->hstage, dout, sizeof(cplx) * ncols, cudaMemcpyDeviceToHost, c->stream));
     PCB_CUDA_OK(cudaStreamSynchronize(c->stream));
     memcpy(out, c->hstage, sizeof(cplx) * ncols);
@@ -620,6 +682,127 @@ int pcb_axpby(pcb_ctx* c, int ncols, const void* const* x, void* const* y, doubl
         PCB_CUDA_OK(cudaGetLastError());
         c->launches++;
     }
+    return 0;
+}
+
+
+// ---- large-grid mode: communicator and slab <-> full-column exchange -------------------------------------------------
+#ifndef PCB_EMU
+static int nccl_load() {
+    if (g_nccl.lib) return 0;
+    const char* names[] = {"libnccl.so.2", "libnccl.so", nullptr};
+    for (int i = 0; names[i] && !g_nccl.lib; ++i) g_nccl.lib = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+    if (!g_nccl.lib) { pcb_set_error("cannot dlopen libnccl.so.2: %s", dlerror()); return -4; }
+#define PCB_SYM(field, name)                                                        \
+    *(void**)(&g_nccl.field) = dlsym(g_nccl.lib, name);                             \
+    if (!g_nccl.field) { pcb_set_error("libnccl: missing symbol %s", name); return -4; }
+    PCB_SYM(GetUniqueId, "ncclGetUniqueId") PCB_SYM(CommInitRank, "ncclCommInitRank") PCB_SYM(CommDestroy, "ncclCommDestroy")
+    PCB_SYM(AllReduce, "ncclAllReduce") PCB_SYM(Send, "ncclSend") PCB_SYM(Recv, "ncclRecv")
+    PCB_SYM(GroupStart, "ncclGroupStart") PCB_SYM(GroupEnd, "ncclGroupEnd") PCB_SYM(GetErrorString, "ncclGetErrorString")
+#undef PCB_SYM
+    return 0;
+}
+#endif
+
+int pcb_comm_unique_id(void* id128) {
+    PCB_CHECK_ARG(id128, "null");
+    memset(id128, 0, 128);
+#ifndef PCB_EMU
+    if (nccl_load()) return -4;
+    const int rc = g_nccl.GetUniqueId((PcbNcclId*)id128);
+    if (rc != 0) { pcb_set_error("ncclGetUniqueId failed: %s", g_nccl.GetErrorString(rc)); return -4; }
+#endif
+    return 0;
+}
+int pcb_comm_init(pcb_ctx* c, const void* id128, int rank, int world) {
+    PCB_CHECK_ARG(c && id128 && world >= 1 && rank >= 0 && rank < world, "bad arguments");
+    if (c->comm) { pcb_set_error("pcb_comm_init: context already has a communicator"); return -2; }
+    PcbComm* cm = new PcbComm;
+    cm->rank = rank; cm->world = world;
+#ifndef PCB_EMU
+    PCB_CUDA_OK(cudaSetDevice(c->device));
+    if (nccl_load()) { delete cm; return -4; }
+    PcbNcclId id;
+    memcpy(&id, id128, 128);
+    const int rc = g_nccl.CommInitRank(&cm->nccl, world, id, rank);
+    if (rc != 0) { pcb_set_error("ncclCommInitRank failed: %s", g_nccl.GetErrorString(rc)); delete cm; return -4; }
+#endif
+    c->comm = cm;
+    return 0;
+}
+/* host-emulation build only (tests): collectives through host callbacks, e.g. torch.distributed gloo */
+int pcb_comm_set_host_callbacks(pcb_ctx* c, void* allreduce_cb, void* p2p_cb) {
+#ifdef PCB_EMU
+    PCB_CHECK_ARG(c && c->comm, "call pcb_comm_init first");
+    c->comm->allreduce_cb = (pcb_allreduce_cb)allreduce_cb;
+    c->comm->p2p_cb = (pcb_p2p_cb)p2p_cb;
+    return 0;
+#else
+    (void)c; (void)allreduce_cb; (void)p2p_cb;
+    pcb_set_error("pcb_comm_set_host_callbacks exists in the host-emulation test build only; the CUDA build uses NCCL");
+    return -2;
+#endif
+}
+int pcb_comm_destroy(pcb_ctx* c) {
+    if (!c || !c->comm) return 0;
+#ifndef PCB_EMU
+    PCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+    if (c->comm->nccl) g_nccl.CommDestroy(c->comm->nccl);
+#endif
+    delete c->comm;
+    c->comm = nullptr;
+    return 0;
+}
+
+/* Exchange between the row-sharded (slab) layout of the dense phase and whole columns for the operator.
+ * zb[0..world]: i2-plane boundaries of the slabs (zb[rank] == ctx z0).  Column j lives as a slab column slab_cols[j] on
+ * every rank and as a whole column full_cols[j] on rank owners[j] only (ignored elsewhere).
+ * to_full = 1: every rank sends its three component segments of column j to owners[j];  to_full = 0: the reverse. */
+int pcb_slab_exchange(pcb_ctx* c, int to_full, int ncols, const int* owners, const int* zb, void* const* slab_cols, void* const* full_cols) {
+    PCB_CHECK_ARG(c && c->comm && owners && zb && slab_cols && full_cols && ncols > 0, "bad arguments / no communicator");
+    PcbComm* cm = c->comm;
+    const long long plane = (long long)c->N * c->N;
+    PCB_CHECK_ARG(zb[cm->rank] == c->z0 && zb[cm->rank + 1] == c->z1, "zb does not match this slab context");
+    PCB_CUDA_OK(cudaSetDevice(c->device));
+    std::vector<int> is_send, peer;
+    std::vector<void*> ptr;
+    std::vector<long long> bytes;
+    for (int j = 0; j < ncols; ++j) {
+        const int o = owners[j];
+        PCB_CHECK_ARG(o >= 0 && o < cm->world, "owner out of range");
+        for (int comp = 0; comp < 3; ++comp) {
+            cplx* mine = (cplx*)slab_cols[j] + comp * c->nloc;
+            if (o == cm->rank) {
+                cplx* full = (cplx*)full_cols[j] + comp * c->nn;
+                for (int g = 0; g < cm->world; ++g) {
+                    cplx* seg = full + (long long)zb[g] * plane;
+                    const long long nb = (long long)(zb[g + 1] - zb[g]) * plane * (long long)sizeof(cplx);
+                    if (g == cm->rank) {
+                        if (to_full) PCB_CUDA_OK(cudaMemcpyAsync(seg, mine, nb, cudaMemcpyDeviceToDevice, c->stream));
+                        else PCB_CUDA_OK(cudaMemcpyAsync(mine, seg, nb, cudaMemcpyDeviceToDevice, c->stream));
+                    } else {
+                        is_send.push_back(to_full ? 0 : 1); peer.push_back(g); ptr.push_back(seg); bytes.push_back(nb);
+                    }
+                }
+            } else {
+                is_send.push_back(to_full ? 1 : 0); peer.push_back(o); ptr.push_back(mine);
+                bytes.push_back(c->nloc * (long long)sizeof(cplx));
+            }
+        }
+    }
+    const int nops = (int)is_send.size();
+    if (nops == 0) return 0;
+#ifdef PCB_EMU
+    if (!cm->p2p_cb) { pcb_set_error("host-emu communicator has no p2p callback"); return -4; }
+    if (cm->p2p_cb(nops, is_send.data(), peer.data(), ptr.data(), bytes.data()) != 0) { pcb_set_error("p2p callback failed"); return -4; }
+#else
+    int rc = g_nccl.GroupStart();
+    for (int i = 0; i < nops && rc == 0; ++i)
+        rc = is_send[i] ? g_nccl.Send(ptr[i], (size_t)bytes[i], PCB_NCCL_UINT8, peer[i], cm->nccl, c->stream)
+                        : g_nccl.Recv(ptr[i], (size_t)bytes[i], PCB_NCCL_UINT8, peer[i], cm->nccl, c->stream);
+    const int rc2 = g_nccl.GroupEnd();
+    if (rc != 0 || rc2 != 0) { pcb_set_error("NCCL send/recv group failed: %s", g_nccl.GetErrorString(rc ? rc : rc2)); return -4; }
+#endif
     return 0;
 }
 

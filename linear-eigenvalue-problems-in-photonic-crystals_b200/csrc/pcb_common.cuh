@@ -91,6 +91,8 @@ enum { PCB_DIEL_NONE = 0, PCB_DIEL_CHIRAL = 1, PCB_DIEL_TRIVIAL = 2, PCB_DIEL_CR
 struct PcbOp {
     int N;
     long long nn;             // N^3
+    long long nloc;           // cells owned by the context: N^3, or (z1 - z0) N^2 on a slab context (large-grid mode)
+    int z0;                   // first i2 plane of the slab (0 on a full context)
     const cplx* T;            // [3][3][N] symbol tables (device)
     double gamma;             // penalty gamma (= pnt; the symbols in T are already / SCAL)
     double shift;             // shift added by H

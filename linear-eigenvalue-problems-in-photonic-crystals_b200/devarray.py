@@ -34,13 +34,19 @@ def default_device():
 class Context:
     """One GPU + one grid size N (pcb_ctx)."""
 
-    def __init__(self, N, device=None):
+    def __init__(self, N, device=None, slab=None):
+        """slab = (z0, z1): a slab context of the large-grid mode owning the i2 planes [z0, z1) of every column."""
         self.N = int(N)
         self.nn = self.N ** 3
-        self.R = 3 * self.nn
+        self.slab = None if slab is None else (int(slab[0]), int(slab[1]))
+        self.nloc = self.nn if slab is None else (self.slab[1] - self.slab[0]) * self.N ** 2
+        self.R = 3 * self.nloc          # rows of a column on this context
         self.device = default_device() if device is None else int(device)
         h = C.c_void_p()
-        L.check(L.lib().pcb_ctx_create(self.device, self.N, C.byref(h)), "pcb_ctx_create")
+        if slab is None:
+            L.check(L.lib().pcb_ctx_create(self.device, self.N, C.byref(h)), "pcb_ctx_create")
+        else:
+            L.check(L.lib().pcb_ctx_create_slab(self.device, self.N, self.slab[0], self.slab[1], C.byref(h)), "pcb_ctx_create_slab")
         self.h = h
         self._lib = L.lib()
         _immortal.append(self)      # see drop_contexts(): destroyed at interpreter exit only

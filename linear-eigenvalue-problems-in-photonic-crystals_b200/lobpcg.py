@@ -169,5 +169,5 @@ def _residual_helper(ctx):
     key = id(ctx)
     if key not in _helpers:
         from .discretization import FourierSymbols
-        _helpers[key] = Operator(FourierSymbols(ctx.N, 1, np.eye(3)), 0.0, 0.0, 0.0, None, device=ctx.device)
+        _helpers[key] = Operator(FourierSymbols(ctx.N, 1, np.eye(3)), 0.0, 0.0, 0.0, None, ctx=ctx)
     return _helpers[key]

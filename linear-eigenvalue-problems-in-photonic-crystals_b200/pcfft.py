@@ -24,14 +24,16 @@ from .discretization import (DielHandle, FourierSymbols, PenaltySymbols, Precond
 class Operator:
     """One k-point's operator on one GPU (pcb_op): symbol tables + gamma/shift + dielectric."""
 
-    def __init__(self, a_fft, gamma=0.0, shift=0.0, pshift=None, diel=None, device=None):
+    def __init__(self, a_fft, gamma=0.0, shift=0.0, pshift=None, diel=None, device=None, ctx=None):
         if not isinstance(a_fft, FourierSymbols):
             raise TypeError("a_fft must come from discretization.fft_blocks (FourierSymbols descriptor)")
         if diel is not None and not isinstance(diel, DielHandle):
             raise TypeError("Diels must be a handle from discretization.*_handle, or None for the identity")
         self.a_fft, self.diel = a_fft, diel
         self.N = a_fft.N
-        self.ctx = diel.ctx if diel is not None else devarray.get_context(self.N, device)
+        self.ctx = ctx if ctx is not None else (diel.ctx if diel is not None else devarray.get_context(self.N, device))
+        if diel is not None and diel.ctx is not self.ctx:
+            raise ValueError("dielectric handle lives on another context")
         if diel is not None and diel.n != self.N:
             raise ValueError(f"dielectric handle is for n = {diel.n}, symbols for n = {self.N}")
         self.gamma, self.shift = float(gamma), float(shift)

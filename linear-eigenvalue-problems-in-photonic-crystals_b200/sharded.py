@@ -1,0 +1,135 @@
+"""Large-grid mode (BASELINE config 5): one eigenproblem spread over the GPUs of a node.
+
+The dense LOBPCG phase is ROW-sharded: rank g owns the i2 planes [zb[g], zb[g+1]) of every column of S and HS (a "slab"
+context), so residual / preconditioner / update are local and the Gram pair needs exactly one NCCL all-reduce of the
+n_loc x n_loc matrices (done inside pcb_gram2).  The operator needs whole columns (3-D FFTs): the active columns are dealt
+round-robin to the ranks, gathered from the slabs with one grouped ncclSend/ncclRecv (pcb_slab_exchange), transformed by
+the ordinary single-GPU kernels, and scattered back.  The reference has no multi-GPU path; the solver code is the same
+`lobpcg_sep_softlock` -- `ShardedOperator` offers the interface of `pcfft.Operator`.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from . import devarray
+from .devarray import Context, DeviceBlock
+from .pcfft import Operator, OperatorCallable, _sym_consistency
+
+
+def slab_bounds(N, world):
+    """i2-plane boundaries zb[0..world]: contiguous slabs, sizes differing by at most one plane."""
+    base, extra = divmod(N, world)
+    zb = [0]
+    for g in range(world):
+        zb.append(zb[-1] + base + (1 if g < extra else 0))
+    return zb
+
+
+class SlabComm:
+    """Rank-local state of the large-grid mode: full context (operator), slab context (dense phase), communicator."""
+
+    def __init__(self, N, rank, world, unique_id=None, device=None, host_callbacks=None):
+        """unique_id: the 128 bytes of pcb_comm_unique_id() from rank 0, distributed by the caller (e.g. with
+        torch.distributed.broadcast_object_list).  host_callbacks=(allreduce, p2p) is accepted by the host-emulation test
+        build only."""
+        self.N, self.rank, self.world = int(N), int(rank), int(world)
+        self.zb = slab_bounds(self.N, self.world)
+        if self.zb[self.rank + 1] == self.zb[self.rank]:
+            raise ValueError("more ranks than grid planes")
+        self.full = devarray.get_context(N, device)
+        self.slab = Context(N, self.full.device, slab=(self.zb[rank], self.zb[rank + 1]))
+        uid = unique_id if unique_id is not None else new_unique_id()
+        buf = (C.c_char * 128).from_buffer_copy(bytes(uid))
+        L.check(L.lib().pcb_comm_init(self.slab.h, buf, self.rank, self.world), "pcb_comm_init")
+        if host_callbacks is not None:
+            self._cbs = host_callbacks    # keep the ctypes callbacks alive
+            L.check(L.lib().pcb_comm_set_host_callbacks(self.slab.h, C.cast(host_callbacks[0], C.c_void_p),
+                                                        C.cast(host_callbacks[1], C.c_void_p)), "pcb_comm_set_host_callbacks")
+        self._zb_c = (C.c_int * (self.world + 1))(*self.zb)
+        self._work = {}
+
+    def exchange(self, to_full, owners, slab_block, full_ptrs):
+        own = (C.c_int * len(owners))(*owners)
+        fp = (C.c_void_p * len(owners))(*[p if p else None for p in full_ptrs])
+        L.check(L.lib().pcb_slab_exchange(self.slab.h, 1 if to_full else 0, len(owners), own, self._zb_c,
+                                          L.ptr_array(slab_block.ptrs), fp), "pcb_slab_exchange")
+
+    def work_blocks(self, ncols):
+        """Two cached blocks of whole columns on the full context (operator input / output)."""
+        have = self._work.get("n", 0)
+        if have < ncols:
+            self._work = {"n": ncols, "in": self.full.empty(ncols), "out": self.full.empty(ncols)}
+        return self._work["in"], self._work["out"]
+
+    def gather_rows(self, slab_block):
+        """Whole columns of a slab block on every rank as a host array (tests / small problems): all-gather through the
+        exchange, one owner at a time."""
+        out = np.zeros((3 * self.N ** 3, slab_block.k), dtype=np.complex128)
+        for o in range(self.world):
+            win, _ = self.work_blocks(slab_block.k)
+            owners = [o] * slab_block.k
+            self.exchange(True, owners, slab_block, win.ptrs[:slab_block.k] if o == self.rank else [0] * slab_block.k)
+            self.slab.sync()
+            if o == self.rank:
+                out = win.cols(range(slab_block.k)).get()
+        return out
+
+    def close(self):
+        L.check(L.lib().pcb_comm_destroy(self.slab.h), "pcb_comm_destroy")
+
+
+def new_unique_id():
+    buf = (C.c_char * 128)()
+    L.check(L.lib().pcb_comm_unique_id(buf), "pcb_comm_unique_id")
+    return bytes(buf)
+
+
+class ShardedOperator:
+    """pcfft.Operator interface over slab blocks: P and the residual are slab-local, A / H go through whole columns."""
+
+    def __init__(self, comm, a_fft, gamma, shift, pshift, diel=None):
+        self.comm = comm
+        self.ctx = comm.slab
+        self.full = Operator(a_fft, gamma, shift, pshift, diel, ctx=comm.full)
+        self.local = Operator(a_fft, gamma, shift, pshift, None, ctx=comm.slab)     # symbols only: residual + preconditioner
+        self.gamma, self.shift, self.pshift = self.full.gamma, self.full.shift, self.full.pshift
+
+    def residual(self, x, hx, w, lambdas, precond=True):
+        return self.local.residual(x, hx, w, lambdas, precond=precond)
+
+    def apply_into(self, mode, src, dst):
+        if src.k == 0:
+            return dst
+        if mode == L.APPLY_P:
+            return self.local.apply_into(mode, src, dst)
+        cm = self.comm
+        k = src.k
+        owners = [j % cm.world for j in range(k)]
+        mine = [j for j in range(k) if owners[j] == cm.rank]
+        win, wout = cm.work_blocks((k + cm.world - 1) // cm.world)
+        pin, pout = [0] * k, [0] * k
+        for slot, j in enumerate(mine):
+            pin[j], pout[j] = win.ptrs[slot], wout.ptrs[slot]
+        cm.exchange(True, owners, src, pin)            # slabs -> whole columns on their owners
+        cm.slab.sync()
+        if mine:
+            self.full.apply_into(mode, win.cols(range(len(mine))), wout.cols(range(len(mine))))
+            cm.full.sync()
+        cm.exchange(False, owners, dst, pout)          # whole columns -> slabs
+        cm.slab.sync()
+        return dst
+
+    def apply(self, mode, x, out=None):
+        blk, was_host = devarray.as_block(self.ctx, x)
+        res = DeviceBlock(self.ctx, blk.k, vec=blk.vec)
+        self.apply_into(mode, blk, res)
+        return res.get() if was_host else res
+
+
+def pc_mfd_handle_sharded(comm, a_fft, b_fft, Diels, inv_fft, shift=0.0):
+    """(A_func, H_func, P_func) over slab blocks: numerical_experiments.pc_mfd_handle for the large-grid mode.
+    `Diels` must live on comm.full (discretization.*_handle(n, d_flag) on this rank's device)."""
+    gamma, pshift = _sym_consistency(a_fft, b_fft, inv_fft)
+    op = ShardedOperator(comm, a_fft, gamma, shift, pshift if pshift is not None else shift, Diels)
+    return OperatorCallable(op, L.APPLY_A), OperatorCallable(op, L.APPLY_H), OperatorCallable(op, L.APPLY_P)
