@@ -47,6 +47,13 @@ struct Plan {
     // index maps of the strided (y/z) passes
     PCB_HD static int lin(int n1, int n2) { return PFA ? (R2 * n1 + R1 * n2) % N : n1 * R2 + n2; }
     PCB_HD static int lout(int k1, int k2) { return PFA ? (R2 * U * k1 + R1 * V * k2) % N : k1 + R1 * k2; }
+    // the same maps split into a per-digit part (a compile-time constant in unrolled loops, or computed once per item)
+    // and a conditional subtract instead of a modulo per element
+    PCB_HD static int lin1(int n1) { return PFA ? (R2 * n1) % N : n1 * R2; }
+    PCB_HD static int lin2(int n2) { return PFA ? (R1 * n2) % N : n2; }
+    PCB_HD static int lout1(int k1) { return PFA ? (R2 * U * k1) % N : k1; }
+    PCB_HD static int lout2(int k2) { return PFA ? (R1 * V * k2) % N : R1 * k2; }
+    PCB_HD static int wrap(int s) { return PFA ? (s >= N ? s - N : s) : s; }
 };
 
 // z = a x v  (cross product, _kernels.py:51-66)
@@ -164,8 +171,14 @@ __global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * P::R1 * P::R2P * 16,
 // Reads the work column W (in Fourier-x order), the source column X (MODE 2) and writes OUT
 // (OUT may alias W: each CTA only touches its own rows).
 // ---------------------------------------------------------------------------------------
+#ifdef PCB_EMU
+PCB_D void pcb_prefetch_l2(const void*) {}
+#else
+PCB_D void pcb_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
+#endif
+
 template <class P, int LX, int NT, int MODE>
-__global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * P::R1 * P::R2P * 16, P::R1, 3)) k_xinv(PcbOp op, PcbCols cols, const cplx* __restrict__ tw) {
+__global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * P::R1 * P::R2P * 16, P::R1, 4)) k_xinv(PcbOp op, PcbCols cols, const cplx* __restrict__ tw) {
     constexpr int N = P::N, R1 = P::R1, R2 = P::R2, R2P = P::R2P;
     PCB_DYN_SMEM(cplx, sm);   // [3][LX][R1][R2P]
     const int col = blockIdx.y;
@@ -174,16 +187,21 @@ __global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * P::R1 * P::R2P * 16,
     const long long nn = op.nn;
     const int row0 = blockIdx.x * LX;
     const int nrows = N * N;
+    const int nr = (nrows - row0 < LX) ? nrows - row0 : LX;      // rows of this tile
     const int tid = threadIdx.x;
 
+    if (MODE == 2) {   // the epilogue re-reads X: pull this tile's lines (3 contiguous chunks) towards L2 now
+        const int lines = (nr * N * (int)sizeof(cplx) + 127) / 128;
+        for (int l = tid; l < 3 * lines; l += NT)
+            pcb_prefetch_l2(reinterpret_cast<const char*>(X + (l / lines) * nn + (long long)row0 * N) + (l % lines) * 128);
+    }
+    // inverse radix R2 over k2 (fixed k1): global (Fourier order, k = k1 + R1*k2) -> registers -> shared
     for (int item = tid; item < 3 * LX * R1; item += NT) {
-        const int k1 = item % R1;
-        const int r = (item / R1) % LX;
-        const int c = item / (R1 * LX);
-        const int row = row0 + r;
-        if (row >= nrows) continue;
+        const int k1 = item % R1, cr = item / R1;
+        const int r = cr % LX, c = cr / LX;
+        if (r >= nr) continue;
         cplx v[R2];
-        const cplx* __restrict__ src = W + c * nn + (long long)row * N + k1;
+        const cplx* __restrict__ src = W + c * nn + (long long)(row0 + r) * N + k1;
         PCB_UNROLL
         for (int k2 = 0; k2 < R2; ++k2) v[k2] = src[R1 * k2];
         Dft<R2, +1>::run(v);
@@ -191,55 +209,58 @@ __global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * P::R1 * P::R2P * 16,
         for (int n2 = 0; n2 < R2; ++n2) {
             cplx val = v[n2];
             if (k1 > 0) { const cplx t = __ldg(tw + k1 * R2 + n2); val = cmul(val, cmake(t.x, -t.y)); }
-            sm[((c * LX + r) * R1 + k1) * R2P + n2] = val;
+            sm[(cr * R1 + k1) * R2P + n2] = val;
         }
     }
     __syncthreads();
-    for (int item = tid; item < LX * R2; item += NT) {
-        const int r = item / R2, n2 = item % R2;
-        const int row = row0 + r;
-        if (row >= nrows) continue;
-        const int i1 = row % N, i2 = row / N;
-        cplx v[3][R1];
+    // inverse radix R1 over k1 (fixed n2), in place: slot (n1, n2) <-> i0 = n1*R2 + n2
+    for (int item = tid; item < 3 * LX * R2; item += NT) {
+        const int n2 = item % R2, cr = item / R2;
+        if (cr % LX >= nr) continue;
+        cplx v[R1];
         PCB_UNROLL
-        for (int c = 0; c < 3; ++c) {
+        for (int k1 = 0; k1 < R1; ++k1) v[k1] = sm[(cr * R1 + k1) * R2P + n2];
+        Dft<R1, +1>::run(v);
+        PCB_UNROLL
+        for (int n1 = 0; n1 < R1; ++n1) sm[(cr * R1 + n1) * R2P + n2] = v[n1];
+    }
+    __syncthreads();
+    // point-wise epilogue, fully coalesced: 1/N^3, k x v, (+ gamma conj(k)(k.x) + shift x), store
+    constexpr int PB = 4;     // points per thread and batch: all X loads of a batch are issued before they are used
+    for (int e0 = tid; e0 < nr * N; e0 += PB * NT) {
+        cplx x[PB][3];
+        if (MODE == 2) {
             PCB_UNROLL
-            for (int k1 = 0; k1 < R1; ++k1) v[c][k1] = sm[((c * LX + r) * R1 + k1) * R2P + n2];
-            Dft<R1, +1>::run(v[c]);
-        }
-        cplx kc[3];
-        if (MODE) {
-            PCB_UNROLL
-            for (int c = 0; c < 3; ++c) {
-                const cplx b = __ldg(op.T + (c * 3 + 1) * N + i1);
-                const cplx d = __ldg(op.T + (c * 3 + 2) * N + i2);
-                kc[c] = cadd(b, d);
+            for (int q = 0; q < PB; ++q) {
+                const int e = e0 + q * NT;
+                if (e < nr * N) {
+                    PCB_UNROLL
+                    for (int c = 0; c < 3; ++c) x[q][c] = X[c * nn + (long long)row0 * N + e];
+                }
             }
         }
         PCB_UNROLL
-        for (int n1 = 0; n1 < R1; ++n1) {
-            const int i0 = n1 * R2 + n2;
-            const long long e = (long long)row * N + i0;
+        for (int q = 0; q < PB; ++q) {
+            const int e = e0 + q * NT;
+            if (e >= nr * N) continue;
+            const int r = e / N, i0 = e % N;
+            const int row = row0 + r;
+            const int slot = (r * R1 + i0 / R2) * R2P + i0 % R2;
             cplx u[3], z[3];
             PCB_UNROLL
-            for (int c = 0; c < 3; ++c) u[c] = cscale(v[c][n1], op.inv_n3);
+            for (int c = 0; c < 3; ++c) u[c] = cscale(sm[c * LX * R1 * R2P + slot], op.inv_n3);
             if (MODE) {
-                cplx k[3];
-                PCB_UNROLL
-                for (int c = 0; c < 3; ++c) k[c] = cadd(kc[c], __ldg(op.T + (c * 3 + 0) * N + i0));
-                pcb_cross(k, u, z);
+                const Sym3 sy = pcb_symbol(op.T, N, i0, row % N, row / N);
+                pcb_cross(sy.k, u, z);
                 if (MODE == 2) {
-                    cplx x[3];
-                    PCB_UNROLL
-                    for (int c = 0; c < 3; ++c) x[c] = X[c * nn + e];
                     // gamma K_B x = gamma conj(k) (k . x)   (h_block with D_B, pcfft.py:176)
-                    cplx dot = cadd(cadd(cmul(k[0], x[0]), cmul(k[1], x[1])), cmul(k[2], x[2]));
+                    cplx dot = cadd(cadd(cmul(sy.k[0], x[q][0]), cmul(sy.k[1], x[q][1])), cmul(sy.k[2], x[q][2]));
                     dot = cscale(dot, op.gamma);
                     PCB_UNROLL
                     for (int c = 0; c < 3; ++c) {
-                        cplx t = cfmac(k[c], dot, z[c]);
-                        t.x = fma(op.shift, x[c].x, t.x);
-                        t.y = fma(op.shift, x[c].y, t.y);
+                        cplx t = cfmac(sy.k[c], dot, z[c]);
+                        t.x = fma(op.shift, x[q][c].x, t.x);
+                        t.y = fma(op.shift, x[q][c].y, t.y);
                         z[c] = t;
                     }
                 }
@@ -248,7 +269,7 @@ __global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * P::R1 * P::R2P * 16,
                 for (int c = 0; c < 3; ++c) z[c] = u[c];
             }
             PCB_UNROLL
-            for (int c = 0; c < 3; ++c) W[c * nn + e] = z[c];
+            for (int c = 0; c < 3; ++c) W[c * nn + (long long)row0 * N + e] = z[c];
         }
     }
 }
@@ -328,14 +349,16 @@ PCB_HD void pcb_diel_point(const PcbOp& op, unsigned m, cplx u[3]) {
 // one of two shared-memory stages with cp.async while the previous tile is transformed.  The line element with
 // digits (a, b) always lives in slot P::lin(a, b) of its stage, so all four radix steps exchange in place.
 // ---------------------------------------------------------------------------------------
-template <class P>
-PCB_D void pcb_ztile_load(cplx* __restrict__ st, const cplx* __restrict__ Y, long long nn, int t0, int i1, int tid, int nthr) {
+template <class P, int NT>
+PCB_D void pcb_ztile_load(cplx* __restrict__ st, const cplx* __restrict__ Y, long long nn, int t0, int i1, int tid) {
     constexpr int N = P::N;
-    for (int e = tid; e < 3 * N * 8; e += nthr) {
-        const int i0l = e % 8, i2 = (e / 8) % N, c = e / (8 * N);
-        const int i0 = t0 * 8 + i0l;
-        if (i0 < N) pcb_cp16(st + (c * N + i2) * 8 + i0l, Y + c * nn + ((long long)i2 * N + i1) * N + i0);
-    }
+    const int i0l = tid % 8, i0 = t0 * 8 + i0l;
+    if (i0 >= N) return;
+    const cplx* __restrict__ src = Y + (long long)i1 * N + i0;
+    PCB_UNROLL
+    for (int c = 0; c < 3; ++c)
+        for (int i2 = tid / 8; i2 < N; i2 += NT / 8)
+            pcb_cp16(st + (c * N + i2) * 8 + i0l, src + c * nn + (long long)i2 * N * N);
 }
 
 template <class P, int DIEL, int NT>
@@ -347,18 +370,17 @@ __global__ void __launch_bounds__(NT, (DIEL == 2 ? 1 : 2)) k_zmid(PcbOp op, PcbC
     constexpr int NT0 = (N + 7) / 8;
     const int tpc = NT0 * N;
     const int total = tpc * ncols;
-    const long long sline = (long long)N * N;
     const int tid = threadIdx.x;
 
     int tile = blockIdx.x, stage = 0;
     if (tile < total) {
-        pcb_ztile_load<P>(sm, cols.out[tile / tpc], nn, (tile % tpc) % NT0, (tile % tpc) / NT0, tid, NT);
+        pcb_ztile_load<P, NT>(sm, cols.out[tile / tpc], nn, (tile % tpc) % NT0, (tile % tpc) / NT0, tid);
         pcb_cp_commit();
     }
     for (; tile < total; tile += gridDim.x) {
         const int next = tile + gridDim.x;
         if (next < total) {
-            pcb_ztile_load<P>(sm + (stage ^ 1) * STAGE, cols.out[next / tpc], nn, (next % tpc) % NT0, (next % tpc) / NT0, tid, NT);
+            pcb_ztile_load<P, NT>(sm + (stage ^ 1) * STAGE, cols.out[next / tpc], nn, (next % tpc) % NT0, (next % tpc) / NT0, tid);
             pcb_cp_commit();
             pcb_cp_wait<1>();
         } else {
@@ -373,15 +395,17 @@ __global__ void __launch_bounds__(NT, (DIEL == 2 ? 1 : 2)) k_zmid(PcbOp op, PcbC
         for (int item = tid; item < 3 * R2 * 8; item += NT) {
             const int i0l = item % 8, n2 = (item / 8) % R2, c = item / (8 * R2);
             if (t0 * 8 + i0l >= N) continue;
+            cplx* __restrict__ sc = st + c * N * 8 + i0l;
+            const int b2 = P::lin2(n2);
             cplx v[R1];
             PCB_UNROLL
-            for (int n1 = 0; n1 < R1; ++n1) v[n1] = st[(c * N + P::lin(n1, n2)) * 8 + i0l];
+            for (int n1 = 0; n1 < R1; ++n1) v[n1] = sc[P::wrap(P::lin1(n1) + b2) * 8];
             Dft<R1, -1>::run(v);
             PCB_UNROLL
             for (int k1 = 0; k1 < R1; ++k1) {
                 cplx val = v[k1];
                 if (!P::PFA && k1 > 0) val = cmul(val, __ldg(tw + k1 * R2 + n2));
-                st[(c * N + P::lin(k1, n2)) * 8 + i0l] = val;
+                sc[P::wrap(P::lin1(k1) + b2) * 8] = val;
             }
         }
         __syncthreads();
@@ -391,14 +415,16 @@ __global__ void __launch_bounds__(NT, (DIEL == 2 ? 1 : 2)) k_zmid(PcbOp op, PcbC
                 const int i0l = item % 8, k1 = item / 8;
                 const int i0 = t0 * 8 + i0l;
                 if (i0 >= N) continue;
+                const int b1 = P::lin1(k1), o1 = P::lout1(k1);
+                const unsigned char* __restrict__ mp = op.mask + (long long)i1 * N + i0;
                 unsigned char mk[R2];
                 PCB_UNROLL
-                for (int k2 = 0; k2 < R2; ++k2) mk[k2] = __ldg(op.mask + ((long long)P::lout(k1, k2) * N + i1) * N + i0);
+                for (int k2 = 0; k2 < R2; ++k2) mk[k2] = __ldg(mp + P::wrap(o1 + P::lout2(k2)) * (N * N));
                 cplx v[3][R2];
                 PCB_UNROLL
                 for (int c = 0; c < 3; ++c) {
                     PCB_UNROLL
-                    for (int n2 = 0; n2 < R2; ++n2) v[c][n2] = st[(c * N + P::lin(k1, n2)) * 8 + i0l];
+                    for (int n2 = 0; n2 < R2; ++n2) v[c][n2] = st[(c * N + P::wrap(b1 + P::lin2(n2))) * 8 + i0l];
                     Dft<R2, -1>::run(v[c]);
                 }
                 PCB_UNROLL
@@ -414,7 +440,7 @@ __global__ void __launch_bounds__(NT, (DIEL == 2 ? 1 : 2)) k_zmid(PcbOp op, PcbC
                     for (int n2 = 0; n2 < R2; ++n2) {
                         cplx val = v[c][n2];
                         if (!P::PFA && k1 > 0) { const cplx t = __ldg(tw + k1 * R2 + n2); val = cmul(val, cmake(t.x, -t.y)); }
-                        st[(c * N + P::lin(k1, n2)) * 8 + i0l] = val;
+                        st[(c * N + P::wrap(b1 + P::lin2(n2))) * 8 + i0l] = val;
                     }
                 }
             }
@@ -423,27 +449,30 @@ __global__ void __launch_bounds__(NT, (DIEL == 2 ? 1 : 2)) k_zmid(PcbOp op, PcbC
                 const int i0l = item % 8, k1 = (item / 8) % R1, c = item / (8 * R1);
                 const int i0 = t0 * 8 + i0l;
                 if (i0 >= N) continue;
+                const int b1 = P::lin1(k1), o1 = P::lout1(k1);
+                cplx* __restrict__ sc = st + c * N * 8 + i0l;
                 unsigned char mk[R2];
                 if (DIEL == 1) {
+                    const unsigned char* __restrict__ mp = op.mask + (long long)i1 * N + i0;
                     PCB_UNROLL
-                    for (int k2 = 0; k2 < R2; ++k2) mk[k2] = __ldg(op.mask + ((long long)P::lout(k1, k2) * N + i1) * N + i0);
+                    for (int k2 = 0; k2 < R2; ++k2) mk[k2] = __ldg(mp + P::wrap(o1 + P::lout2(k2)) * (N * N));
                 }
                 cplx v[R2];
                 PCB_UNROLL
-                for (int n2 = 0; n2 < R2; ++n2) v[n2] = st[(c * N + P::lin(k1, n2)) * 8 + i0l];
+                for (int n2 = 0; n2 < R2; ++n2) v[n2] = sc[P::wrap(b1 + P::lin2(n2)) * 8];
                 Dft<R2, -1>::run(v);
                 if (DIEL == 1) {
-                    const double sc = op.ediag[c];
+                    const double scl = op.ediag[c];
                     PCB_UNROLL
                     for (int k2 = 0; k2 < R2; ++k2)
-                        if ((mk[k2] >> c) & 1u) v[k2] = cscale(v[k2], sc);
+                        if ((mk[k2] >> c) & 1u) v[k2] = cscale(v[k2], scl);
                 }
                 Dft<R2, +1>::run(v);
                 PCB_UNROLL
                 for (int n2 = 0; n2 < R2; ++n2) {
                     cplx val = v[n2];
                     if (!P::PFA && k1 > 0) { const cplx t = __ldg(tw + k1 * R2 + n2); val = cmul(val, cmake(t.x, -t.y)); }
-                    st[(c * N + P::lin(k1, n2)) * 8 + i0l] = val;
+                    sc[P::wrap(b1 + P::lin2(n2)) * 8] = val;
                 }
             }
         }
@@ -453,13 +482,15 @@ __global__ void __launch_bounds__(NT, (DIEL == 2 ? 1 : 2)) k_zmid(PcbOp op, PcbC
             const int i0l = item % 8, n2 = (item / 8) % R2, c = item / (8 * R2);
             const int i0 = t0 * 8 + i0l;
             if (i0 >= N) continue;
+            const cplx* __restrict__ sc = st + c * N * 8 + i0l;
+            const int b2 = P::lin2(n2);
             cplx v[R1];
             PCB_UNROLL
-            for (int k1 = 0; k1 < R1; ++k1) v[k1] = st[(c * N + P::lin(k1, n2)) * 8 + i0l];
+            for (int k1 = 0; k1 < R1; ++k1) v[k1] = sc[P::wrap(P::lin1(k1) + b2) * 8];
             Dft<R1, +1>::run(v);
             cplx* __restrict__ base = Y + c * nn + (long long)i1 * N + i0;
             PCB_UNROLL
-            for (int n1 = 0; n1 < R1; ++n1) base[P::lin(n1, n2) * sline] = v[n1];
+            for (int n1 = 0; n1 < R1; ++n1) base[(long long)P::wrap(P::lin1(n1) + b2) * (N * N)] = v[n1];
         }
         __syncthreads();
         stage ^= 1;
