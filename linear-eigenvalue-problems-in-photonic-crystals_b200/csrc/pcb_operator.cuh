@@ -84,10 +84,11 @@ template <int N> PCB_D void pcb_cp_wait() { asm volatile("cp.async.wait_group %0
 
 // ---------------------------------------------------------------------------------------
 // Pass 1: x-lines forward.  SYM: 0 plain FFT, 1 multiply by K_A^H = (-conj k) x . on load.
-// Tile = LX consecutive rows (a row = all i0 for one (i1,i2)), all three components; one CTA per tile.  A point-wise phase
-// (all threads, perfectly coalesced, batched loads) applies the symbol and stages the tile; two radix phases run in place.  (A persistent cp.async double-buffered variant was measured on B200 at
-// N = 120: its extra index arithmetic and barriers cost what the prefetch gained -- 0.63 vs 0.61 ms forward, 1.00 vs
-// 0.85 ms inverse for 16 columns -- so the simple form stays; the z pass, with twice the arithmetic per byte, keeps it.)
+// Tile = LX consecutive rows (a row = all i0 for one (i1,i2)), all three components; one CTA per tile, registers stage the
+// radix-R1 input, shared memory the exchange.  Measured alternatives on B200 (N = 120, 16 columns): a persistent cp.async
+// double-buffered variant 0.63 ms and a three-phase variant with a coalesced point-wise prologue 0.53 ms, vs 0.51 ms for this
+// form with the 4-CTAs/SM register cap -- so the simple form stays (the inverse pass, which also re-reads X, does gain from
+// the three-phase structure; the z pass, with twice the arithmetic per byte, from the cp.async pipeline).
 // ---------------------------------------------------------------------------------------
 template <class P, int LX, int NT, int SYM>
 __global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * P::R1 * P::R2P * 16, P::R1, 4)) k_xfwd(PcbOp op, PcbCols cols, const cplx* __restrict__ tw) {
@@ -99,69 +100,68 @@ __global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * P::R1 * P::R2P * 16,
     const long long nn = op.nn;
     const int row0 = blockIdx.x * LX;
     const int nrows = N * N;
-    const int nr = (nrows - row0 < LX) ? nrows - row0 : LX;
     const int tid = threadIdx.x;
 
-    // point-wise prologue, fully coalesced: load the tile (3 contiguous chunks), v = (-conj k) x x, stage in slot (n1, n2)
-    constexpr int PB = 4;     // points per thread and batch: the loads of a batch are issued before they are used
-    for (int e0 = tid; e0 < nr * N; e0 += PB * NT) {
-        cplx x[PB][3];
-        PCB_UNROLL
-        for (int q = 0; q < PB; ++q) {
-            const int e = e0 + q * NT;
-            if (e < nr * N) {
-                PCB_UNROLL
-                for (int c = 0; c < 3; ++c) x[q][c] = X[c * nn + (long long)row0 * N + e];
+    for (int item = tid; item < LX * R2; item += NT) {
+        const int r = item / R2, n2 = item % R2;
+        const int row = row0 + r;
+        if (row >= nrows) continue;
+        const int i1 = row % N, i2 = row / N;
+        cplx v[3][R1];
+        cplx kc[3];
+        if (SYM) {
+            PCB_UNROLL
+            for (int c = 0; c < 3; ++c) {
+                const cplx b = __ldg(op.T + (c * 3 + 1) * N + i1);
+                const cplx d = __ldg(op.T + (c * 3 + 2) * N + i2);
+                kc[c] = cadd(b, d);
             }
         }
         PCB_UNROLL
-        for (int q = 0; q < PB; ++q) {
-            const int e = e0 + q * NT;
-            if (e >= nr * N) continue;
-            const int r = e / N, i0 = e % N;
-            const int slot = (r * R1 + i0 / R2) * R2P + i0 % R2;
+        for (int n1 = 0; n1 < R1; ++n1) {
+            const int i0 = n1 * R2 + n2;
+            const long long e = (long long)row * N + i0;
+            cplx x[3];
+            PCB_UNROLL
+            for (int c = 0; c < 3; ++c) x[c] = X[c * nn + e];
             if (SYM) {
-                const int row = row0 + r;
-                const Sym3 sy = pcb_symbol(op.T, N, i0, row % N, row / N);
                 cplx a[3], z[3];
                 PCB_UNROLL
-                for (int c = 0; c < 3; ++c) a[c] = cmake(-sy.k[c].x, sy.k[c].y);   // -conj(k)
-                pcb_cross(a, x[q], z);
+                for (int c = 0; c < 3; ++c) {
+                    const cplx k = cadd(kc[c], __ldg(op.T + (c * 3 + 0) * N + i0));
+                    a[c] = cmake(-k.x, k.y);   // -conj(k)
+                }
+                pcb_cross(a, x, z);
                 PCB_UNROLL
-                for (int c = 0; c < 3; ++c) sm[c * LX * R1 * R2P + slot] = z[c];
+                for (int c = 0; c < 3; ++c) v[c][n1] = z[c];
             } else {
                 PCB_UNROLL
-                for (int c = 0; c < 3; ++c) sm[c * LX * R1 * R2P + slot] = x[q][c];
+                for (int c = 0; c < 3; ++c) v[c][n1] = x[c];
+            }
+        }
+        PCB_UNROLL
+        for (int c = 0; c < 3; ++c) {
+            Dft<R1, -1>::run(v[c]);
+            PCB_UNROLL
+            for (int k1 = 0; k1 < R1; ++k1) {
+                cplx val = v[c][k1];
+                if (k1 > 0) val = cmul(val, __ldg(tw + k1 * R2 + n2));
+                sm[((c * LX + r) * R1 + k1) * R2P + n2] = val;
             }
         }
     }
     __syncthreads();
-    // radix R1 over n1 (fixed n2), twiddle, in place
-    for (int item = tid; item < 3 * LX * R2; item += NT) {
-        const int n2 = item % R2, cr = item / R2;          // cr = c*LX + r
-        if (cr % LX >= nr) continue;
-        cplx v[R1];
-        PCB_UNROLL
-        for (int n1 = 0; n1 < R1; ++n1) v[n1] = sm[(cr * R1 + n1) * R2P + n2];
-        Dft<R1, -1>::run(v);
-        PCB_UNROLL
-        for (int k1 = 0; k1 < R1; ++k1) {
-            cplx val = v[k1];
-            if (k1 > 0) val = cmul(val, __ldg(tw + k1 * R2 + n2));
-            sm[(cr * R1 + k1) * R2P + n2] = val;
-        }
-    }
-    __syncthreads();
-    // radix R2 over n2 (fixed k1) and store: k = k1 + R1*k2
     for (int item = tid; item < 3 * LX * R1; item += NT) {
-        const int k1 = item % R1, cr = item / R1;
-        const int r = cr % LX, c = cr / LX;
-        if (r >= nr) continue;
+        const int k1 = item % R1;
+        const int r = (item / R1) % LX;
+        const int c = item / (R1 * LX);
+        const int row = row0 + r;
+        if (row >= nrows) continue;
         cplx v[R2];
         PCB_UNROLL
-        for (int n2 = 0; n2 < R2; ++n2) v[n2] = sm[(cr * R1 + k1) * R2P + n2];
+        for (int n2 = 0; n2 < R2; ++n2) v[n2] = sm[((c * LX + r) * R1 + k1) * R2P + n2];
         Dft<R2, -1>::run(v);
-        cplx* __restrict__ dst = Y + c * nn + (long long)(row0 + r) * N + k1;
+        cplx* __restrict__ dst = Y + c * nn + (long long)row * N + k1;
         PCB_UNROLL
         for (int k2 = 0; k2 < R2; ++k2) dst[R1 * k2] = v[k2];
     }
