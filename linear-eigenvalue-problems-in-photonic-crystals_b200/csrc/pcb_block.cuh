@@ -194,41 +194,24 @@ PCB_HD void pcb_pair_from_index(int p, int nb, int& ia, int& ib) {   // row-majo
     ia = a; ib = a + rem;
 }
 
-// Work split: a unit = (tile pair, k4-step of the stage); units are dealt to the warps in contiguous, equal ranges
-// (split = 1: a pair may be shared by two consecutive warps, each writing its part to its own slot of the partial buffer),
-// so all warps of a CTA reach the stage barrier together.  split = 0 (large n): whole pairs per warp.
 __global__ void __launch_bounds__(32 * PCB_GM_MAXW, 1)
-k_gram2(PcbColList S, PcbColList HS, int n, int nt, long long R, int split, cplx* __restrict__ partial /* [gridDim.x][2 slots][2][nc*nc] */) {
+k_gram2(PcbColList S, PcbColList HS, int n, int nt, long long R, cplx* __restrict__ partial /* [gridDim.x][2][nc*nc] */) {
     PCB_DYN_SMEM(cplx, sm);                      // [2 stages][2: S, HS][nc][LD]
     const int nc = 8 * nt;
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int warp = tid >> 5, lane = tid & 31, W = nthr >> 5;
     const int g = lane >> 2, tig = lane & 3;
     const size_t matElems = (size_t)nc * PCB_GM_LD;
-    constexpr int STEPS = PCB_GM_TR / 2;
-    // units of this warp: [u0, u1)
+    // tile pairs of this warp
     const int npairs = nt * (nt + 1) / 2;
-    int u0, u1;
-    if (split) {
-        const int units = npairs * STEPS, upw = (units + W - 1) / W;
-        u0 = warp * upw; u1 = u0 + upw; if (u1 > units) u1 = units; if (u0 > units) u0 = units;
-    } else {
-        const int base = npairs / W, extra = npairs % W;
-        const int p0 = warp * base + (warp < extra ? warp : extra);
-        u0 = p0 * STEPS; u1 = (p0 + base + (warp < extra ? 1 : 0)) * STEPS;
-    }
-    const int pfirst = u0 / STEPS;
-    const int cnt = (u1 > u0) ? (u1 - 1) / STEPS - pfirst + 1 : 0;      // pairs touched (<= PCB_GM_PPW by construction)
-    int ta[PCB_GM_PPW], tb[PCB_GM_PPW], s0[PCB_GM_PPW], s1[PCB_GM_PPW];
+    const int base = npairs / W, extra = npairs % W;
+    const int cnt = base + (warp < extra ? 1 : 0);
+    const int p0 = warp * base + (warp < extra ? warp : extra);
+    int ta[PCB_GM_PPW], tb[PCB_GM_PPW];
     PCB_UNROLL
     for (int i = 0; i < PCB_GM_PPW; ++i) {
-        ta[i] = tb[i] = 0; s0[i] = s1[i] = 0;
-        if (i < cnt) {
-            pcb_pair_from_index(pfirst + i, nt, ta[i], tb[i]);
-            const int lo = (pfirst + i) * STEPS, hi = lo + STEPS;
-            s0[i] = (u0 > lo ? u0 : lo) - lo;
-            s1[i] = (u1 < hi ? u1 : hi) - lo;
-        }
+        ta[i] = tb[i] = 0;
+        if (i < cnt) pcb_pair_from_index(p0 + i, nt, ta[i], tb[i]);
     }
     double acc[PCB_GM_PPW][4][2];
     PCB_UNROLL
@@ -262,18 +245,16 @@ k_gram2(PcbColList S, PcbColList HS, int n, int nt, long long R, int split, cplx
         const long long tn = t + gridDim.x;
         if (tn < ntiles) { load_tile(tn, stage ^ 1); pcb_cp_wait<1>(); } else { pcb_cp_wait<0>(); }
         __syncthreads();
-        const double* sS = reinterpret_cast<const double*>(sm + (size_t)(stage * 2) * matElems);
-        const double* sH = reinterpret_cast<const double*>(sm + (size_t)(stage * 2 + 1) * matElems);
+        const double* s0 = reinterpret_cast<const double*>(sm + (size_t)(stage * 2) * matElems);
+        const double* h0 = reinterpret_cast<const double*>(sm + (size_t)(stage * 2 + 1) * matElems);
         PCB_UNROLL
         for (int i = 0; i < PCB_GM_PPW; ++i) {
             if (i < cnt) {
-                const double* pa = sS + (size_t)(ta[i] * 8 + g) * (2 * PCB_GM_LD);
-                const double* pb = sS + (size_t)(tb[i] * 8 + g) * (2 * PCB_GM_LD);
-                const double* ph = sH + (size_t)(tb[i] * 8 + g) * (2 * PCB_GM_LD);
-#ifndef PCB_EMU
-#pragma unroll 4
-#endif
-                for (int step = s0[i]; step < s1[i]; ++step) {
+                const double* pa = s0 + (size_t)(ta[i] * 8 + g) * (2 * PCB_GM_LD);
+                const double* pb = s0 + (size_t)(tb[i] * 8 + g) * (2 * PCB_GM_LD);
+                const double* ph = h0 + (size_t)(tb[i] * 8 + g) * (2 * PCB_GM_LD);
+                PCB_UNROLL
+                for (int step = 0; step < PCB_GM_TR / 2; ++step) {
                     const int o = 4 * step + tig, os = 4 * step + (tig ^ 1);
                     const double a = pa[o];
                     const double a2 = (tig & 1) ? -a : a;
@@ -287,23 +268,22 @@ k_gram2(PcbColList S, PcbColList HS, int n, int nt, long long R, int split, cplx
         __syncthreads();
         stage ^= 1;
     }
-    cplx* out = partial + (size_t)blockIdx.x * 4 * nc * nc;
+    cplx* out = partial + (size_t)blockIdx.x * 2 * nc * nc;
     PCB_UNROLL
     for (int i = 0; i < PCB_GM_PPW; ++i) {
         if (i < cnt) {
-            cplx* o2 = out + ((s0[i] > 0) ? 2 * nc * nc : 0);      // a pair continued from the previous warp goes to slot 1
             const int ra = ta[i] * 8 + g;
             PCB_UNROLL
             for (int j = 0; j < 2; ++j) {
                 const int cb = tb[i] * 8 + 2 * tig + j;
-                o2[ra * nc + cb] = cmake(acc[i][0][j], acc[i][1][j]);
-                o2[nc * nc + ra * nc + cb] = cmake(acc[i][2][j], acc[i][3][j]);
+                out[ra * nc + cb] = cmake(acc[i][0][j], acc[i][1][j]);
+                out[nc * nc + ra * nc + cb] = cmake(acc[i][2][j], acc[i][3][j]);
             }
         }
     }
 }
 
-// Sum the per-CTA partials (both slots) in fixed order and complete the Hermitian matrices:
+// Sum the per-CTA partials in fixed order and complete the Hermitian matrices:
 // entry (a,b) was accumulated iff tile(a) <= tile(b); the others are conj of (b,a).
 __global__ void k_gram_finish(const cplx* __restrict__ partial, int nblocks, int nt, cplx* __restrict__ out /* [2][nc*nc] */) {
     const int nc = 8 * nt;
@@ -314,10 +294,7 @@ __global__ void k_gram_finish(const cplx* __restrict__ partial, int nblocks, int
     const bool direct = (a / 8) <= (b / 8);
     const int src = direct ? a * nc + b : b * nc + a;
     cplx v = cmake(0.0, 0.0);
-    for (int k = 0; k < nblocks; ++k) {
-        const cplx* pk = partial + (size_t)k * 4 * nc * nc + which * nc * nc + src;
-        v = cadd(v, cadd(pk[0], pk[2 * nc * nc]));
-    }
+    for (int k = 0; k < nblocks; ++k) v = cadd(v, partial[(size_t)k * 2 * nc * nc + which * nc * nc + src]);
     out[e] = direct ? v : cconj(v);
 }
 

@@ -558,26 +558,21 @@ int pcb_gram2(pcb_ctx* c, int n, const void* const* s, const void* const* hs, vo
     const int npairs = nt * (nt + 1) / 2;
     int W = 4 * ((npairs + 4 * PCB_GM_PPW - 1) / (4 * PCB_GM_PPW));     // multiple of 4 warps, <= PPW tile pairs per warp
     if (W > PCB_GM_MAXW) { pcb_set_error("pcb_gram2: n = %d needs %d warps", n, W); return -2; }
-    // equal (pair, k-step) ranges per warp when a range can touch at most PPW pairs: ceil(16 npairs / W) <= 16 (PPW-1) + 1
-    const int steps = PCB_GM_TR / 2;
-    const int upw = (npairs * steps + W - 1) / W;       // >= steps: a pair is shared by at most two consecutive warps (two slots)
-    const int split = (upw <= steps * (PCB_GM_PPW - 1) + 1 && upw >= steps) ? 1 : 0;
     const size_t smem = sizeof(cplx) * 4 * (size_t)nc * PCB_GM_LD;
     const long long ntiles = (c->R + PCB_GM_TR - 1) / PCB_GM_TR;
     int per_sm = (int)((size_t)224 * 1024 / (smem + 1024)); if (per_sm < 1) per_sm = 1;
     const int by_threads = 2048 / (32 * W); if (per_sm > by_threads) per_sm = by_threads;
     if (per_sm > 4) per_sm = 4;
     long long gx = (long long)c->sms * per_sm; if (gx > ntiles) gx = ntiles;
-    const size_t pbytes = sizeof(cplx) * (size_t)gx * 4 * nc * nc;       // two slots per CTA
+    const size_t pbytes = sizeof(cplx) * (size_t)gx * 2 * nc * nc;
     if (ensure_partial(c, pbytes)) return -1;
     if (ensure_dsmall(c, sizeof(cplx) * 2 * PCB_MAXL * PCB_MAXL + 65536)) return -1;
     if (ensure_hstage(c, sizeof(cplx) * 2 * PCB_MAXL * PCB_MAXL + 65536)) return -1;
-    PCB_CUDA_OK(cudaMemsetAsync(c->partial, 0, pbytes, c->stream));
 #ifndef PCB_EMU
     if (smem > 48 * 1024) PCB_CUDA_OK(cudaFuncSetAttribute(k_gram2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 #endif
     dim3 grid((unsigned)gx, 1, 1);
-    PCB_LAUNCH(k_gram2, grid, dim3(32 * W, 1, 1), smem, c->stream, S, HS, n, nt, c->R, split, (cplx*)c->partial);
+    PCB_LAUNCH(k_gram2, grid, dim3(32 * W, 1, 1), smem, c->stream, S, HS, n, nt, c->R, (cplx*)c->partial);
     PCB_CUDA_OK(cudaGetLastError());
     cplx* dout = (cplx*)c->dsmall;
     const int ne = 2 * nc * nc;
