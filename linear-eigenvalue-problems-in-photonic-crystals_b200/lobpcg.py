@@ -138,7 +138,7 @@ def lobpcg_sep_softlock(h_func_in, p_func, x0, nev, shift=0.0, tol=TOL, maxiter=
 
         try:
             ss, shs = gram_pair(s_loc, hs_loc)
-            lambdas, eigvec = rr_small(ss, shs)
+            lambdas, eigvec = rr_small(ss, shs, min_rank=m)
         except np.linalg.LinAlgError:
             return None, None, None
         if np.isnan(lambdas).any() or np.isnan(eigvec).any():

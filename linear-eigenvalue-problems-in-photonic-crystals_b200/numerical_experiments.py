@@ -175,7 +175,7 @@ def _load_or_init_record(path_bandgap, var_it, var_fq, n_k, type, d_flag, n):
 
 
 def bandgap(n, d_flag, solver=lobpcg_sep_softlock, type=TYPE0, eps_opt=0, indices=None, nev=NEV, seed=None,
-            path=None, tol=TOL / SCAL / SCAL):
+            path=None, tol=TOL / SCAL / SCAL, only=None):
     """Band structure along the lattice's k-path, one warm-started LOBPCG solve per point, checkpointed to
     JSON after every point (numerical_experiments.py:313-496).  Returns the list of failed indices.
     `nev` (default NEV), `seed` (reproducible random starts) and `path` (output file) are additions."""
@@ -194,6 +194,10 @@ def bandgap(n, d_flag, solver=lobpcg_sep_softlock, type=TYPE0, eps_opt=0, indice
     gap_rec_it, gap_rec_fq = gap_lib[var_it], gap_lib[var_fq]
     if indices is None:
         indices = list(range(n_k)) if uncomputed is None else uncomputed
+        if only is not None:          # resume restricted to the given rows (the file may hold other ranks' empty rows)
+            indices = [i for i in indices if i in set(only)]
+            if not indices:
+                return []
     elif len(indices) == 0:
         return []
     indices = [int(i) for i in indices]
@@ -276,7 +280,7 @@ def merge_records(parts, n_k, nev=NEV):
 
 
 def bandgap_sharded(n, d_flag, rank, world, type=TYPE0, eps_opt=0, nev=NEV, seed=1000, out_dir=None, indices=None,
-                    gather=None, tol=TOL / SCAL / SCAL):
+                    gather=None, tol=TOL / SCAL / SCAL, retry=1):
     """k-path sharding over `world` processes (one GPU each): rank r solves chunk r of the path (or of `indices`)
     into its own JSON file; with `gather` (callable: obj -> list of objs on rank 0, e.g. a torch.distributed
     gather_object wrapper) rank 0 merges all rows into the reference-format file.  No collective touches the data path."""
@@ -288,6 +292,14 @@ def bandgap_sharded(n, d_flag, rank, world, type=TYPE0, eps_opt=0, nev=NEV, seed
     if os.path.exists(part_path):
         os.remove(part_path)
     errs = bandgap(n, d_flag, type=type, eps_opt=eps_opt, indices=mine, nev=nev, seed=seed, path=part_path, tol=tol) if mine else []
+    # A warm start can make [X W] numerically rank deficient (e.g. the point after Gamma, whose zero modes are pure gradients):
+    # the reference records [-1,-1] and recomputes such rows from a random start when bandgap() is called again
+    # (numerical_experiments.py:370-390); do that second call here.
+    for attempt in range(retry):
+        if not errs:
+            break
+        errs = bandgap(n, d_flag, type=type, eps_opt=eps_opt, indices=None, nev=nev, seed=seed + 7919 * (attempt + 1),
+                       path=part_path, tol=tol, only=errs)
     rows = {"iterations": {}, "frequencies": {}, "errors": errs}
     if mine:
         with open(part_path) as f:

@@ -27,9 +27,29 @@ def gram_pair(s, hs):
     return G, T
 
 
-def rr_small(ss, shs):
-    """L = inv(chol(G)); eigh(L T L^H); E = L^H V (orthogonalization.py:148-151) on the small matrices."""
-    Lm = np.linalg.inv(np.linalg.cholesky(ss))
+RANK_TOL = 1e-14      # relative eigenvalue threshold of the rank-revealing fallback below
+
+
+def rr_small(ss, shs, min_rank=None):
+    """L = inv(chol(G)); eigh(L T L^H); E = L^H V (orthogonalization.py:148-151) on the small matrices.
+
+    Fallback when G is numerically singular (Cholesky breaks down): the reference's CuPy path does not notice the
+    breakdown (cuSOLVER potrf reports it through `info`, which cupy.linalg.cholesky ignores) and carries on with a partly
+    unfactorised L; NumPy raises.  Typical trigger: the k-point after Gamma, warm-started with Gamma's zero modes (pure
+    gradients), where K_P^-1 r is parallel to x up to ~1e-8 and cond(G) ~ 1e16.  Here the search space is instead whitened
+    through the eigen-decomposition of G with the null directions (eigenvalue < RANK_TOL * max) removed -- the standard
+    rank-revealing Rayleigh-Ritz; E then has fewer columns than rows.  Well-conditioned cases never take this branch."""
+    try:
+        Lm = np.linalg.inv(np.linalg.cholesky(ss))
+    except np.linalg.LinAlgError:
+        w, U = np.linalg.eigh(ss)
+        keep = w > RANK_TOL * w[-1]
+        if min_rank is not None and keep.sum() < min_rank:
+            raise
+        Wh = U[:, keep] / np.sqrt(w[keep])
+        t = Wh.conj().T @ shs @ Wh
+        lam, v = np.linalg.eigh(hermitize(t))
+        return lam, Wh @ v
     t = (Lm @ shs) @ Lm.conj().T
     lam, v = np.linalg.eigh(t)
     return lam, Lm.conj().T @ v
