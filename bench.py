@@ -262,8 +262,12 @@ def main():
 
     peak, peak_src = measured_peak()
     achieved = B_OP_PER_N3 * n ** 3 * m / (ms_step * 1e-3) / 1e9 * 1.0     # per rank: every rank runs the same step
+    # DRAM bytes of one launch (= one 16-column block apply) from the ncu --set full capture of these kernels at this
+    # shape (profiles/r01_c_final_ncu.md: dram__bytes_read.sum + dram__bytes_write.sum over the five passes); null otherwise
+    traffic = 14.51e9 if (n == 120 and m == 16) else None
     roofline = {"bound": "hbm", "kernel": "op-apply = 5 fused FFT passes (k_xfwd, k_line, k_zmid, k_line, k_xinv)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "fp64_pipe_busy_ms_per_launch": 1.46 if (n == 120 and m == 16) else None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": B_OP_PER_N3 * n ** 3 * m,
                 "moved_bytes_per_launch": float(pass_bytes.sum()), "moved_GBps": float(pass_bytes.sum() / (ms_step * 1e-3) / 1e9)}
 
