@@ -203,6 +203,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="pcb200", choices=["pcb200", "reference"])
     ap.add_argument("--n", type=int, default=N_GRID)
+    ap.add_argument("--cols", type=int, default=M_BLOCK, help="block width m (16 for 10 bands, 32 for 20 bands)")
     ap.add_argument("--kpoints", type=int, default=3, help="k-points per rank for the LOBPCG leg (0 = skip)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
@@ -217,7 +218,7 @@ def main():
     pcb.set_device(dist.local)
     if pcb.backend() != "cuda-sm_100a":
         raise SystemExit("bench.py requires the CUDA build of libpcb200.so")
-    n, m = args.n, M_BLOCK
+    n, m = args.n, args.cols
     ne, mfd = pcb.numerical_experiments, pcb.discretization
     ctx = pcb.get_context(n)
     alphas, chunk = fcc_alpha(pcb, dist.rank, dist.world)
