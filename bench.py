@@ -287,19 +287,19 @@ def main():
             return ctx.timer_stop() / reps
 
         t = timed(lambda: op.residual(S[:, :m], HS[:, :m], S[:, m:2 * m], lam, precond=True))
-        blocks.append({"name": "residual+norms+precond (m=16)", "ms": t, "GBps": 3 * m * Rb / t / 1e6})
+        blocks.append({"name": f"residual+norms+precond (m={m})", "ms": t, "GBps": 3 * m * Rb / t / 1e6})
         G = np.empty((3 * m, 3 * m), dtype=np.complex128); T = np.empty_like(G)
         t = timed(lambda: L.check(L.lib().pcb_gram2(ctx.h, 3 * m, L.ptr_array(S.ptrs), L.ptr_array(HS.ptrs), G.ctypes.data, T.ctypes.data), "gram2"))
         nl = 3 * m
-        blocks.append({"name": "gram pair (n_loc=48)", "ms": t, "GBps": 2 * nl * Rb / t / 1e6,
+        blocks.append({"name": f"gram pair (n_loc={3 * m})", "ms": t, "GBps": 2 * nl * Rb / t / 1e6,
                        "GFLOPs": 8.0 * ctx.R * nl * (nl + 1) / t / 1e6})
         E = np.ascontiguousarray(np.random.default_rng(0).standard_normal((nl, m)) + 0j) / nl
         t = timed(lambda: L.check(L.lib().pcb_update(ctx.h, m, nl, L.ptr_array(S.ptrs), L.ptr_array(HS.ptrs), L.ptr_array(S[:, 2 * m:].ptrs),
                                                      L.ptr_array(HS[:, 2 * m:].ptrs), E.ctypes.data), "update"))
-        blocks.append({"name": "fused update (m=16, n_loc=48)", "ms": t, "GBps": (2 * nl + 4 * m) * Rb / t / 1e6,
+        blocks.append({"name": f"fused update (m={m}, n_loc={3 * m})", "ms": t, "GBps": (2 * nl + 4 * m) * Rb / t / 1e6,
                        "GFLOPs": 16.0 * ctx.R * m * nl / t / 1e6})
         t = timed(lambda: op.apply_into(L.APPLY_H, S[:, :m], HS[:, :m]))
-        blocks.append({"name": "H apply (16 columns)", "ms": t, "GBps": B_OP_PER_N3 * n ** 3 * m / t / 1e6})
+        blocks.append({"name": f"H apply ({m} columns)", "ms": t, "GBps": B_OP_PER_N3 * n ** 3 * m / t / 1e6})
         del S, HS
 
     # ---- end to end: host (pinned) buffers through the reference-facing callable ---------------------------------

@@ -363,7 +363,7 @@ PCB_D void pcb_ztile_load(cplx* __restrict__ st, const cplx* __restrict__ Y, lon
 }
 
 template <class P, int DIEL, int NT>
-__global__ void __launch_bounds__(NT, (DIEL == 2 ? 1 : 2)) k_zmid(PcbOp op, PcbCols cols, const cplx* __restrict__ tw, int ncols) {
+__global__ void __launch_bounds__(NT, ((DIEL == 2 || NT > 256) ? 1 : 2)) k_zmid(PcbOp op, PcbCols cols, const cplx* __restrict__ tw, int ncols) {
     constexpr int N = P::N, R1 = P::R1, R2 = P::R2;
     constexpr int STAGE = 3 * N * 8;
     PCB_DYN_SMEM(cplx, sm);   // [2 stages][3][N][8]

@@ -11,12 +11,13 @@ namespace {
 
 typedef Plan<PCB_N, PCB_R1, PCB_R2> P;
 constexpr int NT = 128;      // y lines and split z passes (one CTA per tile)
-constexpr int NTP = 256;     // persistent x / z-mid kernels
+constexpr int NTP = 256;     // persistent z-mid kernel: 2 CTAs/SM of 256 threads when two stages fit twice in shared memory,
 constexpr int kRowBytes = 3 * P::R1 * P::R2P * (int)sizeof(cplx);
 constexpr int LX = (8 * kRowBytes <= 65536) ? 8 : (4 * kRowBytes <= 65536) ? 4 : (2 * kRowBytes <= 65536) ? 2 : 1;
 constexpr int kStageX = LX * kRowBytes;               // one x-tile (three components)
 constexpr int kSmemL = 3 * P::N * 8 * (int)sizeof(cplx);
 constexpr int kSmemZ = 2 * kSmemL;                       // two stages
+constexpr int NTZ = (2 * (kSmemZ + 1024) <= 224 * 1024) ? NTP : 512;   // ... else one CTA/SM of 512 threads
 
 template <class K>
 int set_smem(K kern, int bytes) {
@@ -40,7 +41,7 @@ inline int ctas_per_sm(int smem, int regs_hint_threads) {
         PCB_CUDA_OK(cudaGetLastError());                                            \
     } while (0)
 // persistent CTAs striding over (column, tile)
-#define PCB_GO_P(KERN, TILES, SMEM, MAXCTA)                                         \
+#define PCB_GO_P(KERN, NTHR, TILES, SMEM, MAXCTA)                                   \
     do {                                                                            \
         auto kfn = KERN;                                                            \
         if (set_smem(kfn, (SMEM))) return -1;                                       \
@@ -48,7 +49,7 @@ inline int ctas_per_sm(int smem, int regs_hint_threads) {
         const long long tot = (long long)(TILES) * ncols;                           \
         if (gx > tot) gx = tot;                                                     \
         dim3 grid((unsigned)gx, 1, 1);                                              \
-        PCB_LAUNCH(kfn, grid, dim3(NTP, 1, 1), (size_t)(SMEM), s, op, cols, tw, ncols); \
+        PCB_LAUNCH(kfn, grid, dim3((NTHR), 1, 1), (size_t)(SMEM), s, op, cols, tw, ncols); \
         PCB_CUDA_OK(cudaGetLastError());                                            \
     } while (0)
 
@@ -67,9 +68,9 @@ int run_pass(const PcbOp& op, const PcbCols& cols, int ncols, int pass_id, const
         case PCB_PASS_XINV_A:   PCB_GO((k_xinv<P, LX, NT, 1>), GX, kStageX); break;
         case PCB_PASS_XINV_H:   PCB_GO((k_xinv<P, LX, NT, 2>), GX, kStageX); break;
         case PCB_PASS_ZMID:
-            if (op.diel == PCB_DIEL_NONE) PCB_GO_P((k_zmid<P, 0, NTP>), GL, kSmemZ, 2);
-            else if (op.diel == PCB_DIEL_CHIRAL) PCB_GO_P((k_zmid<P, 1, NTP>), GL, kSmemZ, 2);
-            else if (op.diel == PCB_DIEL_TRIVIAL) PCB_GO_P((k_zmid<P, 2, NTP>), GL, kSmemZ, 2);
+            if (op.diel == PCB_DIEL_NONE) PCB_GO_P((k_zmid<P, 0, NTZ>), NTZ, GL, kSmemZ, 2);
+            else if (op.diel == PCB_DIEL_CHIRAL) PCB_GO_P((k_zmid<P, 1, NTZ>), NTZ, GL, kSmemZ, 2);
+            else if (op.diel == PCB_DIEL_TRIVIAL) PCB_GO_P((k_zmid<P, 2, NTP>), NTP, GL, kSmemZ, 2)   // v[3][R2] per thread: keep 256 threads;
             else { pcb_set_error("zmid: dielectric type %d has no fused z pass", op.diel); return -1; }
             break;
         default: pcb_set_error("unknown pass id %d", pass_id); return -1;
