@@ -70,7 +70,7 @@ int run_pass(const PcbOp& op, const PcbCols& cols, int ncols, int pass_id, const
         case PCB_PASS_ZMID:
             if (op.diel == PCB_DIEL_NONE) PCB_GO_P((k_zmid<P, 0, NTZ>), NTZ, GL, kSmemZ, 2);
             else if (op.diel == PCB_DIEL_CHIRAL) PCB_GO_P((k_zmid<P, 1, NTZ>), NTZ, GL, kSmemZ, 2);
-            else if (op.diel == PCB_DIEL_TRIVIAL) PCB_GO_P((k_zmid<P, 2, NTP>), NTP, GL, kSmemZ, 2)   // v[3][R2] per thread: keep 256 threads;
+            else if (op.diel == PCB_DIEL_TRIVIAL) PCB_GO_P((k_zmid<P, 2, NTP>), NTP, GL, kSmemZ, 2);   // v[3][R2] per thread: keep 256 threads
             else { pcb_set_error("zmid: dielectric type %d has no fused z pass", op.diel); return -1; }
             break;
         default: pcb_set_error("unknown pass id %d", pass_id); return -1;
