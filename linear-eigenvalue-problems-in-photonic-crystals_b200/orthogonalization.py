@@ -70,8 +70,29 @@ def rayleigh_ritz_chol_sep(s, hs):
     return lam, vec, time.time() - t0
 
 
+def GEP_chol(T, G, herm=True, slice=None):
+    """Small dense GEP T v = lambda G v reduced to an SEP by Cholesky (orthogonalization.py:99-115); host matrices.
+    Returns (lambdas, eigvec, seconds), optionally the first `slice` pairs."""
+    t0 = time.time()
+    T, G = np.asarray(T), np.asarray(G)
+    Lm = np.linalg.inv(np.linalg.cholesky(G))
+    Tw = (Lm @ T) @ Lm.conj().T
+    lam, vec = np.linalg.eigh(Tw) if herm else np.linalg.eig(Tw)
+    vec = Lm.conj().T @ vec
+    dt = time.time() - t0
+    if slice is None:
+        return lam, vec, dt
+    return lam[:slice], vec[:, :slice], dt
+
+
 def short_qr(x):
-    """CholQR: x inv(chol(herm(x^H x)))^H (orthogonalization.py:36-46) on a DeviceBlock, in place."""
+    """CholQR: x inv(chol(herm(x^H x)))^H (orthogonalization.py:36-46) on a DeviceBlock, in place; NumPy input is
+    uploaded, orthonormalised on the device and returned as a host array."""
+    if not isinstance(x, DeviceBlock):
+        from .pcfft import _to_device
+        xb = _to_device(x)
+        short_qr(xb)
+        return xb.get()
     G, _ = gram_pair(x, x)
     Linv = np.linalg.inv(np.linalg.cholesky(G))
     E = np.ascontiguousarray(Linv.conj().T)
@@ -79,12 +100,11 @@ def short_qr(x):
 
 
 def block_times_small(x, E):
-    """x <- x @ E for a DeviceBlock x (R x m) and host E (m x m), via the fused update kernel with an empty P part."""
+    """x <- x @ E for a DeviceBlock x (R x m) and host E (m x m), via the fused update kernel with an empty W/P part."""
     m = x.k
-    tmp = DeviceBlock(x.ctx, m)
-    hx_dummy = DeviceBlock(x.ctx, m)
-    hx_dummy.assign(x)
+    hx, p_out, hp_out = x.copy(), DeviceBlock(x.ctx, m), DeviceBlock(x.ctx, m)     # HS twin and (zero) P outputs of the kernel
     E = np.ascontiguousarray(E, dtype=np.complex128)
-    L.check(L.lib().pcb_update(x.ctx.h, m, m, L.ptr_array(x.ptrs), L.ptr_array(hx_dummy.ptrs), L.ptr_array(tmp.ptrs),
-                               L.ptr_array(DeviceBlock(x.ctx, m).ptrs), E.ctypes.data), "pcb_update")
+    L.check(L.lib().pcb_update(x.ctx.h, m, m, L.ptr_array(x.ptrs), L.ptr_array(hx.ptrs), L.ptr_array(p_out.ptrs),
+                               L.ptr_array(hp_out.ptrs), E.ctypes.data), "pcb_update")
+    x.ctx.sync()          # the temporaries may be released once the kernel has run
     return x

@@ -108,3 +108,21 @@ def test_fft_roundtrip_and_scipy(pcb):
         assert relerr(F.get(), want) < 1e-13, N
         back = pcb.pcfft.fftn3(F, inverse=True)
         assert relerr(back.get(), a) < 1e-13, N
+
+
+def test_short_qr_and_gep_chol(pcb):
+    """CholQR of a block on the device (orthogonalization.py:36-46) and the small GEP helper (:99-115)."""
+    ctx, a, A = _blocks(pcb, 6, 9, 21)
+    Q = pcb.orthogonalization.short_qr(A)
+    q = Q.get()
+    assert relerr(q.conj().T @ q, np.eye(9)) < 1e-12
+    l = np.linalg.cholesky((a.conj().T @ a + (a.conj().T @ a).conj().T) / 2)
+    assert relerr(q, a @ np.linalg.inv(l.conj().T)) < 1e-11
+    rng = np.random.default_rng(3)
+    B = rng.standard_normal((7, 7)) + 1j * rng.standard_normal((7, 7))
+    G = B @ B.conj().T + 7 * np.eye(7)
+    T = (B + B.conj().T) / 2
+    lam, vec, _ = pcb.orthogonalization.GEP_chol(T, G)
+    assert np.allclose(T @ vec, G @ vec * lam, atol=1e-10)
+    import scipy.linalg
+    assert np.allclose(lam, scipy.linalg.eigh(T, G, eigvals_only=True), atol=1e-11)
