@@ -1,0 +1,42 @@
+"""Where does a LOBPCG solve spend its time?  Wraps the five C-ABI calls and the host RR with synchronising timers."""
+import importlib, os, sys, time, json
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ.setdefault("PCB200_QUIET", "1")
+pcb = importlib.import_module("linear-eigenvalue-problems-in-photonic-crystals_b200")
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 120
+d_flag = sys.argv[2] if len(sys.argv) > 2 else "fcc"
+typ = sys.argv[3] if len(sys.argv) > 3 else "chiral"
+mfd, ne, lob, orth = pcb.discretization, pcb.numerical_experiments, pcb.lobpcg, pcb.orthogonalization
+ctx = pcb.get_context(N)
+T = {}
+def timed(name, fn):
+    def w(*a, **k):
+        ctx.sync(); t0 = time.perf_counter(); r = fn(*a, **k); ctx.sync(); T[name] = T.get(name, 0.0) + time.perf_counter() - t0; return r
+    return w
+alpha = pcb.dielectric.kpath(d_flag)[0]
+relax, pnt = mfd.set_relaxation(alpha)
+a_fft, b_fft = mfd.fft_blocks(N, 1, pcb.dielectric.diel_info(d_flag, option="ct"), alpha=alpha)
+inv_fft = mfd.inverse_3_times_3_B(b_fft, pnt, relax[0])
+A, H, P = ne.pc_mfd_handle(a_fft, (pnt * b_fft[0], pnt * b_fft[1]), getattr(mfd, typ + "_handle")(N, d_flag), inv_fft, relax[0])
+x0 = ctx.random_block(16, 1000)
+lam, x, info = lob.lobpcg_sep_softlock(H, P, x0, 10)     # warm-up (JIT-free, but first-touch allocations)
+op = H.op
+op.apply_into = timed("apply_H", op.apply_into)
+op.residual = timed("residual", op.residual)
+lob.gram_pair = timed("gram_pair", lob.gram_pair)
+lob.rr_small = timed("rr_small(host)", lob.rr_small)
+lib = pcb._lib.lib()
+class LibProxy:
+    def __getattr__(self, n):
+        f = getattr(lib, n)
+        return timed(n, f) if n == "pcb_update" else f
+pcb._lib._lib = LibProxy()
+x0 = ctx.random_block(16, 1000)
+t0 = time.perf_counter()
+lam, x, info = lob.lobpcg_sep_softlock(H, P, x0, 10)
+wall = time.perf_counter() - t0
+its = int(info[0])
+out = {"N": N, "iterations": its, "solver_s": float(info[1]), "wall_s": wall, "per_phase_ms_per_iteration": {k: 1e3 * v / its for k, v in T.items()},
+       "sum_phases_ms_per_iteration": 1e3 * sum(T.values()) / its}
+print(json.dumps(out))
