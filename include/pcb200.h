@@ -95,7 +95,8 @@ void pcb_op_destroy(pcb_op* op);
 int pcb_apply(pcb_op* op, int mode, int ncols, const void* const* in, void* const* out);
 
 /* Same as pcb_apply for PCB_APPLY_A / PCB_APPLY_H, with a CUDA event between the passes: pass_ms[i] = device time of
- * pass i (x-forward+K_A^H, y-forward, z-forward+M+z-inverse, y-inverse, x-inverse+K_A+gamma K_B+shift), npass <- 5.
+ * pass i.  Five-pass operator: (x-forward+K_A^H, y-forward, z-forward+M+z-inverse, y-inverse, x-inverse+K_A+gamma K_B+shift),
+ * npass <- 5; plane mode (N % 8 == 0, N <= 120, identity/isotropic M): (x-forward, fused y/z/M/z/y plane pass, x-inverse), npass <- 3.
  * Measurement aid for bench.py's per-pass roofline; not used by the solver. */
 int pcb_apply_timed(pcb_op* op, int mode, int ncols, const void* const* in, void* const* out, float* pass_ms, int* npass);
 

@@ -81,11 +81,13 @@ struct pcb_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     long long launches = 0;
     int sms = 148;
+    int use_plane = 1;              // PCB200_PLANE=0 forces the five-pass operator (A/B measurements)
 };
 struct pcb_diel {
     pcb_ctx* ctx;
     int kind;
     unsigned char* mask;    // [nn] (padded to 4)
+    unsigned char* maskT;   // [i0][i2][i1] copy for the plane mode (null when the size has no plane pass)
     double ediag[3];
     cplx eoff[3];
     PcbStencil st;
@@ -181,6 +183,7 @@ static int ctx_create(int device, int N, int z0, int z1, pcb_ctx** out) {
     pcb_ctx* c = new pcb_ctx;
     c->device = device; c->N = N; c->nn = (long long)N * N * N; c->plan = plan;
     c->z0 = z0; c->z1 = z1; c->nloc = (long long)(z1 - z0) * N * N; c->R = 3 * c->nloc;
+    { const char* e = getenv("PCB200_PLANE"); c->use_plane = (plan->plane_mode && !(e && e[0] == '0')) ? 1 : 0; }
 #ifndef PCB_EMU
     cudaDeviceProp prop;
     PCB_CUDA_OK(cudaGetDeviceProperties(&prop, device));
@@ -321,7 +324,7 @@ int pcb_diel_create(pcb_ctx* c, int kind, const int64_t* ind_e, long long n_e, c
     PCB_CHECK_ARG(out && kind >= PCB_DIEL_NONE && kind <= PCB_DIEL_CROSSDOF, "bad kind");
     PCB_CUDA_OK(cudaSetDevice(c->device));
     pcb_diel* d = new pcb_diel;
-    d->ctx = c; d->kind = kind; d->mask = nullptr;
+    d->ctx = c; d->kind = kind; d->mask = nullptr; d->maskT = nullptr;
     for (int i = 0; i < 3; ++i) { d->ediag[i] = ediag ? ediag[i] : 1.0; d->eoff[i] = eoff ? cmake(eoff[2 * i], eoff[2 * i + 1]) : cmake(0.0, 0.0); }
     d->st.k = 1; for (int i = 0; i < 8; ++i) d->st.w[i] = 0.0;
     if (kind == PCB_DIEL_CROSSDOF) {
@@ -347,6 +350,13 @@ int pcb_diel_create(pcb_ctx* c, int kind, const int64_t* ind_e, long long n_e, c
         PCB_CUDA_OK(cudaStreamSynchronize(c->stream));
         PCB_CUDA_OK(cudaFree(dind));
     }
+    if (c->plan->plane_mode) {
+        PCB_CUDA_OK(cudaMalloc(&d->maskT, mbytes));
+        PCB_LAUNCH(k_mask_transpose, dim3((unsigned)((c->nn + 255) / 256), 1, 1), dim3(256, 1, 1), 0, c->stream,
+                   (const unsigned char*)d->mask, d->maskT, c->N);
+        PCB_CUDA_OK(cudaGetLastError());
+        c->launches++;
+    }
     PCB_CUDA_OK(cudaStreamSynchronize(c->stream));
     *out = d;
     return 0;
@@ -356,6 +366,7 @@ void pcb_diel_destroy(pcb_diel* d) {
     cudaSetDevice(d->ctx->device);
     cudaStreamSynchronize(d->ctx->stream);
     if (d->mask) cudaFree(d->mask);
+    if (d->maskT) cudaFree(d->maskT);
     delete d;
 }
 
@@ -368,6 +379,7 @@ static void op_fill(pcb_op* o, double gamma, double shift, double pshift, pcb_di
     o->d.inv_n3 = 1.0 / (double)c->nn;
     o->d.diel = diel ? diel->kind : PCB_DIEL_NONE;
     o->d.mask = diel ? diel->mask : nullptr;
+    o->d.maskT = diel ? diel->maskT : nullptr;
     for (int i = 0; i < 3; ++i) {
         o->d.ediag[i] = diel ? diel->ediag[i] : 1.0;
         o->d.eoff[i] = diel ? diel->eoff[i] : cmake(0.0, 0.0);
@@ -438,7 +450,15 @@ int pcb_apply(pcb_op* o, int mode, int ncols, const void* const* in, void* const
                 break;
             case PCB_APPLY_A: case PCB_APPLY_H: {
                 const int last = (mode == PCB_APPLY_A) ? PCB_PASS_XINV_A : PCB_PASS_XINV_H;
-                if (!cross) {
+                const bool plane = c->use_plane && (o->d.diel == PCB_DIEL_NONE || o->d.diel == PCB_DIEL_CHIRAL);
+                if (plane) {
+                    // three passes: x forward -> transposed scratch, fused y/z/M/z/y on (i1,i2) planes, x inverse -> out
+                    if (ensure_scratch(c, sizeof(cplx) * (size_t)c->R * (size_t)kc)) return -1;
+                    for (int j = 0; j < kc; ++j) cols.wrk[j] = c->scratch + (size_t)j * c->R;
+                    const int seq[3] = {PCB_PASS_XFWD_SYM_T, PCB_PASS_MID, (mode == PCB_APPLY_A) ? PCB_PASS_XINV_A_T : PCB_PASS_XINV_H_T};
+                    for (int i = 0; i < 3; ++i) if (pl->pass(o->d, cols, kc, seq[i], c->tw, c->stream, c->sms)) return -1;
+                    c->launches += 3;
+                } else if (!cross) {
                     const int seq[5] = {PCB_PASS_XFWD_SYM, PCB_PASS_YFWD, PCB_PASS_ZMID, PCB_PASS_YINV, last};
                     for (int i = 0; i < 5; ++i) if (pl->pass(o->d, cols, kc, seq[i], c->tw, c->stream, c->sms)) return -1;
                     c->launches += 5;

@@ -26,6 +26,7 @@
 struct PcbCols {
     const cplx* in[PCB_MAXC];   // source columns (X)
     cplx* out[PCB_MAXC];        // destination / work columns
+    cplx* wrk[PCB_MAXC];        // plane mode: scratch columns holding the transposed layout W'[c][i0][i2][i1]
 };
 
 // occupancy hint of the x passes: ask for `want` CTAs/SM (caps registers) only where the tile is small enough to allow it
@@ -54,6 +55,10 @@ struct Plan {
     PCB_HD static int lout1(int k1) { return PFA ? (R2 * U * k1) % N : k1; }
     PCB_HD static int lout2(int k2) { return PFA ? (R1 * V * k2) % N : R1 * k2; }
     PCB_HD static int wrap(int s) { return PFA ? (s >= N ? s - N : s) : s; }
+    // output index held by slot s after a forward transform whose digits (k1, k2) sit in slot lin(k1, k2)
+    PCB_HD static int coord(int s) {
+        return PFA ? lout(((s % R1) * U) % R1, ((s % R2) * V) % R2) : (s / R2) + R1 * (s % R2);
+    }
 };
 
 // z = a x v  (cross product, _kernels.py:51-66)
@@ -90,13 +95,17 @@ template <int N> PCB_D void pcb_cp_wait() { asm volatile("cp.async.wait_group %0
 // form with the 4-CTAs/SM register cap -- so the simple form stays (the inverse pass, which also re-reads X, does gain from
 // the three-phase structure; the z pass, with twice the arithmetic per byte, from the cp.async pipeline).
 // ---------------------------------------------------------------------------------------
-template <class P, int LX, int NT, int SYM>
-__global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * P::R1 * P::R2P * 16, P::R1, 4)) k_xfwd(PcbOp op, PcbCols cols, const cplx* __restrict__ tw) {
+// TRN = 1 (plane mode): the output goes to the scratch column in the transposed layout W'[c][k][i2][i1] (8 consecutive i1 of
+// one k = a 128-byte segment), so that the fused y/z pass finds every (i1, i2) plane contiguous; rows get one element of
+// padding in shared memory (RS) to keep the row-fastest reads of that store pattern conflict-free.
+template <class P, int LX, int NT, int SYM, int TRN = 0>
+__global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * (P::R1 * P::R2P + TRN) * 16, P::R1, 4)) k_xfwd(PcbOp op, PcbCols cols, const cplx* __restrict__ tw) {
     constexpr int N = P::N, R1 = P::R1, R2 = P::R2, R2P = P::R2P;
-    PCB_DYN_SMEM(cplx, sm);   // [3][LX][R1][R2P]
+    constexpr int RS = R1 * R2P + TRN;      // row stride in shared memory
+    PCB_DYN_SMEM(cplx, sm);   // [3][LX][RS]
     const int col = blockIdx.y;
     const cplx* __restrict__ X = cols.in[col];
-    cplx* __restrict__ Y = cols.out[col];
+    cplx* __restrict__ Y = TRN ? cols.wrk[col] : cols.out[col];
     const long long nn = op.nn;
     const int row0 = blockIdx.x * LX;
     const int nrows = N * N;
@@ -146,24 +155,30 @@ __global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * P::R1 * P::R2P * 16,
             for (int k1 = 0; k1 < R1; ++k1) {
                 cplx val = v[c][k1];
                 if (k1 > 0) val = cmul(val, __ldg(tw + k1 * R2 + n2));
-                sm[((c * LX + r) * R1 + k1) * R2P + n2] = val;
+                sm[(c * LX + r) * RS + k1 * R2P + n2] = val;
             }
         }
     }
     __syncthreads();
     for (int item = tid; item < 3 * LX * R1; item += NT) {
-        const int k1 = item % R1;
-        const int r = (item / R1) % LX;
+        const int k1 = TRN ? (item / LX) % R1 : item % R1;
+        const int r = TRN ? item % LX : (item / R1) % LX;
         const int c = item / (R1 * LX);
         const int row = row0 + r;
         if (row >= nrows) continue;
         cplx v[R2];
         PCB_UNROLL
-        for (int n2 = 0; n2 < R2; ++n2) v[n2] = sm[((c * LX + r) * R1 + k1) * R2P + n2];
+        for (int n2 = 0; n2 < R2; ++n2) v[n2] = sm[(c * LX + r) * RS + k1 * R2P + n2];
         Dft<R2, -1>::run(v);
-        cplx* __restrict__ dst = Y + c * nn + (long long)row * N + k1;
-        PCB_UNROLL
-        for (int k2 = 0; k2 < R2; ++k2) dst[R1 * k2] = v[k2];
+        if (TRN) {      // W'[c][k][i2][i1], k = k1 + R1*k2: consecutive threads = consecutive i1
+            cplx* __restrict__ dst = Y + c * nn + (long long)k1 * N * N + row;      // row = i1 + N*i2
+            PCB_UNROLL
+            for (int k2 = 0; k2 < R2; ++k2) dst[(long long)R1 * k2 * N * N] = v[k2];
+        } else {
+            cplx* __restrict__ dst = Y + c * nn + (long long)row * N + k1;
+            PCB_UNROLL
+            for (int k2 = 0; k2 < R2; ++k2) dst[R1 * k2] = v[k2];
+        }
     }
 }
 
@@ -178,13 +193,15 @@ PCB_D void pcb_prefetch_l2(const void*) {}
 PCB_D void pcb_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
 #endif
 
-template <class P, int LX, int NT, int MODE>
-__global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * P::R1 * P::R2P * 16, P::R1, 4)) k_xinv(PcbOp op, PcbCols cols, const cplx* __restrict__ tw) {
+template <class P, int LX, int NT, int MODE, int TRN = 0>
+__global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * (P::R1 * P::R2P + TRN) * 16, P::R1, 4)) k_xinv(PcbOp op, PcbCols cols, const cplx* __restrict__ tw) {
     constexpr int N = P::N, R1 = P::R1, R2 = P::R2, R2P = P::R2P;
-    PCB_DYN_SMEM(cplx, sm);   // [3][LX][R1][R2P]
+    constexpr int RS = R1 * R2P + TRN;      // row stride in shared memory (see k_xfwd)
+    PCB_DYN_SMEM(cplx, sm);   // [3][LX][RS]
     const int col = blockIdx.y;
     const cplx* __restrict__ X = cols.in[col];
     cplx* __restrict__ W = cols.out[col];
+    const cplx* __restrict__ WT = cols.wrk[col];      // TRN: transposed work column W'[c][k][i2][i1]
     const long long nn = op.nn;
     const int row0 = blockIdx.x * LX;
     const int nrows = N * N;
@@ -198,19 +215,27 @@ __global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * P::R1 * P::R2P * 16,
     }
     // inverse radix R2 over k2 (fixed k1): global (Fourier order, k = k1 + R1*k2) -> registers -> shared
     for (int item = tid; item < 3 * LX * R1; item += NT) {
-        const int k1 = item % R1, cr = item / R1;
-        const int r = cr % LX, c = cr / LX;
+        const int k1 = TRN ? (item / LX) % R1 : item % R1;
+        const int r = TRN ? item % LX : (item / R1) % LX;
+        const int c = item / (R1 * LX);
+        const int cr = c * LX + r;
         if (r >= nr) continue;
         cplx v[R2];
-        const cplx* __restrict__ src = W + c * nn + (long long)(row0 + r) * N + k1;
-        PCB_UNROLL
-        for (int k2 = 0; k2 < R2; ++k2) v[k2] = src[R1 * k2];
+        if (TRN) {
+            const cplx* __restrict__ src = WT + c * nn + (long long)k1 * N * N + (row0 + r);
+            PCB_UNROLL
+            for (int k2 = 0; k2 < R2; ++k2) v[k2] = src[(long long)R1 * k2 * N * N];
+        } else {
+            const cplx* __restrict__ src = W + c * nn + (long long)(row0 + r) * N + k1;
+            PCB_UNROLL
+            for (int k2 = 0; k2 < R2; ++k2) v[k2] = src[R1 * k2];
+        }
         Dft<R2, +1>::run(v);
         PCB_UNROLL
         for (int n2 = 0; n2 < R2; ++n2) {
             cplx val = v[n2];
             if (k1 > 0) { const cplx t = __ldg(tw + k1 * R2 + n2); val = cmul(val, cmake(t.x, -t.y)); }
-            sm[(cr * R1 + k1) * R2P + n2] = val;
+            sm[cr * RS + k1 * R2P + n2] = val;
         }
     }
     __syncthreads();
@@ -220,10 +245,10 @@ __global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * P::R1 * P::R2P * 16,
         if (cr % LX >= nr) continue;
         cplx v[R1];
         PCB_UNROLL
-        for (int k1 = 0; k1 < R1; ++k1) v[k1] = sm[(cr * R1 + k1) * R2P + n2];
+        for (int k1 = 0; k1 < R1; ++k1) v[k1] = sm[cr * RS + k1 * R2P + n2];
         Dft<R1, +1>::run(v);
         PCB_UNROLL
-        for (int n1 = 0; n1 < R1; ++n1) sm[(cr * R1 + n1) * R2P + n2] = v[n1];
+        for (int n1 = 0; n1 < R1; ++n1) sm[cr * RS + n1 * R2P + n2] = v[n1];
     }
     __syncthreads();
     // point-wise epilogue, fully coalesced: 1/N^3, k x v, (+ gamma conj(k)(k.x) + shift x), store
@@ -246,10 +271,10 @@ __global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * P::R1 * P::R2P * 16,
             if (e >= nr * N) continue;
             const int r = e / N, i0 = e % N;
             const int row = row0 + r;
-            const int slot = (r * R1 + i0 / R2) * R2P + i0 % R2;
+            const int slot = r * RS + (i0 / R2) * R2P + i0 % R2;
             cplx u[3], z[3];
             PCB_UNROLL
-            for (int c = 0; c < 3; ++c) u[c] = cscale(sm[c * LX * R1 * R2P + slot], op.inv_n3);
+            for (int c = 0; c < 3; ++c) u[c] = cscale(sm[c * LX * RS + slot], op.inv_n3);
             if (MODE) {
                 const Sym3 sy = pcb_symbol(op.T, N, i0, row % N, row / N);
                 pcb_cross(sy.k, u, z);
@@ -499,17 +524,165 @@ __global__ void __launch_bounds__(NT, ((DIEL == 2 || NT > 256) ? 1 : 2)) k_zmid(
 }
 
 // ---------------------------------------------------------------------------------------
+// Plane mode, pass 2 of 3: forward y, forward z, M, inverse z, inverse y on one (i1, i2) plane held in shared memory.
+// The x pass wrote the transposed layout W'[c][i0][i2][i1], so the plane of (c, i0) is one contiguous chunk of N^2 elements;
+// a CTA (N/8 warps, one per SM, persistent) keeps it in shared memory with row stride N+1 (row-fastest accesses of the y
+// steps stay conflict-free; N = 120: 232 320 B of the 232 448 B a CTA can have).  Warp w owns rows i2 in [8w, 8w+8) for the
+// y steps and slots i1 in [8w, 8w+8) for the z steps, so only two CTA-wide barriers per plane are needed (row -> column
+// ownership and back); loading, the y steps and storing of different warps overlap each other.  HBM traffic of the whole
+// operator drops from 11 to 7 column transfers per op-apply.  DIEL: 0 identity, 1 component-wise (chiral); the coupled
+// 3x3 dielectrics need all three components of a point and stay on the five-pass path.
+// ---------------------------------------------------------------------------------------
+template <class P, int DIEL>
+__global__ void __launch_bounds__(P::N / 8 * 32, 1) k_mid(PcbOp op, PcbCols cols, const cplx* __restrict__ tw, int ncols) {
+    constexpr int N = P::N, R1 = P::R1, R2 = P::R2;
+    constexpr int LD = N + 1;                    // row stride (complex)
+    static_assert(N % 8 == 0, "plane mode needs N % 8 == 0");
+    PCB_DYN_SMEM(cplx, pl);   // [N rows i2][LD]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long nn = op.nn;
+    const int total = 3 * N * ncols;
+    cplx* __restrict__ myrows = pl + (8 * warp) * LD;
+
+    for (int pid = blockIdx.x; pid < total; pid += gridDim.x) {
+        const int col = pid / (3 * N), c = (pid / N) % 3, i0 = pid % N;
+        cplx* __restrict__ base = cols.wrk[col] + c * nn + (long long)i0 * N * N + (long long)(8 * warp) * N;   // this warp's 8 rows
+        // ---- load own rows (contiguous 8*N elements) ----
+        for (int e = lane; e < 8 * N; e += 32) pcb_cp16(myrows + (e / N) * LD + e % N, base + e);
+        pcb_cp_commit();
+        pcb_cp_wait<0>();
+        __syncwarp();
+        // ---- forward y on own rows: lanes = (row fastest, digit) ----
+        for (int it = lane; it < 8 * R2; it += 32) {
+            cplx* __restrict__ row = myrows + (it % 8) * LD;
+            const int n2 = it / 8, b2 = P::lin2(n2);
+            cplx v[R1];
+            PCB_UNROLL
+            for (int n1 = 0; n1 < R1; ++n1) v[n1] = row[P::wrap(P::lin1(n1) + b2)];
+            Dft<R1, -1>::run(v);
+            PCB_UNROLL
+            for (int k1 = 0; k1 < R1; ++k1) {
+                cplx val = v[k1];
+                if (!P::PFA && k1 > 0) val = cmul(val, __ldg(tw + k1 * R2 + n2));
+                row[P::wrap(P::lin1(k1) + b2)] = val;
+            }
+        }
+        __syncwarp();
+        for (int it = lane; it < 8 * R1; it += 32) {
+            cplx* __restrict__ row = myrows + (it % 8) * LD;
+            const int k1 = it / 8, b1 = P::lin1(k1);
+            cplx v[R2];
+            PCB_UNROLL
+            for (int n2 = 0; n2 < R2; ++n2) v[n2] = row[P::wrap(b1 + P::lin2(n2))];
+            Dft<R2, -1>::run(v);
+            PCB_UNROLL
+            for (int k2 = 0; k2 < R2; ++k2) row[P::wrap(b1 + P::lin2(k2))] = v[k2];
+        }
+        __syncthreads();
+        // ---- z on own slots (columns 8w .. 8w+7): lanes = (slot fastest, digit) ----
+        cplx* __restrict__ mycols = pl + 8 * warp;
+        for (int it = lane; it < 8 * R2; it += 32) {
+            cplx* __restrict__ cp = mycols + it % 8;
+            const int n2 = it / 8, b2 = P::lin2(n2);
+            cplx v[R1];
+            PCB_UNROLL
+            for (int n1 = 0; n1 < R1; ++n1) v[n1] = cp[P::wrap(P::lin1(n1) + b2) * LD];
+            Dft<R1, -1>::run(v);
+            PCB_UNROLL
+            for (int k1 = 0; k1 < R1; ++k1) {
+                cplx val = v[k1];
+                if (!P::PFA && k1 > 0) val = cmul(val, __ldg(tw + k1 * R2 + n2));
+                cp[P::wrap(P::lin1(k1) + b2) * LD] = val;
+            }
+        }
+        __syncwarp();
+        for (int it = lane; it < 8 * R1; it += 32) {
+            cplx* __restrict__ cp = mycols + it % 8;
+            const int k1 = it / 8, b1 = P::lin1(k1), o1 = P::lout1(k1);
+            unsigned char mk[R2];
+            if (DIEL == 1) {
+                const int i1 = P::coord(8 * warp + it % 8);     // real-space i1 of this slot after the forward y transform
+                const unsigned char* __restrict__ mp = op.maskT + (long long)i0 * N * N + i1;
+                PCB_UNROLL
+                for (int k2 = 0; k2 < R2; ++k2) mk[k2] = __ldg(mp + P::wrap(o1 + P::lout2(k2)) * N);
+            }
+            cplx v[R2];
+            PCB_UNROLL
+            for (int n2 = 0; n2 < R2; ++n2) v[n2] = cp[P::wrap(b1 + P::lin2(n2)) * LD];
+            Dft<R2, -1>::run(v);
+            if (DIEL == 1) {
+                const double scl = op.ediag[c];
+                PCB_UNROLL
+                for (int k2 = 0; k2 < R2; ++k2)
+                    if ((mk[k2] >> c) & 1u) v[k2] = cscale(v[k2], scl);
+            }
+            Dft<R2, +1>::run(v);
+            PCB_UNROLL
+            for (int n2 = 0; n2 < R2; ++n2) {
+                cplx val = v[n2];
+                if (!P::PFA && k1 > 0) { const cplx t = __ldg(tw + k1 * R2 + n2); val = cmul(val, cmake(t.x, -t.y)); }
+                cp[P::wrap(b1 + P::lin2(n2)) * LD] = val;
+            }
+        }
+        __syncwarp();
+        for (int it = lane; it < 8 * R2; it += 32) {
+            cplx* __restrict__ cp = mycols + it % 8;
+            const int n2 = it / 8, b2 = P::lin2(n2);
+            cplx v[R1];
+            PCB_UNROLL
+            for (int k1 = 0; k1 < R1; ++k1) v[k1] = cp[P::wrap(P::lin1(k1) + b2) * LD];
+            Dft<R1, +1>::run(v);
+            PCB_UNROLL
+            for (int n1 = 0; n1 < R1; ++n1) cp[P::wrap(P::lin1(n1) + b2) * LD] = v[n1];
+        }
+        __syncthreads();
+        // ---- inverse y on own rows, then store them ----
+        for (int it = lane; it < 8 * R1; it += 32) {
+            cplx* __restrict__ row = myrows + (it % 8) * LD;
+            const int k1 = it / 8, b1 = P::lin1(k1);
+            cplx v[R2];
+            PCB_UNROLL
+            for (int k2 = 0; k2 < R2; ++k2) v[k2] = row[P::wrap(b1 + P::lin2(k2))];
+            Dft<R2, +1>::run(v);
+            PCB_UNROLL
+            for (int n2 = 0; n2 < R2; ++n2) {
+                cplx val = v[n2];
+                if (!P::PFA && k1 > 0) { const cplx t = __ldg(tw + k1 * R2 + n2); val = cmul(val, cmake(t.x, -t.y)); }
+                row[P::wrap(b1 + P::lin2(n2))] = val;
+            }
+        }
+        __syncwarp();
+        for (int it = lane; it < 8 * R2; it += 32) {
+            cplx* __restrict__ row = myrows + (it % 8) * LD;
+            const int n2 = it / 8, b2 = P::lin2(n2);
+            cplx v[R1];
+            PCB_UNROLL
+            for (int k1 = 0; k1 < R1; ++k1) v[k1] = row[P::wrap(P::lin1(k1) + b2)];
+            Dft<R1, +1>::run(v);
+            PCB_UNROLL
+            for (int n1 = 0; n1 < R1; ++n1) row[P::wrap(P::lin1(n1) + b2)] = v[n1];
+        }
+        __syncwarp();
+        for (int e = lane; e < 8 * N; e += 32) base[e] = myrows[(e / N) * LD + e % N];
+        __syncwarp();      // own rows are free again for the next plane's loads
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Launch table: one entry per supported grid size, filled by the per-size translation units.
 // ---------------------------------------------------------------------------------------
 struct PcbOpLaunch {
     int N;
     int r1, r2;
+    int plane_mode;   // 1: the fused (i1,i2)-plane pass exists for this size (N % 8 == 0 and the plane fits in shared memory)
     // mode: 0 plain 3-D FFT forward, 1 plain inverse (1/N^3), 2 A = AMA^H, 3 H = AMA^H + gamma B^H B + shift
     int (*apply)(const PcbOp& op, const PcbCols& cols, int ncols, int mode, const cplx* tw, cudaStream_t s, int sms);
     // split passes used by the cross-DoF dielectric and by the tests: pass ids below
     int (*pass)(const PcbOp& op, const PcbCols& cols, int ncols, int pass_id, const cplx* tw, cudaStream_t s, int sms);
 };
 enum { PCB_PASS_XFWD_SYM = 0, PCB_PASS_XFWD = 1, PCB_PASS_YFWD = 2, PCB_PASS_ZFWD = 3, PCB_PASS_ZINV = 4,
-       PCB_PASS_YINV = 5, PCB_PASS_XINV = 6, PCB_PASS_XINV_A = 7, PCB_PASS_XINV_H = 8, PCB_PASS_ZMID = 9 };
+       PCB_PASS_YINV = 5, PCB_PASS_XINV = 6, PCB_PASS_XINV_A = 7, PCB_PASS_XINV_H = 8, PCB_PASS_ZMID = 9,
+       // plane mode (three passes, transposed scratch columns in cols.wrk)
+       PCB_PASS_XFWD_SYM_T = 10, PCB_PASS_MID = 11, PCB_PASS_XINV_A_T = 12, PCB_PASS_XINV_H_T = 13 };
 
 const PcbOpLaunch* pcb_find_plan(int N);

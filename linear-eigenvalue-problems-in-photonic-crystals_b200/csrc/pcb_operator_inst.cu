@@ -3,6 +3,9 @@
 // sizes build in parallel and each object only carries the codelets it needs.
 #include "pcb_operator.cuh"
 
+#ifndef PCB_NTP
+#define PCB_NTP 256
+#endif
 #ifndef PCB_N
 #error "compile with -DPCB_N -DPCB_R1 -DPCB_R2"
 #endif
@@ -11,7 +14,7 @@ namespace {
 
 typedef Plan<PCB_N, PCB_R1, PCB_R2> P;
 constexpr int NT = 128;      // y lines and split z passes (one CTA per tile)
-constexpr int NTP = 256;     // persistent z-mid kernel: 2 CTAs/SM of 256 threads when two stages fit twice in shared memory,
+constexpr int NTP = PCB_NTP;     // persistent z-mid kernel: 2 CTAs/SM of 256 threads when two stages fit twice in shared memory,
 constexpr int kRowBytes = 3 * P::R1 * P::R2P * (int)sizeof(cplx);
 constexpr int LX = (8 * kRowBytes <= 65536) ? 8 : (4 * kRowBytes <= 65536) ? 4 : (2 * kRowBytes <= 65536) ? 2 : 1;
 constexpr int kStageX = LX * kRowBytes;               // one x-tile (three components)
@@ -53,8 +56,34 @@ inline int ctas_per_sm(int smem, int regs_hint_threads) {
         PCB_CUDA_OK(cudaGetLastError());                                            \
     } while (0)
 
+// plane mode: N % 8 == 0, tiles of 8 rows must not straddle an i2 plane, and N x (N+1) complex fit in one CTA's shared memory
+constexpr bool kPlane = (P::N % 8 == 0) && (LX == 8) && ((long long)P::N * (P::N + 1) * 16 <= 232448);
+constexpr int kSmemMid = P::N * (P::N + 1) * (int)sizeof(cplx);
+constexpr int kStageXT = 3 * LX * (P::R1 * P::R2P + 1) * (int)sizeof(cplx);
+
 constexpr int GX = (P::N * P::N + LX - 1) / LX;          // x tiles per column
 constexpr int GL = ((P::N + 7) / 8) * P::N;              // strided-line tiles per column
+
+// plane-mode passes exist only for sizes with kPlane (the kernels are not even instantiated otherwise)
+template <bool ENABLED, class PP>
+struct PlanePass {
+    static int go(const PcbOp&, const PcbCols&, int, int, const cplx*, cudaStream_t, int) {
+        pcb_set_error("plane mode is not available for N = %d", PP::N);
+        return -1;
+    }
+};
+template <class PP>
+struct PlanePass<true, PP> {
+    static int go(const PcbOp& op, const PcbCols& cols, int ncols, int pass_id, const cplx* tw, cudaStream_t s, int sms) {
+        if (pass_id == PCB_PASS_XFWD_SYM_T) PCB_GO((k_xfwd<PP, LX, NT, 1, 1>), GX, kStageXT);
+        else if (pass_id == PCB_PASS_XINV_A_T) PCB_GO((k_xinv<PP, LX, NT, 1, 1>), GX, kStageXT);
+        else if (pass_id == PCB_PASS_XINV_H_T) PCB_GO((k_xinv<PP, LX, NT, 2, 1>), GX, kStageXT);
+        else if (op.diel == PCB_DIEL_NONE) PCB_GO_P((k_mid<PP, 0>), (PP::N / 8 * 32), 3 * PP::N, kSmemMid, 1);
+        else if (op.diel == PCB_DIEL_CHIRAL) PCB_GO_P((k_mid<PP, 1>), (PP::N / 8 * 32), 3 * PP::N, kSmemMid, 1);
+        else { pcb_set_error("plane mode: dielectric type %d not supported", op.diel); return -1; }
+        return 0;
+    }
+};
 
 int run_pass(const PcbOp& op, const PcbCols& cols, int ncols, int pass_id, const cplx* tw, cudaStream_t s, int sms) {
     switch (pass_id) {
@@ -73,6 +102,8 @@ int run_pass(const PcbOp& op, const PcbCols& cols, int ncols, int pass_id, const
             else if (op.diel == PCB_DIEL_TRIVIAL) PCB_GO_P((k_zmid<P, 2, NTP>), NTP, GL, kSmemZ, 2);   // v[3][R2] per thread: keep 256 threads
             else { pcb_set_error("zmid: dielectric type %d has no fused z pass", op.diel); return -1; }
             break;
+        case PCB_PASS_XFWD_SYM_T: case PCB_PASS_MID: case PCB_PASS_XINV_A_T: case PCB_PASS_XINV_H_T:
+            return PlanePass<kPlane, P>::go(op, cols, ncols, pass_id, tw, s, sms);
         default: pcb_set_error("unknown pass id %d", pass_id); return -1;
     }
     return 0;
@@ -101,4 +132,4 @@ int run_apply(const PcbOp& op, const PcbCols& cols, int ncols, int mode, const c
 
 #define PCB_CAT2(a, b) a##b
 #define PCB_CAT(a, b) PCB_CAT2(a, b)
-extern const PcbOpLaunch PCB_CAT(pcb_plan_, PCB_N) = {PCB_N, PCB_R1, PCB_R2, run_apply, run_pass};
+extern const PcbOpLaunch PCB_CAT(pcb_plan_, PCB_N) = {PCB_N, PCB_R1, PCB_R2, kPlane ? 1 : 0, run_apply, run_pass};

@@ -86,6 +86,16 @@ class Context:
     def empty(self, k):
         return DeviceBlock(self, int(k))
 
+    def work_block(self, tag, k):
+        """A cached k-column block (solver work space S / HS): cudaMalloc/cudaFree of several GB per k-point would cost
+        as much as a few LOBPCG iterations.  The caller must not keep views beyond its own call."""
+        pool = self.__dict__.setdefault("_work_blocks", {})
+        blk = pool.get(tag)
+        if blk is None or blk.k < k:
+            pool[tag] = None          # release the smaller block first
+            blk = pool[tag] = DeviceBlock(self, int(k))
+        return blk if blk.k == k else blk.cols(range(k))
+
     def from_host(self, x):
         return DeviceBlock.from_host(self, x)
 

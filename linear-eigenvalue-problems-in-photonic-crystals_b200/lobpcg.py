@@ -73,7 +73,7 @@ def lobpcg_sep_softlock(h_func_in, p_func, x0, nev, shift=0.0, tol=TOL, maxiter=
             return y
     res_op = op if op is not None else _residual_helper(ctx)
 
-    S, HS = ctx.empty(3 * m), ctx.empty(3 * m)
+    S, HS = ctx.work_block("lobpcg.S", 3 * m), ctx.work_block("lobpcg.HS", 3 * m)     # cached across solves
     X, W, P = S[:, :m], S[:, m:2 * m], S[:, 2 * m:]
     HX, HW, HP = HS[:, :m], HS[:, m:2 * m], HS[:, 2 * m:]
     if isinstance(x0, DeviceBlock):

@@ -50,3 +50,21 @@ def test_symbols_vs_reference_golden(pcb, golden):
         assert relerr(a_fft.toarray(), z[k + "_a"]) < 1e-14
         b0, b1 = mfd.PenaltySymbols(a_fft, pnt).toarray()
         assert relerr(b0, z[k + "_b0"]) < 1e-14 and relerr(b1, z[k + "_b1"]) < 1e-14
+
+
+@pytest.mark.parametrize("N,d_flag,typ,alpha", [
+    (8, "sc_curv", "chiral", [np.pi, np.pi, np.pi]),          # N % 8 == 0: three-pass plane mode (fused y/z pass)
+    (16, "fcc", "chiral", [0.3, 2 * np.pi, 0.0]),
+    (16, "bcc_sg", None, [0.0, 0.0, 0.0]),
+    (16, "sc_curv", "pseudochiral_trivial", [np.pi, 0.0, 0.0]),   # coupled 3x3 M: five-pass path
+    (12, "fcc", "chiral", [np.pi, np.pi, 0.0]),                    # N % 8 != 0: five-pass path
+])
+def test_operator_vs_oracle_small(pcb, oracle, N, d_flag, typ, alpha):
+    alpha = np.array(alpha, dtype=float)
+    case = {"N": N, "d_flag": d_flag, "alpha": alpha, "type": typ, "eps_opt": 0, "m": 2, "seed": 31 + N}
+    A, H, P, Diels, x = _setup(pcb, oracle, case)
+    a, b, inv, shift, _ = oracle.assemble_symbols(N, d_flag, alpha)
+    diel = (lambda v: v) if typ is None else oracle.HANDLES[typ](N, d_flag)
+    Ao, Ho, Po = oracle.pc_mfd_handle(a, b, diel, inv, shift)
+    assert relerr(H(x), Ho(x)) < TOL
+    assert relerr(A(x), Ao(x)) < TOL
