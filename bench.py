@@ -255,20 +255,25 @@ def main():
         pcb._lib.check(pcb._lib.lib().pcb_apply_timed(op.h, pcb._lib.APPLY_H, m, pcb._lib.ptr_array(X.ptrs),
                                                       pcb._lib.ptr_array(Y.ptrs), buf, C.byref(npass)), "pcb_apply_timed")
         pass_ms += np.array(buf[:5])
-    pass_ms /= reps
+    pass_ms = pass_ms[:npass.value] / reps
     col_bytes = 48.0 * n ** 3            # one column, one direction
-    pass_bytes = np.array([2, 2, 2, 2, 3]) * col_bytes * m
-    names = ["x_fwd+KAh", "y_fwd", "z_fwd+M+z_inv", "y_inv", "x_inv+KA+gKB+shift"]
+    if npass.value == 3:                  # plane mode: x forward (transposed store), fused y/z/M/z/y plane pass, x inverse
+        pass_cols, names = [2, 2, 3], ["x_fwd+KAh -> W'", "y,z fwd + M + z,y inv on (i1,i2) planes", "x_inv+KA+gKB+shift"]
+        kernel_desc = "op-apply = 3 passes (k_xfwd<T>, k_mid, k_xinv<T>)"
+    else:
+        pass_cols, names = [2, 2, 2, 2, 3], ["x_fwd+KAh", "y_fwd", "z_fwd+M+z_inv", "y_inv", "x_inv+KA+gKB+shift"]
+        kernel_desc = "op-apply = 5 passes (k_xfwd, k_line, k_zmid, k_line, k_xinv)"
+    pass_bytes = np.array(pass_cols) * col_bytes * m
     passes = [{"name": nm, "ms": float(t), "GBps": float(b / (t * 1e-3) / 1e9)} for nm, t, b in zip(names, pass_ms, pass_bytes)]
 
     peak, peak_src = measured_peak()
     achieved = B_OP_PER_N3 * n ** 3 * m / (ms_step * 1e-3) / 1e9 * 1.0     # per rank: every rank runs the same step
     # DRAM bytes of one launch (= one 16-column block apply) from the ncu --set full capture of these kernels at this
     # shape (profiles/r01_c_final_ncu.md: dram__bytes_read.sum + dram__bytes_write.sum over the five passes); null otherwise
-    traffic = 14.51e9 if (n == 120 and m == 16) else None
-    roofline = {"bound": "hbm", "kernel": "op-apply = 5 fused FFT passes (k_xfwd, k_line, k_zmid, k_line, k_xinv)",
+    traffic = None
+    roofline = {"bound": "hbm", "kernel": kernel_desc,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "fp64_pipe_busy_ms_per_launch": 1.46 if (n == 120 and m == 16) else None,
+                "traffic_note": "filled from the ncu capture of this build, see profiles/README.md",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": B_OP_PER_N3 * n ** 3 * m,
                 "moved_bytes_per_launch": float(pass_bytes.sum()), "moved_GBps": float(pass_bytes.sum() / (ms_step * 1e-3) / 1e9)}
 

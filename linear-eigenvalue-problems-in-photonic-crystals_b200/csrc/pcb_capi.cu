@@ -522,19 +522,27 @@ int pcb_apply_timed(pcb_op* o, int mode, int ncols, const void* const* in, void*
     PCB_CUDA_OK(cudaSetDevice(c->device));
     PcbCols cols;
     for (int j = 0; j < ncols; ++j) { cols.in[j] = (const cplx*)in[j]; cols.out[j] = (cplx*)out[j]; }
-    const int seq[5] = {PCB_PASS_XFWD_SYM, PCB_PASS_YFWD, PCB_PASS_ZMID, PCB_PASS_YINV, mode == PCB_APPLY_A ? PCB_PASS_XINV_A : PCB_PASS_XINV_H};
+    const bool plane = c->use_plane && (o->d.diel == PCB_DIEL_NONE || o->d.diel == PCB_DIEL_CHIRAL);
+    int seq[5] = {PCB_PASS_XFWD_SYM, PCB_PASS_YFWD, PCB_PASS_ZMID, PCB_PASS_YINV, mode == PCB_APPLY_A ? PCB_PASS_XINV_A : PCB_PASS_XINV_H};
+    int n = 5;
+    if (plane) {
+        if (ensure_scratch(c, sizeof(cplx) * (size_t)c->R * (size_t)ncols)) return -1;
+        for (int j = 0; j < ncols; ++j) cols.wrk[j] = c->scratch + (size_t)j * c->R;
+        seq[0] = PCB_PASS_XFWD_SYM_T; seq[1] = PCB_PASS_MID; seq[2] = mode == PCB_APPLY_A ? PCB_PASS_XINV_A_T : PCB_PASS_XINV_H_T;
+        n = 3;
+    }
     cudaEvent_t ev[6];
     for (int i = 0; i < 6; ++i) PCB_CUDA_OK(cudaEventCreate(&ev[i]));
     PCB_CUDA_OK(cudaEventRecord(ev[0], c->stream));
-    for (int i = 0; i < 5; ++i) {
+    for (int i = 0; i < n; ++i) {
         if (c->plan->pass(o->d, cols, ncols, seq[i], c->tw, c->stream, c->sms)) return -1;
         PCB_CUDA_OK(cudaEventRecord(ev[i + 1], c->stream));
     }
-    c->launches += 5;
-    PCB_CUDA_OK(cudaEventSynchronize(ev[5]));
-    for (int i = 0; i < 5; ++i) PCB_CUDA_OK(cudaEventElapsedTime(&pass_ms[i], ev[i], ev[i + 1]));
+    c->launches += n;
+    PCB_CUDA_OK(cudaEventSynchronize(ev[n]));
+    for (int i = 0; i < n; ++i) PCB_CUDA_OK(cudaEventElapsedTime(&pass_ms[i], ev[i], ev[i + 1]));
     for (int i = 0; i < 6; ++i) PCB_CUDA_OK(cudaEventDestroy(ev[i]));
-    *npass = 5;
+    *npass = n;
     return 0;
 }
 
