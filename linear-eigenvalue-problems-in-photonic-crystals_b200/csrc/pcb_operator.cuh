@@ -387,11 +387,13 @@ PCB_D void pcb_ztile_load(cplx* __restrict__ st, const cplx* __restrict__ Y, lon
             pcb_cp16(st + (c * N + i2) * 8 + i0l, src + c * nn + (long long)i2 * N * N);
 }
 
-template <class P, int DIEL, int NT>
+// NSTAGE = 2: the next tile streams into the other stage while this one is transformed; NSTAGE = 1 (large N, where two stages
+// would leave one CTA per SM): load, wait, transform in the single stage and rely on the co-resident CTAs for overlap.
+template <class P, int DIEL, int NT, int NSTAGE = 2>
 __global__ void __launch_bounds__(NT, ((DIEL == 2 || NT > 256) ? 1 : 2)) k_zmid(PcbOp op, PcbCols cols, const cplx* __restrict__ tw, int ncols) {
     constexpr int N = P::N, R1 = P::R1, R2 = P::R2;
     constexpr int STAGE = 3 * N * 8;
-    PCB_DYN_SMEM(cplx, sm);   // [2 stages][3][N][8]
+    PCB_DYN_SMEM(cplx, sm);   // [NSTAGE][3][N][8]
     const long long nn = op.nn;
     constexpr int NT0 = (N + 7) / 8;
     const int tpc = NT0 * N;
@@ -399,13 +401,17 @@ __global__ void __launch_bounds__(NT, ((DIEL == 2 || NT > 256) ? 1 : 2)) k_zmid(
     const int tid = threadIdx.x;
 
     int tile = blockIdx.x, stage = 0;
-    if (tile < total) {
+    if (NSTAGE == 2 && tile < total) {
         pcb_ztile_load<P, NT>(sm, cols.out[tile / tpc], nn, (tile % tpc) % NT0, (tile % tpc) / NT0, tid);
         pcb_cp_commit();
     }
     for (; tile < total; tile += gridDim.x) {
         const int next = tile + gridDim.x;
-        if (next < total) {
+        if (NSTAGE == 1) {
+            pcb_ztile_load<P, NT>(sm, cols.out[tile / tpc], nn, (tile % tpc) % NT0, (tile % tpc) / NT0, tid);
+            pcb_cp_commit();
+            pcb_cp_wait<0>();
+        } else if (next < total) {
             pcb_ztile_load<P, NT>(sm + (stage ^ 1) * STAGE, cols.out[next / tpc], nn, (next % tpc) % NT0, (next % tpc) / NT0, tid);
             pcb_cp_commit();
             pcb_cp_wait<1>();
@@ -519,7 +525,7 @@ __global__ void __launch_bounds__(NT, ((DIEL == 2 || NT > 256) ? 1 : 2)) k_zmid(
             for (int n1 = 0; n1 < R1; ++n1) base[(long long)P::wrap(P::lin1(n1) + b2) * (N * N)] = v[n1];
         }
         __syncthreads();
-        stage ^= 1;
+        if (NSTAGE == 2) stage ^= 1;
     }
 }
 

@@ -20,7 +20,9 @@ constexpr int LX = (8 * kRowBytes <= 65536) ? 8 : (4 * kRowBytes <= 65536) ? 4 :
 constexpr int kStageX = LX * kRowBytes;               // one x-tile (three components)
 constexpr int kSmemL = 3 * P::N * 8 * (int)sizeof(cplx);
 constexpr int kSmemZ = 2 * kSmemL;                       // two stages
-constexpr int NTZ = (2 * (kSmemZ + 1024) <= 224 * 1024) ? NTP : 512;   // ... else one CTA/SM of 512 threads
+constexpr int NSTZ = (2 * (kSmemZ + 1024) <= 224 * 1024) ? 2 : 1;         // ... else single-stage tiles, still several CTAs per SM
+constexpr int kSmemZU = NSTZ * kSmemL;
+constexpr int NTZ = NTP;
 
 template <class K>
 int set_smem(K kern, int bytes) {
@@ -97,9 +99,9 @@ int run_pass(const PcbOp& op, const PcbCols& cols, int ncols, int pass_id, const
         case PCB_PASS_XINV_A:   PCB_GO((k_xinv<P, LX, NT, 1>), GX, kStageX); break;
         case PCB_PASS_XINV_H:   PCB_GO((k_xinv<P, LX, NT, 2>), GX, kStageX); break;
         case PCB_PASS_ZMID:
-            if (op.diel == PCB_DIEL_NONE) PCB_GO_P((k_zmid<P, 0, NTZ>), NTZ, GL, kSmemZ, 2);
-            else if (op.diel == PCB_DIEL_CHIRAL) PCB_GO_P((k_zmid<P, 1, NTZ>), NTZ, GL, kSmemZ, 2);
-            else if (op.diel == PCB_DIEL_TRIVIAL) PCB_GO_P((k_zmid<P, 2, NTP>), NTP, GL, kSmemZ, 2);   // v[3][R2] per thread: keep 256 threads
+            if (op.diel == PCB_DIEL_NONE) PCB_GO_P((k_zmid<P, 0, NTZ, NSTZ>), NTZ, GL, kSmemZU, 3);
+            else if (op.diel == PCB_DIEL_CHIRAL) PCB_GO_P((k_zmid<P, 1, NTZ, NSTZ>), NTZ, GL, kSmemZU, 3);
+            else if (op.diel == PCB_DIEL_TRIVIAL) PCB_GO_P((k_zmid<P, 2, NTP, NSTZ>), NTP, GL, kSmemZU, 2);   // v[3][R2] per thread: keep 256 threads
             else { pcb_set_error("zmid: dielectric type %d has no fused z pass", op.diel); return -1; }
             break;
         case PCB_PASS_XFWD_SYM_T: case PCB_PASS_MID: case PCB_PASS_XINV_A_T: case PCB_PASS_XINV_H_T:
