@@ -7,6 +7,7 @@ int64 index lists, which the C ABI packs into a per-cell bit mask.  The ``.bin``
 (raw little-endian int64) and directory layout are the reference's.
 """
 import os
+import tempfile
 import time
 
 import numpy as np
@@ -182,6 +183,11 @@ def diel_io_index(N, d_flag, dofs="edge", gpu=True, cache=True):
         return rng.integers(0, 3 * N ** 3 - 1, size=int(0.372 * 3 * N ** 3)).astype(np.int64)
     t0 = time.time()
     path = os.path.join(DIEL_PATH, dofs + "_dofs", f"{d_flag}_{N}.bin")
+    if not os.path.isdir(os.path.dirname(path)):
+        # no reference-style directory in the working directory: keep the same raw-int64 files in a per-user cache so that
+        # the geometry (seconds of NumPy at N = 120, per process) is evaluated once per machine, not once per run and rank
+        root = os.environ.get("PCB200_CACHE", os.path.join(tempfile.gettempdir(), "pcb200_index_cache"))
+        path = os.path.join(root, dofs + "_dofs", f"{d_flag}_{N}.bin")
     if (N, d_flag, dofs) in _index_cache:
         ind = _index_cache[(N, d_flag, dofs)]
     elif os.path.exists(path):
@@ -189,9 +195,15 @@ def diel_io_index(N, d_flag, dofs="edge", gpu=True, cache=True):
         say(f"{GREEN}Index file already exists.{RESET}")
     else:
         ind = compute_index(N, d_flag, dofs)
-        if cache and os.path.isdir(os.path.dirname(path)):
+        if cache:
             say(f"{RED}New lattice type {d_flag} or size {N} isn't computed.{RESET}")
-            ind.tofile(path)
+            try:
+                os.makedirs(os.path.dirname(path), exist_ok=True)
+                tmp = f"{path}.{os.getpid()}.tmp"
+                ind.tofile(tmp)
+                os.replace(tmp, path)          # atomic: concurrent ranks may race for the same file
+            except OSError:
+                pass
     _index_cache[(N, d_flag, dofs)] = ind
     say(f"Dielectric {dofs} indices for {d_flag} with N = {N} loaded, {time.time() - t0:<6.3f}s elapsed.")
     return ind
