@@ -451,6 +451,12 @@ int pcb_apply(pcb_op* o, int mode, int ncols, const void* const* in, void* const
             case PCB_APPLY_A: case PCB_APPLY_H: {
                 const int last = (mode == PCB_APPLY_A) ? PCB_PASS_XINV_A : PCB_PASS_XINV_H;
                 const bool plane = c->use_plane && (o->d.diel == PCB_DIEL_NONE || o->d.diel == PCB_DIEL_CHIRAL);
+                if (mode == PCB_APPLY_H && !plane)
+                    for (int j = 0; j < kc; ++j)
+                        if (cols.in[j] == cols.out[j]) {
+                            pcb_set_error("pcb_apply(PCB_APPLY_H): in[%d] == out[%d]; the last pass re-reads X, use distinct columns", j0 + j, j0 + j);
+                            return -2;
+                        }
                 if (plane) {
                     // three passes: x forward -> transposed scratch, fused y/z/M/z/y on (i1,i2) planes, x inverse -> out
                     if (ensure_scratch(c, sizeof(cplx) * (size_t)c->R * (size_t)kc)) return -1;

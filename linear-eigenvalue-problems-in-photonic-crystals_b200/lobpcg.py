@@ -51,7 +51,7 @@ def _context_of(h_func_in, x0):
 
 
 def lobpcg_sep_softlock(h_func_in, p_func, x0, nev, shift=0.0, tol=TOL, maxiter=MAXITER, history=False,
-                        longortho=False, singleprecision=False, maxstagniter=50, trace=None):
+                        longortho=False, singleprecision=False, maxstagniter=50, trace=None, _lock=True):
     """LOBPCG with soft locking; [X, W, P] and their images live in two 3m-column device blocks.
 
     Returns ``(lambdas[:m] - shift, x, info)`` with ``x`` a DeviceBlock (R x m), ``info = [iterations,
@@ -102,13 +102,15 @@ def lobpcg_sep_softlock(h_func_in, p_func, x0, nev, shift=0.0, tol=TOL, maxiter=
         # residual (+ preconditioner on the fused path), norms, active set
         res_nrms = res_op.residual(X, HX, W, lambdas[:m], precond=op is not None)
         res_his[iter_] = np.linalg.norm(res_nrms[:nev])
-        ind_act = np.where(res_nrms > tol)[0]
+        ind_act = np.where(res_nrms > tol)[0] if _lock else np.arange(m)
         n_act = len(ind_act)
         if trace is not None:
             trace.append({"res": res_nrms.copy(), "n_act": n_act, "lambdas": np.array(lambdas[:m])})
         say(f"Iter = {iter_:<4d}, res_nrm = {np.linalg.norm(res_nrms):<6.2e}, n_act = {n_act:<3d}.", end=" ")
         if np.isnan(res_nrms).any():
             say(f"{RED}Nan occurs in residuals.{RESET}")
+            if not _lock:
+                raise ValueError(f"{RED}Nan occurs in residuals.{RESET}")      # lobpcg_sep_nolock raises (lobpcg.py:139-140)
             return None, None, None
         if (iter_ > maxstagniter and (res_nrms[0] > 1000 or res_nrms[0] > res_his[1])) or \
                 (iter_ > 2 * maxstagniter and res_nrms[0] > 50):
@@ -159,6 +161,17 @@ def lobpcg_sep_softlock(h_func_in, p_func, x0, nev, shift=0.0, tol=TOL, maxiter=
         info = np.append(info, res_his[1:iter_])
     x = X.copy()      # detach the result from the 3m-column work block
     return lambdas[:m] - shift, x, info
+
+
+def lobpcg_sep_nolock(h_func, p_func, x0, nev, tol=TOL, maxiter=MAXITER, history=False, longortho=False,
+                      singleprecision=False):
+    """LOBPCG without locking (lobpcg.py:76-193): every column stays in the search space [X W P] until the first `nev`
+    residuals are below `tol`.  Same kernels as the soft-locking solver with the full index set as the active set (the
+    reference's version only works while all columns are active; this is its intended behaviour).
+    Returns (lambdas[:m], x, info); NaN residuals raise ValueError like the reference."""
+    lam, x, info = lobpcg_sep_softlock(h_func, p_func, x0, nev, shift=0.0, tol=tol, maxiter=maxiter, history=history,
+                                       longortho=longortho, singleprecision=singleprecision, maxstagniter=10 ** 9, _lock=False)
+    return lam, x, info
 
 
 _helpers = {}

@@ -78,3 +78,27 @@ def test_warm_start_after_gamma_is_rank_deficient_but_solved(pcb, oracle):
     lam_c, x_c, info_c = solve(al[60], oracle.random_x0(3 * N ** 3, 16, 4))  # cold start
     assert lam_w is not None and lam_c is not None
     assert np.allclose(lam_w[:10], lam_c[:10], rtol=1e-6, atol=1e-7)
+
+
+def test_nolock_variant_and_error_paths(pcb, oracle):
+    """lobpcg_sep_nolock reaches the same eigenvalues as the soft-locking solver; argument errors surface as PcbError."""
+    N, d = (8, "sc_curv")
+    mfd, ne = pcb.discretization, pcb.numerical_experiments
+    alpha = np.array([np.pi, np.pi, 0.0])
+    relax, pnt = mfd.set_relaxation(alpha)
+    a_fft, b_fft = mfd.fft_blocks(N, 1, pcb.dielectric.diel_info(d, option="ct"), alpha=alpha)
+    inv_fft = mfd.inverse_3_times_3_B(b_fft, pnt, relax[0])
+    A, H, P = ne.pc_mfd_handle(a_fft, (pnt * b_fft[0], pnt * b_fft[1]), mfd.pseudochiral_trivial_handle(N, d), inv_fft, relax[0])
+    x0 = oracle.random_x0(3 * N ** 3, 8, 9)
+    lam_s, _, info_s = pcb.lobpcg.lobpcg_sep_softlock(H, P, x0, 5)
+    lam_n, _, info_n = pcb.lobpcg.lobpcg_sep_nolock(H, P, x0, 5)
+    assert np.allclose(lam_s[:5], lam_n[:5], rtol=1e-6)
+    with pytest.raises(NotImplementedError):
+        pcb.lobpcg.lobpcg_sep_softlock(H, P, x0, 5, longortho=True)
+    # H must not run in place on the five-pass path (coupled 3x3 dielectric): the C ABI reports it
+    ctx = pcb.get_context(N)
+    X = ctx.from_host(x0)
+    with pytest.raises(pcb.PcbError):
+        H.op.apply_into(pcb._lib.APPLY_H, X, X)
+    with pytest.raises(pcb.PcbError):
+        pcb.devarray.Context(7)            # no FFT plan for N = 7
