@@ -2,8 +2,9 @@
 //
 //   k_resid_precond : W = K_P^-1 (X diag(lambda) - HX) and column 2-norms of the raw residual in one pass
 //                     (lobpcg.py:394-397 + numerical_experiments.py:83 / pcfft.py:50-70 / discretization.py:284-295)
-//   k_gram2         : G = S^H S, T = S^H HS for a list of columns, Hermitian half only (orthogonalization.py:143-144)
-//   k_update        : P <- [W P] E_wp, X <- X E_x + P (same for HS) in one pass (lobpcg.py:1248-1270)
+//   k_gram2         : G = S^H S, T = S^H HS for a list of columns, Hermitian half only, on the FP64 tensor pipe
+//                     (mma.sync m8n8k4 = SASS DMMA; orthogonalization.py:143-144)
+//   k_update        : P <- [W P] E_wp, X <- X E_x + P (same for HS) in one pass, also DMMA (lobpcg.py:1248-1270)
 //   k_coldots       : diag(A^H B) for column pairs (numerical_experiments.py:105-111, environment.py:131-157)
 //   layout helpers  : row-major (R, k) host layout <-> planar columns, index list -> bit mask
 // All reductions are two-stage (per-CTA partials, then a fixed-order sum) so results are deterministic.

@@ -2,22 +2,24 @@
 // (reference: pcfft.py:130-181, _kernels.py:13-71, discretization.py:352-401) as hand-written
 // mixed-radix complex128 FFT passes with the Fourier symbols and the dielectric multiply fused in.
 //
-// One block apply = five global passes over the destination column (all in place except the
-// first, which reads X and writes the destination):
+// Two pass structures (chosen per call in pcb_capi.cu):
 //
-//   xfwd   x-lines:  y = (-conj k) x x  fused on load, forward FFT along i0          (K_A^H, pass 1)
-//   yline  y-lines:  forward FFT along i1                                            (pass 2)
-//   zmid   z-lines:  forward FFT along i2, M (point-wise, real space), inverse FFT   (pass 3)
-//   yline  y-lines:  inverse FFT along i1                                            (pass 4)
-//   xinv   x-lines:  inverse FFT along i0, 1/N^3, k x v, + gamma conj(k)(k.x) + shift x on store
+// PLANE MODE -- three global passes, 7 column transfers per op-apply (N % 8 == 0, N <= 120, identity / isotropic M):
+//   k_xfwd<T>  x-lines:  y = (-conj k) x x fused on load, forward FFT along i0, stored TRANSPOSED as W'[c][i0][i2][i1]
+//   k_mid      one (i1,i2) plane per CTA in shared memory: forward y, forward z, M, inverse z, inverse y, in place
+//   k_xinv<T>  x-lines:  inverse FFT along i0 from W', 1/N^3, k x v, + gamma conj(k)(k.x) + shift x, natural layout
 //
-// Every 1-D FFT of length N = R1*R2 is two in-register radix codelets with ONE shared-memory
-// exchange between them:  global -> regs (radix R1) -> smem -> regs (radix R2) -> global.
-// y/z lines are processed for 8 consecutive i0 at once (128-byte segments, fully coalesced);
-// coprime factorisations use the Good-Thomas maps there (no twiddles), x-lines always use
-// Cooley-Tukey so that global accesses stay contiguous.  The z pass keeps the data in
-// registers between the last forward radix and the first inverse radix, so FFT+M+IFFT along
-// z costs two exchanges.
+// FIVE PASSES -- 11 column transfers (any N with a plan, coupled 3x3 M; the cross-DoF M splits pass 3 around a stencil kernel):
+//   k_xfwd     x-lines:  y = (-conj k) x x  fused on load, forward FFT along i0          (K_A^H, pass 1)
+//   k_line     y-lines:  forward FFT along i1                                            (pass 2)
+//   k_zmid     z-lines:  forward FFT along i2, M (point-wise, real space), inverse FFT   (pass 3)
+//   k_line     y-lines:  inverse FFT along i1                                            (pass 4)
+//   k_xinv     x-lines:  inverse FFT along i0, 1/N^3, k x v, + gamma conj(k)(k.x) + shift x on store
+//
+// Every 1-D FFT of length N = R1*R2 is two in-register radix codelets (pcb_codelets.cuh) with one shared-memory
+// exchange between them.  y/z lines are processed for 8 consecutive i0 at once (128-byte segments, fully coalesced);
+// coprime factorisations use the Good-Thomas maps there (no twiddles), x-lines always use Cooley-Tukey so that global
+// accesses stay contiguous.  Around M the data stays in registers between the last forward and the first inverse radix.
 #pragma once
 #include "pcb_common.cuh"
 
