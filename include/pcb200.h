@@ -109,6 +109,10 @@ int pcb_residual(pcb_op* op, int precond, int ncols, const void* const* x, const
  * Only one triangle (of 4x4 column blocks) is accumulated and completed by conjugation: HS must be H S with H Hermitian,
  * so that S^H HS is Hermitian up to rounding -- which is the only way the solver uses it. */
 int pcb_gram2(pcb_ctx* ctx, int n, const void* const* s, const void* const* hs, void* G, void* T);
+/* Same, accumulating only the rows of the first `ntop` columns (rounded up to a multiple of 8): rows a < ntop of G and T (and,
+ * by Hermitian completion, their columns) are valid, the rest is zero.  Used by the solver's incremental Gram update, where
+ * only the new block W changes between iterations and the [X P] blocks follow from the previous Rayleigh-Ritz rotation. */
+int pcb_gram2_top(pcb_ctx* ctx, int n, int ntop, const void* const* s, const void* const* hs, void* G, void* T);
 /* _sep_update_after_rr (lobpcg.py:1248-1270): s/hs list the n_loc input columns [X(m) | W_act | P_act];
  * E is (n_loc x m) row-major complex128 on the host.  Pn = [W_act P_act] E[m:], X <- X E[:m] + Pn (in place), P <- Pn. */
 int pcb_update(pcb_ctx* ctx, int m, int n_loc, void* const* s, void* const* hs, void* const* p_out, void* const* hp_out,

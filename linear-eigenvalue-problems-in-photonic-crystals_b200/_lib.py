@@ -53,6 +53,7 @@ SIGNATURES = {
     "pcb_apply_timed": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_void_pp, c_void_pp, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "pcb_residual": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_void_pp, c_void_pp, c_void_pp, c_double_p, c_double_p]),
     "pcb_gram2": (C.c_int, [C.c_void_p, C.c_int, c_void_pp, c_void_pp, C.c_void_p, C.c_void_p]),
+    "pcb_gram2_top": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_void_pp, c_void_pp, C.c_void_p, C.c_void_p]),
     "pcb_update": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_void_pp, c_void_pp, c_void_pp, c_void_pp, C.c_void_p]),
     "pcb_coldots": (C.c_int, [C.c_void_p, C.c_int, c_void_pp, c_void_pp, C.c_void_p]),
     "pcb_axpby": (C.c_int, [C.c_void_p, C.c_int, c_void_pp, c_void_pp, C.c_double, C.c_double]),

@@ -205,15 +205,14 @@ PCB_HD void pcb_pair_from_index(int p, int nb, int& ia, int& ib) {   // row-majo
 }
 
 __global__ void __launch_bounds__(32 * PCB_GM_MAXW, 1)
-k_gram2(PcbColList S, PcbColList HS, int n, int nt, long long R, cplx* __restrict__ partial /* [gridDim.x][2][nc*nc] */) {
+k_gram2(PcbColList S, PcbColList HS, int n, int nt, int npairs, long long R, cplx* __restrict__ partial /* [gridDim.x][2][nc*nc] */) {
     PCB_DYN_SMEM(cplx, sm);                      // [2 stages][2: S, HS][nc][LD]
     const int nc = 8 * nt;
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int warp = tid >> 5, lane = tid & 31, W = nthr >> 5;
     const int g = lane >> 2, tig = lane & 3;
     const size_t matElems = (size_t)nc * PCB_GM_LD;
-    // tile pairs of this warp
-    const int npairs = nt * (nt + 1) / 2;
+    // tile pairs of this warp: the first `npairs` pairs of the row-major upper triangle (all of it, or only the leading tile rows)
     const int base = npairs / W, extra = npairs % W;
     const int cnt = base + (warp < extra ? 1 : 0);
     const int p0 = warp * base + (warp < extra ? warp : extra);
@@ -294,8 +293,8 @@ k_gram2(PcbColList S, PcbColList HS, int n, int nt, long long R, cplx* __restric
 }
 
 // Sum the per-CTA partials in fixed order and complete the Hermitian matrices:
-// entry (a,b) was accumulated iff tile(a) <= tile(b); the others are conj of (b,a).
-__global__ void k_gram_finish(const cplx* __restrict__ partial, int nblocks, int nt, cplx* __restrict__ out /* [2][nc*nc] */) {
+// entry (a,b) was accumulated iff tile(a) <= tile(b) and tile(a) < ttop; the others are conj of (b,a) (or zero if neither was).
+__global__ void k_gram_finish(const cplx* __restrict__ partial, int nblocks, int nt, int ttop, cplx* __restrict__ out /* [2][nc*nc] */) {
     const int nc = 8 * nt;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= 2 * nc * nc) return;
@@ -303,6 +302,7 @@ __global__ void k_gram_finish(const cplx* __restrict__ partial, int nblocks, int
     const int a = ab / nc, b = ab % nc;
     const bool direct = (a / 8) <= (b / 8);
     const int src = direct ? a * nc + b : b * nc + a;
+    if ((direct ? a : b) / 8 >= ttop) { out[e] = cmake(0.0, 0.0); return; }
     cplx v = cmake(0.0, 0.0);
     for (int k = 0; k < nblocks; ++k) v = cadd(v, partial[(size_t)k * 2 * nc * nc + which * nc * nc + src]);
     out[e] = direct ? v : cconj(v);

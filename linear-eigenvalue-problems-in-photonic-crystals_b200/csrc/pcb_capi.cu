@@ -584,12 +584,16 @@ int pcb_residual(pcb_op* o, int precond, int ncols, const void* const* x, const 
 }
 
 int pcb_gram2(pcb_ctx* c, int n, const void* const* s, const void* const* hs, void* G, void* T) {
-    PCB_CHECK_ARG(c && s && hs && G && T && n > 0 && n <= PCB_MAXL, "bad arguments (n <= 96)");
+    return pcb_gram2_top(c, n, n, s, hs, G, T);
+}
+int pcb_gram2_top(pcb_ctx* c, int n, int ntop, const void* const* s, const void* const* hs, void* G, void* T) {
+    PCB_CHECK_ARG(c && s && hs && G && T && n > 0 && n <= PCB_MAXL && ntop > 0 && ntop <= n, "bad arguments (n <= 96, 0 < ntop <= n)");
     PCB_CUDA_OK(cudaSetDevice(c->device));
     const int nt = (n + 7) / 8, nc = 8 * nt;
+    const int ttop = (ntop + 7) / 8;                       // leading tile rows to accumulate
     PcbColList S, HS;
     for (int j = 0; j < PCB_MAXL; ++j) { S.p[j] = (j < n) ? (const cplx*)s[j] : nullptr; HS.p[j] = (j < n) ? (const cplx*)hs[j] : nullptr; }
-    const int npairs = nt * (nt + 1) / 2;
+    const int npairs = ttop * nt - ttop * (ttop - 1) / 2;  // pairs (ta < ttop, tb >= ta) = a prefix of the row-major upper triangle
     int W = 4 * ((npairs + 4 * PCB_GM_PPW - 1) / (4 * PCB_GM_PPW));     // multiple of 4 warps, <= PPW tile pairs per warp
     if (W > PCB_GM_MAXW) { pcb_set_error("pcb_gram2: n = %d needs %d warps", n, W); return -2; }
     const size_t smem = sizeof(cplx) * 4 * (size_t)nc * PCB_GM_LD;
@@ -606,11 +610,11 @@ int pcb_gram2(pcb_ctx* c, int n, const void* const* s, const void* const* hs, vo
     if (smem > 48 * 1024) PCB_CUDA_OK(cudaFuncSetAttribute(k_gram2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 #endif
     dim3 grid((unsigned)gx, 1, 1);
-    PCB_LAUNCH(k_gram2, grid, dim3(32 * W, 1, 1), smem, c->stream, S, HS, n, nt, c->R, (cplx*)c->partial);
+    PCB_LAUNCH(k_gram2, grid, dim3(32 * W, 1, 1), smem, c->stream, S, HS, n, nt, npairs, c->R, (cplx*)c->partial);
     PCB_CUDA_OK(cudaGetLastError());
     cplx* dout = (cplx*)c->dsmall;
     const int ne = 2 * nc * nc;
-    PCB_LAUNCH(k_gram_finish, dim3((unsigned)((ne + 127) / 128), 1, 1), dim3(128, 1, 1), 0, c->stream, (const cplx*)c->partial, (int)gx, nt, dout);
+    PCB_LAUNCH(k_gram_finish, dim3((unsigned)((ne + 127) / 128), 1, 1), dim3(128, 1, 1), 0, c->stream, (const cplx*)c->partial, (int)gx, nt, ttop, dout);
     PCB_CUDA_OK(cudaGetLastError());
     c->launches += 2;
     if (comm_allreduce(c, (double*)dout, 2LL * ne)) return -1;      // large-grid mode: sum of the per-slab Gram pairs (NCCL)

@@ -30,6 +30,16 @@ def gram_pair(s, hs):
 RANK_TOL = 1e-14      # relative eigenvalue threshold of the rank-revealing fallback below
 
 
+def gram_pair_top(s, hs, ntop):
+    """Rows of the first `ntop` columns of the Gram pair (pcb_gram2_top): (G, T) with rows/columns < ntop valid."""
+    n = s.k
+    G = np.empty((n, n), dtype=np.complex128)
+    T = np.empty((n, n), dtype=np.complex128)
+    L.check(L.lib().pcb_gram2_top(s.ctx.h, n, int(ntop), L.ptr_array(s.ptrs), L.ptr_array(hs.ptrs), G.ctypes.data, T.ctypes.data),
+            "pcb_gram2_top")
+    return G, T
+
+
 def rr_small(ss, shs, min_rank=None):
     """L = inv(chol(G)); eigh(L T L^H); E = L^H V (orthogonalization.py:148-151) on the small matrices.
 
