@@ -595,6 +595,7 @@ int pcb_gram2_top(pcb_ctx* c, int n, int ntop, const void* const* s, const void*
     for (int j = 0; j < PCB_MAXL; ++j) { S.p[j] = (j < n) ? (const cplx*)s[j] : nullptr; HS.p[j] = (j < n) ? (const cplx*)hs[j] : nullptr; }
     const int npairs = ttop * nt - ttop * (ttop - 1) / 2;  // pairs (ta < ttop, tb >= ta) = a prefix of the row-major upper triangle
     int W = 4 * ((npairs + 4 * PCB_GM_PPW - 1) / (4 * PCB_GM_PPW));     // multiple of 4 warps, <= PPW tile pairs per warp
+    { const int w8 = 4 * ((npairs + 3) / 4); if (W < 8 && w8 > W) W = w8 < 8 ? w8 : 8; }   // few pairs: still 8 warps (2 CTAs/SM) for latency hiding
     if (W > PCB_GM_MAXW) { pcb_set_error("pcb_gram2: n = %d needs %d warps", n, W); return -2; }
     const size_t smem = sizeof(cplx) * 4 * (size_t)nc * PCB_GM_LD;
     const long long ntiles = (c->R + PCB_GM_TR - 1) / PCB_GM_TR;

@@ -126,3 +126,16 @@ def test_short_qr_and_gep_chol(pcb):
     assert np.allclose(T @ vec, G @ vec * lam, atol=1e-10)
     import scipy.linalg
     assert np.allclose(lam, scipy.linalg.eigh(T, G, eigvals_only=True), atol=1e-11)
+
+
+@pytest.mark.parametrize("N,n,ntop", [(6, 48, 16), (6, 48, 5), (8, 24, 8), (6, 33, 20), (6, 96, 32)])
+def test_gram_pair_top_rows(pcb, N, n, ntop):
+    """pcb_gram2_top: only the leading rows are accumulated; rows/columns < ntop equal the full Gram pair."""
+    ctx, s, S = _blocks(pcb, N, n, 11)
+    d = np.random.default_rng(12).standard_normal((ctx.R, 1))
+    hs = d * s
+    HS = ctx.from_host(hs)
+    G, T = pcb.orthogonalization.gram_pair_top(S, HS, ntop)
+    g, t = s.conj().T @ s, s.conj().T @ hs
+    assert relerr(G[:ntop, :], g[:ntop, :]) < 1e-13 and relerr(G[:, :ntop], g[:, :ntop]) < 1e-13
+    assert relerr(T[:ntop, :], t[:ntop, :]) < 1e-13 and relerr(T[:, :ntop], t[:, :ntop]) < 1e-13

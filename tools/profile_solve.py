@@ -25,6 +25,7 @@ op = H.op
 op.apply_into = timed("apply_H", op.apply_into)
 op.residual = timed("residual", op.residual)
 lob.gram_pair = timed("gram_pair", lob.gram_pair)
+lob.gram_pair_top = timed("gram_pair_top", lob.gram_pair_top)
 lob.rr_small = timed("rr_small(host)", lob.rr_small)
 lib = pcb._lib.lib()
 class LibProxy:
