@@ -81,9 +81,12 @@ def recompute_normalize_print(lambdas_in, x, A_func, shift=0.0, scal=SCAL):
     if not isinstance(x, DeviceBlock):
         n = round((np.asarray(x).shape[0] // 3) ** (1 / 3))
         x = DeviceBlock.from_host(devarray.get_context(n), x)
-    adax = A_func(x)
+    if isinstance(A_func, OperatorCallable) and A_func.op.ctx is x.ctx:
+        adax = A_func.op.apply_into(A_func.mode, x, x.ctx.work_block("recompute.adax", x.k))   # cached work space
+    else:
+        adax = A_func(x)
     lambdas_pnt = lambdas_in - shift if shift > 0.0 else lambdas_in.copy()
-    tmp = DeviceBlock(x.ctx, x.k)
+    tmp = x.ctx.work_block("recompute.tmp", x.k)
     res = _residual_helper(x.ctx).residual(x, adax, tmp, lambdas_pnt, precond=False)    # ||x lambda - A x||
     lambdas_re = (column_dots(x, adax) / column_dots(x, x)).real
     for i in np.where(np.isnan(lambdas_pnt))[0]:
