@@ -304,7 +304,10 @@ __global__ void k_gram_finish(const cplx* __restrict__ partial, int nblocks, int
     const int src = direct ? a * nc + b : b * nc + a;
     if ((direct ? a : b) / 8 >= ttop) { out[e] = cmake(0.0, 0.0); return; }
     cplx v = cmake(0.0, 0.0);
-    for (int k = 0; k < nblocks; ++k) v = cadd(v, partial[(size_t)k * 2 * nc * nc + which * nc * nc + src]);
+#ifndef PCB_EMU
+#pragma unroll 8
+#endif
+    for (int k = 0; k < nblocks; ++k) v = cadd(v, partial[(size_t)k * 2 * nc * nc + which * nc * nc + src]);   // independent loads, fixed order
     out[e] = direct ? v : cconj(v);
 }
 
