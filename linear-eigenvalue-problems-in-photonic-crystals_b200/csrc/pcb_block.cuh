@@ -476,43 +476,61 @@ __global__ void __launch_bounds__(256) k_diel_point(PcbOp op, const cplx* __rest
 struct PcbStencil { int k; double w[8]; };   // taps w[j] at offsets (1-k+j), j < 2k
 PCB_HD int pcb_wrap(int i, int N) { i %= N; return i < 0 ? i + N : i; }
 
-__global__ void __launch_bounds__(128) k_diel_crossdof(PcbOp op, PcbStencil st, const cplx* __restrict__ X, cplx* __restrict__ Y) {
+// K > 0: 2K taps known at compile time (K = 1 is the reference's default, discretization.py:403); K = 0: runtime st.k.
+// One thread per grid point and column (blockIdx.y): all three output components (gather form); out of place.
+template <int K>
+__global__ void __launch_bounds__(256) k_diel_crossdof(PcbOp op, PcbStencil st, PcbCols cols) {
     const int N = op.N;
     const long long nn = op.nn;
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= nn) return;
-    int i[3] = {(int)(p % N), (int)((p / N) % N), (int)(p / ((long long)N * N))};
-    const unsigned mp = op.mask[p];
+    const cplx* __restrict__ X = cols.in[blockIdx.y];
+    cplx* __restrict__ Y = cols.out[blockIdx.y];
+    const int i[3] = {(int)(p % N), (int)((p / N) % N), (int)(p / ((long long)N * N))};
+    const long long stride[3] = {1, N, (long long)N * N};
+    const unsigned mp = __ldg(op.mask + p);
     cplx y[3];
     PCB_UNROLL
     for (int c = 0; c < 3; ++c) y[c] = cscale(X[c * nn + p], ((mp >> c) & 1u) ? op.ediag[c] : 1.0);
     // pairs (a,b): (0,1) c-axis 2, ct-axis 1;  (0,2) c-axis 2, ct-axis 0;  (1,2) c-axis 1, ct-axis 0
-    const int PA[3] = {0, 0, 1}, PB[3] = {1, 2, 2}, CAX[3] = {2, 2, 1}, TAX[3] = {1, 0, 0};
-    const int taps = 2 * st.k;
+    constexpr int PA[3] = {0, 0, 1}, PB[3] = {1, 2, 2}, CAX[3] = {2, 2, 1}, TAX[3] = {1, 0, 0};
+    const int kk = K > 0 ? K : st.k;
+    const int taps = 2 * kk;
+    PCB_UNROLL
     for (int pr = 0; pr < 3; ++pr) {
         const cplx e = op.eoff[pr];
         if (e.x == 0.0 && e.y == 0.0) continue;
         const int a = PA[pr], b = PB[pr], cax = CAX[pr], tax = TAX[pr];
         const double Ia = (double)((mp >> a) & 1u), Ib_p = (double)((mp >> b) & 1u);
+        const cplx* __restrict__ Xa = X + a * nn;
+        const cplx* __restrict__ Xb = X + b * nn;
         cplx sa = cmake(0.0, 0.0), sb = cmake(0.0, 0.0);
-        for (int j1 = 0; j1 < taps; ++j1) {
-            for (int j2 = 0; j2 < taps; ++j2) {
-                const double w = st.w[j1] * st.w[j2];
-                const int oc = 1 - st.k + j1, ot = 1 - st.k + j2;
-                // y_a(p) += e/2 * T(p,q) (I_a(p) + I_b(q)) x_b(q),  q = p + oc on c-axis, - ot on ct-axis
-                int q[3] = {i[0], i[1], i[2]};
-                q[cax] = pcb_wrap(i[cax] + oc, N);
-                q[tax] = pcb_wrap(i[tax] - ot, N);
-                const long long qi = q[0] + (long long)N * (q[1] + (long long)N * q[2]);
-                const double Ibq = (double)((op.mask[qi] >> b) & 1u);
-                sa = cadd(sa, cscale(X[b * nn + qi], w * 0.5 * (Ia + Ibq)));
-                // y_b(p) += conj(e)/2 * T(p',p) (I_a(p') + I_b(p)) x_a(p'),  p' = p - oc on c-axis, + ot on ct-axis
-                int pp[3] = {i[0], i[1], i[2]};
-                pp[cax] = pcb_wrap(i[cax] - oc, N);
-                pp[tax] = pcb_wrap(i[tax] + ot, N);
-                const long long pi_ = pp[0] + (long long)N * (pp[1] + (long long)N * pp[2]);
-                const double Iap = (double)((op.mask[pi_] >> a) & 1u);
-                sb = cadd(sb, cscale(X[a * nn + pi_], w * 0.5 * (Iap + Ib_p)));
+#ifndef PCB_EMU
+#pragma unroll
+#endif
+        for (int j1 = 0; j1 < (K > 0 ? 2 * K : taps); ++j1) {
+            const int oc = 1 - kk + j1;
+            // wrapped displacement along the c-axis for +oc and -oc (|oc| <= k < N)
+            const int cp = i[cax] + oc, cm = i[cax] - oc;
+            const long long dcp = (long long)(cp >= N ? oc - N : (cp < 0 ? oc + N : oc)) * stride[cax];
+            const long long dcm = (long long)(cm >= N ? -oc - N : (cm < 0 ? -oc + N : -oc)) * stride[cax];
+#ifndef PCB_EMU
+#pragma unroll
+#endif
+            for (int j2 = 0; j2 < (K > 0 ? 2 * K : taps); ++j2) {
+                const int ot = 1 - kk + j2;
+                const double w = st.w[j1] * st.w[j2] * 0.5;
+                const int tm = i[tax] - ot, tp = i[tax] + ot;
+                const long long dtm = (long long)(tm >= N ? -ot - N : (tm < 0 ? -ot + N : -ot)) * stride[tax];
+                const long long dtp = (long long)(tp >= N ? ot - N : (tp < 0 ? ot + N : ot)) * stride[tax];
+                // y_a(p) += e/2 * T(p,q) (I_a(p) + I_b(q)) x_b(q),  q = p + oc on the c-axis, - ot on the ct-axis
+                const long long qi = p + dcp + dtm;
+                const double Ibq = (double)((__ldg(op.mask + qi) >> b) & 1u);
+                sa = cadd(sa, cscale(Xb[qi], w * (Ia + Ibq)));
+                // y_b(p) += conj(e)/2 * T(p',p) (I_a(p') + I_b(p)) x_a(p'),  p' = p - oc on the c-axis, + ot on the ct-axis
+                const long long pi_ = p + dcm + dtp;
+                const double Iap = (double)((__ldg(op.mask + pi_) >> a) & 1u);
+                sb = cadd(sb, cscale(Xa[pi_], w * (Iap + Ib_p)));
             }
         }
         y[a] = cfma(e, sa, y[a]);

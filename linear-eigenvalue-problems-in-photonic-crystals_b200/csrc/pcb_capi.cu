@@ -417,10 +417,15 @@ void pcb_op_destroy(pcb_op* o) {
     delete o;
 }
 
-static int launch_crossdof(pcb_op* o, const cplx* X, cplx* Y) {
+// Y_j = M_CrossDoF X_j for kc columns in one launch (blockIdx.y = column)
+static int launch_crossdof(pcb_op* o, int kc, const cplx* const* X, cplx* const* Y) {
     pcb_ctx* c = o->ctx;
-    dim3 grid((unsigned)((c->nn + 127) / 128), 1, 1);
-    PCB_LAUNCH(k_diel_crossdof, grid, dim3(128, 1, 1), 0, c->stream, o->d, o->diel->st, X, Y);
+    PcbCols cols;
+    for (int j = 0; j < kc; ++j) { cols.in[j] = X[j]; cols.out[j] = Y[j]; }
+    dim3 grid((unsigned)((c->nn + 255) / 256), (unsigned)kc, 1);
+    if (o->diel->st.k == 1) PCB_LAUNCH(k_diel_crossdof<1>, grid, dim3(256, 1, 1), 0, c->stream, o->d, o->diel->st, cols);
+    else if (o->diel->st.k == 2) PCB_LAUNCH(k_diel_crossdof<2>, grid, dim3(256, 1, 1), 0, c->stream, o->d, o->diel->st, cols);
+    else PCB_LAUNCH(k_diel_crossdof<0>, grid, dim3(256, 1, 1), 0, c->stream, o->d, o->diel->st, cols);
     PCB_CUDA_OK(cudaGetLastError());
     c->launches++;
     return 0;
@@ -475,10 +480,10 @@ int pcb_apply(pcb_op* o, int mode, int ncols, const void* const* in, void* const
                     for (int j = 0; j < kc; ++j) tmp.out[j] = c->scratch + (size_t)j * c->R;
                     const int fwd[3] = {PCB_PASS_XFWD_SYM, PCB_PASS_YFWD, PCB_PASS_ZFWD};
                     for (int i = 0; i < 3; ++i) if (pl->pass(o->d, tmp, kc, fwd[i], c->tw, c->stream, c->sms)) return -1;
-                    for (int j = 0; j < kc; ++j) if (launch_crossdof(o, tmp.out[j], cols.out[j])) return -1;
+                    if (launch_crossdof(o, kc, tmp.out, cols.out)) return -1;
                     const int inv[3] = {PCB_PASS_ZINV, PCB_PASS_YINV, last};
                     for (int i = 0; i < 3; ++i) if (pl->pass(o->d, cols, kc, inv[i], c->tw, c->stream, c->sms)) return -1;
-                    c->launches += 6;
+                    c->launches += 6;   // + the stencil launch counted in launch_crossdof
                 }
             } break;
             case PCB_APPLY_P: {
@@ -492,16 +497,15 @@ int pcb_apply(pcb_op* o, int mode, int ncols, const void* const* in, void* const
                 c->launches++;
             } break;
             case PCB_APPLY_M:
-                for (int j = 0; j < kc; ++j) {
-                    if (cross) {
-                        PCB_CHECK_ARG(cols.in[j] != cols.out[j], "cross-DoF dielectric cannot run in place");
-                        if (launch_crossdof(o, cols.in[j], cols.out[j])) return -1;
-                    } else {
-                        dim3 grid((unsigned)grid_for(c, c->nn, 256, 8), 1, 1);
-                        PCB_LAUNCH(k_diel_point, grid, dim3(256, 1, 1), 0, c->stream, o->d, cols.in[j], cols.out[j]);
-                        PCB_CUDA_OK(cudaGetLastError());
-                        c->launches++;
-                    }
+                if (cross) {
+                    for (int j = 0; j < kc; ++j) PCB_CHECK_ARG(cols.in[j] != cols.out[j], "cross-DoF dielectric cannot run in place");
+                    if (launch_crossdof(o, kc, cols.in, cols.out)) return -1;
+                }
+                for (int j = 0; j < kc && !cross; ++j) {
+                    dim3 grid((unsigned)grid_for(c, c->nn, 256, 8), 1, 1);
+                    PCB_LAUNCH(k_diel_point, grid, dim3(256, 1, 1), 0, c->stream, o->d, cols.in[j], cols.out[j]);
+                    PCB_CUDA_OK(cudaGetLastError());
+                    c->launches++;
                 }
                 break;
             case PCB_APPLY_KA: case PCB_APPLY_KAH: case PCB_APPLY_KB: {

@@ -392,7 +392,7 @@ PCB_D void pcb_ztile_load(cplx* __restrict__ st, const cplx* __restrict__ Y, lon
 // NSTAGE = 2: the next tile streams into the other stage while this one is transformed; NSTAGE = 1 (large N, where two stages
 // would leave one CTA per SM): load, wait, transform in the single stage and rely on the co-resident CTAs for overlap.
 template <class P, int DIEL, int NT, int NSTAGE = 2>
-__global__ void __launch_bounds__(NT, ((DIEL == 2 || NT > 256) ? 1 : 2)) k_zmid(PcbOp op, PcbCols cols, const cplx* __restrict__ tw, int ncols) {
+__global__ void __launch_bounds__(NT, (NT > 256 ? 1 : 2)) k_zmid(PcbOp op, PcbCols cols, const cplx* __restrict__ tw, int ncols) {
     constexpr int N = P::N, R1 = P::R1, R2 = P::R2;
     constexpr int STAGE = 3 * N * 8;
     PCB_DYN_SMEM(cplx, sm);   // [NSTAGE][3][N][8]
@@ -445,37 +445,47 @@ __global__ void __launch_bounds__(NT, ((DIEL == 2 || NT > 256) ? 1 : 2)) k_zmid(
         __syncthreads();
         // forward radix R2 (-> real space), M, inverse radix R2
         if (DIEL == 2) {
-            for (int item = tid; item < R1 * 8; item += NT) {
-                const int i0l = item % 8, k1 = item / 8;
+            // coupled 3x3 M: the three components of a point meet in shared memory.  Per-component radix items (as for the
+            // other dielectrics, v[R2] registers instead of v[3][R2]) around a point-wise phase; the real-space value with
+            // digits (k1, k2) sits in slot lin(k1, k2) and belongs to grid index i2 = lout(k1, k2).
+            for (int item = tid; item < 3 * R1 * 8; item += NT) {
+                const int i0l = item % 8, k1 = (item / 8) % R1, c = item / (8 * R1);
+                if (t0 * 8 + i0l >= N) continue;
+                const int b1 = P::lin1(k1);
+                cplx* __restrict__ sc = st + c * N * 8 + i0l;
+                cplx v[R2];
+                PCB_UNROLL
+                for (int n2 = 0; n2 < R2; ++n2) v[n2] = sc[P::wrap(b1 + P::lin2(n2)) * 8];
+                Dft<R2, -1>::run(v);
+                PCB_UNROLL
+                for (int k2 = 0; k2 < R2; ++k2) sc[P::wrap(b1 + P::lin2(k2)) * 8] = v[k2];
+            }
+            __syncthreads();
+            for (int e = tid; e < N * 8; e += NT) {
+                const int i0l = e % 8, slot = e / 8;
                 const int i0 = t0 * 8 + i0l;
                 if (i0 >= N) continue;
-                const int b1 = P::lin1(k1), o1 = P::lout1(k1);
-                const unsigned char* __restrict__ mp = op.mask + (long long)i1 * N + i0;
-                unsigned char mk[R2];
+                const int i2 = P::coord(slot);
+                const unsigned mk = __ldg(op.mask + ((long long)i2 * N + i1) * N + i0);
+                cplx u[3] = {st[slot * 8 + i0l], st[(N + slot) * 8 + i0l], st[(2 * N + slot) * 8 + i0l]};
+                pcb_diel_point(op, mk, u);
+                st[slot * 8 + i0l] = u[0]; st[(N + slot) * 8 + i0l] = u[1]; st[(2 * N + slot) * 8 + i0l] = u[2];
+            }
+            __syncthreads();
+            for (int item = tid; item < 3 * R1 * 8; item += NT) {
+                const int i0l = item % 8, k1 = (item / 8) % R1, c = item / (8 * R1);
+                if (t0 * 8 + i0l >= N) continue;
+                const int b1 = P::lin1(k1);
+                cplx* __restrict__ sc = st + c * N * 8 + i0l;
+                cplx v[R2];
                 PCB_UNROLL
-                for (int k2 = 0; k2 < R2; ++k2) mk[k2] = __ldg(mp + P::wrap(o1 + P::lout2(k2)) * (N * N));
-                cplx v[3][R2];
+                for (int k2 = 0; k2 < R2; ++k2) v[k2] = sc[P::wrap(b1 + P::lin2(k2)) * 8];
+                Dft<R2, +1>::run(v);
                 PCB_UNROLL
-                for (int c = 0; c < 3; ++c) {
-                    PCB_UNROLL
-                    for (int n2 = 0; n2 < R2; ++n2) v[c][n2] = st[(c * N + P::wrap(b1 + P::lin2(n2))) * 8 + i0l];
-                    Dft<R2, -1>::run(v[c]);
-                }
-                PCB_UNROLL
-                for (int k2 = 0; k2 < R2; ++k2) {
-                    cplx u[3] = {v[0][k2], v[1][k2], v[2][k2]};
-                    pcb_diel_point(op, mk[k2], u);
-                    v[0][k2] = u[0]; v[1][k2] = u[1]; v[2][k2] = u[2];
-                }
-                PCB_UNROLL
-                for (int c = 0; c < 3; ++c) {
-                    Dft<R2, +1>::run(v[c]);
-                    PCB_UNROLL
-                    for (int n2 = 0; n2 < R2; ++n2) {
-                        cplx val = v[c][n2];
-                        if (!P::PFA && k1 > 0) { const cplx t = __ldg(tw + k1 * R2 + n2); val = cmul(val, cmake(t.x, -t.y)); }
-                        st[(c * N + P::wrap(b1 + P::lin2(n2))) * 8 + i0l] = val;
-                    }
+                for (int n2 = 0; n2 < R2; ++n2) {
+                    cplx val = v[n2];
+                    if (!P::PFA && k1 > 0) { const cplx t = __ldg(tw + k1 * R2 + n2); val = cmul(val, cmake(t.x, -t.y)); }
+                    sc[P::wrap(b1 + P::lin2(n2)) * 8] = val;
                 }
             }
         } else {
