@@ -68,3 +68,27 @@ def test_operator_vs_oracle_small(pcb, oracle, N, d_flag, typ, alpha):
     Ao, Ho, Po = oracle.pc_mfd_handle(a, b, diel, inv, shift)
     assert relerr(H(x), Ho(x)) < TOL
     assert relerr(A(x), Ao(x)) < TOL
+
+
+def test_dropin_symbol_multiplies_and_fft(pcb, oracle):
+    """The reference-named point-wise functions: A_block (K_A, K_A^H), H_block (gamma K_B, K_P^-1) and the batched FFT."""
+    N, d_flag = 8, "fcc"
+    alpha = np.array([0.4, 2 * np.pi, 0.1])
+    mfd, pcfft = pcb.discretization, pcb.pcfft
+    relax, pnt = mfd.set_relaxation(alpha)
+    a_fft, b_fft = mfd.fft_blocks(N, 1, pcb.dielectric.diel_info(d_flag, option="ct"), alpha=alpha)
+    inv_fft = mfd.inverse_3_times_3_B(b_fft, pnt, relax[0])
+    ao, bo, io, shift, gamma = oracle.assemble_symbols(N, d_flag, alpha)
+    x = oracle.random_x0(3 * N ** 3, 3, 77)
+    assert relerr(pcfft.A_block(x, a_fft), oracle.a_block(x, ao)) < TOL
+    assert relerr(pcfft.A_block_kernel(x, -a_fft.conj()), oracle.a_block(x, -ao.conj())) < TOL
+    assert relerr(pcfft.H_block_kernel(x, (pnt * b_fft[0], pnt * b_fft[1])), oracle.h_block(x, bo)) < TOL
+    assert relerr(pcfft.H_block(x, inv_fft), oracle.h_block(x, io)) < TOL
+    v = x[:, 0]                                              # 1-D vectors keep their shape
+    assert pcfft.H_block(v, inv_fft).shape == v.shape
+    assert relerr(pcfft.AMA_BB(v, a_fft, (pnt * b_fft[0], pnt * b_fft[1]), None, relax[0]),
+                  oracle.AMA_BB(v, ao, bo, lambda u: u, shift)) < TOL
+    import scipy.fft as sfft
+    F = pcfft.fftn3(x)
+    want = np.concatenate([sfft.fftn(x[c * N ** 3:(c + 1) * N ** 3].reshape(N, N, N, 3), axes=(0, 1, 2)).reshape(N ** 3, 3) for c in range(3)])
+    assert relerr(F, want) < TOL
