@@ -92,3 +92,23 @@ def test_dropin_symbol_multiplies_and_fft(pcb, oracle):
     F = pcfft.fftn3(x)
     want = np.concatenate([sfft.fftn(x[c * N ** 3:(c + 1) * N ** 3].reshape(N, N, N, 3), axes=(0, 1, 2)).reshape(N ** 3, 3) for c in range(3)])
     assert relerr(F, want) < TOL
+
+
+@pytest.mark.parametrize("typ", ["chiral", "pseudochiral_crossdof"])
+def test_fourth_order_stencils_k2(pcb, oracle, typ):
+    """Stencil half-width k = 2 (4-point mimetic stencils, discretization.py:152-193; cross-DoF averaging with 4 taps)."""
+    N, d_flag, k = 12, "sc_curv", 2
+    alpha = np.array([np.pi, 0.3, 0.0])
+    mfd, ne = pcb.discretization, pcb.numerical_experiments
+    relax, pnt = mfd.set_relaxation(alpha)
+    a_fft, b_fft = mfd.fft_blocks(N, k, pcb.dielectric.diel_info(d_flag, option="ct"), alpha=alpha)
+    inv_fft = mfd.inverse_3_times_3_B(b_fft, pnt, relax[0])
+    Diels = getattr(mfd, typ + "_handle")(N, d_flag, k=k)
+    A, H, P = ne.pc_mfd_handle(a_fft, (pnt * b_fft[0], pnt * b_fft[1]), Diels, inv_fft, relax[0])
+    ao, bo, io, shift, _ = oracle.assemble_symbols(N, d_flag, alpha, k=k)
+    diel = oracle.HANDLES[typ](N, d_flag, k=k) if typ == "pseudochiral_crossdof" else oracle.HANDLES[typ](N, d_flag)
+    Ao, Ho, Po = oracle.pc_mfd_handle(ao, bo, diel, io, shift)
+    x = oracle.random_x0(3 * N ** 3, 2, 5)
+    assert relerr(H(x), Ho(x)) < TOL
+    assert relerr(P(x), Po(x)) < TOL
+    assert relerr(Diels(x), diel(x)) < TOL
