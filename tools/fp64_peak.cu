@@ -32,6 +32,25 @@ __global__ void k_dmma(double* out, int iters) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// larger FP64 MMA shapes (PTX: sm_90+): m16n8k8 = 1024 FMA per warp instruction, A 4 regs, B 2 regs, C 4 regs per lane.
+// On sm_100a ptxas lowers it to a sequence of DMMA.8x8x4 (cuobjdump -sass shows no other DMMA shape), so it brings no
+// operand-traffic advantage over issuing m8n8k4 directly; kept here as the evidence.
+__global__ void k_dmma16(double* out, int iters) {
+    double c[4][4];
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) c[i][j] = 0.0;
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, b0 = 1.0 + threadIdx.x * 1e-6, b1 = b0 + 1e-3;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            asm volatile("mma.sync.aligned.m16n8k8.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                         : "+d"(c[i][0]), "+d"(c[i][1]), "+d"(c[i][2]), "+d"(c[i][3])
+                         : "d"(a0), "d"(a1), "d"(a2), "d"(a3), "d"(b0), "d"(b1));
+    }
+    double s = 0;
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) s += c[i][j];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 __global__ void k_lds(double* out, int iters) {
     extern __shared__ double2 sm[];
     for (int i = threadIdx.x; i < 2048; i += blockDim.x) sm[i] = make_double2(i, 1.0);
@@ -65,6 +84,10 @@ int main() {
         cudaEventRecord(e0); k_dmma<<<blocks, threads>>>(out, iters); cudaEventRecord(e1); cudaEventSynchronize(e1);
         cudaEventElapsedTime(&ms, e0, e1);
         printf("DMMA  threads/CTA %4d: %.2f TFLOP/s\n", threads, 2.0 * 256 * 8 * iters * (double)blocks * (threads / 32) / (ms * 1e-3) / 1e12);
+        k_dmma16<<<blocks, threads>>>(out, 100); cudaDeviceSynchronize();
+        cudaEventRecord(e0); k_dmma16<<<blocks, threads>>>(out, iters / 4); cudaEventRecord(e1); cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ms, e0, e1);
+        printf("DMMA m16n8k8 threads/CTA %4d: %.2f TFLOP/s\n", threads, 2.0 * 1024 * 4 * (iters / 4) * (double)blocks * (threads / 32) / (ms * 1e-3) / 1e12);
     }
     {
         const int threads = 512, blocks = sms * 4, iters = 20000;
