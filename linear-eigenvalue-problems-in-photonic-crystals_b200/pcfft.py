@@ -66,16 +66,25 @@ class Operator:
 
     def apply(self, mode, x, out=None):
         """Functional form used by the drop-in callables: returns a new array of x's kind
-        (`out`: optional preallocated host array -- e.g. pinned -- receiving the result of a host-array call)."""
-        blk, was_host = devarray.as_block(self.ctx, x)
-        res = DeviceBlock(self.ctx, blk.k, vec=blk.vec)
-        self.apply_into(mode, blk, res)
-        if not was_host:
+        (`out`: optional preallocated host array -- e.g. pinned -- receiving the result of a host-array call).
+        Host-array calls stage through cached device blocks (no cudaMalloc/cudaFree of GB-sized blocks per call)."""
+        if isinstance(x, DeviceBlock):
+            blk, _ = devarray.as_block(self.ctx, x)
+            res = DeviceBlock(self.ctx, blk.k, vec=blk.vec)
+            self.apply_into(mode, blk, res)
             return res
+        x = np.asarray(x)
+        vec = x.ndim == 1
+        k = 1 if vec else x.shape[1]
+        blk = self.ctx.work_block("apply.in", k)
+        res = self.ctx.work_block("apply.out", k)
+        blk.set(x)
+        self.apply_into(mode, blk, res)
         if out is not None:
             res.get(out=out.reshape(self.ctx.R, -1))
             return out
-        return res.get()
+        y = res.get()
+        return y.reshape(-1) if vec else y
 
     def residual(self, x, hx, w, lambdas, precond=True):
         """w_j = [K_P^-1] (lambda_j x_j - hx_j); returns ||lambda_j x_j - hx_j||_2 (lobpcg.py:394-397,442)."""
