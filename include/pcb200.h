@@ -94,6 +94,12 @@ void pcb_op_destroy(pcb_op* op);
  * its last pass) and PCB_APPLY_M with the cross-DoF dielectric; distinct columns must not overlap. */
 int pcb_apply(pcb_op* op, int mode, int ncols, const void* const* in, void* const* out);
 
+/* Y_host = op(X_host): the reference-facing call with host arrays -- x_host, y_host are the reference's row-major (3N^3, k)
+ * blocks (leading dimensions in elements; pinned memory from pcb_host_alloc makes the copies asynchronous).  Chunks of 8 columns
+ * flow through an H2D / compute / D2H pipeline on three streams so that both PCIe directions overlap.  Replaces
+ * `cp.asarray(x)` + H_func / A_func / P_func + `.get()` of a NumPy caller (numerical_experiments.py:73-85). */
+int pcb_apply_host(pcb_op* op, int mode, int k, const void* x_host, long long ldx, void* y_host, long long ldy);
+
 /* Same as pcb_apply for PCB_APPLY_A / PCB_APPLY_H, with a CUDA event between the passes: pass_ms[i] = device time of
  * pass i.  Five-pass operator: (x-forward+K_A^H, y-forward, z-forward+M+z-inverse, y-inverse, x-inverse+K_A+gamma K_B+shift),
  * npass <- 5; plane mode (N % 8 == 0, N <= 120, identity/isotropic M): (x-forward, fused y/z/M/z/y plane pass, x-inverse), npass <- 3.

@@ -50,6 +50,7 @@ SIGNATURES = {
     "pcb_op_update": (C.c_int, [C.c_void_p, c_double_p, C.c_double, C.c_double, C.c_double, C.c_void_p]),
     "pcb_op_destroy": (None, [C.c_void_p]),
     "pcb_apply": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_void_pp, c_void_pp]),
+    "pcb_apply_host": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong]),
     "pcb_apply_timed": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_void_pp, c_void_pp, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "pcb_residual": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_void_pp, c_void_pp, c_void_pp, c_double_p, c_double_p]),
     "pcb_gram2": (C.c_int, [C.c_void_p, C.c_int, c_void_pp, c_void_pp, C.c_void_p, C.c_void_p]),

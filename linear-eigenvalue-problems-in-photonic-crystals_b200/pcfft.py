@@ -73,18 +73,20 @@ class Operator:
             res = DeviceBlock(self.ctx, blk.k, vec=blk.vec)
             self.apply_into(mode, blk, res)
             return res
-        x = np.asarray(x)
+        x = np.ascontiguousarray(x, dtype=np.complex128)
         vec = x.ndim == 1
         k = 1 if vec else x.shape[1]
-        blk = self.ctx.work_block("apply.in", k)
-        res = self.ctx.work_block("apply.out", k)
-        blk.set(x)
-        self.apply_into(mode, blk, res)
-        if out is not None:
-            res.get(out=out.reshape(self.ctx.R, -1))
-            return out
-        y = res.get()
-        return y.reshape(-1) if vec else y
+        if x.shape[0] != self.ctx.R:
+            raise ValueError(f"expected {self.ctx.R} rows, got {x.shape[0]}")
+        if self.ctx.slab is not None:
+            raise ValueError("host-array calls need a full (non-slab) context")
+        y = out if out is not None else np.empty((self.ctx.R, k), dtype=np.complex128)
+        y2 = y.reshape(self.ctx.R, k)
+        if not y2.flags.c_contiguous or y2.dtype != np.complex128:
+            raise ValueError("out must be a C-contiguous complex128 array")
+        # H2D / compute / D2H pipeline over column chunks inside the C ABI
+        L.check(self._lib.pcb_apply_host(self.h, mode, k, x.ctypes.data, k, y2.ctypes.data, k), "pcb_apply_host")
+        return y.reshape(-1) if (vec and out is None) else y
 
     def residual(self, x, hx, w, lambdas, precond=True):
         """w_j = [K_P^-1] (lambda_j x_j - hx_j); returns ||lambda_j x_j - hx_j||_2 (lobpcg.py:394-397,442)."""
