@@ -71,6 +71,13 @@ def owari_cuda():
     return time.time()
 
 
+def norm(X):
+    """Frobenius norm of a block / 2-norm of a vector (environment.py:117-129), reduced on the device."""
+    from . import pcfft
+    import numpy as _np
+    return float(_np.sqrt(_np.sum(pcfft.column_dots(X, X).real)))
+
+
 def norms(X):
     """Column 2-norms (environment.py:131-143) of a DeviceBlock or NumPy array."""
     from . import pcfft

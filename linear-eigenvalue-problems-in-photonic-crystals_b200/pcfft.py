@@ -184,6 +184,8 @@ def A_block(x, D):
 
 
 A_block_kernel = A_block
+A_block_dim1 = A_block      # the reference's 1-D twins (pcfft.py:72-89,110-124): vectors keep their shape here
+H_block_dim1 = H_block
 
 
 def diel_apply(handle, x):
