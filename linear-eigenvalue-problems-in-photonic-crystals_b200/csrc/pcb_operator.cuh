@@ -420,10 +420,29 @@ __global__ void __launch_bounds__(NT, (NT > 256 ? 1 : 2)) k_zmid(PcbOp op, PcbCo
         } else {
             pcb_cp_wait<0>();
         }
+        const int t0 = (tile % tpc) % NT0, i1 = (tile % tpc) / NT0;
+        // dielectric bits of this thread's radix-R2 items (bit k2 = component c of point (i0, i1, i2 = lout(k1,k2)) in Omega_1),
+        // fetched before the barrier so that the mask latency hides behind the tile load and the first radix step
+        constexpr int ZI = (3 * R1 * 8 + NT - 1) / NT;
+        unsigned mbits[ZI];
+        if (DIEL == 1) {
+            PCB_UNROLL
+            for (int q = 0; q < ZI; ++q) {
+                const int item = tid + NT * q;
+                unsigned w = 0u;
+                const int i0 = t0 * 8 + item % 8;
+                if (item < 3 * R1 * 8 && i0 < N) {
+                    const int o1 = P::lout1((item / 8) % R1), cc = item / (8 * R1);
+                    const unsigned char* __restrict__ mp = op.mask + (long long)i1 * N + i0;
+                    PCB_UNROLL
+                    for (int k2 = 0; k2 < R2; ++k2) w |= ((unsigned)(__ldg(mp + P::wrap(o1 + P::lout2(k2)) * (N * N)) >> cc) & 1u) << k2;
+                }
+                mbits[q] = w;
+            }
+        }
         __syncthreads();
         cplx* __restrict__ st = sm + stage * STAGE;
         cplx* __restrict__ Y = cols.out[tile / tpc];
-        const int t0 = (tile % tpc) % NT0, i1 = (tile % tpc) / NT0;
 
         // forward radix R1 over n1 (fixed n2)
         for (int item = tid; item < 3 * R2 * 8; item += NT) {
@@ -489,27 +508,24 @@ __global__ void __launch_bounds__(NT, (NT > 256 ? 1 : 2)) k_zmid(PcbOp op, PcbCo
                 }
             }
         } else {
-            for (int item = tid; item < 3 * R1 * 8; item += NT) {
+            PCB_UNROLL
+            for (int q = 0; q < ZI; ++q) {
+                const int item = tid + NT * q;
+                if (item >= 3 * R1 * 8) break;
                 const int i0l = item % 8, k1 = (item / 8) % R1, c = item / (8 * R1);
                 const int i0 = t0 * 8 + i0l;
                 if (i0 >= N) continue;
-                const int b1 = P::lin1(k1), o1 = P::lout1(k1);
+                const int b1 = P::lin1(k1);
                 cplx* __restrict__ sc = st + c * N * 8 + i0l;
-                unsigned char mk[R2];
-                if (DIEL == 1) {
-                    const unsigned char* __restrict__ mp = op.mask + (long long)i1 * N + i0;
-                    PCB_UNROLL
-                    for (int k2 = 0; k2 < R2; ++k2) mk[k2] = __ldg(mp + P::wrap(o1 + P::lout2(k2)) * (N * N));
-                }
                 cplx v[R2];
                 PCB_UNROLL
                 for (int n2 = 0; n2 < R2; ++n2) v[n2] = sc[P::wrap(b1 + P::lin2(n2)) * 8];
                 Dft<R2, -1>::run(v);
                 if (DIEL == 1) {
                     const double scl = op.ediag[c];
+                    const unsigned w = mbits[q];
                     PCB_UNROLL
-                    for (int k2 = 0; k2 < R2; ++k2)
-                        if ((mk[k2] >> c) & 1u) v[k2] = cscale(v[k2], scl);
+                    for (int k2 = 0; k2 < R2; ++k2) v[k2] = cscale(v[k2], ((w >> k2) & 1u) ? scl : 1.0);   // branch-free
                 }
                 Dft<R2, +1>::run(v);
                 PCB_UNROLL
@@ -568,6 +584,25 @@ __global__ void __launch_bounds__(P::N / 8 * 32, 1) k_mid(PcbOp op, PcbCols cols
         // ---- load own rows (contiguous 8*N elements) ----
         for (int e = lane; e < 8 * N; e += 32) pcb_cp16(myrows + (e / N) * LD + e % N, base + e);
         pcb_cp_commit();
+        // dielectric bits this lane needs in the z step (items it = lane + 32 q: slot 8w + it%8, digit k1 = it/8), one word per
+        // item with bit k2 = "component c of point (i0, i1, i2 = lout(k1,k2)) lies in Omega_1": fetched now, so that the mask
+        // latency hides behind the row loads instead of stalling the middle of the z step
+        constexpr int ZI = (8 * R1 + 31) / 32;
+        unsigned mbits[ZI];
+        if (DIEL == 1) {
+            PCB_UNROLL
+            for (int q = 0; q < ZI; ++q) {
+                const int it = lane + 32 * q;
+                unsigned w = 0u;
+                if (it < 8 * R1) {
+                    const int i1 = P::coord(8 * warp + it % 8), o1 = P::lout1(it / 8);
+                    const unsigned char* __restrict__ mp = op.maskT + (long long)i0 * N * N + i1;
+                    PCB_UNROLL
+                    for (int k2 = 0; k2 < R2; ++k2) w |= ((unsigned)(__ldg(mp + P::wrap(o1 + P::lout2(k2)) * N) >> c) & 1u) << k2;
+                }
+                mbits[q] = w;
+            }
+        }
         pcb_cp_wait<0>();
         __syncwarp();
         // ---- forward y on own rows: lanes = (row fastest, digit) ----
@@ -614,25 +649,21 @@ __global__ void __launch_bounds__(P::N / 8 * 32, 1) k_mid(PcbOp op, PcbCols cols
             }
         }
         __syncwarp();
-        for (int it = lane; it < 8 * R1; it += 32) {
+        PCB_UNROLL
+        for (int q = 0; q < ZI; ++q) {
+            const int it = lane + 32 * q;
+            if (it >= 8 * R1) break;
             cplx* __restrict__ cp = mycols + it % 8;
-            const int k1 = it / 8, b1 = P::lin1(k1), o1 = P::lout1(k1);
-            unsigned char mk[R2];
-            if (DIEL == 1) {
-                const int i1 = P::coord(8 * warp + it % 8);     // real-space i1 of this slot after the forward y transform
-                const unsigned char* __restrict__ mp = op.maskT + (long long)i0 * N * N + i1;
-                PCB_UNROLL
-                for (int k2 = 0; k2 < R2; ++k2) mk[k2] = __ldg(mp + P::wrap(o1 + P::lout2(k2)) * N);
-            }
+            const int k1 = it / 8, b1 = P::lin1(k1);
             cplx v[R2];
             PCB_UNROLL
             for (int n2 = 0; n2 < R2; ++n2) v[n2] = cp[P::wrap(b1 + P::lin2(n2)) * LD];
             Dft<R2, -1>::run(v);
             if (DIEL == 1) {
                 const double scl = op.ediag[c];
+                const unsigned w = mbits[q];
                 PCB_UNROLL
-                for (int k2 = 0; k2 < R2; ++k2)
-                    if ((mk[k2] >> c) & 1u) v[k2] = cscale(v[k2], scl);
+                for (int k2 = 0; k2 < R2; ++k2) v[k2] = cscale(v[k2], ((w >> k2) & 1u) ? scl : 1.0);   // branch-free: no divergence
             }
             Dft<R2, +1>::run(v);
             PCB_UNROLL
