@@ -73,15 +73,6 @@ __global__ void k_mask_from_index(const long long* __restrict__ ind, long long n
     atomicOr(mask32 + (cell >> 2), (1u << c) << (8 * (int)(cell & 3)));
 }
 
-// maskT[(i0*N + i2)*N + i1] = mask[(i2*N + i1)*N + i0]  (plane mode reads the mask of one (i1,i2) plane contiguously)
-__global__ void k_mask_transpose(const unsigned char* __restrict__ mask, unsigned char* __restrict__ maskT, int N) {
-    const long long nn = (long long)N * N * N;
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nn) return;
-    const int i1 = (int)(t % N), i2 = (int)((t / N) % N), i0 = (int)(t / ((long long)N * N));
-    maskT[t] = mask[((long long)i2 * N + i1) * N + i0];
-}
-
 // ---- preconditioner symbol: inverse of K_P = K_A K_A^H + gamma K_B + shift I at one grid point --------
 // (inverse_3_times_3_B -> inverse_3_times_3_block, discretization.py:224-295, cofactor formulas)
 struct PcbPinv { double f11, f22, f33; cplx f12, f13, f23; };

@@ -91,7 +91,7 @@ struct pcb_diel {
     pcb_ctx* ctx;
     int kind;
     unsigned char* mask;    // [nn] (padded to 4)
-    unsigned char* maskT;   // [i0][i2][i1] copy for the plane mode (null when the size has no plane pass)
+    unsigned* mbits;        // plane mode: per-item dielectric bit words (k_mask_bits); null when the size has no plane pass
     double ediag[3];
     cplx eoff[3];
     PcbStencil st;
@@ -334,7 +334,7 @@ int pcb_diel_create(pcb_ctx* c, int kind, const int64_t* ind_e, long long n_e, c
     PCB_CHECK_ARG(out && kind >= PCB_DIEL_NONE && kind <= PCB_DIEL_CROSSDOF, "bad kind");
     PCB_CUDA_OK(cudaSetDevice(c->device));
     pcb_diel* d = new pcb_diel;
-    d->ctx = c; d->kind = kind; d->mask = nullptr; d->maskT = nullptr;
+    d->ctx = c; d->kind = kind; d->mask = nullptr; d->mbits = nullptr;
     for (int i = 0; i < 3; ++i) { d->ediag[i] = ediag ? ediag[i] : 1.0; d->eoff[i] = eoff ? cmake(eoff[2 * i], eoff[2 * i + 1]) : cmake(0.0, 0.0); }
     d->st.k = 1; for (int i = 0; i < 8; ++i) d->st.w[i] = 0.0;
     if (kind == PCB_DIEL_CROSSDOF) {
@@ -361,10 +361,13 @@ int pcb_diel_create(pcb_ctx* c, int kind, const int64_t* ind_e, long long n_e, c
         PCB_CUDA_OK(cudaFree(dind));
     }
     if (c->plan->plane_mode) {
-        PCB_CUDA_OK(cudaMalloc(&d->maskT, mbytes));
-        PCB_LAUNCH(k_mask_transpose, dim3((unsigned)((c->nn + 255) / 256), 1, 1), dim3(256, 1, 1), 0, c->stream,
-                   (const unsigned char*)d->mask, d->maskT, c->N);
-        PCB_CUDA_OK(cudaGetLastError());
+        PCB_CUDA_OK(cudaMalloc(&d->mbits, sizeof(unsigned) * 3 * (size_t)c->N * c->N * c->plan->r1));
+        PcbOp tmp;
+        memset(&tmp, 0, sizeof tmp);
+        tmp.N = c->N; tmp.nn = c->nn; tmp.nloc = c->nloc; tmp.mask = d->mask; tmp.mbits = d->mbits;
+        PcbCols none;
+        memset(&none, 0, sizeof none);
+        if (c->plan->pass(tmp, none, 1, PCB_PASS_MASKBITS, c->tw, c->stream, c->sms)) return -1;
         c->launches++;
     }
     PCB_CUDA_OK(cudaStreamSynchronize(c->stream));
@@ -376,7 +379,7 @@ void pcb_diel_destroy(pcb_diel* d) {
     cudaSetDevice(d->ctx->device);
     cudaStreamSynchronize(d->ctx->stream);
     if (d->mask) cudaFree(d->mask);
-    if (d->maskT) cudaFree(d->maskT);
+    if (d->mbits) cudaFree(d->mbits);
     delete d;
 }
 
@@ -389,7 +392,7 @@ static void op_fill(pcb_op* o, double gamma, double shift, double pshift, pcb_di
     o->d.inv_n3 = 1.0 / (double)c->nn;
     o->d.diel = diel ? diel->kind : PCB_DIEL_NONE;
     o->d.mask = diel ? diel->mask : nullptr;
-    o->d.maskT = diel ? diel->maskT : nullptr;
+    o->d.mbits = diel ? diel->mbits : nullptr;
     for (int i = 0; i < 3; ++i) {
         o->d.ediag[i] = diel ? diel->ediag[i] : 1.0;
         o->d.eoff[i] = diel ? diel->eoff[i] : cmake(0.0, 0.0);

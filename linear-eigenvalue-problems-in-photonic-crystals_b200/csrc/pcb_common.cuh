@@ -100,7 +100,7 @@ struct PcbOp {
     double inv_n3;            // 1 / N^3 (normalisation of the inverse transform)
     int diel;                 // PCB_DIEL_*
     const unsigned char* mask;  // [nn] bit c: edge DoF of component c in Omega_1; bit 3: volume DoF
-    const unsigned char* maskT; // the same bytes transposed to [i0][i2][i1] (plane mode)
+    const unsigned* mbits;      // plane mode: [c][i0][slot][k1] words, bit k2 = component c of (i0, i1 = coord(slot), i2 = lout(k1,k2)) in Omega_1
     double ediag[3];          // diagonal entries inside Omega_1 (chiral: 1/eps for all three)
     cplx eoff[3];             // eps_12, eps_13, eps_23 (trivial / crossdof)
 };

@@ -557,6 +557,24 @@ __global__ void __launch_bounds__(NT, (NT > 256 ? 1 : 2)) k_zmid(PcbOp op, PcbCo
     }
 }
 
+// Plane mode set-up (once per dielectric): mbits[c][i0][slot][k1], bit k2 = "component c of grid point
+// (i0, i1 = coord(slot), i2 = lout(k1, k2)) lies in Omega_1" -- exactly the 15 (R2) flags one radix-R2 item of k_mid needs.
+template <class P>
+__global__ void k_mask_bits(PcbOp op, unsigned* __restrict__ out) {
+    constexpr int N = P::N, R1 = P::R1, R2 = P::R2;
+    const long long total = 3LL * N * N * R1;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int k1 = (int)(t % R1), slot = (int)((t / R1) % N), i0 = (int)((t / ((long long)R1 * N)) % N), c = (int)(t / ((long long)R1 * N * N));
+    const int i1 = P::coord(slot), o1 = P::lout1(k1);
+    unsigned w = 0u;
+    for (int k2 = 0; k2 < R2; ++k2) {
+        const int i2 = P::wrap(o1 + P::lout2(k2));
+        w |= ((unsigned)(op.mask[((long long)i2 * N + i1) * N + i0] >> c) & 1u) << k2;
+    }
+    out[t] = w;
+}
+
 // ---------------------------------------------------------------------------------------
 // Plane mode, pass 2 of 3: forward y, forward z, M, inverse z, inverse y on one (i1, i2) plane held in shared memory.
 // The x pass wrote the transposed layout W'[c][i0][i2][i1], so the plane of (c, i0) is one contiguous chunk of N^2 elements;
@@ -584,23 +602,15 @@ __global__ void __launch_bounds__(P::N / 8 * 32, 1) k_mid(PcbOp op, PcbCols cols
         // ---- load own rows (contiguous 8*N elements) ----
         for (int e = lane; e < 8 * N; e += 32) pcb_cp16(myrows + (e / N) * LD + e % N, base + e);
         pcb_cp_commit();
-        // dielectric bits this lane needs in the z step (items it = lane + 32 q: slot 8w + it%8, digit k1 = it/8), one word per
-        // item with bit k2 = "component c of point (i0, i1, i2 = lout(k1,k2)) lies in Omega_1": fetched now, so that the mask
-        // latency hides behind the row loads instead of stalling the middle of the z step
+        // dielectric bits this lane needs in the z step (items it = lane + 32 q: slot 8w + it%8, digit k1 = it/8): one precomputed
+        // word per item (k_mask_bits), fetched now so that its latency hides behind the row loads
         constexpr int ZI = (8 * R1 + 31) / 32;
         unsigned mbits[ZI];
         if (DIEL == 1) {
             PCB_UNROLL
             for (int q = 0; q < ZI; ++q) {
                 const int it = lane + 32 * q;
-                unsigned w = 0u;
-                if (it < 8 * R1) {
-                    const int i1 = P::coord(8 * warp + it % 8), o1 = P::lout1(it / 8);
-                    const unsigned char* __restrict__ mp = op.maskT + (long long)i0 * N * N + i1;
-                    PCB_UNROLL
-                    for (int k2 = 0; k2 < R2; ++k2) w |= ((unsigned)(__ldg(mp + P::wrap(o1 + P::lout2(k2)) * N) >> c) & 1u) << k2;
-                }
-                mbits[q] = w;
+                mbits[q] = (it < 8 * R1) ? __ldg(op.mbits + (((long long)c * N + i0) * N + 8 * warp + it % 8) * R1 + it / 8) : 0u;
             }
         }
         pcb_cp_wait<0>();
@@ -732,6 +742,7 @@ struct PcbOpLaunch {
 enum { PCB_PASS_XFWD_SYM = 0, PCB_PASS_XFWD = 1, PCB_PASS_YFWD = 2, PCB_PASS_ZFWD = 3, PCB_PASS_ZINV = 4,
        PCB_PASS_YINV = 5, PCB_PASS_XINV = 6, PCB_PASS_XINV_A = 7, PCB_PASS_XINV_H = 8, PCB_PASS_ZMID = 9,
        // plane mode (three passes, transposed scratch columns in cols.wrk)
-       PCB_PASS_XFWD_SYM_T = 10, PCB_PASS_MID = 11, PCB_PASS_XINV_A_T = 12, PCB_PASS_XINV_H_T = 13 };
+       PCB_PASS_XFWD_SYM_T = 10, PCB_PASS_MID = 11, PCB_PASS_XINV_A_T = 12, PCB_PASS_XINV_H_T = 13,
+       PCB_PASS_MASKBITS = 14 /* set-up: op.mask -> (unsigned*)op.mbits */ };
 
 const PcbOpLaunch* pcb_find_plan(int N);
