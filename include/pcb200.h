@@ -108,7 +108,9 @@ int pcb_apply_timed(pcb_op* op, int mode, int ncols, const void* const* in, void
 
 /* LOBPCG block kernels
  * pcb_residual: r_j = lambda_j x_j - hx_j (lobpcg.py:394-395); norms2[j] = ||r_j||^2 (environment.norms :131-143);
- *   precond = 0: w_j = r_j;  1: w_j = K_P^-1 r_j (p_func fused, lobpcg.py:442).  norms2 is HOST memory. */
+ *   precond = 0: w_j = r_j;  1: w_j = K_P^-1 r_j (p_func fused, lobpcg.py:442);  2: w_j = K_P^-1 c64(r_j) and
+ *   3: w_j = c64(r_j), the residual rounded to complex64 and widened again -- the single-precision hand-over to the
+ *   preconditioner of lobpcg_sep_softlock_mixedprecision (lobpcg.py:574-577).  norms2 (always of the unrounded r_j) is HOST memory. */
 int pcb_residual(pcb_op* op, int precond, int ncols, const void* const* x, const void* const* hx, void* const* w,
                  const double* lambda, double* norms2);
 /* G = S^H S, T = S^H HS, both hermitized (orthogonalization.py:26-33,143-144); n x n row-major complex128 on the HOST.

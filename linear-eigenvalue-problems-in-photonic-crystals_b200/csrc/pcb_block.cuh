@@ -114,7 +114,9 @@ struct PcbResidArgs {
 
 // MODE 0: W = lambda X - HX (no preconditioner);  1: W = K_P^-1 (lambda X - HX);  2: W = K_P^-1 X (P_func alone)
 // partial[(blockIdx.x * ncols) + j] = sum over this CTA's points of |r_j|^2  (raw residual, before K_P^-1)
-template <int MODE>
+// RND: the residual is rounded to complex64 and widened again before K_P^-1 -- the `.astype(complex64)` hand-over of
+// lobpcg_sep_softlock_mixedprecision (lobpcg.py:574-577); the norms are those of the unrounded residual (:544-545).
+template <int MODE, bool RND = false>
 __global__ void __launch_bounds__(256) k_resid_precond(PcbOp op, PcbResidArgs a, int ncols, double* __restrict__ partial) {
     __shared__ double red[8][PCB_RP_CH];
     const int N = op.N;
@@ -145,6 +147,10 @@ __global__ void __launch_bounds__(256) k_resid_precond(PcbOp op, PcbResidArgs a,
                     }
                 }
                 acc[j] += cabs2(r[0]) + cabs2(r[1]) + cabs2(r[2]);
+                if (RND) {
+                    PCB_UNROLL
+                    for (int c = 0; c < 3; ++c) r[c] = cmake((double)(float)r[c].x, (double)(float)r[c].y);
+                }
                 if (MODE) pcb_pinv_apply(f, r, w);
                 else { w[0] = r[0]; w[1] = r[1]; w[2] = r[2]; }
                 PCB_UNROLL

@@ -623,7 +623,7 @@ int pcb_apply_host(pcb_op* o, int mode, int k, const void* x_host, long long ldx
 // ---- block kernels ----------------------------------------------------------------------------------------------
 int pcb_residual(pcb_op* o, int precond, int ncols, const void* const* x, const void* const* hx, void* const* w,
                  const double* lambda, double* norms2) {
-    PCB_CHECK_ARG(o && x && hx && w && lambda && norms2 && ncols > 0, "bad arguments");
+    PCB_CHECK_ARG(o && x && hx && w && lambda && norms2 && ncols > 0 && precond >= 0 && precond <= 3, "bad arguments");
     pcb_ctx* c = o->ctx;
     PCB_CUDA_OK(cudaSetDevice(c->device));
     const int gx = grid_for(c, c->nloc, 256, 4);
@@ -636,7 +636,9 @@ int pcb_residual(pcb_op* o, int precond, int ncols, const void* const* x, const 
             a.x[j] = (const cplx*)x[j0 + j]; a.hx[j] = (const cplx*)hx[j0 + j]; a.w[j] = (cplx*)w[j0 + j]; a.lambda[j] = lambda[j0 + j];
         }
         dim3 grid((unsigned)gx, (unsigned)((kc + PCB_RP_CH - 1) / PCB_RP_CH), 1);
-        if (precond) PCB_LAUNCH(k_resid_precond<1>, grid, dim3(256, 1, 1), 0, c->stream, o->d, a, kc, c->partial);
+        if (precond == 1) PCB_LAUNCH(k_resid_precond<1>, grid, dim3(256, 1, 1), 0, c->stream, o->d, a, kc, c->partial);
+        else if (precond == 2) PCB_LAUNCH((k_resid_precond<1, true>), grid, dim3(256, 1, 1), 0, c->stream, o->d, a, kc, c->partial);
+        else if (precond == 3) PCB_LAUNCH((k_resid_precond<0, true>), grid, dim3(256, 1, 1), 0, c->stream, o->d, a, kc, c->partial);
         else PCB_LAUNCH(k_resid_precond<0>, grid, dim3(256, 1, 1), 0, c->stream, o->d, a, kc, c->partial);
         PCB_CUDA_OK(cudaGetLastError());
         double* dout = c->partial + (size_t)gx * PCB_MAXC_RP;

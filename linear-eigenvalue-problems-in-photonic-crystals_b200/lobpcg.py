@@ -62,7 +62,7 @@ GRAM_REFRESH = 8
 
 def lobpcg_sep_softlock(h_func_in, p_func, x0, nev, shift=0.0, tol=TOL, maxiter=MAXITER, history=False,
                         longortho=False, singleprecision=False, maxstagniter=50, trace=None, _lock=True,
-                        incremental_gram=None):
+                        incremental_gram=None, _mixed=False):
     """LOBPCG with soft locking; [X, W, P] and their images live in two 3m-column device blocks.
 
     Returns ``(lambdas[:m] - shift, x, info)`` with ``x`` a DeviceBlock (R x m), ``info = [iterations,
@@ -96,12 +96,16 @@ def lobpcg_sep_softlock(h_func_in, p_func, x0, nev, shift=0.0, tol=TOL, maxiter=
         op.apply_into(L.APPLY_H, X, HX)
     else:
         _call_into(h_func, X, HX)
-    # Initial lambda (lobpcg.py:379-381): the m x m Gram matrices are themselves fed to RR.
     ss, shs = gram_pair(X, HX)
-    try:
-        lambdas, _ = rr_small(hermitize(ss.conj().T @ ss), hermitize(ss.conj().T @ shs))
-    except np.linalg.LinAlgError:
-        return None, None, None
+    if _mixed:
+        # mixed-precision variant: plain eigenvalues of herm(X^H HX) (lobpcg.py:524)
+        lambdas = np.linalg.eigvalsh(shs)
+    else:
+        # Initial lambda (lobpcg.py:379-381): the m x m Gram matrices are themselves fed to RR.
+        try:
+            lambdas, _ = rr_small(hermitize(ss.conj().T @ ss), hermitize(ss.conj().T @ shs))
+        except np.linalg.LinAlgError:
+            return None, None, None
     res_his = np.empty(maxiter)
     ctx.sync()
     say(f"Time for LOBPCG initialization: {time.time() - t_h:<6.2f}s.")
@@ -114,7 +118,7 @@ def lobpcg_sep_softlock(h_func_in, p_func, x0, nev, shift=0.0, tol=TOL, maxiter=
     for iter_ in range(maxiter):
         t_iter_h = time.time()
         # residual (+ preconditioner on the fused path), norms, active set
-        res_nrms = res_op.residual(X, HX, W, lambdas[:m], precond=op is not None)
+        res_nrms = res_op.residual(X, HX, W, lambdas[:m], precond=op is not None, single=_mixed)
         res_his[iter_] = np.linalg.norm(res_nrms[:nev])
         ind_act = np.where(res_nrms > tol)[0] if _lock else np.arange(m)
         n_act = len(ind_act)
@@ -123,8 +127,8 @@ def lobpcg_sep_softlock(h_func_in, p_func, x0, nev, shift=0.0, tol=TOL, maxiter=
         say(f"Iter = {iter_:<4d}, res_nrm = {np.linalg.norm(res_nrms):<6.2e}, n_act = {n_act:<3d}.", end=" ")
         if np.isnan(res_nrms).any():
             say(f"{RED}Nan occurs in residuals.{RESET}")
-            if not _lock:
-                raise ValueError(f"{RED}Nan occurs in residuals.{RESET}")      # lobpcg_sep_nolock raises (lobpcg.py:139-140)
+            if not _lock or _mixed:
+                raise ValueError(f"{RED}Nan occurs in residuals.{RESET}")      # lobpcg_sep_nolock raises (lobpcg.py:139-140,549)
             return None, None, None
         if (iter_ > maxstagniter and (res_nrms[0] > 1000 or res_nrms[0] > res_his[1])) or \
                 (iter_ > 2 * maxstagniter and res_nrms[0] > 50):
@@ -205,6 +209,22 @@ def lobpcg_sep_softlock(h_func_in, p_func, x0, nev, shift=0.0, tol=TOL, maxiter=
         info = np.append(info, res_his[1:iter_])
     x = X.copy()      # detach the result from the 3m-column work block
     return lambdas[:m] - shift, x, info
+
+
+def lobpcg_sep_softlock_mixedprecision(h_func, p_func, x0, nev, tol=TOL, maxiter=MAXITER, history=False, longortho=False,
+                                       trace=None):
+    """Soft-locking LOBPCG whose preconditioner input is handed over in single precision (lobpcg.py:494-629): the residual
+    block is rounded to complex64 (and widened again) before K_P^-1 -- fused into pcb_residual (precond = 2) -- while H,
+    the Gram pair, Rayleigh-Ritz and the update stay complex128.  Differences from ``lobpcg_sep_softlock`` kept from the
+    reference: initial lambda = eigvalsh(herm(X^H HX)) (:524), no stagnation rules, NaN residuals raise ValueError (:549),
+    no shift argument, and the return value is ``(lambdas[:nev], x[:, :nev], info)`` (:629)."""
+    if longortho:
+        raise NotImplementedError("longortho (rayleigh_ritz_qr_sep) is outside the ported hot path")
+    lam, x, info = lobpcg_sep_softlock(h_func, p_func, x0, nev, shift=0.0, tol=tol, maxiter=maxiter, history=history,
+                                       maxstagniter=10 ** 9, trace=trace, _mixed=True)
+    if lam is None:
+        raise ValueError("Rayleigh-Ritz failed in lobpcg_sep_softlock_mixedprecision")
+    return lam[:nev], x[:, :nev], info
 
 
 def lobpcg_sep_nolock(h_func, p_func, x0, nev, tol=TOL, maxiter=MAXITER, history=False, longortho=False,

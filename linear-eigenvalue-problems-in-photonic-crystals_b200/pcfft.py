@@ -88,12 +88,13 @@ class Operator:
         L.check(self._lib.pcb_apply_host(self.h, mode, k, x.ctypes.data, k, y2.ctypes.data, k), "pcb_apply_host")
         return y.reshape(-1) if (vec and out is None) else y
 
-    def residual(self, x, hx, w, lambdas, precond=True):
-        """w_j = [K_P^-1] (lambda_j x_j - hx_j); returns ||lambda_j x_j - hx_j||_2 (lobpcg.py:394-397,442)."""
+    def residual(self, x, hx, w, lambdas, precond=True, single=False):
+        """w_j = [K_P^-1] (lambda_j x_j - hx_j); returns ||lambda_j x_j - hx_j||_2 (lobpcg.py:394-397,442).
+        ``single``: the residual is rounded to complex64 before the preconditioner (lobpcg.py:574-577)."""
         k = x.k
         lam = np.ascontiguousarray(lambdas, dtype=np.float64)
         out = np.empty(k, dtype=np.float64)
-        L.check(self._lib.pcb_residual(self.h, 1 if precond else 0, k, L.ptr_array(x.ptrs), L.ptr_array(hx.ptrs),
+        L.check(self._lib.pcb_residual(self.h, (2 if precond else 3) if single else (1 if precond else 0), k, L.ptr_array(x.ptrs), L.ptr_array(hx.ptrs),
                                        L.ptr_array(w.ptrs), lam.ctypes.data_as(L.c_double_p),
                                        out.ctypes.data_as(L.c_double_p)), "pcb_residual")
         return np.sqrt(out)

@@ -574,6 +574,61 @@ def lobpcg_sep_softlock(h_func_in, p_func, x0, nev, shift=0.0, tol=TOL, maxiter=
     return lambdas[:m] - shift, s[:, :m], info
 
 
+def lobpcg_sep_softlock_mixedprecision(h_func, p_func, x0, nev, tol=TOL, maxiter=MAXITER, history=False, trace=None):
+    """Soft-locking LOBPCG with the preconditioner input rounded to complex64 (lobpcg.py:494-629).
+
+    Same iteration as ``lobpcg_sep_softlock`` except: initial lambda = eigvalsh(herm(X^H HX)) (:524), no stagnation
+    rules, NaN residuals raise (:549), ``p_func`` receives ``W.astype(complex64)`` and its result is widened again
+    (:574-577), and the return value is ``(lambdas[:nev], s[:, :nev], info)`` (:629)."""
+    m = x0.shape[1]
+    R = x0.shape[0]
+    res_his = np.empty(maxiter)
+    s = np.empty((R, 3 * m), dtype=np.complex128)
+    hs = np.empty((R, 3 * m), dtype=np.complex128)
+    s[:, :m] = x0
+    hs[:, :m] = h_func(s[:, :m])
+    lambdas = np.linalg.eigvalsh(hermitize(s[:, :m].conj().T @ hs[:, :m]))
+    t0 = time.time()
+    it = 0
+    for it in range(maxiter):
+        s[:, m:2 * m] = s[:, :m] * lambdas - hs[:, :m]
+        res = column_norms(s[:, m:2 * m])
+        res_his[it] = np.linalg.norm(res[:nev])
+        if np.isnan(res).any():
+            raise ValueError("Nan occurs in residuals.")
+        act = np.where(res > tol)[0]
+        n_act = len(act)
+        if trace is not None:
+            trace.append({"res": res.copy(), "n_act": n_act, "lambdas": np.array(lambdas[:m])})
+        n_loc = m + 2 * n_act if it > 0 else m + n_act
+        if max(res[:nev]) < tol:
+            break
+        if n_act < m:
+            for i0 in range(n_act):
+                s[:, m + i0] = s[:, m + act[i0]]
+            for i0 in range(n_act):
+                s[:, m + n_act + i0] = s[:, 2 * m + act[i0]]
+                hs[:, m + n_act + i0] = hs[:, 2 * m + act[i0]]
+        s[:, m:m + n_act] = np.asarray(p_func(s[:, m:m + n_act].astype(np.complex64))).astype(np.complex128)
+        hs[:, m:m + n_act] = h_func(s[:, m:m + n_act])
+        lambdas, E = rayleigh_ritz_chol_sep(s[:, :n_loc], hs[:, :n_loc])
+        lambdas, E = lambdas[:m], E[:, :m]
+        if it > 0:
+            pn = s[:, m + n_act:n_loc] @ E[m + n_act:] + s[:, m:m + n_act] @ E[m:m + n_act]
+            hpn = hs[:, m + n_act:n_loc] @ E[m + n_act:] + hs[:, m:m + n_act] @ E[m:m + n_act]
+        else:
+            pn = s[:, m:m + n_act] @ E[m:]
+            hpn = hs[:, m:m + n_act] @ E[m:]
+        s[:, 2 * m:] = pn
+        hs[:, 2 * m:] = hpn
+        s[:, :m] = s[:, :m] @ E[:m] + pn
+        hs[:, :m] = hs[:, :m] @ E[:m] + hpn
+    info = np.array([it, time.time() - t0])
+    if history:
+        info = np.append(info, res_his[1:it])
+    return lambdas[:nev], s[:, :nev], info
+
+
 # ---------------------------------------------------------------------------
 # Post-processing  (numerical_experiments.py:87-158)
 # ---------------------------------------------------------------------------

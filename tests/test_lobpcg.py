@@ -102,3 +102,79 @@ def test_nolock_variant_and_error_paths(pcb, oracle):
         H.op.apply_into(pcb._lib.APPLY_H, X, X)
     with pytest.raises(pcb.PcbError):
         pcb.devarray.Context(7)            # no FFT plan for N = 7
+
+
+def _mixed_golden():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "mixedprecision_golden.json")) as f:
+        return json.load(f)["cases"]
+
+
+def test_oracle_mixedprecision_vs_reference_golden(oracle):
+    """The oracle's restatement of lobpcg_sep_softlock_mixedprecision (lobpcg.py:494-629) against the reference run."""
+    case = _mixed_golden()[0]
+    N, d, alpha, nev = case["N"], case["d_flag"], np.array(case["alpha"]), case["nev"]
+    a, b, inv, shift, _ = oracle.assemble_symbols(N, d, alpha)
+    diel = getattr(oracle, case["type"] + "_handle")(N, d, eps_opt=case["eps_opt"])
+    _, H, P = oracle.pc_mfd_handle(a, b, diel, inv, shift)
+    lam, x, info = oracle.lobpcg_sep_softlock_mixedprecision(H, P, oracle.random_x0(3 * N ** 3, case["m"], case["seed"]), nev,
+                                                             history=True)
+    assert lam.shape == (nev,) and x.shape == (3 * N ** 3, nev)
+    assert int(info[0]) == case["iters"]
+    assert np.max(np.abs(lam - case["lambdas"]) / np.abs(case["lambdas"])) < EIG_RTOL
+    assert np.allclose(info[2:], case["res_his"], rtol=2e-3, atol=0)
+
+
+def test_mixedprecision_vs_reference_golden(pcb, oracle):
+    """lobpcg_sep_softlock_mixedprecision: the complex64 hand-over to the preconditioner is fused into pcb_residual
+    (precond = 2); same eigenvalues (1e-10), iteration counts and residual histories as the reference run."""
+    ran = 0
+    for case in _mixed_golden():
+        if pcb.backend_name == "emu" and case["N"] > 8:
+            continue
+        if pcb.backend_name == "emu" and ran >= 1:
+            continue
+        c = dict(case, tol=1e-4)
+        N, d_flag, alpha, typ, nev = c["N"], c["d_flag"], np.array(c["alpha"]), c["type"], c["nev"]
+        ne, mfd = pcb.numerical_experiments, pcb.discretization
+        relax, pnt = mfd.set_relaxation(alpha)
+        a_fft, b_fft = mfd.fft_blocks(N, 1, pcb.dielectric.diel_info(d_flag, option="ct"), alpha=alpha)
+        inv_fft = mfd.inverse_3_times_3_B(b_fft, pnt, relax[0])
+        Diels = getattr(mfd, typ + "_handle")(N, d_flag, eps_opt=c["eps_opt"])
+        A, H, P = ne.pc_mfd_handle(a_fft, (pnt * b_fft[0], pnt * b_fft[1]), Diels, inv_fft, relax[0])
+        x0 = oracle.random_x0(3 * N ** 3, c["m"], c["seed"])
+        lam, x, info = pcb.lobpcg.lobpcg_sep_softlock_mixedprecision(H, P, x0, nev, history=True)
+        assert lam.shape == (nev,) and x.shape == (3 * N ** 3, nev)
+        ref = np.array(c["lambdas"])
+        assert np.max(np.abs(lam - ref) / np.abs(ref)) < EIG_RTOL, c["d_flag"]
+        assert int(info[0]) == c["iters"], (c["d_flag"], info[0], c["iters"])
+        assert np.allclose(info[2:], c["res_his"], rtol=5e-3, atol=0), c["d_flag"]
+        hx = H(x).get()
+        res = np.linalg.norm(hx - x.get() * lam, axis=0)
+        assert np.all(res < 1e-4), c["d_flag"]
+        ran += 1
+    assert ran > 0
+
+
+def test_residual_single_rounding(pcb, oracle):
+    """pcb_residual precond = 2 / 3: K_P^-1 applied to the complex64-rounded residual; norms of the unrounded one."""
+    N = 8
+    mfd, ne = pcb.discretization, pcb.numerical_experiments
+    alpha = np.array([np.pi, 0.3, 0.0])
+    relax, pnt = mfd.set_relaxation(alpha)
+    a_fft, b_fft = mfd.fft_blocks(N, 1, pcb.dielectric.diel_info("sc_curv", option="ct"), alpha=alpha)
+    inv_fft = mfd.inverse_3_times_3_B(b_fft, pnt, relax[0])
+    A, H, P = ne.pc_mfd_handle(a_fft, (pnt * b_fft[0], pnt * b_fft[1]), None, inv_fft, relax[0])
+    ctx = H.op.ctx
+    x, hx = oracle.random_x0(3 * N ** 3, 3, 5), oracle.random_x0(3 * N ** 3, 3, 6)
+    lam = np.array([0.7, -1.3, 2.1])
+    X, HX, W = ctx.from_host(x), ctx.from_host(hx), ctx.from_host(np.zeros_like(x))
+    r = x * lam - hx
+    r32 = r.astype(np.complex64).astype(np.complex128)
+    oa, ob, oi, _, _ = oracle.assemble_symbols(N, "sc_curv", alpha)
+    for precond, want in ((True, oracle.h_block(r32, oi)), (False, r32)):
+        nrm = H.op.residual(X, HX, W, lam, precond=precond, single=True)
+        assert relerr(nrm, np.linalg.norm(r, axis=0)) < 1e-13
+        assert relerr(W.get(), want) < 1e-13
+    assert relerr(r32, r) > 1e-9          # the rounding is really there
