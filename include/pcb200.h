@@ -119,7 +119,9 @@ int pcb_residual(pcb_op* op, int precond, int ncols, const void* const* x, const
 int pcb_gram2(pcb_ctx* ctx, int n, const void* const* s, const void* const* hs, void* G, void* T);
 /* Same, accumulating only the rows of the first `ntop` columns (rounded up to a multiple of 8): rows a < ntop of G and T (and,
  * by Hermitian completion, their columns) are valid, the rest is zero.  Used by the solver's incremental Gram update, where
- * only the new block W changes between iterations and the [X P] blocks follow from the previous Rayleigh-Ritz rotation. */
+ * only the new block W changes between iterations and the [X P] blocks follow from the previous Rayleigh-Ritz rotation.
+ * When ntop (rounded up) < n the rows of T are formed as (hs_a)^H s_b -- equal to s_a^H hs_b for the Hermitian H this
+ * is defined for -- so only the first ntop (rounded up to 8) columns of `hs` are read; the other entries of `hs` may be NULL. */
 int pcb_gram2_top(pcb_ctx* ctx, int n, int ntop, const void* const* s, const void* const* hs, void* G, void* T);
 /* _sep_update_after_rr (lobpcg.py:1248-1270): s/hs list the n_loc input columns [X(m) | W_act | P_act];
  * E is (n_loc x m) row-major complex128 on the host.  Pn = [W_act P_act] E[m:], X <- X E[:m] + Pn (in place), P <- Pn. */

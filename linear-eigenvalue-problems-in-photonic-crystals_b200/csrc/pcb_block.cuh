@@ -183,16 +183,18 @@ __global__ void k_sum_partials(const double* __restrict__ partial, int nblocks, 
 }
 
 // ---- Gram pair on the FP64 tensor pipe (DMMA m8n8k4) ------------------------------------------------------------
-// G = S^H S and T = S^H HS as REAL GEMMs over K = 2R (re/im interleaved, exactly the memory order of a complex column):
-//   Re G_ab = sum_k A[a][k] Bre[k][b],  A[a][2r] = Re s_ra, A[a][2r+1] = Im s_ra,  Bre = same layout for column b
-//   Im G_ab = sum_k A'[a][k] Bsw[k][b], A' = (Re s_ra, -Im s_ra),                   Bsw[2r] = Im s_rb, Bsw[2r+1] = Re s_rb
+// G = S^H S and T = S^H HS.  An entry conj(a) b = (ar br + ai bi) + i (ar bi - ai br) is formed from THREE real products
+// (the 3M scheme: 25 % fewer DMMAs than the four of the real-expanded form),
+//   P1 = sum ar br,  P2 = sum ai bi,  P3 = sum (ar - ai)(br + bi)   ->   Re = P1 + P2,  Im = P3 - P1 + P2,
+// each a real GEMM over the rows: one DMMA (8 x 8 x 4) covers 4 rows of an 8 x 8 column-tile pair.  The three partial sums
+// are all of size |a||b|, the same magnitude the four-product form accumulates, so the rounding error bound is unchanged.
 // Columns are grouped in tiles of 8; only tile pairs (ta <= tb) are accumulated (Hermitian completion in k_gram_finish).
-// Each warp owns up to PCB_GM_PPW tile pairs x {Re G, Im G, Re T, Im T} = 4 DMMAs per pair and k4-step (two rows);
-// a fragment is ONE double per lane, so shared-memory traffic per flop is ~4x lower than with per-thread register tiles.
-// Row tiles of PCB_GM_TR rows are staged [column][row] (+2 rows pad: conflict-free LDS.64) with double-buffered cp.async.
+// Each warp owns up to PPW tile pairs x {G, T} x {P1, P2, P3} = 6 DMMAs per pair and 4-row step; a lane fetches one complex
+// element per operand tile (LDS.128) and derives the third operand with one DADD.
+// Row tiles of PCB_GM_TR rows are staged [column][row] (+4 rows pad: conflict-free LDS.128) with double-buffered cp.async.
 #define PCB_GM_TR 32
-#define PCB_GM_LD (PCB_GM_TR + 2)
-#define PCB_GM_PPW 4
+#define PCB_GM_LD (PCB_GM_TR + 4)
+#define PCB_GM_PPW 2
 #define PCB_GM_MAXW 20
 
 PCB_HD void pcb_pair_from_index(int p, int nb, int& ia, int& ib) {   // row-major upper triangle incl. diagonal
@@ -201,29 +203,32 @@ PCB_HD void pcb_pair_from_index(int p, int nb, int& ia, int& ib) {   // row-majo
     ia = a; ib = a + rem;
 }
 
+// TSIDE (leading tile rows only, pcb_gram2_top): T_ab = conj(hs_a) s_b instead of conj(s_a) hs_b -- the same number for a
+// Hermitian H -- so that only the first `nh` columns of HS are read at all.
+template <int PPW, bool TSIDE>     // PPW tile pairs per warp (1 or 2): the accumulators are 12 PPW doubles per lane
 __global__ void __launch_bounds__(32 * PCB_GM_MAXW, 1)
-k_gram2(PcbColList S, PcbColList HS, int n, int nt, int npairs, long long R, cplx* __restrict__ partial /* [gridDim.x][2][nc*nc] */) {
+k_gram2(PcbColList S, PcbColList HS, int n, int nh, int nt, int pair0, int npairs, long long R, cplx* __restrict__ partial /* [gridDim.x][2][nc*nc] */) {
     PCB_DYN_SMEM(cplx, sm);                      // [2 stages][2: S, HS][nc][LD]
     const int nc = 8 * nt;
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int warp = tid >> 5, lane = tid & 31, W = nthr >> 5;
     const int g = lane >> 2, tig = lane & 3;
     const size_t matElems = (size_t)nc * PCB_GM_LD;
-    // tile pairs of this warp: the first `npairs` pairs of the row-major upper triangle (all of it, or only the leading tile rows)
+    // tile pairs of this warp: pairs [pair0, pair0 + npairs) of the row-major upper triangle
     const int base = npairs / W, extra = npairs % W;
     const int cnt = base + (warp < extra ? 1 : 0);
     const int p0 = warp * base + (warp < extra ? warp : extra);
-    int ta[PCB_GM_PPW], tb[PCB_GM_PPW];
+    int ta[PPW], tb[PPW];
     PCB_UNROLL
-    for (int i = 0; i < PCB_GM_PPW; ++i) {
+    for (int i = 0; i < PPW; ++i) {
         ta[i] = tb[i] = 0;
-        if (i < cnt) pcb_pair_from_index(p0 + i, nt, ta[i], tb[i]);
+        if (i < cnt) pcb_pair_from_index(pair0 + p0 + i, nt, ta[i], tb[i]);
     }
-    double acc[PCB_GM_PPW][4][2];
+    double acc[PPW][6][2];      // [pair][G: P1 P2 P3 | T: P1 P2 P3][c0, c1]
     PCB_UNROLL
-    for (int i = 0; i < PCB_GM_PPW; ++i) {
+    for (int i = 0; i < PPW; ++i) {
         PCB_UNROLL
-        for (int q = 0; q < 4; ++q) acc[i][q][0] = acc[i][q][1] = 0.0;
+        for (int q = 0; q < 6; ++q) acc[i][q][0] = acc[i][q][1] = 0.0;
     }
     // zero the padding columns (never loaded) of both stages
     for (int idx = tid; idx < 4 * (nc - n) * PCB_GM_LD; idx += nthr) {
@@ -239,7 +244,7 @@ k_gram2(PcbColList S, PcbColList HS, int n, int nt, int npairs, long long R, cpl
             const cplx* hp = HS.p[c];
             cplx* ds = d0 + (size_t)c * PCB_GM_LD;
             cplx* dh = ds + matElems;
-            if (sp != nullptr && r < R) { pcb_cp16(ds, sp + r); pcb_cp16(dh, hp + r); }
+            if (sp != nullptr && r < R) { pcb_cp16(ds, sp + r); if (!TSIDE || c < nh) pcb_cp16(dh, hp + r); }
             else { *ds = cmake(0.0, 0.0); *dh = cmake(0.0, 0.0); }
         }
         pcb_cp_commit();
@@ -251,23 +256,31 @@ k_gram2(PcbColList S, PcbColList HS, int n, int nt, int npairs, long long R, cpl
         const long long tn = t + gridDim.x;
         if (tn < ntiles) { load_tile(tn, stage ^ 1); pcb_cp_wait<1>(); } else { pcb_cp_wait<0>(); }
         __syncthreads();
-        const double* s0 = reinterpret_cast<const double*>(sm + (size_t)(stage * 2) * matElems);
-        const double* h0 = reinterpret_cast<const double*>(sm + (size_t)(stage * 2 + 1) * matElems);
+        const cplx* s0 = sm + (size_t)(stage * 2) * matElems;
+        const cplx* h0 = s0 + matElems;
         PCB_UNROLL
-        for (int i = 0; i < PCB_GM_PPW; ++i) {
+        for (int i = 0; i < PPW; ++i) {
             if (i < cnt) {
-                const double* pa = s0 + (size_t)(ta[i] * 8 + g) * (2 * PCB_GM_LD);
-                const double* pb = s0 + (size_t)(tb[i] * 8 + g) * (2 * PCB_GM_LD);
-                const double* ph = h0 + (size_t)(tb[i] * 8 + g) * (2 * PCB_GM_LD);
+                // A fragment: (column ta*8 + g, row 4 step + tig); B fragments: (row 4 step + tig, column tb*8 + g)
+                const cplx* pa = s0 + (size_t)(ta[i] * 8 + g) * PCB_GM_LD + tig;
+                const cplx* pb = s0 + (size_t)(tb[i] * 8 + g) * PCB_GM_LD + tig;
+                const cplx* ph = h0 + (size_t)((TSIDE ? ta[i] : tb[i]) * 8 + g) * PCB_GM_LD + tig;
                 PCB_UNROLL
-                for (int step = 0; step < PCB_GM_TR / 2; ++step) {
-                    const int o = 4 * step + tig, os = 4 * step + (tig ^ 1);
-                    const double a = pa[o];
-                    const double a2 = (tig & 1) ? -a : a;
-                    pcb_dmma(acc[i][0][0], acc[i][0][1], a, pb[o]);
-                    pcb_dmma(acc[i][1][0], acc[i][1][1], a2, pb[os]);
-                    pcb_dmma(acc[i][2][0], acc[i][2][1], a, ph[o]);
-                    pcb_dmma(acc[i][3][0], acc[i][3][1], a2, ph[os]);
+                for (int step = 0; step < PCB_GM_TR / 4; ++step) {
+                    const cplx a = pa[4 * step], b = pb[4 * step], h = ph[4 * step];
+                    const double am = a.x - a.y, bp = b.x + b.y;
+                    pcb_dmma(acc[i][0][0], acc[i][0][1], a.x, b.x);
+                    pcb_dmma(acc[i][1][0], acc[i][1][1], a.y, b.y);
+                    pcb_dmma(acc[i][2][0], acc[i][2][1], am, bp);
+                    if (TSIDE) {          // h is the A operand (column ta of HS)
+                        pcb_dmma(acc[i][3][0], acc[i][3][1], h.x, b.x);
+                        pcb_dmma(acc[i][4][0], acc[i][4][1], h.y, b.y);
+                        pcb_dmma(acc[i][5][0], acc[i][5][1], h.x - h.y, bp);
+                    } else {
+                        pcb_dmma(acc[i][3][0], acc[i][3][1], a.x, h.x);
+                        pcb_dmma(acc[i][4][0], acc[i][4][1], a.y, h.y);
+                        pcb_dmma(acc[i][5][0], acc[i][5][1], am, h.x + h.y);
+                    }
                 }
             }
         }
@@ -276,14 +289,14 @@ k_gram2(PcbColList S, PcbColList HS, int n, int nt, int npairs, long long R, cpl
     }
     cplx* out = partial + (size_t)blockIdx.x * 2 * nc * nc;
     PCB_UNROLL
-    for (int i = 0; i < PCB_GM_PPW; ++i) {
+    for (int i = 0; i < PPW; ++i) {
         if (i < cnt) {
             const int ra = ta[i] * 8 + g;
             PCB_UNROLL
             for (int j = 0; j < 2; ++j) {
                 const int cb = tb[i] * 8 + 2 * tig + j;
-                out[ra * nc + cb] = cmake(acc[i][0][j], acc[i][1][j]);
-                out[nc * nc + ra * nc + cb] = cmake(acc[i][2][j], acc[i][3][j]);
+                out[ra * nc + cb] = cmake(acc[i][0][j] + acc[i][1][j], (acc[i][2][j] - acc[i][0][j]) + acc[i][1][j]);
+                out[nc * nc + ra * nc + cb] = cmake(acc[i][3][j] + acc[i][4][j], (acc[i][5][j] - acc[i][3][j]) + acc[i][4][j]);
             }
         }
     }

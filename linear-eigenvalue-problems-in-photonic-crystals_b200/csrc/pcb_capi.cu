@@ -664,30 +664,53 @@ int pcb_gram2_top(pcb_ctx* c, int n, int ntop, const void* const* s, const void*
     PcbColList S, HS;
     for (int j = 0; j < PCB_MAXL; ++j) { S.p[j] = (j < n) ? (const cplx*)s[j] : nullptr; HS.p[j] = (j < n) ? (const cplx*)hs[j] : nullptr; }
     const int npairs = ttop * nt - ttop * (ttop - 1) / 2;  // pairs (ta < ttop, tb >= ta) = a prefix of the row-major upper triangle
-    int W = 4 * ((npairs + 4 * PCB_GM_PPW - 1) / (4 * PCB_GM_PPW));     // multiple of 4 warps, <= PPW tile pairs per warp
-    { const int w8 = 4 * ((npairs + 3) / 4); if (W < 8 && w8 > W) W = w8 < 8 ? w8 : 8; }   // few pairs: still 8 warps (2 CTAs/SM) for latency hiding
-    if (W > PCB_GM_MAXW) { pcb_set_error("pcb_gram2: n = %d needs %d warps", n, W); return -2; }
+    const bool tside = ttop < nt;                          // leading rows only: T = (HS_top)^H S, the other HS columns are not read
     const size_t smem = sizeof(cplx) * 4 * (size_t)nc * PCB_GM_LD;
     const long long ntiles = (c->R + PCB_GM_TR - 1) / PCB_GM_TR;
-    int per_sm = (int)((size_t)224 * 1024 / (smem + 1024)); if (per_sm < 1) per_sm = 1;
-    const int by_threads = 2048 / (32 * W); if (per_sm > by_threads) per_sm = by_threads;
-    if (per_sm > 4) per_sm = 4;
-    long long gx = (long long)c->sms * per_sm; if (gx > ntiles) gx = ntiles;
-    const size_t pbytes = sizeof(cplx) * (size_t)gx * 2 * nc * nc;
-    if (ensure_partial(c, pbytes)) return -1;
-    if (ensure_dsmall(c, sizeof(cplx) * 2 * PCB_MAXL * PCB_MAXL + 65536)) return -1;
-    if (ensure_hstage(c, sizeof(cplx) * 2 * PCB_MAXL * PCB_MAXL + 65536)) return -1;
+    // One launch covers at most PCB_GM_MAXW * PCB_GM_PPW tile pairs (n <= 64); wider blocks take several launches over equal
+    // shares of the pair list, all writing disjoint entries of the same per-CTA partial matrices (the kernel is DMMA-bound, so
+    // re-reading the columns costs little).  Warps per CTA: every warp gets the same number of pairs where possible (all warps
+    // meet at one barrier per row tile, the slowest one sets the pace), as many warps as that allows.
+    const int cap = PCB_GM_MAXW * PCB_GM_PPW;
+    const int nlaunch = (npairs + cap - 1) / cap, share = (npairs + nlaunch - 1) / nlaunch;
+    long long gx = 0;
+    for (int l = 0; l < nlaunch; ++l) {
+        const int pair0 = l * share, np = (npairs - pair0 < share) ? npairs - pair0 : share;
+        int W = 0;
+        for (int ppw = 1; ppw <= PCB_GM_PPW && W == 0; ++ppw) {
+            const int w = (np + ppw - 1) / ppw;                 // fewest warps with <= ppw pairs each
+            if (w <= PCB_GM_MAXW && ((w * ppw - np) * 8 <= np || ppw == PCB_GM_PPW)) W = w;   // <= 12.5 % idle pair slots
+        }
+        if (W < 4) W = 4;
+        { static const char* ev = getenv("PCB200_GRAM_W"); if (ev && atoi(ev) >= 4 && atoi(ev) <= PCB_GM_MAXW && (np + atoi(ev) - 1) / atoi(ev) <= PCB_GM_PPW) W = atoi(ev); }
+        const int ppw = (np + W - 1) / W;
+        void (*kern)(PcbColList, PcbColList, int, int, int, int, int, long long, cplx*) =
+            tside ? (ppw <= 1 ? k_gram2<1, true> : k_gram2<2, true>) : (ppw <= 1 ? k_gram2<1, false> : k_gram2<2, false>);
+        if (l == 0) {
+            int per_sm = (int)((size_t)224 * 1024 / (smem + 1024)); if (per_sm < 1) per_sm = 1;
+            const int by_threads = 2048 / (32 * W); if (per_sm > by_threads) per_sm = by_threads;
+            if (per_sm > 4) per_sm = 4;
 #ifndef PCB_EMU
-    if (smem > 48 * 1024) PCB_CUDA_OK(cudaFuncSetAttribute(k_gram2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (smem > 48 * 1024) PCB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            { int occ = 0; PCB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * W, smem)); if (occ >= 1 && occ < per_sm) per_sm = occ; }
 #endif
-    dim3 grid((unsigned)gx, 1, 1);
-    PCB_LAUNCH(k_gram2, grid, dim3(32 * W, 1, 1), smem, c->stream, S, HS, n, nt, npairs, c->R, (cplx*)c->partial);
-    PCB_CUDA_OK(cudaGetLastError());
+            gx = (long long)c->sms * per_sm; if (gx > ntiles) gx = ntiles;
+            if (ensure_partial(c, sizeof(cplx) * (size_t)gx * 2 * nc * nc)) return -1;
+            if (ensure_dsmall(c, sizeof(cplx) * 2 * PCB_MAXL * PCB_MAXL + 65536)) return -1;
+            if (ensure_hstage(c, sizeof(cplx) * 2 * PCB_MAXL * PCB_MAXL + 65536)) return -1;
+        }
+#ifndef PCB_EMU
+        else if (smem > 48 * 1024) PCB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#endif
+        PCB_LAUNCH(kern, dim3((unsigned)gx, 1, 1), dim3(32 * W, 1, 1), smem, c->stream, S, HS, n, 8 * ttop, nt, pair0, np, c->R, (cplx*)c->partial);
+        PCB_CUDA_OK(cudaGetLastError());
+        c->launches++;
+    }
     cplx* dout = (cplx*)c->dsmall;
     const int ne = 2 * nc * nc;
     PCB_LAUNCH(k_gram_finish, dim3((unsigned)((ne + 127) / 128), 1, 1), dim3(128, 1, 1), 0, c->stream, (const cplx*)c->partial, (int)gx, nt, ttop, dout);
     PCB_CUDA_OK(cudaGetLastError());
-    c->launches += 2;
+    c->launches += 1;
     if (comm_allreduce(c, (double*)dout, 2LL * ne)) return -1;      // large-grid mode: sum of the per-slab Gram pairs (NCCL)
     PCB_CUDA_OK(cudaMemcpyAsync(c->hstage, dout, sizeof(cplx) * ne, cudaMemcpyDeviceToHost, c->stream));
     PCB_CUDA_OK(cudaStreamSynchronize(c->stream));

@@ -13,7 +13,7 @@ def _blocks(pcb, N, k, seed):
     return ctx, a, ctx.from_host(a)
 
 
-@pytest.mark.parametrize("N,n", [(6, 5), (8, 16), (8, 24), (6, 48), (6, 33)])
+@pytest.mark.parametrize("N,n", [(6, 5), (8, 16), (8, 24), (6, 48), (6, 33), (6, 96)])
 def test_gram_pair(pcb, N, n):
     ctx, s, S = _blocks(pcb, N, n, 1)
     # HS = D S with a real diagonal D: like H S in LOBPCG, S^H HS is Hermitian (pcb_gram2 computes one triangle)
