@@ -329,6 +329,9 @@ __global__ void k_gram_finish(const cplx* __restrict__ partial, int nblocks, int
 // runs over the W/P part (-> Pn, stored to P/HP), then continues over the X part (-> X E_x + Pn, stored in place).
 // A CTA stages TR rows of all input columns of S and HS ([column][row], cp.async double buffer); warp (rt, jp) owns the
 // 8-row tile rt and the output column tiles {2jp, 2jp+1} (4 complex columns each) of both S and HS.
+// Measured alternatives (B200, N = 120, m = 16, n_loc = 48; this form: 2.77 ms = 4.8 TB/s): a third cp.async stage 2.81 ms (the
+// loads are not what it waits for); one of S / HS per stage with 64-row tiles 2.93 ms, with 32-row tiles 3.77 ms (E' fragments
+// are then fetched twice per row tile: the kernel is bound by shared-memory fragment traffic and DMMA issue, not by HBM).
 template <int TR>
 struct PcbUpd {
     static constexpr int LD = TR + 4;      // complex; LD*16 mod 128 == 64: the two k-columns of an A fragment hit disjoint banks
@@ -363,8 +366,8 @@ k_update(PcbColList Sin, PcbColList HSin, PcbColListW Xout, PcbColListW HXout, P
         const long long r = t * TR + rr;
         cplx* d0 = sT + (size_t)(stage * 2) * matElems + rr;
         for (int c = warp * CPW + sub; c < nl; c += W * CPW) {
-            const cplx* sp = Sin.p[c];
-            const cplx* hp = HSin.p[c];
+            const cplx* sp = c < PCB_MAXL ? Sin.p[c] : nullptr;      // columns past the list are zero padding
+            const cplx* hp = c < PCB_MAXL ? HSin.p[c] : nullptr;
             cplx* ds = d0 + (size_t)c * LD;
             cplx* dh = ds + matElems;
             if (sp != nullptr && r < R) { pcb_cp16(ds, sp + r); pcb_cp16(dh, hp + r); }
