@@ -95,8 +95,8 @@ class ShardedOperator:
         self.local = Operator(a_fft, gamma, shift, pshift, None, ctx=comm.slab)     # symbols only: residual + preconditioner
         self.gamma, self.shift, self.pshift = self.full.gamma, self.full.shift, self.full.pshift
 
-    def residual(self, x, hx, w, lambdas, precond=True):
-        return self.local.residual(x, hx, w, lambdas, precond=precond)
+    def residual(self, x, hx, w, lambdas, precond=True, single=False):
+        return self.local.residual(x, hx, w, lambdas, precond=precond, single=single)
 
     def apply_into(self, mode, src, dst):
         if src.k == 0:
