@@ -182,12 +182,16 @@ def bandgap(n, d_flag, solver=lobpcg_sep_softlock, type=TYPE0, eps_opt=0, indice
     """Band structure along the lattice's k-path, one warm-started LOBPCG solve per point, checkpointed to
     JSON after every point (numerical_experiments.py:313-496).  Returns the list of failed indices.
     `nev` (default NEV), `seed` (reproducible random starts) and `path` (output file) are additions."""
+    t_all = time.time()
+    timing = {"setup": 0.0, "assemble": 0.0, "solver": 0.0, "postprocess": 0.0, "checkpoint": 0.0}
+    bandgap.last_timing = timing          # wall seconds by phase (where a band-structure run spends its time)
     ct, sym_points = diel.diel_info(d_flag)
     alphas = diel.kpath(d_flag, GAP)
     n_k = alphas.shape[0]
     Diels = _handle(type, n, d_flag, eps_opt=eps_opt)
     ctx = Diels.ctx if Diels is not None else devarray.get_context(n)
     d_fft, _ = mfd.fft_blocks(n, K, ct)
+    timing["setup"] = time.time() - t_all
 
     path_bandgap = path or (OUTPUT_PATH + type + "/bandgap_" + d_flag + ".json")
     var_it, var_fq = f"{d_flag}_{n}_iterations", f"{d_flag}_{n}_frequencies"
@@ -229,14 +233,19 @@ def bandgap(n, d_flag, solver=lobpcg_sep_softlock, type=TYPE0, eps_opt=0, indice
         inv_fft = (inv_fft[0] * SCAL * SCAL, inv_fft[1] * SCAL * SCAL)
         A_func, H_func, P_func = pc_mfd_handle(a_fft, b_fft, Diels, inv_fft, relax_opt[0])
         say(f"Matrix blocks done, {owari() - t_h:<6.3f}s elapsed.")
+        timing["assemble"] += time.time() - t_h
         try:
+            t_s = time.time()
             lambdas_pnt, x, iters = solver(H_func, P_func, x0, nev, tol=tol)
+            timing["solver"] += time.time() - t_s
             if lambdas_pnt is None:
                 raise RuntimeError("solver returned None (NaN / blow-up)")
             say(f"Gap {idx + 1} out of {n_k} ({d_flag}),"
                 f"alpha = ({alpha[0] / pi:<6.3f}, {alpha[1] / pi:<6.3f}, {alpha[2] / pi:<6.3f})pi is computed.")
             say(f"Iterations = {int(iters[0])}, runtime = {iters[1]:<6.3f}s.\n")
+            t_s = time.time()
             _, lambdas_re = recompute_normalize_print(lambdas_pnt, x, A_func, relax_opt[0])
+            timing["postprocess"] += time.time() - t_s
             gap_rec_it[idx] = [float(v) for v in iters[:2]]
             gap_rec_fq[idx] = [float(v) for v in lambdas_re]
         except Exception as e:          # same policy as the reference: record [-1,-1], restart from random
@@ -251,12 +260,14 @@ def bandgap(n, d_flag, solver=lobpcg_sep_softlock, type=TYPE0, eps_opt=0, indice
         gap_lib[var_it], gap_lib[var_fq] = gap_rec_it, gap_rec_fq
         with open(path_bandgap, "w") as f:
             json.dump(gap_lib, f, indent=4)
+        timing["checkpoint"] += time.time() - t_h
         say(f"{CYAN}Gap info library ({d_flag}) is updated ({idx + 1}/{n_k}), time = {time.time() - t_h:<6.3f}s.{RESET}")
     if err_index:
         say(f"{RED}Error occurs to following indices:{RESET}")
         say(err_index)
     else:
         say(f"{GREEN}All indices computed correctly.{RESET}")
+    timing["total"] = time.time() - t_all
     return err_index
 
 

@@ -56,7 +56,8 @@ def main():
         print(json.dumps({"N": N, "lattice": d_flag, "type": typ, "nev": nev, "gpus": world, "k_points": len(indices),
                           "failed": int((~ok).sum()), "wall_s_incl_setup": wall, "sum_solver_s": float(its[ok, 1].sum()),
                           "mean_s_per_k": float(its[ok, 1].mean()), "mean_iterations": float(its[ok, 0].mean()),
-                          "std_iterations": float(its[ok, 0].std()), "json": final}), flush=True)
+                          "std_iterations": float(its[ok, 0].std()), "json": final,
+                          "rank0_phase_seconds": {k: round(v, 3) for k, v in getattr(ne.bandgap, "last_timing", {}).items()}}), flush=True)
     if world > 1:
         td.destroy_process_group()
 
