@@ -308,6 +308,9 @@ def main():
         nl = 3 * m
         blocks.append({"name": f"gram pair (n_loc={3 * m})", "ms": t, "GBps": 2 * nl * Rb / t / 1e6,
                        "GFLOPs": 8.0 * ctx.R * nl * (nl + 1) / t / 1e6})
+        t = timed(lambda: L.check(L.lib().pcb_gram2_top(ctx.h, nl, m, L.ptr_array(S.ptrs), L.ptr_array(HS.ptrs), G.ctypes.data, T.ctypes.data), "gram2_top"))
+        blocks.append({"name": f"gram pair, rows of W only (n_loc={nl}, n_act={m}; 7 of 8 iterations)", "ms": t,
+                       "GBps": (nl + m) * Rb / t / 1e6, "GFLOPs": 16.0 * ctx.R * m * nl / t / 1e6})
         E = np.ascontiguousarray(np.random.default_rng(0).standard_normal((nl, m)) + 0j) / nl
         t = timed(lambda: L.check(L.lib().pcb_update(ctx.h, m, nl, L.ptr_array(S.ptrs), L.ptr_array(HS.ptrs), L.ptr_array(S[:, 2 * m:].ptrs),
                                                      L.ptr_array(HS[:, 2 * m:].ptrs), E.ctypes.data), "update"))

@@ -26,6 +26,18 @@ from .orthogonalization import gram_pair, gram_pair_top, hermitize, rr_small
 from .pcfft import Operator, OperatorCallable
 
 
+def _small_blas_threads():
+    """Context manager: one BLAS thread while the solver runs.  Its host linear algebra is n_loc x n_loc (<= 96): OpenBLAS'
+    thread hand-off costs more than the products themselves (48 x 48: two matmuls 0.20 ms on 8 threads, 0.06 ms on one), and the
+    GPU idles meanwhile.  No-op without threadpoolctl."""
+    try:
+        from threadpoolctl import threadpool_limits
+        return threadpool_limits(limits=1, user_api="blas")
+    except Exception:
+        import contextlib
+        return contextlib.nullcontext()
+
+
 def _fused_operator(h_func_in, p_func, shift):
     """The Operator when (h_func, p_func) are the callables of pc_mfd_handle for one operator."""
     if (shift == 0.0 and isinstance(h_func_in, OperatorCallable) and isinstance(p_func, OperatorCallable)
@@ -63,6 +75,17 @@ GRAM_REFRESH = 8
 def lobpcg_sep_softlock(h_func_in, p_func, x0, nev, shift=0.0, tol=TOL, maxiter=MAXITER, history=False,
                         longortho=False, singleprecision=False, maxstagniter=50, trace=None, _lock=True,
                         incremental_gram=None, _mixed=False):
+    with _small_blas_threads():
+        return _lobpcg_sep_softlock(h_func_in, p_func, x0, nev, shift, tol, maxiter, history, longortho, singleprecision,
+                                    maxstagniter, trace, _lock, incremental_gram, _mixed)
+
+
+lobpcg_sep_softlock.__doc__ = """LOBPCG with soft locking (lobpcg.py:325-492); see _lobpcg_sep_softlock."""
+
+
+def _lobpcg_sep_softlock(h_func_in, p_func, x0, nev, shift=0.0, tol=TOL, maxiter=MAXITER, history=False,
+                         longortho=False, singleprecision=False, maxstagniter=50, trace=None, _lock=True,
+                         incremental_gram=None, _mixed=False):
     """LOBPCG with soft locking; [X, W, P] and their images live in two 3m-column device blocks.
 
     Returns ``(lambdas[:m] - shift, x, info)`` with ``x`` a DeviceBlock (R x m), ``info = [iterations,
