@@ -205,8 +205,10 @@ PCB_HD void pcb_pair_from_index(int p, int nb, int& ia, int& ib) {   // row-majo
 
 // TSIDE (leading tile rows only, pcb_gram2_top): T_ab = conj(hs_a) s_b instead of conj(s_a) hs_b -- the same number for a
 // Hermitian H -- so that only the first `nh` columns of HS are read at all.
-template <int PPW, bool TSIDE>     // PPW tile pairs per warp (1 or 2): the accumulators are 12 PPW doubles per lane
-__global__ void __launch_bounds__(32 * PCB_GM_MAXW, 1)
+// WMAX: most warps the instantiation is launched with; up to 12 warps two CTAs share an SM (register cap 80), which is what
+// keeps the DMMA pipe fed across the per-tile barriers (ncu: 1 CTA of 11 warps reaches 63 % of the DMMA peak).
+template <int PPW, bool TSIDE, int WMAX>     // PPW tile pairs per warp (1 or 2): the accumulators are 12 PPW doubles per lane
+__global__ void __launch_bounds__(32 * WMAX, WMAX <= 12 ? 2 : 1)
 k_gram2(PcbColList S, PcbColList HS, int n, int nh, int nt, int pair0, int npairs, long long R, cplx* __restrict__ partial /* [gridDim.x][2][nc*nc] */) {
     PCB_DYN_SMEM(cplx, sm);                      // [2 stages][2: S, HS][nc][LD]
     const int nc = 8 * nt;

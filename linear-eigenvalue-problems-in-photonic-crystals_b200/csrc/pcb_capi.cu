@@ -685,13 +685,16 @@ int pcb_gram2_top(pcb_ctx* c, int n, int ntop, const void* const* s, const void*
         { static const char* ev = getenv("PCB200_GRAM_W"); if (ev && atoi(ev) >= 4 && atoi(ev) <= PCB_GM_MAXW && (np + atoi(ev) - 1) / atoi(ev) <= PCB_GM_PPW) W = atoi(ev); }
         const int ppw = (np + W - 1) / W;
         void (*kern)(PcbColList, PcbColList, int, int, int, int, int, long long, cplx*) =
-            tside ? (ppw <= 1 ? k_gram2<1, true> : k_gram2<2, true>) : (ppw <= 1 ? k_gram2<1, false> : k_gram2<2, false>);
+            W <= 12 ? (tside ? (ppw <= 1 ? k_gram2<1, true, 12> : k_gram2<2, true, 12>) : (ppw <= 1 ? k_gram2<1, false, 12> : k_gram2<2, false, 12>))
+                    : (tside ? (ppw <= 1 ? k_gram2<1, true, PCB_GM_MAXW> : k_gram2<2, true, PCB_GM_MAXW>)
+                             : (ppw <= 1 ? k_gram2<1, false, PCB_GM_MAXW> : k_gram2<2, false, PCB_GM_MAXW>));
         if (l == 0) {
             int per_sm = (int)((size_t)224 * 1024 / (smem + 1024)); if (per_sm < 1) per_sm = 1;
             const int by_threads = 2048 / (32 * W); if (per_sm > by_threads) per_sm = by_threads;
             if (per_sm > 4) per_sm = 4;
 #ifndef PCB_EMU
             if (smem > 48 * 1024) PCB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            PCB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
             { int occ = 0; PCB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * W, smem)); if (occ >= 1 && occ < per_sm) per_sm = occ; }
 #endif
             gx = (long long)c->sms * per_sm; if (gx > ntiles) gx = ntiles;
@@ -700,7 +703,10 @@ int pcb_gram2_top(pcb_ctx* c, int n, int ntop, const void* const* s, const void*
             if (ensure_hstage(c, sizeof(cplx) * 2 * PCB_MAXL * PCB_MAXL + 65536)) return -1;
         }
 #ifndef PCB_EMU
-        else if (smem > 48 * 1024) PCB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else {
+            if (smem > 48 * 1024) PCB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            PCB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        }
 #endif
         PCB_LAUNCH(kern, dim3((unsigned)gx, 1, 1), dim3(32 * W, 1, 1), smem, c->stream, S, HS, n, 8 * ttop, nt, pair0, np, c->R, (cplx*)c->partial);
         PCB_CUDA_OK(cudaGetLastError());
