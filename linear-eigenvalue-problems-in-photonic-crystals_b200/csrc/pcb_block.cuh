@@ -333,7 +333,10 @@ __global__ void k_gram_finish(const cplx* __restrict__ partial, int nblocks, int
 // 8-row tile rt and the output column tiles {2jp, 2jp+1} (4 complex columns each) of both S and HS.
 // Measured alternatives (B200, N = 120, m = 16, n_loc = 48; this form: 2.77 ms = 4.8 TB/s): a third cp.async stage 2.81 ms (the
 // loads are not what it waits for); one of S / HS per stage with 64-row tiles 2.93 ms, with 32-row tiles 3.77 ms (E' fragments
-// are then fetched twice per row tile: the kernel is bound by shared-memory fragment traffic and DMMA issue, not by HBM).
+// are then fetched twice per row tile); the 3M product scheme of the Gram kernel (6 DMMAs, two LDS.128 and three LDS.64 per
+// 4 input columns and 8 output columns instead of 8 DMMAs and 12 LDS.64; 12 warps of 48-row tiles) 3.04 ms, and 28.3 vs 23.1 ms
+// at N = 160, m = 32 -- fewer instructions on every pipe, yet slower: with one CTA per SM the 16 warps x 2 short DMMA chains of
+// this form overlap the stage barriers better than 12 warps x 6 chains.
 template <int TR>
 struct PcbUpd {
     static constexpr int LD = TR + 4;      // complex; LD*16 mod 128 == 64: the two k-columns of an A fragment hit disjoint banks
