@@ -139,3 +139,36 @@ def test_gram_pair_top_rows(pcb, N, n, ntop):
     g, t = s.conj().T @ s, s.conj().T @ hs
     assert relerr(G[:ntop, :], g[:ntop, :]) < 1e-13 and relerr(G[:, :ntop], g[:, :ntop]) < 1e-13
     assert relerr(T[:ntop, :], t[:ntop, :]) < 1e-13 and relerr(T[:, :ntop], t[:, :ntop]) < 1e-13
+
+
+def test_block_allocation_cache(pcb):
+    """Context recycles freed blocks of the same size (a band-structure run drops and re-allocates GB blocks per k-point);
+    trim() hands them back to the driver, and data written through a recycled block is what comes back."""
+    import gc
+    ctx = pcb.get_context(6)
+    ctx.trim()
+    a = ctx.from_host(np.full((ctx.R, 3), 1.0 + 2.0j))
+    p0 = a.ptrs[0]
+    nbytes = 16 * ctx.R * 3
+    del a
+    gc.collect()
+    if nbytes >= (1 << 20):          # only blocks of at least 1 MiB are kept
+        assert ctx._alloc_cached == nbytes
+    b = ctx.from_host(np.full((ctx.R, 3), 3.0 - 1.0j))
+    if nbytes >= (1 << 20):
+        assert b.ptrs[0] == p0 and ctx._alloc_cached == 0
+    assert np.all(b.get() == 3.0 - 1.0j)
+    del b
+    gc.collect()
+    freed = ctx.trim()
+    assert ctx._alloc_cached == 0 and (freed == nbytes or nbytes < (1 << 20))
+    big = ctx.empty(400)               # 400 columns of N = 6: above 1 MiB, exercises the cached path on every backend
+    p1 = big.ptrs[0]
+    del big
+    gc.collect()
+    assert ctx._alloc_cached == 16 * ctx.R * 400
+    again = ctx.empty(400)
+    assert again.ptrs[0] == p1
+    del again
+    gc.collect()
+    assert ctx.trim() == 16 * ctx.R * 400
