@@ -648,6 +648,10 @@ __global__ void k_mask_bits(PcbOp op, unsigned* __restrict__ out) {
 
 // ---------------------------------------------------------------------------------------
 // Plane mode, pass 2 of 3: forward y, forward z, M, inverse z, inverse y on one (i1, i2) plane held in shared memory.
+// (Measured alternative, B200, N = 120, 16 columns: moving the radix-8 step of the y transform into the x passes -- whose
+// thread mapping already holds a tile's 8 rows in 8 adjacent lanes, so the step is three shuffle butterflies per value --
+// takes this kernel from 0.90 to 0.745 ms (five shared-memory sweeps instead of seven), but the 180 SHFL per thread-item cost
+// the x passes more: 0.53 -> 0.72 ms and 0.70 -> 0.82 ms, 2.27 ms per apply instead of 2.09.  Reverted; git history has it.)
 // The x pass wrote the transposed layout W'[c][i0][i2][i1], so the plane of (c, i0) is one contiguous chunk of N^2 elements;
 // a CTA (N/8 warps, one per SM, persistent) keeps it in shared memory with row stride N+1 (row-fastest accesses of the y
 // steps stay conflict-free; N = 120: 232 320 B of the 232 448 B a CTA can have).  Warp w owns rows i2 in [8w, 8w+8) for the
