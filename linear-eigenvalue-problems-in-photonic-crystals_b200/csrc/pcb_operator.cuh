@@ -70,44 +70,6 @@ PCB_HD void pcb_cross(const cplx a[3], const cplx v[3], cplx z[3]) {
     z[2] = csub(cmul(a[0], v[1]), cmul(a[1], v[0]));
 }
 
-// ---- 8-point DFT across the 8 lanes of an aligned lane group -------------------------------------------
-// Plane mode keeps the radix-8 step of the y transform out of the shared-memory plane pass: in the x passes the 8 rows of a
-// tile are the 8 inputs n1 = 0..7 of one radix-8 group (i1 = lin(n1, n2y)), and the thread mapping already puts them in 8
-// adjacent lanes, so the step is three shuffle butterflies per value.  Forward is decimation in frequency (lane l holds x[l]
-// on entry and X[bitrev3(l)] on exit), inverse is decimation in time (X[bitrev3(l)] in, x[l] out, unnormalised).
-PCB_HD int pcb_bitrev3(int l) { return ((l & 1) << 2) | (l & 2) | ((l >> 2) & 1); }
-PCB_D cplx pcb_shfl_xor(cplx v, int m) {
-    v.x = __shfl_xor_sync(0xffffffffu, v.x, m);
-    v.y = __shfl_xor_sync(0xffffffffu, v.y, m);
-    return v;
-}
-PCB_D cplx pcb_lane_w8(int l, int sign) {      // exp(sign * 2 pi i (l & 3) / 8)
-    const double h = 0.70710678118654752440;
-    const int q = l & 3;
-    const double re = (q == 0) ? 1.0 : (q == 1) ? h : (q == 2) ? 0.0 : -h;
-    const double im = (q == 0) ? 0.0 : (q == 2) ? 1.0 : h;
-    return cmake(re, sign * im);
-}
-PCB_D cplx pcb_lane_dft8_fwd(cplx v, int l, cplx w /* pcb_lane_w8(l, -1) */) {
-    cplx p = pcb_shfl_xor(v, 4);
-    if (l & 4) v = cmul(csub(p, v), w); else v = cadd(v, p);
-    p = pcb_shfl_xor(v, 2);
-    if (l & 2) { const cplx d = csub(p, v); v = (l & 1) ? cmake(d.y, -d.x) : d; }     // times W4^(l&1) = 1 or -i
-    else v = cadd(v, p);
-    p = pcb_shfl_xor(v, 1);
-    return (l & 1) ? csub(p, v) : cadd(v, p);
-}
-PCB_D cplx pcb_lane_dft8_inv(cplx v, int l, cplx w /* pcb_lane_w8(l, +1) */) {
-    cplx p = pcb_shfl_xor(v, 1);
-    v = (l & 1) ? csub(p, v) : cadd(v, p);
-    if ((l & 3) == 3) v = cmake(-v.y, v.x);                                             // upper pair: times conj(W4^(l&1)) = 1 or +i
-    p = pcb_shfl_xor(v, 2);
-    v = (l & 2) ? csub(p, v) : cadd(v, p);
-    if (l & 4) v = cmul(v, w);
-    p = pcb_shfl_xor(v, 4);
-    return (l & 4) ? csub(p, v) : cadd(v, p);
-}
-
 // ---- cp.async (LDGSTS) helpers: global -> shared without staging in registers ------------------------
 #ifdef PCB_EMU
 PCB_D void pcb_cp16(cplx* dst, const cplx* src) { *dst = *src; }
@@ -150,14 +112,10 @@ __global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * (P::R1 * P::R2P + TR
     const int row0 = blockIdx.x * LX;
     const int nrows = N * N;
     const int tid = threadIdx.x;
-    // TRN: tile (i2, n2y) = the 8 rows i1 = lin(n1y, n2y), n1y = 0..7, of one radix-8 group of the y transform
-    static_assert(!TRN || (LX == 8 && R1 == 8 && N % 8 == 0), "plane mode: 8-row tiles, R1 = 8");
-    const int ty_i2 = row0 / N, ty_n2 = (row0 % N) / 8;
-    auto row_of = [&](int r) { return TRN ? ty_i2 * N + P::wrap(P::lin1(r) + P::lin2(ty_n2)) : row0 + r; };
 
     for (int item = tid; item < LX * R2; item += NT) {
         const int r = item / R2, n2 = item % R2;
-        const int row = row_of(r);
+        const int row = row0 + r;
         if (row >= nrows) continue;
         const int i1 = row % N, i2 = row / N;
         cplx v[3][R1];
@@ -214,19 +172,10 @@ __global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * (P::R1 * P::R2P + TR
         PCB_UNROLL
         for (int n2 = 0; n2 < R2; ++n2) v[n2] = sm[(c * LX + r) * RS + k1 * R2P + n2];
         Dft<R2, -1>::run(v);
-        if (TRN) {      // W'[c][k][i2][8 n2y + l], k = k1 + R1*k2: lane l = r ends up with the y digit k1y = bitrev3(l)
-            const int l = r;                        // = lane & 7 (LX == 8 divides the warp size and NT)
-            const cplx w8 = pcb_lane_w8(l, -1);
-            const int k1y = pcb_bitrev3(l);
-            cplx ty = cmake(1.0, 0.0);
-            if (!P::PFA && k1y > 0) ty = __ldg(tw + k1y * R2 + ty_n2);
-            cplx* __restrict__ dst = Y + c * nn + (long long)k1 * N * N + row;      // row = storage position 8 n2y + l + N*i2
+        if (TRN) {      // W'[c][k][i2][i1], k = k1 + R1*k2: consecutive threads = consecutive i1
+            cplx* __restrict__ dst = Y + c * nn + (long long)k1 * N * N + row;      // row = i1 + N*i2
             PCB_UNROLL
-            for (int k2 = 0; k2 < R2; ++k2) {
-                cplx val = pcb_lane_dft8_fwd(v[k2], l, w8);
-                if (!P::PFA) val = cmul(val, ty);
-                dst[(long long)R1 * k2 * N * N] = val;
-            }
+            for (int k2 = 0; k2 < R2; ++k2) dst[(long long)R1 * k2 * N * N] = v[k2];
         } else {
             cplx* __restrict__ dst = Y + c * nn + (long long)row * N + k1;
             PCB_UNROLL
@@ -260,25 +209,11 @@ __global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * (P::R1 * P::R2P + TR
     const int nrows = N * N;
     const int nr = (nrows - row0 < LX) ? nrows - row0 : LX;      // rows of this tile
     const int tid = threadIdx.x;
-    // TRN: tile (i2, n2y) = the 8 rows i1 = lin(n1y, n2y) of one radix-8 group of the y transform (see k_xfwd)
-    static_assert(!TRN || (LX == 8 && R1 == 8 && N % 8 == 0), "plane mode: 8-row tiles, R1 = 8");
-    const int ty_i2 = row0 / N, ty_n2 = (row0 % N) / 8;
-    auto row_of = [&](int r) { return TRN ? ty_i2 * N + P::wrap(P::lin1(r) + P::lin2(ty_n2)) : row0 + r; };
 
-    if (MODE == 2) {   // the epilogue re-reads X: pull this tile's lines (one contiguous chunk per row and component) towards L2 now
-        if (TRN) {
-            constexpr int lines = (N * (int)sizeof(cplx) + 127) / 128 + 1;      // a row need not start on a line boundary
-            for (int l = tid; l < 3 * 8 * lines; l += NT) {
-                const int c = l / (8 * lines), r = (l / lines) % 8, q = l % lines;
-                const char* base = reinterpret_cast<const char*>(X + c * nn + (long long)row_of(r) * N);
-                const char* a = reinterpret_cast<const char*>(reinterpret_cast<unsigned long long>(base) & ~127ull) + q * 128;
-                if (a < base + N * sizeof(cplx)) pcb_prefetch_l2(a);
-            }
-        } else {
-            const int lines = (nr * N * (int)sizeof(cplx) + 127) / 128;
-            for (int l = tid; l < 3 * lines; l += NT)
-                pcb_prefetch_l2(reinterpret_cast<const char*>(X + (l / lines) * nn + (long long)row0 * N) + (l % lines) * 128);
-        }
+    if (MODE == 2) {   // the epilogue re-reads X: pull this tile's lines (3 contiguous chunks) towards L2 now
+        const int lines = (nr * N * (int)sizeof(cplx) + 127) / 128;
+        for (int l = tid; l < 3 * lines; l += NT)
+            pcb_prefetch_l2(reinterpret_cast<const char*>(X + (l / lines) * nn + (long long)row0 * N) + (l % lines) * 128);
     }
     // inverse radix R2 over k2 (fixed k1): global (Fourier order, k = k1 + R1*k2) -> registers -> shared
     for (int item = tid; item < 3 * LX * R1; item += NT) {
@@ -289,12 +224,9 @@ __global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * (P::R1 * P::R2P + TR
         if (r >= nr) continue;
         cplx v[R2];
         if (TRN) {
-            const cplx* __restrict__ src = WT + c * nn + (long long)k1 * N * N + (row0 + r);      // storage position 8 n2y + l
+            const cplx* __restrict__ src = WT + c * nn + (long long)k1 * N * N + (row0 + r);
             PCB_UNROLL
             for (int k2 = 0; k2 < R2; ++k2) v[k2] = src[(long long)R1 * k2 * N * N];
-            const cplx w8 = pcb_lane_w8(r, +1);       // last y step: inverse radix 8 over the lanes (digit bitrev3(l) in, row n1y = l out)
-            PCB_UNROLL
-            for (int k2 = 0; k2 < R2; ++k2) v[k2] = pcb_lane_dft8_inv(v[k2], r, w8);
         } else {
             const cplx* __restrict__ src = W + c * nn + (long long)(row0 + r) * N + k1;
             PCB_UNROLL
@@ -330,9 +262,8 @@ __global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * (P::R1 * P::R2P + TR
             for (int q = 0; q < PB; ++q) {
                 const int e = e0 + q * NT;
                 if (e < nr * N) {
-                    const long long g = TRN ? (long long)row_of(e / N) * N + e % N : (long long)row0 * N + e;
                     PCB_UNROLL
-                    for (int c = 0; c < 3; ++c) x[q][c] = X[c * nn + g];
+                    for (int c = 0; c < 3; ++c) x[q][c] = X[c * nn + (long long)row0 * N + e];
                 }
             }
         }
@@ -341,7 +272,7 @@ __global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * (P::R1 * P::R2P + TR
             const int e = e0 + q * NT;
             if (e >= nr * N) continue;
             const int r = e / N, i0 = e % N;
-            const int row = row_of(r);
+            const int row = row0 + r;
             const int slot = r * RS + (i0 / R2) * R2P + i0 % R2;
             cplx u[3], z[3];
             PCB_UNROLL
@@ -366,7 +297,7 @@ __global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * (P::R1 * P::R2P + TR
                 for (int c = 0; c < 3; ++c) z[c] = u[c];
             }
             PCB_UNROLL
-            for (int c = 0; c < 3; ++c) W[c * nn + (TRN ? (long long)row * N + i0 : (long long)row0 * N + e)] = z[c];
+            for (int c = 0; c < 3; ++c) W[c * nn + (long long)row0 * N + e] = z[c];
         }
     }
 }
@@ -627,8 +558,7 @@ __global__ void __launch_bounds__(NT, (NT > 256 ? 1 : 2)) k_zmid(PcbOp op, PcbCo
 }
 
 // Plane mode set-up (once per dielectric): mbits[c][i0][slot][k1], bit k2 = "component c of grid point
-// (i0, i1 = y-coordinate of storage position `slot`, i2 = lout(k1, k2)) lies in Omega_1" -- exactly the R2 flags one radix-R2
-// item of k_mid needs.
+// (i0, i1 = coord(slot), i2 = lout(k1, k2)) lies in Omega_1" -- exactly the 15 (R2) flags one radix-R2 item of k_mid needs.
 template <class P>
 __global__ void k_mask_bits(PcbOp op, unsigned* __restrict__ out) {
     constexpr int N = P::N, R1 = P::R1, R2 = P::R2;
@@ -636,8 +566,7 @@ __global__ void k_mask_bits(PcbOp op, unsigned* __restrict__ out) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total) return;
     const int k1 = (int)(t % R1), slot = (int)((t / R1) % N), i0 = (int)((t / ((long long)R1 * N)) % N), c = (int)(t / ((long long)R1 * N * N));
-    // storage position slot = 8 k2y + l of the y direction holds the output digits (k1y = bitrev3(l), k2y)
-    const int i1 = P::wrap(P::lout1(pcb_bitrev3(slot % 8)) + P::lout2(slot / 8)), o1 = P::lout1(k1);
+    const int i1 = P::coord(slot), o1 = P::lout1(k1);
     unsigned w = 0u;
     for (int k2 = 0; k2 < R2; ++k2) {
         const int i2 = P::wrap(o1 + P::lout2(k2));
@@ -690,16 +619,31 @@ __global__ void __launch_bounds__(P::N / 8 * 32, 1) k_mid(PcbOp op, PcbCols cols
         }
         pcb_cp_wait<0>();
         __syncwarp();
-        // ---- forward y on own rows: only the radix-R2 step (the radix-8 step was done across lanes in k_xfwd<T>; position
-        // 8 n2 + l of a row holds digit k1y = bitrev3(l), twiddled) -- lanes = (row fastest, l) ----
+        // ---- forward y on own rows: lanes = (row fastest, digit) ----
+        for (int it = lane; it < 8 * R2; it += 32) {
+            cplx* __restrict__ row = myrows + (it % 8) * LD;
+            const int n2 = it / 8, b2 = P::lin2(n2);
+            cplx v[R1];
+            PCB_UNROLL
+            for (int n1 = 0; n1 < R1; ++n1) v[n1] = row[P::wrap(P::lin1(n1) + b2)];
+            Dft<R1, -1>::run(v);
+            PCB_UNROLL
+            for (int k1 = 0; k1 < R1; ++k1) {
+                cplx val = v[k1];
+                if (!P::PFA && k1 > 0) val = cmul(val, __ldg(tw + k1 * R2 + n2));
+                row[P::wrap(P::lin1(k1) + b2)] = val;
+            }
+        }
+        __syncwarp();
         for (int it = lane; it < 8 * R1; it += 32) {
-            cplx* __restrict__ row = myrows + (it % 8) * LD + it / 8;
+            cplx* __restrict__ row = myrows + (it % 8) * LD;
+            const int k1 = it / 8, b1 = P::lin1(k1);
             cplx v[R2];
             PCB_UNROLL
-            for (int n2 = 0; n2 < R2; ++n2) v[n2] = row[8 * n2];
+            for (int n2 = 0; n2 < R2; ++n2) v[n2] = row[P::wrap(b1 + P::lin2(n2))];
             Dft<R2, -1>::run(v);
             PCB_UNROLL
-            for (int k2 = 0; k2 < R2; ++k2) row[8 * k2] = v[k2];
+            for (int k2 = 0; k2 < R2; ++k2) row[P::wrap(b1 + P::lin2(k2))] = v[k2];
         }
         __syncthreads();
         // ---- z on own slots (columns 8w .. 8w+7): lanes = (slot fastest, digit) ----
@@ -755,20 +699,31 @@ __global__ void __launch_bounds__(P::N / 8 * 32, 1) k_mid(PcbOp op, PcbCols cols
             for (int n1 = 0; n1 < R1; ++n1) cp[P::wrap(P::lin1(n1) + b2) * LD] = v[n1];
         }
         __syncthreads();
-        // ---- inverse y on own rows: the radix-R2 step (+ conjugate twiddle); the radix-8 step follows in k_xinv<T> ----
+        // ---- inverse y on own rows, then store them ----
         for (int it = lane; it < 8 * R1; it += 32) {
-            cplx* __restrict__ row = myrows + (it % 8) * LD + it / 8;
-            const int k1 = pcb_bitrev3(it / 8);
+            cplx* __restrict__ row = myrows + (it % 8) * LD;
+            const int k1 = it / 8, b1 = P::lin1(k1);
             cplx v[R2];
             PCB_UNROLL
-            for (int k2 = 0; k2 < R2; ++k2) v[k2] = row[8 * k2];
+            for (int k2 = 0; k2 < R2; ++k2) v[k2] = row[P::wrap(b1 + P::lin2(k2))];
             Dft<R2, +1>::run(v);
             PCB_UNROLL
             for (int n2 = 0; n2 < R2; ++n2) {
                 cplx val = v[n2];
                 if (!P::PFA && k1 > 0) { const cplx t = __ldg(tw + k1 * R2 + n2); val = cmul(val, cmake(t.x, -t.y)); }
-                row[8 * n2] = val;
+                row[P::wrap(b1 + P::lin2(n2))] = val;
             }
+        }
+        __syncwarp();
+        for (int it = lane; it < 8 * R2; it += 32) {
+            cplx* __restrict__ row = myrows + (it % 8) * LD;
+            const int n2 = it / 8, b2 = P::lin2(n2);
+            cplx v[R1];
+            PCB_UNROLL
+            for (int k1 = 0; k1 < R1; ++k1) v[k1] = row[P::wrap(P::lin1(k1) + b2)];
+            Dft<R1, +1>::run(v);
+            PCB_UNROLL
+            for (int n1 = 0; n1 < R1; ++n1) row[P::wrap(P::lin1(n1) + b2)] = v[n1];
         }
         __syncwarp();
         for (int e = lane; e < 8 * N; e += 32) base[e] = myrows[(e / N) * LD + e % N];

@@ -58,9 +58,8 @@ inline int ctas_per_sm(int smem, int regs_hint_threads) {
         PCB_CUDA_OK(cudaGetLastError());                                            \
     } while (0)
 
-// plane mode: R1 = 8 (the x passes do the radix-8 step of the y transform across the 8 lanes that hold a tile's 8 rows), 8-row
-// tiles, and N x (N+1) complex fit in one CTA's shared memory
-constexpr bool kPlane = (P::R1 == 8) && (P::N % 8 == 0) && (LX == 8) && ((long long)P::N * (P::N + 1) * 16 <= 232448);
+// plane mode: N % 8 == 0, tiles of 8 rows must not straddle an i2 plane, and N x (N+1) complex fit in one CTA's shared memory
+constexpr bool kPlane = (P::N % 8 == 0) && (LX == 8) && ((long long)P::N * (P::N + 1) * 16 <= 232448);
 constexpr int kSmemMid = P::N * (P::N + 1) * (int)sizeof(cplx);
 constexpr int kStageXT = 3 * LX * (P::R1 * P::R2P + 1) * (int)sizeof(cplx);
 

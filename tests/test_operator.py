@@ -53,10 +53,8 @@ def test_symbols_vs_reference_golden(pcb, golden):
 
 
 @pytest.mark.parametrize("N,d_flag,typ,alpha", [
-    (8, "sc_curv", "chiral", [np.pi, np.pi, np.pi]),
-    (24, "fcc", "chiral", [0.3, 2 * np.pi, 0.0]),              # R1 = 8: three-pass plane mode (radix-8 y step across lanes in the x passes)
-    (24, "bcc_sg", None, [0.0, 0.0, 0.0]),                      # plane mode, identity M
-    (16, "fcc", "chiral", [0.3, 2 * np.pi, 0.0]),              # plane mode with Cooley-Tukey twiddles (16 = 8 x 2)
+    (8, "sc_curv", "chiral", [np.pi, np.pi, np.pi]),          # N % 8 == 0: three-pass plane mode (fused y/z pass)
+    (16, "fcc", "chiral", [0.3, 2 * np.pi, 0.0]),
     (16, "bcc_sg", None, [0.0, 0.0, 0.0]),
     (16, "sc_curv", "pseudochiral_trivial", [np.pi, 0.0, 0.0]),   # coupled 3x3 M: five-pass path
     (12, "fcc", "chiral", [np.pi, np.pi, 0.0]),                    # N % 8 != 0: five-pass path
