@@ -343,7 +343,7 @@ struct PcbUpd {
 };
 
 template <int TR, int JW>   // JW = output column tiles (of 4 complex columns) per warp
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(TR == 48 ? 768 : 512, 1)
 k_update(PcbColList Sin, PcbColList HSin, PcbColListW Xout, PcbColListW HXout, PcbColListW Pout, PcbColListW HPout,
          const cplx* __restrict__ E, int m, int kx, int kp, int MPp, long long R) {
     constexpr int LD = PcbUpd<TR>::LD;
@@ -365,18 +365,23 @@ k_update(PcbColList Sin, PcbColList HSin, PcbColListW Xout, PcbColListW HXout, P
         sEr[(size_t)(2 * k + 1) * LDE + 2 * j] = -e.y;  sEr[(size_t)(2 * k + 1) * LDE + 2 * j + 1] = e.x;
     }
     const long long ntiles = (R + TR - 1) / TR;
-    auto load_tile = [&](long long t, int stage) {      // TR lanes of a warp per column (two columns per trip when TR == 16)
-        constexpr int CPW = 32 / TR;
-        const int sub = lane / TR, rr = lane % TR;
-        const long long r = t * TR + rr;
-        cplx* d0 = sT + (size_t)(stage * 2) * matElems + rr;
+    auto load_tile = [&](long long t, int stage) {      // TR lanes of a warp per column (two columns per trip when TR == 16,
+        constexpr int CPW = TR >= 32 ? 1 : 32 / TR;      // a second, half-filled trip over the rows when TR == 48)
+        const int sub = TR >= 32 ? 0 : lane / TR, rr0 = TR >= 32 ? lane : lane % TR;
+        cplx* d0 = sT + (size_t)(stage * 2) * matElems;
         for (int c = warp * CPW + sub; c < nl; c += W * CPW) {
             const cplx* sp = c < PCB_MAXL ? Sin.p[c] : nullptr;      // columns past the list are zero padding
             const cplx* hp = c < PCB_MAXL ? HSin.p[c] : nullptr;
-            cplx* ds = d0 + (size_t)c * LD;
-            cplx* dh = ds + matElems;
-            if (sp != nullptr && r < R) { pcb_cp16(ds, sp + r); pcb_cp16(dh, hp + r); }
-            else { *ds = cmake(0.0, 0.0); *dh = cmake(0.0, 0.0); }
+            PCB_UNROLL
+            for (int q = 0; q < (TR + 31) / 32; ++q) {
+                const int rr = rr0 + 32 * q;
+                if (TR % 32 != 0 && TR > 32 && rr >= TR) break;
+                const long long r = t * TR + rr;
+                cplx* ds = d0 + (size_t)c * LD + rr;
+                cplx* dh = ds + matElems;
+                if (sp != nullptr && r < R) { pcb_cp16(ds, sp + r); pcb_cp16(dh, hp + r); }
+                else { *ds = cmake(0.0, 0.0); *dh = cmake(0.0, 0.0); }
+            }
         }
         pcb_cp_commit();
     };
