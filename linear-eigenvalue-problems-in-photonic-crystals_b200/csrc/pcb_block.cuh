@@ -342,7 +342,7 @@ struct PcbUpd {
     static constexpr int LD = TR + 4;      // complex; LD*16 mod 128 == 64: the two k-columns of an A fragment hit disjoint banks
 };
 
-template <int TR, int JW>   // JW = output column tiles (of 4 complex columns) per warp
+template <int TR, int JW, int NST = 2>   // JW = output column tiles (of 4 complex columns) per warp; NST = cp.async stages
 __global__ void __launch_bounds__(TR == 48 ? 768 : 512, 1)
 k_update(PcbColList Sin, PcbColList HSin, PcbColListW Xout, PcbColListW HXout, PcbColListW Pout, PcbColListW HPout,
          const cplx* __restrict__ E, int m, int kx, int kp, int MPp, long long R) {
@@ -387,12 +387,27 @@ k_update(PcbColList Sin, PcbColList HSin, PcbColListW Xout, PcbColListW HXout, P
     };
     long long t = blockIdx.x;
     int stage = 0;
-    if (t < ntiles) load_tile(t, 0);
+    if (NST == 2) {
+        if (t < ntiles) load_tile(t, 0);
+    } else {      // three stages: two tiles in flight, ONE barrier per tile (the buffer refilled below was read two barriers ago)
+        PCB_UNROLL
+        for (int i = 0; i < NST - 1; ++i) {
+            const long long tt = t + (long long)i * gridDim.x;
+            if (tt < ntiles) load_tile(tt, i); else pcb_cp_commit();
+        }
+    }
     const double* bbase = sEr + (size_t)tig * LDE + 8 * (JW * jp) + g;    // B fragment: row 2k + tig, column 8 jt + g
     for (; t < ntiles; t += gridDim.x) {
-        const long long tn = t + gridDim.x;
-        if (tn < ntiles) { load_tile(tn, stage ^ 1); pcb_cp_wait<1>(); } else { pcb_cp_wait<0>(); }
-        __syncthreads();
+        if (NST == 2) {
+            const long long tn = t + gridDim.x;
+            if (tn < ntiles) { load_tile(tn, stage ^ 1); pcb_cp_wait<1>(); } else { pcb_cp_wait<0>(); }
+            __syncthreads();
+        } else {
+            pcb_cp_wait<NST - 2>();
+            __syncthreads();
+            const long long tn = t + (long long)(NST - 1) * gridDim.x;
+            if (tn < ntiles) load_tile(tn, (stage + NST - 1) % NST); else pcb_cp_commit();
+        }
         const double* s0 = reinterpret_cast<const double*>(sT + (size_t)(stage * 2) * matElems);
         const double* h0 = reinterpret_cast<const double*>(sT + (size_t)(stage * 2 + 1) * matElems);
         double acc[2][JW][2];     // [S|HS][j-tile][c0,c1]
@@ -436,8 +451,8 @@ k_update(PcbColList Sin, PcbColList HSin, PcbColListW Xout, PcbColListW HXout, P
                 }
             }
         }
-        __syncthreads();
-        stage ^= 1;
+        if (NST == 2) { __syncthreads(); stage ^= 1; }
+        else stage = (stage + 1) % NST;
     }
 }
 

@@ -767,9 +767,13 @@ int pcb_update(pcb_ctx* c, int m, int nl, void* const* s, void* const* hs, void*
     // 48-row tiles with 24 warps (6 row tiles x 4 column tiles) when they fit: more thin warps overlap the stage barriers better
     static const char* ev_tr = getenv("PCB200_UPD_TR");
     const bool wide = JT == 4 && smem48 <= (size_t)224 * 1024 && !(ev_tr && atoi(ev_tr) == 32);
-    const int TR = wide ? 48 : big ? 32 : 16;
-    const size_t smem = wide ? smem48 : big ? smem32 : smem16;
-    const int JW = (wide || (TR / 8) * JT <= 16) ? 1 : 2;  // one column tile per warp while that keeps <= 16 warps per CTA
+    static const char* ev_nst = getenv("PCB200_UPD_NST");
+    const size_t smem32x3 = sizeof(cplx) * (2 * (size_t)nlp * MPp + 6 * (size_t)nlp * PcbUpd<32>::LD);
+    // m = 16: three 32-row stages with one barrier per tile (2.71 ms at n_loc = 48; 48-row tiles x 24 warps 2.76, two stages 2.77)
+    const bool deep = !(ev_nst && atoi(ev_nst) == 2) && JT == 4 && smem32x3 <= (size_t)224 * 1024;
+    const int TR = deep ? 32 : wide ? 48 : big ? 32 : 16;
+    const size_t smem = deep ? smem32x3 : wide ? smem48 : big ? smem32 : smem16;
+    const int JW = (deep || wide || (TR / 8) * JT <= 16) ? 1 : 2;  // one column tile per warp while that keeps <= 16 warps per CTA
     const int warps = (TR / 8) * (JT / JW);
     const long long ntiles = (c->R + TR - 1) / TR;
     int per_sm = (int)((size_t)224 * 1024 / (smem + 1024)); if (per_sm < 1) per_sm = 1; if (per_sm > 4) per_sm = 4;
@@ -784,7 +788,8 @@ int pcb_update(pcb_ctx* c, int m, int nl, void* const* s, void* const* hs, void*
 #else
 #define PCB_UPD_GO(K) PCB_LAUNCH(K, grid, block, smem, c->stream, Sin, HSin, X, HX, P, HP, dE, m, kx, kp, MPp, c->R)
 #endif
-    if (wide) PCB_UPD_GO((k_update<48, 1>));
+    if (deep) PCB_UPD_GO((k_update<32, 1, 3>));
+    else if (wide) PCB_UPD_GO((k_update<48, 1>));
     else if (big && JW == 1) PCB_UPD_GO((k_update<32, 1>));
     else if (big) PCB_UPD_GO((k_update<32, 2>));
     else if (JW == 1) PCB_UPD_GO((k_update<16, 1>));
