@@ -18,6 +18,10 @@ constexpr int NTP = PCB_NTP;     // persistent z-mid kernel: 2 CTAs/SM of 256 th
 constexpr int kRowBytes = 3 * P::R1 * P::R2P * (int)sizeof(cplx);
 constexpr int LX = (8 * kRowBytes <= 65536) ? 8 : (4 * kRowBytes <= 65536) ? 4 : (2 * kRowBytes <= 65536) ? 2 : 1;
 constexpr int kStageX = LX * kRowBytes;               // one x-tile (three components)
+// forward x pass: 64-thread CTAs where the first radix step has at most 64 items (LX * R2: N = 192, 240, 256) -- with 128 threads
+// half of them would sit out the phase that issues the loads (N = 256, 8 columns: 4.48 -> 2.69 ms; the inverse pass, whose
+// loading phase has 3 LX R1 items, gets slower with 64 threads, 4.40 -> 5.01 ms, and keeps 128)
+constexpr int NTX = (LX * P::R2 <= 64) ? 64 : NT;
 constexpr int kSmemL = 3 * P::N * 8 * (int)sizeof(cplx);
 constexpr int kSmemZ = 2 * kSmemL;                       // two stages
 constexpr int NSTZ = (2 * (kSmemZ + 1024) <= 224 * 1024) ? 2 : 1;         // ... else single-stage tiles, still several CTAs per SM
@@ -43,6 +47,14 @@ inline int ctas_per_sm(int smem, int regs_hint_threads) {
         if (set_smem(kfn, (SMEM))) return -1;                                       \
         dim3 grid((unsigned)(GRIDX), (unsigned)ncols, 1);                           \
         PCB_LAUNCH(kfn, grid, dim3(NT, 1, 1), (size_t)(SMEM), s, op, cols, tw);      \
+        PCB_CUDA_OK(cudaGetLastError());                                            \
+    } while (0)
+#define PCB_GO_X(KERN, GRIDX, SMEM)                                                 \
+    do {                                                                            \
+        auto kfn = KERN;                                                            \
+        if (set_smem(kfn, (SMEM))) return -1;                                       \
+        dim3 grid((unsigned)(GRIDX), (unsigned)ncols, 1);                           \
+        PCB_LAUNCH(kfn, grid, dim3(NTX, 1, 1), (size_t)(SMEM), s, op, cols, tw);     \
         PCB_CUDA_OK(cudaGetLastError());                                            \
     } while (0)
 // persistent CTAs striding over (column, tile)
@@ -95,8 +107,8 @@ struct PlanePass<true, PP> {
 
 int run_pass(const PcbOp& op, const PcbCols& cols, int ncols, int pass_id, const cplx* tw, cudaStream_t s, int sms) {
     switch (pass_id) {
-        case PCB_PASS_XFWD_SYM: PCB_GO((k_xfwd<P, LX, NT, 1>), GX, kStageX); break;
-        case PCB_PASS_XFWD:     PCB_GO((k_xfwd<P, LX, NT, 0>), GX, kStageX); break;
+        case PCB_PASS_XFWD_SYM: PCB_GO_X((k_xfwd<P, LX, NTX, 1>), GX, kStageX); break;
+        case PCB_PASS_XFWD:     PCB_GO_X((k_xfwd<P, LX, NTX, 0>), GX, kStageX); break;
         case PCB_PASS_YFWD:     PCB_GO((k_line<P, 1, -1, NT>), GL, kSmemL); break;
         case PCB_PASS_ZFWD:     PCB_GO((k_line<P, 2, -1, NT>), GL, kSmemL); break;
         case PCB_PASS_ZINV:     PCB_GO((k_line<P, 2, +1, NT>), GL, kSmemL); break;
