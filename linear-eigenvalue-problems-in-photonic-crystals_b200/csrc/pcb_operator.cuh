@@ -94,7 +94,7 @@ template <int N> PCB_D void pcb_cp_wait() { asm volatile("cp.async.wait_group %0
 // Tile = LX consecutive rows (a row = all i0 for one (i1,i2)), all three components; one CTA per tile, registers stage the
 // radix-R1 input, shared memory the exchange.  Measured alternatives on B200 (N = 120, 16 columns): a persistent cp.async
 // double-buffered variant 0.63 ms and a three-phase variant with a coalesced point-wise prologue 0.53 ms, vs 0.51 ms for this
-// form with the 4-CTAs/SM register cap (4-row tiles with 64 threads and 8 CTAs/SM: 0.55 ms in plane mode) -- so the simple form
+// form with the 4-CTAs/SM register cap (plane mode: 4-row tiles with 64 threads and 8 CTAs/SM 0.55 ms, 16-row tiles with 256 threads and 2 CTAs/SM 0.57 ms) -- so the simple form
 // stays (the inverse pass, which also re-reads X, does gain from
 // the three-phase structure; the z pass, with twice the arithmetic per byte, from the cp.async pipeline).
 // ---------------------------------------------------------------------------------------
