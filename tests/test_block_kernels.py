@@ -172,3 +172,28 @@ def test_block_allocation_cache(pcb):
     del again
     gc.collect()
     assert ctx.trim() == 16 * ctx.R * 400
+
+
+def test_gram_top_with_the_real_operator(pcb, oracle):
+    """The leading-rows Gram pair forms T as (H W)^H S instead of W^H (H S): with the actual Hermitian operator (FFT passes,
+    dielectric, penalty term) both agree to rounding, which is what the incremental Gram update of the solver relies on."""
+    N, d = 8, "sc_curv"
+    mfd, ne = pcb.discretization, pcb.numerical_experiments
+    alpha = np.array([np.pi, 0.4, -1.1])
+    relax, pnt = mfd.set_relaxation(alpha)
+    a_fft, b_fft = mfd.fft_blocks(N, 1, pcb.dielectric.diel_info(d, option="ct"), alpha=alpha)
+    inv_fft = mfd.inverse_3_times_3_B(b_fft, pnt, relax[0])
+    A, H, P = ne.pc_mfd_handle(a_fft, (pnt * b_fft[0], pnt * b_fft[1]), mfd.chiral_handle(N, d), inv_fft, relax[0])
+    ctx = H.op.ctx
+    n, ntop = 24, 8
+    s = oracle.random_x0(3 * N ** 3, n, 21)
+    S = ctx.from_host(s)
+    HS = ctx.empty(n)
+    H.op.apply_into(pcb._lib.APPLY_H, S, HS)
+    hs = HS.get()
+    G, T = pcb.orthogonalization.gram_pair_top(S, HS, ntop)
+    g, t = s.conj().T @ s, s.conj().T @ hs
+    assert relerr(G[:ntop, :], g[:ntop, :]) < 1e-13
+    assert relerr(T[:ntop, :], t[:ntop, :]) < 1e-12
+    Gf, Tf = pcb.orthogonalization.gram_pair(S, HS)
+    assert relerr(Tf, (t + t.conj().T) / 2) < 1e-12
