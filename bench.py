@@ -274,16 +274,15 @@ def main():
 
     peak, peak_src = measured_peak()
     achieved = B_OP_PER_N3 * n ** 3 * m / (ms_step * 1e-3) / 1e9 * 1.0     # per rank: every rank runs the same step
-    # DRAM bytes of one launch (= one 16-column block apply) from the ncu --set full capture of these kernels at this
-    # shape (profiles/r01_c_final_ncu.md: dram__bytes_read.sum + dram__bytes_write.sum over the five passes); null otherwise
     # DRAM bytes of one launch (= one 16-column block apply) from ncu --set full captures of exactly these kernels and this
-    # shape: plane mode profiles/r01_d_plane_mode_ncu.md (5.478 GB read + 3.859 GB written), five-pass r01_c_final_ncu.md
+    # shape (dram__bytes_read.sum + dram__bytes_write.sum summed over the passes): plane mode profiles/r01_f_final_ncu.md
+    # (5.487 GB read + 3.864 GB written), five-pass profiles/r01_c_final_ncu.md; null for other shapes
     traffic = None
     if n == 120 and m == 16:
-        traffic = 9.337e9 if npass.value == 3 else 14.51e9
+        traffic = 9.351e9 if npass.value == 3 else 14.51e9
     roofline = {"bound": "hbm", "kernel": kernel_desc,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_[cd]_*_ncu.md",
+                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_f_final_ncu.md (plane mode) / r01_c_final_ncu.md (five-pass)",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": B_OP_PER_N3 * n ** 3 * m,
                 "moved_bytes_per_launch": float(pass_bytes.sum()), "moved_GBps": float(pass_bytes.sum() / (ms_step * 1e-3) / 1e9)}
 
