@@ -89,6 +89,39 @@ PCB_D void pcb_cp_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> PCB_D void pcb_cp_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 #endif
 
+// ---- bulk (TMA, 1-D) copies with mbarrier completion: one thread moves a whole row, no LSU instructions per element ----
+#ifndef PCB_EMU
+PCB_D unsigned pcb_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+PCB_D void pcb_mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(pcb_smem_u32(bar)), "r"(count));
+}
+PCB_D void pcb_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(pcb_smem_u32(bar)), "r"(bytes) : "memory");
+}
+PCB_D void pcb_mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "PCB_MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra PCB_MBAR_DONE;\n"
+        "bra PCB_MBAR_WAIT;\n"
+        "PCB_MBAR_DONE:\n"
+        "}\n" ::"r"(pcb_smem_u32(bar)), "r"(parity) : "memory");
+}
+PCB_D void pcb_bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(pcb_smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(pcb_smem_u32(bar)) : "memory");
+}
+PCB_D void pcb_bulk_store(void* gdst, const void* smem_src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(pcb_smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+PCB_D void pcb_bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+PCB_D void pcb_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+PCB_D void pcb_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+PCB_D void pcb_fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+#endif
+
 // ---------------------------------------------------------------------------------------
 // Pass 1: x-lines forward.  SYM: 0 plain FFT, 1 multiply by K_A^H = (-conj k) x . on load.
 // Tile = LX consecutive rows (a row = all i0 for one (i1,i2)), all three components; one CTA per tile, registers stage the
@@ -590,23 +623,48 @@ __global__ void k_mask_bits(PcbOp op, unsigned* __restrict__ out) {
 // operator drops from 11 to 7 column transfers per op-apply.  DIEL: 0 identity, 1 component-wise (chiral); the coupled
 // 3x3 dielectrics need all three components of a point and stay on the five-pass path.
 // ---------------------------------------------------------------------------------------
-template <class P, int DIEL>
+// TMA = 1 (default on the device): the rows of a plane are moved by bulk copies -- cp.async.bulk, one elected lane per warp
+// issues eight row copies against the warp's own mbarrier; the store goes back the same way after a proxy fence -- instead
+// of per-element cp.async / LDS + STG loops: 960 LDGSTS and 960 LDS+STG per warp and plane leave the LSU queue, which the
+// radix steps need (N = 120, 16 columns: 0.884 -> 0.818 ms; PCB200_MID_TMA=0 selects the loop form, which is also what the
+// host-emulation build runs).
+template <class P, int DIEL, int TMA = 0>
 __global__ void __launch_bounds__(P::N / 8 * 32, 1) k_mid(PcbOp op, PcbCols cols, const cplx* __restrict__ tw, int ncols) {
     constexpr int N = P::N, R1 = P::R1, R2 = P::R2;
     constexpr int LD = N + 1;                    // row stride (complex)
     static_assert(N % 8 == 0, "plane mode needs N % 8 == 0");
-    PCB_DYN_SMEM(cplx, pl);   // [N rows i2][LD]
+    PCB_DYN_SMEM(cplx, pl);   // [N rows i2][LD] (+ one mbarrier per warp behind it when TMA)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long nn = op.nn;
     const int total = 3 * N * ncols;
     cplx* __restrict__ myrows = pl + (8 * warp) * LD;
+#ifndef PCB_EMU
+    unsigned long long* mybar = reinterpret_cast<unsigned long long*>(pl + (size_t)N * LD) + warp;
+    unsigned phase = 0;
+    if (TMA) {
+        if (lane == 0) { pcb_mbar_init(mybar, 1); pcb_fence_mbar_init(); }
+        __syncthreads();
+    }
+#endif
 
     for (int pid = blockIdx.x; pid < total; pid += gridDim.x) {
         const int col = pid / (3 * N), c = (pid / N) % 3, i0 = pid % N;
         cplx* __restrict__ base = cols.wrk[col] + c * nn + (long long)i0 * N * N + (long long)(8 * warp) * N;   // this warp's 8 rows
         // ---- load own rows (contiguous 8*N elements) ----
-        for (int e = lane; e < 8 * N; e += 32) pcb_cp16(myrows + (e / N) * LD + e % N, base + e);
-        pcb_cp_commit();
+#ifndef PCB_EMU
+        if (TMA) {
+            if (lane == 0) {
+                pcb_bulk_wait_read();                       // the previous plane's bulk stores have read these rows
+                pcb_mbar_expect_tx(mybar, 8u * N * (unsigned)sizeof(cplx));
+                PCB_UNROLL
+                for (int r = 0; r < 8; ++r) pcb_bulk_load(myrows + r * LD, base + r * N, N * (unsigned)sizeof(cplx), mybar);
+            }
+        } else
+#endif
+        {
+            for (int e = lane; e < 8 * N; e += 32) pcb_cp16(myrows + (e / N) * LD + e % N, base + e);
+            pcb_cp_commit();
+        }
         // dielectric bits this lane needs in the z step (items it = lane + 32 q: slot 8w + it%8, digit k1 = it/8): one precomputed
         // word per item (k_mask_bits), fetched now so that its latency hides behind the row loads
         constexpr int ZI = (8 * R1 + 31) / 32;
@@ -618,6 +676,9 @@ __global__ void __launch_bounds__(P::N / 8 * 32, 1) k_mid(PcbOp op, PcbCols cols
                 mbits[q] = (it < 8 * R1) ? __ldg(op.mbits + (((long long)c * N + i0) * N + 8 * warp + it % 8) * R1 + it / 8) : 0u;
             }
         }
+#ifndef PCB_EMU
+        if (TMA) { pcb_mbar_wait(mybar, phase); phase ^= 1u; } else
+#endif
         pcb_cp_wait<0>();
         __syncwarp();
         // ---- forward y on own rows: lanes = (row fastest, digit) ----
@@ -727,9 +788,23 @@ __global__ void __launch_bounds__(P::N / 8 * 32, 1) k_mid(PcbOp op, PcbCols cols
             for (int n1 = 0; n1 < R1; ++n1) row[P::wrap(P::lin1(n1) + b2)] = v[n1];
         }
         __syncwarp();
+#ifndef PCB_EMU
+        if (TMA) {
+            pcb_fence_async_smem();                         // the rows were written through the generic proxy
+            __syncwarp();
+            if (lane == 0) {
+                PCB_UNROLL
+                for (int r = 0; r < 8; ++r) pcb_bulk_store(base + r * N, myrows + r * LD, N * (unsigned)sizeof(cplx));
+                pcb_bulk_commit();
+            }
+        } else
+#endif
         for (int e = lane; e < 8 * N; e += 32) base[e] = myrows[(e / N) * LD + e % N];
         __syncwarp();      // own rows are free again for the next plane's loads
     }
+#ifndef PCB_EMU
+    if (TMA && lane == 0) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");      // stores done before the CTA exits
+#endif
 }
 
 // ---------------------------------------------------------------------------------------

@@ -98,8 +98,17 @@ struct PlanePass<true, PP> {
         if (pass_id == PCB_PASS_XFWD_SYM_T) PCB_GO((k_xfwd<PP, LX, NT, 1, 1>), GX, kStageXT);
         else if (pass_id == PCB_PASS_XINV_A_T) PCB_GO((k_xinv<PP, LX, NT, 1, 1>), GX, kStageXT);
         else if (pass_id == PCB_PASS_XINV_H_T) PCB_GO((k_xinv<PP, LX, NT, 2, 1>), GX, kStageXT);
-        else if (op.diel == PCB_DIEL_NONE) PCB_GO_P((k_mid<PP, 0>), (PP::N / 8 * 32), 3 * PP::N, kSmemMid, 1);
-        else if (op.diel == PCB_DIEL_CHIRAL) PCB_GO_P((k_mid<PP, 1>), (PP::N / 8 * 32), 3 * PP::N, kSmemMid, 1);
+        else if (op.diel == PCB_DIEL_NONE || op.diel == PCB_DIEL_CHIRAL) {
+            static const char* ev = getenv("PCB200_MID_TMA");
+            const bool tma = !(ev && ev[0] == '0') && kSmemMid + 128 <= 232448;      // default; PCB200_MID_TMA=0: cp.async / LDS+STG row loops
+            if (tma) {
+                if (op.diel == PCB_DIEL_NONE) PCB_GO_P((k_mid<PP, 0, 1>), (PP::N / 8 * 32), 3 * PP::N, kSmemMid + 128, 1);
+                else PCB_GO_P((k_mid<PP, 1, 1>), (PP::N / 8 * 32), 3 * PP::N, kSmemMid + 128, 1);
+            } else {
+                if (op.diel == PCB_DIEL_NONE) PCB_GO_P((k_mid<PP, 0>), (PP::N / 8 * 32), 3 * PP::N, kSmemMid, 1);
+                else PCB_GO_P((k_mid<PP, 1>), (PP::N / 8 * 32), 3 * PP::N, kSmemMid, 1);
+            }
+        }
         else { pcb_set_error("plane mode: dielectric type %d not supported", op.diel); return -1; }
         return 0;
     }
