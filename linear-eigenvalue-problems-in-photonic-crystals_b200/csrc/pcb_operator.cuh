@@ -127,7 +127,8 @@ PCB_D void pcb_fence_mbar_init() { asm volatile("fence.mbarrier_init.release.clu
 // Tile = LX consecutive rows (a row = all i0 for one (i1,i2)), all three components; one CTA per tile, registers stage the
 // radix-R1 input, shared memory the exchange.  Measured alternatives on B200 (N = 120, 16 columns): a persistent cp.async
 // double-buffered variant 0.63 ms and a three-phase variant with a coalesced point-wise prologue 0.53 ms, vs 0.51 ms for this
-// form with the 4-CTAs/SM register cap (plane mode: 4-row tiles with 64 threads and 8 CTAs/SM 0.55 ms, 16-row tiles with 256 threads and 2 CTAs/SM 0.57 ms) -- so the simple form
+// form with the 4-CTAs/SM register cap (plane mode: 4-row tiles with 64 threads and 8 CTAs/SM 0.55 ms, 16-row tiles with 256 threads and 2 CTAs/SM 0.57 ms, persistent CTAs
+// with TMA bulk row copies into one in-place tile buffer and the next tile issued behind the second radix step 0.64 ms) -- so the simple form
 // stays (the inverse pass, which also re-reads X, does gain from
 // the three-phase structure; the z pass, with twice the arithmetic per byte, from the cp.async pipeline).
 // ---------------------------------------------------------------------------------------
