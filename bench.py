@@ -149,6 +149,20 @@ def build_ops(pcb, n, alpha, Diels):
     return ne.pc_mfd_handle(a_fft, b_fft, Diels, inv_fft, relax[0]), relax[0]
 
 
+def host_threads():
+    """Host threads the CPU legs use: every core of the box, set EXPLICITLY (torchrun exports OMP_NUM_THREADS=1 for N > 1, which
+    would otherwise change the BLAS pool between the N = 1 and N > 1 runs of the reference arm)."""
+    cores = os.cpu_count() or 1
+    info = {"cores": cores, "scipy_fft_workers": cores, "blas_threads": None}
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+        threadpool_limits(limits=cores)
+        info["blas_threads"] = max([t.get("num_threads", 1) for t in threadpool_info() if t.get("user_api") == "blas"] or [1])
+    except Exception:
+        pass
+    return info
+
+
 def cpu_apply_rate(n, alpha, cols, reps, warm, workers):
     """Oracle port of AMA_BB (oracle/pc_oracle.py) on the host: op-applies/s on `cols` columns."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -175,22 +189,24 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    th = host_threads()
+    cores = th["cores"]
     n = args.n
     pcb = importlib.import_module(PKG)
     alphas = pcb.dielectric.kpath(LATTICE)
     alpha = alphas[0]
-    cols = 1
+    cols = args.cols          # the same 16-column block apply per step as the CUDA arm (same_config)
     t0 = time.perf_counter()
     rate, times = cpu_apply_rate(n, alpha, cols, args.steps, args.warmup, cores)
     ms = 1e3 * sum(times) / len(times)
-    sample = f"{cols} column(s) of the {M_BLOCK}-column block per step (H apply, N={n}, scipy.fft workers={cores})"
+    sample = (f"the full {cols}-column block per step (H apply, N={n}; oracle port of pcfft.AMA_BB, scipy.fft workers={cores}, "
+              f"BLAS threads={th['blas_threads']}); the reference itself is Python + CuPy and cannot run on this box")
     line = {"impl": "reference", "metric": "op_applies_per_sec", "value": rate, "unit": "op-applies/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{LATTICE} {DTYPE_TYPE} eps=13 N={n} m={M_BLOCK} H block apply (configs[1])", "N": n,
                        "lattice": LATTICE, "type": DTYPE_TYPE, "cols_per_step": cols},
-            "cpu_baseline": {"value": rate, "unit": "op-applies/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": rate, "unit": "op-applies/s", "cores": cores, "kind": "port", "sample": sample, "threads": th},
             "e2e": {"value": rate, "unit": "op-applies/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": time.perf_counter() - t0}
     print(json.dumps(line), flush=True)

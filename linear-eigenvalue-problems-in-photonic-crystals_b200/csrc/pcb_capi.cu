@@ -84,7 +84,8 @@ struct pcb_ctx {
     int use_plane = 1;              // PCB200_PLANE=0 forces the five-pass operator (A/B measurements)
     // pcb_apply_host pipeline: copy streams, two slots of (row-major staging in/out, planar columns in/out), events
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
-    cplx* hp_buf = nullptr;         // one allocation: 2 slots x 4 regions of R x PCB_HOST_CH elements
+    cplx* hp_buf = nullptr;         // one allocation: 2 slots x 4 regions of R x hp_cols elements
+    int hp_cols = 0;                // columns per pipeline chunk the staging was sized for (<= PCB_HOST_CH)
     cudaEvent_t hp_ev[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
 };
 struct pcb_diel {
@@ -172,6 +173,7 @@ int pcb_supported_sizes(int* sizes, int cap) {
 }
 
 static int ctx_create(int device, int N, int z0, int z1, pcb_ctx** out);
+void pcb_ctx_destroy(pcb_ctx* c);
 int pcb_ctx_create(int device, int N, pcb_ctx** out) { return ctx_create(device, N, 0, N, out); }
 int pcb_ctx_create_slab(int device, int N, int z0, int z1, pcb_ctx** out) {
     if (z0 < 0 || z1 > N || z0 >= z1) { pcb_set_error("pcb_ctx_create_slab: need 0 <= z0 < z1 <= N"); return -2; }
@@ -192,23 +194,24 @@ static int ctx_create(int device, int N, int z0, int z1, pcb_ctx** out) {
     { const char* e = getenv("PCB200_PLANE"); c->use_plane = (plan->plane_mode && !(e && e[0] == '0')) ? 1 : 0; }
 #ifndef PCB_EMU
     cudaDeviceProp prop;
-    PCB_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    PCB_CUDA_OK_OR(cudaGetDeviceProperties(&prop, device), delete c);
     c->sms = prop.multiProcessorCount;
-    if (prop.major < 10) { pcb_set_error("pcb_ctx_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); delete c; return -3; }
+    // the binary holds sm_100a code only (arch-specific, not forward compatible): refuse every other part cleanly
+    if (prop.major != 10 || prop.minor != 0) { pcb_set_error("pcb_ctx_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); delete c; return -3; }
 #else
     c->sms = 2;
 #endif
-    PCB_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    PCB_CUDA_OK(cudaEventCreate(&c->ev0));
-    PCB_CUDA_OK(cudaEventCreate(&c->ev1));
+    PCB_CUDA_OK_OR(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), delete c);
+    PCB_CUDA_OK_OR(cudaEventCreate(&c->ev0), pcb_ctx_destroy(c));
+    PCB_CUDA_OK_OR(cudaEventCreate(&c->ev1), pcb_ctx_destroy(c));
     std::vector<cplx> tw((size_t)N);
     for (int k1 = 0; k1 < plan->r1; ++k1)
         for (int n2 = 0; n2 < plan->r2; ++n2) {
             const double ang = -2.0 * M_PI * (double)((long long)k1 * n2 % N) / (double)N;
             tw[(size_t)k1 * plan->r2 + n2] = cmake(cos(ang), sin(ang));
         }
-    PCB_CUDA_OK(cudaMalloc(&c->tw, sizeof(cplx) * N));
-    PCB_CUDA_OK(cudaMemcpy(c->tw, tw.data(), sizeof(cplx) * N, cudaMemcpyHostToDevice));
+    PCB_CUDA_OK_OR(cudaMalloc(&c->tw, sizeof(cplx) * N), pcb_ctx_destroy(c));
+    PCB_CUDA_OK_OR(cudaMemcpy(c->tw, tw.data(), sizeof(cplx) * N, cudaMemcpyHostToDevice), pcb_ctx_destroy(c));
     *out = c;
     return 0;
 }
@@ -216,7 +219,7 @@ extern "C" {
 void pcb_ctx_destroy(pcb_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->tw) cudaFree(c->tw);
     if (c->partial) cudaFree(c->partial);
     if (c->dsmall) cudaFree(c->dsmall);
@@ -226,9 +229,9 @@ void pcb_ctx_destroy(pcb_ctx* c) {
     if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
     if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
     for (int a = 0; a < 2; ++a) for (int b = 0; b < 4; ++b) if (c->hp_ev[a][b]) cudaEventDestroy(c->hp_ev[a][b]);
-    cudaEventDestroy(c->ev0);
-    cudaEventDestroy(c->ev1);
-    cudaStreamDestroy(c->stream);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
 int pcb_sync(pcb_ctx* c) { PCB_CUDA_OK(cudaStreamSynchronize(c->stream)); PCB_CUDA_OK(cudaGetLastError()); return 0; }
@@ -329,6 +332,7 @@ int pcb_fill_uniform(pcb_ctx* c, int k, void* const* cols, unsigned long long se
 }
 
 // ---- dielectric -----------------------------------------------------------------------------------------------
+void pcb_diel_destroy(pcb_diel* d);
 int pcb_diel_create(pcb_ctx* c, int kind, const int64_t* ind_e, long long n_e, const int64_t* ind_v, long long n_v,
                     const double* ediag, const double* eoff, int k, const double* stencil, pcb_diel** out) {
     PCB_CHECK_ARG(out && kind >= PCB_DIEL_NONE && kind <= PCB_DIEL_CROSSDOF, "bad kind");
@@ -343,34 +347,36 @@ int pcb_diel_create(pcb_ctx* c, int kind, const int64_t* ind_e, long long n_e, c
         for (int i = 0; i < 2 * k; ++i) d->st.w[i] = stencil[i];
     }
     const size_t mbytes = (size_t)((c->nn + 3) / 4) * 4;
-    PCB_CUDA_OK(cudaMalloc(&d->mask, mbytes));
-    PCB_CUDA_OK(cudaMemsetAsync(d->mask, 0, mbytes, c->stream));
+    PCB_CUDA_OK_OR(cudaMalloc(&d->mask, mbytes), pcb_diel_destroy(d));
+    PCB_CUDA_OK_OR(cudaMemsetAsync(d->mask, 0, mbytes, c->stream), pcb_diel_destroy(d));
     const int64_t* lists[2] = {ind_e, ind_v};
     const long long counts[2] = {n_e, (kind == PCB_DIEL_TRIVIAL) ? n_v : 0};
     for (int which = 0; which < 2; ++which) {
         const long long n = counts[which];
         if (n <= 0 || !lists[which]) continue;
         long long* dind = nullptr;
-        PCB_CUDA_OK(cudaMalloc(&dind, sizeof(long long) * (size_t)n));
-        PCB_CUDA_OK(cudaMemcpyAsync(dind, lists[which], sizeof(long long) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+        PCB_CUDA_OK_OR(cudaMalloc(&dind, sizeof(long long) * (size_t)n), pcb_diel_destroy(d));
+#define PCB_DIEL_FAIL do { cudaStreamSynchronize(c->stream); cudaFree(dind); pcb_diel_destroy(d); } while (0)
+        PCB_CUDA_OK_OR(cudaMemcpyAsync(dind, lists[which], sizeof(long long) * (size_t)n, cudaMemcpyHostToDevice, c->stream), PCB_DIEL_FAIL);
         dim3 grid((unsigned)((n + 255) / 256), 1, 1);
         PCB_LAUNCH(k_mask_from_index, grid, dim3(256, 1, 1), 0, c->stream, (const long long*)dind, n, c->nn, which, (unsigned*)d->mask);
-        PCB_CUDA_OK(cudaGetLastError());
+        PCB_CUDA_OK_OR(cudaGetLastError(), PCB_DIEL_FAIL);
         c->launches++;
-        PCB_CUDA_OK(cudaStreamSynchronize(c->stream));
-        PCB_CUDA_OK(cudaFree(dind));
+        PCB_CUDA_OK_OR(cudaStreamSynchronize(c->stream), PCB_DIEL_FAIL);
+#undef PCB_DIEL_FAIL
+        PCB_CUDA_OK_OR(cudaFree(dind), pcb_diel_destroy(d));
     }
     if (c->plan->plane_mode) {
-        PCB_CUDA_OK(cudaMalloc(&d->mbits, sizeof(unsigned) * 3 * (size_t)c->N * c->N * c->plan->r1));
+        PCB_CUDA_OK_OR(cudaMalloc(&d->mbits, sizeof(unsigned) * 3 * (size_t)c->N * c->N * c->plan->r1), pcb_diel_destroy(d));
         PcbOp tmp;
         memset(&tmp, 0, sizeof tmp);
         tmp.N = c->N; tmp.nn = c->nn; tmp.nloc = c->nloc; tmp.mask = d->mask; tmp.mbits = d->mbits;
         PcbCols none;
         memset(&none, 0, sizeof none);
-        if (c->plan->pass(tmp, none, 1, PCB_PASS_MASKBITS, c->tw, c->stream, c->sms)) return -1;
+        if (c->plan->pass(tmp, none, 1, PCB_PASS_MASKBITS, c->tw, c->stream, c->sms)) { pcb_diel_destroy(d); return -1; }
         c->launches++;
     }
-    PCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+    PCB_CUDA_OK_OR(cudaStreamSynchronize(c->stream), pcb_diel_destroy(d));
     *out = d;
     return 0;
 }
@@ -554,17 +560,19 @@ int pcb_apply_timed(pcb_op* o, int mode, int ncols, const void* const* in, void*
         seq[0] = PCB_PASS_XFWD_SYM_T; seq[1] = PCB_PASS_MID; seq[2] = mode == PCB_APPLY_A ? PCB_PASS_XINV_A_T : PCB_PASS_XINV_H_T;
         n = 3;
     }
-    cudaEvent_t ev[6];
-    for (int i = 0; i < 6; ++i) PCB_CUDA_OK(cudaEventCreate(&ev[i]));
-    PCB_CUDA_OK(cudaEventRecord(ev[0], c->stream));
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+#define PCB_EV_FREE do { for (int q = 0; q < 6; ++q) if (ev[q]) cudaEventDestroy(ev[q]); } while (0)
+    for (int i = 0; i < 6; ++i) PCB_CUDA_OK_OR(cudaEventCreate(&ev[i]), PCB_EV_FREE);
+    PCB_CUDA_OK_OR(cudaEventRecord(ev[0], c->stream), PCB_EV_FREE);
     for (int i = 0; i < n; ++i) {
-        if (c->plan->pass(o->d, cols, ncols, seq[i], c->tw, c->stream, c->sms)) return -1;
-        PCB_CUDA_OK(cudaEventRecord(ev[i + 1], c->stream));
+        if (c->plan->pass(o->d, cols, ncols, seq[i], c->tw, c->stream, c->sms)) { cudaStreamSynchronize(c->stream); PCB_EV_FREE; return -1; }
+        PCB_CUDA_OK_OR(cudaEventRecord(ev[i + 1], c->stream), PCB_EV_FREE);
     }
     c->launches += n;
-    PCB_CUDA_OK(cudaEventSynchronize(ev[n]));
-    for (int i = 0; i < n; ++i) PCB_CUDA_OK(cudaEventElapsedTime(&pass_ms[i], ev[i], ev[i + 1]));
-    for (int i = 0; i < 6; ++i) PCB_CUDA_OK(cudaEventDestroy(ev[i]));
+    PCB_CUDA_OK_OR(cudaEventSynchronize(ev[n]), PCB_EV_FREE);
+    for (int i = 0; i < n; ++i) PCB_CUDA_OK_OR(cudaEventElapsedTime(&pass_ms[i], ev[i], ev[i + 1]), PCB_EV_FREE);
+    PCB_EV_FREE;
+#undef PCB_EV_FREE
     *npass = n;
     return 0;
 }
@@ -573,17 +581,33 @@ int pcb_apply_timed(pcb_op* o, int mode, int ncols, const void* const* in, void*
 // The block travels in chunks of PCB_HOST_CH columns (2-D copies of 128-byte rows run at full PCIe speed) through a
 // three-stream pipeline -- H2D of chunk c+1, transpose + apply + transpose of chunk c, D2H of chunk c-1 overlap -- so both PCIe
 // directions are busy at once; with pinned host memory a 16-column block at N = 120 takes ~3 instead of 4 chunk-copy times.
+static int apply_host_pipeline(pcb_op* o, int mode, int k, const void* x_host, long long ldx, void* y_host, long long ldy);
 int pcb_apply_host(pcb_op* o, int mode, int k, const void* x_host, long long ldx, void* y_host, long long ldy) {
     PCB_CHECK_ARG(o && x_host && y_host && k > 0 && ldx >= k && ldy >= k, "bad arguments");
     pcb_ctx* c = o->ctx;
     PCB_CUDA_OK(cudaSetDevice(c->device));
-    const size_t R = (size_t)c->R, CH = PCB_HOST_CH;
     if (!c->s_h2d) {
         PCB_CUDA_OK(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
         PCB_CUDA_OK(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
         for (int a = 0; a < 2; ++a) for (int b = 0; b < 4; ++b) PCB_CUDA_OK(cudaEventCreateWithFlags(&c->hp_ev[a][b], cudaEventDisableTiming));
-        PCB_CUDA_OK(cudaMalloc(&c->hp_buf, sizeof(cplx) * R * CH * 8));
     }
+    // staging: 2 slots x 4 regions of R x min(k, CH) elements (a single-vector call takes 1/8 of the block-call size)
+    const int chw = k < PCB_HOST_CH ? k : PCB_HOST_CH;
+    if (chw > c->hp_cols) {
+        if (c->hp_buf) { PCB_CUDA_OK(cudaStreamSynchronize(c->stream)); PCB_CUDA_OK(cudaFree(c->hp_buf)); c->hp_buf = nullptr; c->hp_cols = 0; }
+        PCB_CUDA_OK(cudaMalloc(&c->hp_buf, sizeof(cplx) * (size_t)c->R * (size_t)chw * 8));
+        c->hp_cols = chw;
+    }
+    const int rc = apply_host_pipeline(o, mode, k, x_host, ldx, y_host, ldy);
+    if (rc != 0) {      // no copy may still target the caller's buffers when an error is reported
+        cudaStreamSynchronize(c->s_h2d); cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->s_d2h);
+        (void)cudaGetLastError();
+    }
+    return rc;
+}
+static int apply_host_pipeline(pcb_op* o, int mode, int k, const void* x_host, long long ldx, void* y_host, long long ldy) {
+    pcb_ctx* c = o->ctx;
+    const size_t R = (size_t)c->R, CH = (size_t)c->hp_cols;
     PCB_CUDA_OK(cudaStreamSynchronize(c->stream));
     enum { EV_H2D = 0, EV_INFREE = 1, EV_CMP = 2, EV_OUTFREE = 3 };
     const int nchunks = (int)((k + CH - 1) / CH);
@@ -838,8 +862,15 @@ int pcb_axpby(pcb_ctx* c, int ncols, const void* const* x, void* const* y, doubl
 #ifndef PCB_EMU
 static int nccl_load() {
     if (g_nccl.lib) return 0;
+    // Order: PCB200_NCCL_LIB (explicit path), a copy the process has already mapped (e.g. torch's bundled NCCL: RTLD_NOLOAD, so
+    // that two different NCCL builds never coexist), then the default search path.  RTLD_LOCAL: nothing else resolves against it.
     const char* names[] = {"libnccl.so.2", "libnccl.so", nullptr};
-    for (int i = 0; names[i] && !g_nccl.lib; ++i) g_nccl.lib = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+    if (const char* ev = getenv("PCB200_NCCL_LIB")) {
+        g_nccl.lib = dlopen(ev, RTLD_NOW | RTLD_LOCAL);
+        if (!g_nccl.lib) { pcb_set_error("cannot dlopen PCB200_NCCL_LIB=%s: %s", ev, dlerror()); return -4; }
+    }
+    for (int i = 0; names[i] && !g_nccl.lib; ++i) g_nccl.lib = dlopen(names[i], RTLD_NOW | RTLD_LOCAL | RTLD_NOLOAD);
+    for (int i = 0; names[i] && !g_nccl.lib; ++i) g_nccl.lib = dlopen(names[i], RTLD_NOW | RTLD_LOCAL);
     if (!g_nccl.lib) { pcb_set_error("cannot dlopen libnccl.so.2: %s", dlerror()); return -4; }
 #define PCB_SYM(field, name)                                                        \
     *(void**)(&g_nccl.field) = dlsym(g_nccl.lib, name);                             \

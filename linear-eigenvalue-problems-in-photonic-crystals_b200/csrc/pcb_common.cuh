@@ -77,6 +77,18 @@ void pcb_set_error(const char* fmt, ...);
         cudaError_t e_ = (expr);                                                          \
         if (e_ != cudaSuccess) {                                                          \
             pcb_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            (void)cudaGetLastError(); /* a recoverable failure (e.g. cudaMalloc) must not poison later launch checks */ \
+            return -1;                                                                    \
+        }                                                                                 \
+    } while (0)
+// same, running CLEANUP (a statement) before returning: frees partially built objects on the failure paths
+#define PCB_CUDA_OK_OR(expr, CLEANUP)                                                     \
+    do {                                                                                  \
+        cudaError_t e_ = (expr);                                                          \
+        if (e_ != cudaSuccess) {                                                          \
+            pcb_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            (void)cudaGetLastError();                                                     \
+            CLEANUP;                                                                      \
             return -1;                                                                    \
         }                                                                                 \
     } while (0)

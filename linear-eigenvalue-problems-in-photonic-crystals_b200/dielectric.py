@@ -175,6 +175,25 @@ _FLAGS = {"sc_flat1": FLAG_sc_flat1, "sc_flat2": FLAG_sc_flat2, "sc_curv": FLAG_
 
 
 _index_cache = {}     # (N, d_flag, dofs) -> int64 indices (in-process complement of the on-disk .bin cache)
+_geom_digest = []
+
+
+def _geometry_digest():
+    """Short digest of this module's source (the FLAG_* / mesh definitions): versions the private on-disk index cache."""
+    if not _geom_digest:
+        import hashlib
+        with open(__file__, "rb") as f:
+            _geom_digest.append(hashlib.sha256(f.read()).hexdigest()[:12])
+    return _geom_digest[0]
+
+
+def _cache_dir_is_private(root):
+    """True when the cache root belongs to this user and nobody else may write to it."""
+    try:
+        st = os.stat(root)
+    except OSError:
+        return False
+    return st.st_uid == os.getuid() and (st.st_mode & 0o022) == 0
 
 
 def compute_index(N, d_flag, dofs="edge"):
@@ -199,19 +218,29 @@ def diel_io_index(N, d_flag, dofs="edge", gpu=True, cache=True):
     if not os.path.isdir(os.path.dirname(path)):
         # no reference-style directory in the working directory: keep the same raw-int64 files in a per-user cache so that
         # the geometry (seconds of NumPy at N = 120, per process) is evaluated once per machine, not once per run and rank
-        root = os.environ.get("PCB200_CACHE", os.path.join(tempfile.gettempdir(), "pcb200_index_cache"))
-        path = os.path.join(root, dofs + "_dofs", f"{d_flag}_{N}.bin")
+        # (directory private to the user, file name keyed by a digest of this module's geometry code: a stale file from an
+        # older FLAG_* definition or one planted by another user is never picked up)
+        root = os.environ.get("PCB200_CACHE", os.path.join(tempfile.gettempdir(), f"pcb200_index_cache_{os.getuid()}"))
+        path = os.path.join(root, dofs + "_dofs", f"{d_flag}_{N}_{_geometry_digest()}.bin")
+        private = True
+    else:
+        private = False
+    ind = None
     if (N, d_flag, dofs) in _index_cache:
         ind = _index_cache[(N, d_flag, dofs)]
-    elif os.path.exists(path):
+    elif os.path.exists(path) and (not private or _cache_dir_is_private(os.path.dirname(os.path.dirname(path)))):
         ind = np.fromfile(path, dtype=np.int64)
-        say(f"{GREEN}Index file already exists.{RESET}")
-    else:
+        limit = 3 * N ** 3 if dofs == "edge" else N ** 3
+        if ind.size == 0 or ind.size > limit or ind.min() < 0 or ind.max() >= limit or np.any(np.diff(ind) <= 0):
+            ind = None            # truncated / foreign file: recompute
+        else:
+            say(f"{GREEN}Index file already exists.{RESET}")
+    if ind is None:
         ind = compute_index(N, d_flag, dofs)
         if cache:
             say(f"{RED}New lattice type {d_flag} or size {N} isn't computed.{RESET}")
             try:
-                os.makedirs(os.path.dirname(path), exist_ok=True)
+                os.makedirs(os.path.dirname(path), mode=0o700, exist_ok=True)
                 tmp = f"{path}.{os.getpid()}.tmp"
                 ind.tofile(tmp)
                 os.replace(tmp, path)          # atomic: concurrent ranks may race for the same file

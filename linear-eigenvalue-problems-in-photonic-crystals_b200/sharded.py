@@ -39,6 +39,9 @@ class SlabComm:
             raise ValueError("more ranks than grid planes")
         self.full = devarray.get_context(N, device)
         self.slab = Context(N, self.full.device, slab=(self.zb[rank], self.zb[rank + 1]))
+        if unique_id is None and self.world > 1:
+            raise ValueError("SlabComm: world > 1 needs the unique_id of rank 0 (new_unique_id(), broadcast by the caller); "
+                             "ranks that each generate their own id would block in ncclCommInitRank forever")
         uid = unique_id if unique_id is not None else new_unique_id()
         buf = (C.c_char * 128).from_buffer_copy(bytes(uid))
         L.check(L.lib().pcb_comm_init(self.slab.h, buf, self.rank, self.world), "pcb_comm_init")
