@@ -120,6 +120,26 @@ PCB_D void pcb_bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: 
 PCB_D void pcb_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
 PCB_D void pcb_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 PCB_D void pcb_fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+// ---- thread-block clusters: distributed shared memory (the coupled 3x3 dielectric of the plane pass) ----
+PCB_D unsigned pcb_cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r)); return r; }
+PCB_D unsigned pcb_cluster_id() { unsigned r; asm volatile("mov.u32 %0, %%clusterid.x;\n" : "=r"(r)); return r; }
+PCB_D unsigned pcb_cluster_count() { unsigned r; asm volatile("mov.u32 %0, %%nclusterid.x;\n" : "=r"(r)); return r; }
+PCB_D unsigned pcb_mapa(unsigned smem_addr, unsigned rank) {      // the same shared-memory offset in CTA `rank` of the cluster
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(smem_addr), "r"(rank));
+    return r;
+}
+PCB_D cplx pcb_ld_cluster(unsigned addr) {
+    cplx v;
+    asm volatile("ld.shared::cluster.v2.f64 {%0, %1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+PCB_D void pcb_st_cluster(unsigned addr, cplx v) {
+    asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};\n" ::"r"(addr), "d"(v.x), "d"(v.y) : "memory");
+}
+PCB_D void pcb_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
 #endif
 
 // ---------------------------------------------------------------------------------------
@@ -629,15 +649,27 @@ __global__ void k_mask_bits(PcbOp op, unsigned* __restrict__ out) {
 // of per-element cp.async / LDS + STG loops: 960 LDGSTS and 960 LDS+STG per warp and plane leave the LSU queue, which the
 // radix steps need (N = 120, 16 columns: 0.884 -> 0.818 ms; PCB200_MID_TMA=0 selects the loop form, which is also what the
 // host-emulation build runs).
-template <class P, int DIEL, int TMA = 0>
+// DIEL = 2 (coupled 3x3 point-wise M, discretization.py:368-401): the kernel is launched as CLUSTERS OF THREE CTAs, one per
+// component of the same (column, i0) plane.  The fused z step is split at real space: (A) forward radix R2 and the diagonal
+// entries (bit words as for DIEL = 1) -> own plane; cluster barrier; (B) every CTA takes a third of the rows and, at the
+// points whose volume DoF lies in Omega_1 (byte mask in plane-slot order, k_mask_plane), reads the three components -- one
+// local, two through distributed shared memory --, adds the off-diagonal terms and writes all three back; cluster barrier;
+// (C) inverse radix R2.  With u~ = D u stored by (A), y_a = u~_a + sum_b eps_ab (u~_b / d_b).  Only the coupled points cross
+// the SM-to-SM network (bcc gyroids: 10-20 % of the cells), so the 3x3 dielectric costs one extra shared-memory sweep
+// and two cluster barriers per plane instead of the two extra global passes of the five-pass structure.
+// HALF = 1 / 2: only the forward (y, z) / inverse (z, y) transforms of the plane, M left out -- the cross-DoF dielectric is a
+// stencil across planes and runs as its own kernel on the real-space planes in between (k_diel_crossdof_t, pcb_block.cuh).
+// HALF = 2 loads from cols.out (the stencil's output) and stores to cols.wrk.
+template <class P, int DIEL, int TMA = 0, int HALF = 0>
 __global__ void __launch_bounds__(P::N / 8 * 32, 1) k_mid(PcbOp op, PcbCols cols, const cplx* __restrict__ tw, int ncols) {
     constexpr int N = P::N, R1 = P::R1, R2 = P::R2;
     constexpr int LD = N + 1;                    // row stride (complex)
+    constexpr bool FWD = HALF != 2, INV = HALF != 1;
     static_assert(N % 8 == 0, "plane mode needs N % 8 == 0");
+    static_assert(HALF == 0 || DIEL == 0, "the half passes carry no dielectric");
     PCB_DYN_SMEM(cplx, pl);   // [N rows i2][LD] (+ one mbarrier per warp behind it when TMA)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long nn = op.nn;
-    const int total = 3 * N * ncols;
     cplx* __restrict__ myrows = pl + (8 * warp) * LD;
 #ifndef PCB_EMU
     unsigned long long* mybar = reinterpret_cast<unsigned long long*>(pl + (size_t)N * LD) + warp;
@@ -647,10 +679,23 @@ __global__ void __launch_bounds__(P::N / 8 * 32, 1) k_mid(PcbOp op, PcbCols cols
         __syncthreads();
     }
 #endif
+    // plane enumeration: (column, component, i0) over the CTAs, or (column, i0) over the clusters with the component = cluster rank
+    int first = blockIdx.x, stride = gridDim.x, total = 3 * N * ncols, crank = 0;
+#ifndef PCB_EMU
+    unsigned pbase[3] = {0u, 0u, 0u};
+    double inv_d[3] = {1.0, 1.0, 1.0};
+    if (DIEL == 2) {
+        crank = (int)pcb_cluster_ctarank(); first = (int)pcb_cluster_id(); stride = (int)pcb_cluster_count(); total = N * ncols;
+        PCB_UNROLL
+        for (int r = 0; r < 3; ++r) { pbase[r] = pcb_mapa(pcb_smem_u32(pl), (unsigned)r); inv_d[r] = 1.0 / op.ediag[r]; }
+    }
+#endif
 
-    for (int pid = blockIdx.x; pid < total; pid += gridDim.x) {
-        const int col = pid / (3 * N), c = (pid / N) % 3, i0 = pid % N;
-        cplx* __restrict__ base = cols.wrk[col] + c * nn + (long long)i0 * N * N + (long long)(8 * warp) * N;   // this warp's 8 rows
+    for (int pid = first; pid < total; pid += stride) {
+        const int col = (DIEL == 2) ? pid / N : pid / (3 * N), c = (DIEL == 2) ? crank : (pid / N) % 3, i0 = pid % N;
+        const long long poff = c * nn + (long long)i0 * N * N + (long long)(8 * warp) * N;      // this warp's 8 rows
+        cplx* __restrict__ base = cols.wrk[col] + poff;
+        const cplx* __restrict__ src = (HALF == 2) ? cols.out[col] + poff : base;
         // ---- load own rows (contiguous 8*N elements) ----
 #ifndef PCB_EMU
         if (TMA) {
@@ -658,19 +703,19 @@ __global__ void __launch_bounds__(P::N / 8 * 32, 1) k_mid(PcbOp op, PcbCols cols
                 pcb_bulk_wait_read();                       // the previous plane's bulk stores have read these rows
                 pcb_mbar_expect_tx(mybar, 8u * N * (unsigned)sizeof(cplx));
                 PCB_UNROLL
-                for (int r = 0; r < 8; ++r) pcb_bulk_load(myrows + r * LD, base + r * N, N * (unsigned)sizeof(cplx), mybar);
+                for (int r = 0; r < 8; ++r) pcb_bulk_load(myrows + r * LD, src + r * N, N * (unsigned)sizeof(cplx), mybar);
             }
         } else
 #endif
         {
-            for (int e = lane; e < 8 * N; e += 32) pcb_cp16(myrows + (e / N) * LD + e % N, base + e);
+            for (int e = lane; e < 8 * N; e += 32) pcb_cp16(myrows + (e / N) * LD + e % N, src + e);
             pcb_cp_commit();
         }
         // dielectric bits this lane needs in the z step (items it = lane + 32 q: slot 8w + it%8, digit k1 = it/8): one precomputed
         // word per item (k_mask_bits), fetched now so that its latency hides behind the row loads
         constexpr int ZI = (8 * R1 + 31) / 32;
         unsigned mbits[ZI];
-        if (DIEL == 1) {
+        if (DIEL >= 1) {
             PCB_UNROLL
             for (int q = 0; q < ZI; ++q) {
                 const int it = lane + 32 * q;
@@ -682,113 +727,186 @@ __global__ void __launch_bounds__(P::N / 8 * 32, 1) k_mid(PcbOp op, PcbCols cols
 #endif
         pcb_cp_wait<0>();
         __syncwarp();
-        // ---- forward y on own rows: lanes = (row fastest, digit) ----
-        for (int it = lane; it < 8 * R2; it += 32) {
-            cplx* __restrict__ row = myrows + (it % 8) * LD;
-            const int n2 = it / 8, b2 = P::lin2(n2);
-            cplx v[R1];
-            PCB_UNROLL
-            for (int n1 = 0; n1 < R1; ++n1) v[n1] = row[P::wrap(P::lin1(n1) + b2)];
-            Dft<R1, -1>::run(v);
-            PCB_UNROLL
-            for (int k1 = 0; k1 < R1; ++k1) {
-                cplx val = v[k1];
-                if (!P::PFA && k1 > 0) val = cmul(val, __ldg(tw + k1 * R2 + n2));
-                row[P::wrap(P::lin1(k1) + b2)] = val;
+        if (FWD) {
+            // ---- forward y on own rows: lanes = (row fastest, digit) ----
+            for (int it = lane; it < 8 * R2; it += 32) {
+                cplx* __restrict__ row = myrows + (it % 8) * LD;
+                const int n2 = it / 8, b2 = P::lin2(n2);
+                cplx v[R1];
+                PCB_UNROLL
+                for (int n1 = 0; n1 < R1; ++n1) v[n1] = row[P::wrap(P::lin1(n1) + b2)];
+                Dft<R1, -1>::run(v);
+                PCB_UNROLL
+                for (int k1 = 0; k1 < R1; ++k1) {
+                    cplx val = v[k1];
+                    if (!P::PFA && k1 > 0) val = cmul(val, __ldg(tw + k1 * R2 + n2));
+                    row[P::wrap(P::lin1(k1) + b2)] = val;
+                }
             }
-        }
-        __syncwarp();
-        for (int it = lane; it < 8 * R1; it += 32) {
-            cplx* __restrict__ row = myrows + (it % 8) * LD;
-            const int k1 = it / 8, b1 = P::lin1(k1);
-            cplx v[R2];
-            PCB_UNROLL
-            for (int n2 = 0; n2 < R2; ++n2) v[n2] = row[P::wrap(b1 + P::lin2(n2))];
-            Dft<R2, -1>::run(v);
-            PCB_UNROLL
-            for (int k2 = 0; k2 < R2; ++k2) row[P::wrap(b1 + P::lin2(k2))] = v[k2];
+            __syncwarp();
+            for (int it = lane; it < 8 * R1; it += 32) {
+                cplx* __restrict__ row = myrows + (it % 8) * LD;
+                const int k1 = it / 8, b1 = P::lin1(k1);
+                cplx v[R2];
+                PCB_UNROLL
+                for (int n2 = 0; n2 < R2; ++n2) v[n2] = row[P::wrap(b1 + P::lin2(n2))];
+                Dft<R2, -1>::run(v);
+                PCB_UNROLL
+                for (int k2 = 0; k2 < R2; ++k2) row[P::wrap(b1 + P::lin2(k2))] = v[k2];
+            }
         }
         __syncthreads();
         // ---- z on own slots (columns 8w .. 8w+7): lanes = (slot fastest, digit) ----
         cplx* __restrict__ mycols = pl + 8 * warp;
-        for (int it = lane; it < 8 * R2; it += 32) {
-            cplx* __restrict__ cp = mycols + it % 8;
-            const int n2 = it / 8, b2 = P::lin2(n2);
-            cplx v[R1];
-            PCB_UNROLL
-            for (int n1 = 0; n1 < R1; ++n1) v[n1] = cp[P::wrap(P::lin1(n1) + b2) * LD];
-            Dft<R1, -1>::run(v);
-            PCB_UNROLL
-            for (int k1 = 0; k1 < R1; ++k1) {
-                cplx val = v[k1];
-                if (!P::PFA && k1 > 0) val = cmul(val, __ldg(tw + k1 * R2 + n2));
-                cp[P::wrap(P::lin1(k1) + b2) * LD] = val;
-            }
-        }
-        __syncwarp();
-        PCB_UNROLL
-        for (int q = 0; q < ZI; ++q) {
-            const int it = lane + 32 * q;
-            if (it >= 8 * R1) break;
-            cplx* __restrict__ cp = mycols + it % 8;
-            const int k1 = it / 8, b1 = P::lin1(k1);
-            cplx v[R2];
-            PCB_UNROLL
-            for (int n2 = 0; n2 < R2; ++n2) v[n2] = cp[P::wrap(b1 + P::lin2(n2)) * LD];
-            Dft<R2, -1>::run(v);
-            if (DIEL == 1) {
-                const double scl = op.ediag[c];
-                const unsigned w = mbits[q];
+        if (FWD) {
+            for (int it = lane; it < 8 * R2; it += 32) {
+                cplx* __restrict__ cp = mycols + it % 8;
+                const int n2 = it / 8, b2 = P::lin2(n2);
+                cplx v[R1];
                 PCB_UNROLL
-                for (int k2 = 0; k2 < R2; ++k2) v[k2] = cscale(v[k2], ((w >> k2) & 1u) ? scl : 1.0);   // branch-free: no divergence
+                for (int n1 = 0; n1 < R1; ++n1) v[n1] = cp[P::wrap(P::lin1(n1) + b2) * LD];
+                Dft<R1, -1>::run(v);
+                PCB_UNROLL
+                for (int k1 = 0; k1 < R1; ++k1) {
+                    cplx val = v[k1];
+                    if (!P::PFA && k1 > 0) val = cmul(val, __ldg(tw + k1 * R2 + n2));
+                    cp[P::wrap(P::lin1(k1) + b2) * LD] = val;
+                }
             }
-            Dft<R2, +1>::run(v);
+            __syncwarp();
+        }
+        if (HALF == 0 && DIEL != 2) {
+            // forward radix R2 (-> real space), M, inverse radix R2: the values stay in registers
             PCB_UNROLL
-            for (int n2 = 0; n2 < R2; ++n2) {
-                cplx val = v[n2];
-                if (!P::PFA && k1 > 0) { const cplx t = __ldg(tw + k1 * R2 + n2); val = cmul(val, cmake(t.x, -t.y)); }
-                cp[P::wrap(b1 + P::lin2(n2)) * LD] = val;
+            for (int q = 0; q < ZI; ++q) {
+                const int it = lane + 32 * q;
+                if (it >= 8 * R1) break;
+                cplx* __restrict__ cp = mycols + it % 8;
+                const int k1 = it / 8, b1 = P::lin1(k1);
+                cplx v[R2];
+                PCB_UNROLL
+                for (int n2 = 0; n2 < R2; ++n2) v[n2] = cp[P::wrap(b1 + P::lin2(n2)) * LD];
+                Dft<R2, -1>::run(v);
+                if (DIEL == 1) {
+                    const double scl = op.ediag[c];
+                    const unsigned w = mbits[q];
+                    PCB_UNROLL
+                    for (int k2 = 0; k2 < R2; ++k2) v[k2] = cscale(v[k2], ((w >> k2) & 1u) ? scl : 1.0);   // branch-free: no divergence
+                }
+                Dft<R2, +1>::run(v);
+                PCB_UNROLL
+                for (int n2 = 0; n2 < R2; ++n2) {
+                    cplx val = v[n2];
+                    if (!P::PFA && k1 > 0) { const cplx t = __ldg(tw + k1 * R2 + n2); val = cmul(val, cmake(t.x, -t.y)); }
+                    cp[P::wrap(b1 + P::lin2(n2)) * LD] = val;
+                }
+            }
+        } else {
+            if (FWD) {       // (A) forward radix R2 (-> real space) and the diagonal of M
+                PCB_UNROLL
+                for (int q = 0; q < ZI; ++q) {
+                    const int it = lane + 32 * q;
+                    if (it >= 8 * R1) break;
+                    cplx* __restrict__ cp = mycols + it % 8;
+                    const int b1 = P::lin1(it / 8);
+                    cplx v[R2];
+                    PCB_UNROLL
+                    for (int n2 = 0; n2 < R2; ++n2) v[n2] = cp[P::wrap(b1 + P::lin2(n2)) * LD];
+                    Dft<R2, -1>::run(v);
+                    if (DIEL == 2) {
+                        const double scl = op.ediag[c];
+                        const unsigned w = mbits[q];
+                        PCB_UNROLL
+                        for (int k2 = 0; k2 < R2; ++k2) v[k2] = cscale(v[k2], ((w >> k2) & 1u) ? scl : 1.0);
+                    }
+                    PCB_UNROLL
+                    for (int k2 = 0; k2 < R2; ++k2) cp[P::wrap(b1 + P::lin2(k2)) * LD] = v[k2];
+                }
+            }
+#ifndef PCB_EMU
+            if (DIEL == 2) {   // (B) off-diagonal terms at the coupled points of this CTA's third of the rows
+                pcb_cluster_sync();
+                const int r0 = (crank * N) / 3, r1 = ((crank + 1) * N) / 3;
+                const unsigned char* __restrict__ mp = op.maskp + (long long)i0 * N * N + r0 * N;
+                for (int e = threadIdx.x; e < (r1 - r0) * N; e += N / 8 * 32) {
+                    const unsigned mk = __ldg(mp + e);
+                    if (mk & 8u) {
+                        const unsigned off = (unsigned)(((r0 + e / N) * LD + e % N) * (int)sizeof(cplx));
+                        const cplx u0 = pcb_ld_cluster(pbase[0] + off), u1 = pcb_ld_cluster(pbase[1] + off), u2 = pcb_ld_cluster(pbase[2] + off);
+                        const cplx v0 = cscale(u0, (mk & 1u) ? inv_d[0] : 1.0), v1 = cscale(u1, (mk & 2u) ? inv_d[1] : 1.0),
+                                   v2 = cscale(u2, (mk & 4u) ? inv_d[2] : 1.0);
+                        pcb_st_cluster(pbase[0] + off, cfma(op.eoff[0], v1, cfma(op.eoff[1], v2, u0)));
+                        pcb_st_cluster(pbase[1] + off, cfmac(op.eoff[0], v0, cfma(op.eoff[2], v2, u1)));
+                        pcb_st_cluster(pbase[2] + off, cfmac(op.eoff[1], v0, cfmac(op.eoff[2], v1, u2)));
+                    }
+                }
+                pcb_cluster_sync();
+            }
+#endif
+            if (INV) {       // (C) inverse radix R2
+                PCB_UNROLL
+                for (int q = 0; q < ZI; ++q) {
+                    const int it = lane + 32 * q;
+                    if (it >= 8 * R1) break;
+                    cplx* __restrict__ cp = mycols + it % 8;
+                    const int k1 = it / 8, b1 = P::lin1(k1);
+                    cplx v[R2];
+                    PCB_UNROLL
+                    for (int k2 = 0; k2 < R2; ++k2) v[k2] = cp[P::wrap(b1 + P::lin2(k2)) * LD];
+                    Dft<R2, +1>::run(v);
+                    PCB_UNROLL
+                    for (int n2 = 0; n2 < R2; ++n2) {
+                        cplx val = v[n2];
+                        if (!P::PFA && k1 > 0) { const cplx t = __ldg(tw + k1 * R2 + n2); val = cmul(val, cmake(t.x, -t.y)); }
+                        cp[P::wrap(b1 + P::lin2(n2)) * LD] = val;
+                    }
+                }
             }
         }
-        __syncwarp();
-        for (int it = lane; it < 8 * R2; it += 32) {
-            cplx* __restrict__ cp = mycols + it % 8;
-            const int n2 = it / 8, b2 = P::lin2(n2);
-            cplx v[R1];
-            PCB_UNROLL
-            for (int k1 = 0; k1 < R1; ++k1) v[k1] = cp[P::wrap(P::lin1(k1) + b2) * LD];
-            Dft<R1, +1>::run(v);
-            PCB_UNROLL
-            for (int n1 = 0; n1 < R1; ++n1) cp[P::wrap(P::lin1(n1) + b2) * LD] = v[n1];
+        if (INV) {
+            __syncwarp();
+            for (int it = lane; it < 8 * R2; it += 32) {
+                cplx* __restrict__ cp = mycols + it % 8;
+                const int n2 = it / 8, b2 = P::lin2(n2);
+                cplx v[R1];
+                PCB_UNROLL
+                for (int k1 = 0; k1 < R1; ++k1) v[k1] = cp[P::wrap(P::lin1(k1) + b2) * LD];
+                Dft<R1, +1>::run(v);
+                PCB_UNROLL
+                for (int n1 = 0; n1 < R1; ++n1) cp[P::wrap(P::lin1(n1) + b2) * LD] = v[n1];
+            }
         }
         __syncthreads();
-        // ---- inverse y on own rows, then store them ----
-        for (int it = lane; it < 8 * R1; it += 32) {
-            cplx* __restrict__ row = myrows + (it % 8) * LD;
-            const int k1 = it / 8, b1 = P::lin1(k1);
-            cplx v[R2];
-            PCB_UNROLL
-            for (int k2 = 0; k2 < R2; ++k2) v[k2] = row[P::wrap(b1 + P::lin2(k2))];
-            Dft<R2, +1>::run(v);
-            PCB_UNROLL
-            for (int n2 = 0; n2 < R2; ++n2) {
-                cplx val = v[n2];
-                if (!P::PFA && k1 > 0) { const cplx t = __ldg(tw + k1 * R2 + n2); val = cmul(val, cmake(t.x, -t.y)); }
-                row[P::wrap(b1 + P::lin2(n2))] = val;
+        if (INV) {
+            // ---- inverse y on own rows ----
+            for (int it = lane; it < 8 * R1; it += 32) {
+                cplx* __restrict__ row = myrows + (it % 8) * LD;
+                const int k1 = it / 8, b1 = P::lin1(k1);
+                cplx v[R2];
+                PCB_UNROLL
+                for (int k2 = 0; k2 < R2; ++k2) v[k2] = row[P::wrap(b1 + P::lin2(k2))];
+                Dft<R2, +1>::run(v);
+                PCB_UNROLL
+                for (int n2 = 0; n2 < R2; ++n2) {
+                    cplx val = v[n2];
+                    if (!P::PFA && k1 > 0) { const cplx t = __ldg(tw + k1 * R2 + n2); val = cmul(val, cmake(t.x, -t.y)); }
+                    row[P::wrap(b1 + P::lin2(n2))] = val;
+                }
             }
+            __syncwarp();
+            for (int it = lane; it < 8 * R2; it += 32) {
+                cplx* __restrict__ row = myrows + (it % 8) * LD;
+                const int n2 = it / 8, b2 = P::lin2(n2);
+                cplx v[R1];
+                PCB_UNROLL
+                for (int k1 = 0; k1 < R1; ++k1) v[k1] = row[P::wrap(P::lin1(k1) + b2)];
+                Dft<R1, +1>::run(v);
+                PCB_UNROLL
+                for (int n1 = 0; n1 < R1; ++n1) row[P::wrap(P::lin1(n1) + b2)] = v[n1];
+            }
+            __syncwarp();
         }
-        __syncwarp();
-        for (int it = lane; it < 8 * R2; it += 32) {
-            cplx* __restrict__ row = myrows + (it % 8) * LD;
-            const int n2 = it / 8, b2 = P::lin2(n2);
-            cplx v[R1];
-            PCB_UNROLL
-            for (int k1 = 0; k1 < R1; ++k1) v[k1] = row[P::wrap(P::lin1(k1) + b2)];
-            Dft<R1, +1>::run(v);
-            PCB_UNROLL
-            for (int n1 = 0; n1 < R1; ++n1) row[P::wrap(P::lin1(n1) + b2)] = v[n1];
-        }
-        __syncwarp();
+        // ---- store own rows ----
 #ifndef PCB_EMU
         if (TMA) {
             pcb_fence_async_smem();                         // the rows were written through the generic proxy
@@ -808,6 +926,26 @@ __global__ void __launch_bounds__(P::N / 8 * 32, 1) k_mid(PcbOp op, PcbCols cols
 #endif
 }
 
+// Plane-mode set-up for the coupled dielectric: the byte mask (bit c: edge DoF of component c, bit 3: volume DoF in Omega_1)
+// in the slot order of the plane pass, maskp[i0][row][col] = mask(i0, i1 = coord(col), i2 = coord(row)).
+template <class P>
+__global__ void k_mask_plane(PcbOp op, unsigned char* __restrict__ out) {
+    constexpr int N = P::N;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)N * N * N) return;
+    const int col = (int)(t % N), row = (int)((t / N) % N), i0 = (int)(t / ((long long)N * N));
+    out[t] = op.mask[((long long)P::coord(row) * N + P::coord(col)) * N + i0];
+}
+// slot <-> index tables of the plan: tab[s] = coord(s), tab[N + coord(s)] = s  (the real-space stencil on plane-slot order)
+template <class P>
+__global__ void k_coord_tables(int* __restrict__ tab) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= P::N) return;
+    const int i = P::coord(s);
+    tab[s] = i;
+    tab[P::N + i] = s;
+}
+
 // ---------------------------------------------------------------------------------------
 // Launch table: one entry per supported grid size, filled by the per-size translation units.
 // ---------------------------------------------------------------------------------------
@@ -815,6 +953,7 @@ struct PcbOpLaunch {
     int N;
     int r1, r2;
     int plane_mode;   // 1: the fused (i1,i2)-plane pass exists for this size (N % 8 == 0 and the plane fits in shared memory)
+    int plane_coupled; // 1: ... also for the coupled 3x3 dielectric (clusters of three CTAs; CUDA build only)
     // mode: 0 plain 3-D FFT forward, 1 plain inverse (1/N^3), 2 A = AMA^H, 3 H = AMA^H + gamma B^H B + shift
     int (*apply)(const PcbOp& op, const PcbCols& cols, int ncols, int mode, const cplx* tw, cudaStream_t s, int sms);
     // split passes used by the cross-DoF dielectric and by the tests: pass ids below
@@ -824,6 +963,8 @@ enum { PCB_PASS_XFWD_SYM = 0, PCB_PASS_XFWD = 1, PCB_PASS_YFWD = 2, PCB_PASS_ZFW
        PCB_PASS_YINV = 5, PCB_PASS_XINV = 6, PCB_PASS_XINV_A = 7, PCB_PASS_XINV_H = 8, PCB_PASS_ZMID = 9,
        // plane mode (three passes, transposed scratch columns in cols.wrk)
        PCB_PASS_XFWD_SYM_T = 10, PCB_PASS_MID = 11, PCB_PASS_XINV_A_T = 12, PCB_PASS_XINV_H_T = 13,
-       PCB_PASS_MASKBITS = 14 /* set-up: op.mask -> (unsigned*)op.mbits */ };
+       PCB_PASS_MASKBITS = 14 /* set-up: op.mask -> (unsigned*)op.mbits */,
+       PCB_PASS_MID_FWD = 15, PCB_PASS_MID_INV = 16 /* halves of the plane pass around the cross-DoF stencil */,
+       PCB_PASS_MASKPLANE = 17 /* set-up: op.mask -> (unsigned char*)op.maskp */, PCB_PASS_COORDTAB = 18 /* set-up: (int*)op.ctab */ };
 
 const PcbOpLaunch* pcb_find_plan(int N);

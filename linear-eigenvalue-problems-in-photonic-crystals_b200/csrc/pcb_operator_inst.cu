@@ -73,6 +73,11 @@ inline int ctas_per_sm(int smem, int regs_hint_threads) {
 // plane mode: N % 8 == 0, tiles of 8 rows must not straddle an i2 plane, and N x (N+1) complex fit in one CTA's shared memory
 constexpr bool kPlane = (P::N % 8 == 0) && (LX == 8) && ((long long)P::N * (P::N + 1) * 16 <= 232448);
 constexpr int kSmemMid = P::N * (P::N + 1) * (int)sizeof(cplx);
+#ifdef PCB_EMU
+constexpr bool kPlaneCoupled = false;      // thread-block clusters are not emulated: the coupled dielectric keeps the five-pass path there
+#else
+constexpr bool kPlaneCoupled = kPlane && P::N % 3 == 0 && kSmemMid + 128 <= 232448;
+#endif
 constexpr int kStageXT = 3 * LX * (P::R1 * P::R2P + 1) * (int)sizeof(cplx);
 
 constexpr int GX = (P::N * P::N + LX - 1) / LX;          // x tiles per column
@@ -95,6 +100,62 @@ struct PlanePass<true, PP> {
             PCB_CUDA_OK(cudaGetLastError());
             return 0;
         }
+        if (pass_id == PCB_PASS_MASKPLANE) {
+            const long long total = (long long)PP::N * PP::N * PP::N;
+            PCB_LAUNCH((k_mask_plane<PP>), dim3((unsigned)((total + 255) / 256), 1, 1), dim3(256, 1, 1), 0, s, op, const_cast<unsigned char*>(op.maskp));
+            PCB_CUDA_OK(cudaGetLastError());
+            return 0;
+        }
+        if (pass_id == PCB_PASS_COORDTAB) {
+            PCB_LAUNCH((k_coord_tables<PP>), dim3((unsigned)((PP::N + 127) / 128), 1, 1), dim3(128, 1, 1), 0, s, const_cast<int*>(op.ctab));
+            PCB_CUDA_OK(cudaGetLastError());
+            return 0;
+        }
+        constexpr bool kTma = kSmemMid + 128 <= 232448;
+        if (pass_id == PCB_PASS_MID_FWD || pass_id == PCB_PASS_MID_INV) {      // halves of the plane pass (cross-DoF dielectric)
+#ifndef PCB_EMU
+            if (kTma) {
+                if (pass_id == PCB_PASS_MID_FWD) PCB_GO_P((k_mid<PP, 0, 1, 1>), (PP::N / 8 * 32), 3 * PP::N, kSmemMid + 128, 1);
+                else PCB_GO_P((k_mid<PP, 0, 1, 2>), (PP::N / 8 * 32), 3 * PP::N, kSmemMid + 128, 1);
+                return 0;
+            }
+#endif
+            if (pass_id == PCB_PASS_MID_FWD) PCB_GO_P((k_mid<PP, 0, 0, 1>), (PP::N / 8 * 32), 3 * PP::N, kSmemMid, 1);
+            else PCB_GO_P((k_mid<PP, 0, 0, 2>), (PP::N / 8 * 32), 3 * PP::N, kSmemMid, 1);
+            return 0;
+        }
+#ifndef PCB_EMU
+        if (pass_id == PCB_PASS_MID && op.diel == PCB_DIEL_TRIVIAL) {
+            // coupled 3x3 M: clusters of three CTAs (one component each) exchanging the coupled points through DSMEM
+            static_assert(!kPlaneCoupled || kTma, "the cluster form of the plane pass uses the TMA row copies");
+            auto kfn = k_mid<PP, 2, 1>;
+            const int smem = kSmemMid + 128;
+            if (set_smem(kfn, smem)) return -1;
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof cfg);
+            cudaLaunchAttribute at;
+            at.id = cudaLaunchAttributeClusterDimension;
+            at.val.clusterDim.x = 3; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+            cfg.blockDim = dim3(PP::N / 8 * 32, 1, 1);
+            cfg.dynamicSmemBytes = (size_t)smem;
+            cfg.stream = s;
+            cfg.attrs = &at; cfg.numAttrs = 1;
+            static int max_clusters = 0;      // co-resident clusters of this kernel (one 3-CTA cluster needs three free SMs of one GPC)
+            if (max_clusters == 0) {
+                cfg.gridDim = dim3(3 * 148, 1, 1);
+                PCB_CUDA_OK(cudaOccupancyMaxActiveClusters(&max_clusters, kfn, &cfg));
+                if (const char* ev = getenv("PCB200_MID_CLUSTERS")) { const int v = atoi(ev); if (v >= 1 && v < max_clusters) max_clusters = v; }
+                if (max_clusters < 1) { pcb_set_error("plane mode: no 3-CTA cluster of k_mid fits on this device"); max_clusters = 0; return -1; }
+            }
+            long long ncl = max_clusters;
+            const long long tot = (long long)PP::N * ncols;
+            if (ncl > tot) ncl = tot;
+            cfg.gridDim = dim3((unsigned)(3 * ncl), 1, 1);
+            PCB_CUDA_OK(cudaLaunchKernelEx(&cfg, kfn, op, cols, tw, ncols));
+            PCB_CUDA_OK(cudaGetLastError());
+            return 0;
+        }
+#endif
         if (pass_id == PCB_PASS_XFWD_SYM_T) PCB_GO((k_xfwd<PP, LX, NT, 1, 1>), GX, kStageXT);
         else if (pass_id == PCB_PASS_XINV_A_T) PCB_GO((k_xinv<PP, LX, NT, 1, 1>), GX, kStageXT);
         else if (pass_id == PCB_PASS_XINV_H_T) PCB_GO((k_xinv<PP, LX, NT, 2, 1>), GX, kStageXT);
@@ -132,6 +193,7 @@ int run_pass(const PcbOp& op, const PcbCols& cols, int ncols, int pass_id, const
             else { pcb_set_error("zmid: dielectric type %d has no fused z pass", op.diel); return -1; }
             break;
         case PCB_PASS_XFWD_SYM_T: case PCB_PASS_MID: case PCB_PASS_XINV_A_T: case PCB_PASS_XINV_H_T: case PCB_PASS_MASKBITS:
+        case PCB_PASS_MID_FWD: case PCB_PASS_MID_INV: case PCB_PASS_MASKPLANE: case PCB_PASS_COORDTAB:
             return PlanePass<kPlane, P>::go(op, cols, ncols, pass_id, tw, s, sms);
         default: pcb_set_error("unknown pass id %d", pass_id); return -1;
     }
@@ -161,4 +223,4 @@ int run_apply(const PcbOp& op, const PcbCols& cols, int ncols, int mode, const c
 
 #define PCB_CAT2(a, b) a##b
 #define PCB_CAT(a, b) PCB_CAT2(a, b)
-extern const PcbOpLaunch PCB_CAT(pcb_plan_, PCB_N) = {PCB_N, PCB_R1, PCB_R2, kPlane ? 1 : 0, run_apply, run_pass};
+extern const PcbOpLaunch PCB_CAT(pcb_plan_, PCB_N) = {PCB_N, PCB_R1, PCB_R2, kPlane ? 1 : 0, kPlaneCoupled ? 1 : 0, run_apply, run_pass};
