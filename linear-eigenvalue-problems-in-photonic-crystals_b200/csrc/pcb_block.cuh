@@ -578,6 +578,71 @@ __global__ void __launch_bounds__(256) k_diel_crossdof(PcbOp op, PcbStencil st, 
     for (int c = 0; c < 3; ++c) Y[c * nn + p] = y[c];
 }
 
+// The same operator on the PLANE-SLOT layout of the plane pass (pcb_operator.cuh): columns hold W'[c][i0][row][col] with the
+// real-space point (i0, i1 = coord(col), i2 = coord(row)); ctab = slot -> index and index -> slot tables of the plan.  Reads
+// cols.wrk (output of the forward half of the plane pass), writes cols.out (input of the inverse half).  For the Good-Thomas
+// plans (N = 72, 120) coord is multiplication by a constant mod N, so a +-1 neighbour along i1 is a constant slot shift and the
+// gathers of a warp (lanes along col) stay contiguous.
+template <int K>
+__global__ void __launch_bounds__(256) k_diel_crossdof_t(PcbOp op, PcbStencil st, PcbCols cols) {
+    const int N = op.N;
+    const long long nn = op.nn;
+    const long long pt = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // position in the slot layout
+    if (pt >= nn) return;
+    const cplx* __restrict__ X = cols.wrk[blockIdx.y];
+    cplx* __restrict__ Y = cols.out[blockIdx.y];
+    const int* __restrict__ ctab = op.ctab;
+    const int scol = (int)(pt % N), srow = (int)((pt / N) % N);
+    const int i[3] = {(int)(pt / ((long long)N * N)), __ldg(ctab + scol), __ldg(ctab + srow)};
+    const long long p = i[0] + (long long)N * (i[1] + (long long)N * i[2]);       // natural index (mask)
+    const unsigned mp = __ldg(op.mask + p);
+    cplx y[3];
+    PCB_UNROLL
+    for (int c = 0; c < 3; ++c) y[c] = cscale(X[c * nn + pt], ((mp >> c) & 1u) ? op.ediag[c] : 1.0);
+    constexpr int PA[3] = {0, 0, 1}, PB[3] = {1, 2, 2}, CAX[3] = {2, 2, 1}, TAX[3] = {1, 0, 0};
+    const int kk = K > 0 ? K : st.k;
+    const int taps = 2 * kk;
+    PCB_UNROLL
+    for (int pr = 0; pr < 3; ++pr) {
+        const cplx e = op.eoff[pr];
+        if (e.x == 0.0 && e.y == 0.0) continue;
+        const int a = PA[pr], b = PB[pr], cax = CAX[pr], tax = TAX[pr];
+        const double Ia = (double)((mp >> a) & 1u), Ib_p = (double)((mp >> b) & 1u);
+        const cplx* __restrict__ Xa = X + a * nn;
+        const cplx* __restrict__ Xb = X + b * nn;
+        cplx sa = cmake(0.0, 0.0), sb = cmake(0.0, 0.0);
+#ifndef PCB_EMU
+#pragma unroll
+#endif
+        for (int j1 = 0; j1 < (K > 0 ? 2 * K : taps); ++j1) {
+            const int oc = 1 - kk + j1;
+#ifndef PCB_EMU
+#pragma unroll
+#endif
+            for (int j2 = 0; j2 < (K > 0 ? 2 * K : taps); ++j2) {
+                const int ot = 1 - kk + j2;
+                const double w = st.w[j1] * st.w[j2] * 0.5;
+                // q = p + oc on the c-axis, - ot on the t-axis;  p' = p - oc on the c-axis, + ot on the t-axis
+                int q[3] = {i[0], i[1], i[2]}, r[3] = {i[0], i[1], i[2]};
+                q[cax] = pcb_wrap(i[cax] + oc, N); q[tax] = pcb_wrap(i[tax] - ot, N);
+                r[cax] = pcb_wrap(i[cax] - oc, N); r[tax] = pcb_wrap(i[tax] + ot, N);
+                const long long qm = q[0] + (long long)N * (q[1] + (long long)N * q[2]);
+                const long long rm = r[0] + (long long)N * (r[1] + (long long)N * r[2]);
+                const long long qs = ((long long)q[0] * N + __ldg(ctab + N + q[2])) * N + __ldg(ctab + N + q[1]);
+                const long long rs = ((long long)r[0] * N + __ldg(ctab + N + r[2])) * N + __ldg(ctab + N + r[1]);
+                const double Ibq = (double)((__ldg(op.mask + qm) >> b) & 1u);
+                sa = cadd(sa, cscale(Xb[qs], w * (Ia + Ibq)));
+                const double Iap = (double)((__ldg(op.mask + rm) >> a) & 1u);
+                sb = cadd(sb, cscale(Xa[rs], w * (Iap + Ib_p)));
+            }
+        }
+        y[a] = cfma(e, sa, y[a]);
+        y[b] = cfmac(e, sb, y[b]);
+    }
+    PCB_UNROLL
+    for (int c = 0; c < 3; ++c) Y[c * nn + pt] = y[c];
+}
+
 // ---- stand-alone point-wise symbol multiplies (drop-in A_block / H_block kernels) ---------------------
 // MODE 0: Y = k x X (K_A, _kernels.py:43-71);  1: Y = (-conj k) x X (K_A^H, pcfft.py:148);
 // MODE 2: Y = gamma conj(k) (k . X)  (h_block with D_B = gamma*(|k_c|^2, conj(k_a) k_b), pcfft.py:176)

@@ -70,6 +70,7 @@ struct pcb_ctx {
     cudaStream_t stream = nullptr;
     const PcbOpLaunch* plan = nullptr;
     cplx* tw = nullptr;             // [R1][R2] forward twiddles exp(-2 pi i k1 n2 / N)
+    int* ctab = nullptr;            // plane mode: slot -> index and index -> slot tables of the plan (k_coord_tables)
     double* partial = nullptr;      // reduction partials (device)
     size_t partial_bytes = 0;
     void* hstage = nullptr;         // pinned host staging for small results / E matrices
@@ -82,6 +83,8 @@ struct pcb_ctx {
     long long launches = 0;
     int sms = 148;
     int use_plane = 1;              // PCB200_PLANE=0 forces the five-pass operator (A/B measurements)
+    int use_plane_coupled = 1;      // PCB200_PLANE_COUPLED=0: coupled 3x3 dielectric on the five-pass path
+    int use_plane_cross = 1;        // PCB200_PLANE_CROSS=0: cross-DoF dielectric on the split five-pass path (7 kernels)
     // pcb_apply_host pipeline: copy streams, two slots of (row-major staging in/out, planar columns in/out), events
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cplx* hp_buf = nullptr;         // one allocation: 2 slots x 4 regions of R x hp_cols elements
@@ -93,6 +96,7 @@ struct pcb_diel {
     int kind;
     unsigned char* mask;    // [nn] (padded to 4)
     unsigned* mbits;        // plane mode: per-item dielectric bit words (k_mask_bits); null when the size has no plane pass
+    unsigned char* maskp;   // plane mode, coupled dielectric: byte mask in plane-slot order (k_mask_plane); else null
     double ediag[3];
     cplx eoff[3];
     PcbStencil st;
@@ -192,6 +196,8 @@ static int ctx_create(int device, int N, int z0, int z1, pcb_ctx** out) {
     c->device = device; c->N = N; c->nn = (long long)N * N * N; c->plan = plan;
     c->z0 = z0; c->z1 = z1; c->nloc = (long long)(z1 - z0) * N * N; c->R = 3 * c->nloc;
     { const char* e = getenv("PCB200_PLANE"); c->use_plane = (plan->plane_mode && !(e && e[0] == '0')) ? 1 : 0; }
+    { const char* e = getenv("PCB200_PLANE_COUPLED"); c->use_plane_coupled = !(e && e[0] == '0'); }
+    { const char* e = getenv("PCB200_PLANE_CROSS"); c->use_plane_cross = !(e && e[0] == '0'); }
 #ifndef PCB_EMU
     cudaDeviceProp prop;
     PCB_CUDA_OK_OR(cudaGetDeviceProperties(&prop, device), delete c);
@@ -212,6 +218,14 @@ static int ctx_create(int device, int N, int z0, int z1, pcb_ctx** out) {
         }
     PCB_CUDA_OK_OR(cudaMalloc(&c->tw, sizeof(cplx) * N), pcb_ctx_destroy(c));
     PCB_CUDA_OK_OR(cudaMemcpy(c->tw, tw.data(), sizeof(cplx) * N, cudaMemcpyHostToDevice), pcb_ctx_destroy(c));
+    if (plan->plane_mode) {
+        PCB_CUDA_OK_OR(cudaMalloc(&c->ctab, sizeof(int) * 2 * N), pcb_ctx_destroy(c));
+        PcbOp tmp; memset(&tmp, 0, sizeof tmp);
+        tmp.N = N; tmp.ctab = c->ctab;
+        PcbCols none; memset(&none, 0, sizeof none);
+        if (plan->pass(tmp, none, 1, PCB_PASS_COORDTAB, c->tw, c->stream, c->sms)) { pcb_ctx_destroy(c); return -1; }
+        PCB_CUDA_OK_OR(cudaStreamSynchronize(c->stream), pcb_ctx_destroy(c));
+    }
     *out = c;
     return 0;
 }
@@ -221,6 +235,7 @@ void pcb_ctx_destroy(pcb_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->tw) cudaFree(c->tw);
+    if (c->ctab) cudaFree(c->ctab);
     if (c->partial) cudaFree(c->partial);
     if (c->dsmall) cudaFree(c->dsmall);
     if (c->scratch) cudaFree(c->scratch);
@@ -338,7 +353,7 @@ int pcb_diel_create(pcb_ctx* c, int kind, const int64_t* ind_e, long long n_e, c
     PCB_CHECK_ARG(out && kind >= PCB_DIEL_NONE && kind <= PCB_DIEL_CROSSDOF, "bad kind");
     PCB_CUDA_OK(cudaSetDevice(c->device));
     pcb_diel* d = new pcb_diel;
-    d->ctx = c; d->kind = kind; d->mask = nullptr; d->mbits = nullptr;
+    d->ctx = c; d->kind = kind; d->mask = nullptr; d->mbits = nullptr; d->maskp = nullptr;
     for (int i = 0; i < 3; ++i) { d->ediag[i] = ediag ? ediag[i] : 1.0; d->eoff[i] = eoff ? cmake(eoff[2 * i], eoff[2 * i + 1]) : cmake(0.0, 0.0); }
     d->st.k = 1; for (int i = 0; i < 8; ++i) d->st.w[i] = 0.0;
     if (kind == PCB_DIEL_CROSSDOF) {
@@ -375,6 +390,12 @@ int pcb_diel_create(pcb_ctx* c, int kind, const int64_t* ind_e, long long n_e, c
         memset(&none, 0, sizeof none);
         if (c->plan->pass(tmp, none, 1, PCB_PASS_MASKBITS, c->tw, c->stream, c->sms)) { pcb_diel_destroy(d); return -1; }
         c->launches++;
+        if (c->plan->plane_coupled && kind == PCB_DIEL_TRIVIAL) {
+            PCB_CUDA_OK_OR(cudaMalloc(&d->maskp, (size_t)c->nn), pcb_diel_destroy(d));
+            tmp.maskp = d->maskp;
+            if (c->plan->pass(tmp, none, 1, PCB_PASS_MASKPLANE, c->tw, c->stream, c->sms)) { pcb_diel_destroy(d); return -1; }
+            c->launches++;
+        }
     }
     PCB_CUDA_OK_OR(cudaStreamSynchronize(c->stream), pcb_diel_destroy(d));
     *out = d;
@@ -386,6 +407,7 @@ void pcb_diel_destroy(pcb_diel* d) {
     cudaStreamSynchronize(d->ctx->stream);
     if (d->mask) cudaFree(d->mask);
     if (d->mbits) cudaFree(d->mbits);
+    if (d->maskp) cudaFree(d->maskp);
     delete d;
 }
 
@@ -399,6 +421,8 @@ static void op_fill(pcb_op* o, double gamma, double shift, double pshift, pcb_di
     o->d.diel = diel ? diel->kind : PCB_DIEL_NONE;
     o->d.mask = diel ? diel->mask : nullptr;
     o->d.mbits = diel ? diel->mbits : nullptr;
+    o->d.maskp = diel ? diel->maskp : nullptr;
+    o->d.ctab = c->ctab;
     for (int i = 0; i < 3; ++i) {
         o->d.ediag[i] = diel ? diel->ediag[i] : 1.0;
         o->d.eoff[i] = diel ? diel->eoff[i] : cmake(0.0, 0.0);
@@ -450,6 +474,32 @@ static int launch_crossdof(pcb_op* o, int kc, const cplx* const* X, cplx* const*
     return 0;
 }
 
+// the same on the plane-slot layout: cols.wrk -> cols.out (between the halves of the plane pass)
+static int launch_crossdof_t(pcb_op* o, int kc, const PcbCols& cols) {
+    pcb_ctx* c = o->ctx;
+    dim3 grid((unsigned)((c->nn + 255) / 256), (unsigned)kc, 1);
+    if (o->diel->st.k == 1) PCB_LAUNCH(k_diel_crossdof_t<1>, grid, dim3(256, 1, 1), 0, c->stream, o->d, o->diel->st, cols);
+    else if (o->diel->st.k == 2) PCB_LAUNCH(k_diel_crossdof_t<2>, grid, dim3(256, 1, 1), 0, c->stream, o->d, o->diel->st, cols);
+    else PCB_LAUNCH(k_diel_crossdof_t<0>, grid, dim3(256, 1, 1), 0, c->stream, o->d, o->diel->st, cols);
+    PCB_CUDA_OK(cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
+// Pass structure of an A / H apply: 0 plane mode (3 passes), 1 five passes, 2 five passes split around the
+// cross-DoF stencil (7 kernels), 3 plane mode split around the stencil on the slot layout (5 kernels)
+enum { PCB_STRUCT_PLANE = 0, PCB_STRUCT_FIVE = 1, PCB_STRUCT_CROSS7 = 2, PCB_STRUCT_CROSS5 = 3 };
+static int apply_structure(const pcb_op* o) {
+    const pcb_ctx* c = o->ctx;
+    const int diel = o->d.diel;
+    if (c->use_plane) {
+        if (diel == PCB_DIEL_NONE || diel == PCB_DIEL_CHIRAL) return PCB_STRUCT_PLANE;
+        if (diel == PCB_DIEL_TRIVIAL && c->plan->plane_coupled && c->use_plane_coupled) return PCB_STRUCT_PLANE;
+        if (diel == PCB_DIEL_CROSSDOF && c->use_plane_cross) return PCB_STRUCT_CROSS5;
+    }
+    return diel == PCB_DIEL_CROSSDOF ? PCB_STRUCT_CROSS7 : PCB_STRUCT_FIVE;
+}
+
 int pcb_apply(pcb_op* o, int mode, int ncols, const void* const* in, void* const* out) {
     PCB_CHECK_ARG(o && in && out && ncols > 0, "bad arguments");
     pcb_ctx* c = o->ctx;
@@ -474,21 +524,33 @@ int pcb_apply(pcb_op* o, int mode, int ncols, const void* const* in, void* const
                 break;
             case PCB_APPLY_A: case PCB_APPLY_H: {
                 const int last = (mode == PCB_APPLY_A) ? PCB_PASS_XINV_A : PCB_PASS_XINV_H;
-                const bool plane = c->use_plane && (o->d.diel == PCB_DIEL_NONE || o->d.diel == PCB_DIEL_CHIRAL);
-                if (mode == PCB_APPLY_H && !plane)
+                const int last_t = (mode == PCB_APPLY_A) ? PCB_PASS_XINV_A_T : PCB_PASS_XINV_H_T;
+                const int st = apply_structure(o);
+                if ((mode == PCB_APPLY_H && st != PCB_STRUCT_PLANE) || st == PCB_STRUCT_CROSS5)
                     for (int j = 0; j < kc; ++j)
                         if (cols.in[j] == cols.out[j]) {
-                            pcb_set_error("pcb_apply(PCB_APPLY_H): in[%d] == out[%d]; the last pass re-reads X, use distinct columns", j0 + j, j0 + j);
+                            pcb_set_error("pcb_apply: in[%d] == out[%d]; this pass structure re-reads X / uses out as work space, use distinct columns", j0 + j, j0 + j);
                             return -2;
                         }
-                if (plane) {
+                if (st == PCB_STRUCT_PLANE) {
                     // three passes: x forward -> transposed scratch, fused y/z/M/z/y on (i1,i2) planes, x inverse -> out
                     if (ensure_scratch(c, sizeof(cplx) * (size_t)c->R * (size_t)kc)) return -1;
                     for (int j = 0; j < kc; ++j) cols.wrk[j] = c->scratch + (size_t)j * c->R;
-                    const int seq[3] = {PCB_PASS_XFWD_SYM_T, PCB_PASS_MID, (mode == PCB_APPLY_A) ? PCB_PASS_XINV_A_T : PCB_PASS_XINV_H_T};
+                    const int seq[3] = {PCB_PASS_XFWD_SYM_T, PCB_PASS_MID, last_t};
                     for (int i = 0; i < 3; ++i) if (pl->pass(o->d, cols, kc, seq[i], c->tw, c->stream, c->sms)) return -1;
                     c->launches += 3;
-                } else if (!cross) {
+                } else if (st == PCB_STRUCT_CROSS5) {
+                    // x forward -> scratch, forward half of the plane pass in place, stencil scratch -> out (slot layout),
+                    // inverse half out -> scratch, x inverse scratch -> out
+                    if (ensure_scratch(c, sizeof(cplx) * (size_t)c->R * (size_t)kc)) return -1;
+                    for (int j = 0; j < kc; ++j) cols.wrk[j] = c->scratch + (size_t)j * c->R;
+                    if (pl->pass(o->d, cols, kc, PCB_PASS_XFWD_SYM_T, c->tw, c->stream, c->sms)) return -1;
+                    if (pl->pass(o->d, cols, kc, PCB_PASS_MID_FWD, c->tw, c->stream, c->sms)) return -1;
+                    if (launch_crossdof_t(o, kc, cols)) return -1;
+                    if (pl->pass(o->d, cols, kc, PCB_PASS_MID_INV, c->tw, c->stream, c->sms)) return -1;
+                    if (pl->pass(o->d, cols, kc, last_t, c->tw, c->stream, c->sms)) return -1;
+                    c->launches += 4;   // + the stencil launch counted in launch_crossdof_t
+                } else if (st == PCB_STRUCT_FIVE) {
                     const int seq[5] = {PCB_PASS_XFWD_SYM, PCB_PASS_YFWD, PCB_PASS_ZMID, PCB_PASS_YINV, last};
                     for (int i = 0; i < 5; ++i) if (pl->pass(o->d, cols, kc, seq[i], c->tw, c->stream, c->sms)) return -1;
                     c->launches += 5;
@@ -546,29 +608,40 @@ int pcb_apply(pcb_op* o, int mode, int ncols, const void* const* in, void* const
 int pcb_apply_timed(pcb_op* o, int mode, int ncols, const void* const* in, void* const* out, float* pass_ms, int* npass) {
     PCB_CHECK_ARG(o && in && out && pass_ms && npass && ncols > 0 && ncols <= PCB_MAXC, "bad arguments (ncols <= 32)");
     PCB_CHECK_ARG(mode == PCB_APPLY_A || mode == PCB_APPLY_H, "mode must be PCB_APPLY_A or PCB_APPLY_H");
-    PCB_CHECK_ARG(o->d.diel != PCB_DIEL_CROSSDOF, "not available for the cross-DoF dielectric");
     pcb_ctx* c = o->ctx;
     PCB_CUDA_OK(cudaSetDevice(c->device));
     PcbCols cols;
     for (int j = 0; j < ncols; ++j) { cols.in[j] = (const cplx*)in[j]; cols.out[j] = (cplx*)out[j]; }
-    const bool plane = c->use_plane && (o->d.diel == PCB_DIEL_NONE || o->d.diel == PCB_DIEL_CHIRAL);
-    int seq[5] = {PCB_PASS_XFWD_SYM, PCB_PASS_YFWD, PCB_PASS_ZMID, PCB_PASS_YINV, mode == PCB_APPLY_A ? PCB_PASS_XINV_A : PCB_PASS_XINV_H};
+    const int st = apply_structure(o);
+    const int last = mode == PCB_APPLY_A ? PCB_PASS_XINV_A : PCB_PASS_XINV_H, last_t = mode == PCB_APPLY_A ? PCB_PASS_XINV_A_T : PCB_PASS_XINV_H_T;
+    // kernels of the structure in launch order; -1 / -2 = the cross-DoF stencil (natural / slot layout); up to 7 entries
+    enum { STENCIL = -1, STENCIL_T = -2 };
+    int seq[7] = {PCB_PASS_XFWD_SYM, PCB_PASS_YFWD, PCB_PASS_ZMID, PCB_PASS_YINV, last, 0, 0};
     int n = 5;
-    if (plane) {
-        if (ensure_scratch(c, sizeof(cplx) * (size_t)c->R * (size_t)ncols)) return -1;
+    if (st != PCB_STRUCT_FIVE) if (ensure_scratch(c, sizeof(cplx) * (size_t)c->R * (size_t)ncols)) return -1;
+    PcbCols fwd = cols;      // CROSS7: the forward passes run on the scratch columns
+    if (st == PCB_STRUCT_PLANE) {
         for (int j = 0; j < ncols; ++j) cols.wrk[j] = c->scratch + (size_t)j * c->R;
-        seq[0] = PCB_PASS_XFWD_SYM_T; seq[1] = PCB_PASS_MID; seq[2] = mode == PCB_APPLY_A ? PCB_PASS_XINV_A_T : PCB_PASS_XINV_H_T;
-        n = 3;
+        seq[0] = PCB_PASS_XFWD_SYM_T; seq[1] = PCB_PASS_MID; seq[2] = last_t; n = 3;
+    } else if (st == PCB_STRUCT_CROSS5) {
+        for (int j = 0; j < ncols; ++j) cols.wrk[j] = c->scratch + (size_t)j * c->R;
+        seq[0] = PCB_PASS_XFWD_SYM_T; seq[1] = PCB_PASS_MID_FWD; seq[2] = STENCIL_T; seq[3] = PCB_PASS_MID_INV; seq[4] = last_t; n = 5;
+    } else if (st == PCB_STRUCT_CROSS7) {
+        for (int j = 0; j < ncols; ++j) fwd.out[j] = c->scratch + (size_t)j * c->R;
+        seq[0] = PCB_PASS_XFWD_SYM; seq[1] = PCB_PASS_YFWD; seq[2] = PCB_PASS_ZFWD; seq[3] = STENCIL; seq[4] = PCB_PASS_ZINV; seq[5] = PCB_PASS_YINV; seq[6] = last; n = 7;
     }
-    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-#define PCB_EV_FREE do { for (int q = 0; q < 6; ++q) if (ev[q]) cudaEventDestroy(ev[q]); } while (0)
-    for (int i = 0; i < 6; ++i) PCB_CUDA_OK_OR(cudaEventCreate(&ev[i]), PCB_EV_FREE);
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+#define PCB_EV_FREE do { for (int q = 0; q < 8; ++q) if (ev[q]) cudaEventDestroy(ev[q]); } while (0)
+    for (int i = 0; i < 8; ++i) PCB_CUDA_OK_OR(cudaEventCreate(&ev[i]), PCB_EV_FREE);
     PCB_CUDA_OK_OR(cudaEventRecord(ev[0], c->stream), PCB_EV_FREE);
     for (int i = 0; i < n; ++i) {
-        if (c->plan->pass(o->d, cols, ncols, seq[i], c->tw, c->stream, c->sms)) { cudaStreamSynchronize(c->stream); PCB_EV_FREE; return -1; }
+        int rc;
+        if (seq[i] == STENCIL) rc = launch_crossdof(o, ncols, fwd.out, cols.out);
+        else if (seq[i] == STENCIL_T) rc = launch_crossdof_t(o, ncols, cols);
+        else { rc = c->plan->pass(o->d, (st == PCB_STRUCT_CROSS7 && i < 3) ? fwd : cols, ncols, seq[i], c->tw, c->stream, c->sms); c->launches++; }
+        if (rc) { cudaStreamSynchronize(c->stream); PCB_EV_FREE; return -1; }
         PCB_CUDA_OK_OR(cudaEventRecord(ev[i + 1], c->stream), PCB_EV_FREE);
     }
-    c->launches += n;
     PCB_CUDA_OK_OR(cudaEventSynchronize(ev[n]), PCB_EV_FREE);
     for (int i = 0; i < n; ++i) PCB_CUDA_OK_OR(cudaEventElapsedTime(&pass_ms[i], ev[i], ev[i + 1]), PCB_EV_FREE);
     PCB_EV_FREE;

@@ -58,6 +58,11 @@ def test_symbols_vs_reference_golden(pcb, golden):
     (16, "bcc_sg", None, [0.0, 0.0, 0.0]),
     (16, "sc_curv", "pseudochiral_trivial", [np.pi, 0.0, 0.0]),   # coupled 3x3 M: five-pass path
     (12, "fcc", "chiral", [np.pi, np.pi, 0.0]),                    # N % 8 != 0: five-pass path
+    (8, "bcc_sg", "pseudochiral_crossdof", [0.3, 0.0, 2 * np.pi]),  # plane halves around the stencil on the slot layout (Cooley-Tukey slots)
+    (16, "fcc", "pseudochiral_crossdof", [np.pi, 0.0, 0.0]),
+    (24, "bcc_dg", "pseudochiral_crossdof", [np.pi, np.pi, 0.0]),   # ... Good-Thomas slots (24 = 8 x 3, like 120 = 8 x 15)
+    (24, "sc_curv", "chiral", [np.pi, np.pi, np.pi]),
+    (24, "bcc_sg", "pseudochiral_trivial", [0.0, 0.0, 0.0]),        # CUDA: clusters of three CTAs (24 % 3 == 0)
 ])
 def test_operator_vs_oracle_small(pcb, oracle, N, d_flag, typ, alpha):
     alpha = np.array(alpha, dtype=float)

@@ -31,11 +31,11 @@ for _ in range(reps):
 total = ctx.timer_stop() / reps
 out = {"N": N, "lattice": d_flag, "type": typ, "cols": m, "ms_per_block_apply": total, "op_applies_per_s": m / total * 1e3,
        "frac_of_336N3_roofline": 336.0 * N ** 3 * m / (total * 1e-3) / 6538.6e9}
-if typ != "pseudochiral_crossdof":
-    buf, npass = (C.c_float * 8)(), C.c_int()
-    acc = np.zeros(5)
-    for _ in range(5):
-        L.check(L.lib().pcb_apply_timed(H.op.h, L.APPLY_H, m, L.ptr_array(X.ptrs), L.ptr_array(Y.ptrs), buf, C.byref(npass)), "timed")
-        acc += np.array(buf[:5])
-    out["pass_ms"] = [float(v) / 5 for v in acc[:npass.value]]
+buf, npass = (C.c_float * 8)(), C.c_int()
+acc = np.zeros(8)
+for _ in range(5):
+    L.check(L.lib().pcb_apply_timed(H.op.h, L.APPLY_H, m, L.ptr_array(X.ptrs), L.ptr_array(Y.ptrs), buf, C.byref(npass)), "timed")
+    acc += np.array(buf[:8])
+out["pass_ms"] = [float(v) / 5 for v in acc[:npass.value]]
+out["env"] = {k: v for k, v in os.environ.items() if k.startswith("PCB200_") and k != "PCB200_QUIET"}
 print(json.dumps(out))
