@@ -130,6 +130,23 @@ class Dist:
             self.td.destroy_process_group()
 
 
+def ncu_traffic(n, m, npass):
+    """DRAM bytes of one launch (one m-column block apply: dram__bytes_read.sum + dram__bytes_write.sum over its passes) from the
+    newest committed `ncu --set full` summary of exactly this shape, profiles/*_ncu.json (written by tools/ncu_summary.py next to
+    the .md table).  A STATIC figure from that capture, not measured by this run: (value, "file @ commit") or (None, reason)."""
+    import glob
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu.json"))):
+        try:
+            with open(path) as f:
+                d = json.load(f)
+        except Exception:
+            continue
+        if d.get("N") == n and d.get("cols") == m and d.get("passes") == npass and d.get("dram_bytes_per_apply"):
+            best = (float(d["dram_bytes_per_apply"]), f"static, from {os.path.basename(path)} (commit {d.get('commit', '?')}): ncu dram__bytes_read.sum + dram__bytes_write.sum")
+    return best if best else (None, "no committed ncu capture of this shape")
+
+
 def fcc_alpha(pcb, rank, world):
     """k-point of this rank: first point of its contiguous chunk of the 120-point FCC path (numerical_experiments.kpath_chunks)."""
     ne = pcb.numerical_experiments
@@ -183,6 +200,169 @@ def cpu_apply_rate(n, alpha, cols, reps, warm, workers):
     return cols / (sum(times) / len(times)), times
 
 
+def build_ops_for(pcb, n, lattice, alpha, Diels):
+    mfd, ne = pcb.discretization, pcb.numerical_experiments
+    relax, pnt = mfd.set_relaxation(alpha)
+    ct = pcb.dielectric.diel_info(lattice, option="ct")
+    a_fft, b_fft = mfd.fft_blocks(n, 1, ct, alpha=alpha)
+    inv_fft = mfd.inverse_3_times_3_B(b_fft, pnt, relax[0])
+    b_fft = (pnt * b_fft[0], pnt * b_fft[1])
+    return (a_fft, b_fft, inv_fft, relax[0])
+
+
+def timed_passes(pcb, op, X, Y, m, reps=5):
+    import ctypes as C
+    L = pcb._lib
+    buf, npass = (C.c_float * 8)(), C.c_int()
+    acc = np.zeros(8)
+    for _ in range(reps):
+        L.check(L.lib().pcb_apply_timed(op.h, L.APPLY_H, m, L.ptr_array(X.ptrs), L.ptr_array(Y.ptrs), buf, C.byref(npass)), "pcb_apply_timed")
+        acc += np.array(buf[:8])
+    return [float(v) / reps for v in acc[:npass.value]]
+
+
+def paper2_dielectric_leg(pcb, ctx, n, m, steps, warmup, peak):
+    """Extra keys: the same 16-column H block apply with the Paper-2 dielectrics (BASELINE configs[2]: bcc single gyroid,
+    pseudochiral) -- the coupled 3x3 M (clusters of three CTAs in the plane pass) and the cross-DoF M (plane halves around the
+    stencil kernel).  Roofline against 336 N^3 (and 432 N^3 for the cross-DoF M, whose stencil is a pass of its own)."""
+    mfd, ne, L = pcb.discretization, pcb.numerical_experiments, pcb._lib
+    out = []
+    lattice = "bcc_sg"
+    alpha = pcb.dielectric.kpath(lattice)[0]
+    sym = build_ops_for(pcb, n, lattice, alpha, None)
+    X, Y = ctx.random_block(m, 4321), ctx.empty(m)
+    for typ in ("pseudochiral_trivial", "pseudochiral_crossdof"):
+        Diels = getattr(mfd, typ + "_handle")(n, lattice)
+        A, H, P = ne.pc_mfd_handle(sym[0], sym[1], Diels, sym[2], sym[3])
+        for _ in range(warmup):
+            H.op.apply_into(L.APPLY_H, X, Y)
+        ctx.sync()
+        ctx.timer_start()
+        for _ in range(steps):
+            H.op.apply_into(L.APPLY_H, X, Y)
+        ms = ctx.timer_stop() / steps
+        row = {"workload": f"{lattice} {typ} N={n} m={m} H block apply", "ms_per_step": ms, "op_applies_per_sec": m / ms * 1e3,
+               "pass_ms": timed_passes(pcb, H.op, X, Y, m, 3),
+               "roofline_frac_336N3": 336.0 * n ** 3 * m / (ms * 1e-3) / 1e9 / peak}
+        if typ.endswith("crossdof"):
+            row["roofline_frac_432N3"] = 432.0 * n ** 3 * m / (ms * 1e-3) / 1e9 / peak
+        out.append(row)
+        del A, H, P, Diels
+    return out
+
+
+def large_grid_leg(dist, pcb, n, nev, lattice="sc_curv", typ="chiral", check=True, apply_steps=5):
+    """Large-grid mode (BASELINE configs[4]) on all ranks of this job: ONE eigenproblem, dense phase row-sharded
+    (slab contexts), Gram pair all-reduced with NCCL, operator on whole columns through the slab exchange.  Reports the LOBPCG
+    iteration time, the exchange bandwidth over NVLink, the all-reduce latency and the agreement with a one-GPU solve."""
+    import ctypes as C
+    sh, mfd, ne, L = pcb.sharded, pcb.discretization, pcb.numerical_experiments, pcb._lib
+    uid = [sh.new_unique_id() if dist.rank == 0 else None]
+    dist.td.broadcast_object_list(uid, src=0)
+    comm = sh.SlabComm(n, dist.rank, dist.world, unique_id=uid[0])
+    alpha = np.array([np.pi, np.pi, np.pi])
+    m = nev + round(0.6 * nev)
+    sym = build_ops_for(pcb, n, lattice, alpha, None)
+    Diels = getattr(mfd, typ + "_handle")(n, lattice)
+    A, H, P = sh.pc_mfd_handle_sharded(comm, sym[0], sym[1], Diels, sym[2], sym[3])
+    x0 = comm.slab.random_block(m, 99)
+    # operator applies through the exchange (m columns over all ranks), device-timed on the slab stream
+    y0 = comm.slab.empty(m)
+    for _ in range(2):
+        H.op.apply_into(L.APPLY_H, x0, y0)
+    comm.slab.sync(); comm.full.sync()
+    dist.barrier()
+    comm.slab.timer_start()
+    for _ in range(apply_steps):
+        H.op.apply_into(L.APPLY_H, x0, y0)
+    ms_apply = dist.max(comm.slab.timer_stop() / apply_steps)
+    # the exchange alone: slabs -> whole columns on their owners
+    owners = [j % dist.world for j in range(m)]
+    win, _ = comm.work_blocks((m + dist.world - 1) // dist.world)
+    pin = [win.ptrs[j // dist.world] if owners[j] == dist.rank else 0 for j in range(m)]
+    comm.exchange(True, owners, x0, pin)
+    comm.slab.sync()
+    dist.barrier()
+    comm.slab.timer_start()
+    for _ in range(apply_steps):
+        comm.exchange(True, owners, x0, pin)
+    ms_exch = dist.max(comm.slab.timer_stop() / apply_steps)
+    col_bytes = 48.0 * n ** 3
+    moved = m * col_bytes * (dist.world - 1) / dist.world        # bytes that cross NVLink per exchange (all ranks together)
+    ar = C.c_float()
+    L.check(L.lib().pcb_comm_allreduce_timed(comm.slab.h, 2 * 96 * 96 * 2, 20, C.byref(ar)), "pcb_comm_allreduce_timed")
+    del y0
+    dist.barrier()
+    t0 = time.perf_counter()
+    lam, x, info = pcb.lobpcg.lobpcg_sep_softlock(H, P, x0, nev)
+    wall = dist.max(time.perf_counter() - t0)
+    out = {"N": n, "world": dist.world, "nev": nev, "m": m, "lattice": lattice, "type": typ,
+           "iterations": int(info[0]) if lam is not None else -1,
+           "solver_s": dist.max(float(info[1])) if lam is not None else None, "wall_s": wall,
+           "ms_per_iteration": 1e3 * float(info[1]) / max(1, int(info[0])) if lam is not None else None,
+           "H_apply_ms_per_block": ms_apply, "op_applies_per_sec": m / ms_apply * 1e3,
+           "exchange_ms": ms_exch, "exchange_GBps_aggregate": moved / (ms_exch * 1e-3) / 1e9,
+           "exchange_GBps_per_gpu_each_direction": moved / dist.world / (ms_exch * 1e-3) / 1e9,
+           "gram_allreduce_us": 1e3 * float(ar.value), "collective": "ncclAllReduce (Gram pair, norms) + grouped ncclSend/ncclRecv (slab exchange)",
+           "pipeline_chunks": sh.LG_CHUNKS}
+    if check and dist.rank == 0 and lam is not None:
+        A1, H1, P1 = ne.pc_mfd_handle(sym[0], sym[1], Diels, sym[2], sym[3])
+        x1 = comm.full.random_block(m, 99)
+        lam1, xs1, info1 = pcb.lobpcg.lobpcg_sep_softlock(H1, P1, x1, nev)
+        out["single_gpu"] = {"iterations": int(info1[0]), "solver_s": float(info1[1]),
+                             "max_rel_eig_diff": float(np.max(np.abs(lam[:nev] - lam1[:nev]) / np.abs(lam1[:nev])))}
+        del x1, xs1
+    dist.barrier()
+    del x0, x
+    comm.close()
+    return out
+
+
+def run_large_grid(args):
+    """--mode large-grid: BASELINE configs[4] shape (sc_curv, N = 256, 20 bands on 8 GPUs; pass --n / --nev for smaller boxes)."""
+    dist = Dist(args.gpus)
+    if dist.world < 2:
+        raise SystemExit("--mode large-grid needs torchrun with >= 2 ranks")
+    pcb = importlib.import_module(PKG)
+    pcb.set_device(dist.local)
+    sampler = ClockSampler(dist.local) if dist.rank == 0 else None
+    res = large_grid_leg(dist, pcb, args.n, args.nev, check=args.n <= 160, apply_steps=max(3, args.steps))
+    clocks = sampler.stop() if sampler else None
+    if dist.rank == 0:
+        line = {"metric": "op_applies_per_sec", "value": res["op_applies_per_sec"], "unit": "op-applies/s", "n_gpus": dist.world,
+                "steps": max(3, args.steps), "warmup": 2, "ms_per_step": res["H_apply_ms_per_block"], "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "mode": "large-grid",
+                "config": {"workload": f"sc_curv chiral N={args.n} m={res['m']}: ONE eigenproblem over {dist.world} GPUs (configs[4] shape), "
+                                       "H block apply through the slab exchange", "parallelism": f"rows of S/HS sharded x{dist.world}, NCCL all-reduce of the Gram pair"},
+                "large_grid": res, "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    dist.close()
+
+
+def cpu_full_baseline(n, alpha, cores):
+    """SURVEY 8(d) CPU yard-stick on the oracle port: the C1 solve (sc_curv, chiral, N = 48, 10 bands, rng(0) x0) and three LOBPCG
+    iterations at N = `n` (fcc, chiral) -- minutes of host time, so only with --cpu-full."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pc_oracle as oc
+    pcb = importlib.import_module(PKG)
+    oc.FFT_WORKERS = cores
+    out = {}
+    x0 = oc.random_x0(3 * 48 ** 3, 16, 0)
+    t0 = time.perf_counter()
+    o = oc.eigen_1p(48, "sc_curv", np.array([np.pi, np.pi, np.pi]), type="chiral", nev=10, x0=x0)
+    out["c1_solve_s"] = time.perf_counter() - t0
+    out["c1_iterations"] = int(o["info"][0])
+    a_fft, b_fft, inv_fft, shift, _ = oc.assemble_symbols(n, LATTICE, alpha)
+    ind_e = pcb.dielectric.compute_index(n, LATTICE, "edge")
+    A, H, P = oc.pc_mfd_handle(a_fft, b_fft, oc.chiral_handle(n, LATTICE, ind_e=ind_e), inv_fft, shift)
+    x0 = oc.random_x0(3 * n ** 3, 16, 1)
+    t0 = time.perf_counter()
+    oc.lobpcg_sep_softlock(H, P, x0, 10, maxiter=3)
+    out["lobpcg_3_iterations_s"] = time.perf_counter() - t0
+    out["s_per_iteration"] = out["lobpcg_3_iterations_s"] / 3
+    return out
+
+
 def run_reference(args):
     """--impl reference: the reference algorithm's CPU implementation (oracle port; the reference itself is Python+CuPy and
     cannot be imported on the GPU box) on this arm's config, all host threads, bounded sample per step."""
@@ -224,9 +404,17 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-blocks", action="store_true", help="skip the LOBPCG block-kernel micro-timings")
+    ap.add_argument("--mode", default="kpath", choices=["kpath", "large-grid"],
+                    help="kpath: the headline (one k-point per GPU, no collective); large-grid: one eigenproblem over all ranks (NCCL)")
+    ap.add_argument("--nev", type=int, default=NEV, help="bands (large-grid mode)")
+    ap.add_argument("--no-paper2", action="store_true", help="skip the Paper-2 dielectric legs")
+    ap.add_argument("--no-large-grid", action="store_true", help="N > 1: skip the large-grid (NCCL) leg")
+    ap.add_argument("--cpu-full", action="store_true", help="CPU baseline per SURVEY 8(d): also the C1 solve (N=48) and 3 LOBPCG iterations at N=120 on the host")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.mode == "large-grid":
+        return run_large_grid(args)
     args.warmup = max(args.warmup, 3)
 
     dist = Dist(args.gpus)
@@ -269,15 +457,11 @@ def main():
     value = dist.world * m * args.steps / (ms_total * 1e-3)
 
     # ---- per-pass device times -------------------------------------------------------------------------------
-    import ctypes as C
-    pass_ms = np.zeros(5)
-    reps = 5
-    buf, npass = (C.c_float * 8)(), C.c_int()
-    for _ in range(reps):
-        pcb._lib.check(pcb._lib.lib().pcb_apply_timed(op.h, pcb._lib.APPLY_H, m, pcb._lib.ptr_array(X.ptrs),
-                                                      pcb._lib.ptr_array(Y.ptrs), buf, C.byref(npass)), "pcb_apply_timed")
-        pass_ms += np.array(buf[:5])
-    pass_ms = pass_ms[:npass.value] / reps
+    pass_ms = np.array(timed_passes(pcb, op, X, Y, m, 5))
+
+    class _NP:
+        value = len(pass_ms)
+    npass = _NP()
     col_bytes = 48.0 * n ** 3            # one column, one direction
     if npass.value == 3:                  # plane mode: x forward (transposed store), fused y/z/M/z/y plane pass, x inverse
         pass_cols, names = [2, 2, 3], ["x_fwd+KAh -> W'", "y,z fwd + M + z,y inv on (i1,i2) planes", "x_inv+KA+gKB+shift"]
@@ -293,12 +477,10 @@ def main():
     # DRAM bytes of one launch (= one 16-column block apply) from ncu --set full captures of exactly these kernels and this
     # shape (dram__bytes_read.sum + dram__bytes_write.sum summed over the passes): plane mode profiles/r01_f_final_ncu.md
     # (5.487 GB read + 3.864 GB written), five-pass profiles/r01_c_final_ncu.md; null for other shapes
-    traffic = None
-    if n == 120 and m == 16:
-        traffic = 9.351e9 if npass.value == 3 else 14.51e9
+    traffic, traffic_src = ncu_traffic(n, m, npass.value)
     roofline = {"bound": "hbm", "kernel": kernel_desc,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_f_final_ncu.md (plane mode) / r01_c_final_ncu.md (five-pass)",
+                "traffic_source": traffic_src,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": B_OP_PER_N3 * n ** 3 * m,
                 "moved_bytes_per_launch": float(pass_bytes.sum()), "moved_GBps": float(pass_bytes.sum() / (ms_step * 1e-3) / 1e9)}
 
@@ -375,13 +557,24 @@ def main():
                    "k_indices": [r["k_indices"] for r in allr], "first_of_chunk": "random start (seed 1000+idx), rest warm-started"}
 
     # ---- CPU baseline (rank 0, N=1 only) --------------------------------------------------------------------------
+    # ---- Paper-2 dielectrics (extra keys) and, for N > 1, the large-grid mode with its NCCL collectives ----------------
+    paper2 = None
+    if not args.no_paper2 and n == N_GRID:
+        paper2 = paper2_dielectric_leg(pcb, ctx, n, m, max(5, min(args.steps, 20)), 3, peak)
+    large = None
+    if dist.world > 1 and not args.no_large_grid:
+        large = large_grid_leg(dist, pcb, n, NEV, check=True)
+
     cpu = None
     if dist.rank == 0 and dist.world == 1 and not args.no_cpu:
-        cores = os.cpu_count() or 1
+        th = host_threads()
+        cores = th["cores"]
         cols = 2
         rate, times = cpu_apply_rate(n, alphas[chunk[0]], cols, 3, 1, cores)
-        cpu = {"value": rate, "unit": "op-applies/s", "cores": cores, "kind": "port",
+        cpu = {"value": rate, "unit": "op-applies/s", "cores": cores, "kind": "port", "threads": th,
                "sample": f"{cols} of the {m} columns of one step, 3 timed reps after 1 warm-up (oracle AMA_BB, scipy.fft workers={cores})"}
+        if args.cpu_full:
+            cpu["survey_8d"] = cpu_full_baseline(n, alphas[chunk[0]], cores)
 
     if dist.rank == 0:
         line = {"metric": "op_applies_per_sec", "value": value, "unit": "op-applies/s", "n_gpus": dist.world, "steps": args.steps,
@@ -391,7 +584,7 @@ def main():
                            "N": n, "lattice": LATTICE, "type": DTYPE_TYPE, "cols_per_step": m, "l2": "inputs exceed L2 (1.33 GB per block)",
                            "parallelism": f"k-path sharding x{dist.world}, no collective"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-                "passes": passes, "block_kernels": blocks, "lobpcg": lob}
+                "passes": passes, "block_kernels": blocks, "lobpcg": lob, "paper2_dielectrics": paper2, "large_grid": large}
         print(json.dumps(line), flush=True)
     dist.close()
 

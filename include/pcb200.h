@@ -55,6 +55,10 @@ int pcb_ctx_create(int device, int N, pcb_ctx** ctx);
 void pcb_ctx_destroy(pcb_ctx* ctx);
 int pcb_sync(pcb_ctx* ctx);
 int pcb_launch_count(pcb_ctx* ctx, long long* n);   /* kernels launched by this context so far */
+/* stream ordering between two contexts of one process without a host sync (16 slots per context): pcb_ctx_record marks the work
+ * enqueued on ctx so far, pcb_ctx_wait makes later work of `waiter` start after that mark (the reference is single-stream) */
+int pcb_ctx_record(pcb_ctx* ctx, int slot);
+int pcb_ctx_wait(pcb_ctx* waiter, pcb_ctx* owner, int slot);
 int pcb_mem_info(pcb_ctx* ctx, size_t* free_bytes, size_t* total_bytes);
 int pcb_timer_start(pcb_ctx* ctx);                  /* CUDA event on the context's stream */
 int pcb_timer_stop(pcb_ctx* ctx, float* ms);        /* second event + synchronize + elapsed */
@@ -145,6 +149,8 @@ int pcb_comm_unique_id(void* id128);                                   /* rank 0
 int pcb_comm_init(pcb_ctx* ctx, const void* id128, int rank, int world); /* every rank: ncclCommInitRank on the slab context */
 int pcb_comm_set_host_callbacks(pcb_ctx* ctx, void* allreduce_cb, void* p2p_cb);  /* host-emu test build only */
 int pcb_comm_destroy(pcb_ctx* ctx);
+/* measurement aid: average device time (ms) of one NCCL all-reduce of `count` doubles over the communicator */
+int pcb_comm_allreduce_timed(pcb_ctx* ctx, long long count, int reps, float* ms);
 /* slab layout <-> whole columns on their owner rank, one grouped ncclSend/ncclRecv per call (see pcb_capi.cu) */
 int pcb_slab_exchange(pcb_ctx* ctx, int to_full, int ncols, const int* owners, const int* zb, void* const* slab_cols,
                       void* const* full_cols);

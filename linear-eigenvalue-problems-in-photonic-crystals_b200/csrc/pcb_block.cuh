@@ -594,8 +594,8 @@ __global__ void __launch_bounds__(256) k_diel_crossdof_t(PcbOp op, PcbStencil st
     const int* __restrict__ ctab = op.ctab;
     const int scol = (int)(pt % N), srow = (int)((pt / N) % N);
     const int i[3] = {(int)(pt / ((long long)N * N)), __ldg(ctab + scol), __ldg(ctab + srow)};
-    const long long p = i[0] + (long long)N * (i[1] + (long long)N * i[2]);       // natural index (mask)
-    const unsigned mp = __ldg(op.mask + p);
+    const unsigned char* __restrict__ maskp = op.maskp;      // the byte mask in the same slot order (k_mask_plane): coalesced
+    const unsigned mp = __ldg(maskp + pt);
     cplx y[3];
     PCB_UNROLL
     for (int c = 0; c < 3; ++c) y[c] = cscale(X[c * nn + pt], ((mp >> c) & 1u) ? op.ediag[c] : 1.0);
@@ -626,13 +626,11 @@ __global__ void __launch_bounds__(256) k_diel_crossdof_t(PcbOp op, PcbStencil st
                 int q[3] = {i[0], i[1], i[2]}, r[3] = {i[0], i[1], i[2]};
                 q[cax] = pcb_wrap(i[cax] + oc, N); q[tax] = pcb_wrap(i[tax] - ot, N);
                 r[cax] = pcb_wrap(i[cax] - oc, N); r[tax] = pcb_wrap(i[tax] + ot, N);
-                const long long qm = q[0] + (long long)N * (q[1] + (long long)N * q[2]);
-                const long long rm = r[0] + (long long)N * (r[1] + (long long)N * r[2]);
                 const long long qs = ((long long)q[0] * N + __ldg(ctab + N + q[2])) * N + __ldg(ctab + N + q[1]);
                 const long long rs = ((long long)r[0] * N + __ldg(ctab + N + r[2])) * N + __ldg(ctab + N + r[1]);
-                const double Ibq = (double)((__ldg(op.mask + qm) >> b) & 1u);
+                const double Ibq = (double)((__ldg(maskp + qs) >> b) & 1u);
                 sa = cadd(sa, cscale(Xb[qs], w * (Ia + Ibq)));
-                const double Iap = (double)((__ldg(op.mask + rm) >> a) & 1u);
+                const double Iap = (double)((__ldg(maskp + rs) >> a) & 1u);
                 sb = cadd(sb, cscale(Xa[rs], w * (Iap + Ib_p)));
             }
         }

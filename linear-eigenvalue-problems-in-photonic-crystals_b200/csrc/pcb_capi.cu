@@ -60,6 +60,7 @@ struct PcbComm {
 };
 static PcbNccl g_nccl;
 
+#define PCB_ORDER_EVENTS 16
 struct pcb_ctx {
     int device = 0;
     int N = 0;
@@ -80,6 +81,7 @@ struct pcb_ctx {
     cplx* scratch = nullptr;        // work columns (cross-DoF dielectric, block transposes)
     size_t scratch_bytes = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t order_ev[PCB_ORDER_EVENTS] = {};   // pcb_ctx_record / pcb_ctx_wait: stream ordering between contexts, created on first use
     long long launches = 0;
     int sms = 148;
     int use_plane = 1;              // PCB200_PLANE=0 forces the five-pass operator (A/B measurements)
@@ -244,6 +246,7 @@ void pcb_ctx_destroy(pcb_ctx* c) {
     if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
     if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
     for (int a = 0; a < 2; ++a) for (int b = 0; b < 4; ++b) if (c->hp_ev[a][b]) cudaEventDestroy(c->hp_ev[a][b]);
+    for (int i = 0; i < PCB_ORDER_EVENTS; ++i) if (c->order_ev[i]) cudaEventDestroy(c->order_ev[i]);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -251,6 +254,22 @@ void pcb_ctx_destroy(pcb_ctx* c) {
 }
 int pcb_sync(pcb_ctx* c) { PCB_CUDA_OK(cudaStreamSynchronize(c->stream)); PCB_CUDA_OK(cudaGetLastError()); return 0; }
 int pcb_launch_count(pcb_ctx* c, long long* n) { *n = c->launches; return 0; }
+/* Stream ordering between two contexts of one process (large-grid mode: the slab context's exchange and the full context's
+ * operator run on their own streams): pcb_ctx_record marks "everything enqueued on ctx so far" in slot idx; pcb_ctx_wait makes
+ * all LATER work of `waiter` start only after that mark.  No host synchronisation. */
+int pcb_ctx_record(pcb_ctx* c, int idx) {
+    PCB_CHECK_ARG(c && idx >= 0 && idx < PCB_ORDER_EVENTS, "bad arguments");
+    PCB_CUDA_OK(cudaSetDevice(c->device));
+    if (!c->order_ev[idx]) PCB_CUDA_OK(cudaEventCreateWithFlags(&c->order_ev[idx], cudaEventDisableTiming));
+    PCB_CUDA_OK(cudaEventRecord(c->order_ev[idx], c->stream));
+    return 0;
+}
+int pcb_ctx_wait(pcb_ctx* waiter, pcb_ctx* owner, int idx) {
+    PCB_CHECK_ARG(waiter && owner && idx >= 0 && idx < PCB_ORDER_EVENTS && owner->order_ev[idx], "bad arguments / slot never recorded");
+    PCB_CUDA_OK(cudaSetDevice(waiter->device));
+    PCB_CUDA_OK(cudaStreamWaitEvent(waiter->stream, owner->order_ev[idx], 0));
+    return 0;
+}
 int pcb_mem_info(pcb_ctx* c, size_t* f, size_t* t) { PCB_CUDA_OK(cudaSetDevice(c->device)); PCB_CUDA_OK(cudaMemGetInfo(f, t)); return 0; }
 int pcb_timer_start(pcb_ctx* c) { PCB_CUDA_OK(cudaEventRecord(c->ev0, c->stream)); return 0; }
 int pcb_timer_stop(pcb_ctx* c, float* ms) {
@@ -390,7 +409,7 @@ int pcb_diel_create(pcb_ctx* c, int kind, const int64_t* ind_e, long long n_e, c
         memset(&none, 0, sizeof none);
         if (c->plan->pass(tmp, none, 1, PCB_PASS_MASKBITS, c->tw, c->stream, c->sms)) { pcb_diel_destroy(d); return -1; }
         c->launches++;
-        if (c->plan->plane_coupled && kind == PCB_DIEL_TRIVIAL) {
+        if ((c->plan->plane_coupled && kind == PCB_DIEL_TRIVIAL) || kind == PCB_DIEL_CROSSDOF) {
             PCB_CUDA_OK_OR(cudaMalloc(&d->maskp, (size_t)c->nn), pcb_diel_destroy(d));
             tmp.maskp = d->maskp;
             if (c->plan->pass(tmp, none, 1, PCB_PASS_MASKPLANE, c->tw, c->stream, c->sms)) { pcb_diel_destroy(d); return -1; }
@@ -1003,6 +1022,23 @@ int pcb_comm_destroy(pcb_ctx* c) {
 #endif
     delete c->comm;
     c->comm = nullptr;
+    return 0;
+}
+
+/* Measurement aid: `reps` all-reduces (sum) of `count` doubles over the communicator on the context's stream, timed with CUDA
+ * events; *ms = average device time of one all-reduce (the latency the Gram pair of the large-grid mode pays per iteration). */
+int pcb_comm_allreduce_timed(pcb_ctx* c, long long count, int reps, float* ms) {
+    PCB_CHECK_ARG(c && c->comm && count > 0 && reps > 0 && ms, "bad arguments / no communicator");
+    PCB_CUDA_OK(cudaSetDevice(c->device));
+    if (ensure_dsmall(c, sizeof(double) * (size_t)count > sizeof(cplx) * 2 * PCB_MAXL * PCB_MAXL + 65536 ? sizeof(double) * (size_t)count : sizeof(cplx) * 2 * PCB_MAXL * PCB_MAXL + 65536)) return -1;
+    PCB_CUDA_OK(cudaMemsetAsync(c->dsmall, 0, sizeof(double) * (size_t)count, c->stream));
+    if (comm_allreduce(c, (double*)c->dsmall, count)) return -4;      // warm-up (first call sets up the NCCL channels)
+    PCB_CUDA_OK(cudaEventRecord(c->ev0, c->stream));
+    for (int i = 0; i < reps; ++i) if (comm_allreduce(c, (double*)c->dsmall, count)) return -4;
+    PCB_CUDA_OK(cudaEventRecord(c->ev1, c->stream));
+    PCB_CUDA_OK(cudaEventSynchronize(c->ev1));
+    PCB_CUDA_OK(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    *ms /= (float)reps;
     return 0;
 }
 

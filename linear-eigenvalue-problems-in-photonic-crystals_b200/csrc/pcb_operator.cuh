@@ -142,6 +142,12 @@ PCB_D void pcb_cluster_sync() {
 }
 #endif
 
+#ifdef PCB_EMU
+PCB_D void pcb_prefetch_l2(const void*) {}
+#else
+PCB_D void pcb_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
+#endif
+
 // ---------------------------------------------------------------------------------------
 // Pass 1: x-lines forward.  SYM: 0 plain FFT, 1 multiply by K_A^H = (-conj k) x . on load.
 // Tile = LX consecutive rows (a row = all i0 for one (i1,i2)), all three components; one CTA per tile, registers stage the
@@ -155,6 +161,8 @@ PCB_D void pcb_cluster_sync() {
 // TRN = 1 (plane mode): the output goes to the scratch column in the transposed layout W'[c][k][i2][i1] (8 consecutive i1 of
 // one k = a 128-byte segment), so that the fused y/z pass finds every (i1, i2) plane contiguous; rows get one element of
 // padding in shared memory (RS) to keep the row-fastest reads of that store pattern conflict-free.
+// (Round 2, measured and removed: every CTA asking L2 -- prefetch.global.L2 -- for the rows of the tile 296 / 592 / 1184 blocks ahead,
+// i.e. what a successor CTA on the same SM loads one CTA lifetime later: 0.57-0.59 ms instead of 0.53 ms at N = 120, 16 columns.)
 template <class P, int LX, int NT, int SYM, int TRN = 0>
 __global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * (P::R1 * P::R2P + TRN) * 16, P::R1, 4)) k_xfwd(PcbOp op, PcbCols cols, const cplx* __restrict__ tw) {
     constexpr int N = P::N, R1 = P::R1, R2 = P::R2, R2P = P::R2P;
@@ -244,12 +252,6 @@ __global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * (P::R1 * P::R2P + TR
 // Reads the work column W (in Fourier-x order), the source column X (MODE 2) and writes OUT
 // (OUT may alias W: each CTA only touches its own rows).
 // ---------------------------------------------------------------------------------------
-#ifdef PCB_EMU
-PCB_D void pcb_prefetch_l2(const void*) {}
-#else
-PCB_D void pcb_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
-#endif
-
 template <class P, int LX, int NT, int MODE, int TRN = 0>
 __global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * (P::R1 * P::R2P + TRN) * 16, P::R1, 4)) k_xinv(PcbOp op, PcbCols cols, const cplx* __restrict__ tw) {
     constexpr int N = P::N, R1 = P::R1, R2 = P::R2, R2P = P::R2P;
@@ -722,6 +724,23 @@ __global__ void __launch_bounds__(P::N / 8 * 32, 1) k_mid(PcbOp op, PcbCols cols
                 mbits[q] = (it < 8 * R1) ? __ldg(op.mbits + (((long long)c * N + i0) * N + 8 * warp + it % 8) * R1 + it / 8) : 0u;
             }
         }
+        // coupled dielectric: mask bytes of this thread's points in step (B), point e = threadIdx.x + q * blockDim.x of the CTA's
+        // third of the rows -- also fetched here, ten independent loads whose latency the plane's transforms hide
+        constexpr int NTHR = N / 8 * 32, PBQ = (DIEL == 2) ? ((N + 2) / 3 * N + NTHR - 1) / NTHR : 1;
+        unsigned pmask[(PBQ + 3) / 4];
+        int prow0 = 0, pcnt = 0;
+        if (DIEL == 2) {
+            prow0 = (crank * N) / 3;
+            pcnt = (((crank + 1) * N) / 3 - prow0) * N;
+            const unsigned char* __restrict__ mp = op.maskp + (long long)i0 * N * N + prow0 * N;
+            PCB_UNROLL
+            for (int w = 0; w < (PBQ + 3) / 4; ++w) pmask[w] = 0u;
+            PCB_UNROLL
+            for (int q = 0; q < PBQ; ++q) {
+                const int e = threadIdx.x + q * NTHR;
+                if (e < pcnt) pmask[q / 4] |= (unsigned)__ldg(mp + e) << (8 * (q % 4));
+            }
+        }
 #ifndef PCB_EMU
         if (TMA) { pcb_mbar_wait(mybar, phase); phase ^= 1u; } else
 #endif
@@ -826,12 +845,12 @@ __global__ void __launch_bounds__(P::N / 8 * 32, 1) k_mid(PcbOp op, PcbCols cols
 #ifndef PCB_EMU
             if (DIEL == 2) {   // (B) off-diagonal terms at the coupled points of this CTA's third of the rows
                 pcb_cluster_sync();
-                const int r0 = (crank * N) / 3, r1 = ((crank + 1) * N) / 3;
-                const unsigned char* __restrict__ mp = op.maskp + (long long)i0 * N * N + r0 * N;
-                for (int e = threadIdx.x; e < (r1 - r0) * N; e += N / 8 * 32) {
-                    const unsigned mk = __ldg(mp + e);
+                PCB_UNROLL
+                for (int q = 0; q < PBQ; ++q) {
+                    const int e = threadIdx.x + q * NTHR;
+                    const unsigned mk = (pmask[q / 4] >> (8 * (q % 4))) & 0xffu;      // 0 beyond pcnt
                     if (mk & 8u) {
-                        const unsigned off = (unsigned)(((r0 + e / N) * LD + e % N) * (int)sizeof(cplx));
+                        const unsigned off = (unsigned)(((prow0 + e / N) * LD + e % N) * (int)sizeof(cplx));
                         const cplx u0 = pcb_ld_cluster(pbase[0] + off), u1 = pcb_ld_cluster(pbase[1] + off), u2 = pcb_ld_cluster(pbase[2] + off);
                         const cplx v0 = cscale(u0, (mk & 1u) ? inv_d[0] : 1.0), v1 = cscale(u1, (mk & 2u) ? inv_d[1] : 1.0),
                                    v2 = cscale(u2, (mk & 4u) ? inv_d[2] : 1.0);

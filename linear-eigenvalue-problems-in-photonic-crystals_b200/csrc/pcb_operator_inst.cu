@@ -145,6 +145,7 @@ struct PlanePass<true, PP> {
                 cfg.gridDim = dim3(3 * 148, 1, 1);
                 PCB_CUDA_OK(cudaOccupancyMaxActiveClusters(&max_clusters, kfn, &cfg));
                 if (const char* ev = getenv("PCB200_MID_CLUSTERS")) { const int v = atoi(ev); if (v >= 1 && v < max_clusters) max_clusters = v; }
+                if (getenv("PCB200_DEBUG")) fprintf(stderr, "[pcb200] k_mid<%d, coupled>: %d co-resident clusters of 3 CTAs (%d SMs)\n", PP::N, max_clusters, sms);
                 if (max_clusters < 1) { pcb_set_error("plane mode: no 3-CTA cluster of k_mid fits on this device"); max_clusters = 0; return -1; }
             }
             long long ncl = max_clusters;

@@ -57,6 +57,14 @@ class Context:
     def sync(self):
         L.check(self._lib.pcb_sync(self.h), "pcb_sync")
 
+    def record(self, slot):
+        """Mark the work enqueued on this context's stream so far (pcb_ctx_record)."""
+        L.check(self._lib.pcb_ctx_record(self.h, int(slot)), "pcb_ctx_record")
+
+    def wait_for(self, other, slot):
+        """Later work of this context starts after `other`'s mark `slot` (stream/event ordering, no host sync)."""
+        L.check(self._lib.pcb_ctx_wait(self.h, other.h, int(slot)), "pcb_ctx_wait")
+
     def launches(self):
         n = C.c_longlong()
         L.check(self._lib.pcb_launch_count(self.h, C.byref(n)), "pcb_launch_count")

@@ -8,6 +8,7 @@ the ordinary single-GPU kernels, and scattered back.  The reference has no multi
 `lobpcg_sep_softlock` -- `ShardedOperator` offers the interface of `pcfft.Operator`.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -88,6 +89,9 @@ def new_unique_id():
     return bytes(buf)
 
 
+LG_CHUNKS = int(os.environ.get("PCB200_LG_CHUNKS", "2"))      # pipeline depth of ShardedOperator.apply_into (1 = no overlap)
+
+
 class ShardedOperator:
     """pcfft.Operator interface over slab blocks: P and the residual are slab-local, A / H go through whole columns."""
 
@@ -109,18 +113,31 @@ class ShardedOperator:
         cm = self.comm
         k = src.k
         owners = [j % cm.world for j in range(k)]
-        mine = [j for j in range(k) if owners[j] == cm.rank]
-        win, wout = cm.work_blocks((k + cm.world - 1) // cm.world)
-        pin, pout = [0] * k, [0] * k
-        for slot, j in enumerate(mine):
-            pin[j], pout[j] = win.ptrs[slot], wout.ptrs[slot]
-        cm.exchange(True, owners, src, pin)            # slabs -> whole columns on their owners
-        cm.slab.sync()
-        if mine:
-            self.full.apply_into(mode, win.cols(range(len(mine))), wout.cols(range(len(mine))))
-            cm.full.sync()
-        cm.exchange(False, owners, dst, pout)          # whole columns -> slabs
-        cm.slab.sync()
+        kmax = (k + cm.world - 1) // cm.world                   # most columns any rank owns (slot = j // world)
+        win, wout = cm.work_blocks(kmax)
+        # Pipeline over chunks of slots: the exchange of chunk c+1 (slab stream, NCCL) overlaps the operator on chunk c (full
+        # context's stream), and the way back of chunk c overlaps the operator on chunk c+1.  Ordering is by events between the
+        # two streams -- the host never blocks here; the slab-stream kernels that follow are ordered behind the last exchange.
+        nch = max(1, min(kmax, LG_CHUNKS, 8))
+        bounds = [(i * kmax) // nch for i in range(nch + 1)]
+        chunks = []
+        for ci in range(nch):
+            js = [j for j in range(k) if bounds[ci] <= j // cm.world < bounds[ci + 1]]
+            if js:
+                chunks.append(js)
+        for ci, js in enumerate(chunks):
+            pin = [win.ptrs[j // cm.world] if owners[j] == cm.rank else 0 for j in js]
+            cm.exchange(True, [owners[j] for j in js], src.cols(js), pin)            # slabs -> whole columns on their owners
+            cm.slab.record(ci)
+            mine = [j // cm.world for j in js if owners[j] == cm.rank]
+            if mine:
+                cm.full.wait_for(cm.slab, ci)
+                self.full.apply_into(mode, win.cols(mine), wout.cols(mine))
+            cm.full.record(ci)
+        for ci, js in enumerate(chunks):
+            pout = [wout.ptrs[j // cm.world] if owners[j] == cm.rank else 0 for j in js]
+            cm.slab.wait_for(cm.full, ci)
+            cm.exchange(False, [owners[j] for j in js], dst.cols(js), pout)          # whole columns -> slabs
         return dst
 
     def apply(self, mode, x, out=None):
