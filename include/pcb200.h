@@ -138,6 +138,13 @@ int pcb_coldots(pcb_ctx* ctx, int ncols, const void* const* a, const void* const
 /* y_j = alpha x_j + beta y_j */
 int pcb_axpby(pcb_ctx* ctx, int ncols, const void* const* x, void* const* y, double alpha, double beta);
 
+/* Geometry (dielectric.py:104-261: mesh3d_edge_dofs / mesh3d_volume_dofs, coo = mesh @ inv(ct^T), FLAG_<lattice>): Omega_1 of a
+ * lattice evaluated on the device for all 4 N^3 DoF points.  kind: 0 sc_flat1, 1 sc_flat2, 2 sc_curv, 3 bcc_sg, 4 bcc_dg, 5 fcc;
+ * minv = inv(ct^T) (9 doubles, row-major).  host_mask[cell] bit c = edge DoF of component c inside, bit 3 = volume DoF inside;
+ * host_amb[cell] marks (same bits) the DoFs whose decision margin is below 1e-10 -- the caller re-evaluates those with the
+ * reference's NumPy expression, which keeps the index sets bit-identical.  Both arrays: N^3 bytes of HOST memory. */
+int pcb_geometry_mask(pcb_ctx* ctx, int kind, const double* minv, unsigned char* host_mask, unsigned char* host_amb);
+
 /* ---- large-grid mode (BASELINE config 5): dense phase row-sharded, operator on whole columns ------------
  * A SLAB context owns the i2 planes [z0, z1) of every column: its "column" is 3 * (z1-z0) * N^2 complex128 ([c][local cell]),
  * and pcb_residual / pcb_gram2 / pcb_update / pcb_coldots / pcb_axpby / pcb_fill_uniform / block up/download work on it

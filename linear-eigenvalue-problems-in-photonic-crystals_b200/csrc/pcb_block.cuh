@@ -671,6 +671,97 @@ __global__ void __launch_bounds__(256) k_symbol_point(PcbOp op, PcbCols cols) {
     }
 }
 
+// ---- geometry: the dielectric region Omega_1 evaluated on the device straight into the per-cell bit mask ------------------
+// (dielectric.py:104-261: mesh3d_edge_dofs / mesh3d_volume_dofs, coo = mesh @ inv(ct^T), FLAG_<lattice>(coo)).  One thread per
+// cell classifies its four DoFs -- bit c: edge DoF of component c (half a cell along axis c), bit 3: volume DoF (cell centre).
+// A DoF whose decision margin is below a tolerance (|lhs - rhs| of the deciding inequality; exact ties of the flat lattices,
+// or last-bit differences between this arithmetic and NumPy's) is reported in `amb` with the same bit layout: the host
+// re-evaluates those few points with the reference's own NumPy expression, so the index sets stay bit-identical to the
+// reference's while the O(N^3) work runs here (FCC, N = 120: 34 sphere / spheroid tests for each of 6.9 M points).
+enum { PCB_GEOM_SC_FLAT1 = 0, PCB_GEOM_SC_FLAT2 = 1, PCB_GEOM_SC_CURV = 2, PCB_GEOM_BCC_SG = 3, PCB_GEOM_BCC_DG = 4, PCB_GEOM_FCC = 5 };
+struct PcbGeom { int kind; double minv[9]; };      // minv = inv(ct^T), row-major: coo_j = sum_i mesh_i minv[i][j]
+
+PCB_HD void pcb_geom_point(const PcbGeom& g, double u0, double u1, double u2, bool& inside, bool& amb) {
+    const double x = u0 * g.minv[0] + u1 * g.minv[3] + u2 * g.minv[6];
+    const double y = u0 * g.minv[1] + u1 * g.minv[4] + u2 * g.minv[7];
+    const double z = u0 * g.minv[2] + u1 * g.minv[5] + u2 * g.minv[8];
+    double margin = 1.0;
+    inside = false;
+#define PCB_GEOM_LE(lhs, rhs) ((margin = fmin(margin, fabs((lhs) - (rhs)))), (lhs) <= (rhs))
+#define PCB_GEOM_GE(lhs, rhs) ((margin = fmin(margin, fabs((lhs) - (rhs)))), (lhs) >= (rhs))
+#define PCB_GEOM_LT(lhs, rhs) ((margin = fmin(margin, fabs((lhs) - (rhs)))), (lhs) < (rhs))
+    if (g.kind == PCB_GEOM_SC_FLAT1) {
+        const bool a = PCB_GEOM_LE(x, 0.25), b = PCB_GEOM_LE(y, 0.25), c = PCB_GEOM_LE(z, 0.25);
+        inside = (a && b) || (a && c) || (b && c);
+    } else if (g.kind == PCB_GEOM_SC_FLAT2) {
+        const bool xl = PCB_GEOM_LE(x, 0.25), yl = PCB_GEOM_LE(y, 0.25);
+        const bool z1 = PCB_GEOM_GE(z, 0.25), z2 = PCB_GEOM_LE(z, 0.5), z3 = PCB_GEOM_GE(z, 0.5), z4 = PCB_GEOM_LE(z, 0.75), z5 = PCB_GEOM_GE(z, 0.75);
+        const bool y1 = PCB_GEOM_GE(y, 0.5), y2 = PCB_GEOM_LE(y, 0.75), x1 = PCB_GEOM_GE(x, 0.5), x2 = PCB_GEOM_LE(x, 0.75);
+        inside = (xl && yl) || (xl && z1 && z2) || (y1 && y2 && z3 && z4) || (x1 && x2 && z5);
+    } else if (g.kind == PCB_GEOM_SC_CURV) {
+        const double px = x - 0.5, py = y - 0.5, pz = z - 0.5;
+        const double xx = px * px, yy = py * py, zz = pz * pz;
+        const double rod2 = 0.11 * 0.11, ball2 = 0.345 * 0.345;
+        const bool a = PCB_GEOM_LE(xx + yy + zz, ball2), b = PCB_GEOM_LE(xx + yy, rod2), c = PCB_GEOM_LE(xx + zz, rod2), d = PCB_GEOM_LE(yy + zz, rod2);
+        inside = a || b || c || d;
+    } else if (g.kind == PCB_GEOM_BCC_SG || g.kind == PCB_GEOM_BCC_DG) {
+        const double tp = 2.0 * M_PI;
+        double gy = sin(tp * x) * cos(tp * y) + sin(tp * y) * cos(tp * z) + sin(tp * z) * cos(tp * x);
+        if (g.kind == PCB_GEOM_BCC_DG) gy = fabs(gy);
+        margin = fabs(gy - 1.1);
+        inside = gy > 1.1;
+    } else {      // FCC diamond network: 18 spheres at the lattice sites, 16 prolate spheroids along the bonds
+        const double r2 = 0.12 * 0.12, b_ell = 0.11;
+        const double basis[4][3] = {{0, 0, 0}, {0, 0.5, 0.5}, {0.5, 0, 0.5}, {0.5, 0.5, 0}};
+        const double sites[14][3] = {{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {0, 1, 1}, {1, 0, 1}, {1, 1, 0}, {1, 1, 1},
+                                     {0, 0.5, 0.5}, {0.5, 0, 0.5}, {0.5, 0.5, 0}, {1, 0.5, 0.5}, {0.5, 1, 0.5}, {0.5, 0.5, 1}};
+        for (int s = 0; s < 18; ++s) {
+            const double sx = s < 14 ? sites[s][0] : 0.25 + basis[s - 14][0];
+            const double sy = s < 14 ? sites[s][1] : 0.25 + basis[s - 14][1];
+            const double sz = s < 14 ? sites[s][2] : 0.25 + basis[s - 14][2];
+            const double d2 = (x - sx) * (x - sx) + (y - sy) * (y - sy) + (z - sz) * (z - sz);
+            if (PCB_GEOM_LT(d2, r2)) inside = true;
+        }
+        for (int i = 0; i < 4; ++i) {
+            const double hx = (basis[i][0] - 0.25) / 2, hy = (basis[i][1] - 0.25) / 2, hz = (basis[i][2] - 0.25) / 2;
+            const double mx = (basis[i][0] + 0.25) / 2, my = (basis[i][1] + 0.25) / 2, mz = (basis[i][2] + 0.25) / 2;
+            const double len = sqrt(hx * hx + hy * hy + hz * hz);
+            const double dx = hx / len, dy = hy / len, dz = hz / len;
+            const double major2 = b_ell * b_ell + len * len;
+            for (int j = 0; j < 4; ++j) {
+                const double X0 = x - (mx + basis[j][0]), X1 = y - (my + basis[j][1]), X2 = z - (mz + basis[j][2]);
+                const double al = dx * X0 + dy * X1 + dz * X2;
+                const double along = al * al, across = (X0 * X0 + X1 * X1 + X2 * X2) - along;
+                if (PCB_GEOM_LT(along / major2 + across / (b_ell * b_ell), 1.0)) inside = true;
+            }
+        }
+    }
+#undef PCB_GEOM_LE
+#undef PCB_GEOM_GE
+#undef PCB_GEOM_LT
+    amb = margin < 1e-10;
+}
+
+__global__ void __launch_bounds__(256) k_geom_mask(PcbGeom g, int N, unsigned char* __restrict__ mask, unsigned char* __restrict__ amb) {
+    const long long nn = (long long)N * N * N;
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nn) return;
+    const int i[3] = {(int)(p % N), (int)((p / N) % N), (int)(p / ((long long)N * N))};
+    unsigned m = 0u, a = 0u;
+    PCB_UNROLL
+    for (int d = 0; d < 4; ++d) {      // d < 3: edge DoF of component d; d == 3: cell centre
+        double u[3];
+        PCB_UNROLL
+        for (int ax = 0; ax < 3; ++ax) u[ax] = (d == 3 || d == ax) ? ((double)i[ax] + 0.5) / (double)N : (double)i[ax] / (double)N;
+        bool in, am;
+        pcb_geom_point(g, u[0], u[1], u[2], in, am);
+        m |= (in ? 1u : 0u) << d;
+        a |= (am ? 1u : 0u) << d;
+    }
+    mask[p] = (unsigned char)m;
+    amb[p] = (unsigned char)a;
+}
+
 // ---- x0 = U[0,1) + i U[0,1) on the device: counter-based (splitmix64 of (seed, column, element)) ---------
 PCB_HD unsigned long long pcb_mix64(unsigned long long z) {
     z += 0x9E3779B97F4A7C15ull;

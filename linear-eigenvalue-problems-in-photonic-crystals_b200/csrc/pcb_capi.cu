@@ -365,6 +365,26 @@ int pcb_fill_uniform(pcb_ctx* c, int k, void* const* cols, unsigned long long se
     return 0;
 }
 
+// ---- geometry -------------------------------------------------------------------------------------------------
+int pcb_geometry_mask(pcb_ctx* c, int kind, const double* minv, unsigned char* host_mask, unsigned char* host_amb) {
+    PCB_CHECK_ARG(c && minv && host_mask && host_amb && kind >= PCB_GEOM_SC_FLAT1 && kind <= PCB_GEOM_FCC, "bad arguments");
+    PCB_CUDA_OK(cudaSetDevice(c->device));
+    const size_t nn = (size_t)c->nn;
+    if (ensure_scratch(c, 2 * nn + 256)) return -1;
+    unsigned char* dm = reinterpret_cast<unsigned char*>(c->scratch);
+    unsigned char* da = dm + ((nn + 127) / 128) * 128;
+    PcbGeom g;
+    g.kind = kind;
+    for (int i = 0; i < 9; ++i) g.minv[i] = minv[i];
+    PCB_LAUNCH(k_geom_mask, dim3((unsigned)((nn + 255) / 256), 1, 1), dim3(256, 1, 1), 0, c->stream, g, c->N, dm, da);
+    PCB_CUDA_OK(cudaGetLastError());
+    c->launches++;
+    PCB_CUDA_OK(cudaMemcpyAsync(host_mask, dm, nn, cudaMemcpyDeviceToHost, c->stream));
+    PCB_CUDA_OK(cudaMemcpyAsync(host_amb, da, nn, cudaMemcpyDeviceToHost, c->stream));
+    PCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 // ---- dielectric -----------------------------------------------------------------------------------------------
 void pcb_diel_destroy(pcb_diel* d);
 int pcb_diel_create(pcb_ctx* c, int kind, const int64_t* ind_e, long long n_e, const int64_t* ind_v, long long n_v,
@@ -684,8 +704,11 @@ int pcb_apply_host(pcb_op* o, int mode, int k, const void* x_host, long long ldx
         for (int a = 0; a < 2; ++a) for (int b = 0; b < 4; ++b) PCB_CUDA_OK(cudaEventCreateWithFlags(&c->hp_ev[a][b], cudaEventDisableTiming));
     }
     // staging: 2 slots x 4 regions of R x min(k, CH) elements (a single-vector call takes 1/8 of the block-call size)
-    const int chw = k < PCB_HOST_CH ? k : PCB_HOST_CH;
-    if (chw > c->hp_cols) {
+    static const char* ev_ch = getenv("PCB200_HOST_CH");      // columns per pipeline chunk (default 8 = 128-byte rows of the 2-D copies)
+    int chmax = ev_ch ? atoi(ev_ch) : PCB_HOST_CH;
+    if (chmax < 1 || chmax > PCB_HOST_CH) chmax = PCB_HOST_CH;
+    const int chw = k < chmax ? k : chmax;
+    if (chw != c->hp_cols) {
         if (c->hp_buf) { PCB_CUDA_OK(cudaStreamSynchronize(c->stream)); PCB_CUDA_OK(cudaFree(c->hp_buf)); c->hp_buf = nullptr; c->hp_cols = 0; }
         PCB_CUDA_OK(cudaMalloc(&c->hp_buf, sizeof(cplx) * (size_t)c->R * (size_t)chw * 8));
         c->hp_cols = chw;

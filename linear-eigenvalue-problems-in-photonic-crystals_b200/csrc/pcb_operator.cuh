@@ -651,6 +651,10 @@ __global__ void k_mask_bits(PcbOp op, unsigned* __restrict__ out) {
 // of per-element cp.async / LDS + STG loops: 960 LDGSTS and 960 LDS+STG per warp and plane leave the LSU queue, which the
 // radix steps need (N = 120, 16 columns: 0.884 -> 0.818 ms; PCB200_MID_TMA=0 selects the loop form, which is also what the
 // host-emulation build runs).
+// (Round 2, measured and removed: the radix-R1 steps with two items per lane in flight -- either both loaded before both
+// butterflies, or software-pipelined so that item i+1's loads go out before item i's stores; the shared-memory plane carries no
+// restrict information, so the compiler keeps each trip's loads behind the previous trip's stores.  At the 128-register cap of
+// 15 warps either form spills 400-800 bytes per thread and the pass takes 1.17 instead of 0.82 ms at N = 120, 16 columns.)
 // DIEL = 2 (coupled 3x3 point-wise M, discretization.py:368-401): the kernel is launched as CLUSTERS OF THREE CTAs, one per
 // component of the same (column, i0) plane.  The fused z step is split at real space: (A) forward radix R2 and the diagonal
 // entries (bit words as for DIEL = 1) -> own plane; cluster barrier; (B) every CTA takes a third of the rows and, at the

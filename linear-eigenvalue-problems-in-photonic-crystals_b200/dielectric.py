@@ -203,6 +203,48 @@ def compute_index(N, d_flag, dofs="edge"):
     return np.asarray(_FLAGS[d_flag](mesh @ np.linalg.inv(ct.T)), dtype=np.int64)
 
 
+_GEOM_KIND = {"sc_flat1": 0, "sc_flat2": 1, "sc_curv": 2, "bcc_sg": 3, "bcc_dg": 4, "fcc": 5}
+geometry_stats = {}      # last device evaluation: {"seconds", "ambiguous"} (set-up timing for the runners / bench)
+
+
+def device_index_sets(N, d_flag, ctx=None):
+    """(edge indices, volume indices) of Omega_1 with the O(N^3) classification on the GPU (pcb_geometry_mask).
+
+    The kernel evaluates FLAG_<d_flag> for the 3 N^3 edge and N^3 volume DoF points and reports every point whose deciding
+    inequality has a margin below 1e-10 (exact ties of the flat lattices, last-bit differences to NumPy's arithmetic); only
+    those are re-evaluated here with the NumPy expression of compute_index, so the result is bit-identical to it
+    (tests: every lattice at N = 12 ... 48, FCC / gyroid at N = 120) at a fraction of a second instead of 5-8 s at N = 120."""
+    from . import _lib as L
+    from . import devarray
+    t0 = time.time()
+    ctx = ctx if ctx is not None else devarray.get_context(N)
+    nn = N ** 3
+    minv = np.ascontiguousarray(np.linalg.inv(diel_info(d_flag, option="ct").T), dtype=np.float64)
+    mask, amb = np.empty(nn, dtype=np.uint8), np.empty(nn, dtype=np.uint8)
+    L.check(L.lib().pcb_geometry_mask(ctx.h, _GEOM_KIND[d_flag], minv.ctypes.data_as(L.c_double_p), mask.ctypes.data, amb.ctypes.data),
+            "pcb_geometry_mask")
+    n_amb = 0
+    for d in range(4):
+        cells = np.flatnonzero((amb >> d) & 1)
+        if cells.size == 0:
+            continue
+        n_amb += cells.size
+        i = [cells % N, (cells // N) % N, cells // (N * N)]
+        cols = [(i[ax] + 0.5) / N if (d == 3 or d == ax) else i[ax] / N for ax in range(3)]
+        pts = np.column_stack(cols)
+        if pts.shape[0] == 3:          # FLAG_fcc reads a (3, 3) array as (axis, point): avoid the ambiguous shape
+            pts = np.vstack((pts, pts[:1]))
+        hit = np.zeros(pts.shape[0], dtype=bool)
+        hit[_FLAGS[d_flag](pts @ minv)] = True
+        inside = hit[:cells.size]
+        bit = np.uint8(1 << d)
+        mask[cells] = np.where(inside, mask[cells] | bit, mask[cells] & np.uint8(~bit & 0xFF))
+    ind_e = np.concatenate([c * nn + np.flatnonzero((mask >> c) & 1) for c in range(3)]).astype(np.int64)
+    ind_v = np.flatnonzero((mask >> 3) & 1).astype(np.int64)
+    geometry_stats.update(seconds=time.time() - t0, ambiguous=int(n_amb), N=N, d_flag=d_flag)
+    return ind_e, ind_v
+
+
 def diel_io_index(N, d_flag, dofs="edge", gpu=True, cache=True):
     """Indices of the dielectric edge / volume DoFs (dielectric.py:58-97).
 
@@ -236,7 +278,13 @@ def diel_io_index(N, d_flag, dofs="edge", gpu=True, cache=True):
         else:
             say(f"{GREEN}Index file already exists.{RESET}")
     if ind is None:
-        ind = compute_index(N, d_flag, dofs)
+        if gpu and d_flag in _GEOM_KIND and os.environ.get("PCB200_HOST_GEOMETRY", "0") != "1":
+            # geometry on the device: both index sets come out of one kernel launch (the other one is kept for the next call)
+            ind_e, ind_v = device_index_sets(N, d_flag)
+            _index_cache[(N, d_flag, "edge")], _index_cache[(N, d_flag, "volume")] = ind_e, ind_v
+            ind = ind_e if dofs == "edge" else ind_v
+        else:
+            ind = compute_index(N, d_flag, dofs)
         if cache:
             say(f"{RED}New lattice type {d_flag} or size {N} isn't computed.{RESET}")
             try:

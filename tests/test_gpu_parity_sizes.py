@@ -201,3 +201,15 @@ def test_failed_allocation_does_not_poison_later_launches(gpu):
     X = ctx.random_block(2, 3)       # launches k_fill_uniform
     ctx.sync()                       # raises if the old cudaErrorMemoryAllocation is still pending
     assert np.isfinite(gpu.pcfft.column_norms(X)).all()
+
+
+@pytest.mark.parametrize("d_flag", ["fcc", "bcc_dg", "sc_curv"])
+def test_device_geometry_n120(gpu, d_flag):
+    """SURVEY 8f N4 at the benchmark size: Omega_1 evaluated on the GPU equals the host NumPy evaluation (dielectric.py:201-261)
+    bit for bit and takes well under half a second (host: 5-8 s for FCC)."""
+    N = 120
+    gpu.get_context(N)
+    ind_e, ind_v = gpu.dielectric.device_index_sets(N, d_flag)
+    assert gpu.dielectric.geometry_stats["seconds"] < 0.5
+    assert np.array_equal(ind_e, gpu.dielectric.compute_index(N, d_flag, "edge"))
+    assert np.array_equal(ind_v, gpu.dielectric.compute_index(N, d_flag, "volume"))

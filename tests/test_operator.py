@@ -117,3 +117,16 @@ def test_fourth_order_stencils_k2(pcb, oracle, typ):
     assert relerr(H(x), Ho(x)) < TOL
     assert relerr(P(x), Po(x)) < TOL
     assert relerr(Diels(x), diel(x)) < TOL
+
+
+@pytest.mark.parametrize("d_flag", ["sc_flat1", "sc_flat2", "sc_curv", "bcc_sg", "bcc_dg", "fcc"])
+def test_device_geometry_matches_host(pcb, oracle, d_flag):
+    """Omega_1 classified on the device (pcb_geometry_mask + host arbitration of the boundary points) == the NumPy evaluation
+    of dielectric.py:104-261 bit for bit, for edge and volume DoFs."""
+    sizes = (8, 12, 16) if pcb.backend_name == "emu" else (16, 24, 48, 100)
+    for N in sizes:
+        ind_e, ind_v = pcb.dielectric.device_index_sets(N, d_flag)
+        assert np.array_equal(ind_e, pcb.dielectric.compute_index(N, d_flag, "edge")), (d_flag, N)
+        assert np.array_equal(ind_v, pcb.dielectric.compute_index(N, d_flag, "volume")), (d_flag, N)
+        if N <= 24:
+            assert np.array_equal(ind_e, oracle.diel_index(N, d_flag, "edge"))
