@@ -113,6 +113,7 @@ struct PcbOp {
     int diel;                 // PCB_DIEL_*
     const unsigned char* mask;  // [nn] bit c: edge DoF of component c in Omega_1; bit 3: volume DoF
     const unsigned* mbits;      // plane mode: [c][i0][slot][k1] words, bit k2 = component c of (i0, i1 = coord(slot), i2 = lout(k1,k2)) in Omega_1
+    const unsigned* mbits2;     // five-sweep plane pass (k_mid2): [c][i0][d][col] words, bit k2 (k_mask_bits2)
     const unsigned char* maskp; // plane mode, coupled dielectric: the byte mask in plane-slot order, [i0][row][col] = mask(i0, coord(col), coord(row))
     const int* ctab;            // plane mode: [0, N) slot -> grid index (coord), [N, 2N) grid index -> slot
     double ediag[3];          // diagonal entries inside Omega_1 (chiral: 1/eps for all three)

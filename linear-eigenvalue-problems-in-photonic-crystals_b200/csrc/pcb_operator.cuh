@@ -949,6 +949,279 @@ __global__ void __launch_bounds__(P::N / 8 * 32, 1) k_mid(PcbOp op, PcbCols cols
 #endif
 }
 
+// ---------------------------------------------------------------------------------------
+// Plane mode, pass 2 of 3, FIVE shared-memory sweeps instead of seven (plans N = 8 R2 with odd R2: 24, 72, 120).
+// The seven sweeps of k_mid are y8, y15 | z8, z15 M z15, z8 | y15, y8 (N = 120); the plane pass is bound by shared-memory
+// wavefronts, so the transforms of the two axes are interleaved on 2-D register tiles:
+//     A : y radix-8  x  z radix-4      (32 values per item)        z:  8 = 4 x 2 (Cooley-Tukey inside the Good-Thomas step)
+//     B : y radix-R2 x  z radix-2      (2 R2 values per item)      y:  Cooley-Tukey (unit-stride digits, twiddles in A)
+//     C : z radix-R2, M, z radix-R2 inverse                        (as in k_mid; the z digits sit in slot order d = 2k' + k'')
+//     B', A' : the inverses of B and A.
+// 32 complex values per thread need 128+ registers, so the CTA has 8 warps of up to 255 registers instead of 15 of 128: a
+// HALF-WARP h owns the eight rows rho(n1, h) = lin(n1, h) of one z digit n2 = h -- exactly the rows its items of A, B, B', A'
+// touch -- so those four sweeps, the TMA row loads before them and the TMA row stores after them need no CTA-wide barrier; only
+// C (columns) is bracketed by the two barriers the seven-sweep kernel has as well.  Lane maps: in A the 16 lanes of a half-warp
+// are the y digit n2 (consecutive columns), in B the 8 digits k1 (column stride R2, odd -> distinct banks), in C consecutive
+// columns: every LDS.128 / STS.128 is conflict-free with the row stride N + 1.
+// ---------------------------------------------------------------------------------------
+template <class P>
+struct Mid2 {
+    static constexpr int N = P::N, R2 = P::R2;
+    static constexpr bool OK = (P::R1 == 8) && (R2 % 2 == 1) && (R2 <= 15);
+    static constexpr int NW = (R2 + 1) / 2, NTHR = 32 * NW;      // one half-warp per z digit
+    static constexpr int CI = (8 * N + NTHR - 1) / NTHR;         // items of sweep C per thread
+    PCB_HD static int rho(int n1, int n2) { const int s = R2 * n1 + 8 * n2; return s >= N ? s - N : s; }   // z slot (row) of digits (n1, n2)
+    PCB_HD static int k1z(int d) { return (d >> 1) + 4 * (d & 1); }                                       // z digit held by slot digit d = 2k' + k''
+    PCB_HD static int coordy(int col) { return col / R2 + 8 * (col % R2); }                                // y index held by column col after the forward steps
+};
+
+// mbits2[c][i0][d][col], bit k2 = "component c of grid point (i0, i1 = coordy(col), i2 = lout(k1z(d), k2)) lies in Omega_1"
+template <class P>
+__global__ void k_mask_bits2(PcbOp op, unsigned* __restrict__ out) {
+    typedef Mid2<P> M2;
+    constexpr int N = P::N, R2 = P::R2;
+    const long long total = 3LL * N * 8 * N;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int col = (int)(t % N), d = (int)((t / N) % 8), i0 = (int)((t / (8LL * N)) % N), c = (int)(t / (8LL * N * N));
+    const int i1 = M2::coordy(col), o1 = P::lout1(M2::k1z(d));
+    unsigned w = 0u;
+    for (int k2 = 0; k2 < R2; ++k2) {
+        const int i2 = P::wrap(o1 + P::lout2(k2));
+        w |= ((unsigned)(op.mask[((long long)i2 * N + i1) * N + i0] >> c) & 1u) << k2;
+    }
+    out[t] = w;
+}
+
+template <class P, int DIEL, int TMA = 0>
+__global__ void __launch_bounds__(Mid2<P>::NTHR, 1) k_mid2(PcbOp op, PcbCols cols, const cplx* __restrict__ tw, int ncols) {
+    typedef Mid2<P> M2;
+    constexpr int N = P::N, R2 = P::R2, LD = N + 1, NTHR = M2::NTHR, CI = M2::CI;
+    static_assert(M2::OK, "k_mid2 needs N = 8 * R2 with odd R2 <= 15");
+    PCB_DYN_SMEM(cplx, pl);   // [N rows][LD] (+ one mbarrier per warp behind it when TMA)
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int h = tid >> 4, l = tid & 15;             // half-warp = z digit n2, lane within it
+    const bool hact = h < R2;
+    const int nrw = (2 * warp + 1 < R2) ? 16 : 8;     // rows this warp moves (both half-warps, or one in the last warp)
+    const long long nn = op.nn;
+    const double RH = 0.70710678118654752440;
+#ifndef PCB_EMU
+    unsigned long long* mybar = reinterpret_cast<unsigned long long*>(pl + (size_t)N * LD) + warp;
+    unsigned phase = 0;
+    if (TMA) {
+        if (lane == 0) { pcb_mbar_init(mybar, 1); pcb_fence_mbar_init(); }
+        __syncthreads();
+    }
+#endif
+    int rr[8];                // rows of this half-warp: rr[n1] = rho(n1, h) * LD
+    PCB_UNROLL
+    for (int n1 = 0; n1 < 8; ++n1) rr[n1] = M2::rho(n1, hact ? h : 0) * LD;
+
+    for (int pid = blockIdx.x; pid < 3 * N * ncols; pid += gridDim.x) {
+        const int col = pid / (3 * N), c = (pid / N) % 3, i0 = pid % N;
+        cplx* __restrict__ base = cols.wrk[col] + c * nn + (long long)i0 * N * N;
+        // ---- load the warp's rows ----
+#ifndef PCB_EMU
+        if (TMA) {
+            if (lane == 0) {
+                pcb_bulk_wait_read();                       // the previous plane's bulk stores have read these rows
+                pcb_mbar_expect_tx(mybar, (unsigned)nrw * N * (unsigned)sizeof(cplx));
+                for (int r = 0; r < nrw; ++r) {
+                    const int row = M2::rho(r & 7, 2 * warp + (r >> 3));
+                    pcb_bulk_load(pl + row * LD, base + (long long)row * N, N * (unsigned)sizeof(cplx), mybar);
+                }
+            }
+        } else
+#endif
+        {
+            for (int e = lane; e < nrw * N; e += 32) {
+                const int r = e / N, row = M2::rho(r & 7, 2 * warp + (r >> 3));
+                pcb_cp16(pl + row * LD + e % N, base + (long long)row * N + e % N);
+            }
+            pcb_cp_commit();
+        }
+        unsigned mb[CI];
+        if (DIEL == 1) {
+            PCB_UNROLL
+            for (int q = 0; q < CI; ++q) {
+                const int it = tid + NTHR * q;
+                mb[q] = (it < 8 * N) ? __ldg(op.mbits2 + ((long long)c * N + i0) * (8 * N) + it) : 0u;
+            }
+        }
+#ifndef PCB_EMU
+        if (TMA) { pcb_mbar_wait(mybar, phase); phase ^= 1u; } else
+#endif
+        pcb_cp_wait<0>();
+        __syncwarp();
+
+        // ---- A: forward y radix-8 (columns n1 R2 + n2y) x forward z radix-4 (rows rho(2p + q, h)) ----
+        if (hact && l < R2) {
+            PCB_UNROLL
+            for (int q = 0; q < 2; ++q) {
+                cplx v[4][8];
+                PCB_UNROLL
+                for (int p = 0; p < 4; ++p) {
+                    PCB_UNROLL
+                    for (int n1 = 0; n1 < 8; ++n1) v[p][n1] = pl[rr[2 * p + q] + n1 * R2 + l];
+                }
+                PCB_UNROLL
+                for (int p = 0; p < 4; ++p) Dft<8, -1>::run(v[p]);
+                PCB_UNROLL
+                for (int k1 = 0; k1 < 8; ++k1) {
+                    cplx u[4] = {v[0][k1], v[1][k1], v[2][k1], v[3][k1]};
+                    if (k1 > 0) {
+                        const cplx t = __ldg(tw + k1 * R2 + l);
+                        PCB_UNROLL
+                        for (int p = 0; p < 4; ++p) u[p] = cmul(u[p], t);
+                    }
+                    Dft<4, -1>::run(u);
+                    if (q == 1) {      // w8^{k'}: exp(-2 pi i k' / 8)
+                        u[1] = cmake((u[1].x + u[1].y) * RH, (u[1].y - u[1].x) * RH);
+                        u[2] = cmake(u[2].y, -u[2].x);
+                        u[3] = cmake((u[3].y - u[3].x) * RH, -(u[3].x + u[3].y) * RH);
+                    }
+                    PCB_UNROLL
+                    for (int kp = 0; kp < 4; ++kp) pl[rr[2 * kp + q] + k1 * R2 + l] = u[kp];
+                }
+            }
+        }
+        __syncwarp();
+        // ---- B: forward y radix-R2 (columns k1 R2 + n2y) x forward z radix-2 (rows rho(2k', h), rho(2k' + 1, h)) ----
+        if (hact) {
+            PCB_UNROLL
+            for (int b = 0; b < 2; ++b) {
+                const int item = l + 16 * b, k1 = item & 7, kp = item >> 3;
+                cplx* __restrict__ p0 = pl + M2::rho(2 * kp, h) * LD + k1 * R2;
+                cplx* __restrict__ p1 = pl + M2::rho(2 * kp + 1, h) * LD + k1 * R2;
+                cplx v0[R2], v1[R2];
+                PCB_UNROLL
+                for (int n2 = 0; n2 < R2; ++n2) { v0[n2] = p0[n2]; v1[n2] = p1[n2]; }
+                Dft<R2, -1>::run(v0);
+                Dft<R2, -1>::run(v1);
+                PCB_UNROLL
+                for (int k2 = 0; k2 < R2; ++k2) { p0[k2] = cadd(v0[k2], v1[k2]); p1[k2] = csub(v0[k2], v1[k2]); }
+            }
+        }
+        __syncthreads();
+        // ---- C: z radix-R2 over the rows rho(d, n2), M, inverse; lanes = consecutive columns; two items per trip (both items'
+        //      loads are issued before either transform: the plane carries no restrict information, so item by item every
+        //      load would wait behind the previous item's stores) ----
+        PCB_UNROLL
+        for (int q = 0; q < CI; q += 2) {
+            const int ita = tid + NTHR * q, itb = ita + NTHR;
+            if (ita >= 8 * N) break;
+            const bool hasb = (q + 1 < CI) && itb < 8 * N;
+            const int da = ita / N, db = hasb ? itb / N : 0;
+            cplx* __restrict__ ca = pl + ita % N;
+            cplx* __restrict__ cb = pl + (hasb ? itb % N : 0);
+            cplx va[R2], vb[R2];
+            PCB_UNROLL
+            for (int n2 = 0; n2 < R2; ++n2) va[n2] = ca[M2::rho(da, n2) * LD];
+            if (hasb) {
+                PCB_UNROLL
+                for (int n2 = 0; n2 < R2; ++n2) vb[n2] = cb[M2::rho(db, n2) * LD];
+            }
+            Dft<R2, -1>::run(va);
+            if (DIEL == 1) {
+                const double scl = op.ediag[c];
+                const unsigned w = mb[q];
+                PCB_UNROLL
+                for (int k2 = 0; k2 < R2; ++k2) va[k2] = cscale(va[k2], ((w >> k2) & 1u) ? scl : 1.0);
+            }
+            Dft<R2, +1>::run(va);
+            PCB_UNROLL
+            for (int n2 = 0; n2 < R2; ++n2) ca[M2::rho(da, n2) * LD] = va[n2];
+            if (hasb) {
+                Dft<R2, -1>::run(vb);
+                if (DIEL == 1) {
+                    const double scl = op.ediag[c];
+                    const unsigned w = mb[(q + 1 < CI) ? q + 1 : q];
+                    PCB_UNROLL
+                    for (int k2 = 0; k2 < R2; ++k2) vb[k2] = cscale(vb[k2], ((w >> k2) & 1u) ? scl : 1.0);
+                }
+                Dft<R2, +1>::run(vb);
+                PCB_UNROLL
+                for (int n2 = 0; n2 < R2; ++n2) cb[M2::rho(db, n2) * LD] = vb[n2];
+            }
+        }
+        __syncthreads();
+        // ---- B': inverse z radix-2 x inverse y radix-R2 ----
+        if (hact) {
+            PCB_UNROLL
+            for (int b = 0; b < 2; ++b) {
+                const int item = l + 16 * b, k1 = item & 7, kp = item >> 3;
+                cplx* __restrict__ p0 = pl + M2::rho(2 * kp, h) * LD + k1 * R2;
+                cplx* __restrict__ p1 = pl + M2::rho(2 * kp + 1, h) * LD + k1 * R2;
+                cplx v0[R2], v1[R2];
+                PCB_UNROLL
+                for (int k2 = 0; k2 < R2; ++k2) { const cplx a = p0[k2], bb = p1[k2]; v0[k2] = cadd(a, bb); v1[k2] = csub(a, bb); }
+                Dft<R2, +1>::run(v0);
+                Dft<R2, +1>::run(v1);
+                PCB_UNROLL
+                for (int n2 = 0; n2 < R2; ++n2) { p0[n2] = v0[n2]; p1[n2] = v1[n2]; }
+            }
+        }
+        __syncwarp();
+        // ---- A': conjugate twiddles, inverse z radix-4 x inverse y radix-8 ----
+        if (hact && l < R2) {
+            PCB_UNROLL
+            for (int q = 0; q < 2; ++q) {
+                cplx v[4][8];
+                PCB_UNROLL
+                for (int k1 = 0; k1 < 8; ++k1) {
+                    cplx u[4];
+                    PCB_UNROLL
+                    for (int kp = 0; kp < 4; ++kp) u[kp] = pl[rr[2 * kp + q] + k1 * R2 + l];
+                    if (q == 1) {      // conj w8^{k'}
+                        u[1] = cmake((u[1].x - u[1].y) * RH, (u[1].x + u[1].y) * RH);
+                        u[2] = cmake(-u[2].y, u[2].x);
+                        u[3] = cmake(-(u[3].x + u[3].y) * RH, (u[3].x - u[3].y) * RH);
+                    }
+                    Dft<4, +1>::run(u);
+                    if (k1 > 0) {
+                        const cplx t = __ldg(tw + k1 * R2 + l);
+                        const cplx tc = cmake(t.x, -t.y);
+                        PCB_UNROLL
+                        for (int p = 0; p < 4; ++p) u[p] = cmul(u[p], tc);
+                    }
+                    PCB_UNROLL
+                    for (int p = 0; p < 4; ++p) v[p][k1] = u[p];
+                }
+                PCB_UNROLL
+                for (int p = 0; p < 4; ++p) Dft<8, +1>::run(v[p]);
+                PCB_UNROLL
+                for (int p = 0; p < 4; ++p) {
+                    PCB_UNROLL
+                    for (int n1 = 0; n1 < 8; ++n1) pl[rr[2 * p + q] + n1 * R2 + l] = v[p][n1];
+                }
+            }
+        }
+        __syncwarp();
+        // ---- store the warp's rows ----
+#ifndef PCB_EMU
+        if (TMA) {
+            pcb_fence_async_smem();                         // the rows were written through the generic proxy
+            __syncwarp();
+            if (lane == 0) {
+                for (int r = 0; r < nrw; ++r) {
+                    const int row = M2::rho(r & 7, 2 * warp + (r >> 3));
+                    pcb_bulk_store(base + (long long)row * N, pl + row * LD, N * (unsigned)sizeof(cplx));
+                }
+                pcb_bulk_commit();
+            }
+        } else
+#endif
+        for (int e = lane; e < nrw * N; e += 32) {
+            const int r = e / N, row = M2::rho(r & 7, 2 * warp + (r >> 3));
+            base[(long long)row * N + e % N] = pl[row * LD + e % N];
+        }
+        __syncwarp();      // own rows are free again for the next plane's loads
+    }
+#ifndef PCB_EMU
+    if (TMA && lane == 0) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");      // stores done before the CTA exits
+#endif
+}
+
 // Plane-mode set-up for the coupled dielectric: the byte mask (bit c: edge DoF of component c, bit 3: volume DoF in Omega_1)
 // in the slot order of the plane pass, maskp[i0][row][col] = mask(i0, i1 = coord(col), i2 = coord(row)).
 template <class P>
@@ -977,6 +1250,7 @@ struct PcbOpLaunch {
     int r1, r2;
     int plane_mode;   // 1: the fused (i1,i2)-plane pass exists for this size (N % 8 == 0 and the plane fits in shared memory)
     int plane_coupled; // 1: ... also for the coupled 3x3 dielectric (clusters of three CTAs; CUDA build only)
+    int plane_five;    // 1: the five-sweep form of the plane pass (k_mid2) exists: N = 8 R2, R2 odd
     // mode: 0 plain 3-D FFT forward, 1 plain inverse (1/N^3), 2 A = AMA^H, 3 H = AMA^H + gamma B^H B + shift
     int (*apply)(const PcbOp& op, const PcbCols& cols, int ncols, int mode, const cplx* tw, cudaStream_t s, int sms);
     // split passes used by the cross-DoF dielectric and by the tests: pass ids below
@@ -988,6 +1262,7 @@ enum { PCB_PASS_XFWD_SYM = 0, PCB_PASS_XFWD = 1, PCB_PASS_YFWD = 2, PCB_PASS_ZFW
        PCB_PASS_XFWD_SYM_T = 10, PCB_PASS_MID = 11, PCB_PASS_XINV_A_T = 12, PCB_PASS_XINV_H_T = 13,
        PCB_PASS_MASKBITS = 14 /* set-up: op.mask -> (unsigned*)op.mbits */,
        PCB_PASS_MID_FWD = 15, PCB_PASS_MID_INV = 16 /* halves of the plane pass around the cross-DoF stencil */,
-       PCB_PASS_MASKPLANE = 17 /* set-up: op.mask -> (unsigned char*)op.maskp */, PCB_PASS_COORDTAB = 18 /* set-up: (int*)op.ctab */ };
+       PCB_PASS_MASKPLANE = 17 /* set-up: op.mask -> (unsigned char*)op.maskp */, PCB_PASS_COORDTAB = 18 /* set-up: (int*)op.ctab */,
+       PCB_PASS_MASKBITS2 = 19 /* set-up: op.mask -> (unsigned*)op.mbits2 (five-sweep plane pass) */ };
 
 const PcbOpLaunch* pcb_find_plan(int N);

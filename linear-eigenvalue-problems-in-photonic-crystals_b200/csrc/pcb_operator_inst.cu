@@ -73,6 +73,7 @@ inline int ctas_per_sm(int smem, int regs_hint_threads) {
 // plane mode: N % 8 == 0, tiles of 8 rows must not straddle an i2 plane, and N x (N+1) complex fit in one CTA's shared memory
 constexpr bool kPlane = (P::N % 8 == 0) && (LX == 8) && ((long long)P::N * (P::N + 1) * 16 <= 232448);
 constexpr int kSmemMid = P::N * (P::N + 1) * (int)sizeof(cplx);
+constexpr bool kPlaneFive = kPlane && Mid2<P>::OK;
 #ifdef PCB_EMU
 constexpr bool kPlaneCoupled = false;      // thread-block clusters are not emulated: the coupled dielectric keeps the five-pass path there
 #else
@@ -82,6 +83,38 @@ constexpr int kStageXT = 3 * LX * (P::R1 * P::R2P + 1) * (int)sizeof(cplx);
 
 constexpr int GX = (P::N * P::N + LX - 1) / LX;          // x tiles per column
 constexpr int GL = ((P::N + 7) / 8) * P::N;              // strided-line tiles per column
+
+// five-sweep plane pass (k_mid2): instantiated only for the plans it supports
+template <bool ENABLED, class PP>
+struct PlaneFive {
+    static int go(const PcbOp&, const PcbCols&, int, int, const cplx*, cudaStream_t, int) {
+        pcb_set_error("the five-sweep plane pass is not available for N = %d", PP::N);
+        return -1;
+    }
+};
+template <class PP>
+struct PlaneFive<true, PP> {
+    static int go(const PcbOp& op, const PcbCols& cols, int ncols, int pass_id, const cplx* tw, cudaStream_t s, int sms) {
+        typedef Mid2<PP> M2;
+        if (pass_id == PCB_PASS_MASKBITS2) {
+            const long long total = 3LL * PP::N * 8 * PP::N;
+            PCB_LAUNCH((k_mask_bits2<PP>), dim3((unsigned)((total + 255) / 256), 1, 1), dim3(256, 1, 1), 0, s, op, const_cast<unsigned*>(op.mbits2));
+            PCB_CUDA_OK(cudaGetLastError());
+            return 0;
+        }
+        constexpr int smem_tma = PP::N * (PP::N + 1) * (int)sizeof(cplx) + 128;
+#ifndef PCB_EMU
+        if (smem_tma <= 232448) {
+            if (op.diel == PCB_DIEL_NONE) PCB_GO_P((k_mid2<PP, 0, 1>), M2::NTHR, 3 * PP::N, smem_tma, 1);
+            else PCB_GO_P((k_mid2<PP, 1, 1>), M2::NTHR, 3 * PP::N, smem_tma, 1);
+            return 0;
+        }
+#endif
+        if (op.diel == PCB_DIEL_NONE) PCB_GO_P((k_mid2<PP, 0, 0>), M2::NTHR, 3 * PP::N, smem_tma - 128, 1);
+        else PCB_GO_P((k_mid2<PP, 1, 0>), M2::NTHR, 3 * PP::N, smem_tma - 128, 1);
+        return 0;
+    }
+};
 
 // plane-mode passes exist only for sizes with kPlane (the kernels are not even instantiated otherwise)
 template <bool ENABLED, class PP>
@@ -160,7 +193,10 @@ struct PlanePass<true, PP> {
         if (pass_id == PCB_PASS_XFWD_SYM_T) PCB_GO((k_xfwd<PP, LX, NT, 1, 1>), GX, kStageXT);
         else if (pass_id == PCB_PASS_XINV_A_T) PCB_GO((k_xinv<PP, LX, NT, 1, 1>), GX, kStageXT);
         else if (pass_id == PCB_PASS_XINV_H_T) PCB_GO((k_xinv<PP, LX, NT, 2, 1>), GX, kStageXT);
+        else if (pass_id == PCB_PASS_MASKBITS2) return PlaneFive<kPlaneFive, PP>::go(op, cols, ncols, pass_id, tw, s, sms);
         else if (op.diel == PCB_DIEL_NONE || op.diel == PCB_DIEL_CHIRAL) {
+            static const char* ev5 = getenv("PCB200_MID_FIVE");      // PCB200_MID_FIVE=0: the seven-sweep plane pass (k_mid)
+            if (kPlaneFive && (op.diel == PCB_DIEL_NONE || op.mbits2 != nullptr) && !(ev5 && ev5[0] == '0')) return PlaneFive<kPlaneFive, PP>::go(op, cols, ncols, pass_id, tw, s, sms);
             static const char* ev = getenv("PCB200_MID_TMA");
             const bool tma = !(ev && ev[0] == '0') && kSmemMid + 128 <= 232448;      // default; PCB200_MID_TMA=0: cp.async / LDS+STG row loops
             if (tma) {
@@ -194,7 +230,7 @@ int run_pass(const PcbOp& op, const PcbCols& cols, int ncols, int pass_id, const
             else { pcb_set_error("zmid: dielectric type %d has no fused z pass", op.diel); return -1; }
             break;
         case PCB_PASS_XFWD_SYM_T: case PCB_PASS_MID: case PCB_PASS_XINV_A_T: case PCB_PASS_XINV_H_T: case PCB_PASS_MASKBITS:
-        case PCB_PASS_MID_FWD: case PCB_PASS_MID_INV: case PCB_PASS_MASKPLANE: case PCB_PASS_COORDTAB:
+        case PCB_PASS_MID_FWD: case PCB_PASS_MID_INV: case PCB_PASS_MASKPLANE: case PCB_PASS_COORDTAB: case PCB_PASS_MASKBITS2:
             return PlanePass<kPlane, P>::go(op, cols, ncols, pass_id, tw, s, sms);
         default: pcb_set_error("unknown pass id %d", pass_id); return -1;
     }
@@ -224,4 +260,4 @@ int run_apply(const PcbOp& op, const PcbCols& cols, int ncols, int mode, const c
 
 #define PCB_CAT2(a, b) a##b
 #define PCB_CAT(a, b) PCB_CAT2(a, b)
-extern const PcbOpLaunch PCB_CAT(pcb_plan_, PCB_N) = {PCB_N, PCB_R1, PCB_R2, kPlane ? 1 : 0, kPlaneCoupled ? 1 : 0, run_apply, run_pass};
+extern const PcbOpLaunch PCB_CAT(pcb_plan_, PCB_N) = {PCB_N, PCB_R1, PCB_R2, kPlane ? 1 : 0, kPlaneCoupled ? 1 : 0, kPlaneFive ? 1 : 0, run_apply, run_pass};
