@@ -265,17 +265,27 @@ def large_grid_leg(dist, pcb, n, nev, lattice="sc_curv", typ="chiral", check=Tru
     sym = build_ops_for(pcb, n, lattice, alpha, None)
     Diels = getattr(mfd, typ + "_handle")(n, lattice)
     A, H, P = sh.pc_mfd_handle_sharded(comm, sym[0], sym[1], Diels, sym[2], sym[3])
+    col_bytes = 48.0 * n ** 3
     x0 = comm.slab.random_block(m, 99)
-    # operator applies through the exchange (m columns over all ranks), device-timed on the slab stream
+    # operator applies on m columns spread over all ranks, device-timed on the slab stream.  Blocks from work_block() are mapped
+    # into every rank (CUDA IPC), so this takes the peer-memory path: the x passes read / write the slabs of all ranks over NVLink.
+    # The same applies through the NCCL slab exchange (blocks that are not shared) are timed next to it.
+    xs, ys = comm.slab.work_block("bench.x", m), comm.slab.work_block("bench.y", m)
+    xs.assign(x0)
     y0 = comm.slab.empty(m)
-    for _ in range(2):
-        H.op.apply_into(L.APPLY_H, x0, y0)
-    comm.slab.sync(); comm.full.sync()
-    dist.barrier()
-    comm.slab.timer_start()
-    for _ in range(apply_steps):
-        H.op.apply_into(L.APPLY_H, x0, y0)
-    ms_apply = dist.max(comm.slab.timer_stop() / apply_steps)
+
+    def time_applies(src, dstb):
+        for _ in range(2):
+            H.op.apply_into(L.APPLY_H, src, dstb)
+        comm.slab.sync(); comm.full.sync()
+        dist.barrier()
+        comm.slab.timer_start()
+        for _ in range(apply_steps):
+            H.op.apply_into(L.APPLY_H, src, dstb)
+        return dist.max(comm.slab.timer_stop() / apply_steps)
+
+    ms_apply = time_applies(xs, ys)
+    ms_apply_exch = time_applies(x0, y0)
     # the exchange alone: slabs -> whole columns on their owners
     owners = [j % dist.world for j in range(m)]
     win, _ = comm.work_blocks((m + dist.world - 1) // dist.world)
@@ -287,7 +297,6 @@ def large_grid_leg(dist, pcb, n, nev, lattice="sc_curv", typ="chiral", check=Tru
     for _ in range(apply_steps):
         comm.exchange(True, owners, x0, pin)
     ms_exch = dist.max(comm.slab.timer_stop() / apply_steps)
-    col_bytes = 48.0 * n ** 3
     moved = m * col_bytes * (dist.world - 1) / dist.world        # bytes that cross NVLink per exchange (all ranks together)
     ar = C.c_float()
     L.check(L.lib().pcb_comm_allreduce_timed(comm.slab.h, 2 * 96 * 96 * 2, 20, C.byref(ar)), "pcb_comm_allreduce_timed")
@@ -301,6 +310,9 @@ def large_grid_leg(dist, pcb, n, nev, lattice="sc_curv", typ="chiral", check=Tru
            "solver_s": dist.max(float(info[1])) if lam is not None else None, "wall_s": wall,
            "ms_per_iteration": 1e3 * float(info[1]) / max(1, int(info[0])) if lam is not None else None,
            "H_apply_ms_per_block": ms_apply, "op_applies_per_sec": m / ms_apply * 1e3,
+           "H_apply_path": "peer memory (x passes over NVLink, pcb_apply_dist)" if comm.p2p else "NCCL slab exchange",
+           "H_apply_ms_per_block_exchange_path": ms_apply_exch,
+           "H_apply_nvlink_GBps_aggregate": 2 * m * col_bytes * (dist.world - 1) / dist.world / (ms_apply * 1e-3) / 1e9,
            "exchange_ms": ms_exch, "exchange_GBps_aggregate": moved / (ms_exch * 1e-3) / 1e9,
            "exchange_GBps_per_gpu_each_direction": moved / dist.world / (ms_exch * 1e-3) / 1e9,
            "gram_allreduce_us": 1e3 * float(ar.value), "collective": "ncclAllReduce (Gram pair, norms) + grouped ncclSend/ncclRecv (slab exchange)",

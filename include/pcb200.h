@@ -55,6 +55,9 @@ int pcb_ctx_create(int device, int N, pcb_ctx** ctx);
 void pcb_ctx_destroy(pcb_ctx* ctx);
 int pcb_sync(pcb_ctx* ctx);
 int pcb_launch_count(pcb_ctx* ctx, long long* n);   /* kernels launched by this context so far */
+/* pass-structure switches (A/B measurements, tests): "plane", "plane_coupled", "plane_cross" (0 / 1), "mid_five" (-1 auto, 0, 1);
+ * defaults from the PCB200_* environment variables; seen by operators created or updated afterwards */
+int pcb_ctx_option(pcb_ctx* ctx, const char* name, int value);
 /* stream ordering between two contexts of one process without a host sync (16 slots per context): pcb_ctx_record marks the work
  * enqueued on ctx so far, pcb_ctx_wait makes later work of `waiter` start after that mark (the reference is single-stream) */
 int pcb_ctx_record(pcb_ctx* ctx, int slot);
@@ -156,6 +159,19 @@ int pcb_comm_unique_id(void* id128);                                   /* rank 0
 int pcb_comm_init(pcb_ctx* ctx, const void* id128, int rank, int world); /* every rank: ncclCommInitRank on the slab context */
 int pcb_comm_set_host_callbacks(pcb_ctx* ctx, void* allreduce_cb, void* p2p_cb);  /* host-emu test build only */
 int pcb_comm_destroy(pcb_ctx* ctx);
+/* Large-grid mode over PEER MEMORY (NVLink): instead of gathering whole columns with pcb_slab_exchange, the first and the last
+ * FFT pass of the operator read and write the slabs of all ranks in place (CUDA IPC mappings), tile by tile, so the transfer
+ * overlaps the transforms and no staging copy of the block exists.
+ *   pcb_comm_share   collective: peers[g] <- rank g's allocation `dptr` (base of a pcb_malloc block) mapped into this process
+ *   pcb_comm_unshare closes the mappings
+ *   pcb_comm_barrier stream-ordered barrier over the ranks (one-element ncclAllReduce on the context's stream)
+ *   pcb_apply_dist   PCB_APPLY_A / PCB_APPLY_H on `ncols` columns owned by this rank: src[j*world+g] / dst[j*world+g] are column
+ *                    j's input / output slab on rank g, zb[0..world] the slab boundaries, xcopy[j] / work[j] local full columns */
+int pcb_comm_share(pcb_ctx* ctx, void* dptr, void** peers);
+int pcb_comm_unshare(pcb_ctx* ctx, void** peers);
+int pcb_comm_barrier(pcb_ctx* ctx);
+int pcb_apply_dist(pcb_op* op, int mode, int ncols, const void* const* src, void* const* dst, const int* zb, int world,
+                   void* const* xcopy, void* const* work);
 /* measurement aid: average device time (ms) of one NCCL all-reduce of `count` doubles over the communicator */
 int pcb_comm_allreduce_timed(pcb_ctx* ctx, long long count, int reps, float* ms);
 /* slab layout <-> whole columns on their owner rank, one grouped ncclSend/ncclRecv per call (see pcb_capi.cu) */

@@ -29,6 +29,7 @@ SIGNATURES = {
     "pcb_ctx_destroy": (None, [C.c_void_p]),
     "pcb_sync": (C.c_int, [C.c_void_p]),
     "pcb_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_longlong)]),
+    "pcb_ctx_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "pcb_ctx_record": (C.c_int, [C.c_void_p, C.c_int]),
     "pcb_ctx_wait": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "pcb_mem_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
@@ -66,6 +67,10 @@ SIGNATURES = {
     "pcb_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "pcb_comm_set_host_callbacks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "pcb_comm_destroy": (C.c_int, [C.c_void_p]),
+    "pcb_comm_share": (C.c_int, [C.c_void_p, C.c_void_p, c_void_pp]),
+    "pcb_comm_unshare": (C.c_int, [C.c_void_p, c_void_pp]),
+    "pcb_comm_barrier": (C.c_int, [C.c_void_p]),
+    "pcb_apply_dist": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_void_pp, c_void_pp, C.POINTER(C.c_int), C.c_int, c_void_pp, c_void_pp]),
     "pcb_comm_allreduce_timed": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.POINTER(C.c_float)]),
     "pcb_slab_exchange": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), c_void_pp, c_void_pp]),
 }

@@ -43,6 +43,7 @@ struct PcbNccl {
     int (*CommInitRank)(void**, int, PcbNcclId, int) = nullptr;
     int (*CommDestroy)(void*) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
     int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
@@ -71,6 +72,7 @@ struct pcb_ctx {
     cudaStream_t stream = nullptr;
     const PcbOpLaunch* plan = nullptr;
     cplx* tw = nullptr;             // [R1][R2] forward twiddles exp(-2 pi i k1 n2 / N)
+    PcbDist* ddist = nullptr;       // large-grid mode over peer memory: device copy of the slab pointer table of the current apply
     int* ctab = nullptr;            // plane mode: slot -> index and index -> slot tables of the plan (k_coord_tables)
     double* partial = nullptr;      // reduction partials (device)
     size_t partial_bytes = 0;
@@ -87,6 +89,7 @@ struct pcb_ctx {
     int use_plane = 1;              // PCB200_PLANE=0 forces the five-pass operator (A/B measurements)
     int use_plane_coupled = 1;      // PCB200_PLANE_COUPLED=0: coupled 3x3 dielectric on the five-pass path
     int use_plane_cross = 1;        // PCB200_PLANE_CROSS=0: cross-DoF dielectric on the split five-pass path (7 kernels)
+    int use_mid_five = -1;          // five-sweep plane pass k_mid2: -1 where it is the faster form (R2 >= 15), 0 never, 1 wherever it exists
     // pcb_apply_host pipeline: copy streams, two slots of (row-major staging in/out, planar columns in/out), events
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cplx* hp_buf = nullptr;         // one allocation: 2 slots x 4 regions of R x hp_cols elements
@@ -201,6 +204,7 @@ static int ctx_create(int device, int N, int z0, int z1, pcb_ctx** out) {
     { const char* e = getenv("PCB200_PLANE"); c->use_plane = (plan->plane_mode && !(e && e[0] == '0')) ? 1 : 0; }
     { const char* e = getenv("PCB200_PLANE_COUPLED"); c->use_plane_coupled = !(e && e[0] == '0'); }
     { const char* e = getenv("PCB200_PLANE_CROSS"); c->use_plane_cross = !(e && e[0] == '0'); }
+    { const char* e = getenv("PCB200_MID_FIVE"); c->use_mid_five = e ? (e[0] == '0' ? 0 : 1) : -1; }
 #ifndef PCB_EMU
     cudaDeviceProp prop;
     PCB_CUDA_OK_OR(cudaGetDeviceProperties(&prop, device), delete c);
@@ -239,6 +243,7 @@ void pcb_ctx_destroy(pcb_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->tw) cudaFree(c->tw);
     if (c->ctab) cudaFree(c->ctab);
+    if (c->ddist) cudaFree(c->ddist);
     if (c->partial) cudaFree(c->partial);
     if (c->dsmall) cudaFree(c->dsmall);
     if (c->scratch) cudaFree(c->scratch);
@@ -255,6 +260,17 @@ void pcb_ctx_destroy(pcb_ctx* c) {
 }
 int pcb_sync(pcb_ctx* c) { PCB_CUDA_OK(cudaStreamSynchronize(c->stream)); PCB_CUDA_OK(cudaGetLastError()); return 0; }
 int pcb_launch_count(pcb_ctx* c, long long* n) { *n = c->launches; return 0; }
+/* Pass-structure switches of a context (defaults come from the PCB200_* environment variables at pcb_ctx_create; operators
+ * created or updated afterwards see the new value): "plane", "plane_coupled", "plane_cross" (0 / 1), "mid_five" (-1 auto, 0, 1). */
+int pcb_ctx_option(pcb_ctx* c, const char* name, int value) {
+    PCB_CHECK_ARG(c && name, "null");
+    if (!strcmp(name, "plane")) c->use_plane = (value && c->plan->plane_mode) ? 1 : 0;
+    else if (!strcmp(name, "plane_coupled")) c->use_plane_coupled = value ? 1 : 0;
+    else if (!strcmp(name, "plane_cross")) c->use_plane_cross = value ? 1 : 0;
+    else if (!strcmp(name, "mid_five")) c->use_mid_five = value < 0 ? -1 : (value ? 1 : 0);
+    else { pcb_set_error("pcb_ctx_option: unknown option %s", name); return -2; }
+    return 0;
+}
 /* Stream ordering between two contexts of one process (large-grid mode: the slab context's exchange and the full context's
  * operator run on their own streams): pcb_ctx_record marks "everything enqueued on ctx so far" in slot idx; pcb_ctx_wait makes
  * all LATER work of `waiter` start only after that mark.  No host synchronisation. */
@@ -471,6 +487,8 @@ static void op_fill(pcb_op* o, double gamma, double shift, double pshift, pcb_di
     o->d.maskp = diel ? diel->maskp : nullptr;
     o->d.mbits2 = diel ? diel->mbits2 : nullptr;
     o->d.ctab = c->ctab;
+    o->d.dist = nullptr;
+    o->d.mid_five = (c->plan->plane_five && (c->use_mid_five == 1 || (c->use_mid_five == -1 && c->plan->r2 >= 15))) ? 1 : 0;
     for (int i = 0; i < 3; ++i) {
         o->d.ediag[i] = diel ? diel->ediag[i] : 1.0;
         o->d.eoff[i] = diel ? diel->eoff[i] : cmake(0.0, 0.0);
@@ -548,6 +566,58 @@ static int apply_structure(const pcb_op* o) {
     return diel == PCB_DIEL_CROSSDOF ? PCB_STRUCT_CROSS7 : PCB_STRUCT_FIVE;
 }
 
+// A / H on kc columns (cols.in -> cols.out).  dist: the x passes read / write the slabs of all ranks through o->d.dist
+// (large-grid mode over peer memory); cols.in then holds the local X copies and cols.out local work columns.
+static int apply_AH(pcb_op* o, int mode, PcbCols& cols, int kc, int j0, bool dist) {
+    pcb_ctx* c = o->ctx;
+    const PcbOpLaunch* pl = c->plan;
+    const int first = dist ? PCB_PASS_XFWD_SYM_D : PCB_PASS_XFWD_SYM, first_t = dist ? PCB_PASS_XFWD_SYM_TD : PCB_PASS_XFWD_SYM_T;
+    const int last = (mode == PCB_APPLY_A) ? (dist ? PCB_PASS_XINV_A_D : PCB_PASS_XINV_A) : (dist ? PCB_PASS_XINV_H_D : PCB_PASS_XINV_H);
+    const int last_t = (mode == PCB_APPLY_A) ? (dist ? PCB_PASS_XINV_A_TD : PCB_PASS_XINV_A_T) : (dist ? PCB_PASS_XINV_H_TD : PCB_PASS_XINV_H_T);
+    const int st = apply_structure(o);
+    if ((mode == PCB_APPLY_H && st != PCB_STRUCT_PLANE) || st == PCB_STRUCT_CROSS5 || dist)
+        for (int j = 0; j < kc; ++j)
+            if (cols.in[j] == cols.out[j]) {
+                pcb_set_error("pcb_apply: in[%d] == out[%d]; this pass structure re-reads X / uses out as work space, use distinct columns", j0 + j, j0 + j);
+                return -2;
+            }
+    if (st == PCB_STRUCT_PLANE) {
+        // three passes: x forward -> transposed scratch, fused y/z/M/z/y on (i1,i2) planes, x inverse -> out
+        if (ensure_scratch(c, sizeof(cplx) * (size_t)c->R * (size_t)kc)) return -1;
+        for (int j = 0; j < kc; ++j) cols.wrk[j] = c->scratch + (size_t)j * c->R;
+        const int seq[3] = {first_t, PCB_PASS_MID, last_t};
+        for (int i = 0; i < 3; ++i) if (pl->pass(o->d, cols, kc, seq[i], c->tw, c->stream, c->sms)) return -1;
+        c->launches += 3;
+    } else if (st == PCB_STRUCT_CROSS5) {
+        // x forward -> scratch, forward half of the plane pass in place, stencil scratch -> out (slot layout),
+        // inverse half out -> scratch, x inverse scratch -> out
+        if (ensure_scratch(c, sizeof(cplx) * (size_t)c->R * (size_t)kc)) return -1;
+        for (int j = 0; j < kc; ++j) cols.wrk[j] = c->scratch + (size_t)j * c->R;
+        if (pl->pass(o->d, cols, kc, first_t, c->tw, c->stream, c->sms)) return -1;
+        if (pl->pass(o->d, cols, kc, PCB_PASS_MID_FWD, c->tw, c->stream, c->sms)) return -1;
+        if (launch_crossdof_t(o, kc, cols)) return -1;
+        if (pl->pass(o->d, cols, kc, PCB_PASS_MID_INV, c->tw, c->stream, c->sms)) return -1;
+        if (pl->pass(o->d, cols, kc, last_t, c->tw, c->stream, c->sms)) return -1;
+        c->launches += 4;   // + the stencil launch counted in launch_crossdof_t
+    } else if (st == PCB_STRUCT_FIVE) {
+        const int seq[5] = {first, PCB_PASS_YFWD, PCB_PASS_ZMID, PCB_PASS_YINV, last};
+        for (int i = 0; i < 5; ++i) if (pl->pass(o->d, cols, kc, seq[i], c->tw, c->stream, c->sms)) return -1;
+        c->launches += 5;
+    } else {
+        // cross-DoF M is a stencil in real space: forward passes into scratch, M scratch -> out, inverse in place
+        if (ensure_scratch(c, sizeof(cplx) * (size_t)c->R * (size_t)kc)) return -1;
+        PcbCols tmp = cols;
+        for (int j = 0; j < kc; ++j) tmp.out[j] = c->scratch + (size_t)j * c->R;
+        const int fwd[3] = {first, PCB_PASS_YFWD, PCB_PASS_ZFWD};
+        for (int i = 0; i < 3; ++i) if (pl->pass(o->d, tmp, kc, fwd[i], c->tw, c->stream, c->sms)) return -1;
+        if (launch_crossdof(o, kc, tmp.out, cols.out)) return -1;
+        const int inv[3] = {PCB_PASS_ZINV, PCB_PASS_YINV, last};
+        for (int i = 0; i < 3; ++i) if (pl->pass(o->d, cols, kc, inv[i], c->tw, c->stream, c->sms)) return -1;
+        c->launches += 6;   // + the stencil launch counted in launch_crossdof
+    }
+    return 0;
+}
+
 int pcb_apply(pcb_op* o, int mode, int ncols, const void* const* in, void* const* out) {
     PCB_CHECK_ARG(o && in && out && ncols > 0, "bad arguments");
     pcb_ctx* c = o->ctx;
@@ -570,51 +640,9 @@ int pcb_apply(pcb_op* o, int mode, int ncols, const void* const* in, void* const
                 if (pl->apply(o->d, cols, kc, mode == PCB_APPLY_FFT ? 0 : 1, c->tw, c->stream, c->sms)) return -1;
                 c->launches += 3;
                 break;
-            case PCB_APPLY_A: case PCB_APPLY_H: {
-                const int last = (mode == PCB_APPLY_A) ? PCB_PASS_XINV_A : PCB_PASS_XINV_H;
-                const int last_t = (mode == PCB_APPLY_A) ? PCB_PASS_XINV_A_T : PCB_PASS_XINV_H_T;
-                const int st = apply_structure(o);
-                if ((mode == PCB_APPLY_H && st != PCB_STRUCT_PLANE) || st == PCB_STRUCT_CROSS5)
-                    for (int j = 0; j < kc; ++j)
-                        if (cols.in[j] == cols.out[j]) {
-                            pcb_set_error("pcb_apply: in[%d] == out[%d]; this pass structure re-reads X / uses out as work space, use distinct columns", j0 + j, j0 + j);
-                            return -2;
-                        }
-                if (st == PCB_STRUCT_PLANE) {
-                    // three passes: x forward -> transposed scratch, fused y/z/M/z/y on (i1,i2) planes, x inverse -> out
-                    if (ensure_scratch(c, sizeof(cplx) * (size_t)c->R * (size_t)kc)) return -1;
-                    for (int j = 0; j < kc; ++j) cols.wrk[j] = c->scratch + (size_t)j * c->R;
-                    const int seq[3] = {PCB_PASS_XFWD_SYM_T, PCB_PASS_MID, last_t};
-                    for (int i = 0; i < 3; ++i) if (pl->pass(o->d, cols, kc, seq[i], c->tw, c->stream, c->sms)) return -1;
-                    c->launches += 3;
-                } else if (st == PCB_STRUCT_CROSS5) {
-                    // x forward -> scratch, forward half of the plane pass in place, stencil scratch -> out (slot layout),
-                    // inverse half out -> scratch, x inverse scratch -> out
-                    if (ensure_scratch(c, sizeof(cplx) * (size_t)c->R * (size_t)kc)) return -1;
-                    for (int j = 0; j < kc; ++j) cols.wrk[j] = c->scratch + (size_t)j * c->R;
-                    if (pl->pass(o->d, cols, kc, PCB_PASS_XFWD_SYM_T, c->tw, c->stream, c->sms)) return -1;
-                    if (pl->pass(o->d, cols, kc, PCB_PASS_MID_FWD, c->tw, c->stream, c->sms)) return -1;
-                    if (launch_crossdof_t(o, kc, cols)) return -1;
-                    if (pl->pass(o->d, cols, kc, PCB_PASS_MID_INV, c->tw, c->stream, c->sms)) return -1;
-                    if (pl->pass(o->d, cols, kc, last_t, c->tw, c->stream, c->sms)) return -1;
-                    c->launches += 4;   // + the stencil launch counted in launch_crossdof_t
-                } else if (st == PCB_STRUCT_FIVE) {
-                    const int seq[5] = {PCB_PASS_XFWD_SYM, PCB_PASS_YFWD, PCB_PASS_ZMID, PCB_PASS_YINV, last};
-                    for (int i = 0; i < 5; ++i) if (pl->pass(o->d, cols, kc, seq[i], c->tw, c->stream, c->sms)) return -1;
-                    c->launches += 5;
-                } else {
-                    // cross-DoF M is a stencil in real space: forward passes into scratch, M scratch -> out, inverse in place
-                    if (ensure_scratch(c, sizeof(cplx) * (size_t)c->R * (size_t)kc)) return -1;
-                    PcbCols tmp = cols;
-                    for (int j = 0; j < kc; ++j) tmp.out[j] = c->scratch + (size_t)j * c->R;
-                    const int fwd[3] = {PCB_PASS_XFWD_SYM, PCB_PASS_YFWD, PCB_PASS_ZFWD};
-                    for (int i = 0; i < 3; ++i) if (pl->pass(o->d, tmp, kc, fwd[i], c->tw, c->stream, c->sms)) return -1;
-                    if (launch_crossdof(o, kc, tmp.out, cols.out)) return -1;
-                    const int inv[3] = {PCB_PASS_ZINV, PCB_PASS_YINV, last};
-                    for (int i = 0; i < 3; ++i) if (pl->pass(o->d, cols, kc, inv[i], c->tw, c->stream, c->sms)) return -1;
-                    c->launches += 6;   // + the stencil launch counted in launch_crossdof
-                }
-            } break;
+            case PCB_APPLY_A: case PCB_APPLY_H:
+                if (int rc = apply_AH(o, mode, cols, kc, j0, false)) return rc;
+                break;
             case PCB_APPLY_P: {
                 PcbResidArgs a;
                 for (int j = 0; j < kc; ++j) { a.x[j] = cols.in[j]; a.hx[j] = nullptr; a.w[j] = cols.out[j]; a.lambda[j] = 0.0; }
@@ -1000,7 +1028,7 @@ static int nccl_load() {
     *(void**)(&g_nccl.field) = dlsym(g_nccl.lib, name);                             \
     if (!g_nccl.field) { pcb_set_error("libnccl: missing symbol %s", name); return -4; }
     PCB_SYM(GetUniqueId, "ncclGetUniqueId") PCB_SYM(CommInitRank, "ncclCommInitRank") PCB_SYM(CommDestroy, "ncclCommDestroy")
-    PCB_SYM(AllReduce, "ncclAllReduce") PCB_SYM(Send, "ncclSend") PCB_SYM(Recv, "ncclRecv")
+    PCB_SYM(AllReduce, "ncclAllReduce") PCB_SYM(AllGather, "ncclAllGather") PCB_SYM(Send, "ncclSend") PCB_SYM(Recv, "ncclRecv")
     PCB_SYM(GroupStart, "ncclGroupStart") PCB_SYM(GroupEnd, "ncclGroupEnd") PCB_SYM(GetErrorString, "ncclGetErrorString")
 #undef PCB_SYM
     return 0;
@@ -1055,6 +1083,93 @@ int pcb_comm_destroy(pcb_ctx* c) {
     delete c->comm;
     c->comm = nullptr;
     return 0;
+}
+
+/* ---- large-grid mode over peer memory ------------------------------------------------------------------------------
+ * pcb_comm_share: map one allocation of every rank into every rank (CUDA IPC; the handles travel by ncclAllGather).
+ * dptr must be the base of a pcb_malloc allocation; peers[g] receives rank g's allocation as seen from this process
+ * (peers[rank] = dptr).  Collective over the communicator. */
+int pcb_comm_share(pcb_ctx* c, void* dptr, void** peers) {
+    PCB_CHECK_ARG(c && c->comm && dptr && peers, "bad arguments / no communicator");
+#ifdef PCB_EMU
+    pcb_set_error("pcb_comm_share: peer memory needs the CUDA build (the host-emulation build uses the slab exchange)");
+    return -2;
+#else
+    PcbComm* cm = c->comm;
+    PCB_CHECK_ARG(cm->world <= PCB_MAXW, "at most 8 ranks");
+    PCB_CUDA_OK(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    PCB_CUDA_OK(cudaIpcGetMemHandle(&h, dptr));
+    const size_t hs = sizeof(cudaIpcMemHandle_t);
+    if (ensure_dsmall(c, sizeof(cplx) * 2 * PCB_MAXL * PCB_MAXL + 65536)) return -1;
+    if (ensure_hstage(c, sizeof(cplx) * 2 * PCB_MAXL * PCB_MAXL + 65536)) return -1;
+    char* dall = (char*)c->dsmall;
+    PCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+    memcpy(c->hstage, &h, hs);
+    PCB_CUDA_OK(cudaMemcpyAsync(dall + cm->rank * hs, c->hstage, hs, cudaMemcpyHostToDevice, c->stream));
+    const int rc = g_nccl.AllGather(dall + cm->rank * hs, dall, hs, PCB_NCCL_UINT8, cm->nccl, c->stream);
+    if (rc != 0) { pcb_set_error("ncclAllGather failed: %s", g_nccl.GetErrorString(rc)); return -4; }
+    PCB_CUDA_OK(cudaMemcpyAsync(c->hstage, dall, hs * cm->world, cudaMemcpyDeviceToHost, c->stream));
+    PCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+    for (int g = 0; g < cm->world; ++g) {
+        if (g == cm->rank) { peers[g] = dptr; continue; }
+        cudaIpcMemHandle_t hg;
+        memcpy(&hg, (char*)c->hstage + g * hs, hs);
+        PCB_CUDA_OK(cudaIpcOpenMemHandle(&peers[g], hg, cudaIpcMemLazyEnablePeerAccess));
+    }
+    return 0;
+#endif
+}
+int pcb_comm_unshare(pcb_ctx* c, void** peers) {
+    PCB_CHECK_ARG(c && c->comm && peers, "bad arguments / no communicator");
+#ifndef PCB_EMU
+    PCB_CUDA_OK(cudaSetDevice(c->device));
+    PCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+    for (int g = 0; g < c->comm->world; ++g)
+        if (g != c->comm->rank && peers[g]) { PCB_CUDA_OK(cudaIpcCloseMemHandle(peers[g])); peers[g] = nullptr; }
+#endif
+    return 0;
+}
+/* Stream-ordered barrier over the communicator (a one-element all-reduce on the context's stream): work enqueued behind it
+ * starts only after every rank's work enqueued before its own barrier call has finished. */
+int pcb_comm_barrier(pcb_ctx* c) {
+    PCB_CHECK_ARG(c && c->comm, "no communicator");
+    PCB_CUDA_OK(cudaSetDevice(c->device));
+    if (ensure_dsmall(c, sizeof(cplx) * 2 * PCB_MAXL * PCB_MAXL + 65536)) return -1;
+    return comm_allreduce(c, (double*)((char*)c->dsmall + sizeof(cplx) * 2 * PCB_MAXL * PCB_MAXL), 1);
+}
+/* A / H on whole columns whose data live as slabs on the `world` ranks: src[j * world + g] / dst[j * world + g] = column j's slab
+ * on rank g as mapped by pcb_comm_share (zb: slab boundaries).  xcopy[j] and work[j] are LOCAL full columns of this context
+ * (copy of X for the last pass; work space).  The slab gather / scatter of pcb_slab_exchange is fused into the first and the
+ * last FFT pass, which read and write peer memory over NVLink tile by tile.  Caller: order the ranks with pcb_comm_barrier. */
+int pcb_apply_dist(pcb_op* o, int mode, int ncols, const void* const* src, void* const* dst, const int* zb, int world,
+                   void* const* xcopy, void* const* work) {
+    PCB_CHECK_ARG(o && src && dst && zb && xcopy && work && ncols > 0 && ncols <= PCB_MAXC_DIST && world >= 1 && world <= PCB_MAXW, "bad arguments");
+    PCB_CHECK_ARG(mode == PCB_APPLY_A || mode == PCB_APPLY_H, "mode must be PCB_APPLY_A or PCB_APPLY_H");
+    pcb_ctx* c = o->ctx;
+    PCB_CHECK_ARG(c->nloc == c->nn, "needs a full (non-slab) context");
+    PCB_CHECK_ARG(c->N % c->plan->lx == 0, "grid size not supported by the peer-memory passes (x tiles must not straddle planes)");
+    PCB_CHECK_ARG(zb[0] == 0 && zb[world] == c->N, "zb must cover [0, N]");
+    PCB_CUDA_OK(cudaSetDevice(c->device));
+    if (!c->ddist) PCB_CUDA_OK(cudaMalloc(&c->ddist, sizeof(PcbDist)));
+    if (ensure_hstage(c, sizeof(cplx) * 2 * PCB_MAXL * PCB_MAXL + 65536)) return -1;
+    PCB_CUDA_OK(cudaStreamSynchronize(c->stream));      // the staging table of the previous call has been consumed
+    PcbDist* hd = (PcbDist*)c->hstage;
+    memset(hd, 0, sizeof(PcbDist));
+    hd->world = world;
+    for (int g = 0; g <= world; ++g) hd->zb[g] = zb[g];
+    PcbCols cols;
+    memset(&cols, 0, sizeof cols);
+    for (int j = 0; j < ncols; ++j) {
+        for (int g = 0; g < world; ++g) { hd->src[j][g] = (const cplx*)src[j * world + g]; hd->dst[j][g] = (cplx*)dst[j * world + g]; }
+        cols.in[j] = (const cplx*)xcopy[j];
+        cols.out[j] = (cplx*)work[j];
+    }
+    PCB_CUDA_OK(cudaMemcpyAsync(c->ddist, hd, sizeof(PcbDist), cudaMemcpyHostToDevice, c->stream));
+    o->d.dist = c->ddist;
+    const int rc = apply_AH(o, mode, cols, ncols, 0, true);
+    o->d.dist = nullptr;
+    return rc;
 }
 
 /* Measurement aid: `reps` all-reduces (sum) of `count` doubles over the communicator on the context's stream, timed with CUDA

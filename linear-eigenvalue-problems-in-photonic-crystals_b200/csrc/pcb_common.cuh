@@ -100,6 +100,18 @@ void pcb_set_error(const char* fmt, ...);
 // replacing the reference's 192*N^3-byte symbol arrays (fft_blocks, discretization.py:301-346).
 enum { PCB_DIEL_NONE = 0, PCB_DIEL_CHIRAL = 1, PCB_DIEL_TRIVIAL = 2, PCB_DIEL_CROSSDOF = 3 };
 
+// Large-grid mode over peer memory (NVLink): the columns of one distributed apply live as SLABS on all ranks -- rank g holds the
+// i2 planes [zb[g], zb[g+1]) of every column as [c][local cell] -- and the x passes of the operator read / write them in place
+// through pointers mapped with CUDA IPC (device-resident table, one per context).
+#define PCB_MAXC_DIST 32
+#define PCB_MAXW 8
+struct PcbDist {
+    int world;
+    int zb[PCB_MAXW + 1];
+    const double2* src[PCB_MAXC_DIST][PCB_MAXW];   // input column j, slab of rank g
+    double2* dst[PCB_MAXC_DIST][PCB_MAXW];         // output column j, slab of rank g
+};
+
 struct PcbOp {
     int N;
     long long nn;             // N^3
@@ -115,6 +127,8 @@ struct PcbOp {
     const unsigned* mbits;      // plane mode: [c][i0][slot][k1] words, bit k2 = component c of (i0, i1 = coord(slot), i2 = lout(k1,k2)) in Omega_1
     const unsigned* mbits2;     // five-sweep plane pass (k_mid2): [c][i0][d][col] words, bit k2 (k_mask_bits2)
     const unsigned char* maskp; // plane mode, coupled dielectric: the byte mask in plane-slot order, [i0][row][col] = mask(i0, coord(col), coord(row))
+    int mid_five;               // plane mode: 1 = the five-sweep plane pass (k_mid2), 0 = the seven-sweep one (k_mid)
+    const PcbDist* dist;        // large-grid mode over peer memory: slab pointers of the columns (device memory), else null
     const int* ctab;            // plane mode: [0, N) slot -> grid index (coord), [N, 2N) grid index -> slot
     double ediag[3];          // diagonal entries inside Omega_1 (chiral: 1/eps for all three)
     cplx eoff[3];             // eps_12, eps_13, eps_23 (trivial / crossdof)

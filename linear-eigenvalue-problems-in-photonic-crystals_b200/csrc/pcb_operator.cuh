@@ -163,7 +163,11 @@ PCB_D void pcb_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0
 // padding in shared memory (RS) to keep the row-fastest reads of that store pattern conflict-free.
 // (Round 2, measured and removed: every CTA asking L2 -- prefetch.global.L2 -- for the rows of the tile 296 / 592 / 1184 blocks ahead,
 // i.e. what a successor CTA on the same SM loads one CTA lifetime later: 0.57-0.59 ms instead of 0.53 ms at N = 120, 16 columns.)
-template <class P, int LX, int NT, int SYM, int TRN = 0>
+// DIST = 1 (large-grid mode over peer memory): the input column is not local -- its i2 planes are slabs on the ranks of the job,
+// read here through the IPC-mapped pointers of op.dist (a tile of rows lies in one plane, hence in one rank's slab); the tile is
+// also copied to the local column cols.in[col], which the inverse x pass re-reads for the gamma K_B x + shift x term, so every
+// element crosses NVLink once per direction.  The slab gather of the exchange path is fused into this pass.
+template <class P, int LX, int NT, int SYM, int TRN = 0, int DIST = 0>
 __global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * (P::R1 * P::R2P + TRN) * 16, P::R1, 4)) k_xfwd(PcbOp op, PcbCols cols, const cplx* __restrict__ tw) {
     constexpr int N = P::N, R1 = P::R1, R2 = P::R2, R2P = P::R2P;
     constexpr int RS = R1 * R2P + TRN;      // row stride in shared memory
@@ -175,6 +179,18 @@ __global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * (P::R1 * P::R2P + TR
     const int row0 = blockIdx.x * LX;
     const int nrows = N * N;
     const int tid = threadIdx.x;
+    const cplx* __restrict__ Xs = X;      // where the tile is read from, component stride cs
+    long long cs = nn;
+    cplx* __restrict__ Xc = nullptr;      // DIST: local copy of the column
+    if (DIST) {
+        const PcbDist* __restrict__ d = op.dist;
+        const int i2t = row0 / N;
+        int g = 0;
+        while (g + 1 < d->world && i2t >= d->zb[g + 1]) ++g;
+        cs = (long long)(d->zb[g + 1] - d->zb[g]) * N * N;
+        Xs = d->src[col][g] - (long long)d->zb[g] * N * N;
+        Xc = const_cast<cplx*>(X);
+    }
 
     for (int item = tid; item < LX * R2; item += NT) {
         const int r = item / R2, n2 = item % R2;
@@ -197,7 +213,11 @@ __global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * (P::R1 * P::R2P + TR
             const long long e = (long long)row * N + i0;
             cplx x[3];
             PCB_UNROLL
-            for (int c = 0; c < 3; ++c) x[c] = X[c * nn + e];
+            for (int c = 0; c < 3; ++c) x[c] = Xs[c * cs + e];
+            if (DIST) {
+                PCB_UNROLL
+                for (int c = 0; c < 3; ++c) Xc[c * nn + e] = x[c];
+            }
             if (SYM) {
                 cplx a[3], z[3];
                 PCB_UNROLL
@@ -252,7 +272,10 @@ __global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * (P::R1 * P::R2P + TR
 // Reads the work column W (in Fourier-x order), the source column X (MODE 2) and writes OUT
 // (OUT may alias W: each CTA only touches its own rows).
 // ---------------------------------------------------------------------------------------
-template <class P, int LX, int NT, int MODE, int TRN = 0>
+// DIST = 1 (large-grid mode over peer memory): the result rows go straight into the output column's slab on the rank that owns
+// their i2 plane (IPC-mapped pointers of op.dist) -- the slab scatter of the exchange path fused into this pass; X is re-read
+// from the local copy the forward pass left in cols.in[col].
+template <class P, int LX, int NT, int MODE, int TRN = 0, int DIST = 0>
 __global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * (P::R1 * P::R2P + TRN) * 16, P::R1, 4)) k_xinv(PcbOp op, PcbCols cols, const cplx* __restrict__ tw) {
     constexpr int N = P::N, R1 = P::R1, R2 = P::R2, R2P = P::R2P;
     constexpr int RS = R1 * R2P + TRN;      // row stride in shared memory (see k_xfwd)
@@ -266,6 +289,16 @@ __global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * (P::R1 * P::R2P + TR
     const int nrows = N * N;
     const int nr = (nrows - row0 < LX) ? nrows - row0 : LX;      // rows of this tile
     const int tid = threadIdx.x;
+    cplx* __restrict__ Wd = W;            // where the tile is stored, component stride cs
+    long long cs = nn;
+    if (DIST) {
+        const PcbDist* __restrict__ d = op.dist;
+        const int i2t = row0 / N;
+        int g = 0;
+        while (g + 1 < d->world && i2t >= d->zb[g + 1]) ++g;
+        cs = (long long)(d->zb[g + 1] - d->zb[g]) * N * N;
+        Wd = d->dst[col][g] - (long long)d->zb[g] * N * N;
+    }
 
     if (MODE == 2) {   // the epilogue re-reads X: pull this tile's lines (3 contiguous chunks) towards L2 now
         const int lines = (nr * N * (int)sizeof(cplx) + 127) / 128;
@@ -354,7 +387,7 @@ __global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * (P::R1 * P::R2P + TR
                 for (int c = 0; c < 3; ++c) z[c] = u[c];
             }
             PCB_UNROLL
-            for (int c = 0; c < 3; ++c) W[c * nn + (long long)row0 * N + e] = z[c];
+            for (int c = 0; c < 3; ++c) Wd[c * cs + (long long)row0 * N + e] = z[c];
         }
     }
 }
@@ -1251,6 +1284,7 @@ struct PcbOpLaunch {
     int plane_mode;   // 1: the fused (i1,i2)-plane pass exists for this size (N % 8 == 0 and the plane fits in shared memory)
     int plane_coupled; // 1: ... also for the coupled 3x3 dielectric (clusters of three CTAs; CUDA build only)
     int plane_five;    // 1: the five-sweep form of the plane pass (k_mid2) exists: N = 8 R2, R2 odd
+    int lx;            // rows per tile of the x passes (a tile must lie in one i2 plane for the peer-memory passes: N % lx == 0)
     // mode: 0 plain 3-D FFT forward, 1 plain inverse (1/N^3), 2 A = AMA^H, 3 H = AMA^H + gamma B^H B + shift
     int (*apply)(const PcbOp& op, const PcbCols& cols, int ncols, int mode, const cplx* tw, cudaStream_t s, int sms);
     // split passes used by the cross-DoF dielectric and by the tests: pass ids below
@@ -1263,6 +1297,9 @@ enum { PCB_PASS_XFWD_SYM = 0, PCB_PASS_XFWD = 1, PCB_PASS_YFWD = 2, PCB_PASS_ZFW
        PCB_PASS_MASKBITS = 14 /* set-up: op.mask -> (unsigned*)op.mbits */,
        PCB_PASS_MID_FWD = 15, PCB_PASS_MID_INV = 16 /* halves of the plane pass around the cross-DoF stencil */,
        PCB_PASS_MASKPLANE = 17 /* set-up: op.mask -> (unsigned char*)op.maskp */, PCB_PASS_COORDTAB = 18 /* set-up: (int*)op.ctab */,
-       PCB_PASS_MASKBITS2 = 19 /* set-up: op.mask -> (unsigned*)op.mbits2 (five-sweep plane pass) */ };
+       PCB_PASS_MASKBITS2 = 19 /* set-up: op.mask -> (unsigned*)op.mbits2 (five-sweep plane pass) */,
+       // large-grid mode over peer memory: x passes reading / writing the slabs of all ranks (op.dist)
+       PCB_PASS_XFWD_SYM_D = 20, PCB_PASS_XINV_A_D = 21, PCB_PASS_XINV_H_D = 22,
+       PCB_PASS_XFWD_SYM_TD = 23, PCB_PASS_XINV_A_TD = 24, PCB_PASS_XINV_H_TD = 25 };
 
 const PcbOpLaunch* pcb_find_plan(int N);

@@ -190,13 +190,15 @@ struct PlanePass<true, PP> {
             return 0;
         }
 #endif
-        if (pass_id == PCB_PASS_XFWD_SYM_T) PCB_GO((k_xfwd<PP, LX, NT, 1, 1>), GX, kStageXT);
+        if (pass_id == PCB_PASS_XFWD_SYM_TD) PCB_GO((k_xfwd<PP, LX, NT, 1, 1, 1>), GX, kStageXT);
+        else if (pass_id == PCB_PASS_XINV_A_TD) PCB_GO((k_xinv<PP, LX, NT, 1, 1, 1>), GX, kStageXT);
+        else if (pass_id == PCB_PASS_XINV_H_TD) PCB_GO((k_xinv<PP, LX, NT, 2, 1, 1>), GX, kStageXT);
+        else if (pass_id == PCB_PASS_XFWD_SYM_T) PCB_GO((k_xfwd<PP, LX, NT, 1, 1>), GX, kStageXT);
         else if (pass_id == PCB_PASS_XINV_A_T) PCB_GO((k_xinv<PP, LX, NT, 1, 1>), GX, kStageXT);
         else if (pass_id == PCB_PASS_XINV_H_T) PCB_GO((k_xinv<PP, LX, NT, 2, 1>), GX, kStageXT);
         else if (pass_id == PCB_PASS_MASKBITS2) return PlaneFive<kPlaneFive, PP>::go(op, cols, ncols, pass_id, tw, s, sms);
         else if (op.diel == PCB_DIEL_NONE || op.diel == PCB_DIEL_CHIRAL) {
-            static const char* ev5 = getenv("PCB200_MID_FIVE");      // PCB200_MID_FIVE=0: the seven-sweep plane pass (k_mid)
-            if (kPlaneFive && (op.diel == PCB_DIEL_NONE || op.mbits2 != nullptr) && !(ev5 && ev5[0] == '0')) return PlaneFive<kPlaneFive, PP>::go(op, cols, ncols, pass_id, tw, s, sms);
+            if (kPlaneFive && op.mid_five && (op.diel == PCB_DIEL_NONE || op.mbits2 != nullptr)) return PlaneFive<kPlaneFive, PP>::go(op, cols, ncols, pass_id, tw, s, sms);
             static const char* ev = getenv("PCB200_MID_TMA");
             const bool tma = !(ev && ev[0] == '0') && kSmemMid + 128 <= 232448;      // default; PCB200_MID_TMA=0: cp.async / LDS+STG row loops
             if (tma) {
@@ -223,6 +225,9 @@ int run_pass(const PcbOp& op, const PcbCols& cols, int ncols, int pass_id, const
         case PCB_PASS_XINV:     PCB_GO((k_xinv<P, LX, NT, 0>), GX, kStageX); break;
         case PCB_PASS_XINV_A:   PCB_GO((k_xinv<P, LX, NT, 1>), GX, kStageX); break;
         case PCB_PASS_XINV_H:   PCB_GO((k_xinv<P, LX, NT, 2>), GX, kStageX); break;
+        case PCB_PASS_XFWD_SYM_D: PCB_GO_X((k_xfwd<P, LX, NTX, 1, 0, 1>), GX, kStageX); break;
+        case PCB_PASS_XINV_A_D:   PCB_GO((k_xinv<P, LX, NT, 1, 0, 1>), GX, kStageX); break;
+        case PCB_PASS_XINV_H_D:   PCB_GO((k_xinv<P, LX, NT, 2, 0, 1>), GX, kStageX); break;
         case PCB_PASS_ZMID:
             if (op.diel == PCB_DIEL_NONE) PCB_GO_P((k_zmid<P, 0, NTZ, NSTZ>), NTZ, GL, kSmemZU, 3);
             else if (op.diel == PCB_DIEL_CHIRAL) PCB_GO_P((k_zmid<P, 1, NTZ, NSTZ>), NTZ, GL, kSmemZU, 3);
@@ -231,6 +236,7 @@ int run_pass(const PcbOp& op, const PcbCols& cols, int ncols, int pass_id, const
             break;
         case PCB_PASS_XFWD_SYM_T: case PCB_PASS_MID: case PCB_PASS_XINV_A_T: case PCB_PASS_XINV_H_T: case PCB_PASS_MASKBITS:
         case PCB_PASS_MID_FWD: case PCB_PASS_MID_INV: case PCB_PASS_MASKPLANE: case PCB_PASS_COORDTAB: case PCB_PASS_MASKBITS2:
+        case PCB_PASS_XFWD_SYM_TD: case PCB_PASS_XINV_A_TD: case PCB_PASS_XINV_H_TD:
             return PlanePass<kPlane, P>::go(op, cols, ncols, pass_id, tw, s, sms);
         default: pcb_set_error("unknown pass id %d", pass_id); return -1;
     }
@@ -260,4 +266,4 @@ int run_apply(const PcbOp& op, const PcbCols& cols, int ncols, int mode, const c
 
 #define PCB_CAT2(a, b) a##b
 #define PCB_CAT(a, b) PCB_CAT2(a, b)
-extern const PcbOpLaunch PCB_CAT(pcb_plan_, PCB_N) = {PCB_N, PCB_R1, PCB_R2, kPlane ? 1 : 0, kPlaneCoupled ? 1 : 0, kPlaneFive ? 1 : 0, run_apply, run_pass};
+extern const PcbOpLaunch PCB_CAT(pcb_plan_, PCB_N) = {PCB_N, PCB_R1, PCB_R2, kPlane ? 1 : 0, kPlaneCoupled ? 1 : 0, kPlaneFive ? 1 : 0, LX, run_apply, run_pass};

@@ -57,6 +57,10 @@ class Context:
     def sync(self):
         L.check(self._lib.pcb_sync(self.h), "pcb_sync")
 
+    def option(self, name, value):
+        """Pass-structure switch of this context (pcb_ctx_option); applies to operators created or updated afterwards."""
+        L.check(self._lib.pcb_ctx_option(self.h, name.encode(), int(value)), "pcb_ctx_option")
+
     def record(self, slot):
         """Mark the work enqueued on this context's stream so far (pcb_ctx_record)."""
         L.check(self._lib.pcb_ctx_record(self.h, int(slot)), "pcb_ctx_record")
@@ -134,6 +138,9 @@ class Context:
         if blk is None or blk.k < k:
             pool[tag] = None          # release the smaller block first
             blk = pool[tag] = DeviceBlock(self, int(k))
+            hook = getattr(self, "_on_work_block", None)      # large-grid mode: map the solver's work space into all ranks
+            if hook is not None:
+                hook(blk)
         return blk if blk.k == k else blk.cols(range(k))
 
     def from_host(self, x):

@@ -52,6 +52,44 @@ class SlabComm:
                                                         C.cast(host_callbacks[1], C.c_void_p)), "pcb_comm_set_host_callbacks")
         self._zb_c = (C.c_int * (self.world + 1))(*self.zb)
         self._work = {}
+        # Peer-memory mode (CUDA build, world <= 8): the solver's work blocks S / HS (Context.work_block) are mapped into every
+        # rank with CUDA IPC when they are created -- a collective step, reached by all ranks at the same point of the SPMD
+        # solver -- so that the operator can read and write the slabs in place over NVLink (ShardedOperator.apply_into).
+        self._shared = {}       # allocation base pointer -> (list of peer base pointers, allocation bytes)
+        self.p2p = (host_callbacks is None and L.backend() == "cuda-sm_100a" and self.world <= 8
+                    and os.environ.get("PCB200_LG_P2P", "1") != "0")
+        if self.p2p:
+            self.slab._on_work_block = self.share_block
+        self.rows_of = [3 * (self.zb[g + 1] - self.zb[g]) * self.N ** 2 for g in range(self.world)]
+
+    def share_block(self, blk):
+        """Collective: map the allocation behind `blk` (a slab DeviceBlock) into all ranks."""
+        for a in blk._owners:
+            if a.ptr in self._shared:
+                continue
+            peers = (C.c_void_p * self.world)()
+            L.check(L.lib().pcb_comm_share(self.slab.h, C.c_void_p(a.ptr), peers), "pcb_comm_share")
+            self._shared[a.ptr] = ([int(p or 0) for p in peers], a)
+
+    def peer_pointers(self, blk):
+        """For every column of a slab block: its pointer on each rank, or None when the block is not shared."""
+        out = []
+        stride = 16 * self.slab.R
+        for p in blk.ptrs:
+            hit = None
+            for base, (peers, a) in self._shared.items():
+                if any(o is a for o in blk._owners) and base <= p and (p - base) % stride == 0:
+                    j = (p - base) // stride
+                    hit = [peers[g] + 16 * self.rows_of[g] * j for g in range(self.world)]
+                    break
+            if hit is None:
+                return None
+            out.append(hit)
+        return out
+
+    def barrier(self):
+        """Stream-ordered barrier over the ranks on the slab stream (one-element all-reduce)."""
+        L.check(L.lib().pcb_comm_barrier(self.slab.h), "pcb_comm_barrier")
 
     def exchange(self, to_full, owners, slab_block, full_ptrs):
         own = (C.c_int * len(owners))(*owners)
@@ -80,6 +118,14 @@ class SlabComm:
         return out
 
     def close(self):
+        self.slab.sync()
+        self.full.sync()
+        for base, (peers, a) in list(self._shared.items()):
+            arr = (C.c_void_p * self.world)(*[p if p else None for p in peers])
+            L.check(L.lib().pcb_comm_unshare(self.slab.h, arr), "pcb_comm_unshare")
+        self._shared.clear()
+        self.slab._on_work_block = None
+        self.slab.__dict__.pop("_work_blocks", None)      # shared work space must not outlive its mappings
         L.check(L.lib().pcb_comm_destroy(self.slab.h), "pcb_comm_destroy")
 
 
@@ -115,6 +161,26 @@ class ShardedOperator:
         owners = [j % cm.world for j in range(k)]
         kmax = (k + cm.world - 1) // cm.world                   # most columns any rank owns (slot = j // world)
         win, wout = cm.work_blocks(kmax)
+        if cm.p2p:
+            sp, dp = cm.peer_pointers(src), cm.peer_pointers(dst)
+            if sp is not None and dp is not None:
+                # Peer-memory path: every rank applies the operator to its own columns, reading the input slabs of all ranks in
+                # the first FFT pass and writing the output slabs of all ranks in the last one (pcb_apply_dist); the two
+                # stream-ordered barriers make the producers' writes visible before and the results visible after.
+                mine = [j for j in range(k) if owners[j] == cm.rank]
+                cm.barrier()
+                cm.slab.record(0)
+                if mine:
+                    nm, w = len(mine), cm.world
+                    srcs = (C.c_void_p * (nm * w))(*[sp[j][g] for j in mine for g in range(w)])
+                    dsts = (C.c_void_p * (nm * w))(*[dp[j][g] for j in mine for g in range(w)])
+                    cm.full.wait_for(cm.slab, 0)
+                    L.check(L.lib().pcb_apply_dist(self.full.h, mode, nm, srcs, dsts, cm._zb_c, w,
+                                                   L.ptr_array(win.ptrs[:nm]), L.ptr_array(wout.ptrs[:nm])), "pcb_apply_dist")
+                cm.full.record(1)
+                cm.slab.wait_for(cm.full, 1)
+                cm.barrier()
+                return dst
         # Pipeline over chunks of slots: the exchange of chunk c+1 (slab stream, NCCL) overlaps the operator on chunk c (full
         # context's stream), and the way back of chunk c overlaps the operator on chunk c+1.  Ordering is by events between the
         # two streams -- the host never blocks here; the slab-stream kernels that follow are ordered behind the last exchange.

@@ -130,3 +130,28 @@ def test_device_geometry_matches_host(pcb, oracle, d_flag):
         assert np.array_equal(ind_v, pcb.dielectric.compute_index(N, d_flag, "volume")), (d_flag, N)
         if N <= 24:
             assert np.array_equal(ind_e, oracle.diel_index(N, d_flag, "edge"))
+
+
+@pytest.mark.parametrize("typ", ["chiral", None])
+def test_five_sweep_plane_pass(pcb, oracle, typ):
+    """k_mid2 (2-D register tiles, five shared-memory sweeps; the default at N = 120) forced on at N = 24 = 8 x 3, where the
+    emulation can run it, against the oracle; the seven-sweep pass gives the same result to rounding."""
+    N, d_flag = 24, "fcc"
+    alpha = np.array([0.3 * np.pi, 2 * np.pi, 0.0])
+    ctx = pcb.get_context(N)
+    case = {"N": N, "d_flag": d_flag, "alpha": alpha, "type": typ, "eps_opt": 0, "m": 2, "seed": 9}
+    a, b, inv, shift, _ = oracle.assemble_symbols(N, d_flag, alpha)
+    diel = (lambda v: v) if typ is None else oracle.HANDLES[typ](N, d_flag)
+    Ao, Ho, Po = oracle.pc_mfd_handle(a, b, diel, inv, shift)
+    out = {}
+    try:
+        for five in (1, 0):
+            ctx.option("mid_five", five)
+            A, H, P, Diels, x = _setup(pcb, oracle, case)
+            out[five] = H(x)
+            assert relerr(out[five], Ho(x)) < TOL
+            assert relerr(A(x), Ao(x)) < TOL
+    finally:
+        ctx.option("mid_five", -1)
+    assert relerr(out[1], out[0]) < 1e-14
+    assert not np.array_equal(out[1], out[0])      # two different kernels did run
