@@ -310,7 +310,8 @@ def large_grid_leg(dist, pcb, n, nev, lattice="sc_curv", typ="chiral", check=Tru
            "solver_s": dist.max(float(info[1])) if lam is not None else None, "wall_s": wall,
            "ms_per_iteration": 1e3 * float(info[1]) / max(1, int(info[0])) if lam is not None else None,
            "H_apply_ms_per_block": ms_apply, "op_applies_per_sec": m / ms_apply * 1e3,
-           "H_apply_path": "peer memory (x passes over NVLink, pcb_apply_dist)" if comm.p2p else "NCCL slab exchange",
+           "H_apply_path": {0: "NCCL slab exchange both ways", 1: "peer memory: both x passes read / write the slabs of all ranks over NVLink (pcb_apply_dist)",
+                            2: "NCCL gather (pipelined) + scatter fused into the last FFT pass over peer memory (pcb_apply_dist)"}[comm.p2p_mode if comm.p2p else 0],
            "H_apply_ms_per_block_exchange_path": ms_apply_exch,
            "H_apply_nvlink_GBps_aggregate": 2 * m * col_bytes * (dist.world - 1) / dist.world / (ms_apply * 1e-3) / 1e9,
            "exchange_ms": ms_exch, "exchange_GBps_aggregate": moved / (ms_exch * 1e-3) / 1e9,
@@ -410,7 +411,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="pcb200", choices=["pcb200", "reference"])
-    ap.add_argument("--n", type=int, default=N_GRID)
+    ap.add_argument("--n", "--grid", dest="n", type=int, default=N_GRID, help="grid size N (use --grid under torchrun, whose parser trips over --n)")
     ap.add_argument("--cols", type=int, default=M_BLOCK, help="block width m (16 for 10 bands, 32 for 20 bands)")
     ap.add_argument("--kpoints", type=int, default=3, help="k-points per rank for the LOBPCG leg (0 = skip)")
     ap.add_argument("--e2e-steps", type=int, default=5)

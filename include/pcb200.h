@@ -166,7 +166,9 @@ int pcb_comm_destroy(pcb_ctx* ctx);
  *   pcb_comm_unshare closes the mappings
  *   pcb_comm_barrier stream-ordered barrier over the ranks (one-element ncclAllReduce on the context's stream)
  *   pcb_apply_dist   PCB_APPLY_A / PCB_APPLY_H on `ncols` columns owned by this rank: src[j*world+g] / dst[j*world+g] are column
- *                    j's input / output slab on rank g, zb[0..world] the slab boundaries, xcopy[j] / work[j] local full columns */
+ *                    j's input / output slab on rank g, zb[0..world] the slab boundaries, xcopy[j] / work[j] local full columns;
+ *                    src == NULL: xcopy[j] already holds the whole input column (gathered with pcb_slab_exchange) and only the
+ *                    scatter of the result is fused into the last pass */
 int pcb_comm_share(pcb_ctx* ctx, void* dptr, void** peers);
 int pcb_comm_unshare(pcb_ctx* ctx, void** peers);
 int pcb_comm_barrier(pcb_ctx* ctx);

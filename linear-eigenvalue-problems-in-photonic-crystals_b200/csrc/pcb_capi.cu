@@ -568,12 +568,14 @@ static int apply_structure(const pcb_op* o) {
 
 // A / H on kc columns (cols.in -> cols.out).  dist: the x passes read / write the slabs of all ranks through o->d.dist
 // (large-grid mode over peer memory); cols.in then holds the local X copies and cols.out local work columns.
-static int apply_AH(pcb_op* o, int mode, PcbCols& cols, int kc, int j0, bool dist) {
+// (dist bit 0: the input columns are distributed, bit 1: the output columns are.)
+static int apply_AH(pcb_op* o, int mode, PcbCols& cols, int kc, int j0, int dist) {
     pcb_ctx* c = o->ctx;
     const PcbOpLaunch* pl = c->plan;
-    const int first = dist ? PCB_PASS_XFWD_SYM_D : PCB_PASS_XFWD_SYM, first_t = dist ? PCB_PASS_XFWD_SYM_TD : PCB_PASS_XFWD_SYM_T;
-    const int last = (mode == PCB_APPLY_A) ? (dist ? PCB_PASS_XINV_A_D : PCB_PASS_XINV_A) : (dist ? PCB_PASS_XINV_H_D : PCB_PASS_XINV_H);
-    const int last_t = (mode == PCB_APPLY_A) ? (dist ? PCB_PASS_XINV_A_TD : PCB_PASS_XINV_A_T) : (dist ? PCB_PASS_XINV_H_TD : PCB_PASS_XINV_H_T);
+    const bool din = dist & 1, dout = dist & 2;
+    const int first = din ? PCB_PASS_XFWD_SYM_D : PCB_PASS_XFWD_SYM, first_t = din ? PCB_PASS_XFWD_SYM_TD : PCB_PASS_XFWD_SYM_T;
+    const int last = (mode == PCB_APPLY_A) ? (dout ? PCB_PASS_XINV_A_D : PCB_PASS_XINV_A) : (dout ? PCB_PASS_XINV_H_D : PCB_PASS_XINV_H);
+    const int last_t = (mode == PCB_APPLY_A) ? (dout ? PCB_PASS_XINV_A_TD : PCB_PASS_XINV_A_T) : (dout ? PCB_PASS_XINV_H_TD : PCB_PASS_XINV_H_T);
     const int st = apply_structure(o);
     if ((mode == PCB_APPLY_H && st != PCB_STRUCT_PLANE) || st == PCB_STRUCT_CROSS5 || dist)
         for (int j = 0; j < kc; ++j)
@@ -641,7 +643,7 @@ int pcb_apply(pcb_op* o, int mode, int ncols, const void* const* in, void* const
                 c->launches += 3;
                 break;
             case PCB_APPLY_A: case PCB_APPLY_H:
-                if (int rc = apply_AH(o, mode, cols, kc, j0, false)) return rc;
+                if (int rc = apply_AH(o, mode, cols, kc, j0, 0)) return rc;
                 break;
             case PCB_APPLY_P: {
                 PcbResidArgs a;
@@ -1144,7 +1146,7 @@ int pcb_comm_barrier(pcb_ctx* c) {
  * last FFT pass, which read and write peer memory over NVLink tile by tile.  Caller: order the ranks with pcb_comm_barrier. */
 int pcb_apply_dist(pcb_op* o, int mode, int ncols, const void* const* src, void* const* dst, const int* zb, int world,
                    void* const* xcopy, void* const* work) {
-    PCB_CHECK_ARG(o && src && dst && zb && xcopy && work && ncols > 0 && ncols <= PCB_MAXC_DIST && world >= 1 && world <= PCB_MAXW, "bad arguments");
+    PCB_CHECK_ARG(o && dst && zb && xcopy && work && ncols > 0 && ncols <= PCB_MAXC_DIST && world >= 1 && world <= PCB_MAXW, "bad arguments");
     PCB_CHECK_ARG(mode == PCB_APPLY_A || mode == PCB_APPLY_H, "mode must be PCB_APPLY_A or PCB_APPLY_H");
     pcb_ctx* c = o->ctx;
     PCB_CHECK_ARG(c->nloc == c->nn, "needs a full (non-slab) context");
@@ -1161,13 +1163,13 @@ int pcb_apply_dist(pcb_op* o, int mode, int ncols, const void* const* src, void*
     PcbCols cols;
     memset(&cols, 0, sizeof cols);
     for (int j = 0; j < ncols; ++j) {
-        for (int g = 0; g < world; ++g) { hd->src[j][g] = (const cplx*)src[j * world + g]; hd->dst[j][g] = (cplx*)dst[j * world + g]; }
+        for (int g = 0; g < world; ++g) { hd->src[j][g] = src ? (const cplx*)src[j * world + g] : nullptr; hd->dst[j][g] = (cplx*)dst[j * world + g]; }
         cols.in[j] = (const cplx*)xcopy[j];
         cols.out[j] = (cplx*)work[j];
     }
     PCB_CUDA_OK(cudaMemcpyAsync(c->ddist, hd, sizeof(PcbDist), cudaMemcpyHostToDevice, c->stream));
     o->d.dist = c->ddist;
-    const int rc = apply_AH(o, mode, cols, ncols, 0, true);
+    const int rc = apply_AH(o, mode, cols, ncols, 0, src ? 3 : 2);      // src == null: xcopy[] already holds the whole input columns
     o->d.dist = nullptr;
     return rc;
 }

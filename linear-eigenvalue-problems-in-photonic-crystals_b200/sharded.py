@@ -56,8 +56,14 @@ class SlabComm:
         # rank with CUDA IPC when they are created -- a collective step, reached by all ranks at the same point of the SPMD
         # solver -- so that the operator can read and write the slabs in place over NVLink (ShardedOperator.apply_into).
         self._shared = {}       # allocation base pointer -> (list of peer base pointers, allocation bytes)
-        self.p2p = (host_callbacks is None and L.backend() == "cuda-sm_100a" and self.world <= 8
-                    and os.environ.get("PCB200_LG_P2P", "1") != "0")
+        # PCB200_LG_P2P: 0 = NCCL exchange both ways; 1 = both x passes over peer memory; 2 = NCCL gather + peer-memory scatter fused
+        # into the last pass; unset = measured best: 1 on two GPUs (1.9 vs 3.9 ms per 16-column apply at N = 120), 2 on more
+        # (the forward x pass cannot keep enough loads in flight against the NVLink latency when 7/8 of its input is remote;
+        # stores are posted, so the last pass does not mind -- N = 256 on 8 GPUs: 21.2 ms both ways over peer memory, 15.5 ms
+        # with the pipelined exchange, see profiles/)
+        mode = os.environ.get("PCB200_LG_P2P")
+        self.p2p_mode = int(mode) if mode in ("0", "1", "2") else (1 if self.world <= 2 else 2)
+        self.p2p = (host_callbacks is None and L.backend() == "cuda-sm_100a" and self.world <= 8 and self.p2p_mode != 0)
         if self.p2p:
             self.slab._on_work_block = self.share_block
         self.rows_of = [3 * (self.zb[g + 1] - self.zb[g]) * self.N ** 2 for g in range(self.world)]
@@ -161,7 +167,36 @@ class ShardedOperator:
         owners = [j % cm.world for j in range(k)]
         kmax = (k + cm.world - 1) // cm.world                   # most columns any rank owns (slot = j // world)
         win, wout = cm.work_blocks(kmax)
-        if cm.p2p:
+        if cm.p2p and cm.p2p_mode == 2:
+            dp = cm.peer_pointers(dst)
+            if dp is not None:
+                # NCCL gather of the input slabs (pipelined over chunks of columns as below), the operator on whole columns, and
+                # the scatter of the result fused into the last FFT pass, which stores every row straight into the slab of the
+                # rank that owns its plane (posted writes over NVLink).  The gather orders the ranks before (every rank sends
+                # after its own earlier work), one stream-ordered barrier after.
+                nch = max(1, min(kmax, LG_CHUNKS, 8))
+                bounds = [(i * kmax) // nch for i in range(nch + 1)]
+                for ci in range(nch):
+                    js = [j for j in range(k) if bounds[ci] <= j // cm.world < bounds[ci + 1]]
+                    if not js:
+                        continue
+                    pin = [win.ptrs[j // cm.world] if owners[j] == cm.rank else 0 for j in js]
+                    cm.exchange(True, [owners[j] for j in js], src.cols(js), pin)
+                    cm.slab.record(ci)
+                    mine = [j for j in js if owners[j] == cm.rank]
+                    if mine:
+                        nm, w = len(mine), cm.world
+                        dsts = (C.c_void_p * (nm * w))(*[dp[j][g] for j in mine for g in range(w)])
+                        slots = [j // cm.world for j in mine]
+                        cm.full.wait_for(cm.slab, ci)
+                        L.check(L.lib().pcb_apply_dist(self.full.h, mode, nm, None, dsts, cm._zb_c, w,
+                                                       L.ptr_array([win.ptrs[sl] for sl in slots]),
+                                                       L.ptr_array([wout.ptrs[sl] for sl in slots])), "pcb_apply_dist")
+                cm.full.record(15)
+                cm.slab.wait_for(cm.full, 15)
+                cm.barrier()
+                return dst
+        if cm.p2p and cm.p2p_mode == 1:
             sp, dp = cm.peer_pointers(src), cm.peer_pointers(dst)
             if sp is not None and dp is not None:
                 # Peer-memory path: every rank applies the operator to its own columns, reading the input slabs of all ranks in
