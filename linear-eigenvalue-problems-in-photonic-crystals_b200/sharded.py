@@ -56,13 +56,14 @@ class SlabComm:
         # rank with CUDA IPC when they are created -- a collective step, reached by all ranks at the same point of the SPMD
         # solver -- so that the operator can read and write the slabs in place over NVLink (ShardedOperator.apply_into).
         self._shared = {}       # allocation base pointer -> (list of peer base pointers, allocation bytes)
-        # PCB200_LG_P2P: 0 = NCCL exchange both ways; 1 = both x passes over peer memory; 2 = NCCL gather + peer-memory scatter fused
-        # into the last pass; unset = measured best: 1 on two GPUs (1.9 vs 3.9 ms per 16-column apply at N = 120), 2 on more
-        # (the forward x pass cannot keep enough loads in flight against the NVLink latency when 7/8 of its input is remote;
-        # stores are posted, so the last pass does not mind -- N = 256 on 8 GPUs: 21.2 ms both ways over peer memory, 15.5 ms
-        # with the pipelined exchange, see profiles/)
+        # PCB200_LG_P2P: 0 = NCCL exchange both ways (pipelined over column chunks); 1 = both x passes of the operator read / write
+        # the slabs of all ranks over peer memory; 2 = NCCL gather + scatter fused into the last pass over peer memory.
+        # Unset = the measured best: 1 on two GPUs (N = 120, 16 columns: 1.94 ms per apply vs 2.82 (mode 2) and 3.86 (mode 0)),
+        # 0 on more (N = 256, 32 columns on 8 GPUs: 15.5 ms (mode 0) vs 21.2 (mode 1) and 20.0 (mode 2): with 7/8 of the data remote
+        # the x passes -- 16-byte accesses per thread, loads in flight for a fraction of a CTA's life -- reach 280-350 GB/s per GPU
+        # over NVLink where NCCL's copy kernels reach 534 GB/s per direction; profiles/README.md)
         mode = os.environ.get("PCB200_LG_P2P")
-        self.p2p_mode = int(mode) if mode in ("0", "1", "2") else (1 if self.world <= 2 else 2)
+        self.p2p_mode = int(mode) if mode in ("0", "1", "2") else (1 if self.world <= 2 else 0)
         self.p2p = (host_callbacks is None and L.backend() == "cuda-sm_100a" and self.world <= 8 and self.p2p_mode != 0)
         if self.p2p:
             self.slab._on_work_block = self.share_block
