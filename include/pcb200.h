@@ -136,6 +136,12 @@ int pcb_gram2_top(pcb_ctx* ctx, int n, int ntop, const void* const* s, const voi
  * E is (n_loc x m) row-major complex128 on the host.  Pn = [W_act P_act] E[m:], X <- X E[:m] + Pn (in place), P <- Pn. */
 int pcb_update(pcb_ctx* ctx, int m, int n_loc, void* const* s, void* const* hs, void* const* p_out, void* const* hp_out,
                const void* E);
+/* pcb_update and, fused into the same pass for m <= 16, the NEXT iteration's residual / norms / preconditioner (lobpcg.py:1248-1270
+ * followed by :394-397,442): with the new Ritz values `lambda` (m doubles, host), w_out_j = K_P^-1 (lambda_j x_j - hx_j) on the updated
+ * X, HX and norms2[j] = ||lambda_j x_j - hx_j||^2 (HOST).  The residual is formed from the update's accumulators, so X and HX are not
+ * re-read; wider blocks run pcb_update + pcb_residual back to back.  w_out may be the W columns that are inputs of the update. */
+int pcb_update_resid(pcb_op* op, int m, int nl, void* const* s, void* const* hs, void* const* p_out, void* const* hp_out, const void* E,
+                     const double* lambda, void* const* w_out, double* norms2);
 /* out[j] = a_j^H b_j (complex128 on the host) -- diag(x^H y) of numerical_experiments.py:105-111, environment.dots */
 int pcb_coldots(pcb_ctx* ctx, int ncols, const void* const* a, const void* const* b, void* out);
 /* y_j = alpha x_j + beta y_j */

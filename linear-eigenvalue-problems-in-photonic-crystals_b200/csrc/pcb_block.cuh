@@ -456,6 +456,143 @@ k_update(PcbColList Sin, PcbColList HSin, PcbColListW Xout, PcbColListW HXout, P
     }
 }
 
+// ---- subspace update FUSED with the next residual, its norms and the preconditioner ------------------------------------
+// (lobpcg.py:1248-1270 followed by :394-397 and :442 of the next iteration.)  After the Rayleigh-Ritz step the new Ritz values
+// are known, and the new X' = X E_x + P', HX' = HX E_x + HP' sit in the accumulator fragments of k_update -- (Re, Im) of one
+// element per lane -- so r = lambda X' - HX' and |r|^2 cost nothing to form there, instead of a separate pass that re-reads the
+// 2m columns X', HX' one launch later.  The preconditioner K_P^-1 couples the three components of a grid point, so this form
+// of the kernel takes its row tiles as 3 components x 16 cells (48 rows, 24 warps = 6 row tiles x 4 column tiles): the raw
+// residual of a tile goes through 12 KB of shared memory, 256 threads apply the 3x3 symbol inverse (one grid point and column
+// each) and store W.  m <= 16 (10-band runs); other widths keep pcb_update + pcb_residual.
+struct PcbUpdRes { cplx* w[16]; double lambda[16]; };
+
+__global__ void __launch_bounds__(768, 1)
+k_update_res(PcbOp op, PcbColList Sin, PcbColList HSin, PcbColListW Xout, PcbColListW HXout, PcbColListW Pout, PcbColListW HPout, PcbUpdRes rs,
+             const cplx* __restrict__ E, int m, int kx, int kp, int MPp, double* __restrict__ partial /* [gridDim.x][16] */) {
+    constexpr int TR = 48, TC = 16, LD = PcbUpd<48>::LD, RT = TR / 8, RS = 17;
+    PCB_DYN_SMEM(cplx, sm);
+    __shared__ double red[24][4];
+    const int nl = kx + kp;
+    const int LDE = 2 * MPp;
+    double* sEr = reinterpret_cast<double*>(sm);     // [2 nl][LDE] real-expanded E (see k_update)
+    cplx* sT = sm + (size_t)2 * nl * MPp;            // [2 stages][2: S, HS][nl][LD]
+    const size_t matElems = (size_t)nl * LD;
+    cplx* sR = sT + 4 * matElems;                    // [TR][RS] raw residual of the tile
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int warp = tid >> 5, lane = tid & 31, W = nthr >> 5;
+    const int g = lane >> 2, tig = lane & 3;
+    const int rt = warp % RT, jp = warp / RT;
+    const long long nloc = op.nloc;
+    const int N = op.N;
+    for (int i = tid; i < nl * MPp; i += nthr) {
+        const cplx e = E[i];
+        const int k = i / MPp, j = i % MPp;
+        sEr[(size_t)(2 * k) * LDE + 2 * j] = e.x;       sEr[(size_t)(2 * k) * LDE + 2 * j + 1] = e.y;
+        sEr[(size_t)(2 * k + 1) * LDE + 2 * j] = -e.y;  sEr[(size_t)(2 * k + 1) * LDE + 2 * j + 1] = e.x;
+    }
+    const long long ntiles = (nloc + TC - 1) / TC;
+    // row rr of tile t: component rr / 16, cell t*16 + rr % 16
+    auto load_tile = [&](long long t, int stage) {
+        cplx* d0 = sT + (size_t)(stage * 2) * matElems;
+        for (int c = warp; c < nl; c += W) {
+            const cplx* sp = c < PCB_MAXL ? Sin.p[c] : nullptr;
+            const cplx* hp = c < PCB_MAXL ? HSin.p[c] : nullptr;
+            PCB_UNROLL
+            for (int q = 0; q < 2; ++q) {
+                const int rr = lane + 32 * q;
+                if (rr >= TR) break;
+                const long long cell = t * TC + rr % TC;
+                const long long r = (long long)(rr / TC) * nloc + cell;
+                cplx* ds = d0 + (size_t)c * LD + rr;
+                cplx* dh = ds + matElems;
+                if (sp != nullptr && cell < nloc) { pcb_cp16(ds, sp + r); pcb_cp16(dh, hp + r); }
+                else { *ds = cmake(0.0, 0.0); *dh = cmake(0.0, 0.0); }
+            }
+        }
+        pcb_cp_commit();
+    };
+    long long t = blockIdx.x;
+    int stage = 0;
+    if (t < ntiles) load_tile(t, 0);
+    const double* bbase = sEr + (size_t)tig * LDE + 8 * jp + g;
+    const int jj = jp * 4 + tig;                     // this lane's output column
+    const double lam = jj < 16 ? rs.lambda[jj] : 0.0;
+    double nrm = 0.0;
+    for (; t < ntiles; t += gridDim.x) {
+        const long long tn = t + gridDim.x;
+        if (tn < ntiles) { load_tile(tn, stage ^ 1); pcb_cp_wait<1>(); } else { pcb_cp_wait<0>(); }
+        __syncthreads();
+        const double* s0 = reinterpret_cast<const double*>(sT + (size_t)(stage * 2) * matElems);
+        const double* h0 = reinterpret_cast<const double*>(sT + (size_t)(stage * 2 + 1) * matElems);
+        double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+        const int rr = rt * 8 + g;
+        const long long cell = t * TC + rr % TC;
+        const long long r = (long long)(rr / TC) * nloc + cell;
+        const bool live = cell < nloc && jj < m;
+        const int aoff = (tig >> 1) * (2 * LD) + rr * 2 + (tig & 1);
+        PCB_UNROLL
+        for (int part = 0; part < 2; ++part) {
+            const int k0 = part == 0 ? kx : 0, k1 = part == 0 ? nl : kx;
+#ifndef PCB_EMU
+#pragma unroll 4
+#endif
+            for (int k = k0; k < k1; k += 2) {
+                const double as = s0[(size_t)k * (2 * LD) + aoff];
+                const double ah = h0[(size_t)k * (2 * LD) + aoff];
+                const double bj = bbase[(size_t)(2 * k) * LDE];
+                pcb_dmma(acc[0][0], acc[0][1], as, bj);
+                pcb_dmma(acc[1][0], acc[1][1], ah, bj);
+            }
+            if (part == 0) {
+                if (live) {
+                    Pout.p[jj][r] = cmake(acc[0][0], acc[0][1]);
+                    HPout.p[jj][r] = cmake(acc[1][0], acc[1][1]);
+                }
+            } else {
+                cplx res = cmake(0.0, 0.0);
+                if (live) {
+                    Xout.p[jj][r] = cmake(acc[0][0], acc[0][1]);
+                    HXout.p[jj][r] = cmake(acc[1][0], acc[1][1]);
+                    res = cmake(fma(acc[0][0], lam, -acc[1][0]), fma(acc[0][1], lam, -acc[1][1]));      // lambda x' - hx'
+                    nrm += cabs2(res);
+                }
+                if (jj < 16) sR[rr * RS + jj] = res;
+            }
+        }
+        __syncthreads();
+        stage ^= 1;
+        // preconditioner on the tile: one grid point and column per thread (256 of the 768 threads)
+        if (tid < TC * 16) {
+            const int cl = tid % TC, col = tid / TC;
+            const long long p = t * TC + cl;
+            if (p < nloc && col < m) {
+                const int i0 = (int)(p % N), i1 = (int)((p / N) % N), i2 = op.z0 + (int)(p / ((long long)N * N));
+                const Sym3 sy = pcb_symbol(op.T, N, i0, i1, i2);
+                const PcbPinv f = pcb_pinv(sy.k, op.gamma, op.pshift);
+                const cplx rv[3] = {sR[cl * RS + col], sR[(TC + cl) * RS + col], sR[(2 * TC + cl) * RS + col]};
+                cplx wv[3];
+                pcb_pinv_apply(f, rv, wv);
+                cplx* __restrict__ wp = rs.w[col];
+                PCB_UNROLL
+                for (int c = 0; c < 3; ++c) wp[c * nloc + p] = wv[c];
+            }
+        }
+        // (the next tile's sR writes come after its own top-of-loop barrier: no further barrier needed here)
+    }
+    // column norms: lanes with the same tig hold the same column
+    nrm += __shfl_xor_sync(0xffffffffu, nrm, 4);
+    nrm += __shfl_xor_sync(0xffffffffu, nrm, 8);
+    nrm += __shfl_xor_sync(0xffffffffu, nrm, 16);
+    if (g == 0) red[warp][tig] = nrm;
+    __syncthreads();
+    if (tid < 16) {
+        const int jq = tid / 4, tq = tid % 4;
+        double v = 0.0;
+        for (int q = 0; q < RT; ++q) v += red[jq * RT + q][tq];
+        partial[(long long)blockIdx.x * 16 + tid] = v;
+    }
+}
+
 // ---- diag(A^H B) for column pairs -------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_coldots(PcbColList A, PcbColList B, int ncols, long long R, cplx* __restrict__ partial) {
     __shared__ double red[8][2];

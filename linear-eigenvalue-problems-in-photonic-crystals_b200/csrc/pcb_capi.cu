@@ -911,7 +911,21 @@ int pcb_gram2_top(pcb_ctx* c, int n, int ntop, const void* const* s, const void*
     return 0;
 }
 
+static int update_impl(pcb_ctx* c, pcb_op* o, int m, int nl, void* const* s, void* const* hs, void* const* p_out, void* const* hp_out, const void* E,
+                       const double* lambda, void* const* w_out, double* norms2);
 int pcb_update(pcb_ctx* c, int m, int nl, void* const* s, void* const* hs, void* const* p_out, void* const* hp_out, const void* E) {
+    return update_impl(c, nullptr, m, nl, s, hs, p_out, hp_out, E, nullptr, nullptr, nullptr);
+}
+/* pcb_update followed by pcb_residual(precond = 1) on the new X, HX with the new Ritz values `lambda`: w_out_j = K_P^-1 (lambda_j x_j - hx_j),
+ * norms2[j] = ||lambda_j x_j - hx_j||^2 (HOST).  For m <= 16 one kernel does both (k_update_res: the residual is formed from the
+ * accumulator fragments, X and HX are not re-read); wider blocks run the two kernels back to back. */
+int pcb_update_resid(pcb_op* o, int m, int nl, void* const* s, void* const* hs, void* const* p_out, void* const* hp_out, const void* E,
+                     const double* lambda, void* const* w_out, double* norms2) {
+    PCB_CHECK_ARG(o && lambda && w_out && norms2, "bad arguments");
+    return update_impl(o->ctx, o, m, nl, s, hs, p_out, hp_out, E, lambda, w_out, norms2);
+}
+static int update_impl(pcb_ctx* c, pcb_op* o, int m, int nl, void* const* s, void* const* hs, void* const* p_out, void* const* hp_out, const void* E,
+                       const double* lambda, void* const* w_out, double* norms2) {
     PCB_CHECK_ARG(c && s && hs && p_out && hp_out && E && m > 0 && nl >= m && nl <= PCB_MAXL && m <= 32, "bad arguments");
     PCB_CUDA_OK(cudaSetDevice(c->device));
     const int MP = 8 * ((m + 7) / 8), MPp = MP + 2, JT = MP / 4;       // output columns padded to 8; E' row stride (conflict-free)
@@ -954,6 +968,32 @@ int pcb_update(pcb_ctx* c, int m, int nl, void* const* s, void* const* hs, void*
     const int JW = (deep || wide || (TR / 8) * JT <= 16) ? 1 : 2;  // one column tile per warp while that keeps <= 16 warps per CTA
     const int warps = (TR / 8) * (JT / JW);
     const long long ntiles = (c->R + TR - 1) / TR;
+    if (o) {
+        // fused form: 3 components x 16 cells per tile, 24 warps, two stages + 12 KB for the raw residual of the tile
+        const size_t smem_f = smem48 + sizeof(cplx) * 48 * 17;
+        static const char* ev_f = getenv("PCB200_FUSED_RESID");
+        if (JT == 4 && m <= 16 && smem_f <= (size_t)226 * 1024 && !(ev_f && ev_f[0] == '0')) {
+            PcbUpdRes rs;
+            for (int j = 0; j < 16; ++j) { rs.w[j] = j < m ? (cplx*)w_out[j] : nullptr; rs.lambda[j] = j < m ? lambda[j] : 0.0; }
+            const long long nt = (c->nloc + 15) / 16;
+            long long gxf = c->sms; if (gxf > nt) gxf = nt;
+            if (ensure_partial(c, sizeof(double) * ((size_t)gxf * 16 + 16))) return -1;
+#ifndef PCB_EMU
+            if (smem_f > 48 * 1024) PCB_CUDA_OK(cudaFuncSetAttribute(k_update_res, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
+#endif
+            PCB_LAUNCH(k_update_res, dim3((unsigned)gxf, 1, 1), dim3(768, 1, 1), smem_f, c->stream, o->d, Sin, HSin, X, HX, P, HP, rs, dE, m, kx, kp, MPp, c->partial);
+            PCB_CUDA_OK(cudaGetLastError());
+            double* dout = c->partial + (size_t)gxf * 16;
+            PCB_LAUNCH(k_sum_partials, dim3(1, 1, 1), dim3(64, 1, 1), 0, c->stream, (const double*)c->partial, (int)gxf, 16, dout);
+            PCB_CUDA_OK(cudaGetLastError());
+            c->launches += 2;
+            if (comm_allreduce(c, dout, m)) return -1;
+            PCB_CUDA_OK(cudaMemcpyAsync(c->hstage, dout, sizeof(double) * m, cudaMemcpyDeviceToHost, c->stream));
+            PCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+            memcpy(norms2, c->hstage, sizeof(double) * m);
+            return 0;
+        }
+    }
     int per_sm = (int)((size_t)224 * 1024 / (smem + 1024)); if (per_sm < 1) per_sm = 1; if (per_sm > 4) per_sm = 4;
     long long gx = (long long)c->sms * per_sm; if (gx > ntiles) gx = ntiles;
     dim3 grid((unsigned)gx, 1, 1), block((unsigned)(32 * warps), 1, 1);
@@ -974,6 +1014,7 @@ int pcb_update(pcb_ctx* c, int m, int nl, void* const* s, void* const* hs, void*
     else PCB_UPD_GO((k_update<16, 2>));
     PCB_CUDA_OK(cudaGetLastError());
     c->launches++;
+    if (o) return pcb_residual(o, 1, m, (const void* const*)s, (const void* const*)hs, w_out, lambda, norms2);      // wide blocks: two kernels
     return 0;
 }
 

@@ -5,7 +5,8 @@
 (:379-381), the iteration-0 search space without P, the absolute residual test and the ascending
 soft-lock order -- but every O(R) step is one fused kernel of libpcb200.so:
 
-    residual + column norms + preconditioner      pcb_residual   (lobpcg.py:394-397,442)
+    residual + column norms + preconditioner      pcb_residual   (lobpcg.py:394-397,442; first iteration only -- afterwards
+                                                   fused into the update of the previous iteration, pcb_update_resid)
     soft-lock "compaction"                         pointer lists  (lobpcg.py:431-436: no data moves)
     H on the active block                          pcb_apply      (lobpcg.py:443)
     Gram pair S^H S, S^H HS                        pcb_gram2      (orthogonalization.py:143-144)
@@ -136,12 +137,19 @@ def _lobpcg_sep_softlock(h_func_in, p_func, x0, nev, shift=0.0, tol=TOL, maxiter
     if incremental_gram is None:
         incremental_gram = os.environ.get("PCB200_FULL_GRAM", "0") != "1"
     g_xp = t_xp = None        # Gram pair of [X | P] (2m x 2m) implied by the last Rayleigh-Ritz rotation
+    # The residual of iteration i+1 only needs the Ritz values and the X, HX that the update of iteration i produces, so that
+    # update also forms it (from its accumulators: X and HX are not read again), applies K_P^-1 and returns the norms.
+    fuse_resid = op is not None and not _mixed and os.environ.get("PCB200_FUSED_RESID", "1") != "0"
+    next_nrms = None
     t_tot_h = time.time()
     iter_ = 0
     for iter_ in range(maxiter):
         t_iter_h = time.time()
         # residual (+ preconditioner on the fused path), norms, active set
-        res_nrms = res_op.residual(X, HX, W, lambdas[:m], precond=op is not None, single=_mixed)
+        if next_nrms is not None:
+            res_nrms, next_nrms = next_nrms, None
+        else:
+            res_nrms = res_op.residual(X, HX, W, lambdas[:m], precond=op is not None, single=_mixed)
         res_his[iter_] = np.linalg.norm(res_nrms[:nev])
         ind_act = np.where(res_nrms > tol)[0] if _lock else np.arange(m)
         n_act = len(ind_act)
@@ -219,9 +227,12 @@ def _lobpcg_sep_softlock(h_func_in, p_func, x0, nev, shift=0.0, tol=TOL, maxiter
             g_xp = hermitize(ee.conj().T @ ss @ ee)
             t_xp = hermitize(ee.conj().T @ shs @ ee)
 
-        # _sep_update_after_rr (lobpcg.py:1248-1270) in one pass
-        L.check(L.lib().pcb_update(ctx.h, m, n_loc, L.ptr_array(s_loc.ptrs), L.ptr_array(hs_loc.ptrs),
-                                   L.ptr_array(P.ptrs), L.ptr_array(HP.ptrs), eigvec.ctypes.data), "pcb_update")
+        # _sep_update_after_rr (lobpcg.py:1248-1270) in one pass (+ the next residual, norms and K_P^-1 on the fused path)
+        if fuse_resid:
+            next_nrms = op.update_resid(m, n_loc, s_loc, hs_loc, P, HP, eigvec, lambdas, W)
+        else:
+            L.check(L.lib().pcb_update(ctx.h, m, n_loc, L.ptr_array(s_loc.ptrs), L.ptr_array(hs_loc.ptrs),
+                                       L.ptr_array(P.ptrs), L.ptr_array(HP.ptrs), eigvec.ctypes.data), "pcb_update")
         say(f"Runtime = {time.time() - t_iter_h:<6.4f}s.")
 
     ctx.sync()

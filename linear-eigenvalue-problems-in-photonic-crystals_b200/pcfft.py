@@ -100,6 +100,17 @@ class Operator:
         return np.sqrt(out)
 
 
+    def update_resid(self, m, n_loc, s_loc, hs_loc, P, HP, E, lambdas, W):
+        """_sep_update_after_rr (lobpcg.py:1248-1270) fused with the next iteration's residual, norms and preconditioner
+        (:394-397,442): returns ||lambda_j x_j - hx_j||_2 of the UPDATED X, HX; W receives K_P^-1 of those residuals."""
+        lam = np.ascontiguousarray(lambdas, dtype=np.float64)
+        out = np.empty(m, dtype=np.float64)
+        L.check(self._lib.pcb_update_resid(self.h, m, n_loc, L.ptr_array(s_loc.ptrs), L.ptr_array(hs_loc.ptrs), L.ptr_array(P.ptrs),
+                                           L.ptr_array(HP.ptrs), E.ctypes.data, lam.ctypes.data_as(L.c_double_p), L.ptr_array(W.ptrs),
+                                           out.ctypes.data_as(L.c_double_p)), "pcb_update_resid")
+        return np.sqrt(out)
+
+
 class OperatorCallable:
     """What pc_mfd_handle returns instead of a lambda: callable like the reference's closures, and
     recognisable by the solver so that it can run the fused device path."""

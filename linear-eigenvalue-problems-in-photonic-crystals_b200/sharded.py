@@ -158,6 +158,9 @@ class ShardedOperator:
     def residual(self, x, hx, w, lambdas, precond=True, single=False):
         return self.local.residual(x, hx, w, lambdas, precond=precond, single=single)
 
+    def update_resid(self, *args):
+        return self.local.update_resid(*args)       # row-local on the slabs; the norms are all-reduced inside the C ABI
+
     def apply_into(self, mode, src, dst):
         if src.k == 0:
             return dst

@@ -197,3 +197,41 @@ def test_gram_top_with_the_real_operator(pcb, oracle):
     assert relerr(T[:ntop, :], t[:ntop, :]) < 1e-12
     Gf, Tf = pcb.orthogonalization.gram_pair(S, HS)
     assert relerr(Tf, (t + t.conj().T) / 2) < 1e-12
+
+
+@pytest.mark.parametrize("N,m,n_act,first", [(6, 16, 16, False), (8, 16, 5, False), (6, 10, 7, True), (8, 8, 3, False), (6, 32, 9, False)])
+def test_update_fused_with_residual(pcb, oracle, N, m, n_act, first):
+    """pcb_update_resid: the update (lobpcg.py:1248-1270) plus the NEXT residual / norms / K_P^-1 (:394-397,442) in one pass
+    (k_update_res for m <= 16; two kernels for wider blocks) against NumPy + the oracle's preconditioner."""
+    alpha = np.array([0.3, 0.0, 0.1])
+    ne, mfd = pcb.numerical_experiments, pcb.discretization
+    relax, pnt = mfd.set_relaxation(alpha)
+    a_fft, b_fft = mfd.fft_blocks(N, 1, pcb.dielectric.diel_info("fcc", option="ct"), alpha=alpha)
+    inv_fft = mfd.inverse_3_times_3_B(b_fft, pnt, relax[0])
+    A, H, P = ne.pc_mfd_handle(a_fft, (pnt * b_fft[0], pnt * b_fft[1]), None, inv_fft, relax[0])
+    ctx, s, S = _blocks(pcb, N, 3 * m, 3)
+    _, hs, HS = _blocks(pcb, N, 3 * m, 4)
+    rng = np.random.default_rng(5)
+    act = np.sort(rng.choice(m, n_act, replace=False))
+    n_loc = m + (1 if first else 2) * n_act
+    E = np.ascontiguousarray(rng.standard_normal((n_loc, m)) + 1j * rng.standard_normal((n_loc, m))) / np.sqrt(n_loc)
+    lam = np.linspace(0.5, 3.0, m)
+    X, W, Pb = S[:, :m], S[:, m:2 * m], S[:, 2 * m:]
+    HX, HW, HP = HS[:, :m], HS[:, m:2 * m], HS[:, 2 * m:]
+    DB = pcb.devarray.DeviceBlock
+    s_loc = DB(ctx, _owners=S._owners, _ptrs=X.ptrs + W.cols(act).ptrs + ([] if first else Pb.cols(act).ptrs))
+    hs_loc = DB(ctx, _owners=HS._owners, _ptrs=HX.ptrs + HW.cols(act).ptrs + ([] if first else HP.cols(act).ptrs))
+    nr = H.op.update_resid(m, n_loc, s_loc, hs_loc, Pb, HP, E, lam, W)
+    new = {}
+    for key, a in (("s", s), ("hs", hs)):
+        cols = [a[:, m + act]] + ([] if first else [a[:, 2 * m + act]])
+        pn = np.concatenate(cols, axis=1) @ E[m:]
+        new[key] = (a[:, :m] @ E[:m] + pn, pn)
+    got_s, got_hs = S.get(), HS.get()
+    assert relerr(got_s[:, :m], new["s"][0]) < 1e-13 and relerr(got_s[:, 2 * m:], new["s"][1]) < 1e-13
+    assert relerr(got_hs[:, :m], new["hs"][0]) < 1e-13 and relerr(got_hs[:, 2 * m:], new["hs"][1]) < 1e-13
+    assert np.array_equal(got_hs[:, m:2 * m], hs[:, m:2 * m])          # HW untouched
+    r = new["s"][0] * lam - new["hs"][0]
+    assert np.allclose(nr, np.linalg.norm(r, axis=0), rtol=1e-12)
+    ao, bo, io, sh, _ = oracle.assemble_symbols(N, "fcc", alpha)
+    assert relerr(got_s[:, m:2 * m], oracle.h_block(r, io)) < 1e-11      # W = K_P^-1 r

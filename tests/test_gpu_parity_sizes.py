@@ -213,3 +213,11 @@ def test_device_geometry_n120(gpu, d_flag):
     assert gpu.dielectric.geometry_stats["seconds"] < 0.5
     assert np.array_equal(ind_e, gpu.dielectric.compute_index(N, d_flag, "edge"))
     assert np.array_equal(ind_v, gpu.dielectric.compute_index(N, d_flag, "volume"))
+
+
+@pytest.mark.parametrize("m,n_act", [(16, 16), (16, 6)])
+def test_fused_update_residual_n48(gpu, oracle, m, n_act):
+    """k_update_res at R = 331 776 rows (thousands of 3 x 16-cell tiles per CTA: the double-buffered steady state)."""
+    import test_block_kernels as tb
+    gpu.backend_name = "cuda"
+    tb.test_update_fused_with_residual(gpu, oracle, 48, m, n_act, False)
