@@ -478,7 +478,7 @@ def main():
     col_bytes = 48.0 * n ** 3            # one column, one direction
     if npass.value == 3:                  # plane mode: x forward (transposed store), fused y/z/M/z/y plane pass, x inverse
         pass_cols, names = [2, 2, 3], ["x_fwd+KAh -> W'", "y,z fwd + M + z,y inv on (i1,i2) planes", "x_inv+KA+gKB+shift"]
-        kernel_desc = "op-apply = 3 passes (k_xfwd<T>, k_mid, k_xinv<T>)"
+        kernel_desc = "op-apply = 3 passes (k_xfwd<T>, k_mid2 [five-sweep plane pass; k_mid where N != 8 x odd], k_xinv<T>)"
     else:
         pass_cols, names = [2, 2, 2, 2, 3], ["x_fwd+KAh", "y_fwd", "z_fwd+M+z_inv", "y_inv", "x_inv+KA+gKB+shift"]
         kernel_desc = "op-apply = 5 passes (k_xfwd, k_line, k_zmid, k_line, k_xinv)"
@@ -526,6 +526,9 @@ def main():
                                                      L.ptr_array(HS[:, 2 * m:].ptrs), E.ctypes.data), "update"))
         blocks.append({"name": f"fused update (m={m}, n_loc={3 * m})", "ms": t, "GBps": (2 * nl + 4 * m) * Rb / t / 1e6,
                        "GFLOPs": 16.0 * ctx.R * m * nl / t / 1e6})
+        t = timed(lambda: op.update_resid(m, nl, S, HS, S[:, 2 * m:], HS[:, 2 * m:], E, lam, S[:, m:2 * m]))
+        blocks.append({"name": f"fused update + next residual/norms/precond (m={m}, n_loc={3 * m}; replaces the two kernels above it and the residual)",
+                       "ms": t, "GBps": (2 * nl + 5 * m) * Rb / t / 1e6, "GFLOPs": 16.0 * ctx.R * m * nl / t / 1e6})
         t = timed(lambda: op.apply_into(L.APPLY_H, S[:, :m], HS[:, :m]))
         blocks.append({"name": f"H apply ({m} columns)", "ms": t, "GBps": B_OP_PER_N3 * n ** 3 * m / t / 1e6})
         del S, HS

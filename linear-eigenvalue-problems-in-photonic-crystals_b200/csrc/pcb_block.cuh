@@ -465,11 +465,43 @@ k_update(PcbColList Sin, PcbColList HSin, PcbColListW Xout, PcbColListW HXout, P
 // residual of a tile goes through 12 KB of shared memory, 256 threads apply the 3x3 symbol inverse (one grid point and column
 // each) and store W.  m <= 16 (10-band runs); other widths keep pcb_update + pcb_residual.
 struct PcbUpdRes { cplx* w[16]; double lambda[16]; };
+// On the device the 256 preconditioner threads are EIGHT EXTRA WARPS (warps 24-31 of a 1024-thread CTA) that trail the 24 DMMA
+// warps by one tile: the raw residual is double-buffered in shared memory and handed over with named barriers (bar.arrive /
+// bar.sync), so the ~1000-cycle dependency chain of the symbol inverse overlaps the next tile's products instead of holding
+// all 24 warps at a CTA barrier (measured with that barrier: 7.65 ms per LOBPCG iteration, i.e. no gain over the separate
+// residual pass at 7.57 ms).  The host-emulation build runs the same phases back to back with 768 threads.
+#ifndef PCB_EMU
+PCB_D void pcb_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(n) : "memory"); }
+PCB_D void pcb_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;\n" ::"r"(id), "r"(n) : "memory"); }
+#define PCB_UPDRES_THREADS 1024
+#else
+#define PCB_UPDRES_THREADS 768
+#endif
 
-__global__ void __launch_bounds__(768, 1)
+// K_P^-1 on the raw residual of one tile (sR: [48][17]): grid point `cl` of the tile and column `col` per thread
+PCB_D void pcb_updres_precond(const PcbOp& op, const PcbUpdRes& rs, const cplx* __restrict__ sR, long long t, int idx, int m) {
+    constexpr int TC = 16, RS = 17;
+    const int cl = idx % TC, col = idx / TC;
+    const long long nloc = op.nloc;
+    const long long p = t * TC + cl;
+    if (p < nloc && col < m) {
+        const int N = op.N;
+        const int i0 = (int)(p % N), i1 = (int)((p / N) % N), i2 = op.z0 + (int)(p / ((long long)N * N));
+        const Sym3 sy = pcb_symbol(op.T, N, i0, i1, i2);
+        const PcbPinv f = pcb_pinv(sy.k, op.gamma, op.pshift);
+        const cplx rv[3] = {sR[cl * RS + col], sR[(TC + cl) * RS + col], sR[(2 * TC + cl) * RS + col]};
+        cplx wv[3];
+        pcb_pinv_apply(f, rv, wv);
+        cplx* __restrict__ wp = rs.w[col];
+        PCB_UNROLL
+        for (int c = 0; c < 3; ++c) wp[c * nloc + p] = wv[c];
+    }
+}
+
+__global__ void __launch_bounds__(PCB_UPDRES_THREADS, 1)
 k_update_res(PcbOp op, PcbColList Sin, PcbColList HSin, PcbColListW Xout, PcbColListW HXout, PcbColListW Pout, PcbColListW HPout, PcbUpdRes rs,
              const cplx* __restrict__ E, int m, int kx, int kp, int MPp, double* __restrict__ partial /* [gridDim.x][16] */) {
-    constexpr int TR = 48, TC = 16, LD = PcbUpd<48>::LD, RT = TR / 8, RS = 17;
+    constexpr int TR = 48, TC = 16, LD = PcbUpd<48>::LD, RT = TR / 8, RS = 17, NC = 768;     // NC = threads of the 24 product warps
     PCB_DYN_SMEM(cplx, sm);
     __shared__ double red[24][4];
     const int nl = kx + kp;
@@ -477,20 +509,34 @@ k_update_res(PcbOp op, PcbColList Sin, PcbColList HSin, PcbColListW Xout, PcbCol
     double* sEr = reinterpret_cast<double*>(sm);     // [2 nl][LDE] real-expanded E (see k_update)
     cplx* sT = sm + (size_t)2 * nl * MPp;            // [2 stages][2: S, HS][nl][LD]
     const size_t matElems = (size_t)nl * LD;
-    cplx* sR = sT + 4 * matElems;                    // [TR][RS] raw residual of the tile
-    const int tid = threadIdx.x, nthr = blockDim.x;
-    const int warp = tid >> 5, lane = tid & 31, W = nthr >> 5;
+    cplx* sR = sT + 4 * matElems;                    // [2][TR][RS] raw residual of the tile (double-buffered on the device)
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, tig = lane & 3;
-    const int rt = warp % RT, jp = warp / RT;
     const long long nloc = op.nloc;
-    const int N = op.N;
-    for (int i = tid; i < nl * MPp; i += nthr) {
+    const long long ntiles = (nloc + TC - 1) / TC;
+#ifndef PCB_EMU
+    enum { BAR_PROD = 1, BAR_FULL = 2, BAR_EMPTY = 4 };      // named barriers: product warps; sR[b] written (+b); sR[b] consumed (+b)
+    if (warp >= 24) {      // ---- preconditioner warps ----
+        int it = 0;
+        for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+            const int b = it & 1;
+            pcb_bar_sync(BAR_FULL + b, PCB_UPDRES_THREADS);
+            pcb_updres_precond(op, rs, sR + b * TR * RS, t, tid - NC, m);
+            if (t + 2 * (long long)gridDim.x < ntiles) pcb_bar_arrive(BAR_EMPTY + b, PCB_UPDRES_THREADS);
+        }
+        __syncthreads();      // the final reduction's barrier
+        return;
+    }
+#endif
+    const int W = NC >> 5;
+    const int rt = warp % RT, jp = warp / RT;
+    for (int i = tid; i < nl * MPp; i += NC) {
         const cplx e = E[i];
         const int k = i / MPp, j = i % MPp;
         sEr[(size_t)(2 * k) * LDE + 2 * j] = e.x;       sEr[(size_t)(2 * k) * LDE + 2 * j + 1] = e.y;
         sEr[(size_t)(2 * k + 1) * LDE + 2 * j] = -e.y;  sEr[(size_t)(2 * k + 1) * LDE + 2 * j + 1] = e.x;
     }
-    const long long ntiles = (nloc + TC - 1) / TC;
     // row rr of tile t: component rr / 16, cell t*16 + rr % 16
     auto load_tile = [&](long long t, int stage) {
         cplx* d0 = sT + (size_t)(stage * 2) * matElems;
@@ -511,17 +557,22 @@ k_update_res(PcbOp op, PcbColList Sin, PcbColList HSin, PcbColListW Xout, PcbCol
         }
         pcb_cp_commit();
     };
+#ifndef PCB_EMU
+#define PCB_PROD_SYNC() pcb_bar_sync(BAR_PROD, NC)
+#else
+#define PCB_PROD_SYNC() __syncthreads()
+#endif
     long long t = blockIdx.x;
-    int stage = 0;
+    int stage = 0, it = 0;
     if (t < ntiles) load_tile(t, 0);
     const double* bbase = sEr + (size_t)tig * LDE + 8 * jp + g;
     const int jj = jp * 4 + tig;                     // this lane's output column
     const double lam = jj < 16 ? rs.lambda[jj] : 0.0;
     double nrm = 0.0;
-    for (; t < ntiles; t += gridDim.x) {
+    for (; t < ntiles; t += gridDim.x, ++it) {
         const long long tn = t + gridDim.x;
         if (tn < ntiles) { load_tile(tn, stage ^ 1); pcb_cp_wait<1>(); } else { pcb_cp_wait<0>(); }
-        __syncthreads();
+        PCB_PROD_SYNC();
         const double* s0 = reinterpret_cast<const double*>(sT + (size_t)(stage * 2) * matElems);
         const double* h0 = reinterpret_cast<const double*>(sT + (size_t)(stage * 2 + 1) * matElems);
         double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
@@ -530,6 +581,12 @@ k_update_res(PcbOp op, PcbColList Sin, PcbColList HSin, PcbColListW Xout, PcbCol
         const long long r = (long long)(rr / TC) * nloc + cell;
         const bool live = cell < nloc && jj < m;
         const int aoff = (tig >> 1) * (2 * LD) + rr * 2 + (tig & 1);
+#ifndef PCB_EMU
+        const int b = it & 1;
+#else
+        const int b = 0;
+#endif
+        cplx* __restrict__ sRb = sR + b * TR * RS;
         PCB_UNROLL
         for (int part = 0; part < 2; ++part) {
             const int k0 = part == 0 ? kx : 0, k1 = part == 0 ? nl : kx;
@@ -556,29 +613,22 @@ k_update_res(PcbOp op, PcbColList Sin, PcbColList HSin, PcbColListW Xout, PcbCol
                     res = cmake(fma(acc[0][0], lam, -acc[1][0]), fma(acc[0][1], lam, -acc[1][1]));      // lambda x' - hx'
                     nrm += cabs2(res);
                 }
-                if (jj < 16) sR[rr * RS + jj] = res;
+#ifndef PCB_EMU
+                if (it >= 2) pcb_bar_sync(BAR_EMPTY + b, PCB_UPDRES_THREADS);      // the preconditioner warps are done with this buffer
+#endif
+                if (jj < 16) sRb[rr * RS + jj] = res;
+#ifndef PCB_EMU
+                pcb_bar_arrive(BAR_FULL + b, PCB_UPDRES_THREADS);
+#endif
             }
         }
-        __syncthreads();
+        PCB_PROD_SYNC();
         stage ^= 1;
-        // preconditioner on the tile: one grid point and column per thread (256 of the 768 threads)
-        if (tid < TC * 16) {
-            const int cl = tid % TC, col = tid / TC;
-            const long long p = t * TC + cl;
-            if (p < nloc && col < m) {
-                const int i0 = (int)(p % N), i1 = (int)((p / N) % N), i2 = op.z0 + (int)(p / ((long long)N * N));
-                const Sym3 sy = pcb_symbol(op.T, N, i0, i1, i2);
-                const PcbPinv f = pcb_pinv(sy.k, op.gamma, op.pshift);
-                const cplx rv[3] = {sR[cl * RS + col], sR[(TC + cl) * RS + col], sR[(2 * TC + cl) * RS + col]};
-                cplx wv[3];
-                pcb_pinv_apply(f, rv, wv);
-                cplx* __restrict__ wp = rs.w[col];
-                PCB_UNROLL
-                for (int c = 0; c < 3; ++c) wp[c * nloc + p] = wv[c];
-            }
-        }
-        // (the next tile's sR writes come after its own top-of-loop barrier: no further barrier needed here)
+#ifdef PCB_EMU
+        if (tid < TC * 16) pcb_updres_precond(op, rs, sRb, t, tid, m);      // (the next tile's sR writes follow its top-of-loop barrier)
+#endif
     }
+#undef PCB_PROD_SYNC
     // column norms: lanes with the same tig hold the same column
     nrm += __shfl_xor_sync(0xffffffffu, nrm, 4);
     nrm += __shfl_xor_sync(0xffffffffu, nrm, 8);

@@ -970,7 +970,7 @@ static int update_impl(pcb_ctx* c, pcb_op* o, int m, int nl, void* const* s, voi
     const long long ntiles = (c->R + TR - 1) / TR;
     if (o) {
         // fused form: 3 components x 16 cells per tile, 24 warps, two stages + 12 KB for the raw residual of the tile
-        const size_t smem_f = smem48 + sizeof(cplx) * 48 * 17;
+        const size_t smem_f = smem48 + sizeof(cplx) * 2 * 48 * 17;
         static const char* ev_f = getenv("PCB200_FUSED_RESID");
         if (JT == 4 && m <= 16 && smem_f <= (size_t)226 * 1024 && !(ev_f && ev_f[0] == '0')) {
             PcbUpdRes rs;
@@ -981,7 +981,7 @@ static int update_impl(pcb_ctx* c, pcb_op* o, int m, int nl, void* const* s, voi
 #ifndef PCB_EMU
             if (smem_f > 48 * 1024) PCB_CUDA_OK(cudaFuncSetAttribute(k_update_res, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
 #endif
-            PCB_LAUNCH(k_update_res, dim3((unsigned)gxf, 1, 1), dim3(768, 1, 1), smem_f, c->stream, o->d, Sin, HSin, X, HX, P, HP, rs, dE, m, kx, kp, MPp, c->partial);
+            PCB_LAUNCH(k_update_res, dim3((unsigned)gxf, 1, 1), dim3(PCB_UPDRES_THREADS, 1, 1), smem_f, c->stream, o->d, Sin, HSin, X, HX, P, HP, rs, dE, m, kx, kp, MPp, c->partial);
             PCB_CUDA_OK(cudaGetLastError());
             double* dout = c->partial + (size_t)gxf * 16;
             PCB_LAUNCH(k_sum_partials, dim3(1, 1, 1), dim3(64, 1, 1), 0, c->stream, (const double*)c->partial, (int)gxf, 16, dout);
