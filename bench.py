@@ -365,6 +365,17 @@ def cpu_full_baseline(n, alpha, cores):
     o = oc.eigen_1p(48, "sc_curv", np.array([np.pi, np.pi, np.pi]), type="chiral", nev=10, x0=x0)
     out["c1_solve_s"] = time.perf_counter() - t0
     out["c1_iterations"] = int(o["info"][0])
+    # the same solve (same x0) on the GPU, for the record next to it
+    mfd, ne = pcb.discretization, pcb.numerical_experiments
+    al = np.array([np.pi, np.pi, np.pi])
+    relax, pnt = mfd.set_relaxation(al)
+    af, bf = mfd.fft_blocks(48, 1, pcb.dielectric.diel_info("sc_curv", option="ct"), alpha=al)
+    iv = mfd.inverse_3_times_3_B(bf, pnt, relax[0])
+    A1, H1, P1 = ne.pc_mfd_handle(af, (pnt * bf[0], pnt * bf[1]), mfd.chiral_handle(48, "sc_curv"), iv, relax[0])
+    lam_g, _, info_g = pcb.lobpcg.lobpcg_sep_softlock(H1, P1, x0, 10)
+    out["c1_gpu_solve_s"] = float(info_g[1])
+    out["c1_gpu_iterations"] = int(info_g[0])
+    out["c1_max_rel_eig_diff_gpu_vs_cpu"] = float(np.max(np.abs(lam_g[:10] - o["lambdas"][:10]) / np.abs(o["lambdas"][:10])))
     a_fft, b_fft, inv_fft, shift, _ = oc.assemble_symbols(n, LATTICE, alpha)
     ind_e = pcb.dielectric.compute_index(n, LATTICE, "edge")
     A, H, P = oc.pc_mfd_handle(a_fft, b_fft, oc.chiral_handle(n, LATTICE, ind_e=ind_e), inv_fft, shift)

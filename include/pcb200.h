@@ -142,6 +142,10 @@ int pcb_update(pcb_ctx* ctx, int m, int n_loc, void* const* s, void* const* hs, 
  * re-read; wider blocks run pcb_update + pcb_residual back to back.  w_out may be the W columns that are inputs of the update. */
 int pcb_update_resid(pcb_op* op, int m, int nl, void* const* s, void* const* hs, void* const* p_out, void* const* hp_out, const void* E,
                      const double* lambda, void* const* w_out, double* norms2);
+/* the same in two halves: _start enqueues the kernels and returns (host bookkeeping overlaps the GPU), _wait delivers norms2 */
+int pcb_update_resid_start(pcb_op* op, int m, int nl, void* const* s, void* const* hs, void* const* p_out, void* const* hp_out, const void* E,
+                           const double* lambda, void* const* w_out);
+int pcb_update_resid_wait(pcb_op* op, int m, double* norms2);
 /* out[j] = a_j^H b_j (complex128 on the host) -- diag(x^H y) of numerical_experiments.py:105-111, environment.dots */
 int pcb_coldots(pcb_ctx* ctx, int ncols, const void* const* a, const void* const* b, void* out);
 /* y_j = alpha x_j + beta y_j */

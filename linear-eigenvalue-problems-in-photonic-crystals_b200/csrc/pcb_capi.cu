@@ -72,6 +72,9 @@ struct pcb_ctx {
     cudaStream_t stream = nullptr;
     const PcbOpLaunch* plan = nullptr;
     cplx* tw = nullptr;             // [R1][R2] forward twiddles exp(-2 pi i k1 n2 / N)
+    double pending_norms[32];       // pcb_update_resid_start / _wait: norms of a fused update whose result has not been fetched yet
+    int pending_state = 0;          // 0 none, 1 on their way into hstage (stream not yet synchronised), 2 ready in pending_norms
+    int pending_m = 0;
     PcbDist* ddist = nullptr;       // large-grid mode over peer memory: device copy of the slab pointer table of the current apply
     int* ctab = nullptr;            // plane mode: slot -> index and index -> slot tables of the plan (k_coord_tables)
     double* partial = nullptr;      // reduction partials (device)
@@ -988,9 +991,11 @@ static int update_impl(pcb_ctx* c, pcb_op* o, int m, int nl, void* const* s, voi
             PCB_CUDA_OK(cudaGetLastError());
             c->launches += 2;
             if (comm_allreduce(c, dout, m)) return -1;
-            PCB_CUDA_OK(cudaMemcpyAsync(c->hstage, dout, sizeof(double) * m, cudaMemcpyDeviceToHost, c->stream));
+            char* hn = (char*)c->hstage + sizeof(cplx) * 2 * PCB_MAXL * PCB_MAXL;      // behind the E staging area
+            PCB_CUDA_OK(cudaMemcpyAsync(hn, dout, sizeof(double) * m, cudaMemcpyDeviceToHost, c->stream));
+            if (!norms2) { c->pending_state = 1; c->pending_m = m; return 0; }      // pcb_update_resid_start: fetched by _wait
             PCB_CUDA_OK(cudaStreamSynchronize(c->stream));
-            memcpy(norms2, c->hstage, sizeof(double) * m);
+            memcpy(norms2, hn, sizeof(double) * m);
             return 0;
         }
     }
@@ -1014,7 +1019,31 @@ static int update_impl(pcb_ctx* c, pcb_op* o, int m, int nl, void* const* s, voi
     else PCB_UPD_GO((k_update<16, 2>));
     PCB_CUDA_OK(cudaGetLastError());
     c->launches++;
-    if (o) return pcb_residual(o, 1, m, (const void* const*)s, (const void* const*)hs, w_out, lambda, norms2);      // wide blocks: two kernels
+    if (o) {      // wide blocks: two kernels
+        double* dst = norms2 ? norms2 : c->pending_norms;
+        const int rc = pcb_residual(o, 1, m, (const void* const*)s, (const void* const*)hs, w_out, lambda, dst);
+        if (!norms2 && rc == 0) { c->pending_state = 2; c->pending_m = m; }
+        return rc;
+    }
+    return 0;
+}
+/* pcb_update_resid in two halves: _start enqueues everything and returns while the GPU works (the caller's host-side
+ * bookkeeping -- the rotated Gram blocks of the incremental Gram pair -- overlaps the kernel), _wait returns the norms. */
+int pcb_update_resid_start(pcb_op* o, int m, int nl, void* const* s, void* const* hs, void* const* p_out, void* const* hp_out, const void* E,
+                           const double* lambda, void* const* w_out) {
+    PCB_CHECK_ARG(o && lambda && w_out, "bad arguments");
+    o->ctx->pending_state = 0;
+    return update_impl(o->ctx, o, m, nl, s, hs, p_out, hp_out, E, lambda, w_out, nullptr);
+}
+int pcb_update_resid_wait(pcb_op* o, int m, double* norms2) {
+    PCB_CHECK_ARG(o && norms2 && o->ctx->pending_state != 0 && o->ctx->pending_m == m, "no pending pcb_update_resid_start of this width");
+    pcb_ctx* c = o->ctx;
+    if (c->pending_state == 1) {
+        PCB_CUDA_OK(cudaSetDevice(c->device));
+        PCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+        memcpy(norms2, (char*)c->hstage + sizeof(cplx) * 2 * PCB_MAXL * PCB_MAXL, sizeof(double) * m);
+    } else memcpy(norms2, c->pending_norms, sizeof(double) * m);
+    c->pending_state = 0;
     return 0;
 }
 

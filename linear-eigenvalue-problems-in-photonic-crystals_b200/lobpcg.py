@@ -219,6 +219,14 @@ def _lobpcg_sep_softlock(h_func_in, p_func, x0, nev, shift=0.0, tol=TOL, maxiter
             say(f"{RED}Nan occurs after Rayleigh-Ritz procedure.{RESET}")
             return None, None, None
         lambdas, eigvec = lambdas[:m], np.ascontiguousarray(eigvec[:, :m])
+        # _sep_update_after_rr (lobpcg.py:1248-1270) in one pass (+ the next residual, norms and K_P^-1 on the fused path, enqueued
+        # before the host-side bookkeeping below so that the two overlap)
+        wait_nrms = None
+        if fuse_resid:
+            wait_nrms = op.update_resid_start(m, n_loc, s_loc, hs_loc, P, HP, eigvec, lambdas, W)
+        else:
+            L.check(L.lib().pcb_update(ctx.h, m, n_loc, L.ptr_array(s_loc.ptrs), L.ptr_array(hs_loc.ptrs),
+                                       L.ptr_array(P.ptrs), L.ptr_array(HP.ptrs), eigvec.ctypes.data), "pcb_update")
         if incremental_gram:
             # Gram pair of the rotated blocks X' = S E, P' = S E_p (E_p = E with the X rows zeroed), all m columns of P'
             e_p = eigvec.copy()
@@ -227,12 +235,8 @@ def _lobpcg_sep_softlock(h_func_in, p_func, x0, nev, shift=0.0, tol=TOL, maxiter
             g_xp = hermitize(ee.conj().T @ ss @ ee)
             t_xp = hermitize(ee.conj().T @ shs @ ee)
 
-        # _sep_update_after_rr (lobpcg.py:1248-1270) in one pass (+ the next residual, norms and K_P^-1 on the fused path)
-        if fuse_resid:
-            next_nrms = op.update_resid(m, n_loc, s_loc, hs_loc, P, HP, eigvec, lambdas, W)
-        else:
-            L.check(L.lib().pcb_update(ctx.h, m, n_loc, L.ptr_array(s_loc.ptrs), L.ptr_array(hs_loc.ptrs),
-                                       L.ptr_array(P.ptrs), L.ptr_array(HP.ptrs), eigvec.ctypes.data), "pcb_update")
+        if wait_nrms is not None:
+            next_nrms = wait_nrms()
         say(f"Runtime = {time.time() - t_iter_h:<6.4f}s.")
 
     ctx.sync()

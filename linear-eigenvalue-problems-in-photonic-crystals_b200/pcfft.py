@@ -111,6 +111,21 @@ class Operator:
         return np.sqrt(out)
 
 
+    def update_resid_start(self, m, n_loc, s_loc, hs_loc, P, HP, E, lambdas, W):
+        """update_resid without waiting for the result: returns a callable that delivers the norms (host work overlaps the GPU)."""
+        lam = np.ascontiguousarray(lambdas, dtype=np.float64)
+        keep = (E, lam, s_loc, hs_loc)      # alive until the kernels have been enqueued (the C side stages E synchronously)
+        L.check(self._lib.pcb_update_resid_start(self.h, m, n_loc, L.ptr_array(s_loc.ptrs), L.ptr_array(hs_loc.ptrs), L.ptr_array(P.ptrs),
+                                                 L.ptr_array(HP.ptrs), E.ctypes.data, lam.ctypes.data_as(L.c_double_p),
+                                                 L.ptr_array(W.ptrs)), "pcb_update_resid_start")
+
+        def wait():
+            out = np.empty(m, dtype=np.float64)
+            L.check(self._lib.pcb_update_resid_wait(self.h, m, out.ctypes.data_as(L.c_double_p)), "pcb_update_resid_wait")
+            return np.sqrt(out)
+        return wait
+
+
 class OperatorCallable:
     """What pc_mfd_handle returns instead of a lambda: callable like the reference's closures, and
     recognisable by the solver so that it can run the fused device path."""

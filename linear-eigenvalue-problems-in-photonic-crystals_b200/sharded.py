@@ -161,6 +161,9 @@ class ShardedOperator:
     def update_resid(self, *args):
         return self.local.update_resid(*args)       # row-local on the slabs; the norms are all-reduced inside the C ABI
 
+    def update_resid_start(self, *args):
+        return self.local.update_resid_start(*args)
+
     def apply_into(self, mode, src, dst):
         if src.k == 0:
             return dst
