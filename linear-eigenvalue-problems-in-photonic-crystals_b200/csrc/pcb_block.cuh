@@ -698,8 +698,6 @@ __global__ void __launch_bounds__(256) k_diel_point(PcbOp op, const cplx* __rest
 // Cross-DoF dielectric (discretization.py:403-453): diagonal + eps_ab * S_ab couplings,
 // S_ab = (I_a T_ab + T_ab I_b)/2,  T_ab = c (x) c^T on two of the three axes (stencil c with 2k taps).
 // One thread per grid point computes all three output components (gather form); out of place.
-struct PcbStencil { int k; double w[8]; };   // taps w[j] at offsets (1-k+j), j < 2k
-PCB_HD int pcb_wrap(int i, int N) { i %= N; return i < 0 ? i + N : i; }
 
 // K > 0: 2K taps known at compile time (K = 1 is the reference's default, discretization.py:403); K = 0: runtime st.k.
 // One thread per grid point and column (blockIdx.y): all three output components (gather form); out of place.
@@ -826,6 +824,39 @@ __global__ void __launch_bounds__(256) k_diel_crossdof_t(PcbOp op, PcbStencil st
     }
     PCB_UNROLL
     for (int c = 0; c < 3; ++c) Y[c * nn + pt] = y[c];
+}
+
+// Set-up for the fused stencil-on-load: bit 4 + c of the slot-ordered mask byte = "component c at this point has a non-zero
+// cross-DoF coupling term" (its own DoF or any tap of a pair with eps_ab != 0 lies in Omega_1) -- elsewhere M is the identity
+// for that component and the plane pass touches nothing.  src: k_mask_plane's bytes (bits 0-3), dst: the same plus bits 4-6.
+__global__ void __launch_bounds__(256) k_mask_active(PcbOp op, const unsigned char* __restrict__ src, unsigned char* __restrict__ dst) {
+    const int N = op.N;
+    const long long pt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pt >= op.nn) return;
+    const int* __restrict__ ctab = op.ctab;
+    const int i[3] = {(int)(pt / ((long long)N * N)), ctab[(int)(pt % N)], ctab[(int)((pt / N) % N)]};
+    const unsigned mp = src[pt];
+    constexpr int PA[3] = {0, 0, 1}, PB[3] = {1, 2, 2}, CAX[3] = {2, 2, 1}, TAX[3] = {1, 0, 0};
+    const int kk = op.sten.k;
+    unsigned act = 0u;
+    for (int pr = 0; pr < 3; ++pr) {
+        const cplx e = op.eoff[pr];
+        if (e.x == 0.0 && e.y == 0.0) continue;
+        const int a = PA[pr], b = PB[pr], cax = CAX[pr], tax = TAX[pr];
+        act |= (((mp >> a) & 1u) << a) | (((mp >> b) & 1u) << b);
+        for (int j1 = 0; j1 < 2 * kk; ++j1)
+            for (int j2 = 0; j2 < 2 * kk; ++j2) {
+                const int oc = 1 - kk + j1, ot = 1 - kk + j2;
+                int q[3] = {i[0], i[1], i[2]}, r[3] = {i[0], i[1], i[2]};
+                q[cax] = pcb_wrap(i[cax] + oc, N); q[tax] = pcb_wrap(i[tax] - ot, N);
+                r[cax] = pcb_wrap(i[cax] - oc, N); r[tax] = pcb_wrap(i[tax] + ot, N);
+                const long long qs = ((long long)q[0] * N + ctab[N + q[2]]) * N + ctab[N + q[1]];
+                const long long rs = ((long long)r[0] * N + ctab[N + r[2]]) * N + ctab[N + r[1]];
+                act |= ((unsigned)(src[qs] >> b) & 1u) << a;      // y_a(p) sees I_b(q)
+                act |= ((unsigned)(src[rs] >> a) & 1u) << b;      // y_b(p) sees I_a(r)
+            }
+    }
+    dst[pt] = (unsigned char)((mp & 15u) | (act << 4));
 }
 
 // ---- stand-alone point-wise symbol multiplies (drop-in A_block / H_block kernels) ---------------------

@@ -91,7 +91,8 @@ struct pcb_ctx {
     int sms = 148;
     int use_plane = 1;              // PCB200_PLANE=0 forces the five-pass operator (A/B measurements)
     int use_plane_coupled = 1;      // PCB200_PLANE_COUPLED=0: coupled 3x3 dielectric on the five-pass path
-    int use_plane_cross = 1;        // PCB200_PLANE_CROSS=0: cross-DoF dielectric on the split five-pass path (7 kernels)
+    int use_plane_cross = 1;        // cross-DoF dielectric: 1 = plane halves with the stencil fused into the inverse half (4 kernels, default),
+                                    // 2 = plane halves around the stencil kernel (5 kernels), 0 (PCB200_PLANE_CROSS=0) = split five-pass path (7 kernels)
     int use_mid_five = -1;          // five-sweep plane pass k_mid2: -1 where it is the faster form (R2 >= 15), 0 never, 1 wherever it exists
     // pcb_apply_host pipeline: copy streams, two slots of (row-major staging in/out, planar columns in/out), events
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
@@ -206,7 +207,7 @@ static int ctx_create(int device, int N, int z0, int z1, pcb_ctx** out) {
     c->z0 = z0; c->z1 = z1; c->nloc = (long long)(z1 - z0) * N * N; c->R = 3 * c->nloc;
     { const char* e = getenv("PCB200_PLANE"); c->use_plane = (plan->plane_mode && !(e && e[0] == '0')) ? 1 : 0; }
     { const char* e = getenv("PCB200_PLANE_COUPLED"); c->use_plane_coupled = !(e && e[0] == '0'); }
-    { const char* e = getenv("PCB200_PLANE_CROSS"); c->use_plane_cross = !(e && e[0] == '0'); }
+    { const char* e = getenv("PCB200_PLANE_CROSS"); c->use_plane_cross = e ? (e[0] == '0' ? 0 : (e[0] == '2' ? 2 : 1)) : 1; }
     { const char* e = getenv("PCB200_MID_FIVE"); c->use_mid_five = e ? (e[0] == '0' ? 0 : 1) : -1; }
 #ifndef PCB_EMU
     cudaDeviceProp prop;
@@ -269,7 +270,7 @@ int pcb_ctx_option(pcb_ctx* c, const char* name, int value) {
     PCB_CHECK_ARG(c && name, "null");
     if (!strcmp(name, "plane")) c->use_plane = (value && c->plan->plane_mode) ? 1 : 0;
     else if (!strcmp(name, "plane_coupled")) c->use_plane_coupled = value ? 1 : 0;
-    else if (!strcmp(name, "plane_cross")) c->use_plane_cross = value ? 1 : 0;
+    else if (!strcmp(name, "plane_cross")) c->use_plane_cross = (value == 2) ? 2 : (value ? 1 : 0);
     else if (!strcmp(name, "mid_five")) c->use_mid_five = value < 0 ? -1 : (value ? 1 : 0);
     else { pcb_set_error("pcb_ctx_option: unknown option %s", name); return -2; }
     return 0;
@@ -460,6 +461,19 @@ int pcb_diel_create(pcb_ctx* c, int kind, const int64_t* ind_e, long long n_e, c
             tmp.maskp = d->maskp;
             if (c->plan->pass(tmp, none, 1, PCB_PASS_MASKPLANE, c->tw, c->stream, c->sms)) { pcb_diel_destroy(d); return -1; }
             c->launches++;
+            if (kind == PCB_DIEL_CROSSDOF) {
+                // bits 4-6: where each component has a coupling term at all (the fused stencil-on-load skips the rest)
+                unsigned char* withact = nullptr;
+                PCB_CUDA_OK_OR(cudaMalloc(&withact, (size_t)c->nn), pcb_diel_destroy(d));
+                tmp.ctab = c->ctab; tmp.sten = d->st;
+                for (int i = 0; i < 3; ++i) tmp.eoff[i] = d->eoff[i];
+                PCB_LAUNCH(k_mask_active, dim3((unsigned)((c->nn + 255) / 256), 1, 1), dim3(256, 1, 1), 0, c->stream, tmp, (const unsigned char*)d->maskp, withact);
+                PCB_CUDA_OK_OR(cudaGetLastError(), { cudaFree(withact); pcb_diel_destroy(d); });
+                PCB_CUDA_OK_OR(cudaStreamSynchronize(c->stream), { cudaFree(withact); pcb_diel_destroy(d); });
+                cudaFree(d->maskp);
+                d->maskp = withact;
+                c->launches++;
+            }
         }
     }
     PCB_CUDA_OK_OR(cudaStreamSynchronize(c->stream), pcb_diel_destroy(d));
@@ -489,6 +503,7 @@ static void op_fill(pcb_op* o, double gamma, double shift, double pshift, pcb_di
     o->d.mbits = diel ? diel->mbits : nullptr;
     o->d.maskp = diel ? diel->maskp : nullptr;
     o->d.mbits2 = diel ? diel->mbits2 : nullptr;
+    if (diel) o->d.sten = diel->st; else { o->d.sten.k = 1; for (int i = 0; i < 8; ++i) o->d.sten.w[i] = 0.0; }
     o->d.ctab = c->ctab;
     o->d.dist = nullptr;
     o->d.mid_five = (c->plan->plane_five && (c->use_mid_five == 1 || (c->use_mid_five == -1 && c->plan->r2 >= 15))) ? 1 : 0;
@@ -557,14 +572,14 @@ static int launch_crossdof_t(pcb_op* o, int kc, const PcbCols& cols) {
 
 // Pass structure of an A / H apply: 0 plane mode (3 passes), 1 five passes, 2 five passes split around the
 // cross-DoF stencil (7 kernels), 3 plane mode split around the stencil on the slot layout (5 kernels)
-enum { PCB_STRUCT_PLANE = 0, PCB_STRUCT_FIVE = 1, PCB_STRUCT_CROSS7 = 2, PCB_STRUCT_CROSS5 = 3 };
+enum { PCB_STRUCT_PLANE = 0, PCB_STRUCT_FIVE = 1, PCB_STRUCT_CROSS7 = 2, PCB_STRUCT_CROSS5 = 3, PCB_STRUCT_CROSS4 = 4 };
 static int apply_structure(const pcb_op* o) {
     const pcb_ctx* c = o->ctx;
     const int diel = o->d.diel;
     if (c->use_plane) {
         if (diel == PCB_DIEL_NONE || diel == PCB_DIEL_CHIRAL) return PCB_STRUCT_PLANE;
         if (diel == PCB_DIEL_TRIVIAL && c->plan->plane_coupled && c->use_plane_coupled) return PCB_STRUCT_PLANE;
-        if (diel == PCB_DIEL_CROSSDOF && c->use_plane_cross) return PCB_STRUCT_CROSS5;
+        if (diel == PCB_DIEL_CROSSDOF && c->use_plane_cross) return c->use_plane_cross == 2 ? PCB_STRUCT_CROSS5 : PCB_STRUCT_CROSS4;
     }
     return diel == PCB_DIEL_CROSSDOF ? PCB_STRUCT_CROSS7 : PCB_STRUCT_FIVE;
 }
@@ -580,7 +595,7 @@ static int apply_AH(pcb_op* o, int mode, PcbCols& cols, int kc, int j0, int dist
     const int last = (mode == PCB_APPLY_A) ? (dout ? PCB_PASS_XINV_A_D : PCB_PASS_XINV_A) : (dout ? PCB_PASS_XINV_H_D : PCB_PASS_XINV_H);
     const int last_t = (mode == PCB_APPLY_A) ? (dout ? PCB_PASS_XINV_A_TD : PCB_PASS_XINV_A_T) : (dout ? PCB_PASS_XINV_H_TD : PCB_PASS_XINV_H_T);
     const int st = apply_structure(o);
-    if ((mode == PCB_APPLY_H && st != PCB_STRUCT_PLANE) || st == PCB_STRUCT_CROSS5 || dist)
+    if ((mode == PCB_APPLY_H && st != PCB_STRUCT_PLANE) || st == PCB_STRUCT_CROSS5 || st == PCB_STRUCT_CROSS4 || dist)
         for (int j = 0; j < kc; ++j)
             if (cols.in[j] == cols.out[j]) {
                 pcb_set_error("pcb_apply: in[%d] == out[%d]; this pass structure re-reads X / uses out as work space, use distinct columns", j0 + j, j0 + j);
@@ -593,6 +608,14 @@ static int apply_AH(pcb_op* o, int mode, PcbCols& cols, int kc, int j0, int dist
         const int seq[3] = {first_t, PCB_PASS_MID, last_t};
         for (int i = 0; i < 3; ++i) if (pl->pass(o->d, cols, kc, seq[i], c->tw, c->stream, c->sms)) return -1;
         c->launches += 3;
+    } else if (st == PCB_STRUCT_CROSS4) {
+        // x forward -> scratch, forward half of the plane pass scratch -> out (real-space planes, slot layout), inverse half with
+        // the stencil applied on load out -> scratch, x inverse scratch -> out
+        if (ensure_scratch(c, sizeof(cplx) * (size_t)c->R * (size_t)kc)) return -1;
+        for (int j = 0; j < kc; ++j) cols.wrk[j] = c->scratch + (size_t)j * c->R;
+        const int seq[4] = {first_t, PCB_PASS_MID_FWD_O, PCB_PASS_MID_INV_ST, last_t};
+        for (int i = 0; i < 4; ++i) if (pl->pass(o->d, cols, kc, seq[i], c->tw, c->stream, c->sms)) return -1;
+        c->launches += 4;
     } else if (st == PCB_STRUCT_CROSS5) {
         // x forward -> scratch, forward half of the plane pass in place, stencil scratch -> out (slot layout),
         // inverse half out -> scratch, x inverse scratch -> out
@@ -704,6 +727,9 @@ int pcb_apply_timed(pcb_op* o, int mode, int ncols, const void* const* in, void*
     if (st == PCB_STRUCT_PLANE) {
         for (int j = 0; j < ncols; ++j) cols.wrk[j] = c->scratch + (size_t)j * c->R;
         seq[0] = PCB_PASS_XFWD_SYM_T; seq[1] = PCB_PASS_MID; seq[2] = last_t; n = 3;
+    } else if (st == PCB_STRUCT_CROSS4) {
+        for (int j = 0; j < ncols; ++j) cols.wrk[j] = c->scratch + (size_t)j * c->R;
+        seq[0] = PCB_PASS_XFWD_SYM_T; seq[1] = PCB_PASS_MID_FWD_O; seq[2] = PCB_PASS_MID_INV_ST; seq[3] = last_t; n = 4;
     } else if (st == PCB_STRUCT_CROSS5) {
         for (int j = 0; j < ncols; ++j) cols.wrk[j] = c->scratch + (size_t)j * c->R;
         seq[0] = PCB_PASS_XFWD_SYM_T; seq[1] = PCB_PASS_MID_FWD; seq[2] = STENCIL_T; seq[3] = PCB_PASS_MID_INV; seq[4] = last_t; n = 5;

@@ -112,6 +112,9 @@ struct PcbDist {
     double2* dst[PCB_MAXC_DIST][PCB_MAXW];         // output column j, slab of rank g
 };
 
+struct PcbStencil { int k; double w[8]; };   // averaging stencil of the cross-DoF dielectric: taps w[j] at offsets (1-k+j), j < 2k
+PCB_HD int pcb_wrap(int i, int N) { i %= N; return i < 0 ? i + N : i; }
+
 struct PcbOp {
     int N;
     long long nn;             // N^3
@@ -127,6 +130,7 @@ struct PcbOp {
     const unsigned* mbits;      // plane mode: [c][i0][slot][k1] words, bit k2 = component c of (i0, i1 = coord(slot), i2 = lout(k1,k2)) in Omega_1
     const unsigned* mbits2;     // five-sweep plane pass (k_mid2): [c][i0][d][col] words, bit k2 (k_mask_bits2)
     const unsigned char* maskp; // plane mode, coupled dielectric: the byte mask in plane-slot order, [i0][row][col] = mask(i0, coord(col), coord(row))
+    PcbStencil sten;            // cross-DoF dielectric: its averaging stencil (the fused stencil-on-load of the plane pass)
     int mid_five;               // plane mode: 1 = the five-sweep plane pass (k_mid2), 0 = the seven-sweep one (k_mid)
     const PcbDist* dist;        // large-grid mode over peer memory: slab pointers of the columns (device memory), else null
     const int* ctab;            // plane mode: [0, N) slot -> grid index (coord), [N, 2N) grid index -> slot

@@ -688,6 +688,53 @@ __global__ void k_mask_bits(PcbOp op, unsigned* __restrict__ out) {
 // butterflies, or software-pipelined so that item i+1's loads go out before item i's stores; the shared-memory plane carries no
 // restrict information, so the compiler keeps each trip's loads behind the previous trip's stores.  At the 128-register cap of
 // 15 warps either form spills 400-800 bytes per thread and the pass takes 1.17 instead of 0.82 ms at N = 120, 16 columns.)
+// Cross-DoF dielectric (discretization.py:403-453) on the PLANE-SLOT layout, one output component at one point: the
+// off-diagonal part  sum_b eps_cb (S_cb x_b)(p)  with S_ab = (I_a T_ab + T_ab I_b)/2, T_ab = c (x) c^T on two axes (2k taps each).
+// X: a column in the slot layout W'[c][i0][row][col] (point (i0, coord(col), coord(row))), maskp the byte mask in the same
+// order, ctab the slot <-> index tables.  i[] = grid indices of the point, mp = its mask byte.
+template <int K>
+PCB_D cplx pcb_crossdof_couple(const PcbOp& op, int c, const int i[3], unsigned mp, const cplx* __restrict__ X) {
+    const int N = op.N;
+    const long long nn = op.nn;
+    const int* __restrict__ ctab = op.ctab;
+    const unsigned char* __restrict__ maskp = op.maskp;
+    constexpr int PA[3] = {0, 0, 1}, PB[3] = {1, 2, 2}, CAX[3] = {2, 2, 1}, TAX[3] = {1, 0, 0};
+    const int kk = K > 0 ? K : op.sten.k;
+    cplx out = cmake(0.0, 0.0);
+    PCB_UNROLL
+    for (int pr = 0; pr < 3; ++pr) {
+        const cplx e = op.eoff[pr];
+        const int a = PA[pr], b = PB[pr], cax = CAX[pr], tax = TAX[pr];
+        if ((c != a && c != b) || (e.x == 0.0 && e.y == 0.0)) continue;
+        const bool first = (c == a);                 // y_a += e S x_b   |   y_b += conj(e) S^T x_a
+        const int other = first ? b : a;
+        const double Ic = (double)((mp >> c) & 1u);
+        const cplx* __restrict__ Xo = X + other * nn;
+        cplx sacc = cmake(0.0, 0.0);
+#ifndef PCB_EMU
+#pragma unroll
+#endif
+        for (int j1 = 0; j1 < (K > 0 ? 2 * K : 2 * kk); ++j1) {
+            const int oc = 1 - kk + j1;
+#ifndef PCB_EMU
+#pragma unroll
+#endif
+            for (int j2 = 0; j2 < (K > 0 ? 2 * K : 2 * kk); ++j2) {
+                const int ot = 1 - kk + j2;
+                const double w = op.sten.w[j1] * op.sten.w[j2] * 0.5;
+                int q[3] = {i[0], i[1], i[2]};
+                q[cax] = pcb_wrap(i[cax] + (first ? oc : -oc), N);
+                q[tax] = pcb_wrap(i[tax] + (first ? -ot : ot), N);
+                const long long qs = ((long long)q[0] * N + __ldg(ctab + N + q[2])) * N + __ldg(ctab + N + q[1]);
+                const double Io = (double)((__ldg(maskp + qs) >> other) & 1u);
+                sacc = cadd(sacc, cscale(Xo[qs], w * (Ic + Io)));
+            }
+        }
+        out = first ? cfma(e, sacc, out) : cfmac(e, sacc, out);
+    }
+    return out;
+}
+
 // DIEL = 2 (coupled 3x3 point-wise M, discretization.py:368-401): the kernel is launched as CLUSTERS OF THREE CTAs, one per
 // component of the same (column, i0) plane.  The fused z step is split at real space: (A) forward radix R2 and the diagonal
 // entries (bit words as for DIEL = 1) -> own plane; cluster barrier; (B) every CTA takes a third of the rows and, at the
@@ -699,7 +746,13 @@ __global__ void k_mask_bits(PcbOp op, unsigned* __restrict__ out) {
 // HALF = 1 / 2: only the forward (y, z) / inverse (z, y) transforms of the plane, M left out -- the cross-DoF dielectric is a
 // stencil across planes and runs as its own kernel on the real-space planes in between (k_diel_crossdof_t, pcb_block.cuh).
 // HALF = 2 loads from cols.out (the stencil's output) and stores to cols.wrk.
-template <class P, int DIEL, int TMA = 0, int HALF = 0>
+// STEN (with the halves): the stencil is FUSED into the inverse half instead -- HALF = 1 then stores its real-space planes to
+// cols.out, and HALF = 2, once a warp's rows have landed, applies M to them in shared memory: the diagonal entry, and at the
+// points flagged by k_mask_active (a quarter of the cells for the gyroids) the coupling terms, whose taps it gathers from the
+// real-space planes of the other components in cols.out (same or neighbouring i0; L2 hits, the planes of a wave of CTAs are
+// adjacent).  Four kernels, 9 column transfers instead of five kernels / 11.  STEN = 2 * K + 1 encodes the stencil half-width
+// K at compile time (K = 1, 2), STEN = 1 reads it from op.sten.
+template <class P, int DIEL, int TMA = 0, int HALF = 0, int STEN = 0>
 __global__ void __launch_bounds__(P::N / 8 * 32, 1) k_mid(PcbOp op, PcbCols cols, const cplx* __restrict__ tw, int ncols) {
     constexpr int N = P::N, R1 = P::R1, R2 = P::R2;
     constexpr int LD = N + 1;                    // row stride (complex)
@@ -733,8 +786,8 @@ __global__ void __launch_bounds__(P::N / 8 * 32, 1) k_mid(PcbOp op, PcbCols cols
     for (int pid = first; pid < total; pid += stride) {
         const int col = (DIEL == 2) ? pid / N : pid / (3 * N), c = (DIEL == 2) ? crank : (pid / N) % 3, i0 = pid % N;
         const long long poff = c * nn + (long long)i0 * N * N + (long long)(8 * warp) * N;      // this warp's 8 rows
-        cplx* __restrict__ base = cols.wrk[col] + poff;
-        const cplx* __restrict__ src = (HALF == 2) ? cols.out[col] + poff : base;
+        cplx* __restrict__ base = ((STEN && HALF == 1) ? cols.out[col] : cols.wrk[col]) + poff;
+        const cplx* __restrict__ src = (HALF == 2) ? cols.out[col] + poff : cols.wrk[col] + poff;
         // ---- load own rows (contiguous 8*N elements) ----
 #ifndef PCB_EMU
         if (TMA) {
@@ -783,6 +836,25 @@ __global__ void __launch_bounds__(P::N / 8 * 32, 1) k_mid(PcbOp op, PcbCols cols
 #endif
         pcb_cp_wait<0>();
         __syncwarp();
+        if (STEN && HALF == 2) {
+            // ---- M on own rows (real space): diagonal, and the cross-DoF coupling gathered from the other components' planes ----
+            const unsigned char* __restrict__ mrow = op.maskp + ((long long)i0 * N + 8 * warp) * N;
+            const cplx* __restrict__ Xcol = cols.out[col];
+            const int* __restrict__ ctab = op.ctab;
+            for (int e = lane; e < 8 * N; e += 32) {
+                const unsigned mk = __ldg(mrow + e);
+                if ((mk >> c) & 17u) {      // own DoF in Omega_1 (bit c) or a coupling term present (bit 4 + c)
+                    const int rl = e / N, cl = e % N;
+                    cplx v = cscale(myrows[rl * LD + cl], ((mk >> c) & 1u) ? op.ediag[c] : 1.0);
+                    if ((mk >> (4 + c)) & 1u) {
+                        const int ii[3] = {i0, __ldg(ctab + cl), __ldg(ctab + 8 * warp + rl)};
+                        v = cadd(v, pcb_crossdof_couple<(STEN - 1) / 2>(op, c, ii, mk, Xcol));
+                    }
+                    myrows[rl * LD + cl] = v;
+                }
+            }
+            __syncwarp();
+        }
         if (FWD) {
             // ---- forward y on own rows: lanes = (row fastest, digit) ----
             for (int it = lane; it < 8 * R2; it += 32) {
@@ -1300,6 +1372,9 @@ enum { PCB_PASS_XFWD_SYM = 0, PCB_PASS_XFWD = 1, PCB_PASS_YFWD = 2, PCB_PASS_ZFW
        PCB_PASS_MASKBITS2 = 19 /* set-up: op.mask -> (unsigned*)op.mbits2 (five-sweep plane pass) */,
        // large-grid mode over peer memory: x passes reading / writing the slabs of all ranks (op.dist)
        PCB_PASS_XFWD_SYM_D = 20, PCB_PASS_XINV_A_D = 21, PCB_PASS_XINV_H_D = 22,
-       PCB_PASS_XFWD_SYM_TD = 23, PCB_PASS_XINV_A_TD = 24, PCB_PASS_XINV_H_TD = 25 };
+       PCB_PASS_XFWD_SYM_TD = 23, PCB_PASS_XINV_A_TD = 24, PCB_PASS_XINV_H_TD = 25,
+       // cross-DoF dielectric with the stencil fused into the inverse half of the plane pass (four kernels)
+       PCB_PASS_MID_FWD_O = 26 /* forward half, planes -> cols.out */, PCB_PASS_MID_INV_ST = 27 /* stencil on load + inverse half, cols.out -> cols.wrk */,
+       PCB_PASS_MASKACTIVE = 28 /* set-up: bits 4-6 of op.maskp */ };
 
 const PcbOpLaunch* pcb_find_plan(int N);

@@ -145,6 +145,23 @@ struct PlanePass<true, PP> {
             return 0;
         }
         constexpr bool kTma = kSmemMid + 128 <= 232448;
+        if (pass_id == PCB_PASS_MID_FWD_O || pass_id == PCB_PASS_MID_INV_ST) {      // ... with the stencil fused into the inverse half
+            const int k = op.sten.k;
+#ifndef PCB_EMU
+            if (kTma) {
+                if (pass_id == PCB_PASS_MID_FWD_O) PCB_GO_P((k_mid<PP, 0, 1, 1, 1>), (PP::N / 8 * 32), 3 * PP::N, kSmemMid + 128, 1);
+                else if (k == 1) PCB_GO_P((k_mid<PP, 0, 1, 2, 3>), (PP::N / 8 * 32), 3 * PP::N, kSmemMid + 128, 1);
+                else if (k == 2) PCB_GO_P((k_mid<PP, 0, 1, 2, 5>), (PP::N / 8 * 32), 3 * PP::N, kSmemMid + 128, 1);
+                else PCB_GO_P((k_mid<PP, 0, 1, 2, 1>), (PP::N / 8 * 32), 3 * PP::N, kSmemMid + 128, 1);
+                return 0;
+            }
+#endif
+            if (pass_id == PCB_PASS_MID_FWD_O) PCB_GO_P((k_mid<PP, 0, 0, 1, 1>), (PP::N / 8 * 32), 3 * PP::N, kSmemMid, 1);
+            else if (k == 1) PCB_GO_P((k_mid<PP, 0, 0, 2, 3>), (PP::N / 8 * 32), 3 * PP::N, kSmemMid, 1);
+            else if (k == 2) PCB_GO_P((k_mid<PP, 0, 0, 2, 5>), (PP::N / 8 * 32), 3 * PP::N, kSmemMid, 1);
+            else PCB_GO_P((k_mid<PP, 0, 0, 2, 1>), (PP::N / 8 * 32), 3 * PP::N, kSmemMid, 1);
+            return 0;
+        }
         if (pass_id == PCB_PASS_MID_FWD || pass_id == PCB_PASS_MID_INV) {      // halves of the plane pass (cross-DoF dielectric)
 #ifndef PCB_EMU
             if (kTma) {
@@ -236,7 +253,7 @@ int run_pass(const PcbOp& op, const PcbCols& cols, int ncols, int pass_id, const
             break;
         case PCB_PASS_XFWD_SYM_T: case PCB_PASS_MID: case PCB_PASS_XINV_A_T: case PCB_PASS_XINV_H_T: case PCB_PASS_MASKBITS:
         case PCB_PASS_MID_FWD: case PCB_PASS_MID_INV: case PCB_PASS_MASKPLANE: case PCB_PASS_COORDTAB: case PCB_PASS_MASKBITS2:
-        case PCB_PASS_XFWD_SYM_TD: case PCB_PASS_XINV_A_TD: case PCB_PASS_XINV_H_TD:
+        case PCB_PASS_XFWD_SYM_TD: case PCB_PASS_XINV_A_TD: case PCB_PASS_XINV_H_TD: case PCB_PASS_MID_FWD_O: case PCB_PASS_MID_INV_ST:
             return PlanePass<kPlane, P>::go(op, cols, ncols, pass_id, tw, s, sms);
         default: pcb_set_error("unknown pass id %d", pass_id); return -1;
     }

@@ -155,3 +155,23 @@ def test_five_sweep_plane_pass(pcb, oracle, typ):
         ctx.option("mid_five", -1)
     assert relerr(out[1], out[0]) < 1e-14
     assert not np.array_equal(out[1], out[0])      # two different kernels did run
+
+
+@pytest.mark.parametrize("structure", [1, 2, 0])
+def test_crossdof_pass_structures(pcb, oracle, structure):
+    """The three pass structures of the cross-DoF dielectric give the oracle's H: 1 = plane halves with the stencil fused into
+    the inverse half (default), 2 = plane halves around the stencil kernel on the slot layout, 0 = split five-pass path.
+    eps_opt = 3 couples all three component pairs (in-plane and across i0 planes)."""
+    N, d_flag = 16, "bcc_dg"
+    alpha = np.array([np.pi, 0.0, np.pi])
+    ctx = pcb.get_context(N)
+    case = {"N": N, "d_flag": d_flag, "alpha": alpha, "type": "pseudochiral_crossdof", "eps_opt": 3, "m": 2, "seed": 21}
+    a, b, inv, shift, _ = oracle.assemble_symbols(N, d_flag, alpha)
+    Ao, Ho, Po = oracle.pc_mfd_handle(a, b, oracle.HANDLES["pseudochiral_crossdof"](N, d_flag, eps_opt=3), inv, shift)
+    try:
+        ctx.option("plane_cross", structure)
+        A, H, P, Diels, x = _setup(pcb, oracle, case)
+        assert relerr(H(x), Ho(x)) < TOL
+        assert relerr(A(x), Ao(x)) < TOL
+    finally:
+        ctx.option("plane_cross", 1)
