@@ -692,15 +692,18 @@ __global__ void k_mask_bits(PcbOp op, unsigned* __restrict__ out) {
 // off-diagonal part  sum_b eps_cb (S_cb x_b)(p)  with S_ab = (I_a T_ab + T_ab I_b)/2, T_ab = c (x) c^T on two axes (2k taps each).
 // X: a column in the slot layout W'[c][i0][row][col] (point (i0, coord(col), coord(row))), maskp the byte mask in the same
 // order, ctab the slot <-> index tables.  i[] = grid indices of the point, mp = its mask byte.
-template <int K>
+// (N and the stencil half-width are compile-time here and all index arithmetic is 32-bit with conditional wraps: written with
+// runtime N, 64-bit indices and % the ~1000 instructions per coupled point made the fused pass issue-bound -- 1.33 ms instead of
+// the 1.19 ms of the two separate kernels at N = 120.)
+template <int N, int K>
 PCB_D cplx pcb_crossdof_couple(const PcbOp& op, int c, const int i[3], unsigned mp, const cplx* __restrict__ X) {
-    const int N = op.N;
-    const long long nn = op.nn;
+    const int nn = N * N * N;
     const int* __restrict__ ctab = op.ctab;
     const unsigned char* __restrict__ maskp = op.maskp;
     constexpr int PA[3] = {0, 0, 1}, PB[3] = {1, 2, 2}, CAX[3] = {2, 2, 1}, TAX[3] = {1, 0, 0};
     const int kk = K > 0 ? K : op.sten.k;
     cplx out = cmake(0.0, 0.0);
+    const double Ic = (double)((mp >> c) & 1u);
     PCB_UNROLL
     for (int pr = 0; pr < 3; ++pr) {
         const cplx e = op.eoff[pr];
@@ -708,24 +711,30 @@ PCB_D cplx pcb_crossdof_couple(const PcbOp& op, int c, const int i[3], unsigned 
         if ((c != a && c != b) || (e.x == 0.0 && e.y == 0.0)) continue;
         const bool first = (c == a);                 // y_a += e S x_b   |   y_b += conj(e) S^T x_a
         const int other = first ? b : a;
-        const double Ic = (double)((mp >> c) & 1u);
         const cplx* __restrict__ Xo = X + other * nn;
         cplx sacc = cmake(0.0, 0.0);
 #ifndef PCB_EMU
 #pragma unroll
 #endif
         for (int j1 = 0; j1 < (K > 0 ? 2 * K : 2 * kk); ++j1) {
-            const int oc = 1 - kk + j1;
+            const int oc = first ? 1 - kk + j1 : -(1 - kk + j1);
+            int qc = i[cax] + oc;
+            qc += (qc < 0) ? N : 0; qc -= (qc >= N) ? N : 0;
+            // slot-layout position contributed by the c-axis index (axis 0: plane, 1: column, 2: row)
+            const int pc = cax == 0 ? qc * (N * N) : (cax == 1 ? __ldg(ctab + N + qc) : __ldg(ctab + N + qc) * N);
 #ifndef PCB_EMU
 #pragma unroll
 #endif
             for (int j2 = 0; j2 < (K > 0 ? 2 * K : 2 * kk); ++j2) {
-                const int ot = 1 - kk + j2;
+                const int ot = first ? -(1 - kk + j2) : 1 - kk + j2;
+                int qt = i[tax] + ot;
+                qt += (qt < 0) ? N : 0; qt -= (qt >= N) ? N : 0;
+                const int pt = tax == 0 ? qt * (N * N) : (tax == 1 ? __ldg(ctab + N + qt) : __ldg(ctab + N + qt) * N);
+                // the third axis keeps the point's own index
+                const int rest = 3 - cax - tax;
+                const int po = rest == 0 ? i[0] * (N * N) : (rest == 1 ? __ldg(ctab + N + i[1]) : __ldg(ctab + N + i[2]) * N);
+                const int qs = pc + pt + po;
                 const double w = op.sten.w[j1] * op.sten.w[j2] * 0.5;
-                int q[3] = {i[0], i[1], i[2]};
-                q[cax] = pcb_wrap(i[cax] + (first ? oc : -oc), N);
-                q[tax] = pcb_wrap(i[tax] + (first ? -ot : ot), N);
-                const long long qs = ((long long)q[0] * N + __ldg(ctab + N + q[2])) * N + __ldg(ctab + N + q[1]);
                 const double Io = (double)((__ldg(maskp + qs) >> other) & 1u);
                 sacc = cadd(sacc, cscale(Xo[qs], w * (Ic + Io)));
             }
@@ -848,7 +857,7 @@ __global__ void __launch_bounds__(P::N / 8 * 32, 1) k_mid(PcbOp op, PcbCols cols
                     cplx v = cscale(myrows[rl * LD + cl], ((mk >> c) & 1u) ? op.ediag[c] : 1.0);
                     if ((mk >> (4 + c)) & 1u) {
                         const int ii[3] = {i0, __ldg(ctab + cl), __ldg(ctab + 8 * warp + rl)};
-                        v = cadd(v, pcb_crossdof_couple<(STEN - 1) / 2>(op, c, ii, mk, Xcol));
+                        v = cadd(v, pcb_crossdof_couple<N, (STEN - 1) / 2>(op, c, ii, mk, Xcol));
                     }
                     myrows[rl * LD + cl] = v;
                 }
