@@ -24,9 +24,18 @@ constexpr int kStageX = LX * kRowBytes;               // one x-tile (three compo
 constexpr int NTX = (LX * P::R2 <= 64) ? 64 : NT;
 constexpr int kSmemL = 3 * P::N * 8 * (int)sizeof(cplx);
 constexpr int kSmemZ = 2 * kSmemL;                       // two stages
-constexpr int NSTZ = (2 * (kSmemZ + 1024) <= 224 * 1024) ? 2 : 1;         // ... else single-stage tiles, still several CTAs per SM
+// ... else (N >= 160) single-stage tiles with 2-3 CTAs of 256 threads per SM.  (Round 2, measured: when two stages still fit ONCE,
+// one CTA of 512 threads per SM with the cp.async double buffer -- the same 16 warps and pipeline depth per SM as the small
+// sizes, no spills -- is slower: N = 160, 16 columns 2.09 vs 1.79 ms, N = 256, 8 columns 4.08 vs 3.31 ms; build with
+// -DPCB_ZMID_WIDE=1 to get that form.)
+#ifndef PCB_ZMID_WIDE
+#define PCB_ZMID_WIDE 0
+#endif
+constexpr bool kZTwice = 2 * (kSmemZ + 1024) <= 224 * 1024;
+constexpr bool kZWide = !kZTwice && PCB_ZMID_WIDE && (kSmemZ + 1024 <= 227 * 1024);
+constexpr int NSTZ = (kZTwice || kZWide) ? 2 : 1;         // ... else single-stage tiles, still several CTAs per SM
 constexpr int kSmemZU = NSTZ * kSmemL;
-constexpr int NTZ = NTP;
+constexpr int NTZ = kZWide ? 512 : NTP;
 
 template <class K>
 int set_smem(K kern, int bytes) {
@@ -248,7 +257,7 @@ int run_pass(const PcbOp& op, const PcbCols& cols, int ncols, int pass_id, const
         case PCB_PASS_ZMID:
             if (op.diel == PCB_DIEL_NONE) PCB_GO_P((k_zmid<P, 0, NTZ, NSTZ>), NTZ, GL, kSmemZU, 3);
             else if (op.diel == PCB_DIEL_CHIRAL) PCB_GO_P((k_zmid<P, 1, NTZ, NSTZ>), NTZ, GL, kSmemZU, 3);
-            else if (op.diel == PCB_DIEL_TRIVIAL) PCB_GO_P((k_zmid<P, 2, NTP, NSTZ>), NTP, GL, kSmemZU, 2);   // v[3][R2] per thread: keep 256 threads
+            else if (op.diel == PCB_DIEL_TRIVIAL) PCB_GO_P((k_zmid<P, 2, NTZ, NSTZ>), NTZ, GL, kSmemZU, 2);
             else { pcb_set_error("zmid: dielectric type %d has no fused z pass", op.diel); return -1; }
             break;
         case PCB_PASS_XFWD_SYM_T: case PCB_PASS_MID: case PCB_PASS_XINV_A_T: case PCB_PASS_XINV_H_T: case PCB_PASS_MASKBITS:
