@@ -85,7 +85,11 @@ class Operator:
         if not y2.flags.c_contiguous or y2.dtype != np.complex128:
             raise ValueError("out must be a C-contiguous complex128 array")
         # H2D / compute / D2H pipeline over column chunks inside the C ABI
-        L.check(self._lib.pcb_apply_host(self.h, mode, k, x.ctypes.data, k, y2.ctypes.data, k), "pcb_apply_host")
+        rc = self._lib.pcb_apply_host(self.h, mode, k, x.ctypes.data, k, y2.ctypes.data, k)
+        if rc != 0 and b"memory" in self._lib.pcb_last_error().lower() and self.ctx.trim():
+            # the staging of the pipeline is a plain cudaMalloc: give the context's cached blocks back and try once more
+            rc = self._lib.pcb_apply_host(self.h, mode, k, x.ctypes.data, k, y2.ctypes.data, k)
+        L.check(rc, "pcb_apply_host")
         return y.reshape(-1) if (vec and out is None) else y
 
     def residual(self, x, hx, w, lambdas, precond=True, single=False):
