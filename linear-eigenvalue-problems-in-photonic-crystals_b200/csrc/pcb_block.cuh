@@ -683,15 +683,8 @@ __global__ void __launch_bounds__(256) k_diel_point(PcbOp op, const cplx* __rest
         cplx u[3] = {X[p], X[nn + p], X[2 * nn + p]};
         unsigned m = op.diel ? op.mask[p] : 0u;
         if (op.diel == PCB_DIEL_CHIRAL) m &= 7u;
-        // (inline copy of pcb_diel_point to keep this header independent of pcb_operator.cuh)
-        const double d0 = (m & 1u) ? op.ediag[0] : 1.0, d1 = (m & 2u) ? op.ediag[1] : 1.0, d2 = (m & 4u) ? op.ediag[2] : 1.0;
-        cplx y0 = cscale(u[0], d0), y1 = cscale(u[1], d1), y2 = cscale(u[2], d2);
-        if (m & 8u) {
-            y0 = cfma(op.eoff[0], u[1], cfma(op.eoff[1], u[2], y0));
-            y1 = cfmac(op.eoff[0], u[0], cfma(op.eoff[2], u[2], y1));
-            y2 = cfmac(op.eoff[1], u[0], cfmac(op.eoff[2], u[1], y2));
-        }
-        Y[p] = y0; Y[nn + p] = y1; Y[2 * nn + p] = y2;
+        pcb_diel_point(op, m, u);
+        Y[p] = u[0]; Y[nn + p] = u[1]; Y[2 * nn + p] = u[2];
     }
 }
 

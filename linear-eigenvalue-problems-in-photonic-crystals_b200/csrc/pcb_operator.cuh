@@ -116,6 +116,9 @@ PCB_D void pcb_bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, unsig
 PCB_D void pcb_bulk_store(void* gdst, const void* smem_src, unsigned bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(pcb_smem_u32(smem_src)), "r"(bytes) : "memory");
 }
+PCB_D void pcb_bulk_prefetch_l2(const void* gsrc, unsigned bytes) {      // TMA prefetch of a contiguous chunk into L2 (no shared-memory destination)
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(gsrc), "r"(bytes) : "memory");
+}
 PCB_D void pcb_bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
 PCB_D void pcb_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
 PCB_D void pcb_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
@@ -1107,7 +1110,7 @@ __global__ void k_mask_bits2(PcbOp op, unsigned* __restrict__ out) {
     out[t] = w;
 }
 
-template <class P, int DIEL, int TMA = 0>
+template <class P, int DIEL, int TMA = 0, int PF = 0>
 __global__ void __launch_bounds__(Mid2<P>::NTHR, 1) k_mid2(PcbOp op, PcbCols cols, const cplx* __restrict__ tw, int ncols) {
     typedef Mid2<P> M2;
     constexpr int N = P::N, R2 = P::R2, LD = N + 1, NTHR = M2::NTHR, CI = M2::CI;
@@ -1143,6 +1146,16 @@ __global__ void __launch_bounds__(Mid2<P>::NTHR, 1) k_mid2(PcbOp op, PcbCols col
                 for (int r = 0; r < nrw; ++r) {
                     const int row = M2::rho(r & 7, 2 * warp + (r >> 3));
                     pcb_bulk_load(pl + row * LD, base + (long long)row * N, N * (unsigned)sizeof(cplx), mybar);
+                }
+                if (PF) {      // the rows this warp will load for the CTA's next plane: ask L2 for them now (one TMA prefetch per row)
+                    const int np = pid + gridDim.x;
+                    if (np < 3 * N * ncols) {
+                        const cplx* nb = cols.wrk[np / (3 * N)] + ((np / N) % 3) * nn + (long long)(np % N) * N * N;
+                        for (int r = 0; r < nrw; ++r) {
+                            const int row = M2::rho(r & 7, 2 * warp + (r >> 3));
+                            pcb_bulk_prefetch_l2(nb + (long long)row * N, N * (unsigned)sizeof(cplx));
+                        }
+                    }
                 }
             }
         } else

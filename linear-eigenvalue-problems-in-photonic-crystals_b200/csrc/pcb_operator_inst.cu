@@ -114,6 +114,12 @@ struct PlaneFive<true, PP> {
         constexpr int smem_tma = PP::N * (PP::N + 1) * (int)sizeof(cplx) + 128;
 #ifndef PCB_EMU
         if (smem_tma <= 232448) {
+            static const char* evpf = getenv("PCB200_MID_PF");      // PCB200_MID_PF=1: TMA prefetch of the CTA's next plane into L2
+            if (evpf && evpf[0] == '1') {
+                if (op.diel == PCB_DIEL_NONE) PCB_GO_P((k_mid2<PP, 0, 1, 1>), M2::NTHR, 3 * PP::N, smem_tma, 1);
+                else PCB_GO_P((k_mid2<PP, 1, 1, 1>), M2::NTHR, 3 * PP::N, smem_tma, 1);
+                return 0;
+            }
             if (op.diel == PCB_DIEL_NONE) PCB_GO_P((k_mid2<PP, 0, 1>), M2::NTHR, 3 * PP::N, smem_tma, 1);
             else PCB_GO_P((k_mid2<PP, 1, 1>), M2::NTHR, 3 * PP::N, smem_tma, 1);
             return 0;

@@ -9,9 +9,10 @@ reference`` legs may import it.
 
 Pinning: every function below is checked against the UNMODIFIED reference
 modules, executed in this container through ``oracle/refshim`` (NumPy-backed
-``cupy``), by ``oracle/make_golden.py`` (which also writes ``tests/golden/``)
-and by ``tests/test_oracle_vs_reference.py`` (skipped where ``/root/reference``
-is absent).  The third-party arithmetic (FFT, GEMM, Cholesky, eigh) is CuPy ->
+``cupy``), by ``oracle/make_golden.py``, ``oracle/make_golden_mixed.py`` and
+``oracle/make_golden_c1.py`` (which assert the agreement and write the fixtures
+of ``tests/golden/``); ``tests/test_operator.py`` / ``tests/test_lobpcg.py`` then
+hold the oracle and the CUDA path against those fixtures on every run.  The third-party arithmetic (FFT, GEMM, Cholesky, eigh) is CuPy ->
 cuFFT/cuBLAS/cuSOLVER in the reference (no pinned version) and
 pocketfft/OpenBLAS/LAPACK here: standard DFT/GEMM/zheevd semantics.
 
