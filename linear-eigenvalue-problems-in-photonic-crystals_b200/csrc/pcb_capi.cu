@@ -108,6 +108,7 @@ struct pcb_diel {
     unsigned char* mask;    // [nn] (padded to 4)
     unsigned* mbits;        // plane mode: per-item dielectric bit words (k_mask_bits); null when the size has no plane pass
     unsigned* mbits2;       // five-sweep plane pass: bit words in its item order (k_mask_bits2); else null
+    unsigned char* maskp2;  // five-sweep plane pass, coupled dielectric: byte mask in its slot order (k_mask_plane2); else null
     unsigned char* maskp;   // plane mode, coupled dielectric: byte mask in plane-slot order (k_mask_plane); else null
     double ediag[3];
     cplx eoff[3];
@@ -415,7 +416,7 @@ int pcb_diel_create(pcb_ctx* c, int kind, const int64_t* ind_e, long long n_e, c
     PCB_CHECK_ARG(out && kind >= PCB_DIEL_NONE && kind <= PCB_DIEL_CROSSDOF, "bad kind");
     PCB_CUDA_OK(cudaSetDevice(c->device));
     pcb_diel* d = new pcb_diel;
-    d->ctx = c; d->kind = kind; d->mask = nullptr; d->mbits = nullptr; d->mbits2 = nullptr; d->maskp = nullptr;
+    d->ctx = c; d->kind = kind; d->mask = nullptr; d->mbits = nullptr; d->mbits2 = nullptr; d->maskp = nullptr; d->maskp2 = nullptr;
     for (int i = 0; i < 3; ++i) { d->ediag[i] = ediag ? ediag[i] : 1.0; d->eoff[i] = eoff ? cmake(eoff[2 * i], eoff[2 * i + 1]) : cmake(0.0, 0.0); }
     d->st.k = 1; for (int i = 0; i < 8; ++i) d->st.w[i] = 0.0;
     if (kind == PCB_DIEL_CROSSDOF) {
@@ -452,7 +453,13 @@ int pcb_diel_create(pcb_ctx* c, int kind, const int64_t* ind_e, long long n_e, c
         memset(&none, 0, sizeof none);
         if (c->plan->pass(tmp, none, 1, PCB_PASS_MASKBITS, c->tw, c->stream, c->sms)) { pcb_diel_destroy(d); return -1; }
         c->launches++;
-        if (c->plan->plane_five && kind == PCB_DIEL_CHIRAL) {
+        if (c->plan->plane_five && c->plan->plane_coupled && kind == PCB_DIEL_TRIVIAL) {
+            PCB_CUDA_OK_OR(cudaMalloc(&d->maskp2, (size_t)c->nn), pcb_diel_destroy(d));
+            tmp.maskp2 = d->maskp2;
+            if (c->plan->pass(tmp, none, 1, PCB_PASS_MASKPLANE2, c->tw, c->stream, c->sms)) { pcb_diel_destroy(d); return -1; }
+            c->launches++;
+        }
+        if (c->plan->plane_five && (kind == PCB_DIEL_CHIRAL || (kind == PCB_DIEL_TRIVIAL && c->plan->plane_coupled))) {
             PCB_CUDA_OK_OR(cudaMalloc(&d->mbits2, sizeof(unsigned) * 3 * (size_t)c->N * c->N * 8), pcb_diel_destroy(d));
             tmp.mbits2 = d->mbits2;
             if (c->plan->pass(tmp, none, 1, PCB_PASS_MASKBITS2, c->tw, c->stream, c->sms)) { pcb_diel_destroy(d); return -1; }
@@ -490,6 +497,7 @@ void pcb_diel_destroy(pcb_diel* d) {
     if (d->mbits) cudaFree(d->mbits);
     if (d->maskp) cudaFree(d->maskp);
     if (d->mbits2) cudaFree(d->mbits2);
+    if (d->maskp2) cudaFree(d->maskp2);
     delete d;
 }
 
@@ -505,6 +513,7 @@ static void op_fill(pcb_op* o, double gamma, double shift, double pshift, pcb_di
     o->d.mbits = diel ? diel->mbits : nullptr;
     o->d.maskp = diel ? diel->maskp : nullptr;
     o->d.mbits2 = diel ? diel->mbits2 : nullptr;
+    o->d.maskp2 = diel ? diel->maskp2 : nullptr;
     if (diel) o->d.sten = diel->st; else { o->d.sten.k = 1; for (int i = 0; i < 8; ++i) o->d.sten.w[i] = 0.0; }
     o->d.ctab = c->ctab;
     o->d.dist = nullptr;

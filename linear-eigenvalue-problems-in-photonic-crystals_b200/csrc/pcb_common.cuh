@@ -129,6 +129,7 @@ struct PcbOp {
     const unsigned char* mask;  // [nn] bit c: edge DoF of component c in Omega_1; bit 3: volume DoF
     const unsigned* mbits;      // plane mode: [c][i0][slot][k1] words, bit k2 = component c of (i0, i1 = coord(slot), i2 = lout(k1,k2)) in Omega_1
     const unsigned* mbits2;     // five-sweep plane pass (k_mid2): [c][i0][d][col] words, bit k2 (k_mask_bits2)
+    const unsigned char* maskp2; // the same byte mask in the slot order of the five-sweep plane pass (k_mask_plane2), coupled dielectric
     const unsigned char* maskp; // plane mode, coupled dielectric: the byte mask in plane-slot order, [i0][row][col] = mask(i0, coord(col), coord(row))
     PcbStencil sten;            // cross-DoF dielectric: its averaging stencil (the fused stencil-on-load of the plane pass)
     int mid_five;               // plane mode: 1 = the five-sweep plane pass (k_mid2), 0 = the seven-sweep one (k_mid)

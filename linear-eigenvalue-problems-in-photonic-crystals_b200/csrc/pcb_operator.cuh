@@ -1090,7 +1090,23 @@ struct Mid2 {
     PCB_HD static int rho(int n1, int n2) { const int s = R2 * n1 + 8 * n2; return s >= N ? s - N : s; }   // z slot (row) of digits (n1, n2)
     PCB_HD static int k1z(int d) { return (d >> 1) + 4 * (d & 1); }                                       // z digit held by slot digit d = 2k' + k''
     PCB_HD static int coordy(int col) { return col / R2 + 8 * (col % R2); }                                // y index held by column col after the forward steps
+    // z index held by row `row` after the forward steps: row = rho(d, k2) -> d = row R2^-1 mod 8, k2 = row 8^-1 mod R2
+    PCB_HD static int coordz(int row) {
+        const int d = ((row % 8) * P::U) % 8, k2 = ((row % R2) * P::V) % R2;
+        return P::wrap(P::lout1(k1z(d)) + P::lout2(k2));
+    }
 };
+
+// the byte mask in the slot order of k_mid2 (coupled dielectric on clusters): maskp2[i0][row][col] = mask(i0, coordy(col), coordz(row))
+template <class P>
+__global__ void k_mask_plane2(PcbOp op, unsigned char* __restrict__ out) {
+    typedef Mid2<P> M2;
+    constexpr int N = P::N;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)N * N * N) return;
+    const int col = (int)(t % N), row = (int)((t / N) % N), i0 = (int)(t / ((long long)N * N));
+    out[t] = op.mask[((long long)M2::coordz(row) * N + M2::coordy(col)) * N + i0];
+}
 
 // mbits2[c][i0][d][col], bit k2 = "component c of grid point (i0, i1 = coordy(col), i2 = lout(k1z(d), k2)) lies in Omega_1"
 template <class P>
@@ -1110,11 +1126,19 @@ __global__ void k_mask_bits2(PcbOp op, unsigned* __restrict__ out) {
     out[t] = w;
 }
 
+// DIEL = 2: the coupled 3x3 dielectric on clusters of three CTAs, exactly as in k_mid<2>: sweep C is split at real space --
+// forward radix-R2 + diagonal -> plane, cluster barrier, off-diagonal terms at the coupled points of this CTA's third of the rows
+// through distributed shared memory (byte mask in this kernel's slot order, op.maskp2), cluster barrier, inverse radix-R2.
 template <class P, int DIEL, int TMA = 0, int PF = 0>
 __global__ void __launch_bounds__(Mid2<P>::NTHR, 1) k_mid2(PcbOp op, PcbCols cols, const cplx* __restrict__ tw, int ncols) {
     typedef Mid2<P> M2;
     constexpr int N = P::N, R2 = P::R2, LD = N + 1, NTHR = M2::NTHR, CI = M2::CI;
     static_assert(M2::OK, "k_mid2 needs N = 8 * R2 with odd R2 <= 15");
+    int first = blockIdx.x, stride = gridDim.x, total = 3 * N * ncols, crank = 0;
+#ifndef PCB_EMU
+    unsigned pbase[3] = {0u, 0u, 0u};
+    double inv_d[3] = {1.0, 1.0, 1.0};
+#endif
     PCB_DYN_SMEM(cplx, pl);   // [N rows][LD] (+ one mbarrier per warp behind it when TMA)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int h = tid >> 4, l = tid & 15;             // half-warp = z digit n2, lane within it
@@ -1133,9 +1157,16 @@ __global__ void __launch_bounds__(Mid2<P>::NTHR, 1) k_mid2(PcbOp op, PcbCols col
     int rr[8];                // rows of this half-warp: rr[n1] = rho(n1, h) * LD
     PCB_UNROLL
     for (int n1 = 0; n1 < 8; ++n1) rr[n1] = M2::rho(n1, hact ? h : 0) * LD;
+#ifndef PCB_EMU
+    if (DIEL == 2) {
+        crank = (int)pcb_cluster_ctarank(); first = (int)pcb_cluster_id(); stride = (int)pcb_cluster_count(); total = N * ncols;
+        PCB_UNROLL
+        for (int r = 0; r < 3; ++r) { pbase[r] = pcb_mapa(pcb_smem_u32(pl), (unsigned)r); inv_d[r] = 1.0 / op.ediag[r]; }
+    }
+#endif
 
-    for (int pid = blockIdx.x; pid < 3 * N * ncols; pid += gridDim.x) {
-        const int col = pid / (3 * N), c = (pid / N) % 3, i0 = pid % N;
+    for (int pid = first; pid < total; pid += stride) {
+        const int col = (DIEL == 2) ? pid / N : pid / (3 * N), c = (DIEL == 2) ? crank : (pid / N) % 3, i0 = pid % N;
         cplx* __restrict__ base = cols.wrk[col] + c * nn + (long long)i0 * N * N;
         // ---- load the warp's rows ----
 #ifndef PCB_EMU
@@ -1147,7 +1178,7 @@ __global__ void __launch_bounds__(Mid2<P>::NTHR, 1) k_mid2(PcbOp op, PcbCols col
                     const int row = M2::rho(r & 7, 2 * warp + (r >> 3));
                     pcb_bulk_load(pl + row * LD, base + (long long)row * N, N * (unsigned)sizeof(cplx), mybar);
                 }
-                if (PF) {      // the rows this warp will load for the CTA's next plane: ask L2 for them now (one TMA prefetch per row)
+                if (PF && DIEL != 2) {      // the rows this warp will load for the CTA's next plane: ask L2 for them now (one TMA prefetch per row)
                     const int np = pid + gridDim.x;
                     if (np < 3 * N * ncols) {
                         const cplx* nb = cols.wrk[np / (3 * N)] + ((np / N) % 3) * nn + (long long)(np % N) * N * N;
@@ -1168,11 +1199,27 @@ __global__ void __launch_bounds__(Mid2<P>::NTHR, 1) k_mid2(PcbOp op, PcbCols col
             pcb_cp_commit();
         }
         unsigned mb[CI];
-        if (DIEL == 1) {
+        if (DIEL >= 1) {
             PCB_UNROLL
             for (int q = 0; q < CI; ++q) {
                 const int it = tid + NTHR * q;
                 mb[q] = (it < 8 * N) ? __ldg(op.mbits2 + ((long long)c * N + i0) * (8 * N) + it) : 0u;
+            }
+        }
+        // coupled dielectric: mask bytes of this thread's points of step (B) (point e = tid + q NTHR of the CTA's third of the rows)
+        constexpr int PBQ = (DIEL == 2) ? ((N + 2) / 3 * N + NTHR - 1) / NTHR : 1;
+        unsigned pmask[(PBQ + 3) / 4];
+        int prow0 = 0;
+        if (DIEL == 2) {
+            prow0 = (crank * N) / 3;
+            const int pcnt = (((crank + 1) * N) / 3 - prow0) * N;
+            const unsigned char* __restrict__ mp = op.maskp2 + (long long)i0 * N * N + prow0 * N;
+            PCB_UNROLL
+            for (int w = 0; w < (PBQ + 3) / 4; ++w) pmask[w] = 0u;
+            PCB_UNROLL
+            for (int q = 0; q < PBQ; ++q) {
+                const int e = tid + q * NTHR;
+                if (e < pcnt) pmask[q / 4] |= (unsigned)__ldg(mp + e) << (8 * (q % 4));
             }
         }
 #ifndef PCB_EMU
@@ -1230,48 +1277,101 @@ __global__ void __launch_bounds__(Mid2<P>::NTHR, 1) k_mid2(PcbOp op, PcbCols col
             }
         }
         __syncthreads();
-        // ---- C: z radix-R2 over the rows rho(d, n2), M, inverse; lanes = consecutive columns; two items per trip (both items'
-        //      loads are issued before either transform: the plane carries no restrict information, so item by item every
-        //      load would wait behind the previous item's stores) ----
-        PCB_UNROLL
-        for (int q = 0; q < CI; q += 2) {
-            const int ita = tid + NTHR * q, itb = ita + NTHR;
-            if (ita >= 8 * N) break;
-            const bool hasb = (q + 1 < CI) && itb < 8 * N;
-            const int da = ita / N, db = hasb ? itb / N : 0;
-            cplx* __restrict__ ca = pl + ita % N;
-            cplx* __restrict__ cb = pl + (hasb ? itb % N : 0);
-            cplx va[R2], vb[R2];
+        if (DIEL == 2) {
+#ifndef PCB_EMU
+            // ---- C1: z radix-R2 forward (-> real space) and the diagonal of M ----
             PCB_UNROLL
-            for (int n2 = 0; n2 < R2; ++n2) va[n2] = ca[M2::rho(da, n2) * LD];
-            if (hasb) {
+            for (int q = 0; q < CI; ++q) {
+                const int it = tid + NTHR * q;
+                if (it >= 8 * N) break;
+                const int d = it / N;
+                cplx* __restrict__ cp = pl + it % N;
+                cplx v[R2];
                 PCB_UNROLL
-                for (int n2 = 0; n2 < R2; ++n2) vb[n2] = cb[M2::rho(db, n2) * LD];
-            }
-            Dft<R2, -1>::run(va);
-            if (DIEL == 1) {
+                for (int n2 = 0; n2 < R2; ++n2) v[n2] = cp[M2::rho(d, n2) * LD];
+                Dft<R2, -1>::run(v);
                 const double scl = op.ediag[c];
                 const unsigned w = mb[q];
                 PCB_UNROLL
-                for (int k2 = 0; k2 < R2; ++k2) va[k2] = cscale(va[k2], ((w >> k2) & 1u) ? scl : 1.0);
+                for (int k2 = 0; k2 < R2; ++k2) cp[M2::rho(d, k2) * LD] = cscale(v[k2], ((w >> k2) & 1u) ? scl : 1.0);
             }
-            Dft<R2, +1>::run(va);
+            // ---- (B): off-diagonal terms at the coupled points of this CTA's third of the rows, through distributed shared memory ----
+            pcb_cluster_sync();
             PCB_UNROLL
-            for (int n2 = 0; n2 < R2; ++n2) ca[M2::rho(da, n2) * LD] = va[n2];
-            if (hasb) {
-                Dft<R2, -1>::run(vb);
+            for (int q = 0; q < PBQ; ++q) {
+                const int e = tid + q * NTHR;
+                const unsigned mk = (pmask[q / 4] >> (8 * (q % 4))) & 0xffu;      // 0 beyond the CTA's share
+                if (mk & 8u) {
+                    const unsigned off = (unsigned)(((prow0 + e / N) * LD + e % N) * (int)sizeof(cplx));
+                    const cplx u0 = pcb_ld_cluster(pbase[0] + off), u1 = pcb_ld_cluster(pbase[1] + off), u2 = pcb_ld_cluster(pbase[2] + off);
+                    const cplx v0 = cscale(u0, (mk & 1u) ? inv_d[0] : 1.0), v1 = cscale(u1, (mk & 2u) ? inv_d[1] : 1.0),
+                               v2 = cscale(u2, (mk & 4u) ? inv_d[2] : 1.0);
+                    pcb_st_cluster(pbase[0] + off, cfma(op.eoff[0], v1, cfma(op.eoff[1], v2, u0)));
+                    pcb_st_cluster(pbase[1] + off, cfmac(op.eoff[0], v0, cfma(op.eoff[2], v2, u1)));
+                    pcb_st_cluster(pbase[2] + off, cfmac(op.eoff[1], v0, cfmac(op.eoff[2], v1, u2)));
+                }
+            }
+            pcb_cluster_sync();
+            // ---- C2: z radix-R2 inverse ----
+            PCB_UNROLL
+            for (int q = 0; q < CI; ++q) {
+                const int it = tid + NTHR * q;
+                if (it >= 8 * N) break;
+                const int d = it / N;
+                cplx* __restrict__ cp = pl + it % N;
+                cplx v[R2];
+                PCB_UNROLL
+                for (int k2 = 0; k2 < R2; ++k2) v[k2] = cp[M2::rho(d, k2) * LD];
+                Dft<R2, +1>::run(v);
+                PCB_UNROLL
+                for (int n2 = 0; n2 < R2; ++n2) cp[M2::rho(d, n2) * LD] = v[n2];
+            }
+            __syncthreads();
+#endif
+        } else {
+            // ---- C: z radix-R2 over the rows rho(d, n2), M, inverse; lanes = consecutive columns; two items per trip (both items'
+            //      loads are issued before either transform: the plane carries no restrict information, so item by item every
+            //      load would wait behind the previous item's stores) ----
+            PCB_UNROLL
+            for (int q = 0; q < CI; q += 2) {
+                const int ita = tid + NTHR * q, itb = ita + NTHR;
+                if (ita >= 8 * N) break;
+                const bool hasb = (q + 1 < CI) && itb < 8 * N;
+                const int da = ita / N, db = hasb ? itb / N : 0;
+                cplx* __restrict__ ca = pl + ita % N;
+                cplx* __restrict__ cb = pl + (hasb ? itb % N : 0);
+                cplx va[R2], vb[R2];
+                PCB_UNROLL
+                for (int n2 = 0; n2 < R2; ++n2) va[n2] = ca[M2::rho(da, n2) * LD];
+                if (hasb) {
+                    PCB_UNROLL
+                    for (int n2 = 0; n2 < R2; ++n2) vb[n2] = cb[M2::rho(db, n2) * LD];
+                }
+                Dft<R2, -1>::run(va);
                 if (DIEL == 1) {
                     const double scl = op.ediag[c];
-                    const unsigned w = mb[(q + 1 < CI) ? q + 1 : q];
+                    const unsigned w = mb[q];
                     PCB_UNROLL
-                    for (int k2 = 0; k2 < R2; ++k2) vb[k2] = cscale(vb[k2], ((w >> k2) & 1u) ? scl : 1.0);
+                    for (int k2 = 0; k2 < R2; ++k2) va[k2] = cscale(va[k2], ((w >> k2) & 1u) ? scl : 1.0);
                 }
-                Dft<R2, +1>::run(vb);
+                Dft<R2, +1>::run(va);
                 PCB_UNROLL
-                for (int n2 = 0; n2 < R2; ++n2) cb[M2::rho(db, n2) * LD] = vb[n2];
+                for (int n2 = 0; n2 < R2; ++n2) ca[M2::rho(da, n2) * LD] = va[n2];
+                if (hasb) {
+                    Dft<R2, -1>::run(vb);
+                    if (DIEL == 1) {
+                        const double scl = op.ediag[c];
+                        const unsigned w = mb[(q + 1 < CI) ? q + 1 : q];
+                        PCB_UNROLL
+                        for (int k2 = 0; k2 < R2; ++k2) vb[k2] = cscale(vb[k2], ((w >> k2) & 1u) ? scl : 1.0);
+                    }
+                    Dft<R2, +1>::run(vb);
+                    PCB_UNROLL
+                    for (int n2 = 0; n2 < R2; ++n2) cb[M2::rho(db, n2) * LD] = vb[n2];
+                }
             }
+            __syncthreads();
         }
-        __syncthreads();
         // ---- B': inverse z radix-2 x inverse y radix-R2 ----
         if (hact) {
             PCB_UNROLL
@@ -1397,6 +1497,6 @@ enum { PCB_PASS_XFWD_SYM = 0, PCB_PASS_XFWD = 1, PCB_PASS_YFWD = 2, PCB_PASS_ZFW
        PCB_PASS_XFWD_SYM_TD = 23, PCB_PASS_XINV_A_TD = 24, PCB_PASS_XINV_H_TD = 25,
        // cross-DoF dielectric with the stencil fused into the inverse half of the plane pass (four kernels)
        PCB_PASS_MID_FWD_O = 26 /* forward half, planes -> cols.out */, PCB_PASS_MID_INV_ST = 27 /* stencil on load + inverse half, cols.out -> cols.wrk */,
-       PCB_PASS_MASKACTIVE = 28 /* set-up: bits 4-6 of op.maskp */ };
+       PCB_PASS_MASKACTIVE = 28 /* set-up: bits 4-6 of op.maskp */, PCB_PASS_MASKPLANE2 = 29 /* set-up: op.mask -> (unsigned char*)op.maskp2 */ };
 
 const PcbOpLaunch* pcb_find_plan(int N);

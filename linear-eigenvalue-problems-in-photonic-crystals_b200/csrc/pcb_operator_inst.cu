@@ -93,6 +93,37 @@ constexpr int kStageXT = 3 * LX * (P::R1 * P::R2P + 1) * (int)sizeof(cplx);
 constexpr int GX = (P::N * P::N + LX - 1) / LX;          // x tiles per column
 constexpr int GL = ((P::N + 7) / 8) * P::N;              // strided-line tiles per column
 
+#ifndef PCB_EMU
+// persistent launch on clusters of three CTAs (one per component): as many clusters as can be co-resident
+template <class K>
+int launch_cluster3(K kfn, int threads, int smem, int planes, const PcbOp& op, const PcbCols& cols, const cplx* tw, int ncols, cudaStream_t s, int sms, int N) {
+    if (set_smem(kfn, smem)) return -1;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = 3; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+    cfg.blockDim = dim3((unsigned)threads, 1, 1);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = s;
+    cfg.attrs = &at; cfg.numAttrs = 1;
+    static int max_clusters = 0;      // per kernel instantiation: co-resident clusters (a 3-CTA cluster needs three free SMs of one GPC)
+    if (max_clusters == 0) {
+        cfg.gridDim = dim3(3 * 148, 1, 1);
+        PCB_CUDA_OK(cudaOccupancyMaxActiveClusters(&max_clusters, kfn, &cfg));
+        if (const char* ev = getenv("PCB200_MID_CLUSTERS")) { const int v = atoi(ev); if (v >= 1 && v < max_clusters) max_clusters = v; }
+        if (getenv("PCB200_DEBUG")) fprintf(stderr, "[pcb200] plane pass, coupled M, N = %d, %d threads: %d co-resident clusters of 3 CTAs (%d SMs)\n", N, threads, max_clusters, sms);
+        if (max_clusters < 1) { pcb_set_error("plane mode: no 3-CTA cluster of the plane pass fits on this device"); max_clusters = 0; return -1; }
+    }
+    long long ncl = max_clusters;
+    if (ncl > planes) ncl = planes;
+    cfg.gridDim = dim3((unsigned)(3 * ncl), 1, 1);
+    PCB_CUDA_OK(cudaLaunchKernelEx(&cfg, kfn, op, cols, tw, ncols));
+    PCB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+#endif
+
 // five-sweep plane pass (k_mid2): instantiated only for the plans it supports
 template <bool ENABLED, class PP>
 struct PlaneFive {
@@ -112,7 +143,17 @@ struct PlaneFive<true, PP> {
             return 0;
         }
         constexpr int smem_tma = PP::N * (PP::N + 1) * (int)sizeof(cplx) + 128;
+        if (pass_id == PCB_PASS_MASKPLANE2) {
+            const long long total = (long long)PP::N * PP::N * PP::N;
+            PCB_LAUNCH((k_mask_plane2<PP>), dim3((unsigned)((total + 255) / 256), 1, 1), dim3(256, 1, 1), 0, s, op, const_cast<unsigned char*>(op.maskp2));
+            PCB_CUDA_OK(cudaGetLastError());
+            return 0;
+        }
 #ifndef PCB_EMU
+        if (op.diel == PCB_DIEL_TRIVIAL) {
+            if (smem_tma > 232448 || PP::N % 3 != 0) { pcb_set_error("five-sweep plane pass: coupled M not available for N = %d", PP::N); return -1; }
+            return launch_cluster3(k_mid2<PP, 2, 1>, M2::NTHR, smem_tma, PP::N * ncols, op, cols, tw, ncols, s, sms, PP::N);
+        }
         if (smem_tma <= 232448) {
             static const char* evpf = getenv("PCB200_MID_PF");      // PCB200_MID_PF=1: TMA prefetch of the CTA's next plane into L2
             if (evpf && evpf[0] == '1') {
@@ -193,33 +234,9 @@ struct PlanePass<true, PP> {
         if (pass_id == PCB_PASS_MID && op.diel == PCB_DIEL_TRIVIAL) {
             // coupled 3x3 M: clusters of three CTAs (one component each) exchanging the coupled points through DSMEM
             static_assert(!kPlaneCoupled || kTma, "the cluster form of the plane pass uses the TMA row copies");
-            auto kfn = k_mid<PP, 2, 1>;
-            const int smem = kSmemMid + 128;
-            if (set_smem(kfn, smem)) return -1;
-            cudaLaunchConfig_t cfg;
-            memset(&cfg, 0, sizeof cfg);
-            cudaLaunchAttribute at;
-            at.id = cudaLaunchAttributeClusterDimension;
-            at.val.clusterDim.x = 3; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
-            cfg.blockDim = dim3(PP::N / 8 * 32, 1, 1);
-            cfg.dynamicSmemBytes = (size_t)smem;
-            cfg.stream = s;
-            cfg.attrs = &at; cfg.numAttrs = 1;
-            static int max_clusters = 0;      // co-resident clusters of this kernel (one 3-CTA cluster needs three free SMs of one GPC)
-            if (max_clusters == 0) {
-                cfg.gridDim = dim3(3 * 148, 1, 1);
-                PCB_CUDA_OK(cudaOccupancyMaxActiveClusters(&max_clusters, kfn, &cfg));
-                if (const char* ev = getenv("PCB200_MID_CLUSTERS")) { const int v = atoi(ev); if (v >= 1 && v < max_clusters) max_clusters = v; }
-                if (getenv("PCB200_DEBUG")) fprintf(stderr, "[pcb200] k_mid<%d, coupled>: %d co-resident clusters of 3 CTAs (%d SMs)\n", PP::N, max_clusters, sms);
-                if (max_clusters < 1) { pcb_set_error("plane mode: no 3-CTA cluster of k_mid fits on this device"); max_clusters = 0; return -1; }
-            }
-            long long ncl = max_clusters;
-            const long long tot = (long long)PP::N * ncols;
-            if (ncl > tot) ncl = tot;
-            cfg.gridDim = dim3((unsigned)(3 * ncl), 1, 1);
-            PCB_CUDA_OK(cudaLaunchKernelEx(&cfg, kfn, op, cols, tw, ncols));
-            PCB_CUDA_OK(cudaGetLastError());
-            return 0;
+            if (kPlaneFive && op.mid_five && op.mbits2 != nullptr && op.maskp2 != nullptr)
+                return PlaneFive<kPlaneFive, PP>::go(op, cols, ncols, pass_id, tw, s, sms);
+            return launch_cluster3(k_mid<PP, 2, 1>, PP::N / 8 * 32, kSmemMid + 128, PP::N * ncols, op, cols, tw, ncols, s, sms, PP::N);
         }
 #endif
         if (pass_id == PCB_PASS_XFWD_SYM_TD) PCB_GO((k_xfwd<PP, LX, NT, 1, 1, 1>), GX, kStageXT);
@@ -228,7 +245,7 @@ struct PlanePass<true, PP> {
         else if (pass_id == PCB_PASS_XFWD_SYM_T) PCB_GO((k_xfwd<PP, LX, NT, 1, 1>), GX, kStageXT);
         else if (pass_id == PCB_PASS_XINV_A_T) PCB_GO((k_xinv<PP, LX, NT, 1, 1>), GX, kStageXT);
         else if (pass_id == PCB_PASS_XINV_H_T) PCB_GO((k_xinv<PP, LX, NT, 2, 1>), GX, kStageXT);
-        else if (pass_id == PCB_PASS_MASKBITS2) return PlaneFive<kPlaneFive, PP>::go(op, cols, ncols, pass_id, tw, s, sms);
+        else if (pass_id == PCB_PASS_MASKBITS2 || pass_id == PCB_PASS_MASKPLANE2) return PlaneFive<kPlaneFive, PP>::go(op, cols, ncols, pass_id, tw, s, sms);
         else if (op.diel == PCB_DIEL_NONE || op.diel == PCB_DIEL_CHIRAL) {
             if (kPlaneFive && op.mid_five && (op.diel == PCB_DIEL_NONE || op.mbits2 != nullptr)) return PlaneFive<kPlaneFive, PP>::go(op, cols, ncols, pass_id, tw, s, sms);
             static const char* ev = getenv("PCB200_MID_TMA");
@@ -268,7 +285,7 @@ int run_pass(const PcbOp& op, const PcbCols& cols, int ncols, int pass_id, const
             break;
         case PCB_PASS_XFWD_SYM_T: case PCB_PASS_MID: case PCB_PASS_XINV_A_T: case PCB_PASS_XINV_H_T: case PCB_PASS_MASKBITS:
         case PCB_PASS_MID_FWD: case PCB_PASS_MID_INV: case PCB_PASS_MASKPLANE: case PCB_PASS_COORDTAB: case PCB_PASS_MASKBITS2:
-        case PCB_PASS_XFWD_SYM_TD: case PCB_PASS_XINV_A_TD: case PCB_PASS_XINV_H_TD: case PCB_PASS_MID_FWD_O: case PCB_PASS_MID_INV_ST:
+        case PCB_PASS_XFWD_SYM_TD: case PCB_PASS_XINV_A_TD: case PCB_PASS_XINV_H_TD: case PCB_PASS_MID_FWD_O: case PCB_PASS_MID_INV_ST: case PCB_PASS_MASKPLANE2:
             return PlanePass<kPlane, P>::go(op, cols, ncols, pass_id, tw, s, sms);
         default: pcb_set_error("unknown pass id %d", pass_id); return -1;
     }

@@ -132,16 +132,16 @@ def test_device_geometry_matches_host(pcb, oracle, d_flag):
             assert np.array_equal(ind_e, oracle.diel_index(N, d_flag, "edge"))
 
 
-@pytest.mark.parametrize("typ", ["chiral", None])
+@pytest.mark.parametrize("typ", ["chiral", None, "pseudochiral_trivial"])
 def test_five_sweep_plane_pass(pcb, oracle, typ):
     """k_mid2 (2-D register tiles, five shared-memory sweeps; the default at N = 120) forced on at N = 24 = 8 x 3, where the
     emulation can run it, against the oracle; the seven-sweep pass gives the same result to rounding."""
     N, d_flag = 24, "fcc"
     alpha = np.array([0.3 * np.pi, 2 * np.pi, 0.0])
     ctx = pcb.get_context(N)
-    case = {"N": N, "d_flag": d_flag, "alpha": alpha, "type": typ, "eps_opt": 0, "m": 2, "seed": 9}
+    case = {"N": N, "d_flag": d_flag, "alpha": alpha, "type": typ, "eps_opt": 3 if typ == "pseudochiral_trivial" else 0, "m": 2, "seed": 9}
     a, b, inv, shift, _ = oracle.assemble_symbols(N, d_flag, alpha)
-    diel = (lambda v: v) if typ is None else oracle.HANDLES[typ](N, d_flag)
+    diel = (lambda v: v) if typ is None else oracle.HANDLES[typ](N, d_flag, eps_opt=case["eps_opt"])
     Ao, Ho, Po = oracle.pc_mfd_handle(a, b, diel, inv, shift)
     out = {}
     try:
@@ -153,8 +153,9 @@ def test_five_sweep_plane_pass(pcb, oracle, typ):
             assert relerr(A(x), Ao(x)) < TOL
     finally:
         ctx.option("mid_five", -1)
-    assert relerr(out[1], out[0]) < 1e-14
-    assert not np.array_equal(out[1], out[0])      # two different kernels did run
+    assert relerr(out[1], out[0]) < 1e-13
+    if not (typ == "pseudochiral_trivial" and pcb.backend_name == "emu"):      # (no clusters in the emulation: five-pass path both times)
+        assert not np.array_equal(out[1], out[0])      # two different kernels did run
 
 
 @pytest.mark.parametrize("structure", [1, 2, 0])
