@@ -91,10 +91,9 @@ struct pcb_ctx {
     int sms = 148;
     int use_plane = 1;              // PCB200_PLANE=0 forces the five-pass operator (A/B measurements)
     int use_plane_coupled = 1;      // PCB200_PLANE_COUPLED=0: coupled 3x3 dielectric on the five-pass path
-    int use_plane_cross = 2;        // cross-DoF dielectric: 2 = plane halves around the stencil kernel on the slot layout (5 kernels, default:
-                                    // 2.97 ms per 16 columns at N = 120), 1 = stencil fused into the inverse half as a gather on load (4 kernels,
-                                    // 9 column transfers, but 3.07 ms: the 15 warps of the plane pass cannot hide the L2 latency of the gathers
-                                    // the way the stand-alone kernel's occupancy does -- 1.27 ms vs 0.60 + 0.59 ms), 0 = split five-pass path (7 kernels)
+    int use_plane_cross = 1;        // cross-DoF dielectric: 1 = plane halves with the stencil fused into the inverse half as a gather on load
+                                    // (4 kernels, 9 column transfers, default: 2.73 ms per 16 columns at N = 120), 2 = plane halves around the
+                                    // stencil kernel on the slot layout (5 kernels, 2.97 ms), 0 = split five-pass path (7 kernels, 3.54 ms)
     int use_mid_five = -1;          // five-sweep plane pass k_mid2: -1 where it is the faster form (R2 >= 15), 0 never, 1 wherever it exists
     // pcb_apply_host pipeline: copy streams, two slots of (row-major staging in/out, planar columns in/out), events
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
@@ -210,7 +209,7 @@ static int ctx_create(int device, int N, int z0, int z1, pcb_ctx** out) {
     c->z0 = z0; c->z1 = z1; c->nloc = (long long)(z1 - z0) * N * N; c->R = 3 * c->nloc;
     { const char* e = getenv("PCB200_PLANE"); c->use_plane = (plan->plane_mode && !(e && e[0] == '0')) ? 1 : 0; }
     { const char* e = getenv("PCB200_PLANE_COUPLED"); c->use_plane_coupled = !(e && e[0] == '0'); }
-    { const char* e = getenv("PCB200_PLANE_CROSS"); c->use_plane_cross = e ? (e[0] == '0' ? 0 : (e[0] == '1' ? 1 : 2)) : 2; }
+    { const char* e = getenv("PCB200_PLANE_CROSS"); c->use_plane_cross = e ? (e[0] == '0' ? 0 : (e[0] == '2' ? 2 : 1)) : 1; }
     { const char* e = getenv("PCB200_MID_FIVE"); c->use_mid_five = e ? (e[0] == '0' ? 0 : 1) : -1; }
 #ifndef PCB_EMU
     cudaDeviceProp prop;
@@ -273,7 +272,7 @@ int pcb_ctx_option(pcb_ctx* c, const char* name, int value) {
     PCB_CHECK_ARG(c && name, "null");
     if (!strcmp(name, "plane")) c->use_plane = (value && c->plan->plane_mode) ? 1 : 0;
     else if (!strcmp(name, "plane_coupled")) c->use_plane_coupled = value ? 1 : 0;
-    else if (!strcmp(name, "plane_cross")) c->use_plane_cross = (value == 1) ? 1 : (value ? 2 : 0);
+    else if (!strcmp(name, "plane_cross")) c->use_plane_cross = (value == 2) ? 2 : (value ? 1 : 0);
     else if (!strcmp(name, "mid_five")) c->use_mid_five = value < 0 ? -1 : (value ? 1 : 0);
     else { pcb_set_error("pcb_ctx_option: unknown option %s", name); return -2; }
     return 0;

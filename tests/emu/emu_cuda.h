@@ -205,6 +205,25 @@ inline T shfl(T v, int src_lane) {
     return r;
 }
 
+// warp vote: true if the predicate holds on any lane of the calling fiber's warp (all lanes of the warp must call it)
+inline bool vote_any(bool pred) {
+    Block* b = cur_block();
+    Fiber& f = cur_fiber();
+    const int w = f.lin / 32, l = f.lin % 32;
+    const int nt = (int)b->fibers.size();
+    int v = pred ? 1 : 0;
+    memcpy(b->xchg[w][l], &v, sizeof(int));
+    yield_state(2);
+    bool any = false;
+    for (int k = 0; k < 32 && w * 32 + k < nt; ++k) {
+        int o;
+        memcpy(&o, b->xchg[w][k], sizeof(int));
+        any = any || (o != 0);
+    }
+    yield_state(2);
+    return any;
+}
+
 // mma.sync.aligned.m8n8k4.row.col.f64: D(8x8) += A(8x4) * B(4x8); lane holds A[lane>>2][lane&3], B[lane&3][lane>>2],
 // C[lane>>2][2*(lane&3) + {0,1}]  (PTX ISA fragment layout).
 inline void mma884(double& c0, double& c1, double a, double b) {
@@ -241,6 +260,8 @@ template <class T> static inline T __shfl_down_sync(unsigned, T v, int d, int = 
     return pcbemu::shfl(v, (pcbemu::cur_fiber().lin % 32) + d);
 }
 template <class T> static inline T __shfl_sync(unsigned, T v, int src, int = 32) { return pcbemu::shfl(v, src); }
+static inline bool __any_sync(unsigned, bool pred) { return pcbemu::vote_any(pred); }
+static inline int __ffs(int v) { return v == 0 ? 0 : __builtin_ffs(v); }
 template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline double atomicAdd(double* p, double v) { double o = *p; *p += v; return o; }
 static inline int atomicAdd(int* p, int v) { int o = *p; *p += v; return o; }

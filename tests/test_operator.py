@@ -160,8 +160,8 @@ def test_five_sweep_plane_pass(pcb, oracle, typ):
 
 @pytest.mark.parametrize("structure", [1, 2, 0])
 def test_crossdof_pass_structures(pcb, oracle, structure):
-    """The three pass structures of the cross-DoF dielectric give the oracle's H: 2 = plane halves around the stencil kernel on
-    the slot layout (default), 1 = plane halves with the stencil fused into the inverse half, 0 = split five-pass path.
+    """The three pass structures of the cross-DoF dielectric give the oracle's H: 1 = plane halves with the stencil fused into
+    the inverse half (default), 2 = plane halves around the stencil kernel on the slot layout, 0 = split five-pass path.
     eps_opt = 3 couples all three component pairs (in-plane and across i0 planes)."""
     N, d_flag = 16, "bcc_dg"
     alpha = np.array([np.pi, 0.0, np.pi])
@@ -175,4 +175,4 @@ def test_crossdof_pass_structures(pcb, oracle, structure):
         assert relerr(H(x), Ho(x)) < TOL
         assert relerr(A(x), Ao(x)) < TOL
     finally:
-        ctx.option("plane_cross", 2)
+        ctx.option("plane_cross", 1)
