@@ -270,6 +270,97 @@ __global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * (P::R1 * P::R2P + TR
     }
 }
 
+// Plane-mode forward x pass on TWO consecutive tiles per CTA (K_A^H on load, transposed store): the raw loads of the second
+// tile are issued before the radix-R2 phase of the first, so a CTA has loads in flight for about a third of its life instead of a
+// fifth (ncu of k_xfwd<T>: long_scoreboard 69 %, DRAM 61 %); the price is 3 instead of 4 CTAs per SM (24 complex values wait in
+// registers through a phase that needs R2 more).  One phase-1 item per thread (LX R2 <= NT).
+// (Longer chains -- 4, 8, 16 tiles per CTA with the same ping-pong -- spill 1.3-10 KB per thread whether the loop is unrolled
+// or not and run at 0.85-0.91 ms; two tiles: 0.50 ms against 0.53 ms for k_xfwd<T> at N = 120, 16 columns.)
+template <class P, int LX, int NT>
+__global__ void __launch_bounds__(NT, 3) k_xfwd2(PcbOp op, PcbCols cols, const cplx* __restrict__ tw) {
+    constexpr int N = P::N, R1 = P::R1, R2 = P::R2, R2P = P::R2P;
+    constexpr int RS = R1 * R2P + 1;
+    static_assert(LX * R2 <= NT, "one radix-R1 item per thread");
+    PCB_DYN_SMEM(cplx, sm);   // [3][LX][RS]
+    const int col = blockIdx.y;
+    const cplx* __restrict__ X = cols.in[col];
+    cplx* __restrict__ Y = cols.wrk[col];
+    const long long nn = op.nn;
+    const int nrows = N * N;
+    const int tid = threadIdx.x;
+    const int r = tid / R2, n2 = tid % R2;      // phase-1 item of this thread
+    const bool has1 = tid < LX * R2;
+
+    auto load_raw = [&](int row0, cplx (&x)[3][R1]) {
+        const int row = row0 + r;
+        if (has1 && row < nrows) {
+            PCB_UNROLL
+            for (int n1 = 0; n1 < R1; ++n1) {
+                const long long e = (long long)row * N + n1 * R2 + n2;
+                PCB_UNROLL
+                for (int c = 0; c < 3; ++c) x[c][n1] = X[c * nn + e];
+            }
+        }
+    };
+    auto phase1 = [&](int row0, cplx (&x)[3][R1]) {      // (-conj k) x . on the loaded values, radix R1, twiddles -> shared memory
+        const int row = row0 + r;
+        if (!(has1 && row < nrows)) return;
+        const int i1 = row % N, i2 = row / N;
+        cplx kc[3];
+        PCB_UNROLL
+        for (int c = 0; c < 3; ++c) kc[c] = cadd(__ldg(op.T + (c * 3 + 1) * N + i1), __ldg(op.T + (c * 3 + 2) * N + i2));
+        PCB_UNROLL
+        for (int n1 = 0; n1 < R1; ++n1) {
+            const int i0 = n1 * R2 + n2;
+            cplx a[3], xin[3] = {x[0][n1], x[1][n1], x[2][n1]}, z[3];
+            PCB_UNROLL
+            for (int c = 0; c < 3; ++c) {
+                const cplx k = cadd(kc[c], __ldg(op.T + (c * 3 + 0) * N + i0));
+                a[c] = cmake(-k.x, k.y);
+            }
+            pcb_cross(a, xin, z);
+            PCB_UNROLL
+            for (int c = 0; c < 3; ++c) x[c][n1] = z[c];
+        }
+        PCB_UNROLL
+        for (int c = 0; c < 3; ++c) {
+            Dft<R1, -1>::run(x[c]);
+            PCB_UNROLL
+            for (int k1 = 0; k1 < R1; ++k1) {
+                cplx val = x[c][k1];
+                if (k1 > 0) val = cmul(val, __ldg(tw + k1 * R2 + n2));
+                sm[(c * LX + r) * RS + k1 * R2P + n2] = val;
+            }
+        }
+    };
+    auto phase2 = [&](int row0) {      // radix R2 from shared memory, transposed store W'[c][k][i2][i1]
+        for (int item = tid; item < 3 * LX * R1; item += NT) {
+            const int k1 = (item / LX) % R1, rr = item % LX, c = item / (R1 * LX);
+            const int row = row0 + rr;
+            if (row >= nrows) continue;
+            cplx v[R2];
+            PCB_UNROLL
+            for (int m2 = 0; m2 < R2; ++m2) v[m2] = sm[(c * LX + rr) * RS + k1 * R2P + m2];
+            Dft<R2, -1>::run(v);
+            cplx* __restrict__ dst = Y + c * nn + (long long)k1 * N * N + row;
+            PCB_UNROLL
+            for (int k2 = 0; k2 < R2; ++k2) dst[(long long)R1 * k2 * N * N] = v[k2];
+        }
+    };
+
+    const int row0 = blockIdx.x * (2 * LX);
+    cplx xa[3][R1], xb[3][R1];
+    load_raw(row0, xa);
+    phase1(row0, xa);
+    load_raw(row0 + LX, xb);       // in flight during the radix-R2 phase of the first tile
+    __syncthreads();
+    phase2(row0);
+    __syncthreads();
+    phase1(row0 + LX, xb);
+    __syncthreads();
+    phase2(row0 + LX);
+}
+
 // ---------------------------------------------------------------------------------------
 // Pass 5: x-lines inverse.  MODE 0: plain IFFT * 1/N^3;  1: A = K_A . ;  2: H = K_A . + gamma K_B x + shift x
 // Reads the work column W (in Fourier-x order), the source column X (MODE 2) and writes OUT

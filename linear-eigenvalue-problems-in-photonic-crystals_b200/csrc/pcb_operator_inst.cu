@@ -172,6 +172,20 @@ struct PlaneFive<true, PP> {
     }
 };
 
+template <bool OK, class PP>
+struct XFwd2 { static int go(const PcbOp&, const PcbCols&, int, const cplx*, cudaStream_t) { return -1; } };
+template <class PP>
+struct XFwd2<true, PP> {
+    static int go(const PcbOp& op, const PcbCols& cols, int ncols, const cplx* tw, cudaStream_t s) {
+        auto kfn = k_xfwd2<PP, LX, NT>;
+        if (set_smem(kfn, kStageXT)) return -1;
+        dim3 grid((unsigned)((GX + 1) / 2), (unsigned)ncols, 1);
+        PCB_LAUNCH(kfn, grid, dim3(NT, 1, 1), (size_t)kStageXT, s, op, cols, tw);
+        PCB_CUDA_OK(cudaGetLastError());
+        return 0;
+    }
+};
+
 // plane-mode passes exist only for sizes with kPlane (the kernels are not even instantiated otherwise)
 template <bool ENABLED, class PP>
 struct PlanePass {
@@ -242,7 +256,11 @@ struct PlanePass<true, PP> {
         if (pass_id == PCB_PASS_XFWD_SYM_TD) PCB_GO((k_xfwd<PP, LX, NT, 1, 1, 1>), GX, kStageXT);
         else if (pass_id == PCB_PASS_XINV_A_TD) PCB_GO((k_xinv<PP, LX, NT, 1, 1, 1>), GX, kStageXT);
         else if (pass_id == PCB_PASS_XINV_H_TD) PCB_GO((k_xinv<PP, LX, NT, 2, 1, 1>), GX, kStageXT);
-        else if (pass_id == PCB_PASS_XFWD_SYM_T) PCB_GO((k_xfwd<PP, LX, NT, 1, 1>), GX, kStageXT);
+        else if (pass_id == PCB_PASS_XFWD_SYM_T) {
+            static const char* ev2 = getenv("PCB200_XFWD2");      // default: two tiles per CTA, the second tile's loads behind the first tile's radix-R2 phase (PCB200_XFWD2=0: one tile per CTA)
+            if (LX * PP::R2 <= NT && PP::N >= 64 && !(ev2 && ev2[0] == '0')) {      // (N = 48: 0.058 vs 0.051 ms, one tile per CTA stays) if (XFwd2<(LX * PP::R2 <= NT && PP::N >= 64), PP>::go(op, cols, ncols, tw, s)) return -1; }
+            else PCB_GO((k_xfwd<PP, LX, NT, 1, 1>), GX, kStageXT);
+        }
         else if (pass_id == PCB_PASS_XINV_A_T) PCB_GO((k_xinv<PP, LX, NT, 1, 1>), GX, kStageXT);
         else if (pass_id == PCB_PASS_XINV_H_T) PCB_GO((k_xinv<PP, LX, NT, 2, 1>), GX, kStageXT);
         else if (pass_id == PCB_PASS_MASKBITS2 || pass_id == PCB_PASS_MASKPLANE2) return PlaneFive<kPlaneFive, PP>::go(op, cols, ncols, pass_id, tw, s, sms);
