@@ -258,7 +258,8 @@ struct PlanePass<true, PP> {
         else if (pass_id == PCB_PASS_XINV_H_TD) PCB_GO((k_xinv<PP, LX, NT, 2, 1, 1>), GX, kStageXT);
         else if (pass_id == PCB_PASS_XFWD_SYM_T) {
             static const char* ev2 = getenv("PCB200_XFWD2");      // default: two tiles per CTA, the second tile's loads behind the first tile's radix-R2 phase (PCB200_XFWD2=0: one tile per CTA)
-            if (LX * PP::R2 <= NT && PP::N >= 64 && !(ev2 && ev2[0] == '0')) {      // (N = 48: 0.058 vs 0.051 ms, one tile per CTA stays) if (XFwd2<(LX * PP::R2 <= NT && PP::N >= 64), PP>::go(op, cols, ncols, tw, s)) return -1; }
+            // (N = 48: 0.058 vs 0.051 ms -- below N = 64 one tile per CTA stays)
+            if (LX * PP::R2 <= NT && PP::N >= 64 && !(ev2 && ev2[0] == '0')) { if (XFwd2<(LX * PP::R2 <= NT && PP::N >= 64), PP>::go(op, cols, ncols, tw, s)) return -1; }
             else PCB_GO((k_xfwd<PP, LX, NT, 1, 1>), GX, kStageXT);
         }
         else if (pass_id == PCB_PASS_XINV_A_T) PCB_GO((k_xinv<PP, LX, NT, 1, 1>), GX, kStageXT);
