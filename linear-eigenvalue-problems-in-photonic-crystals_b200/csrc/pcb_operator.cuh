@@ -1569,6 +1569,10 @@ __global__ void __launch_bounds__(Mid2<P>::NTHR, 1) k_mid2(PcbOp op, PcbCols col
 #endif
 }
 
+// (Round 2, measured and removed: k_mid3 -- a warp working on its two row sets one after the other with all 32 lanes, each set on
+// its own mbarrier, so that the reload of set 0 for the next plane is in flight behind the inverse sweeps of set 1 and that of
+// set 1 behind the forward sweeps of set 0: identical results, 0.822 vs 0.807 ms.  Together with the L2-prefetch variant this
+// says the plane pass does not wait for its rows; it waits for dependent FP64 issue and the two CTA barriers around sweep C.)
 // Plane-mode set-up for the coupled dielectric: the byte mask (bit c: edge DoF of component c, bit 3: volume DoF in Omega_1)
 // in the slot order of the plane pass, maskp[i0][row][col] = mask(i0, i1 = coord(col), i2 = coord(row)).
 template <class P>
