@@ -24,7 +24,7 @@ EMU_DIR = os.path.join(ROOT, "tests", "emu")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false", "-Xptxas", "-warn-spills"]
-NVCC_FLAGS = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
+NVCC_FLAGS = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + os.environ.get("PCB200_NVCC_EXTRA", "").split()
 GXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-DPCB_EMU", "-x", "c++", "-include", os.path.join(EMU_DIR, "emu_cuda.h"),
              "-I", EMU_DIR, "-Wno-unknown-pragmas", "-Wno-unused-value", "-fno-strict-aliasing"]
 

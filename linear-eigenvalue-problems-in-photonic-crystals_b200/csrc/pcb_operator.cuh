@@ -369,8 +369,11 @@ __global__ void __launch_bounds__(NT, 3) k_xfwd2(PcbOp op, PcbCols cols, const c
 // DIST = 1 (large-grid mode over peer memory): the result rows go straight into the output column's slab on the rank that owns
 // their i2 plane (IPC-mapped pointers of op.dist) -- the slab scatter of the exchange path fused into this pass; X is re-read
 // from the local copy the forward pass left in cols.in[col].
+#ifndef PCB_XINV_CTAS
+#define PCB_XINV_CTAS 4
+#endif
 template <class P, int LX, int NT, int MODE, int TRN = 0, int DIST = 0>
-__global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * (P::R1 * P::R2P + TRN) * 16, P::R1, 4)) k_xinv(PcbOp op, PcbCols cols, const cplx* __restrict__ tw) {
+__global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * (P::R1 * P::R2P + TRN) * 16, P::R1, (TRN ? PCB_XINV_CTAS : 4))) k_xinv(PcbOp op, PcbCols cols, const cplx* __restrict__ tw) {
     constexpr int N = P::N, R1 = P::R1, R2 = P::R2, R2P = P::R2P;
     constexpr int RS = R1 * R2P + TRN;      // row stride in shared memory (see k_xfwd)
     PCB_DYN_SMEM(cplx, sm);   // [3][LX][RS]
