@@ -98,7 +98,8 @@ int pcb_op_update(pcb_op* op, const double* tables, double gamma, double shift, 
 void pcb_op_destroy(pcb_op* op);
 
 /* Y_j = op(X_j), j < ncols.  in[j] == out[j] (in place) is allowed for every mode except PCB_APPLY_H (which re-reads X in
- * its last pass) and PCB_APPLY_M with the cross-DoF dielectric; distinct columns must not overlap. */
+ * its last pass), PCB_APPLY_A / PCB_APPLY_M with the cross-DoF dielectric (out serves as work space of the plane halves / the
+ * stencil gathers); the call fails with -2 in those cases.  Distinct columns must not overlap. */
 int pcb_apply(pcb_op* op, int mode, int ncols, const void* const* in, void* const* out);
 
 /* Y_host = op(X_host): the reference-facing call with host arrays -- x_host, y_host are the reference's row-major (3N^3, k)
