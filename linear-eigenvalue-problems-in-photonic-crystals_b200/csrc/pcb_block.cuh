@@ -771,7 +771,7 @@ __global__ void __launch_bounds__(256) k_diel_crossdof_t(PcbOp op, PcbStencil st
     cplx* __restrict__ Y = cols.out[blockIdx.y];
     const int* __restrict__ ctab = op.ctab;
     const int scol = (int)(pt % N), srow = (int)((pt / N) % N);
-    const int i[3] = {(int)(pt / ((long long)N * N)), __ldg(ctab + scol), __ldg(ctab + srow)};
+    const int i[3] = {(int)(pt / ((long long)N * N)), __ldg(ctab + scol), __ldg(ctab + 2 * N + srow)};
     const unsigned char* __restrict__ maskp = op.maskp;      // the byte mask in the same slot order (k_mask_plane): coalesced
     const unsigned mp = __ldg(maskp + pt);
     cplx y[3];
@@ -804,8 +804,8 @@ __global__ void __launch_bounds__(256) k_diel_crossdof_t(PcbOp op, PcbStencil st
                 int q[3] = {i[0], i[1], i[2]}, r[3] = {i[0], i[1], i[2]};
                 q[cax] = pcb_wrap(i[cax] + oc, N); q[tax] = pcb_wrap(i[tax] - ot, N);
                 r[cax] = pcb_wrap(i[cax] - oc, N); r[tax] = pcb_wrap(i[tax] + ot, N);
-                const long long qs = ((long long)q[0] * N + __ldg(ctab + N + q[2])) * N + __ldg(ctab + N + q[1]);
-                const long long rs = ((long long)r[0] * N + __ldg(ctab + N + r[2])) * N + __ldg(ctab + N + r[1]);
+                const long long qs = ((long long)q[0] * N + __ldg(ctab + 3 * N + q[2])) * N + __ldg(ctab + N + q[1]);
+                const long long rs = ((long long)r[0] * N + __ldg(ctab + 3 * N + r[2])) * N + __ldg(ctab + N + r[1]);
                 const double Ibq = (double)((__ldg(maskp + qs) >> b) & 1u);
                 sa = cadd(sa, cscale(Xb[qs], w * (Ia + Ibq)));
                 const double Iap = (double)((__ldg(maskp + rs) >> a) & 1u);
@@ -827,7 +827,7 @@ __global__ void __launch_bounds__(256) k_mask_active(PcbOp op, const unsigned ch
     const long long pt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (pt >= op.nn) return;
     const int* __restrict__ ctab = op.ctab;
-    const int i[3] = {(int)(pt / ((long long)N * N)), ctab[(int)(pt % N)], ctab[(int)((pt / N) % N)]};
+    const int i[3] = {(int)(pt / ((long long)N * N)), ctab[(int)(pt % N)], ctab[2 * N + (int)((pt / N) % N)]};
     const unsigned mp = src[pt];
     constexpr int PA[3] = {0, 0, 1}, PB[3] = {1, 2, 2}, CAX[3] = {2, 2, 1}, TAX[3] = {1, 0, 0};
     const int kk = op.sten.k;
@@ -843,8 +843,8 @@ __global__ void __launch_bounds__(256) k_mask_active(PcbOp op, const unsigned ch
                 int q[3] = {i[0], i[1], i[2]}, r[3] = {i[0], i[1], i[2]};
                 q[cax] = pcb_wrap(i[cax] + oc, N); q[tax] = pcb_wrap(i[tax] - ot, N);
                 r[cax] = pcb_wrap(i[cax] - oc, N); r[tax] = pcb_wrap(i[tax] + ot, N);
-                const long long qs = ((long long)q[0] * N + ctab[N + q[2]]) * N + ctab[N + q[1]];
-                const long long rs = ((long long)r[0] * N + ctab[N + r[2]]) * N + ctab[N + r[1]];
+                const long long qs = ((long long)q[0] * N + ctab[3 * N + q[2]]) * N + ctab[N + q[1]];
+                const long long rs = ((long long)r[0] * N + ctab[3 * N + r[2]]) * N + ctab[N + r[1]];
                 act |= ((unsigned)(src[qs] >> b) & 1u) << a;      // y_a(p) sees I_b(q)
                 act |= ((unsigned)(src[rs] >> a) & 1u) << b;      // y_b(p) sees I_a(r)
             }

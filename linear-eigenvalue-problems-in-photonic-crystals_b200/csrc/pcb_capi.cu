@@ -94,6 +94,8 @@ struct pcb_ctx {
     int use_plane_cross = 1;        // cross-DoF dielectric: 1 = plane halves with the stencil fused into the inverse half as a gather on load
                                     // (4 kernels, 9 column transfers, default: 2.73 ms per 16 columns at N = 120), 2 = plane halves around the
                                     // stencil kernel on the slot layout (5 kernels, 2.97 ms), 0 = split five-pass path (7 kernels, 3.54 ms)
+    int zsplit = 0;                 // plane mode in its z-split form (half planes): the only plane mode of N = 128, 144, 160; PCB200_PLANE_SPLIT=1 /
+                                    // pcb_ctx_option "plane_split" select it for the smaller sizes that have it (A/B measurements, tests)
     int use_mid_five = -1;          // five-sweep plane pass k_mid2: -1 where it is the faster form (R2 >= 15), 0 never, 1 wherever it exists
     // pcb_apply_host pipeline: copy streams, two slots of (row-major staging in/out, planar columns in/out), events
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
@@ -109,6 +111,7 @@ struct pcb_diel {
     unsigned* mbits2;       // five-sweep plane pass: bit words in its item order (k_mask_bits2); else null
     unsigned char* maskp2;  // five-sweep plane pass, coupled dielectric: byte mask in its slot order (k_mask_plane2); else null
     unsigned char* maskp;   // plane mode, coupled dielectric: byte mask in plane-slot order (k_mask_plane); else null
+    int zsplit;             // the plane-mode form (ctx->zsplit) the slot-ordered masks were built for
     double ediag[3];
     cplx eoff[3];
     PcbStencil st;
@@ -196,6 +199,15 @@ int pcb_ctx_create_slab(int device, int N, int z0, int z1, pcb_ctx** out) {
     return ctx_create(device, N, z0, z1, out);
 }
 }  // extern "C"
+// slot <-> index tables of the plane layout in the context's plane-mode form
+static int ctx_coord_tables(pcb_ctx* c) {
+    PcbOp tmp; memset(&tmp, 0, sizeof tmp);
+    tmp.N = c->N; tmp.ctab = c->ctab; tmp.zsplit = c->zsplit;
+    PcbCols none; memset(&none, 0, sizeof none);
+    if (c->plan->pass(tmp, none, 1, PCB_PASS_COORDTAB, c->tw, c->stream, c->sms)) return -1;
+    PCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
 static int ctx_create(int device, int N, int z0, int z1, pcb_ctx** out) {
     PCB_CHECK_ARG(out, "null");
     const PcbOpLaunch* plan = pcb_find_plan(N);
@@ -211,6 +223,7 @@ static int ctx_create(int device, int N, int z0, int z1, pcb_ctx** out) {
     { const char* e = getenv("PCB200_PLANE_COUPLED"); c->use_plane_coupled = !(e && e[0] == '0'); }
     { const char* e = getenv("PCB200_PLANE_CROSS"); c->use_plane_cross = e ? (e[0] == '0' ? 0 : (e[0] == '2' ? 2 : 1)) : 1; }
     { const char* e = getenv("PCB200_MID_FIVE"); c->use_mid_five = e ? (e[0] == '0' ? 0 : 1) : -1; }
+    { const char* e = getenv("PCB200_PLANE_SPLIT"); c->zsplit = (plan->plane_split == 2 || (plan->plane_split == 1 && e && e[0] == '1')) ? 1 : 0; }
 #ifndef PCB_EMU
     cudaDeviceProp prop;
     PCB_CUDA_OK_OR(cudaGetDeviceProperties(&prop, device), delete c);
@@ -223,21 +236,30 @@ static int ctx_create(int device, int N, int z0, int z1, pcb_ctx** out) {
     PCB_CUDA_OK_OR(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), delete c);
     PCB_CUDA_OK_OR(cudaEventCreate(&c->ev0), pcb_ctx_destroy(c));
     PCB_CUDA_OK_OR(cudaEventCreate(&c->ev1), pcb_ctx_destroy(c));
-    std::vector<cplx> tw((size_t)N);
+    // [0, N): twiddles of the plan; z-split plane mode: [N, N + N/2) twiddles of the plan of N/2, [N + N/2, 2N) the split twiddles w_N^n
+    std::vector<cplx> tw((size_t)2 * N, cmake(0.0, 0.0));
     for (int k1 = 0; k1 < plan->r1; ++k1)
         for (int n2 = 0; n2 < plan->r2; ++n2) {
             const double ang = -2.0 * M_PI * (double)((long long)k1 * n2 % N) / (double)N;
             tw[(size_t)k1 * plan->r2 + n2] = cmake(cos(ang), sin(ang));
         }
-    PCB_CUDA_OK_OR(cudaMalloc(&c->tw, sizeof(cplx) * N), pcb_ctx_destroy(c));
-    PCB_CUDA_OK_OR(cudaMemcpy(c->tw, tw.data(), sizeof(cplx) * N, cudaMemcpyHostToDevice), pcb_ctx_destroy(c));
+    if (plan->plane_split) {
+        const int nz = N / 2;
+        for (int k1 = 0; k1 < plan->zr1; ++k1)
+            for (int n2 = 0; n2 < plan->zr2; ++n2) {
+                const double ang = -2.0 * M_PI * (double)((long long)k1 * n2 % nz) / (double)nz;
+                tw[(size_t)N + (size_t)k1 * plan->zr2 + n2] = cmake(cos(ang), sin(ang));
+            }
+        for (int n = 0; n < nz; ++n) {
+            const double ang = -2.0 * M_PI * (double)n / (double)N;
+            tw[(size_t)N + nz + n] = cmake(cos(ang), sin(ang));
+        }
+    }
+    PCB_CUDA_OK_OR(cudaMalloc(&c->tw, sizeof(cplx) * 2 * N), pcb_ctx_destroy(c));
+    PCB_CUDA_OK_OR(cudaMemcpy(c->tw, tw.data(), sizeof(cplx) * 2 * N, cudaMemcpyHostToDevice), pcb_ctx_destroy(c));
     if (plan->plane_mode) {
-        PCB_CUDA_OK_OR(cudaMalloc(&c->ctab, sizeof(int) * 2 * N), pcb_ctx_destroy(c));
-        PcbOp tmp; memset(&tmp, 0, sizeof tmp);
-        tmp.N = N; tmp.ctab = c->ctab;
-        PcbCols none; memset(&none, 0, sizeof none);
-        if (plan->pass(tmp, none, 1, PCB_PASS_COORDTAB, c->tw, c->stream, c->sms)) { pcb_ctx_destroy(c); return -1; }
-        PCB_CUDA_OK_OR(cudaStreamSynchronize(c->stream), pcb_ctx_destroy(c));
+        PCB_CUDA_OK_OR(cudaMalloc(&c->ctab, sizeof(int) * 4 * N), pcb_ctx_destroy(c));
+        if (ctx_coord_tables(c)) { pcb_ctx_destroy(c); return -1; }
     }
     *out = c;
     return 0;
@@ -274,6 +296,17 @@ int pcb_ctx_option(pcb_ctx* c, const char* name, int value) {
     else if (!strcmp(name, "plane_coupled")) c->use_plane_coupled = value ? 1 : 0;
     else if (!strcmp(name, "plane_cross")) c->use_plane_cross = (value == 2) ? 2 : (value ? 1 : 0);
     else if (!strcmp(name, "mid_five")) c->use_mid_five = value < 0 ? -1 : (value ? 1 : 0);
+    else if (!strcmp(name, "plane_split")) {
+        // the form of the plane mode (0 whole planes, 1 z-split half planes) where the size has both; dielectrics carry masks in the slot
+        // order of the form they were created under and must be re-created after a change (pcb_op_create / _update check)
+        const int want = (c->plan->plane_split == 2 || (c->plan->plane_split == 1 && value)) ? 1 : 0;
+        if (want != c->zsplit) {
+            PCB_CUDA_OK(cudaSetDevice(c->device));
+            PCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+            c->zsplit = want;
+            if (c->ctab && ctx_coord_tables(c)) return -1;
+        }
+    }
     else { pcb_set_error("pcb_ctx_option: unknown option %s", name); return -2; }
     return 0;
 }
@@ -443,28 +476,31 @@ int pcb_diel_create(pcb_ctx* c, int kind, const int64_t* ind_e, long long n_e, c
 #undef PCB_DIEL_FAIL
         PCB_CUDA_OK_OR(cudaFree(dind), pcb_diel_destroy(d));
     }
+    d->zsplit = c->zsplit;
+    const bool whole = !c->zsplit;      // whole-plane forms only: five-sweep pass, clusters for the coupled dielectric
     if (c->plan->plane_mode) {
-        PCB_CUDA_OK_OR(cudaMalloc(&d->mbits, sizeof(unsigned) * 3 * (size_t)c->N * c->N * c->plan->r1), pcb_diel_destroy(d));
+        const size_t words = c->zsplit ? (size_t)2 * c->plan->zr1 : (size_t)c->plan->r1;
+        PCB_CUDA_OK_OR(cudaMalloc(&d->mbits, sizeof(unsigned) * 3 * (size_t)c->N * c->N * words), pcb_diel_destroy(d));
         PcbOp tmp;
         memset(&tmp, 0, sizeof tmp);
-        tmp.N = c->N; tmp.nn = c->nn; tmp.nloc = c->nloc; tmp.mask = d->mask; tmp.mbits = d->mbits;
+        tmp.N = c->N; tmp.nn = c->nn; tmp.nloc = c->nloc; tmp.mask = d->mask; tmp.mbits = d->mbits; tmp.zsplit = c->zsplit;
         PcbCols none;
         memset(&none, 0, sizeof none);
         if (c->plan->pass(tmp, none, 1, PCB_PASS_MASKBITS, c->tw, c->stream, c->sms)) { pcb_diel_destroy(d); return -1; }
         c->launches++;
-        if (c->plan->plane_five && c->plan->plane_coupled && kind == PCB_DIEL_TRIVIAL) {
+        if (whole && c->plan->plane_five && c->plan->plane_coupled && kind == PCB_DIEL_TRIVIAL) {
             PCB_CUDA_OK_OR(cudaMalloc(&d->maskp2, (size_t)c->nn), pcb_diel_destroy(d));
             tmp.maskp2 = d->maskp2;
             if (c->plan->pass(tmp, none, 1, PCB_PASS_MASKPLANE2, c->tw, c->stream, c->sms)) { pcb_diel_destroy(d); return -1; }
             c->launches++;
         }
-        if (c->plan->plane_five && (kind == PCB_DIEL_CHIRAL || (kind == PCB_DIEL_TRIVIAL && c->plan->plane_coupled))) {
+        if (whole && c->plan->plane_five && (kind == PCB_DIEL_CHIRAL || (kind == PCB_DIEL_TRIVIAL && c->plan->plane_coupled))) {
             PCB_CUDA_OK_OR(cudaMalloc(&d->mbits2, sizeof(unsigned) * 3 * (size_t)c->N * c->N * 8), pcb_diel_destroy(d));
             tmp.mbits2 = d->mbits2;
             if (c->plan->pass(tmp, none, 1, PCB_PASS_MASKBITS2, c->tw, c->stream, c->sms)) { pcb_diel_destroy(d); return -1; }
             c->launches++;
         }
-        if ((c->plan->plane_coupled && kind == PCB_DIEL_TRIVIAL) || kind == PCB_DIEL_CROSSDOF) {
+        if ((whole && c->plan->plane_coupled && kind == PCB_DIEL_TRIVIAL) || kind == PCB_DIEL_CROSSDOF) {
             PCB_CUDA_OK_OR(cudaMalloc(&d->maskp, (size_t)c->nn), pcb_diel_destroy(d));
             tmp.maskp = d->maskp;
             if (c->plan->pass(tmp, none, 1, PCB_PASS_MASKPLANE, c->tw, c->stream, c->sms)) { pcb_diel_destroy(d); return -1; }
@@ -515,10 +551,11 @@ static void op_fill(pcb_op* o, double gamma, double shift, double pshift, pcb_di
     o->d.maskp2 = diel ? diel->maskp2 : nullptr;
     if (diel) o->d.sten = diel->st; else { o->d.sten.k = 1; for (int i = 0; i < 8; ++i) o->d.sten.w[i] = 0.0; }
     o->d.ctab = c->ctab;
+    o->d.zsplit = c->zsplit;
     o->d.dist = nullptr;
     // five-sweep plane pass: where it is the faster form -- N = 8 x 15 with the identity / isotropic M (0.80 vs 0.815 ms); the coupled M
     // on clusters is faster in the seven-sweep kernel (1.20 vs 1.44 ms: with 8 warps the split sweep C and the DSMEM step cost more)
-    o->d.mid_five = (c->plan->plane_five && (c->use_mid_five == 1 ||
+    o->d.mid_five = (c->plan->plane_five && !c->zsplit && (c->use_mid_five == 1 ||
                      (c->use_mid_five == -1 && c->plan->r2 >= 15 && o->d.diel != PCB_DIEL_TRIVIAL))) ? 1 : 0;
     for (int i = 0; i < 3; ++i) {
         o->d.ediag[i] = diel ? diel->ediag[i] : 1.0;
@@ -529,6 +566,7 @@ int pcb_op_update(pcb_op* o, const double* tables, double gamma, double shift, d
     PCB_CHECK_ARG(o && tables, "null");
     pcb_ctx* c = o->ctx;
     PCB_CHECK_ARG(!diel || diel->ctx == c, "dielectric belongs to another context");
+    PCB_CHECK_ARG(!diel || diel->zsplit == c->zsplit, "dielectric was created under the other plane-mode form (plane_split); re-create it");
     PCB_CUDA_OK(cudaSetDevice(c->device));
     const size_t bytes = sizeof(cplx) * 9 * (size_t)c->N;
     if (ensure_hstage(c, bytes > 65536 ? bytes : 65536)) return -1;
@@ -589,9 +627,9 @@ enum { PCB_STRUCT_PLANE = 0, PCB_STRUCT_FIVE = 1, PCB_STRUCT_CROSS7 = 2, PCB_STR
 static int apply_structure(const pcb_op* o) {
     const pcb_ctx* c = o->ctx;
     const int diel = o->d.diel;
-    if (c->use_plane) {
+    if (c->use_plane && (c->zsplit || c->plan->plane_split != 2)) {
         if (diel == PCB_DIEL_NONE || diel == PCB_DIEL_CHIRAL) return PCB_STRUCT_PLANE;
-        if (diel == PCB_DIEL_TRIVIAL && c->plan->plane_coupled && c->use_plane_coupled) return PCB_STRUCT_PLANE;
+        if (diel == PCB_DIEL_TRIVIAL && c->plan->plane_coupled && c->use_plane_coupled && !c->zsplit) return PCB_STRUCT_PLANE;
         if (diel == PCB_DIEL_CROSSDOF && c->use_plane_cross) return c->use_plane_cross == 2 ? PCB_STRUCT_CROSS5 : PCB_STRUCT_CROSS4;
     }
     return diel == PCB_DIEL_CROSSDOF ? PCB_STRUCT_CROSS7 : PCB_STRUCT_FIVE;
@@ -607,7 +645,8 @@ static int apply_AH(pcb_op* o, int mode, PcbCols& cols, int kc, int j0, int dist
     const int first = din ? PCB_PASS_XFWD_SYM_D : PCB_PASS_XFWD_SYM, first_t = din ? PCB_PASS_XFWD_SYM_TD : PCB_PASS_XFWD_SYM_T;
     const int last = (mode == PCB_APPLY_A) ? (dout ? PCB_PASS_XINV_A_D : PCB_PASS_XINV_A) : (dout ? PCB_PASS_XINV_H_D : PCB_PASS_XINV_H);
     const int last_t = (mode == PCB_APPLY_A) ? (dout ? PCB_PASS_XINV_A_TD : PCB_PASS_XINV_A_T) : (dout ? PCB_PASS_XINV_H_TD : PCB_PASS_XINV_H_T);
-    const int st = apply_structure(o);
+    int st = apply_structure(o);
+    if (dist && c->zsplit) st = (o->d.diel == PCB_DIEL_CROSSDOF) ? PCB_STRUCT_CROSS7 : PCB_STRUCT_FIVE;      // no peer-memory x passes on split tiles
     if ((mode == PCB_APPLY_H && st != PCB_STRUCT_PLANE) || st == PCB_STRUCT_CROSS5 || st == PCB_STRUCT_CROSS4 || dist)
         for (int j = 0; j < kc; ++j)
             if (cols.in[j] == cols.out[j]) {

@@ -134,7 +134,8 @@ struct PcbOp {
     PcbStencil sten;            // cross-DoF dielectric: its averaging stencil (the fused stencil-on-load of the plane pass)
     int mid_five;               // plane mode: 1 = the five-sweep plane pass (k_mid2), 0 = the seven-sweep one (k_mid)
     const PcbDist* dist;        // large-grid mode over peer memory: slab pointers of the columns (device memory), else null
-    const int* ctab;            // plane mode: [0, N) slot -> grid index (coord), [N, 2N) grid index -> slot
+    const int* ctab;            // plane mode: [0, N) column slot -> grid index (coord), [N, 2N) grid index -> column slot, [2N, 4N) the same for rows
+    int zsplit;                 // plane mode: 1 = z-split form (half planes, ZSplit in pcb_operator.cuh)
     double ediag[3];          // diagonal entries inside Omega_1 (chiral: 1/eps for all three)
     cplx eoff[3];             // eps_12, eps_13, eps_23 (trivial / crossdof)
 };

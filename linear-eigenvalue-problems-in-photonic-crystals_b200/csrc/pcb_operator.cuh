@@ -22,6 +22,7 @@
 // accesses stay contiguous.  Around M the data stays in registers between the last forward and the first inverse radix.
 #pragma once
 #include "pcb_common.cuh"
+#include <type_traits>
 
 #define PCB_MAXC 32   // columns per launch (pointer lists travel in kernel parameter space)
 
@@ -61,6 +62,36 @@ struct Plan {
     PCB_HD static int coord(int s) {
         return PFA ? lout(((s % R1) * U) % R1, ((s % R2) * V) % R2) : (s / R2) + R1 * (s % R2);
     }
+};
+
+// the plan of a grid size by number (pcb_plans.inc): the z-split plane mode needs the plan of N / 2 next to the one of N
+template <int N_>
+struct PlanOf { static constexpr bool ok = false; typedef Plan<N_, N_, 1> type; };
+#define PCB_PLAN(n, r1, r2) template <> struct PlanOf<n> { static constexpr bool ok = true; typedef Plan<n, r1, r2> type; };
+#include "pcb_plans.inc"
+#undef PCB_PLAN
+
+// Z-SPLIT PLANE MODE (ZS = 2; N = 128, 144, 160, where an N x (N+1) plane no longer fits one SM's shared memory): the first
+// radix-2 step of the z transform -- decimation in frequency, pairs (i2', i2' + N/2) -- is done by the forward x pass, whose
+// tiles then hold 4 consecutive i1 of BOTH planes i2' and i2' + N/2:
+//     E_h[i2'] = (x[i2'] + (-1)^h x[i2' + N/2]) w_N^(h i2'),   h = 0, 1,
+// stored at plane row h N/2 + i2' (the position the inputs came from), so that every (i1, i2) plane falls into two independent
+// HALF planes of N/2 x N elements whose z transform has length N/2 (output k' of half h is grid index i2 = 2 k' + h).  The
+// plane pass runs on half planes (one per CTA, N/16 warps, 16 columns per warp in the z steps), and the inverse x pass undoes
+// the split on load: x[i2' + j N/2] = e[i2'] + (-1)^j conj(w_N^i2') o[i2'].  Three passes and 7 column transfers as in plane
+// mode proper, instead of the five passes / 11 transfers these sizes had.  tw: [0, N) twiddles of the plan of N, [N, N + N/2)
+// those of the plan of N/2, [N + N/2, 2N) the split twiddles w_N^n.
+template <class P, int ZS>
+struct ZSplit {
+    static constexpr int N = P::N, NZ = N / ZS;
+    typedef typename PlanOf<NZ>::type PZ;
+    // row r of x tile `tile` (LX rows: LX / ZS consecutive i1 of each of the ZS planes i2' + h NZ) -> i1 + N i2
+    template <int LX> PCB_HD static int row(int tile, int r) {
+        constexpr int LH = LX / ZS;
+        return ZS == 1 ? tile * LX + r : ((tile / (N / LH)) + (r / LH) * NZ) * N + (tile % (N / LH)) * LH + r % LH;
+    }
+    // grid index i2 of plane row rho (= h NZ + slot of the plan of NZ)
+    PCB_HD static int coord_row(int rho) { return ZS == 1 ? P::coord(rho) : ZS * PZ::coord(rho % NZ) + rho / NZ; }
 };
 
 // z = a x v  (cross product, _kernels.py:51-66)
@@ -170,10 +201,14 @@ PCB_D void pcb_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0
 // read here through the IPC-mapped pointers of op.dist (a tile of rows lies in one plane, hence in one rank's slab); the tile is
 // also copied to the local column cols.in[col], which the inverse x pass re-reads for the gamma K_B x + shift x term, so every
 // element crosses NVLink once per direction.  The slab gather of the exchange path is fused into this pass.
-template <class P, int LX, int NT, int SYM, int TRN = 0, int DIST = 0>
+// ZS = 2 (with TRN): z-split plane mode, see ZSplit -- the tile's rows are 4 consecutive i1 of the planes i2' and i2' + N/2, and
+// the radix-2 butterfly of the z transform is applied where the second radix step reads the exchange buffer.
+template <class P, int LX, int NT, int SYM, int TRN = 0, int DIST = 0, int ZS = 1>
 __global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * (P::R1 * P::R2P + TRN) * 16, P::R1, 4)) k_xfwd(PcbOp op, PcbCols cols, const cplx* __restrict__ tw) {
     constexpr int N = P::N, R1 = P::R1, R2 = P::R2, R2P = P::R2P;
     constexpr int RS = R1 * R2P + TRN;      // row stride in shared memory
+    static_assert(ZS == 1 || (TRN == 1 && DIST == 0 && ZS == 2 && LX % 2 == 0 && N % (8 * ZS) == 0), "z-split: plane mode only");
+    typedef ZSplit<P, ZS> ZSP;
     PCB_DYN_SMEM(cplx, sm);   // [3][LX][RS]
     const int col = blockIdx.y;
     const cplx* __restrict__ X = cols.in[col];
@@ -197,7 +232,7 @@ __global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * (P::R1 * P::R2P + TR
 
     for (int item = tid; item < LX * R2; item += NT) {
         const int r = item / R2, n2 = item % R2;
-        const int row = row0 + r;
+        const int row = ZS == 1 ? row0 + r : ZSP::template row<LX>(blockIdx.x, r);
         if (row >= nrows) continue;
         const int i1 = row % N, i2 = row / N;
         cplx v[3][R1];
@@ -252,11 +287,23 @@ __global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * (P::R1 * P::R2P + TR
         const int k1 = TRN ? (item / LX) % R1 : item % R1;
         const int r = TRN ? item % LX : (item / R1) % LX;
         const int c = item / (R1 * LX);
-        const int row = row0 + r;
+        const int row = ZS == 1 ? row0 + r : ZSP::template row<LX>(blockIdx.x, r);
         if (row >= nrows) continue;
         cplx v[R2];
-        PCB_UNROLL
-        for (int n2 = 0; n2 < R2; ++n2) v[n2] = sm[(c * LX + r) * RS + k1 * R2P + n2];
+        if (ZS == 2) {      // E_h = (a + (-1)^h b) w_N^(h i2'): a, b = the rows of the planes i2', i2' + N/2 with this row's i1
+            constexpr int LH = LX / 2;
+            const int ra = r % LH, h = r / LH;
+            const cplx* __restrict__ pa = sm + (c * LX + ra) * RS + k1 * R2P;
+            const cplx wz = h ? __ldg(tw + N + N / 2 + (row / N - N / 2)) : cmake(1.0, 0.0);
+            PCB_UNROLL
+            for (int n2 = 0; n2 < R2; ++n2) {
+                const cplx a = pa[n2], b = pa[LH * RS + n2];
+                v[n2] = h ? cmul(csub(a, b), wz) : cadd(a, b);
+            }
+        } else {
+            PCB_UNROLL
+            for (int n2 = 0; n2 < R2; ++n2) v[n2] = sm[(c * LX + r) * RS + k1 * R2P + n2];
+        }
         Dft<R2, -1>::run(v);
         if (TRN) {      // W'[c][k][i2][i1], k = k1 + R1*k2: consecutive threads = consecutive i1
             cplx* __restrict__ dst = Y + c * nn + (long long)k1 * N * N + row;      // row = i1 + N*i2
@@ -372,10 +419,15 @@ __global__ void __launch_bounds__(NT, 3) k_xfwd2(PcbOp op, PcbCols cols, const c
 #ifndef PCB_XINV_CTAS
 #define PCB_XINV_CTAS 4
 #endif
-template <class P, int LX, int NT, int MODE, int TRN = 0, int DIST = 0>
+// ZS = 2 (with TRN): z-split plane mode (ZSplit) -- tiles as in k_xfwd<.., ZS = 2>; the epilogue recombines the two half planes,
+// x[i2' + j N/2] = e[i2'] + (-1)^j conj(w_N^i2') o[i2'], while it reads the transformed tile.
+template <class P, int LX, int NT, int MODE, int TRN = 0, int DIST = 0, int ZS = 1>
 __global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * (P::R1 * P::R2P + TRN) * 16, P::R1, (TRN ? PCB_XINV_CTAS : 4))) k_xinv(PcbOp op, PcbCols cols, const cplx* __restrict__ tw) {
     constexpr int N = P::N, R1 = P::R1, R2 = P::R2, R2P = P::R2P;
     constexpr int RS = R1 * R2P + TRN;      // row stride in shared memory (see k_xfwd)
+    static_assert(ZS == 1 || (TRN == 1 && DIST == 0 && ZS == 2 && LX % 2 == 0 && N % (8 * ZS) == 0), "z-split: plane mode only");
+    typedef ZSplit<P, ZS> ZSP;
+    constexpr int LH = LX / ZS;             // z-split: the tile is ZS chunks of LH consecutive rows
     PCB_DYN_SMEM(cplx, sm);   // [3][LX][RS]
     const int col = blockIdx.y;
     const cplx* __restrict__ X = cols.in[col];
@@ -397,10 +449,17 @@ __global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * (P::R1 * P::R2P + TR
         Wd = d->dst[col][g] - (long long)d->zb[g] * N * N;
     }
 
-    if (MODE == 2) {   // the epilogue re-reads X: pull this tile's lines (3 contiguous chunks) towards L2 now
+    if (MODE == 2 && ZS == 1) {   // the epilogue re-reads X: pull this tile's lines (3 contiguous chunks) towards L2 now
         const int lines = (nr * N * (int)sizeof(cplx) + 127) / 128;
         for (int l = tid; l < 3 * lines; l += NT)
             pcb_prefetch_l2(reinterpret_cast<const char*>(X + (l / lines) * nn + (long long)row0 * N) + (l % lines) * 128);
+    }
+    if (MODE == 2 && ZS == 2) {   // ... 3 x ZS chunks of LH rows
+        constexpr int lines = (LH * N * (int)sizeof(cplx) + 127) / 128;
+        for (int l = tid; l < 3 * ZS * lines; l += NT) {
+            const int ch = l / lines;
+            pcb_prefetch_l2(reinterpret_cast<const char*>(X + (ch / ZS) * nn + (long long)ZSP::template row<LX>(blockIdx.x, (ch % ZS) * LH) * N) + (l % lines) * 128);
+        }
     }
     // inverse radix R2 over k2 (fixed k1): global (Fourier order, k = k1 + R1*k2) -> registers -> shared
     for (int item = tid; item < 3 * LX * R1; item += NT) {
@@ -411,7 +470,7 @@ __global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * (P::R1 * P::R2P + TR
         if (r >= nr) continue;
         cplx v[R2];
         if (TRN) {
-            const cplx* __restrict__ src = WT + c * nn + (long long)k1 * N * N + (row0 + r);
+            const cplx* __restrict__ src = WT + c * nn + (long long)k1 * N * N + (ZS == 1 ? row0 + r : ZSP::template row<LX>(blockIdx.x, r));
             PCB_UNROLL
             for (int k2 = 0; k2 < R2; ++k2) v[k2] = src[(long long)R1 * k2 * N * N];
         } else {
@@ -442,6 +501,10 @@ __global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * (P::R1 * P::R2P + TR
     __syncthreads();
     // point-wise epilogue, fully coalesced: 1/N^3, k x v, (+ gamma conj(k)(k.x) + shift x), store
     constexpr int PB = 4;     // points per thread and batch: all X loads of a batch are issued before they are used
+    // global position of tile element e (row-major over the tile's rows): contiguous from row0 N, or ZS chunks of LH rows
+    auto gpos = [&](int e) -> long long {
+        return ZS == 1 ? (long long)row0 * N + e : (long long)ZSP::template row<LX>(blockIdx.x, (e / (LH * N)) * LH) * N + e % (LH * N);
+    };
     for (int e0 = tid; e0 < nr * N; e0 += PB * NT) {
         cplx x[PB][3];
         if (MODE == 2) {
@@ -449,8 +512,9 @@ __global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * (P::R1 * P::R2P + TR
             for (int q = 0; q < PB; ++q) {
                 const int e = e0 + q * NT;
                 if (e < nr * N) {
+                    const long long g = gpos(e);
                     PCB_UNROLL
-                    for (int c = 0; c < 3; ++c) x[q][c] = X[c * nn + (long long)row0 * N + e];
+                    for (int c = 0; c < 3; ++c) x[q][c] = X[c * nn + g];
                 }
             }
         }
@@ -459,11 +523,19 @@ __global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * (P::R1 * P::R2P + TR
             const int e = e0 + q * NT;
             if (e >= nr * N) continue;
             const int r = e / N, i0 = e % N;
-            const int row = row0 + r;
-            const int slot = r * RS + (i0 / R2) * R2P + i0 % R2;
+            const int row = ZS == 1 ? row0 + r : ZSP::template row<LX>(blockIdx.x, r);
+            const int slot = (ZS == 1 ? r : r % LH) * RS + (i0 / R2) * R2P + i0 % R2;
             cplx u[3], z[3];
-            PCB_UNROLL
-            for (int c = 0; c < 3; ++c) u[c] = cscale(sm[c * LX * RS + slot], op.inv_n3);
+            if (ZS == 2) {      // x[i2' + j N/2] = e + (-1)^j conj(w_N^i2') o
+                const int j = r / LH;
+                const cplx t = __ldg(tw + N + N / 2 + (row / N - j * (N / 2)));
+                const cplx wc = j ? cmake(-t.x, t.y) : cmake(t.x, -t.y);
+                PCB_UNROLL
+                for (int c = 0; c < 3; ++c) u[c] = cscale(cfma(wc, sm[(c * LX + LH) * RS + slot], sm[c * LX * RS + slot]), op.inv_n3);
+            } else {
+                PCB_UNROLL
+                for (int c = 0; c < 3; ++c) u[c] = cscale(sm[c * LX * RS + slot], op.inv_n3);
+            }
             if (MODE) {
                 const Sym3 sy = pcb_symbol(op.T, N, i0, row % N, row / N);
                 pcb_cross(sy.k, u, z);
@@ -483,8 +555,9 @@ __global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * (P::R1 * P::R2P + TR
                 PCB_UNROLL
                 for (int c = 0; c < 3; ++c) z[c] = u[c];
             }
+            const long long g = gpos(e);
             PCB_UNROLL
-            for (int c = 0; c < 3; ++c) Wd[c * cs + (long long)row0 * N + e] = z[c];
+            for (int c = 0; c < 3; ++c) Wd[c * cs + g] = z[c];
         }
     }
 }
@@ -870,17 +943,20 @@ __global__ void __launch_bounds__(NT, (NT > 256 ? 1 : 2)) k_zmid(PcbOp op, PcbCo
 
 // Plane mode set-up (once per dielectric): mbits[c][i0][slot][k1], bit k2 = "component c of grid point
 // (i0, i1 = coord(slot), i2 = lout(k1, k2)) lies in Omega_1" -- exactly the 15 (R2) flags one radix-R2 item of k_mid needs.
-template <class P>
+template <class P, int ZS = 1>
 __global__ void k_mask_bits(PcbOp op, unsigned* __restrict__ out) {
-    constexpr int N = P::N, R1 = P::R1, R2 = P::R2;
-    const long long total = 3LL * N * N * R1;
+    // z-split (ZS = 2): mbits[c][i0][slot][h][k1], bit k2 = (i0, i1 = coord(slot), i2 = ZS lout_z(k1, k2) + h), digits of the plan of N / ZS
+    typedef typename ZSplit<P, ZS>::PZ PZ;
+    constexpr int N = P::N, R1 = PZ::R1, R2 = PZ::R2;
+    const long long total = 3LL * N * N * ZS * R1;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total) return;
-    const int k1 = (int)(t % R1), slot = (int)((t / R1) % N), i0 = (int)((t / ((long long)R1 * N)) % N), c = (int)(t / ((long long)R1 * N * N));
-    const int i1 = P::coord(slot), o1 = P::lout1(k1);
+    const int k1 = (int)(t % R1), h = (int)((t / R1) % ZS), slot = (int)((t / (R1 * ZS)) % N), i0 = (int)((t / ((long long)R1 * ZS * N)) % N),
+              c = (int)(t / ((long long)R1 * ZS * N * N));
+    const int i1 = P::coord(slot), o1 = PZ::lout1(k1);
     unsigned w = 0u;
     for (int k2 = 0; k2 < R2; ++k2) {
-        const int i2 = P::wrap(o1 + P::lout2(k2));
+        const int i2 = ZS * PZ::wrap(o1 + PZ::lout2(k2)) + h;
         w |= ((unsigned)(op.mask[((long long)i2 * N + i1) * N + i0] >> c) & 1u) << k2;
     }
     out[t] = w;
@@ -943,7 +1019,7 @@ PCB_D cplx pcb_crossdof_couple(const PcbOp& op, int c, const int i[3], unsigned 
             int qc = i[cax] + oc;
             qc += (qc < 0) ? N : 0; qc -= (qc >= N) ? N : 0;
             // slot-layout position contributed by the c-axis index (axis 0: plane, 1: column, 2: row)
-            const int pc = cax == 0 ? qc * (N * N) : (cax == 1 ? __ldg(ctab + N + qc) : __ldg(ctab + N + qc) * N);
+            const int pc = cax == 0 ? qc * (N * N) : (cax == 1 ? __ldg(ctab + N + qc) : __ldg(ctab + 3 * N + qc) * N);
 #ifndef PCB_EMU
 #pragma unroll
 #endif
@@ -951,10 +1027,10 @@ PCB_D cplx pcb_crossdof_couple(const PcbOp& op, int c, const int i[3], unsigned 
                 const int ot = first ? -(1 - kk + j2) : 1 - kk + j2;
                 int qt = i[tax] + ot;
                 qt += (qt < 0) ? N : 0; qt -= (qt >= N) ? N : 0;
-                const int pt = tax == 0 ? qt * (N * N) : (tax == 1 ? __ldg(ctab + N + qt) : __ldg(ctab + N + qt) * N);
+                const int pt = tax == 0 ? qt * (N * N) : (tax == 1 ? __ldg(ctab + N + qt) : __ldg(ctab + 3 * N + qt) * N);
                 // the third axis keeps the point's own index
                 const int rest = 3 - cax - tax;
-                const int po = rest == 0 ? i[0] * (N * N) : (rest == 1 ? __ldg(ctab + N + i[1]) : __ldg(ctab + N + i[2]) * N);
+                const int po = rest == 0 ? i[0] * (N * N) : (rest == 1 ? __ldg(ctab + N + i[1]) : __ldg(ctab + 3 * N + i[2]) * N);
                 const int qs = pc + pt + po;
                 const double w = op.sten.w[j1] * op.sten.w[j2] * 0.5;
                 const unsigned mq = live ? (unsigned)__ldg(maskp + qs) : 0u;
@@ -985,19 +1061,27 @@ PCB_D cplx pcb_crossdof_couple(const PcbOp& op, int c, const int i[3], unsigned 
 // real-space planes of the other components in cols.out (same or neighbouring i0; L2 hits, the planes of a wave of CTAs are
 // adjacent).  Four kernels, 9 column transfers instead of five kernels / 11.  STEN = 2 * K + 1 encodes the stencil half-width
 // K at compile time (K = 1, 2), STEN = 1 reads it from op.sten.
-template <class P, int DIEL, int TMA = 0, int HALF = 0, int STEN = 0>
-__global__ void __launch_bounds__(P::N / 8 * 32, 1) k_mid(PcbOp op, PcbCols cols, const cplx* __restrict__ tw, int ncols) {
+// ZS = 2: z-split plane mode (ZSplit) -- the CTA holds a HALF plane of NZ = N/2 rows (plane rows h NZ .. h NZ + NZ - 1) and N
+// columns; NZ / 8 warps own 8 rows each in the y steps (plan of N) and CW = 16 columns each in the z steps (plan PZ of N/2,
+// twiddles at tw + N); the z output (k1, k2) of half h is grid index i2 = 2 lout_z(k1, k2) + h.
+template <class P, int DIEL, int TMA = 0, int HALF = 0, int STEN = 0, int ZS = 1>
+__global__ void __launch_bounds__(P::N / ZS / 8 * 32, 1) k_mid(PcbOp op, PcbCols cols, const cplx* __restrict__ tw, int ncols) {
+    typedef typename ZSplit<P, ZS>::PZ PZ;
     constexpr int N = P::N, R1 = P::R1, R2 = P::R2;
+    constexpr int NZ = N / ZS, ZR1 = PZ::R1, ZR2 = PZ::R2;      // rows of the CTA's (half) plane and the radices of the z transform
+    constexpr int NW = NZ / 8, CW = N / NW;                     // warps; columns a warp owns in the z steps
     constexpr int LD = N + 1;                    // row stride (complex)
     constexpr bool FWD = HALF != 2, INV = HALF != 1;
-    static_assert(N % 8 == 0, "plane mode needs N % 8 == 0");
+    static_assert(N % 8 == 0 && NZ % 8 == 0 && N % NW == 0, "plane mode needs N % 8 == 0 (z-split: N % 16 == 0)");
     static_assert(HALF == 0 || DIEL == 0, "the half passes carry no dielectric");
-    PCB_DYN_SMEM(cplx, pl);   // [N rows i2][LD] (+ one mbarrier per warp behind it when TMA)
+    static_assert(ZS == 1 || DIEL != 2, "z-split plane mode: no cluster form of the coupled dielectric");
+    const cplx* __restrict__ twz = ZS == 1 ? tw : tw + N;      // twiddles of the z plan
+    PCB_DYN_SMEM(cplx, pl);   // [NZ rows][LD] (+ one mbarrier per warp behind it when TMA)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long nn = op.nn;
     cplx* __restrict__ myrows = pl + (8 * warp) * LD;
 #ifndef PCB_EMU
-    unsigned long long* mybar = reinterpret_cast<unsigned long long*>(pl + (size_t)N * LD) + warp;
+    unsigned long long* mybar = reinterpret_cast<unsigned long long*>(pl + (size_t)NZ * LD) + warp;
     unsigned phase = 0;
     if (TMA) {
         if (lane == 0) { pcb_mbar_init(mybar, 1); pcb_fence_mbar_init(); }
@@ -1005,7 +1089,7 @@ __global__ void __launch_bounds__(P::N / 8 * 32, 1) k_mid(PcbOp op, PcbCols cols
     }
 #endif
     // plane enumeration: (column, component, i0) over the CTAs, or (column, i0) over the clusters with the component = cluster rank
-    int first = blockIdx.x, stride = gridDim.x, total = 3 * N * ncols, crank = 0;
+    int first = blockIdx.x, stride = gridDim.x, total = 3 * N * ZS * ncols, crank = 0;
 #ifndef PCB_EMU
     unsigned pbase[3] = {0u, 0u, 0u};
     double inv_d[3] = {1.0, 1.0, 1.0};
@@ -1017,8 +1101,9 @@ __global__ void __launch_bounds__(P::N / 8 * 32, 1) k_mid(PcbOp op, PcbCols cols
 #endif
 
     for (int pid = first; pid < total; pid += stride) {
-        const int col = (DIEL == 2) ? pid / N : pid / (3 * N), c = (DIEL == 2) ? crank : (pid / N) % 3, i0 = pid % N;
-        const long long poff = c * nn + (long long)i0 * N * N + (long long)(8 * warp) * N;      // this warp's 8 rows
+        const int col = (DIEL == 2) ? pid / N : pid / (3 * N * ZS), c = (DIEL == 2) ? crank : (pid / (N * ZS)) % 3, i0 = (pid / ZS) % N;
+        const int hz = ZS == 1 ? 0 : pid % ZS, prow = hz * NZ + 8 * warp;      // half plane; first plane row of this warp
+        const long long poff = c * nn + (long long)i0 * N * N + (long long)prow * N;      // this warp's 8 rows
         cplx* __restrict__ base = ((STEN && HALF == 1) ? cols.out[col] : cols.wrk[col]) + poff;
         const cplx* __restrict__ src = (HALF == 2) ? cols.out[col] + poff : cols.wrk[col] + poff;
         // ---- load own rows (contiguous 8*N elements) ----
@@ -1038,18 +1123,18 @@ __global__ void __launch_bounds__(P::N / 8 * 32, 1) k_mid(PcbOp op, PcbCols cols
         }
         // dielectric bits this lane needs in the z step (items it = lane + 32 q: slot 8w + it%8, digit k1 = it/8): one precomputed
         // word per item (k_mask_bits), fetched now so that its latency hides behind the row loads
-        constexpr int ZI = (8 * R1 + 31) / 32;
+        constexpr int ZI = (CW * ZR1 + 31) / 32;
         unsigned mbits[ZI];
         if (DIEL >= 1) {
             PCB_UNROLL
             for (int q = 0; q < ZI; ++q) {
                 const int it = lane + 32 * q;
-                mbits[q] = (it < 8 * R1) ? __ldg(op.mbits + (((long long)c * N + i0) * N + 8 * warp + it % 8) * R1 + it / 8) : 0u;
+                mbits[q] = (it < CW * ZR1) ? __ldg(op.mbits + (((((long long)c * N + i0) * N + CW * warp + it % CW) * ZS + hz) * ZR1 + it / CW)) : 0u;
             }
         }
         // coupled dielectric: mask bytes of this thread's points in step (B), point e = threadIdx.x + q * blockDim.x of the CTA's
         // third of the rows -- also fetched here, ten independent loads whose latency the plane's transforms hide
-        constexpr int NTHR = N / 8 * 32, PBQ = (DIEL == 2) ? ((N + 2) / 3 * N + NTHR - 1) / NTHR : 1;
+        constexpr int NTHR = NW * 32, PBQ = (DIEL == 2) ? ((N + 2) / 3 * N + NTHR - 1) / NTHR : 1;
         unsigned pmask[(PBQ + 3) / 4];
         int prow0 = 0, pcnt = 0;
         if (DIEL == 2) {
@@ -1071,19 +1156,20 @@ __global__ void __launch_bounds__(P::N / 8 * 32, 1) k_mid(PcbOp op, PcbCols cols
         __syncwarp();
         if (STEN && HALF == 2) {
             // ---- M on own rows (real space): diagonal, and the cross-DoF coupling gathered from the other components' planes ----
-            const unsigned char* __restrict__ mrow = op.maskp + ((long long)i0 * N + 8 * warp) * N;
+            const unsigned char* __restrict__ mrow = op.maskp + ((long long)i0 * N + prow) * N;
             const cplx* __restrict__ Xcol = cols.out[col];
             const int* __restrict__ ctab = op.ctab;
             // pass 1: the diagonal entry, and a bit per element of this lane that has a coupling term (k_mask_active)
-            static_assert(8 * N <= 32 * 32, "one bit per element of a lane");
-            unsigned actbits = 0u;
+            static_assert(8 * N <= 32 * 64, "one bit per element of a lane");
+            typedef typename std::conditional<(8 * N > 32 * 32), unsigned long long, unsigned>::type abits_t;
+            abits_t actbits = 0u;
             PCB_UNROLL
             for (int q = 0; q < (8 * N + 31) / 32; ++q) {
                 const int e = lane + 32 * q;
                 if (e < 8 * N) {
                     const unsigned mk = __ldg(mrow + e);
                     if ((mk >> c) & 1u) { cplx* pv = myrows + (e / N) * LD + e % N; *pv = cscale(*pv, op.ediag[c]); }
-                    actbits |= ((mk >> (4 + c)) & 1u) << q;
+                    actbits |= (abits_t)((mk >> (4 + c)) & 1u) << q;
                 }
             }
             // pass 2: the coupled elements, GB at a time -- the gathers of a batch (taps of the other components' planes, L2) are all
@@ -1097,14 +1183,14 @@ __global__ void __launch_bounds__(P::N / 8 * 32, 1) k_mid(PcbOp op, PcbCols cols
                 PCB_UNROLL
                 for (int u = 0; u < GB; ++u) {
                     ok[u] = actbits != 0u;
-                    const int q = ok[u] ? __ffs((int)actbits) - 1 : 0;
-                    actbits &= actbits - 1u;
+                    const int q = ok[u] ? (sizeof(abits_t) == 8 ? __ffsll((long long)actbits) : __ffs((int)actbits)) - 1 : 0;
+                    actbits &= actbits - (abits_t)1;
                     eq[u] = lane + 32 * q;
                 }
                 PCB_UNROLL
                 for (int u = 0; u < GB; ++u) {
                     const int rl = eq[u] / N, cl = eq[u] % N;
-                    const int ii[3] = {i0, __ldg(ctab + cl), __ldg(ctab + 8 * warp + rl)};
+                    const int ii[3] = {i0, __ldg(ctab + cl), __ldg(ctab + 2 * N + prow + rl)};
                     const unsigned mk = ok[u] ? (unsigned)__ldg(mrow + eq[u]) : 0u;
                     add[u] = pcb_crossdof_couple<N, (STEN - 1) / 2>(op, c, ii, mk, Xcol, ok[u]);
                 }
@@ -1143,21 +1229,21 @@ __global__ void __launch_bounds__(P::N / 8 * 32, 1) k_mid(PcbOp op, PcbCols cols
             }
         }
         __syncthreads();
-        // ---- z on own slots (columns 8w .. 8w+7): lanes = (slot fastest, digit) ----
-        cplx* __restrict__ mycols = pl + 8 * warp;
+        // ---- z on own slots (columns CW w .. CW w + CW - 1): lanes = (slot fastest, digit) ----
+        cplx* __restrict__ mycols = pl + CW * warp;
         if (FWD) {
-            for (int it = lane; it < 8 * R2; it += 32) {
-                cplx* __restrict__ cp = mycols + it % 8;
-                const int n2 = it / 8, b2 = P::lin2(n2);
-                cplx v[R1];
+            for (int it = lane; it < CW * ZR2; it += 32) {
+                cplx* __restrict__ cp = mycols + it % CW;
+                const int n2 = it / CW, b2 = PZ::lin2(n2);
+                cplx v[ZR1];
                 PCB_UNROLL
-                for (int n1 = 0; n1 < R1; ++n1) v[n1] = cp[P::wrap(P::lin1(n1) + b2) * LD];
-                Dft<R1, -1>::run(v);
+                for (int n1 = 0; n1 < ZR1; ++n1) v[n1] = cp[PZ::wrap(PZ::lin1(n1) + b2) * LD];
+                Dft<ZR1, -1>::run(v);
                 PCB_UNROLL
-                for (int k1 = 0; k1 < R1; ++k1) {
+                for (int k1 = 0; k1 < ZR1; ++k1) {
                     cplx val = v[k1];
-                    if (!P::PFA && k1 > 0) val = cmul(val, __ldg(tw + k1 * R2 + n2));
-                    cp[P::wrap(P::lin1(k1) + b2) * LD] = val;
+                    if (!PZ::PFA && k1 > 0) val = cmul(val, __ldg(twz + k1 * ZR2 + n2));
+                    cp[PZ::wrap(PZ::lin1(k1) + b2) * LD] = val;
                 }
             }
             __syncwarp();
@@ -1167,25 +1253,25 @@ __global__ void __launch_bounds__(P::N / 8 * 32, 1) k_mid(PcbOp op, PcbCols cols
             PCB_UNROLL
             for (int q = 0; q < ZI; ++q) {
                 const int it = lane + 32 * q;
-                if (it >= 8 * R1) break;
-                cplx* __restrict__ cp = mycols + it % 8;
-                const int k1 = it / 8, b1 = P::lin1(k1);
-                cplx v[R2];
+                if (it >= CW * ZR1) break;
+                cplx* __restrict__ cp = mycols + it % CW;
+                const int k1 = it / CW, b1 = PZ::lin1(k1);
+                cplx v[ZR2];
                 PCB_UNROLL
-                for (int n2 = 0; n2 < R2; ++n2) v[n2] = cp[P::wrap(b1 + P::lin2(n2)) * LD];
-                Dft<R2, -1>::run(v);
+                for (int n2 = 0; n2 < ZR2; ++n2) v[n2] = cp[PZ::wrap(b1 + PZ::lin2(n2)) * LD];
+                Dft<ZR2, -1>::run(v);
                 if (DIEL == 1) {
                     const double scl = op.ediag[c];
                     const unsigned w = mbits[q];
                     PCB_UNROLL
-                    for (int k2 = 0; k2 < R2; ++k2) v[k2] = cscale(v[k2], ((w >> k2) & 1u) ? scl : 1.0);   // branch-free: no divergence
+                    for (int k2 = 0; k2 < ZR2; ++k2) v[k2] = cscale(v[k2], ((w >> k2) & 1u) ? scl : 1.0);   // branch-free: no divergence
                 }
-                Dft<R2, +1>::run(v);
+                Dft<ZR2, +1>::run(v);
                 PCB_UNROLL
-                for (int n2 = 0; n2 < R2; ++n2) {
+                for (int n2 = 0; n2 < ZR2; ++n2) {
                     cplx val = v[n2];
-                    if (!P::PFA && k1 > 0) { const cplx t = __ldg(tw + k1 * R2 + n2); val = cmul(val, cmake(t.x, -t.y)); }
-                    cp[P::wrap(b1 + P::lin2(n2)) * LD] = val;
+                    if (!PZ::PFA && k1 > 0) { const cplx t = __ldg(twz + k1 * ZR2 + n2); val = cmul(val, cmake(t.x, -t.y)); }
+                    cp[PZ::wrap(b1 + PZ::lin2(n2)) * LD] = val;
                 }
             }
         } else {
@@ -1193,21 +1279,21 @@ __global__ void __launch_bounds__(P::N / 8 * 32, 1) k_mid(PcbOp op, PcbCols cols
                 PCB_UNROLL
                 for (int q = 0; q < ZI; ++q) {
                     const int it = lane + 32 * q;
-                    if (it >= 8 * R1) break;
-                    cplx* __restrict__ cp = mycols + it % 8;
-                    const int b1 = P::lin1(it / 8);
-                    cplx v[R2];
+                    if (it >= CW * ZR1) break;
+                    cplx* __restrict__ cp = mycols + it % CW;
+                    const int b1 = PZ::lin1(it / CW);
+                    cplx v[ZR2];
                     PCB_UNROLL
-                    for (int n2 = 0; n2 < R2; ++n2) v[n2] = cp[P::wrap(b1 + P::lin2(n2)) * LD];
-                    Dft<R2, -1>::run(v);
+                    for (int n2 = 0; n2 < ZR2; ++n2) v[n2] = cp[PZ::wrap(b1 + PZ::lin2(n2)) * LD];
+                    Dft<ZR2, -1>::run(v);
                     if (DIEL == 2) {
                         const double scl = op.ediag[c];
                         const unsigned w = mbits[q];
                         PCB_UNROLL
-                        for (int k2 = 0; k2 < R2; ++k2) v[k2] = cscale(v[k2], ((w >> k2) & 1u) ? scl : 1.0);
+                        for (int k2 = 0; k2 < ZR2; ++k2) v[k2] = cscale(v[k2], ((w >> k2) & 1u) ? scl : 1.0);
                     }
                     PCB_UNROLL
-                    for (int k2 = 0; k2 < R2; ++k2) cp[P::wrap(b1 + P::lin2(k2)) * LD] = v[k2];
+                    for (int k2 = 0; k2 < ZR2; ++k2) cp[PZ::wrap(b1 + PZ::lin2(k2)) * LD] = v[k2];
                 }
             }
 #ifndef PCB_EMU
@@ -1234,33 +1320,33 @@ __global__ void __launch_bounds__(P::N / 8 * 32, 1) k_mid(PcbOp op, PcbCols cols
                 PCB_UNROLL
                 for (int q = 0; q < ZI; ++q) {
                     const int it = lane + 32 * q;
-                    if (it >= 8 * R1) break;
-                    cplx* __restrict__ cp = mycols + it % 8;
-                    const int k1 = it / 8, b1 = P::lin1(k1);
-                    cplx v[R2];
+                    if (it >= CW * ZR1) break;
+                    cplx* __restrict__ cp = mycols + it % CW;
+                    const int k1 = it / CW, b1 = PZ::lin1(k1);
+                    cplx v[ZR2];
                     PCB_UNROLL
-                    for (int k2 = 0; k2 < R2; ++k2) v[k2] = cp[P::wrap(b1 + P::lin2(k2)) * LD];
-                    Dft<R2, +1>::run(v);
+                    for (int k2 = 0; k2 < ZR2; ++k2) v[k2] = cp[PZ::wrap(b1 + PZ::lin2(k2)) * LD];
+                    Dft<ZR2, +1>::run(v);
                     PCB_UNROLL
-                    for (int n2 = 0; n2 < R2; ++n2) {
+                    for (int n2 = 0; n2 < ZR2; ++n2) {
                         cplx val = v[n2];
-                        if (!P::PFA && k1 > 0) { const cplx t = __ldg(tw + k1 * R2 + n2); val = cmul(val, cmake(t.x, -t.y)); }
-                        cp[P::wrap(b1 + P::lin2(n2)) * LD] = val;
+                        if (!PZ::PFA && k1 > 0) { const cplx t = __ldg(twz + k1 * ZR2 + n2); val = cmul(val, cmake(t.x, -t.y)); }
+                        cp[PZ::wrap(b1 + PZ::lin2(n2)) * LD] = val;
                     }
                 }
             }
         }
         if (INV) {
             __syncwarp();
-            for (int it = lane; it < 8 * R2; it += 32) {
-                cplx* __restrict__ cp = mycols + it % 8;
-                const int n2 = it / 8, b2 = P::lin2(n2);
-                cplx v[R1];
+            for (int it = lane; it < CW * ZR2; it += 32) {
+                cplx* __restrict__ cp = mycols + it % CW;
+                const int n2 = it / CW, b2 = PZ::lin2(n2);
+                cplx v[ZR1];
                 PCB_UNROLL
-                for (int k1 = 0; k1 < R1; ++k1) v[k1] = cp[P::wrap(P::lin1(k1) + b2) * LD];
-                Dft<R1, +1>::run(v);
+                for (int k1 = 0; k1 < ZR1; ++k1) v[k1] = cp[PZ::wrap(PZ::lin1(k1) + b2) * LD];
+                Dft<ZR1, +1>::run(v);
                 PCB_UNROLL
-                for (int n1 = 0; n1 < R1; ++n1) cp[P::wrap(P::lin1(n1) + b2) * LD] = v[n1];
+                for (int n1 = 0; n1 < ZR1; ++n1) cp[PZ::wrap(PZ::lin1(n1) + b2) * LD] = v[n1];
             }
         }
         __syncthreads();
@@ -1702,22 +1788,26 @@ __global__ void __launch_bounds__(Mid2<P>::NTHR, 1) k_mid2(PcbOp op, PcbCols col
 // says the plane pass does not wait for its rows; it waits for dependent FP64 issue and the two CTA barriers around sweep C.)
 // Plane-mode set-up for the coupled dielectric: the byte mask (bit c: edge DoF of component c, bit 3: volume DoF in Omega_1)
 // in the slot order of the plane pass, maskp[i0][row][col] = mask(i0, i1 = coord(col), i2 = coord(row)).
-template <class P>
+template <class P, int ZS = 1>
 __global__ void k_mask_plane(PcbOp op, unsigned char* __restrict__ out) {
     constexpr int N = P::N;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)N * N * N) return;
     const int col = (int)(t % N), row = (int)((t / N) % N), i0 = (int)(t / ((long long)N * N));
-    out[t] = op.mask[((long long)P::coord(row) * N + P::coord(col)) * N + i0];
+    out[t] = op.mask[((long long)ZSplit<P, ZS>::coord_row(row) * N + P::coord(col)) * N + i0];
 }
-// slot <-> index tables of the plan: tab[s] = coord(s), tab[N + coord(s)] = s  (the real-space stencil on plane-slot order)
-template <class P>
+// slot <-> index tables of the plane layout (the real-space stencil on plane-slot order): columns tab[s] = coord(s),
+// tab[N + coord(s)] = s; rows tab[2N + rho] = coord_row(rho), tab[3N + coord_row(rho)] = rho (equal to the column tables
+// except in the z-split plane mode, where row rho = h N/2 + s holds i2 = 2 coord_z(s) + h)
+template <class P, int ZS = 1>
 __global__ void k_coord_tables(int* __restrict__ tab) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= P::N) return;
-    const int i = P::coord(s);
+    const int i = P::coord(s), j = ZSplit<P, ZS>::coord_row(s);
     tab[s] = i;
     tab[P::N + i] = s;
+    tab[2 * P::N + s] = j;
+    tab[3 * P::N + j] = s;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1730,6 +1820,8 @@ struct PcbOpLaunch {
     int plane_coupled; // 1: ... also for the coupled 3x3 dielectric (clusters of three CTAs; CUDA build only)
     int plane_five;    // 1: the five-sweep form of the plane pass (k_mid2) exists: N = 8 R2, R2 odd
     int lx;            // rows per tile of the x passes (a tile must lie in one i2 plane for the peer-memory passes: N % lx == 0)
+    int plane_split;   // z-split plane mode (half planes): 0 not available, 1 selectable, 2 the plane mode of this size
+    int zr1, zr2;      // ... radices of its z plan (the plan of N / 2)
     // mode: 0 plain 3-D FFT forward, 1 plain inverse (1/N^3), 2 A = AMA^H, 3 H = AMA^H + gamma B^H B + shift
     int (*apply)(const PcbOp& op, const PcbCols& cols, int ncols, int mode, const cplx* tw, cudaStream_t s, int sms);
     // split passes used by the cross-DoF dielectric and by the tests: pass ids below

@@ -82,6 +82,9 @@ inline int ctas_per_sm(int smem, int regs_hint_threads) {
 // plane mode: N % 8 == 0, tiles of 8 rows must not straddle an i2 plane, and N x (N+1) complex fit in one CTA's shared memory
 constexpr bool kPlane = (P::N % 8 == 0) && (LX == 8) && ((long long)P::N * (P::N + 1) * 16 <= 232448);
 constexpr int kSmemMid = P::N * (P::N + 1) * (int)sizeof(cplx);
+// z-split plane mode (half planes of N/2 x N; ZSplit in pcb_operator.cuh): N % 16 == 0, a plan for N/2, the half plane fits.  The only
+// plane mode of N = 128, 144, 160; selectable (PCB200_PLANE_SPLIT=1 / pcb_ctx_set "plane_split") for the smaller sizes as well
+constexpr bool kPlaneSplit = (P::N % 16 == 0) && (LX == 8) && PlanOf<P::N / 2>::ok && ((long long)(P::N / 2) * (P::N + 1) * 16 + 128 <= 232448);
 constexpr bool kPlaneFive = kPlane && Mid2<P>::OK;
 #ifdef PCB_EMU
 constexpr bool kPlaneCoupled = false;      // thread-block clusters are not emulated: the coupled dielectric keeps the five-pass path there
@@ -205,100 +208,151 @@ struct XFwd2<true, PP> {
     }
 };
 
+// coupled 3x3 M on clusters of three CTAs / peer-memory x passes: full planes only (not in the z-split plane mode)
+template <bool OK, class PP>
+struct Coupled {
+    static int go(const PcbOp&, const PcbCols&, int, int, const cplx*, cudaStream_t, int) {
+        pcb_set_error("plane mode: no cluster form of the coupled dielectric for N = %d", PP::N);
+        return -1;
+    }
+};
+#ifndef PCB_EMU
+template <class PP>
+struct Coupled<true, PP> {
+    static int go(const PcbOp& op, const PcbCols& cols, int ncols, int pass_id, const cplx* tw, cudaStream_t s, int sms) {
+        if (kPlaneFive && op.mid_five && op.mbits2 != nullptr && op.maskp2 != nullptr)
+            return PlaneFive<kPlaneFive, PP>::go(op, cols, ncols, pass_id, tw, s, sms);
+        return launch_cluster3(k_mid<PP, 2, 1, 0, 0, 1>, PP::N / 8 * 32, kSmemMid + 128, PP::N * ncols, op, cols, tw, ncols, s, sms, PP::N);
+    }
+};
+#endif
+template <bool OK, class PP>
+struct XDist {
+    static int go(const PcbOp&, const PcbCols&, int, int, const cplx*, cudaStream_t) {
+        pcb_set_error("z-split plane mode has no peer-memory x passes (N = %d)", PP::N);
+        return -1;
+    }
+};
+template <class PP>
+struct XDist<true, PP> {
+    static int go(const PcbOp& op, const PcbCols& cols, int ncols, int pass_id, const cplx* tw, cudaStream_t s) {
+        if (pass_id == PCB_PASS_XFWD_SYM_TD) PCB_GO((k_xfwd<PP, LX, NT, 1, 1, 1>), GX, kStageXT);
+        else if (pass_id == PCB_PASS_XINV_A_TD) PCB_GO((k_xinv<PP, LX, NT, 1, 1, 1>), GX, kStageXT);
+        else PCB_GO((k_xinv<PP, LX, NT, 2, 1, 1>), GX, kStageXT);
+        return 0;
+    }
+};
+
 // plane-mode passes exist only for sizes with kPlane (the kernels are not even instantiated otherwise)
-template <bool ENABLED, class PP>
+template <bool ENABLED, class PP, int ZS>
 struct PlanePass {
     static int go(const PcbOp&, const PcbCols&, int, int, const cplx*, cudaStream_t, int) {
         pcb_set_error("plane mode is not available for N = %d", PP::N);
         return -1;
     }
 };
-template <class PP>
-struct PlanePass<true, PP> {
+template <class PP, int ZS>
+struct PlanePass<true, PP, ZS> {
     static int go(const PcbOp& op, const PcbCols& cols, int ncols, int pass_id, const cplx* tw, cudaStream_t s, int sms) {
+        constexpr int kSmemMidZ = PP::N / ZS * (PP::N + 1) * (int)sizeof(cplx);
         if (pass_id == PCB_PASS_MASKBITS) {
-            const long long total = 3LL * PP::N * PP::N * PP::R1;
-            PCB_LAUNCH((k_mask_bits<PP>), dim3((unsigned)((total + 255) / 256), 1, 1), dim3(256, 1, 1), 0, s, op, const_cast<unsigned*>(op.mbits));
+            const long long total = 3LL * PP::N * PP::N * ZS * ZSplit<PP, ZS>::PZ::R1;
+            PCB_LAUNCH((k_mask_bits<PP, ZS>), dim3((unsigned)((total + 255) / 256), 1, 1), dim3(256, 1, 1), 0, s, op, const_cast<unsigned*>(op.mbits));
             PCB_CUDA_OK(cudaGetLastError());
             return 0;
         }
         if (pass_id == PCB_PASS_MASKPLANE) {
             const long long total = (long long)PP::N * PP::N * PP::N;
-            PCB_LAUNCH((k_mask_plane<PP>), dim3((unsigned)((total + 255) / 256), 1, 1), dim3(256, 1, 1), 0, s, op, const_cast<unsigned char*>(op.maskp));
+            PCB_LAUNCH((k_mask_plane<PP, ZS>), dim3((unsigned)((total + 255) / 256), 1, 1), dim3(256, 1, 1), 0, s, op, const_cast<unsigned char*>(op.maskp));
             PCB_CUDA_OK(cudaGetLastError());
             return 0;
         }
         if (pass_id == PCB_PASS_COORDTAB) {
-            PCB_LAUNCH((k_coord_tables<PP>), dim3((unsigned)((PP::N + 127) / 128), 1, 1), dim3(128, 1, 1), 0, s, const_cast<int*>(op.ctab));
+            PCB_LAUNCH((k_coord_tables<PP, ZS>), dim3((unsigned)((PP::N + 127) / 128), 1, 1), dim3(128, 1, 1), 0, s, const_cast<int*>(op.ctab));
             PCB_CUDA_OK(cudaGetLastError());
             return 0;
         }
-        constexpr bool kTma = kSmemMid + 128 <= 232448;
+        constexpr bool kTma = kSmemMidZ + 128 <= 232448;
         if (pass_id == PCB_PASS_MID_FWD_O || pass_id == PCB_PASS_MID_INV_ST) {      // ... with the stencil fused into the inverse half
             const int k = op.sten.k;
 #ifndef PCB_EMU
             if (kTma) {
-                if (pass_id == PCB_PASS_MID_FWD_O) PCB_GO_P((k_mid<PP, 0, 1, 1, 1>), (PP::N / 8 * 32), 3 * PP::N, kSmemMid + 128, 1);
-                else if (k == 1) PCB_GO_P((k_mid<PP, 0, 1, 2, 3>), (PP::N / 8 * 32), 3 * PP::N, kSmemMid + 128, 1);
-                else if (k == 2) PCB_GO_P((k_mid<PP, 0, 1, 2, 5>), (PP::N / 8 * 32), 3 * PP::N, kSmemMid + 128, 1);
-                else PCB_GO_P((k_mid<PP, 0, 1, 2, 1>), (PP::N / 8 * 32), 3 * PP::N, kSmemMid + 128, 1);
+                if (pass_id == PCB_PASS_MID_FWD_O) PCB_GO_P((k_mid<PP, 0, 1, 1, 1, ZS>), (PP::N / ZS / 8 * 32), 3 * PP::N * ZS, kSmemMidZ + 128, 1);
+                else if (k == 1) PCB_GO_P((k_mid<PP, 0, 1, 2, 3, ZS>), (PP::N / ZS / 8 * 32), 3 * PP::N * ZS, kSmemMidZ + 128, 1);
+                else if (k == 2) PCB_GO_P((k_mid<PP, 0, 1, 2, 5, ZS>), (PP::N / ZS / 8 * 32), 3 * PP::N * ZS, kSmemMidZ + 128, 1);
+                else PCB_GO_P((k_mid<PP, 0, 1, 2, 1, ZS>), (PP::N / ZS / 8 * 32), 3 * PP::N * ZS, kSmemMidZ + 128, 1);
                 return 0;
             }
 #endif
-            if (pass_id == PCB_PASS_MID_FWD_O) PCB_GO_P((k_mid<PP, 0, 0, 1, 1>), (PP::N / 8 * 32), 3 * PP::N, kSmemMid, 1);
-            else if (k == 1) PCB_GO_P((k_mid<PP, 0, 0, 2, 3>), (PP::N / 8 * 32), 3 * PP::N, kSmemMid, 1);
-            else if (k == 2) PCB_GO_P((k_mid<PP, 0, 0, 2, 5>), (PP::N / 8 * 32), 3 * PP::N, kSmemMid, 1);
-            else PCB_GO_P((k_mid<PP, 0, 0, 2, 1>), (PP::N / 8 * 32), 3 * PP::N, kSmemMid, 1);
+            if (pass_id == PCB_PASS_MID_FWD_O) PCB_GO_P((k_mid<PP, 0, 0, 1, 1, ZS>), (PP::N / ZS / 8 * 32), 3 * PP::N * ZS, kSmemMidZ, 1);
+            else if (k == 1) PCB_GO_P((k_mid<PP, 0, 0, 2, 3, ZS>), (PP::N / ZS / 8 * 32), 3 * PP::N * ZS, kSmemMidZ, 1);
+            else if (k == 2) PCB_GO_P((k_mid<PP, 0, 0, 2, 5, ZS>), (PP::N / ZS / 8 * 32), 3 * PP::N * ZS, kSmemMidZ, 1);
+            else PCB_GO_P((k_mid<PP, 0, 0, 2, 1, ZS>), (PP::N / ZS / 8 * 32), 3 * PP::N * ZS, kSmemMidZ, 1);
             return 0;
         }
         if (pass_id == PCB_PASS_MID_FWD || pass_id == PCB_PASS_MID_INV) {      // halves of the plane pass (cross-DoF dielectric)
 #ifndef PCB_EMU
             if (kTma) {
-                if (pass_id == PCB_PASS_MID_FWD) PCB_GO_P((k_mid<PP, 0, 1, 1>), (PP::N / 8 * 32), 3 * PP::N, kSmemMid + 128, 1);
-                else PCB_GO_P((k_mid<PP, 0, 1, 2>), (PP::N / 8 * 32), 3 * PP::N, kSmemMid + 128, 1);
+                if (pass_id == PCB_PASS_MID_FWD) PCB_GO_P((k_mid<PP, 0, 1, 1, 0, ZS>), (PP::N / ZS / 8 * 32), 3 * PP::N * ZS, kSmemMidZ + 128, 1);
+                else PCB_GO_P((k_mid<PP, 0, 1, 2, 0, ZS>), (PP::N / ZS / 8 * 32), 3 * PP::N * ZS, kSmemMidZ + 128, 1);
                 return 0;
             }
 #endif
-            if (pass_id == PCB_PASS_MID_FWD) PCB_GO_P((k_mid<PP, 0, 0, 1>), (PP::N / 8 * 32), 3 * PP::N, kSmemMid, 1);
-            else PCB_GO_P((k_mid<PP, 0, 0, 2>), (PP::N / 8 * 32), 3 * PP::N, kSmemMid, 1);
+            if (pass_id == PCB_PASS_MID_FWD) PCB_GO_P((k_mid<PP, 0, 0, 1, 0, ZS>), (PP::N / ZS / 8 * 32), 3 * PP::N * ZS, kSmemMidZ, 1);
+            else PCB_GO_P((k_mid<PP, 0, 0, 2, 0, ZS>), (PP::N / ZS / 8 * 32), 3 * PP::N * ZS, kSmemMidZ, 1);
             return 0;
         }
 #ifndef PCB_EMU
         if (pass_id == PCB_PASS_MID && op.diel == PCB_DIEL_TRIVIAL) {
             // coupled 3x3 M: clusters of three CTAs (one component each) exchanging the coupled points through DSMEM
             static_assert(!kPlaneCoupled || kTma, "the cluster form of the plane pass uses the TMA row copies");
-            if (kPlaneFive && op.mid_five && op.mbits2 != nullptr && op.maskp2 != nullptr)
-                return PlaneFive<kPlaneFive, PP>::go(op, cols, ncols, pass_id, tw, s, sms);
-            return launch_cluster3(k_mid<PP, 2, 1>, PP::N / 8 * 32, kSmemMid + 128, PP::N * ncols, op, cols, tw, ncols, s, sms, PP::N);
+            return Coupled<(kPlaneCoupled && ZS == 1), PP>::go(op, cols, ncols, pass_id, tw, s, sms);
         }
 #endif
-        if (pass_id == PCB_PASS_XFWD_SYM_TD) PCB_GO((k_xfwd<PP, LX, NT, 1, 1, 1>), GX, kStageXT);
-        else if (pass_id == PCB_PASS_XINV_A_TD) PCB_GO((k_xinv<PP, LX, NT, 1, 1, 1>), GX, kStageXT);
-        else if (pass_id == PCB_PASS_XINV_H_TD) PCB_GO((k_xinv<PP, LX, NT, 2, 1, 1>), GX, kStageXT);
-        else if (pass_id == PCB_PASS_XFWD_SYM_T) {
+        if (pass_id == PCB_PASS_XFWD_SYM_TD || pass_id == PCB_PASS_XINV_A_TD || pass_id == PCB_PASS_XINV_H_TD)
+            return XDist<ZS == 1, PP>::go(op, cols, ncols, pass_id, tw, s);
+        if (ZS == 2) {      // z-split plane mode: x passes with the split tiles, plane pass on half planes
+            if (pass_id == PCB_PASS_XFWD_SYM_T) PCB_GO((k_xfwd<PP, LX, NT, 1, 1, 0, ZS>), GX, kStageXT);
+            else if (pass_id == PCB_PASS_XINV_A_T) PCB_GO((k_xinv<PP, LX, NT, 1, 1, 0, ZS>), GX, kStageXT);
+            else if (pass_id == PCB_PASS_XINV_H_T) PCB_GO((k_xinv<PP, LX, NT, 2, 1, 0, ZS>), GX, kStageXT);
+            else if (pass_id == PCB_PASS_MID && (op.diel == PCB_DIEL_NONE || op.diel == PCB_DIEL_CHIRAL)) {
+#ifndef PCB_EMU
+                if (kTma) {
+                    if (op.diel == PCB_DIEL_NONE) PCB_GO_P((k_mid<PP, 0, 1, 0, 0, ZS>), (PP::N / ZS / 8 * 32), 3 * PP::N * ZS, kSmemMidZ + 128, 1);
+                    else PCB_GO_P((k_mid<PP, 1, 1, 0, 0, ZS>), (PP::N / ZS / 8 * 32), 3 * PP::N * ZS, kSmemMidZ + 128, 1);
+                    return 0;
+                }
+#endif
+                if (op.diel == PCB_DIEL_NONE) PCB_GO_P((k_mid<PP, 0, 0, 0, 0, ZS>), (PP::N / ZS / 8 * 32), 3 * PP::N * ZS, kSmemMidZ, 1);
+                else PCB_GO_P((k_mid<PP, 1, 0, 0, 0, ZS>), (PP::N / ZS / 8 * 32), 3 * PP::N * ZS, kSmemMidZ, 1);
+            }
+            else { pcb_set_error("z-split plane mode: pass %d / dielectric type %d not supported", pass_id, op.diel); return -1; }
+            return 0;
+        }
+        if (pass_id == PCB_PASS_XFWD_SYM_T) {
             static const char* ev2 = getenv("PCB200_XFWD2");      // default: two tiles per CTA, the second tile's loads behind the first tile's radix-R2 phase (PCB200_XFWD2=0: one tile per CTA)
             // (N = 48: 0.058 vs 0.051 ms -- below N = 64 one tile per CTA stays)
-            if (LX * PP::R2 <= NT && PP::N >= 64 && !(ev2 && ev2[0] == '0')) { if (XFwd2<(LX * PP::R2 <= NT && PP::N >= 64), PP>::go(op, cols, ncols, tw, s)) return -1; }
+            if (LX * PP::R2 <= NT && PP::N >= 64 && !(ev2 && ev2[0] == '0')) { if (XFwd2<(LX * PP::R2 <= NT && PP::N >= 64 && ZS == 1), PP>::go(op, cols, ncols, tw, s)) return -1; }
             else PCB_GO((k_xfwd<PP, LX, NT, 1, 1>), GX, kStageXT);
         }
         else if (pass_id == PCB_PASS_XINV_A_T || pass_id == PCB_PASS_XINV_H_T) {
-            constexpr bool kInv2 = (3 * LX * PP::R1 > NT) && (3 * LX * PP::R1 <= 2 * NT) && PP::N >= 64;
+            constexpr bool kInv2 = (3 * LX * PP::R1 > NT) && (3 * LX * PP::R1 <= 2 * NT) && PP::N >= 64 && ZS == 1;
             static const char* evi = getenv("PCB200_XINV2");      // experiment: two tiles per CTA in the inverse x pass
             if (kInv2 && evi && evi[0] == '1') { if (XInv2<kInv2, PP>::go(op, cols, ncols, pass_id == PCB_PASS_XINV_A_T ? 1 : 2, tw, s)) return -1; }
             else if (pass_id == PCB_PASS_XINV_A_T) PCB_GO((k_xinv<PP, LX, NT, 1, 1>), GX, kStageXT);
             else PCB_GO((k_xinv<PP, LX, NT, 2, 1>), GX, kStageXT);
         }
-        else if (pass_id == PCB_PASS_MASKBITS2 || pass_id == PCB_PASS_MASKPLANE2) return PlaneFive<kPlaneFive, PP>::go(op, cols, ncols, pass_id, tw, s, sms);
+        else if (pass_id == PCB_PASS_MASKBITS2 || pass_id == PCB_PASS_MASKPLANE2) return PlaneFive<(kPlaneFive && ZS == 1), PP>::go(op, cols, ncols, pass_id, tw, s, sms);
         else if (op.diel == PCB_DIEL_NONE || op.diel == PCB_DIEL_CHIRAL) {
-            if (kPlaneFive && op.mid_five && (op.diel == PCB_DIEL_NONE || op.mbits2 != nullptr)) return PlaneFive<kPlaneFive, PP>::go(op, cols, ncols, pass_id, tw, s, sms);
+            if (kPlaneFive && ZS == 1 && op.mid_five && (op.diel == PCB_DIEL_NONE || op.mbits2 != nullptr)) return PlaneFive<(kPlaneFive && ZS == 1), PP>::go(op, cols, ncols, pass_id, tw, s, sms);
             static const char* ev = getenv("PCB200_MID_TMA");
-            const bool tma = !(ev && ev[0] == '0') && kSmemMid + 128 <= 232448;      // default; PCB200_MID_TMA=0: cp.async / LDS+STG row loops
+            const bool tma = !(ev && ev[0] == '0') && kSmemMidZ + 128 <= 232448;      // default; PCB200_MID_TMA=0: cp.async / LDS+STG row loops
             if (tma) {
-                if (op.diel == PCB_DIEL_NONE) PCB_GO_P((k_mid<PP, 0, 1>), (PP::N / 8 * 32), 3 * PP::N, kSmemMid + 128, 1);
-                else PCB_GO_P((k_mid<PP, 1, 1>), (PP::N / 8 * 32), 3 * PP::N, kSmemMid + 128, 1);
+                if (op.diel == PCB_DIEL_NONE) PCB_GO_P((k_mid<PP, 0, 1, 0, 0, ZS>), (PP::N / ZS / 8 * 32), 3 * PP::N * ZS, kSmemMidZ + 128, 1);
+                else PCB_GO_P((k_mid<PP, 1, 1, 0, 0, ZS>), (PP::N / ZS / 8 * 32), 3 * PP::N * ZS, kSmemMidZ + 128, 1);
             } else {
-                if (op.diel == PCB_DIEL_NONE) PCB_GO_P((k_mid<PP, 0>), (PP::N / 8 * 32), 3 * PP::N, kSmemMid, 1);
-                else PCB_GO_P((k_mid<PP, 1>), (PP::N / 8 * 32), 3 * PP::N, kSmemMid, 1);
+                if (op.diel == PCB_DIEL_NONE) PCB_GO_P((k_mid<PP, 0, 0, 0, 0, ZS>), (PP::N / ZS / 8 * 32), 3 * PP::N * ZS, kSmemMidZ, 1);
+                else PCB_GO_P((k_mid<PP, 1, 0, 0, 0, ZS>), (PP::N / ZS / 8 * 32), 3 * PP::N * ZS, kSmemMidZ, 1);
             }
         }
         else { pcb_set_error("plane mode: dielectric type %d not supported", op.diel); return -1; }
@@ -329,7 +383,8 @@ int run_pass(const PcbOp& op, const PcbCols& cols, int ncols, int pass_id, const
         case PCB_PASS_XFWD_SYM_T: case PCB_PASS_MID: case PCB_PASS_XINV_A_T: case PCB_PASS_XINV_H_T: case PCB_PASS_MASKBITS:
         case PCB_PASS_MID_FWD: case PCB_PASS_MID_INV: case PCB_PASS_MASKPLANE: case PCB_PASS_COORDTAB: case PCB_PASS_MASKBITS2:
         case PCB_PASS_XFWD_SYM_TD: case PCB_PASS_XINV_A_TD: case PCB_PASS_XINV_H_TD: case PCB_PASS_MID_FWD_O: case PCB_PASS_MID_INV_ST: case PCB_PASS_MASKPLANE2:
-            return PlanePass<kPlane, P>::go(op, cols, ncols, pass_id, tw, s, sms);
+            if (op.zsplit) return PlanePass<kPlaneSplit, P, 2>::go(op, cols, ncols, pass_id, tw, s, sms);
+            return PlanePass<kPlane, P, 1>::go(op, cols, ncols, pass_id, tw, s, sms);
         default: pcb_set_error("unknown pass id %d", pass_id); return -1;
     }
     return 0;
@@ -358,4 +413,6 @@ int run_apply(const PcbOp& op, const PcbCols& cols, int ncols, int mode, const c
 
 #define PCB_CAT2(a, b) a##b
 #define PCB_CAT(a, b) PCB_CAT2(a, b)
-extern const PcbOpLaunch PCB_CAT(pcb_plan_, PCB_N) = {PCB_N, PCB_R1, PCB_R2, kPlane ? 1 : 0, kPlaneCoupled ? 1 : 0, kPlaneFive ? 1 : 0, LX, run_apply, run_pass};
+extern const PcbOpLaunch PCB_CAT(pcb_plan_, PCB_N) = {PCB_N, PCB_R1, PCB_R2, (kPlane || kPlaneSplit) ? 1 : 0, kPlaneCoupled ? 1 : 0, kPlaneFive ? 1 : 0, LX,
+                                                      kPlaneSplit ? (kPlane ? 1 : 2) : 0, kPlaneSplit ? PlanOf<(kPlaneSplit ? P::N / 2 : P::N)>::type::R1 : 0,
+                                                      kPlaneSplit ? PlanOf<(kPlaneSplit ? P::N / 2 : P::N)>::type::R2 : 0, run_apply, run_pass};

@@ -40,7 +40,7 @@ def _build_module():
     return mod
 
 
-EMU_SIZES = [6, 8, 12, 16, 24]
+EMU_SIZES = [6, 8, 12, 16, 24, 32]
 
 
 @pytest.fixture(scope="session")

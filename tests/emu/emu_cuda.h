@@ -262,6 +262,7 @@ template <class T> static inline T __shfl_down_sync(unsigned, T v, int d, int = 
 template <class T> static inline T __shfl_sync(unsigned, T v, int src, int = 32) { return pcbemu::shfl(v, src); }
 static inline bool __any_sync(unsigned, bool pred) { return pcbemu::vote_any(pred); }
 static inline int __ffs(int v) { return v == 0 ? 0 : __builtin_ffs(v); }
+static inline int __ffsll(long long v) { return v == 0 ? 0 : __builtin_ffsll(v); }
 template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline double atomicAdd(double* p, double v) { double o = *p; *p += v; return o; }
 static inline int atomicAdd(int* p, int v) { int o = *p; *p += v; return o; }

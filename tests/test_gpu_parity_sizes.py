@@ -66,6 +66,12 @@ def _oracle_ops(pcb, oc, N, d_flag, alpha, typ, eps_opt=0):
     (160, "bcc_dg", "pseudochiral_trivial", [np.pi, 0.0, np.pi], 1),       # BASELINE configs[3]
     (160, "bcc_dg", "pseudochiral_crossdof", [np.pi, 0.0, np.pi], 1),
     (256, "sc_curv", "chiral", [np.pi, np.pi, np.pi], 1),                  # BASELINE configs[4]
+    (160, "fcc", "chiral", [0.3 * np.pi, 2 * np.pi, 0.0], 2),              # z-split plane mode (N = 128, 144, 160): isotropic M ...
+    (160, "sc_curv", None, [np.pi, 0.4, 0.0], 1),
+    (144, "fcc", "chiral", [np.pi, np.pi, 0.0], 1),
+    (144, "bcc_sg", "pseudochiral_crossdof", [np.pi, 0.5 * np.pi, 0.0], 1),   # ... and the cross-DoF halves on half planes
+    (128, "sc_curv", "chiral", [np.pi, np.pi, np.pi], 2),
+    (128, "bcc_dg", "pseudochiral_crossdof", [0.0, 0.0, 2 * np.pi], 1),
 ])
 def test_operator_vs_oracle_at_baseline_sizes(gpu, oracle, N, d_flag, typ, alpha, cols):
     alpha = np.array(alpha, dtype=float)
@@ -74,9 +80,32 @@ def test_operator_vs_oracle_at_baseline_sizes(gpu, oracle, N, d_flag, typ, alpha
     Ao, Ho, Po = _oracle_ops(gpu, oracle, N, d_flag, alpha, typ)
     x = oracle.random_x0(3 * N ** 3, cols, N + cols)
     assert relerr(H(x), Ho(x)) < 1e-12
-    if N <= 120:
+    if N <= 160:
         assert relerr(A(x), Ao(x)) < 1e-12
+    if N <= 120:
         assert relerr(P(x), Po(x)) < 1e-12
+
+
+@pytest.mark.parametrize("N,d_flag,typ", [(64, "fcc", "chiral"), (96, "bcc_sg", "pseudochiral_crossdof"), (96, "sc_curv", None)])
+def test_z_split_plane_mode_at_plane_sizes(gpu, oracle, N, d_flag, typ):
+    """The z-split form of the plane mode forced on where the whole-plane form is the default: both match the oracle."""
+    alpha = np.array([0.3 * np.pi, 2 * np.pi, 0.0])
+    oracle.FFT_WORKERS = os.cpu_count() or 1
+    ctx = gpu.get_context(N)
+    Ao, Ho, Po = _oracle_ops(gpu, oracle, N, d_flag, alpha, typ)
+    x = oracle.random_x0(3 * N ** 3, 2, N)
+    want_a, want_h = Ao(x), Ho(x)
+    out = {}
+    try:
+        for split in (1, 0):
+            ctx.option("plane_split", split)
+            (A, H, P), _ = _ops(gpu, N, d_flag, alpha, typ)
+            out[split] = A(x)
+            assert relerr(out[split], want_a) < 1e-12
+            assert relerr(H(x), want_h) < 1e-12
+    finally:
+        ctx.option("plane_split", 0)
+    assert not np.array_equal(out[0], out[1])
 
 
 def test_operator_16_columns_n120_matches_column_by_column(gpu, oracle):

@@ -176,3 +176,63 @@ def test_crossdof_pass_structures(pcb, oracle, structure):
         assert relerr(A(x), Ao(x)) < TOL
     finally:
         ctx.option("plane_cross", 1)
+
+
+@pytest.mark.parametrize("N,typ,plane_cross,k", [
+    (16, None, 1, 1), (16, "chiral", 1, 1), (16, "pseudochiral_crossdof", 1, 1), (16, "pseudochiral_crossdof", 2, 2),
+    (16, "pseudochiral_trivial", 1, 1),
+    (32, "chiral", 1, 1), (32, "pseudochiral_crossdof", 1, 2),
+])
+def test_z_split_plane_mode(pcb, oracle, N, typ, plane_cross, k):
+    """Z-split plane mode (the plane mode of N = 128, 144, 160: half planes of N/2 x N, the radix-2 step of the z transform inside
+    the x passes; ZSplit in pcb_operator.cuh) forced on at sizes where both forms exist: equal to the oracle, and to the whole-plane
+    form up to rounding while not bit-identical (two different sets of kernels did run).  The coupled 3x3 M has no z-split
+    form and must fall back to the five-pass path."""
+    d_flag = "bcc_dg" if typ and typ.startswith("pseudo") else "fcc"
+    alpha = np.array([0.3 * np.pi, 2 * np.pi, 0.0])
+    ctx = pcb.get_context(N)
+    eps_opt = 3 if typ and typ.startswith("pseudo") else 0
+    a, b, inv, shift, _ = oracle.assemble_symbols(N, d_flag, alpha, k=k)
+    okw = {"k": k} if typ == "pseudochiral_crossdof" else {}
+    diel = (lambda v: v) if typ is None else oracle.HANDLES[typ](N, d_flag, eps_opt=eps_opt, **okw)
+    Ao, Ho, Po = oracle.pc_mfd_handle(a, b, diel, inv, shift)
+    mfd, ne = pcb.discretization, pcb.numerical_experiments
+    x = oracle.random_x0(3 * N ** 3, 2, 77 + N)
+    out = {}
+    try:
+        ctx.option("plane_cross", plane_cross)
+        for split in (1, 0):
+            ctx.option("plane_split", split)
+            relax, pnt = mfd.set_relaxation(alpha)
+            a_fft, b_fft = mfd.fft_blocks(N, k, pcb.dielectric.diel_info(d_flag, option="ct"), alpha=alpha)
+            inv_fft = mfd.inverse_3_times_3_B(b_fft, pnt, relax[0])
+            Diels = None if typ is None else getattr(mfd, typ + "_handle")(N, d_flag, eps_opt=eps_opt, **okw)
+            A, H, P = ne.pc_mfd_handle(a_fft, (pnt * b_fft[0], pnt * b_fft[1]), Diels, inv_fft, relax[0])
+            out[split] = A(x)
+            assert relerr(out[split], Ao(x)) < TOL
+            assert relerr(H(x), Ho(x)) < TOL
+    finally:
+        ctx.option("plane_split", 0)
+        ctx.option("plane_cross", 1)
+    assert relerr(out[1], out[0]) < 1e-13
+    if typ != "pseudochiral_trivial" or pcb.backend_name == "cuda":
+        assert not np.array_equal(out[1], out[0])
+
+
+def test_z_split_dielectric_is_bound_to_its_form(pcb, oracle):
+    """A dielectric carries masks in the slot order of the plane-mode form it was created under: using it after the form of the
+    context changed is refused instead of silently applying a permuted M."""
+    N, d_flag = 16, "fcc"
+    ctx = pcb.get_context(N)
+    mfd, ne = pcb.discretization, pcb.numerical_experiments
+    alpha = np.array([np.pi, 0.0, 0.0])
+    relax, pnt = mfd.set_relaxation(alpha)
+    a_fft, b_fft = mfd.fft_blocks(N, 1, pcb.dielectric.diel_info(d_flag, option="ct"), alpha=alpha)
+    inv_fft = mfd.inverse_3_times_3_B(b_fft, pnt, relax[0])
+    Diels = mfd.chiral_handle(N, d_flag)
+    try:
+        ctx.option("plane_split", 1)
+        with pytest.raises(Exception):
+            ne.pc_mfd_handle(a_fft, (pnt * b_fft[0], pnt * b_fft[1]), Diels, inv_fft, relax[0])
+    finally:
+        ctx.option("plane_split", 0)
