@@ -225,13 +225,27 @@ def paper2_dielectric_leg(pcb, ctx, n, m, steps, warmup, peak):
     """Extra keys: the same 16-column H block apply with the Paper-2 dielectrics (BASELINE configs[2]: bcc single gyroid,
     pseudochiral) -- the coupled 3x3 M (clusters of three CTAs in the plane pass) and the cross-DoF M (plane halves around the
     stencil kernel).  Roofline against 336 N^3 (and 432 N^3 for the cross-DoF M, whose stencil is a pass of its own)."""
+    return dielectric_leg(pcb, ctx, n, m, steps, warmup, peak, "bcc_sg", ("pseudochiral_trivial", "pseudochiral_crossdof"))
+
+
+def larger_grid_leg(pcb, m, steps, warmup, peak, n=160):
+    """Extra key `larger_grids`: the 16-column H block apply at N = 160 (BASELINE configs[3] shape: bcc double gyroid, cross-DoF
+    M; and the isotropic FCC operator) -- the z-split plane mode (half planes, three passes) instead of five passes."""
+    ctx = pcb.get_context(n)
+    try:
+        return (dielectric_leg(pcb, ctx, n, m, steps, warmup, peak, "fcc", ("chiral",))
+                + dielectric_leg(pcb, ctx, n, m, steps, warmup, peak, "bcc_dg", ("pseudochiral_crossdof",)))
+    finally:
+        ctx.trim()
+
+
+def dielectric_leg(pcb, ctx, n, m, steps, warmup, peak, lattice, types):
     mfd, ne, L = pcb.discretization, pcb.numerical_experiments, pcb._lib
     out = []
-    lattice = "bcc_sg"
     alpha = pcb.dielectric.kpath(lattice)[0]
     sym = build_ops_for(pcb, n, lattice, alpha, None)
     X, Y = ctx.random_block(m, 4321), ctx.empty(m)
-    for typ in ("pseudochiral_trivial", "pseudochiral_crossdof"):
+    for typ in types:
         Diels = getattr(mfd, typ + "_handle")(n, lattice)
         A, H, P = ne.pc_mfd_handle(sym[0], sym[1], Diels, sym[2], sym[3])
         for _ in range(warmup):
@@ -588,6 +602,9 @@ def main():
     paper2 = None
     if not args.no_paper2 and n == N_GRID:
         paper2 = paper2_dielectric_leg(pcb, ctx, n, m, max(5, min(args.steps, 20)), 3, peak)
+    larger = None
+    if not args.no_paper2 and n == N_GRID and dist.world == 1:
+        larger = larger_grid_leg(pcb, m, 5, 2, peak)
     large = None
     if dist.world > 1 and not args.no_large_grid:
         large = large_grid_leg(dist, pcb, n, NEV, check=True)
@@ -611,7 +628,7 @@ def main():
                            "N": n, "lattice": LATTICE, "type": DTYPE_TYPE, "cols_per_step": m, "l2": "inputs exceed L2 (1.33 GB per block)",
                            "parallelism": f"k-path sharding x{dist.world}, no collective"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-                "passes": passes, "block_kernels": blocks, "lobpcg": lob, "paper2_dielectrics": paper2, "large_grid": large}
+                "passes": passes, "block_kernels": blocks, "lobpcg": lob, "paper2_dielectrics": paper2, "larger_grids": larger, "large_grid": large}
         print(json.dumps(line), flush=True)
     dist.close()
 

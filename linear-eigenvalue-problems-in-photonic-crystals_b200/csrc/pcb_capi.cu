@@ -224,6 +224,9 @@ static int ctx_create(int device, int N, int z0, int z1, pcb_ctx** out) {
     { const char* e = getenv("PCB200_PLANE_CROSS"); c->use_plane_cross = e ? (e[0] == '0' ? 0 : (e[0] == '2' ? 2 : 1)) : 1; }
     { const char* e = getenv("PCB200_MID_FIVE"); c->use_mid_five = e ? (e[0] == '0' ? 0 : 1) : -1; }
     { const char* e = getenv("PCB200_PLANE_SPLIT"); c->zsplit = (plan->plane_split == 2 || (plan->plane_split == 1 && e && e[0] == '1')) ? 1 : 0; }
+    // cross-DoF M at N >= 160: the stencil as its own kernel between the plane halves (5 kernels) -- gathered on load in the inverse half it
+    // takes 4.06 ms of an 8.84 ms apply at N = 160 (bcc_dg, 16 columns), as a kernel 1.46 ms of 7.79 ms; below that the fused form wins or ties
+    if (!getenv("PCB200_PLANE_CROSS") && c->zsplit && N >= 160) c->use_plane_cross = 2;
 #ifndef PCB_EMU
     cudaDeviceProp prop;
     PCB_CUDA_OK_OR(cudaGetDeviceProperties(&prop, device), delete c);

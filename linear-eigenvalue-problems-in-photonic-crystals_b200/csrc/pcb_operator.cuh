@@ -201,10 +201,15 @@ PCB_D void pcb_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0
 // read here through the IPC-mapped pointers of op.dist (a tile of rows lies in one plane, hence in one rank's slab); the tile is
 // also copied to the local column cols.in[col], which the inverse x pass re-reads for the gamma K_B x + shift x term, so every
 // element crosses NVLink once per direction.  The slab gather of the exchange path is fused into this pass.
+// z-split forward x pass: three CTAs per SM (168 registers) where the first radix is at most 10 -- N = 160: 1.28 vs 1.35 ms per
+// 16 columns, N = 128: 0.62 vs 0.68; with R1 = 12 (N = 144) the cap spills and loses (1.22 vs 1.10 ms)
+#ifndef PCB_XFWD_ZS_CTAS
+#define PCB_XFWD_ZS_CTAS 3
+#endif
 // ZS = 2 (with TRN): z-split plane mode, see ZSplit -- the tile's rows are 4 consecutive i1 of the planes i2' and i2' + N/2, and
 // the radix-2 butterfly of the z transform is applied where the second radix step reads the exchange buffer.
 template <class P, int LX, int NT, int SYM, int TRN = 0, int DIST = 0, int ZS = 1>
-__global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * (P::R1 * P::R2P + TRN) * 16, P::R1, 4)) k_xfwd(PcbOp op, PcbCols cols, const cplx* __restrict__ tw) {
+__global__ void __launch_bounds__(NT, (ZS == 2 ? (P::R1 <= 10 ? PCB_XFWD_ZS_CTAS : 1) : pcb_min_ctas(3 * LX * (P::R1 * P::R2P + TRN) * 16, P::R1, 4))) k_xfwd(PcbOp op, PcbCols cols, const cplx* __restrict__ tw) {
     constexpr int N = P::N, R1 = P::R1, R2 = P::R2, R2P = P::R2P;
     constexpr int RS = R1 * R2P + TRN;      // row stride in shared memory
     static_assert(ZS == 1 || (TRN == 1 && DIST == 0 && ZS == 2 && LX % 2 == 0 && N % (8 * ZS) == 0), "z-split: plane mode only");
@@ -562,129 +567,9 @@ __global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * (P::R1 * P::R2P + TR
     }
 }
 
-// Plane-mode inverse x pass on TWO consecutive tiles per CTA (the counterpart of k_xfwd2): the scattered loads of the second
-// tile's first radix-R2 items (one item per thread) are issued before the point-wise epilogue of the first tile, whose X loads
-// and stores they overlap.  MODE as in k_xinv (1: A, 2: H).
-template <class P, int LX, int NT, int MODE>
-__global__ void __launch_bounds__(NT, 3) k_xinv2(PcbOp op, PcbCols cols, const cplx* __restrict__ tw) {
-    constexpr int N = P::N, R1 = P::R1, R2 = P::R2, R2P = P::R2P;
-    constexpr int RS = R1 * R2P + 1;
-    constexpr int NA = 3 * LX * R1;           // radix-R2 items of a tile
-    static_assert(NA > NT && NA <= 2 * NT, "two trips over the radix-R2 items");
-    PCB_DYN_SMEM(cplx, sm);   // [3][LX][RS]
-    const int col = blockIdx.y;
-    const cplx* __restrict__ X = cols.in[col];
-    cplx* __restrict__ W = cols.out[col];
-    const cplx* __restrict__ WT = cols.wrk[col];
-    const long long nn = op.nn;
-    const int nrows = N * N;
-    const int tid = threadIdx.x;
-
-    auto prefetch_x = [&](int row0) {
-        if (MODE != 2 || row0 >= nrows) return;
-        const int nr = (nrows - row0 < LX) ? nrows - row0 : LX;
-        const int lines = (nr * N * (int)sizeof(cplx) + 127) / 128;
-        for (int l = tid; l < 3 * lines; l += NT)
-            pcb_prefetch_l2(reinterpret_cast<const char*>(X + (l / lines) * nn + (long long)row0 * N) + (l % lines) * 128);
-    };
-    auto load_item = [&](int row0, int item, cplx (&v)[R2]) {      // raw loads of radix-R2 item `item` of the tile at row0
-        const int k1 = (item / LX) % R1, r = item % LX, c = item / (R1 * LX);
-        if (item >= NA || row0 + r >= nrows) return;
-        const cplx* __restrict__ src = WT + c * nn + (long long)k1 * N * N + (row0 + r);
-        PCB_UNROLL
-        for (int k2 = 0; k2 < R2; ++k2) v[k2] = src[(long long)R1 * k2 * N * N];
-    };
-    auto finish_item = [&](int row0, int item, cplx (&v)[R2]) {    // inverse radix R2, conjugate twiddles -> shared memory
-        const int k1 = (item / LX) % R1, r = item % LX, c = item / (R1 * LX);
-        if (item >= NA || row0 + r >= nrows) return;
-        Dft<R2, +1>::run(v);
-        PCB_UNROLL
-        for (int n2 = 0; n2 < R2; ++n2) {
-            cplx val = v[n2];
-            if (k1 > 0) { const cplx t = __ldg(tw + k1 * R2 + n2); val = cmul(val, cmake(t.x, -t.y)); }
-            sm[(c * LX + r) * RS + k1 * R2P + n2] = val;
-        }
-    };
-    auto phase_b = [&](int row0) {      // inverse radix R1 in place
-        const int nr = (nrows - row0 < LX) ? nrows - row0 : LX;
-        for (int item = tid; item < 3 * LX * R2; item += NT) {
-            const int n2 = item % R2, cr = item / R2;
-            if (cr % LX >= nr) continue;
-            cplx v[R1];
-            PCB_UNROLL
-            for (int k1 = 0; k1 < R1; ++k1) v[k1] = sm[cr * RS + k1 * R2P + n2];
-            Dft<R1, +1>::run(v);
-            PCB_UNROLL
-            for (int n1 = 0; n1 < R1; ++n1) sm[cr * RS + n1 * R2P + n2] = v[n1];
-        }
-    };
-    auto phase_c = [&](int row0) {      // point-wise epilogue (see k_xinv)
-        const int nr = (nrows - row0 < LX) ? nrows - row0 : LX;
-        constexpr int PB = 4;
-        for (int e0 = tid; e0 < nr * N; e0 += PB * NT) {
-            cplx x[PB][3];
-            if (MODE == 2) {
-                PCB_UNROLL
-                for (int q = 0; q < PB; ++q) {
-                    const int e = e0 + q * NT;
-                    if (e < nr * N) {
-                        PCB_UNROLL
-                        for (int c = 0; c < 3; ++c) x[q][c] = X[c * nn + (long long)row0 * N + e];
-                    }
-                }
-            }
-            PCB_UNROLL
-            for (int q = 0; q < PB; ++q) {
-                const int e = e0 + q * NT;
-                if (e >= nr * N) continue;
-                const int r = e / N, i0 = e % N;
-                const int row = row0 + r;
-                const int slot = r * RS + (i0 / R2) * R2P + i0 % R2;
-                cplx u[3], z[3];
-                PCB_UNROLL
-                for (int c = 0; c < 3; ++c) u[c] = cscale(sm[c * LX * RS + slot], op.inv_n3);
-                const Sym3 sy = pcb_symbol(op.T, N, i0, row % N, row / N);
-                pcb_cross(sy.k, u, z);
-                if (MODE == 2) {
-                    cplx dot = cadd(cadd(cmul(sy.k[0], x[q][0]), cmul(sy.k[1], x[q][1])), cmul(sy.k[2], x[q][2]));
-                    dot = cscale(dot, op.gamma);
-                    PCB_UNROLL
-                    for (int c = 0; c < 3; ++c) {
-                        cplx t = cfmac(sy.k[c], dot, z[c]);
-                        t.x = fma(op.shift, x[q][c].x, t.x);
-                        t.y = fma(op.shift, x[q][c].y, t.y);
-                        z[c] = t;
-                    }
-                }
-                PCB_UNROLL
-                for (int c = 0; c < 3; ++c) W[c * nn + (long long)row0 * N + e] = z[c];
-            }
-        }
-    };
-
-    const int rowa = blockIdx.x * (2 * LX), rowb = rowa + LX;
-    prefetch_x(rowa);
-    prefetch_x(rowb);
-    cplx va[R2], vb[R2];
-    load_item(rowa, tid, va);
-    load_item(rowa, tid + NT, vb);
-    finish_item(rowa, tid, va);
-    finish_item(rowa, tid + NT, vb);
-    __syncthreads();
-    phase_b(rowa);
-    if (rowb < nrows) load_item(rowb, tid, va);       // in flight during the epilogue of the first tile
-    __syncthreads();
-    phase_c(rowa);
-    if (rowb >= nrows) return;
-    __syncthreads();
-    load_item(rowb, tid + NT, vb);
-    finish_item(rowb, tid, va);
-    finish_item(rowb, tid + NT, vb);
-    __syncthreads();
-    phase_b(rowb);
-    __syncthreads();
-    phase_c(rowb);
-}
+// (Round 2, measured and removed: the inverse x pass on two consecutive tiles per CTA, the counterpart of k_xfwd2 -- the second
+// tile's scattered radix-R2 loads issued before the first tile's point-wise epilogue.  The 15 complex values waiting through an
+// epilogue that itself holds 4 x 3 X values spill 450-670 bytes at 3 CTAs per SM: 0.871 vs 0.693 ms at N = 120, 16 columns.)
 
 // ---------------------------------------------------------------------------------------
 // Passes 2/4 (and the split z passes of the cross-DoF variant): strided lines, in place.
@@ -1101,7 +986,10 @@ __global__ void __launch_bounds__(P::N / ZS / 8 * 32, 1) k_mid(PcbOp op, PcbCols
 #endif
 
     for (int pid = first; pid < total; pid += stride) {
-        const int col = (DIEL == 2) ? pid / N : pid / (3 * N * ZS), c = (DIEL == 2) ? crank : (pid / (N * ZS)) % 3, i0 = (pid / ZS) % N;
+        // z-split: (column, i0, component, half) -- the half planes of all three components of one i0 are in flight together, so the
+        // cross-DoF gathers of the fused stencil find the other components' planes in L2 (a column no longer fits L2 for N > 128)
+        const int col = (DIEL == 2) ? pid / N : pid / (3 * N * ZS);
+        const int c = (DIEL == 2) ? crank : (ZS == 1 ? (pid / N) % 3 : (pid / ZS) % 3), i0 = ZS == 1 ? pid % N : (pid / (3 * ZS)) % N;
         const int hz = ZS == 1 ? 0 : pid % ZS, prow = hz * NZ + 8 * warp;      // half plane; first plane row of this warp
         const long long poff = c * nn + (long long)i0 * N * N + (long long)prow * N;      // this warp's 8 rows
         cplx* __restrict__ base = ((STEN && HALF == 1) ? cols.out[col] : cols.wrk[col]) + poff;

@@ -176,25 +176,6 @@ struct PlaneFive<true, PP> {
 };
 
 template <bool OK, class PP>
-struct XInv2 { static int go(const PcbOp&, const PcbCols&, int, int, const cplx*, cudaStream_t) { return -1; } };
-template <class PP>
-struct XInv2<true, PP> {
-    static int go(const PcbOp& op, const PcbCols& cols, int ncols, int mode, const cplx* tw, cudaStream_t s) {
-        dim3 grid((unsigned)((GX + 1) / 2), (unsigned)ncols, 1);
-        if (mode == 1) {
-            auto kfn = k_xinv2<PP, LX, NT, 1>;
-            if (set_smem(kfn, kStageXT)) return -1;
-            PCB_LAUNCH(kfn, grid, dim3(NT, 1, 1), (size_t)kStageXT, s, op, cols, tw);
-        } else {
-            auto kfn = k_xinv2<PP, LX, NT, 2>;
-            if (set_smem(kfn, kStageXT)) return -1;
-            PCB_LAUNCH(kfn, grid, dim3(NT, 1, 1), (size_t)kStageXT, s, op, cols, tw);
-        }
-        PCB_CUDA_OK(cudaGetLastError());
-        return 0;
-    }
-};
-template <bool OK, class PP>
 struct XFwd2 { static int go(const PcbOp&, const PcbCols&, int, const cplx*, cudaStream_t) { return -1; } };
 template <class PP>
 struct XFwd2<true, PP> {
@@ -335,13 +316,8 @@ struct PlanePass<true, PP, ZS> {
             if (LX * PP::R2 <= NT && PP::N >= 64 && !(ev2 && ev2[0] == '0')) { if (XFwd2<(LX * PP::R2 <= NT && PP::N >= 64 && ZS == 1), PP>::go(op, cols, ncols, tw, s)) return -1; }
             else PCB_GO((k_xfwd<PP, LX, NT, 1, 1>), GX, kStageXT);
         }
-        else if (pass_id == PCB_PASS_XINV_A_T || pass_id == PCB_PASS_XINV_H_T) {
-            constexpr bool kInv2 = (3 * LX * PP::R1 > NT) && (3 * LX * PP::R1 <= 2 * NT) && PP::N >= 64 && ZS == 1;
-            static const char* evi = getenv("PCB200_XINV2");      // experiment: two tiles per CTA in the inverse x pass
-            if (kInv2 && evi && evi[0] == '1') { if (XInv2<kInv2, PP>::go(op, cols, ncols, pass_id == PCB_PASS_XINV_A_T ? 1 : 2, tw, s)) return -1; }
-            else if (pass_id == PCB_PASS_XINV_A_T) PCB_GO((k_xinv<PP, LX, NT, 1, 1>), GX, kStageXT);
-            else PCB_GO((k_xinv<PP, LX, NT, 2, 1>), GX, kStageXT);
-        }
+        else if (pass_id == PCB_PASS_XINV_A_T) PCB_GO((k_xinv<PP, LX, NT, 1, 1>), GX, kStageXT);
+        else if (pass_id == PCB_PASS_XINV_H_T) PCB_GO((k_xinv<PP, LX, NT, 2, 1>), GX, kStageXT);
         else if (pass_id == PCB_PASS_MASKBITS2 || pass_id == PCB_PASS_MASKPLANE2) return PlaneFive<(kPlaneFive && ZS == 1), PP>::go(op, cols, ncols, pass_id, tw, s, sms);
         else if (op.diel == PCB_DIEL_NONE || op.diel == PCB_DIEL_CHIRAL) {
             if (kPlaneFive && ZS == 1 && op.mid_five && (op.diel == PCB_DIEL_NONE || op.mbits2 != nullptr)) return PlaneFive<(kPlaneFive && ZS == 1), PP>::go(op, cols, ncols, pass_id, tw, s, sms);

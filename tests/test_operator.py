@@ -215,7 +215,7 @@ def test_z_split_plane_mode(pcb, oracle, N, typ, plane_cross, k):
         ctx.option("plane_split", 0)
         ctx.option("plane_cross", 1)
     assert relerr(out[1], out[0]) < 1e-13
-    if typ != "pseudochiral_trivial" or pcb.backend_name == "cuda":
+    if typ != "pseudochiral_trivial":      # (the coupled M takes the five-pass path in both forms at N = 16)
         assert not np.array_equal(out[1], out[0])
 
 
