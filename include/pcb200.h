@@ -55,8 +55,10 @@ int pcb_ctx_create(int device, int N, pcb_ctx** ctx);
 void pcb_ctx_destroy(pcb_ctx* ctx);
 int pcb_sync(pcb_ctx* ctx);
 int pcb_launch_count(pcb_ctx* ctx, long long* n);   /* kernels launched by this context so far */
-/* pass-structure switches (A/B measurements, tests): "plane", "plane_coupled", "plane_cross" (0 / 1), "mid_five" (-1 auto, 0, 1);
- * defaults from the PCB200_* environment variables; seen by operators created or updated afterwards */
+/* pass-structure switches (A/B measurements, tests): "plane", "plane_coupled", "plane_cross" (0 / 1 / 2), "mid_five" (-1 auto, 0, 1),
+ * "plane_split" (0 / 1: z-split form of the plane mode where a size has both forms; always on for N = 128, 144, 160; dielectrics
+ * must be re-created after a change); defaults from the PCB200_* environment variables; seen by operators created or updated
+ * afterwards */
 int pcb_ctx_option(pcb_ctx* ctx, const char* name, int value);
 /* stream ordering between two contexts of one process without a host sync (16 slots per context): pcb_ctx_record marks the work
  * enqueued on ctx so far, pcb_ctx_wait makes later work of `waiter` start after that mark (the reference is single-stream) */

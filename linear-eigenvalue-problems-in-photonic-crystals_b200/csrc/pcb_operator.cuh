@@ -4,7 +4,7 @@
 //
 // Two pass structures (chosen per call in pcb_capi.cu):
 //
-// PLANE MODE -- three global passes, 7 column transfers per op-apply (N % 8 == 0, N <= 120, identity / isotropic M):
+// PLANE MODE -- three global passes, 7 column transfers per op-apply (N % 8 == 0, N <= 120; N = 128, 144, 160 in the z-split form, ZSplit below):
 //   k_xfwd<T>  x-lines:  y = (-conj k) x x fused on load, forward FFT along i0, stored TRANSPOSED as W'[c][i0][i2][i1]
 //   k_mid      one (i1,i2) plane per CTA in shared memory: forward y, forward z, M, inverse z, inverse y, in place
 //   k_xinv<T>  x-lines:  inverse FFT along i0 from W', 1/N^3, k x v, + gamma conj(k)(k.x) + shift x, natural layout
@@ -34,6 +34,11 @@ struct PcbCols {
 
 // occupancy hint of the x passes: ask for `want` CTAs/SM (caps registers) only where the tile is small enough to allow it
 constexpr int pcb_min_ctas(int stage_bytes, int r1, int want) { return (want * stage_bytes <= 200 * 1024 && r1 <= 8) ? want : 1; }
+// inverse x pass with a first radix above 8: three CTAs per SM where they fit -- uncapped, N = 256 takes 174 registers, which the
+// allocation granularity (8 per thread) turns into two resident CTAs of four warps instead of three
+constexpr int pcb_min_ctas_inv(int stage_bytes, int r1, int want) {
+    return r1 <= 8 ? pcb_min_ctas(stage_bytes, r1, want) : (3 * stage_bytes <= 200 * 1024 ? 3 : 1);
+}
 constexpr int pcb_gcd(int a, int b) { return b == 0 ? a : pcb_gcd(b, a % b); }
 constexpr int pcb_modinv(int a, int m) {   // a^-1 mod m (m small)
     for (int x = 1; x < m; ++x) if ((a * x) % m == 1) return x;
@@ -426,8 +431,13 @@ __global__ void __launch_bounds__(NT, 3) k_xfwd2(PcbOp op, PcbCols cols, const c
 #endif
 // ZS = 2 (with TRN): z-split plane mode (ZSplit) -- tiles as in k_xfwd<.., ZS = 2>; the epilogue recombines the two half planes,
 // x[i2' + j N/2] = e[i2'] + (-1)^j conj(w_N^i2') o[i2'], while it reads the transformed tile.
+// (z-split sizes: the uncapped kernel takes 170-172 registers, which the allocation granularity turns into TWO resident CTAs of four
+// warps -- ncu: warps active 12 %, DRAM 58 % at N = 160; asking for three caps it at 168.)
+#ifndef PCB_XINV_ZS_CTAS
+#define PCB_XINV_ZS_CTAS 3
+#endif
 template <class P, int LX, int NT, int MODE, int TRN = 0, int DIST = 0, int ZS = 1>
-__global__ void __launch_bounds__(NT, pcb_min_ctas(3 * LX * (P::R1 * P::R2P + TRN) * 16, P::R1, (TRN ? PCB_XINV_CTAS : 4))) k_xinv(PcbOp op, PcbCols cols, const cplx* __restrict__ tw) {
+__global__ void __launch_bounds__(NT, (ZS == 2 ? PCB_XINV_ZS_CTAS : pcb_min_ctas_inv(3 * LX * (P::R1 * P::R2P + TRN) * 16, P::R1, (TRN ? PCB_XINV_CTAS : 4)))) k_xinv(PcbOp op, PcbCols cols, const cplx* __restrict__ tw) {
     constexpr int N = P::N, R1 = P::R1, R2 = P::R2, R2P = P::R2P;
     constexpr int RS = R1 * R2P + TRN;      // row stride in shared memory (see k_xfwd)
     static_assert(ZS == 1 || (TRN == 1 && DIST == 0 && ZS == 2 && LX % 2 == 0 && N % (8 * ZS) == 0), "z-split: plane mode only");
