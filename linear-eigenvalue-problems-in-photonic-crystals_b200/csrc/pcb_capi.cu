@@ -503,7 +503,8 @@ int pcb_diel_create(pcb_ctx* c, int kind, const int64_t* ind_e, long long n_e, c
             if (c->plan->pass(tmp, none, 1, PCB_PASS_MASKBITS2, c->tw, c->stream, c->sms)) { pcb_diel_destroy(d); return -1; }
             c->launches++;
         }
-        if ((whole && c->plan->plane_coupled && kind == PCB_DIEL_TRIVIAL) || kind == PCB_DIEL_CROSSDOF) {
+        const bool coupled_plane = whole ? c->plan->plane_coupled : c->plan->plane_split_coupled;
+        if ((coupled_plane && kind == PCB_DIEL_TRIVIAL) || kind == PCB_DIEL_CROSSDOF) {
             PCB_CUDA_OK_OR(cudaMalloc(&d->maskp, (size_t)c->nn), pcb_diel_destroy(d));
             tmp.maskp = d->maskp;
             if (c->plan->pass(tmp, none, 1, PCB_PASS_MASKPLANE, c->tw, c->stream, c->sms)) { pcb_diel_destroy(d); return -1; }
@@ -632,7 +633,7 @@ static int apply_structure(const pcb_op* o) {
     const int diel = o->d.diel;
     if (c->use_plane && (c->zsplit || c->plan->plane_split != 2)) {
         if (diel == PCB_DIEL_NONE || diel == PCB_DIEL_CHIRAL) return PCB_STRUCT_PLANE;
-        if (diel == PCB_DIEL_TRIVIAL && c->plan->plane_coupled && c->use_plane_coupled && !c->zsplit) return PCB_STRUCT_PLANE;
+        if (diel == PCB_DIEL_TRIVIAL && c->use_plane_coupled && (c->zsplit ? c->plan->plane_split_coupled : c->plan->plane_coupled)) return PCB_STRUCT_PLANE;
         if (diel == PCB_DIEL_CROSSDOF && c->use_plane_cross) return c->use_plane_cross == 2 ? PCB_STRUCT_CROSS5 : PCB_STRUCT_CROSS4;
     }
     return diel == PCB_DIEL_CROSSDOF ? PCB_STRUCT_CROSS7 : PCB_STRUCT_FIVE;

@@ -969,7 +969,6 @@ __global__ void __launch_bounds__(P::N / ZS / 8 * 32, 1) k_mid(PcbOp op, PcbCols
     constexpr bool FWD = HALF != 2, INV = HALF != 1;
     static_assert(N % 8 == 0 && NZ % 8 == 0 && N % NW == 0, "plane mode needs N % 8 == 0 (z-split: N % 16 == 0)");
     static_assert(HALF == 0 || DIEL == 0, "the half passes carry no dielectric");
-    static_assert(ZS == 1 || DIEL != 2, "z-split plane mode: no cluster form of the coupled dielectric");
     const cplx* __restrict__ twz = ZS == 1 ? tw : tw + N;      // twiddles of the z plan
     PCB_DYN_SMEM(cplx, pl);   // [NZ rows][LD] (+ one mbarrier per warp behind it when TMA)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -989,7 +988,7 @@ __global__ void __launch_bounds__(P::N / ZS / 8 * 32, 1) k_mid(PcbOp op, PcbCols
     unsigned pbase[3] = {0u, 0u, 0u};
     double inv_d[3] = {1.0, 1.0, 1.0};
     if (DIEL == 2) {
-        crank = (int)pcb_cluster_ctarank(); first = (int)pcb_cluster_id(); stride = (int)pcb_cluster_count(); total = N * ncols;
+        crank = (int)pcb_cluster_ctarank(); first = (int)pcb_cluster_id(); stride = (int)pcb_cluster_count(); total = N * ZS * ncols;
         PCB_UNROLL
         for (int r = 0; r < 3; ++r) { pbase[r] = pcb_mapa(pcb_smem_u32(pl), (unsigned)r); inv_d[r] = 1.0 / op.ediag[r]; }
     }
@@ -998,8 +997,9 @@ __global__ void __launch_bounds__(P::N / ZS / 8 * 32, 1) k_mid(PcbOp op, PcbCols
     for (int pid = first; pid < total; pid += stride) {
         // z-split: (column, i0, component, half) -- the half planes of all three components of one i0 are in flight together, so the
         // cross-DoF gathers of the fused stencil find the other components' planes in L2 (a column no longer fits L2 for N > 128)
-        const int col = (DIEL == 2) ? pid / N : pid / (3 * N * ZS);
-        const int c = (DIEL == 2) ? crank : (ZS == 1 ? (pid / N) % 3 : (pid / ZS) % 3), i0 = ZS == 1 ? pid % N : (pid / (3 * ZS)) % N;
+        const int col = (DIEL == 2) ? pid / (N * ZS) : pid / (3 * N * ZS);
+        const int c = (DIEL == 2) ? crank : (ZS == 1 ? (pid / N) % 3 : (pid / ZS) % 3);
+        const int i0 = (DIEL == 2) ? (pid / ZS) % N : (ZS == 1 ? pid % N : (pid / (3 * ZS)) % N);
         const int hz = ZS == 1 ? 0 : pid % ZS, prow = hz * NZ + 8 * warp;      // half plane; first plane row of this warp
         const long long poff = c * nn + (long long)i0 * N * N + (long long)prow * N;      // this warp's 8 rows
         cplx* __restrict__ base = ((STEN && HALF == 1) ? cols.out[col] : cols.wrk[col]) + poff;
@@ -1032,13 +1032,13 @@ __global__ void __launch_bounds__(P::N / ZS / 8 * 32, 1) k_mid(PcbOp op, PcbCols
         }
         // coupled dielectric: mask bytes of this thread's points in step (B), point e = threadIdx.x + q * blockDim.x of the CTA's
         // third of the rows -- also fetched here, ten independent loads whose latency the plane's transforms hide
-        constexpr int NTHR = NW * 32, PBQ = (DIEL == 2) ? ((N + 2) / 3 * N + NTHR - 1) / NTHR : 1;
+        constexpr int NTHR = NW * 32, PBQ = (DIEL == 2) ? ((NZ + 2) / 3 * N + NTHR - 1) / NTHR : 1;
         unsigned pmask[(PBQ + 3) / 4];
         int prow0 = 0, pcnt = 0;
         if (DIEL == 2) {
-            prow0 = (crank * N) / 3;
-            pcnt = (((crank + 1) * N) / 3 - prow0) * N;
-            const unsigned char* __restrict__ mp = op.maskp + (long long)i0 * N * N + prow0 * N;
+            prow0 = (crank * NZ) / 3;      // rows of the CTA's (half) plane
+            pcnt = (((crank + 1) * NZ) / 3 - prow0) * N;
+            const unsigned char* __restrict__ mp = op.maskp + (long long)i0 * N * N + (hz * NZ + prow0) * N;
             PCB_UNROLL
             for (int w = 0; w < (PBQ + 3) / 4; ++w) pmask[w] = 0u;
             PCB_UNROLL
@@ -1720,6 +1720,7 @@ struct PcbOpLaunch {
     int lx;            // rows per tile of the x passes (a tile must lie in one i2 plane for the peer-memory passes: N % lx == 0)
     int plane_split;   // z-split plane mode (half planes): 0 not available, 1 selectable, 2 the plane mode of this size
     int zr1, zr2;      // ... radices of its z plan (the plan of N / 2)
+    int plane_split_coupled;   // ... 1: with the cluster form of the coupled 3x3 dielectric (CUDA build only)
     // mode: 0 plain 3-D FFT forward, 1 plain inverse (1/N^3), 2 A = AMA^H, 3 H = AMA^H + gamma B^H B + shift
     int (*apply)(const PcbOp& op, const PcbCols& cols, int ncols, int mode, const cplx* tw, cudaStream_t s, int sms);
     // split passes used by the cross-DoF dielectric and by the tests: pass ids below

@@ -91,6 +91,11 @@ constexpr bool kPlaneCoupled = false;      // thread-block clusters are not emul
 #else
 constexpr bool kPlaneCoupled = kPlane && P::N % 3 == 0 && kSmemMid + 128 <= 232448;
 #endif
+#ifdef PCB_EMU
+constexpr bool kPlaneSplitCoupled = false;
+#else
+constexpr bool kPlaneSplitCoupled = kPlaneSplit;      // coupled 3x3 M on clusters of three CTAs, one half plane per cluster
+#endif
 constexpr int kStageXT = 3 * LX * (P::R1 * P::R2P + 1) * (int)sizeof(cplx);
 
 constexpr int GX = (P::N * P::N + LX - 1) / LX;          // x tiles per column
@@ -190,7 +195,7 @@ struct XFwd2<true, PP> {
 };
 
 // coupled 3x3 M on clusters of three CTAs / peer-memory x passes: full planes only (not in the z-split plane mode)
-template <bool OK, class PP>
+template <bool OK, class PP, int ZS>
 struct Coupled {
     static int go(const PcbOp&, const PcbCols&, int, int, const cplx*, cudaStream_t, int) {
         pcb_set_error("plane mode: no cluster form of the coupled dielectric for N = %d", PP::N);
@@ -198,12 +203,14 @@ struct Coupled {
     }
 };
 #ifndef PCB_EMU
-template <class PP>
-struct Coupled<true, PP> {
+template <class PP, int ZS>
+struct Coupled<true, PP, ZS> {
     static int go(const PcbOp& op, const PcbCols& cols, int ncols, int pass_id, const cplx* tw, cudaStream_t s, int sms) {
-        if (kPlaneFive && op.mid_five && op.mbits2 != nullptr && op.maskp2 != nullptr)
-            return PlaneFive<kPlaneFive, PP>::go(op, cols, ncols, pass_id, tw, s, sms);
-        return launch_cluster3(k_mid<PP, 2, 1, 0, 0, 1>, PP::N / 8 * 32, kSmemMid + 128, PP::N * ncols, op, cols, tw, ncols, s, sms, PP::N);
+        if (ZS == 1 && kPlaneFive && op.mid_five && op.mbits2 != nullptr && op.maskp2 != nullptr)
+            return PlaneFive<(kPlaneFive && ZS == 1), PP>::go(op, cols, ncols, pass_id, tw, s, sms);
+        // (z-split: one cluster per HALF plane -- the three components of the half plane h of (column, i0))
+        return launch_cluster3(k_mid<PP, 2, 1, 0, 0, ZS>, PP::N / ZS / 8 * 32, PP::N / ZS * (PP::N + 1) * (int)sizeof(cplx) + 128, PP::N * ZS * ncols,
+                               op, cols, tw, ncols, s, sms, PP::N);
     }
 };
 #endif
@@ -287,7 +294,7 @@ struct PlanePass<true, PP, ZS> {
         if (pass_id == PCB_PASS_MID && op.diel == PCB_DIEL_TRIVIAL) {
             // coupled 3x3 M: clusters of three CTAs (one component each) exchanging the coupled points through DSMEM
             static_assert(!kPlaneCoupled || kTma, "the cluster form of the plane pass uses the TMA row copies");
-            return Coupled<(kPlaneCoupled && ZS == 1), PP>::go(op, cols, ncols, pass_id, tw, s, sms);
+            return Coupled<(ZS == 1 ? kPlaneCoupled : kPlaneSplitCoupled), PP, ZS>::go(op, cols, ncols, pass_id, tw, s, sms);
         }
 #endif
         if (pass_id == PCB_PASS_XFWD_SYM_TD || pass_id == PCB_PASS_XINV_A_TD || pass_id == PCB_PASS_XINV_H_TD)
@@ -391,4 +398,4 @@ int run_apply(const PcbOp& op, const PcbCols& cols, int ncols, int mode, const c
 #define PCB_CAT(a, b) PCB_CAT2(a, b)
 extern const PcbOpLaunch PCB_CAT(pcb_plan_, PCB_N) = {PCB_N, PCB_R1, PCB_R2, (kPlane || kPlaneSplit) ? 1 : 0, kPlaneCoupled ? 1 : 0, kPlaneFive ? 1 : 0, LX,
                                                       kPlaneSplit ? (kPlane ? 1 : 2) : 0, kPlaneSplit ? PlanOf<(kPlaneSplit ? P::N / 2 : P::N)>::type::R1 : 0,
-                                                      kPlaneSplit ? PlanOf<(kPlaneSplit ? P::N / 2 : P::N)>::type::R2 : 0, run_apply, run_pass};
+                                                      kPlaneSplit ? PlanOf<(kPlaneSplit ? P::N / 2 : P::N)>::type::R2 : 0, kPlaneSplitCoupled ? 1 : 0, run_apply, run_pass};

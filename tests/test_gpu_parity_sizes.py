@@ -72,6 +72,8 @@ def _oracle_ops(pcb, oc, N, d_flag, alpha, typ, eps_opt=0):
     (144, "bcc_sg", "pseudochiral_crossdof", [np.pi, 0.5 * np.pi, 0.0], 1),   # ... and the cross-DoF halves on half planes
     (128, "sc_curv", "chiral", [np.pi, np.pi, np.pi], 2),
     (128, "bcc_dg", "pseudochiral_crossdof", [0.0, 0.0, 2 * np.pi], 1),
+    (144, "bcc_sg", "pseudochiral_trivial", [np.pi / 20, 0.0, 0.0], 1),      # ... and the coupled 3x3 M on clusters of three half-plane CTAs
+    (128, "bcc_dg", "pseudochiral_trivial", [np.pi, np.pi, 0.0], 2),
 ])
 def test_operator_vs_oracle_at_baseline_sizes(gpu, oracle, N, d_flag, typ, alpha, cols):
     alpha = np.array(alpha, dtype=float)
@@ -86,7 +88,8 @@ def test_operator_vs_oracle_at_baseline_sizes(gpu, oracle, N, d_flag, typ, alpha
         assert relerr(P(x), Po(x)) < 1e-12
 
 
-@pytest.mark.parametrize("N,d_flag,typ", [(64, "fcc", "chiral"), (96, "bcc_sg", "pseudochiral_crossdof"), (96, "sc_curv", None)])
+@pytest.mark.parametrize("N,d_flag,typ", [(64, "fcc", "chiral"), (96, "bcc_sg", "pseudochiral_crossdof"), (96, "sc_curv", None),
+                                         (96, "bcc_sg", "pseudochiral_trivial"), (64, "bcc_dg", "pseudochiral_trivial")])
 def test_z_split_plane_mode_at_plane_sizes(gpu, oracle, N, d_flag, typ):
     """The z-split form of the plane mode forced on where the whole-plane form is the default: both match the oracle."""
     alpha = np.array([0.3 * np.pi, 2 * np.pi, 0.0])
