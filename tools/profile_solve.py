@@ -7,6 +7,8 @@ pcb = importlib.import_module("linear-eigenvalue-problems-in-photonic-crystals_b
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 120
 d_flag = sys.argv[2] if len(sys.argv) > 2 else "fcc"
 typ = sys.argv[3] if len(sys.argv) > 3 else "chiral"
+nev = int(sys.argv[4]) if len(sys.argv) > 4 else 10
+m = nev + int(round(0.6 * nev))
 mfd, ne, lob, orth = pcb.discretization, pcb.numerical_experiments, pcb.lobpcg, pcb.orthogonalization
 ctx = pcb.get_context(N)
 T = {}
@@ -19,8 +21,8 @@ relax, pnt = mfd.set_relaxation(alpha)
 a_fft, b_fft = mfd.fft_blocks(N, 1, pcb.dielectric.diel_info(d_flag, option="ct"), alpha=alpha)
 inv_fft = mfd.inverse_3_times_3_B(b_fft, pnt, relax[0])
 A, H, P = ne.pc_mfd_handle(a_fft, (pnt * b_fft[0], pnt * b_fft[1]), getattr(mfd, typ + "_handle")(N, d_flag), inv_fft, relax[0])
-x0 = ctx.random_block(16, 1000)
-lam, x, info = lob.lobpcg_sep_softlock(H, P, x0, 10)     # warm-up (JIT-free, but first-touch allocations)
+x0 = ctx.random_block(m, 1000)
+lam, x, info = lob.lobpcg_sep_softlock(H, P, x0, nev)     # warm-up (JIT-free, but first-touch allocations)
 op = H.op
 op.apply_into = timed("apply_H", op.apply_into)
 op.residual = timed("residual", op.residual)
@@ -39,11 +41,11 @@ class LibProxy:
         f = getattr(lib, n)
         return timed(n, f) if n == "pcb_update" else f
 pcb._lib._lib = LibProxy()
-x0 = ctx.random_block(16, 1000)
+x0 = ctx.random_block(m, 1000)
 t0 = time.perf_counter()
-lam, x, info = lob.lobpcg_sep_softlock(H, P, x0, 10)
+lam, x, info = lob.lobpcg_sep_softlock(H, P, x0, nev)
 wall = time.perf_counter() - t0
 its = int(info[0])
-out = {"N": N, "iterations": its, "solver_s": float(info[1]), "wall_s": wall, "per_phase_ms_per_iteration": {k: 1e3 * v / its for k, v in T.items()},
+out = {"N": N, "nev": nev, "m": m, "iterations": its, "solver_s": float(info[1]), "wall_s": wall, "per_phase_ms_per_iteration": {k: 1e3 * v / its for k, v in T.items()},
        "sum_phases_ms_per_iteration": 1e3 * sum(T.values()) / its}
 print(json.dumps(out))
