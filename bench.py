@@ -229,12 +229,12 @@ def paper2_dielectric_leg(pcb, ctx, n, m, steps, warmup, peak):
 
 
 def larger_grid_leg(pcb, m, steps, warmup, peak, n=160):
-    """Extra key `larger_grids`: the 16-column H block apply at N = 160 (BASELINE configs[3] shape: bcc double gyroid, cross-DoF
-    M; and the isotropic FCC operator) -- the z-split plane mode (half planes, three passes) instead of five passes."""
+    """Extra key `larger_grids`: the 16-column H block apply at N = 160 (BASELINE configs[3] shape: bcc double gyroid, both
+    pseudochiral discretisations; and the isotropic FCC operator) -- the z-split plane mode (half planes) instead of five passes."""
     ctx = pcb.get_context(n)
     try:
         return (dielectric_leg(pcb, ctx, n, m, steps, warmup, peak, "fcc", ("chiral",))
-                + dielectric_leg(pcb, ctx, n, m, steps, warmup, peak, "bcc_dg", ("pseudochiral_crossdof",)))
+                + dielectric_leg(pcb, ctx, n, m, steps, warmup, peak, "bcc_dg", ("pseudochiral_trivial", "pseudochiral_crossdof")))
     finally:
         ctx.trim()
 
