@@ -1,6 +1,6 @@
 """One-off parity sweep on the GPU: H (and A) against the NumPy oracle for every plane-mode size x dielectric type x stencil
 width x eps option (the round-2 pass structures: five-sweep plane pass, coupled M on 3-CTA clusters, cross-DoF plane halves with
-the stencil fused / separate, two-tile forward x pass), plus a few five-pass sizes.  Prints one line per case; exits 1 on a miss.
+the stencil fused / separate, two-tile forward x pass, the z-split plane mode), plus a few five-pass sizes.  Prints one line per case; exits 1 on a miss.
 
     python tools/sweep_parity.py [max_N]
 """
@@ -53,14 +53,15 @@ def case(N, d_flag, typ, k, eps_opt, alpha, options=()):
         eh, ea = relerr(H(x), Ho(x)), relerr(A(x), Ao(x))
     finally:
         for name, val in options:
-            ctx.option(name, {"mid_five": -1, "plane_cross": 1, "plane_coupled": 1, "plane": 1}[name])
+            ctx.option(name, {"mid_five": -1, "plane_cross": 1, "plane_coupled": 1, "plane": 1, "plane_split": 0}[name])
     return eh, ea
 
 
 def main():
     bad = 0
     t0 = time.time()
-    sizes = [n for n in (8, 16, 24, 32, 48, 64, 72, 80, 96, 120, 12, 100) if n <= max_n]
+    sizes = [n for n in (8, 16, 24, 32, 48, 64, 72, 80, 96, 120, 12, 100, 128, 144, 160) if n <= max_n]
+    split_sizes = (16, 32, 48, 64, 96)      # both forms of the plane mode exist: also run the z-split form (the default of 128, 144, 160)
     lattices = {"chiral": "fcc", None: "sc_curv", "pseudochiral_trivial": "bcc_sg", "pseudochiral_crossdof": "bcc_dg"}
     alphas = [np.array([np.pi, 0.3 * np.pi, 0.0]), np.array([0.0, 0.0, 2 * np.pi])]
     n_cases = 0
@@ -75,13 +76,19 @@ def main():
                         variants.append((("plane_cross", 2),))
                     if typ in ("chiral", None, "pseudochiral_trivial") and N in (24, 72):
                         variants.append((("mid_five", 1),))
+                    if N in split_sizes:
+                        variants.append((("plane_split", 1),))
+                        if typ == "pseudochiral_crossdof":
+                            variants.append((("plane_split", 1), ("plane_cross", 2)))
+                    if N > 120 and typ == "pseudochiral_crossdof":
+                        variants = [(("plane_cross", 1),), (("plane_cross", 2),)]
                     for opts in variants:
                         alpha = alphas[n_cases % 2]
                         eh, ea = case(N, lattices[typ], typ, k, eps_opt, alpha, opts)
                         ok = eh < TOL and ea < TOL
                         bad += 0 if ok else 1
                         n_cases += 1
-                        print(f"N={N:3d} {str(typ):22s} eps_opt={eps_opt} k={k} {dict(opts)!s:22s} H {eh:.2e} A {ea:.2e} {'ok' if ok else 'MISS'}", flush=True)
+                        print(f"N={N:3d} {str(typ):22s} eps_opt={eps_opt} k={k} {dict(opts)!s:40s} H {eh:.2e} A {ea:.2e} {'ok' if ok else 'MISS'}", flush=True)
     print(f"{n_cases} cases, {bad} misses, {time.time() - t0:.0f} s")
     sys.exit(1 if bad else 0)
 
