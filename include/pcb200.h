@@ -112,9 +112,11 @@ int pcb_apply_host(pcb_op* op, int mode, int k, const void* x_host, long long ld
 
 /* Same as pcb_apply for PCB_APPLY_A / PCB_APPLY_H, with a CUDA event between the passes: pass_ms[i] = device time of
  * pass i.  Five-pass operator: (x-forward+K_A^H, y-forward, z-forward+M+z-inverse, y-inverse, x-inverse+K_A+gamma K_B+shift),
- * npass <- 5; plane mode (N % 8 == 0, N <= 120; identity / isotropic M, and the coupled 3x3 M when N % 3 == 0 -- clusters of three
- * CTAs): (x-forward, fused y/z/M/z/y plane pass, x-inverse), npass <- 3; cross-DoF M: plane sizes (x-forward, y/z forward on planes,
- * stencil, z/y inverse on planes, x-inverse), npass <- 5, other sizes (x, y, z forward, stencil, z, y, x inverse), npass <- 7.
+ * npass <- 5; plane mode (N % 8 == 0, N <= 120 on whole planes; N = 128, 144, 160 on half planes with the radix-2 step of the z
+ * transform inside the x passes; identity / isotropic M, and the coupled 3x3 M on clusters of three CTAs -- whole planes when
+ * N % 3 == 0): (x-forward, fused y/z/M/z/y plane pass, x-inverse), npass <- 3; cross-DoF M: plane sizes (x-forward, y/z forward on
+ * planes, [stencil kernel, or fused into the next pass: npass <- 4,] z/y inverse on planes, x-inverse), npass <- 5, other sizes
+ * (x, y, z forward, stencil, z, y, x inverse), npass <- 7.
  * pass_ms must hold 8 floats.  Measurement aid for bench.py's per-pass roofline; not used by the solver. */
 int pcb_apply_timed(pcb_op* op, int mode, int ncols, const void* const* in, void* const* out, float* pass_ms, int* npass);
 
