@@ -432,12 +432,14 @@ __global__ void __launch_bounds__(NT, 3) k_xfwd2(PcbOp op, PcbCols cols, const c
 // ZS = 2 (with TRN): z-split plane mode (ZSplit) -- tiles as in k_xfwd<.., ZS = 2>; the epilogue recombines the two half planes,
 // x[i2' + j N/2] = e[i2'] + (-1)^j conj(w_N^i2') o[i2'], while it reads the transformed tile.
 // (z-split sizes: the uncapped kernel takes 170-172 registers, which the allocation granularity turns into TWO resident CTAs of four
-// warps -- ncu: warps active 12 %, DRAM 58 % at N = 160; asking for three caps it at 168.)
+// warps; asking for three caps it at 168.  Measured on one box: N = 128 (R1 = 8) 1.02 -> 0.91 ms per 16 columns, but N = 160 (R1 = 10)
+// 1.97 -> 2.01 ms -- that pass is insensitive to occupancy, to the L2 prefetch of X and to the epilogue batch (PB = 2 / 4 / 8:
+// 2.03 / 2.01 / 2.02 ms) -- so the cap applies where the first radix is 8.)
 #ifndef PCB_XINV_ZS_CTAS
 #define PCB_XINV_ZS_CTAS 3
 #endif
 template <class P, int LX, int NT, int MODE, int TRN = 0, int DIST = 0, int ZS = 1>
-__global__ void __launch_bounds__(NT, (ZS == 2 ? PCB_XINV_ZS_CTAS : pcb_min_ctas_inv(3 * LX * (P::R1 * P::R2P + TRN) * 16, P::R1, (TRN ? PCB_XINV_CTAS : 4)))) k_xinv(PcbOp op, PcbCols cols, const cplx* __restrict__ tw) {
+__global__ void __launch_bounds__(NT, (ZS == 2 ? (P::R1 <= 8 ? PCB_XINV_ZS_CTAS : 1) : pcb_min_ctas_inv(3 * LX * (P::R1 * P::R2P + TRN) * 16, P::R1, (TRN ? PCB_XINV_CTAS : 4)))) k_xinv(PcbOp op, PcbCols cols, const cplx* __restrict__ tw) {
     constexpr int N = P::N, R1 = P::R1, R2 = P::R2, R2P = P::R2P;
     constexpr int RS = R1 * R2P + TRN;      // row stride in shared memory (see k_xfwd)
     static_assert(ZS == 1 || (TRN == 1 && DIST == 0 && ZS == 2 && LX % 2 == 0 && N % (8 * ZS) == 0), "z-split: plane mode only");
@@ -469,7 +471,10 @@ __global__ void __launch_bounds__(NT, (ZS == 2 ? PCB_XINV_ZS_CTAS : pcb_min_ctas
         for (int l = tid; l < 3 * lines; l += NT)
             pcb_prefetch_l2(reinterpret_cast<const char*>(X + (l / lines) * nn + (long long)row0 * N) + (l % lines) * 128);
     }
-    if (MODE == 2 && ZS == 2) {   // ... 3 x ZS chunks of LH rows
+#ifndef PCB_XINV_ZS_PF
+#define PCB_XINV_ZS_PF 1
+#endif
+    if (MODE == 2 && ZS == 2 && PCB_XINV_ZS_PF) {   // ... 3 x ZS chunks of LH rows
         constexpr int lines = (LH * N * (int)sizeof(cplx) + 127) / 128;
         for (int l = tid; l < 3 * ZS * lines; l += NT) {
             const int ch = l / lines;
@@ -515,7 +520,10 @@ __global__ void __launch_bounds__(NT, (ZS == 2 ? PCB_XINV_ZS_CTAS : pcb_min_ctas
     }
     __syncthreads();
     // point-wise epilogue, fully coalesced: 1/N^3, k x v, (+ gamma conj(k)(k.x) + shift x), store
-    constexpr int PB = 4;     // points per thread and batch: all X loads of a batch are issued before they are used
+#ifndef PCB_XINV_PB
+#define PCB_XINV_PB 4
+#endif
+    constexpr int PB = PCB_XINV_PB;     // points per thread and batch: all X loads of a batch are issued before they are used
     // global position of tile element e (row-major over the tile's rows): contiguous from row0 N, or ZS chunks of LH rows
     auto gpos = [&](int e) -> long long {
         return ZS == 1 ? (long long)row0 * N + e : (long long)ZSP::template row<LX>(blockIdx.x, (e / (LH * N)) * LH) * N + e % (LH * N);
